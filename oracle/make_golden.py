@@ -1,0 +1,192 @@
+"""Generate tests/golden/*.pt from the reference itself -- run in the build container:
+
+    python -m oracle.make_golden
+
+Weights are produced by munit_oracle.init_state_dict(seed) (so they can be rebuilt on the
+GPU box without shipping 100+ MB) and loaded into the reference modules; inputs are seeded;
+the fixtures hold the reference's outputs / gradients / losses / post-step weights
+(small tensors whole, big ones as strided samples + sums).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import munit_oracle as O  # noqa: E402
+from oracle import ref_loader  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def summarize(t: torch.Tensor, n=64):
+    """Compact fingerprint of a big tensor: sum, abs-sum, and a strided sample."""
+    f = t.detach().reshape(-1).double()
+    step = max(1, f.numel() // n)
+    return dict(shape=tuple(t.shape), sum=float(f.sum()), asum=float(f.abs().sum()),
+                sample=f[::step][:n].float().clone(), step=step)
+
+
+def seeded_images(seed, b, h, w):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(b, 3, h, w, generator=g) * 2 - 1, torch.rand(b, 3, h, w, generator=g) * 2 - 1
+
+
+def layers_fixture():
+    """Per-layer forward/backward of the reference modules (networks.py) on tiny inputs."""
+    networks, _ = ref_loader.load()
+    torch.manual_seed(7)
+    fx = {}
+    # Conv2dBlock variants: (cin,cout,k,s,p,norm,act)
+    for name, (cin, cout, k, s, p, norm, act, hw) in {
+        "c7_in_relu": (3, 16, 7, 1, 3, "in", "relu", 16),
+        "c4s2_none_lrelu": (16, 24, 4, 2, 1, "none", "lrelu", 16),
+        "c3_in_none": (16, 16, 3, 1, 1, "in", "none", 12),
+        "c5_ln_relu": (24, 16, 5, 1, 2, "ln", "relu", 12),
+        "c7_none_tanh": (16, 3, 7, 1, 3, "none", "tanh", 16),
+    }.items():
+        m = networks.Conv2dBlock(cin, cout, k, s, p, norm=norm, activation=act, pad_type="reflect")
+        x = torch.randn(2, cin, hw, hw, requires_grad=True)
+        y = m(x)
+        gy = torch.randn_like(y)
+        y.backward(gy)
+        fx[name] = dict(args=(cin, cout, k, s, p, norm, act), sd={k_: v.detach().clone() for k_, v in m.state_dict().items()},
+                        x=x.detach().clone(), y=y.detach().clone(), gy=gy, gx=x.grad.clone(),
+                        gw=m.conv.weight.grad.clone(), gb=m.conv.bias.grad.clone(),
+                        gnorm={n: p_.grad.clone() for n, p_ in m.named_parameters() if n.startswith("norm")})
+    # AdaIN
+    m = networks.AdaptiveInstanceNorm2d(64)
+    x = torch.randn(3, 64, 8, 8, requires_grad=True)
+    w = torch.randn(3 * 64, requires_grad=True)
+    b = torch.randn(3 * 64, requires_grad=True)
+    m.weight, m.bias = w, b
+    y = m(x)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    fx["adain"] = dict(x=x.detach().clone(), w=w.detach().clone(), b=b.detach().clone(), y=y.detach().clone(),
+                       gy=gy, gx=x.grad.clone(), gw=w.grad.clone(), gb=b.grad.clone())
+    # LayerNorm
+    m = networks.LayerNorm(32)
+    x = torch.randn(2, 32, 8, 8, requires_grad=True)
+    y = m(x)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    fx["ln"] = dict(x=x.detach().clone(), gamma=m.gamma.detach().clone(), beta=m.beta.detach().clone(),
+                    y=y.detach().clone(), gy=gy, gx=x.grad.clone(), ggamma=m.gamma.grad.clone(), gbeta=m.beta.grad.clone())
+    # avg-pool pyramid divisor
+    d = networks.MsImageDis(3, O.config_256_core()["dis"])
+    x = torch.randn(1, 3, 16, 16)
+    fx["avgpool"] = dict(x=x, y=d.downsample(x))
+    torch.save(fx, os.path.join(OUT, "layers.pt"))
+    print("layers.pt", {k: None for k in fx})
+
+
+def nets_fixture():
+    """Whole-network forwards on seeded weights: AdaINGen_double encode/decode, MsImageDis."""
+    networks, _ = ref_loader.load()
+    cfg = O.config_256_core()
+    gsd = O.init_state_dict(O.gen_spec(cfg["gen"], 3, True), 11, "kaiming")
+    dsd = O.init_state_dict(O.dis_spec(cfg["dis"], 3), 12, "gaussian")
+    gen = networks.AdaINGen_double(3, cfg["gen"])
+    gen.load_state_dict(gsd)
+    dis = networks.MsImageDis(3, cfg["dis"])
+    dis.load_state_dict(dsd)
+    x_a, x_b = seeded_images(1234, 2, 64, 64)
+    with torch.no_grad():
+        c_a, s_a = gen.encode(x_a, 1)
+        c_b, s_b = gen.encode(x_b, 2)
+        x_ab = gen.decode(c_a, s_b, 2)
+        x_ba = gen.decode(c_b, s_a, 1)
+        ap = gen.get_adain_param(s_b, 2)
+        d_out = dis(x_ab)
+        dl = dis.calc_dis_loss(x_ab, x_b)
+        gl = dis.calc_gen_loss(x_ab)
+    # single-generator AdaINGen (gen_state 0) too
+    gsd0 = O.init_state_dict(O.gen_spec(cfg["gen"], 3, False), 13, "kaiming")
+    g0 = networks.AdaINGen(3, cfg["gen"])
+    g0.load_state_dict(gsd0)
+    with torch.no_grad():
+        c0, s0 = g0.encode(x_a)
+        torch.manual_seed(5)
+        s_rand = torch.randn(2, cfg["gen"]["style_dim"], 1, 1)
+        y0 = g0.decode(c0, s_rand)
+    fx = dict(seeds=dict(gen=11, dis=12, gen0=13, img=1234), hw=64, b=2,
+              c_a=summarize(c_a, 256), s_a=s_a.clone(), s_b=s_b.clone(), x_ab=x_ab.clone(), x_ba=x_ba.clone(),
+              adain_params=summarize(ap, 256), d_out=[o.clone() for o in d_out], dis_loss=float(dl), gen_loss=float(gl),
+              s_rand=s_rand, y0=y0.clone(), c0=summarize(c0, 256), s0=s0.clone())
+    torch.save(fx, os.path.join(OUT, "nets.pt"))
+    print("nets.pt ok")
+
+
+def step_fixture(tag, optimizer, gen_state, guided, hw, b, n_steps):
+    """dis_update + gen_update on the shimmed reference trainer (trainer.py:336-561,1133-1186)."""
+    cfg = O.config_256_core(optimizer=optimizer, gen_state=gen_state, guided=guided,
+                            crop_image_height=hw, crop_image_width=hw)
+    torch.manual_seed(0)
+    t = ref_loader.make_trainer(cfg)
+    if gen_state == 1:
+        gsd = O.init_state_dict(O.gen_spec(cfg["gen"], 3, True), 21, "kaiming")
+        t.gen.load_state_dict(gsd)
+    else:
+        ga = O.init_state_dict(O.gen_spec(cfg["gen"], 3, False), 21, "kaiming")
+        gb = O.init_state_dict(O.gen_spec(cfg["gen"], 3, False), 22, "kaiming")
+        t.gen_a.load_state_dict(ga)
+        t.gen_b.load_state_dict(gb)
+    t.dis_a.load_state_dict(O.init_state_dict(O.dis_spec(cfg["dis"], 3), 23, "gaussian"))
+    t.dis_b.load_state_dict(O.init_state_dict(O.dis_spec(cfg["dis"], 3), 24, "gaussian"))
+    x_a, x_b = seeded_images(1234, b, hw, hw)
+    torch.manual_seed(99)  # style-code stream for the updates (trainer.py:366-367,1146-1147)
+    steps = []
+    for it in range(n_steps):
+        t.iterations = it
+        t.update_learning_rate()
+        t.dis_update(x_a, x_b, cfg)
+        dis_g = {f"a/{n}": summarize(p.grad, 16) for n, p in t.dis_a.named_parameters()}
+        t.gen_update(x_a, x_b, cfg)
+        rec = {k: float(getattr(t, k)) for k in dir(t) if k.startswith("loss_") and torch.is_tensor(getattr(t, k))}
+        gens = {"": t.gen} if gen_state == 1 else {"a": t.gen_a, "b": t.gen_b}
+        gen_g = {f"{gn}/{n}": summarize(p.grad, 16) for gn, g in gens.items() for n, p in g.named_parameters()}
+        gen_w = {f"{gn}/{n}": summarize(p.data, 16) for gn, g in gens.items() for n, p in g.named_parameters()}
+        dis_w = {f"a/{n}": summarize(p.data, 16) for n, p in t.dis_a.named_parameters()}
+        dis_w.update({f"b/{n}": summarize(p.data, 16) for n, p in t.dis_b.named_parameters()})
+        steps.append(dict(losses=rec, dis_grads=dis_g, gen_grads=gen_g, gen_w=gen_w, dis_w=dis_w))
+        print(tag, it, {k: round(v, 5) for k, v in rec.items()})
+    fx = dict(cfg=cfg, seeds=dict(gen=21, gen_b=22, dis_a=23, dis_b=24, img=1234, style=99), hw=hw, b=b, steps=steps)
+    torch.save(fx, os.path.join(OUT, f"step_{tag}.pt"))
+
+
+def adam_fixture():
+    """torch.optim.Adam (what trainer.py:41-45 instantiates) and the reference ExtraAdam on a toy problem."""
+    ref_loader.load()
+    ExtraAdam = sys.modules["extraadam"].ExtraAdam
+    g = torch.Generator().manual_seed(3)
+    p0 = torch.randn(257, generator=g)
+    grads = [torch.randn(257, generator=g) for _ in range(4)]
+    out = {}
+    for name, mk in (("adam", lambda p: torch.optim.Adam([p], lr=1e-3, betas=(0.5, 0.999), weight_decay=1e-4)),
+                     ("extraadam", lambda p: ExtraAdam([p], lr=1e-3, betas=(0.5, 0.999), weight_decay=1e-4))):
+        p = torch.nn.Parameter(p0.clone())
+        opt = mk(p)
+        hist = []
+        for it, gr in enumerate(grads):
+            p.grad = gr.clone()
+            if name == "extraadam" and it % 2 == 0:
+                opt.extrapolation()
+            else:
+                opt.step()
+            hist.append(p.data.clone())
+        out[name] = hist
+    torch.save(dict(p0=p0, grads=grads, **out), os.path.join(OUT, "adam.pt"))
+    print("adam.pt ok")
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    layers_fixture()
+    adam_fixture()
+    nets_fixture()
+    step_fixture("g1_guided_adam", "adam", 1, 1, 64, 2, 2)
+    step_fixture("g0_sampled_extraadam", "extraadam", 0, 0, 64, 1, 2)
