@@ -1,0 +1,233 @@
+/* munit_b200 -- C-ABI of the B200-native MUNIT hot path (libmunit_b200.so).
+ *
+ * The reference (cc-ai/MUNIT) has no FFI of its own: its hot path bottoms out in PyTorch ATen calls
+ * (SURVEY.md s2.1).  Each entry point below replaces the ATen call sites cited next to it; the host
+ * side (munit_b200/networks.py, trainer.py) binds them with ctypes -- see INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only; every pointer is a DEVICE pointer unless stated; every
+ * call is asynchronous on the cudaStream_t passed as `void* stream`; the library never allocates
+ * device memory and never synchronises; returns 0 on success, a munit_status otherwise, with a
+ * message available from munit_last_error() (thread-local).  Activations are NHWC bf16
+ * ("act" buffers [N][H+2P][W+2P][C], P = materialised reflect halo), statistics/parameters fp32.
+ */
+#ifndef MUNIT_B200_H
+#define MUNIT_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  MUNIT_OK = 0,
+  MUNIT_ERR_ARG = 1,      /* bad descriptor / alignment */
+  MUNIT_ERR_CUDA = 2,     /* CUDA runtime/driver error  */
+  MUNIT_ERR_NO_DEVICE = 3 /* no sm_100 device           */
+} munit_status;
+
+enum { MUNIT_ACT_NONE = 0, MUNIT_ACT_RELU = 1, MUNIT_ACT_LRELU = 2, MUNIT_ACT_TANH = 3 };
+enum { MUNIT_MAX_TAPS = 49, MUNIT_MAX_PHASES = 4 };
+
+int munit_version(void);
+const char* munit_last_error(void);
+/* Checks for an sm_100 device, resolves cuTensorMapEncodeTiled, sets kernel attributes. */
+int munit_init(void);
+/* Device-side int flag raised by any kernel whose bounded mbarrier wait timed out (debug aid). */
+int munit_error_flag_ptr(void** dev_ptr);
+
+/* ------------------------------------------------------------------------------------------
+ * Tap-GEMM: the implicit-GEMM core behind every convolution (replaces nn.ReflectionPad2d +
+ * nn.Conv2d forward, networks.py:696, and cudnn_convolution_backward_input).
+ *
+ *   out[pix, n] = act( bias[n] + sum_{tap, c} A[coord(pix) + tap_off[tap], c] * B[n, (k0 + tap*chunks*64) + c] )
+ *
+ * A is a bf16 activation tensor described as a rank 3..5 TMA view (innermost dim = channels);
+ * out-of-bounds coordinates read as zero.  A 128-pixel M tile covers (tn x th x tw) output
+ * positions starting at (n0, y0, x0); its TMA coordinate on dim d is
+ *   x0*mx[d] + y0*my[d] + n0*mn[d] + tap_off[tap][d]   (+ 64*chunk on dim 0).
+ * B is the bf16 weight matrix [b_rows][b_k] (K contiguous).  tcgen05.mma, fp32 accumulate in TMEM.
+ * Output pixel (n, y, x), column c is stored (bf16) at
+ *   out + n*o_sn + (y*o_ymul + o_yoff[phase])*o_sy + (x*o_xmul + o_xoff[phase])*o_sx + c.
+ * `phases` > 1 runs several independent weight slices / output offsets in one launch (stride-2
+ * dgrad): phase p uses B columns starting at b_k0[p].
+ */
+typedef struct {
+  const void* a;
+  int32_t a_rank;
+  uint64_t a_dim[5];
+  uint64_t a_stride[5]; /* bytes; a_stride[0] unused */
+  uint32_t a_box[5];    /* a_box[0] == 64; product of the rest == 128 */
+  const void* b;
+  uint64_t b_rows, b_k;
+  int32_t bn; /* N tile: 16, 32, 64, 128 or 256; b_rows % bn == 0 */
+  int32_t tw, th, tn;
+  int32_t out_w, out_h, n_img;
+  int32_t mx[5], my[5], mn[5];
+  int32_t num_taps, chunks;
+  int32_t tap_off[MUNIT_MAX_TAPS][5];
+  int32_t phases;
+  int32_t b_k0[MUNIT_MAX_PHASES];
+  int32_t o_yoff[MUNIT_MAX_PHASES], o_xoff[MUNIT_MAX_PHASES];
+  void* out;
+  int64_t o_sn, o_sy, o_sx;
+  int32_t o_ymul, o_xmul;
+  int32_t n_store; /* columns actually stored per pixel (<= b_rows) */
+  const float* bias; /* [b_rows] or NULL */
+  int32_t act;
+  int32_t stages; /* 0 = auto */
+} munit_tapgemm_desc;
+
+int munit_tapgemm(const munit_tapgemm_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Weight-gradient GEMM (replaces cudnn_convolution_backward_weight):
+ *
+ *   dw[m*s_m + tap*s_t + n*s_n] += sum_{pix} A[pix, m] * B[coordB(pix) + tap_off[tap], n]
+ *
+ * A (dY) and B (X) are bf16 activation tensors as TMA views; the reduction runs over pixel blocks of
+ * 64 positions (pw x ph x pn), split over `ksplit` CTAs that accumulate into fp32 `dw` with
+ * red.global.add (dw must be zero-initialised by the caller).  MN-major UMMA operands.
+ */
+typedef struct {
+  const void* a;
+  int32_t a_rank;
+  uint64_t a_dim[5];
+  uint64_t a_stride[5];
+  uint32_t a_box[5]; /* a_box[0] == 64, product of the rest == 64 */
+  int32_t a_mx[5], a_my[5], a_mn[5];
+  const void* b;
+  int32_t b_rank;
+  uint64_t b_dim[5];
+  uint64_t b_stride[5];
+  uint32_t b_box[5];
+  int32_t b_mx[5], b_my[5], b_mn[5];
+  int32_t pw, ph, pn;           /* pixel block extents, pw*ph*pn == 64 */
+  int32_t out_w, out_h, n_img;  /* pixel space (dY extents) */
+  int32_t m_total, n_total;     /* valid channels of A / of B (per tap) */
+  int32_t bn;                   /* 64, 128 or 256 */
+  int32_t num_taps;
+  int32_t tap_off[MUNIT_MAX_TAPS][5]; /* added to B coordinates */
+  float* dw;
+  int64_t s_m, s_t, s_n;
+  int32_t ksplit; /* 0 = auto */
+  int32_t stages; /* 0 = auto */
+} munit_wgrad_desc;
+
+int munit_wgrad(const munit_wgrad_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Bandwidth kernels (SIMT, 128-bit access).  See DESIGN.md s4 for bytes/element of each.
+ */
+
+/* NCHW fp32 image -> act buffer [N][H+2P][W+2P][CP] bf16 with reflect halo, channels >= C zeroed.
+ * (replaces the NCHW->kernel layout step + nn.ReflectionPad2d of the first conv, networks.py:643) */
+int munit_image_to_act(const float* x, void* act, int n, int c, int h, int w, int pad, int cp, void* stream);
+/* NCHW fp32 image -> kw-expanded buffer E[N][H+2P][WO][KWP*CP] bf16,
+ * E[n,yp,xo,kw,c] = xpad[n,c,yp,xo*sx+kw]; lets a Cin=3 conv run as a kh-tap GEMM with K=64. */
+int munit_image_to_kwexp(const float* x, void* e, int n, int c, int h, int w, int pad, int kw, int sx, int wo, int kwp,
+                         int cp, void* stream);
+/* Adjoint of munit_image_to_kwexp: dx[n,c,y,x] (NCHW fp32) = sum of dE over every (yp,xo,kw) that read it. */
+int munit_kwexp_to_image_grad(const void* de, float* dx, int n, int c, int h, int w, int pad, int kw, int sx, int wo,
+                              int kwp, int cp, void* stream);
+/* act buffer interior (first C channels) -> NCHW fp32. */
+int munit_act_to_nchw(const void* act, float* y, int n, int c, int h, int w, int pad, int cp, void* stream);
+/* NCHW fp32 -> act interior (channels >= C up to CP zeroed); follow with munit_halo_fill. */
+int munit_nchw_to_act(const float* x, void* act, int n, int c, int h, int w, int pad, int cp, void* stream);
+
+/* In-place reflect halo fill of an act buffer from its interior. */
+int munit_halo_fill(void* act, int n, int h, int w, int c, int pad, void* stream);
+
+/* Per-(n,c) shifted sums over H*W of y [N][H][W][C] bf16 (row stride in elements ldp = C):
+ * stats[(n*C+c)*2 + {0,1}] = {sum(x - s), sum((x - s)^2)}, shift[n*C+c] = s = y[n,0,0,c].
+ * (first half of nn.InstanceNorm2d networks.py:657 / F.batch_norm networks.py:834 / LayerNorm :865-871) */
+int munit_norm_stats(const void* y, float* stats, float* shift, int n, int hw, int c, void* stream);
+
+enum { MUNIT_NORM_IN = 0, MUNIT_NORM_ADAIN = 1, MUNIT_NORM_LN = 2 };
+/* stats -> per-(n,c) mean, rinv, and the affine (a, b) with out = a*x + b.
+ * IN: biased var, rsqrt(var+eps).  ADAIN: same, times w[n*ldw + c], plus bias[n*ldw + c].
+ * LN: per-sample mean / unbiased std over C*H*W, 1/(std+eps), per-channel gamma (p_w) / beta (p_b). */
+int munit_norm_finalize(const float* stats, const float* shift, int mode, const float* p_w, const float* p_b,
+                        int64_t ldw, float eps, float* mean, float* rinv, float* a, float* b, int n, int hw, int c,
+                        void* stream);
+/* out_act[interior (+halo) (+2x nearest upsample)] = relu?(a*y + b) (+ residual interior).
+ * residual (may be NULL) is an act buffer with halo res_pad and the same H, W, C. */
+int munit_norm_apply(const void* y, const float* a, const float* b, int relu, const void* residual, int res_pad,
+                     void* out_act, int out_pad, int upsample, int n, int h, int w, int c, void* stream);
+
+/* Backward of norm_apply + norm: g_out is the gradient w.r.t. out_act (full padded / upsampled extent).
+ * pass 1: sums[(n*C+c)*2+{0,1}] = {sum dz, sum dz*xhat}, dz = fold(g_out) * relu'(a*y+b). */
+int munit_norm_bwd_reduce(const void* g_out, int out_pad, int upsample, const void* y, const float* a, const float* b,
+                          int relu, const float* mean, const float* rinv, float* sums, int n, int h, int w, int c,
+                          void* stream);
+/* sums -> dx coefficients (ca, cb, cc): dx = ca*dz + cb*xhat + cc; parameter grads:
+ * ADAIN: g_w[n*ldg + c] = sum dz*xhat, g_b[n*ldg + c] = sum dz; LN: g_w[c], g_b[c] summed over n (+=). */
+int munit_norm_bwd_finalize(const float* sums, int mode, const float* p_w, int64_t ldw, const float* rinv, float eps,
+                            float* ca, float* cb, float* cc, float* g_w, float* g_b, int64_t ldg, int n, int hw, int c,
+                            void* stream);
+/* pass 2: dy [N][H][W][C] bf16 = ca*dz + cb*xhat + cc; optional g_res (act buffer, halo res_pad, halo zeroed) = fold(g_out). */
+int munit_norm_bwd_apply(const void* g_out, int out_pad, int upsample, const void* y, const float* a, const float* b,
+                         int relu, const float* mean, const float* rinv, const float* ca, const float* cb,
+                         const float* cc, void* dy, void* g_res, int res_pad, int n, int h, int w, int c, void* stream);
+
+/* No-norm conv blocks: dy [N][H][W][C] = fold(g_out_act) * act'(out) where out is the forward output
+ * (interior of out_act, halo `pad`; g_out has the same padded extent). */
+int munit_act_bwd(const void* g_out, const void* out_act, int pad, int act, void* dy, int n, int h, int w, int c,
+                  void* stream);
+/* dbias[c] += sum over pixels of dy [npix][C] bf16. */
+int munit_colsum(const void* dy, float* dbias, int64_t npix, int c, void* stream);
+
+/* Weights: fp32 master (OIHW shape stored channels_last = [Cout][KH][KW][Cin]) -> bf16 GEMM shadows.
+ * dst[i] = idx[i] >= 0 ? bf16(src[idx[i]]) : 0 -- the index map (built once per layer on the host) encodes
+ * tap order, channel padding, the dgrad transpose and the stride-2 phase split. */
+int munit_gather_cast(const float* src, const int32_t* idx, void* dst, int64_t n, void* stream);
+/* dst[i] += src[idx[i]] for idx[i] >= 0: moves wgrad results from a padded GEMM layout into .grad. */
+int munit_gather_add(const float* src, const int32_t* idx, float* dst, int64_t n, void* stream);
+int munit_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
+
+/* y[b][o] = act(sum_i x[b][i]*w[o][i] + bias[o])  (nn.Linear networks.py:712,744-748; fp32) */
+int munit_linear_fwd(const float* x, const float* w, const float* bias, float* y, int b, int in, int out, int relu,
+                     void* stream);
+/* dx[b][i] = sum_o dy'[b][o] w[o][i]; dw[o][i] += sum_b dy'[b][o] x[b][i]; db[o] += sum_b dy'; dy' = dy*relu'(y). */
+int munit_linear_bwd(const float* x, const float* w, const float* y, const float* dy, int relu, float* dx, float* dw,
+                     float* db, int b, int in, int out, void* stream);
+
+/* Global average pool over H*W of y [N][HW][C] bf16 -> fp32 [N][C] (AdaptiveAvgPool2d(1), networks.py:471)
+ * and its backward (dy[n,p,c] = g[n,c]/HW * act'(..) is handled by act_bwd; this writes the broadcast). */
+int munit_gap_fwd(const void* y, float* out, int n, int hw, int c, void* stream);
+int munit_gap_bwd(const float* g, void* dy, int n, int hw, int c, void* stream);
+
+/* 1x1 conv C->1 on y [NPIX][C] bf16 (MsImageDis head, networks.py:68) fused with the LSGAN term
+ * mean((o - target)^2) (networks.py:91,109): out[pix] fp32, loss += sum((o-t)^2)/npix * scale. */
+int munit_dis_head_fwd(const void* y, const float* w, const float* bias, float target, float* out, float* loss,
+                       float scale, int64_t npix, int c, void* stream);
+/* do[pix] = gscale*gscale_dev[0]*2*(o - t)/npix (gscale_dev may be NULL); dy[pix][c] = do*w[c]; dw[c] += sum do*y; db += sum do (dw/db may be NULL). */
+int munit_dis_head_bwd(const void* y, const float* w, const float* out, float target, const float* gscale_dev,
+                       float gscale, void* dy, float* dw, float* db, int64_t npix, int c, void* stream);
+
+/* AvgPool2d(3, stride 2, pad 1, count_include_pad=False) on NCHW fp32 (networks.py:32-34) + adjoint (+=). */
+int munit_avgpool3s2_fwd(const float* x, float* y, int nc, int h, int w, void* stream);
+int munit_avgpool3s2_bwd(const float* gy, float* gx, int nc, int h, int w, void* stream);
+
+/* loss += scale * sum|a-b| (trainer.py:290); g = gscale*sign(a-b) written to ga (and -g added to gb if non-NULL). */
+int munit_l1_fwd(const float* a, const float* b, float* loss, float scale, int64_t n, void* stream);
+int munit_l1_bwd(const float* a, const float* b, const float* gscale_dev, float scale, float* ga, float* gb, int64_t n,
+                 void* stream);
+int munit_l1_bf16_fwd(const void* a, const void* b, float* loss, float scale, int64_t n, void* stream);
+int munit_l1_bf16_bwd(const void* a, const void* b, const float* gscale_dev, float scale, void* ga, void* gb,
+                      int64_t n, void* stream);
+
+/* Flat multi-tensor Adam over one contiguous fp32 arena (torch.optim.Adam as resolved by trainer.py:41-45,
+ * and ExtraAdam.update extraadam.py:119-168).  mode 0: torch Adam; 1: legacy formula, extrapolate
+ * (p_saved = p if save; p += u); 2: legacy formula, step (p = p_saved + u).  gscale multiplies the
+ * gradient first (1/world for data parallel).  Optionally refreshes a bf16 copy of p. */
+int munit_adam(float* p, const float* g, float* m, float* v, float* p_saved, void* p_bf16, int64_t n, int mode,
+               int save, float lr, float beta1, float beta2, float eps, float wd, int step, float gscale,
+               void* stream);
+
+int munit_fill_f32(float* p, float v, int64_t n, void* stream);
+int munit_add_bf16(void* dst, const void* src, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUNIT_B200_H */

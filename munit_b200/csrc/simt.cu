@@ -1,0 +1,1166 @@
+// Bandwidth-bound SIMT kernels of the MUNIT hot path (sm_100a): layout conversion, reflect halo,
+// InstanceNorm / AdaIN / LayerNorm forward+backward, activations, pooling, losses, MLP, Adam.
+// All activations are NHWC bf16 accessed as 128-bit (8-channel) vectors; statistics are fp32.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/munit_b200.h"
+#include "common.h"
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+struct F8 {
+  float v[8];
+};
+
+__device__ __forceinline__ F8 load8(const bf16* p) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  F8 r;
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    r.v[2 * i] = f.x;
+    r.v[2 * i + 1] = f.y;
+  }
+  return r;
+}
+__device__ __forceinline__ void store8(bf16* p, const F8& r) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(r.v[2 * i], r.v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ F8 loadf8(const float* p) {
+  F8 r;
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float4 b = *reinterpret_cast<const float4*>(p + 4);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ int reflect(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+// Padded rows/cols that mirror unpadded index r of an axis of length n with reflect halo p
+// (the adjoint of nn.ReflectionPad2d, networks.py:643).  Returns the count (1..3).
+__device__ __forceinline__ int pad_positions(int r, int n, int p, int* pos) {
+  int cnt = 0;
+  pos[cnt++] = r + p;
+  if (r >= 1 && r <= p) pos[cnt++] = p - r;
+  const int rb = n - 1 - r;
+  if (rb >= 1 && rb <= p) pos[cnt++] = p + n - 1 + rb;
+  return cnt;
+}
+
+inline int nblocks(long long n, int threads) { return (int)((n + threads - 1) / threads); }
+
+// ------------------------------------------------------------------ layout
+__global__ void image_to_act_kernel(const float* __restrict__ x, bf16* __restrict__ act, int n, int c, int h, int w,
+                                    int pad, int cp) {
+  const int hp = h + 2 * pad, wp = w + 2 * pad;
+  const long long total = (long long)n * hp * wp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int xp = (int)(i % wp);
+    const int yp = (int)((i / wp) % hp);
+    const int b = (int)(i / ((long long)wp * hp));
+    const int sy = reflect(yp - pad, h), sx = reflect(xp - pad, w);
+    bf16* dst = act + i * cp;
+    for (int c0 = 0; c0 < cp; c0 += 8) {
+      F8 v;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int ch = c0 + e;
+        v.v[e] = ch < c ? x[(((long long)b * c + ch) * h + sy) * w + sx] : 0.f;
+      }
+      store8(dst + c0, v);
+    }
+  }
+}
+
+__global__ void image_to_kwexp_kernel(const float* __restrict__ x, bf16* __restrict__ e, int n, int c, int h, int w,
+                                      int pad, int kw, int sx, int wo, int kwp, int cp) {
+  const int hp = h + 2 * pad;
+  const int vec_per_tap = cp / 8;
+  const long long total = (long long)n * hp * wo * kwp * vec_per_tap;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int cv = (int)(t % vec_per_tap); t /= vec_per_tap;
+    const int k = (int)(t % kwp); t /= kwp;
+    const int xo = (int)(t % wo); t /= wo;
+    const int yp = (int)(t % hp);
+    const int b = (int)(t / hp);
+    F8 v;
+    const int sy = reflect(yp - pad, h);
+    const int sxx = reflect(xo * sx + k - pad, w);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int ch = cv * 8 + q;
+      v.v[q] = (k < kw && ch < c) ? x[(((long long)b * c + ch) * h + sy) * w + sxx] : 0.f;
+    }
+    store8(e + i * 8, v);
+  }
+}
+
+__global__ void kwexp_to_image_grad_kernel(const bf16* __restrict__ de, float* __restrict__ dx, int n, int c, int h,
+                                           int w, int pad, int kw, int sx, int wo, int kwp, int cp) {
+  const int hp = h + 2 * pad;
+  const long long total = (long long)n * h * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w);
+    const int y = (int)((i / w) % h);
+    const int b = (int)(i / ((long long)w * h));
+    int rows[3], cols[3];
+    const int nr = pad_positions(y, h, pad, rows);
+    const int nc = pad_positions(x, w, pad, cols);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < nr; ++r)
+      for (int q = 0; q < nc; ++q) {
+        const int xp = cols[q];
+        for (int k = 0; k < kw; ++k) {
+          const int t = xp - k;
+          if (t < 0 || (t % sx) != 0) continue;
+          const int xo = t / sx;
+          if (xo >= wo) continue;
+          const bf16* src = de + ((((long long)b * hp + rows[r]) * wo + xo) * kwp + k) * cp;
+          for (int ch = 0; ch < c && ch < 4; ++ch) acc[ch] += __bfloat162float(src[ch]);
+        }
+      }
+    for (int ch = 0; ch < c && ch < 4; ++ch) dx[(((long long)b * c + ch) * h + y) * w + x] = acc[ch];
+  }
+}
+
+// act interior [N][H+2P][W+2P][CP] (channels < C) -> NCHW fp32, 32x32 (x, c) smem transpose tiles
+__global__ void act_to_nchw_kernel(const bf16* __restrict__ act, float* __restrict__ out, int n, int c, int h, int w,
+                                   int pad, int cp) {
+  __shared__ float tile[32][33];
+  const int x0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int y = blockIdx.z % h, b = blockIdx.z / h;
+  const int hp = h + 2 * pad, wp = w + 2 * pad;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int x = x0 + r, ch = c0 + threadIdx.x;
+    float v = 0.f;
+    if (x < w && ch < c) v = __bfloat162float(act[(((long long)b * hp + y + pad) * wp + x + pad) * cp + ch]);
+    tile[r][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int ch = c0 + r, x = x0 + threadIdx.x;
+    if (x < w && ch < c) out[(((long long)b * c + ch) * h + y) * w + x] = tile[threadIdx.x][r];
+  }
+}
+
+// NCHW fp32 -> act interior (channels < C; C..CP zero-filled when the block covers them)
+__global__ void nchw_to_act_kernel(const float* __restrict__ in, bf16* __restrict__ act, int n, int c, int h, int w,
+                                   int pad, int cp) {
+  __shared__ float tile[32][33];
+  const int x0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int y = blockIdx.z % h, b = blockIdx.z / h;
+  const int hp = h + 2 * pad, wp = w + 2 * pad;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int ch = c0 + r, x = x0 + threadIdx.x;
+    tile[r][threadIdx.x] = (x < w && ch < c) ? in[(((long long)b * c + ch) * h + y) * w + x] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int x = x0 + r, ch = c0 + threadIdx.x;
+    if (x < w && ch < cp) act[(((long long)b * hp + y + pad) * wp + x + pad) * cp + ch] = __float2bfloat16(tile[threadIdx.x][r]);
+  }
+}
+
+__global__ void halo_fill_kernel(bf16* __restrict__ act, int n, int h, int w, int c, int pad) {
+  const int hp = h + 2 * pad, wp = w + 2 * pad, cg = c / 8;
+  const long long total = (long long)n * hp * wp * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int g = (int)(t % cg); t /= cg;
+    const int xp = (int)(t % wp); t /= wp;
+    const int yp = (int)(t % hp);
+    const int b = (int)(t / hp);
+    const int y = yp - pad, x = xp - pad;
+    if (y >= 0 && y < h && x >= 0 && x < w) continue;
+    const int sy = reflect(y, h) + pad, sx = reflect(x, w) + pad;
+    const uint4 v = *reinterpret_cast<const uint4*>(act + (((long long)b * hp + sy) * wp + sx) * c + g * 8);
+    *reinterpret_cast<uint4*>(act + (((long long)b * hp + yp) * wp + xp) * c + g * 8) = v;
+  }
+}
+
+// ------------------------------------------------------------------ per-(n,c) reductions
+// Block = CG column groups x R rows (CG*R = 256); grid = (splits, N).  `Fn(n, pix, cg)` returns the
+// two 8-channel vectors to accumulate.  Partial sums are combined in smem, then atomically added.
+template <typename Fn>
+__device__ __forceinline__ void reduce_nc(Fn fn, float* __restrict__ out2, int hw, int c) {
+  extern __shared__ float red[];  // [R][C][2]
+  const int cgs = c / 8;
+  const int rows = blockDim.x / cgs;
+  const int cg = threadIdx.x % cgs, r = threadIdx.x / cgs;
+  const int n = blockIdx.y;
+  const int per = (hw + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * per;
+  const int p1 = min(hw, p0 + per);
+  float s0[8], s1[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s0[e] = s1[e] = 0.f;
+  if (r < rows)
+    for (int pix = p0 + r; pix < p1; pix += rows) {
+      F8 u, v;
+      fn(n, pix, cg, u, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        s0[e] += u.v[e];
+        s1[e] += v.v[e];
+      }
+    }
+  if (r < rows) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      red[((r * c) + cg * 8 + e) * 2 + 0] = s0[e];
+      red[((r * c) + cg * 8 + e) * 2 + 1] = s1[e];
+    }
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int rr = 0; rr < rows; ++rr) {
+      a += red[((rr * c) + ch) * 2 + 0];
+      b += red[((rr * c) + ch) * 2 + 1];
+    }
+    atomicAdd(out2 + ((long long)n * c + ch) * 2 + 0, a);
+    atomicAdd(out2 + ((long long)n * c + ch) * 2 + 1, b);
+  }
+}
+
+__global__ void norm_stats_kernel(const bf16* __restrict__ y, float* __restrict__ stats, float* __restrict__ shift,
+                                  int hw, int c) {
+  auto fn = [&](int n, int pix, int cg, F8& u, F8& v) {
+    const F8 s = load8(y + ((long long)n * hw) * c + cg * 8);
+    const F8 x = load8(y + ((long long)n * hw + pix) * c + cg * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float d = x.v[e] - s.v[e];
+      u.v[e] = d;
+      v.v[e] = d * d;
+    }
+  };
+  reduce_nc(fn, stats, hw, c);
+  if (blockIdx.x == 0)
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x)
+      shift[(long long)blockIdx.y * c + ch] = __bfloat162float(y[((long long)blockIdx.y * hw) * c + ch]);
+}
+
+__global__ void colsum_kernel(const bf16* __restrict__ dy, float* __restrict__ out, long long npix, int c) {
+  // grid.x over pixel spans; reuse the (CG x R) mapping with a single "sample".
+  extern __shared__ float red[];
+  const int cgs = c / 8;
+  const int rows = blockDim.x / cgs;
+  const int cg = threadIdx.x % cgs, r = threadIdx.x / cgs;
+  const long long per = (npix + gridDim.x - 1) / gridDim.x;
+  const long long p0 = blockIdx.x * per;
+  const long long p1 = min(npix, p0 + per);
+  float s0[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s0[e] = 0.f;
+  if (r < rows)
+    for (long long pix = p0 + r; pix < p1; pix += rows) {
+      const F8 x = load8(dy + pix * c + cg * 8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s0[e] += x.v[e];
+    }
+  if (r < rows) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[r * c + cg * 8 + e] = s0[e];
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float a = 0.f;
+    for (int rr = 0; rr < rows; ++rr) a += red[rr * c + ch];
+    atomicAdd(out + ch, a);
+  }
+}
+
+// one block per sample
+__global__ void norm_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ shift, int mode,
+                                     const float* __restrict__ p_w, const float* __restrict__ p_b, long long ldw,
+                                     float eps, float* __restrict__ mean, float* __restrict__ rinv,
+                                     float* __restrict__ a, float* __restrict__ b, int hw, int c) {
+  const int n = blockIdx.x;
+  __shared__ double sh[2][32];
+  __shared__ double tot[2];
+  const double cnt = (double)hw;
+  if (mode == MUNIT_NORM_LN) {
+    // sample mean
+    double s = 0.0;
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x)
+      s += cnt * (double)shift[(long long)n * c + ch] + (double)stats[((long long)n * c + ch) * 2];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[0][threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int i = 0; i < (blockDim.x + 31) / 32; ++i) t += sh[0][i];
+      tot[0] = t / (cnt * c);
+    }
+    __syncthreads();
+    const double mu = tot[0];
+    double ss = 0.0;
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+      const double d = mu - (double)shift[(long long)n * c + ch];
+      const double s1 = stats[((long long)n * c + ch) * 2], s2 = stats[((long long)n * c + ch) * 2 + 1];
+      ss += s2 - 2.0 * d * s1 + cnt * d * d;
+    }
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((threadIdx.x & 31) == 0) sh[1][threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int i = 0; i < (blockDim.x + 31) / 32; ++i) t += sh[1][i];
+      tot[1] = t;
+    }
+    __syncthreads();
+    const double nel = cnt * c;
+    const double sd = sqrt(fmax(tot[1], 0.0) / (nel - 1.0));  // unbiased std (networks.py:868,871)
+    const float ri = (float)(1.0 / (sd + (double)eps));       // eps outside the sqrt (networks.py:873)
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+      const float aa = p_w[ch] * ri;
+      mean[(long long)n * c + ch] = (float)mu;
+      rinv[(long long)n * c + ch] = ri;
+      a[(long long)n * c + ch] = aa;
+      b[(long long)n * c + ch] = p_b[ch] - (float)mu * aa;
+    }
+  } else {
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+      const long long i = (long long)n * c + ch;
+      const double m1 = (double)stats[i * 2] / cnt;
+      double var = (double)stats[i * 2 + 1] / cnt - m1 * m1;  // biased (F.batch_norm / InstanceNorm2d)
+      if (var < 0.0) var = 0.0;
+      const float mu = (float)((double)shift[i] + m1);
+      const float ri = (float)(1.0 / sqrt(var + (double)eps));
+      float wv = 1.f, bv = 0.f;
+      if (mode == MUNIT_NORM_ADAIN) {
+        wv = p_w[(long long)n * ldw + ch];
+        bv = p_b[(long long)n * ldw + ch];
+      }
+      const float aa = ri * wv;
+      mean[i] = mu;
+      rinv[i] = ri;
+      a[i] = aa;
+      b[i] = bv - mu * aa;
+    }
+  }
+}
+
+template <int UP>
+__global__ void norm_apply_kernel(const bf16* __restrict__ y, const float* __restrict__ a, const float* __restrict__ b,
+                                  int relu, const bf16* __restrict__ res, int res_pad, bf16* __restrict__ out,
+                                  int out_pad, int n, int h, int w, int c) {
+  const int cg = c / 8;
+  const long long total = (long long)n * h * w * cg;
+  const int ho = h * UP, wo = w * UP;
+  const int hop = ho + 2 * out_pad, wop = wo + 2 * out_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int g = (int)(t % cg); t /= cg;
+    const int x = (int)(t % w); t /= w;
+    const int yy = (int)(t % h);
+    const int bb = (int)(t / h);
+    F8 v = load8(y + i * 8);
+    const F8 fa = loadf8(a + (long long)bb * c + g * 8), fb = loadf8(b + (long long)bb * c + g * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float o = fmaf(v.v[e], fa.v[e], fb.v[e]);
+      if (relu) o = fmaxf(o, 0.f);
+      v.v[e] = o;
+    }
+    if (res) {
+      const F8 r = load8(res + (((long long)bb * (h + 2 * res_pad) + yy + res_pad) * (w + 2 * res_pad) + x + res_pad) * c + g * 8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v.v[e] += r.v[e];
+    }
+    uint4 packed;
+    {
+      __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&packed);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) hh[e] = __floats2bfloat162_rn(v.v[2 * e], v.v[2 * e + 1]);
+    }
+#pragma unroll
+    for (int uy = 0; uy < UP; ++uy) {
+      int rows[3];
+      const int nr = pad_positions(yy * UP + uy, ho, out_pad, rows);
+#pragma unroll
+      for (int ux = 0; ux < UP; ++ux) {
+        int cols[3];
+        const int nc = pad_positions(x * UP + ux, wo, out_pad, cols);
+        for (int r = 0; r < nr; ++r)
+          for (int q = 0; q < nc; ++q)
+            *reinterpret_cast<uint4*>(out + (((long long)bb * hop + rows[r]) * wop + cols[q]) * c + g * 8) = packed;
+      }
+    }
+  }
+}
+
+// gradient w.r.t. the unpadded, un-upsampled pixel: sum of g_out over every position that copied it
+template <int UP>
+__device__ __forceinline__ F8 fold_grad(const bf16* __restrict__ g_out, int bb, int yy, int x, int g, int h, int w,
+                                        int c, int pad) {
+  const int ho = h * UP, wo = w * UP;
+  const int hop = ho + 2 * pad, wop = wo + 2 * pad;
+  F8 acc;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc.v[e] = 0.f;
+#pragma unroll
+  for (int uy = 0; uy < UP; ++uy) {
+    int rows[3];
+    const int nr = pad_positions(yy * UP + uy, ho, pad, rows);
+#pragma unroll
+    for (int ux = 0; ux < UP; ++ux) {
+      int cols[3];
+      const int nc = pad_positions(x * UP + ux, wo, pad, cols);
+      for (int r = 0; r < nr; ++r)
+        for (int q = 0; q < nc; ++q) {
+          const F8 t = load8(g_out + (((long long)bb * hop + rows[r]) * wop + cols[q]) * c + g * 8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc.v[e] += t.v[e];
+        }
+    }
+  }
+  return acc;
+}
+
+template <int UP>
+__global__ void norm_bwd_reduce_kernel(const bf16* __restrict__ g_out, int out_pad, const bf16* __restrict__ y,
+                                       const float* __restrict__ a, const float* __restrict__ b, int relu,
+                                       const float* __restrict__ mean, const float* __restrict__ rinv,
+                                       float* __restrict__ sums, int h, int w, int c) {
+  const int hw = h * w;
+  auto fn = [&](int n, int pix, int cg, F8& u, F8& v) {
+    const int yy = pix / w, x = pix - yy * w;
+    const F8 g = fold_grad<UP>(g_out, n, yy, x, cg, h, w, c, out_pad);
+    const F8 xv = load8(y + ((long long)n * hw + pix) * c + cg * 8);
+    const F8 fa = loadf8(a + (long long)n * c + cg * 8), fb = loadf8(b + (long long)n * c + cg * 8);
+    const F8 fm = loadf8(mean + (long long)n * c + cg * 8), fr = loadf8(rinv + (long long)n * c + cg * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float dz = g.v[e];
+      if (relu && fmaf(xv.v[e], fa.v[e], fb.v[e]) <= 0.f) dz = 0.f;
+      u.v[e] = dz;
+      v.v[e] = dz * (xv.v[e] - fm.v[e]) * fr.v[e];
+    }
+  };
+  reduce_nc(fn, sums, hw, c);
+}
+
+// one block per sample
+__global__ void norm_bwd_finalize_kernel(const float* __restrict__ sums, int mode, const float* __restrict__ p_w,
+                                         long long ldw, const float* __restrict__ rinv, float eps,
+                                         float* __restrict__ ca, float* __restrict__ cb, float* __restrict__ cc,
+                                         float* __restrict__ g_w, float* __restrict__ g_b, long long ldg, int hw,
+                                         int c) {
+  const int n = blockIdx.x;
+  const double cnt = (double)hw;
+  if (mode == MUNIT_NORM_LN) {
+    __shared__ double sh[2][32];
+    __shared__ double tot[2];
+    double g1 = 0.0, g2 = 0.0;
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+      const long long i = (long long)n * c + ch;
+      g1 += (double)p_w[ch] * sums[i * 2];
+      g2 += (double)p_w[ch] * sums[i * 2 + 1];
+      if (g_w) atomicAdd(g_w + ch, sums[i * 2 + 1]);
+      if (g_b) atomicAdd(g_b + ch, sums[i * 2]);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      g1 += __shfl_xor_sync(0xffffffffu, g1, o);
+      g2 += __shfl_xor_sync(0xffffffffu, g2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      sh[0][threadIdx.x >> 5] = g1;
+      sh[1][threadIdx.x >> 5] = g2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t1 = 0.0, t2 = 0.0;
+      for (int i = 0; i < (blockDim.x + 31) / 32; ++i) {
+        t1 += sh[0][i];
+        t2 += sh[1][i];
+      }
+      tot[0] = t1;
+      tot[1] = t2;
+    }
+    __syncthreads();
+    const double nel = cnt * c;
+    const double s = 1.0 / (double)rinv[(long long)n * c];  // sigma + eps
+    const double sigma = fmax(s - (double)eps, 1e-30);
+    const float kc = (float)(-tot[0] / (nel * s));
+    const float kb = (float)(-tot[1] / (sigma * (nel - 1.0)));
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+      const long long i = (long long)n * c + ch;
+      ca[i] = (float)((double)p_w[ch] / s);
+      cb[i] = kb;
+      cc[i] = kc;
+    }
+  } else {
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+      const long long i = (long long)n * c + ch;
+      const float wv = (mode == MUNIT_NORM_ADAIN) ? p_w[(long long)n * ldw + ch] : 1.f;
+      const float A = rinv[i] * wv;
+      ca[i] = A;
+      cc[i] = (float)(-(double)A * sums[i * 2] / cnt);
+      cb[i] = (float)(-(double)A * sums[i * 2 + 1] / cnt);
+      if (mode == MUNIT_NORM_ADAIN) {
+        if (g_w) g_w[(long long)n * ldg + ch] = sums[i * 2 + 1];
+        if (g_b) g_b[(long long)n * ldg + ch] = sums[i * 2];
+      }
+    }
+  }
+}
+
+template <int UP>
+__global__ void norm_bwd_apply_kernel(const bf16* __restrict__ g_out, int out_pad, const bf16* __restrict__ y,
+                                      const float* __restrict__ a, const float* __restrict__ b, int relu,
+                                      const float* __restrict__ mean, const float* __restrict__ rinv,
+                                      const float* __restrict__ ca, const float* __restrict__ cb,
+                                      const float* __restrict__ cc, bf16* __restrict__ dy, bf16* __restrict__ g_res,
+                                      int res_pad, int n, int h, int w, int c) {
+  const int cg = c / 8;
+  const long long total = (long long)n * h * w * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int g = (int)(t % cg); t /= cg;
+    const int x = (int)(t % w); t /= w;
+    const int yy = (int)(t % h);
+    const int bb = (int)(t / h);
+    const F8 gr = fold_grad<UP>(g_out, bb, yy, x, g, h, w, c, out_pad);
+    const F8 xv = load8(y + i * 8);
+    const long long o = (long long)bb * c + g * 8;
+    const F8 fa = loadf8(a + o), fb = loadf8(b + o), fm = loadf8(mean + o), fr = loadf8(rinv + o);
+    const F8 fca = loadf8(ca + o), fcb = loadf8(cb + o), fcc = loadf8(cc + o);
+    F8 d;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float dz = gr.v[e];
+      if (relu && fmaf(xv.v[e], fa.v[e], fb.v[e]) <= 0.f) dz = 0.f;
+      const float xh = (xv.v[e] - fm.v[e]) * fr.v[e];
+      d.v[e] = fmaf(fca.v[e], dz, fmaf(fcb.v[e], xh, fcc.v[e]));
+    }
+    store8(dy + i * 8, d);
+    if (g_res) store8(g_res + (((long long)bb * (h + 2 * res_pad) + yy + res_pad) * (w + 2 * res_pad) + x + res_pad) * c + g * 8, gr);
+  }
+}
+
+__global__ void act_bwd_kernel(const bf16* __restrict__ g_out, const bf16* __restrict__ out_act, int pad, int act,
+                               bf16* __restrict__ dy, int n, int h, int w, int c) {
+  const int cg = c / 8;
+  const long long total = (long long)n * h * w * cg;
+  const int hp = h + 2 * pad, wp = w + 2 * pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int g = (int)(t % cg); t /= cg;
+    const int x = (int)(t % w); t /= w;
+    const int yy = (int)(t % h);
+    const int bb = (int)(t / h);
+    F8 gr = fold_grad<1>(g_out, bb, yy, x, g, h, w, c, pad);
+    if (act != MUNIT_ACT_NONE) {
+      const F8 o = load8(out_act + (((long long)bb * hp + yy + pad) * wp + x + pad) * c + g * 8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (act == MUNIT_ACT_RELU) gr.v[e] = o.v[e] > 0.f ? gr.v[e] : 0.f;
+        else if (act == MUNIT_ACT_LRELU) gr.v[e] = o.v[e] > 0.f ? gr.v[e] : 0.2f * gr.v[e];
+        else gr.v[e] *= (1.f - o.v[e] * o.v[e]);
+      }
+    }
+    store8(dy + i * 8, gr);
+  }
+}
+
+// ------------------------------------------------------------------ weights
+__global__ void gather_cast_kernel(const float* __restrict__ src, const int* __restrict__ idx, bf16* __restrict__ dst,
+                                   long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int j = idx[i];
+    dst[i] = __float2bfloat16(j >= 0 ? src[j] : 0.f);
+  }
+}
+__global__ void gather_add_kernel(const float* __restrict__ src, const int* __restrict__ idx, float* __restrict__ dst,
+                                  long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int j = idx[i];
+    if (j >= 0) dst[i] += src[j];
+  }
+}
+__global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16(src[i]);
+}
+
+// ------------------------------------------------------------------ MLP (fp32, tiny)
+// one warp per (b, o): y[b][o] = act(sum_i x[b][i] w[o][i] + bias[o])
+__global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                  const float* __restrict__ bias, float* __restrict__ y, int b, int in, int out,
+                                  int relu) {
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= (long long)b * out) return;
+  const int o = (int)(warp % out), bb = (int)(warp / out);
+  float acc = 0.f;
+  for (int i = lane; i < in; i += 32) acc = fmaf(x[(long long)bb * in + i], w[(long long)o * in + i], acc);
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (lane == 0) {
+    acc += bias ? bias[o] : 0.f;
+    y[(long long)bb * out + o] = relu ? fmaxf(acc, 0.f) : acc;
+  }
+}
+// dx[b][i] = sum_o dyp[b][o] w[o][i]   (thread per (b,i))
+__global__ void linear_bwd_dx_kernel(const float* __restrict__ w, const float* __restrict__ y,
+                                     const float* __restrict__ dy, int relu, float* __restrict__ dx, int b, int in,
+                                     int out) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= (long long)b * in) return;
+  const int i = (int)(t % in), bb = (int)(t / in);
+  float acc = 0.f;
+  for (int o = 0; o < out; ++o) {
+    float g = dy[(long long)bb * out + o];
+    if (relu && y[(long long)bb * out + o] <= 0.f) g = 0.f;
+    acc = fmaf(g, w[(long long)o * in + i], acc);
+  }
+  dx[t] = acc;
+}
+// dw[o][i] += sum_b dyp[b][o] x[b][i]; db[o] += sum_b dyp[b][o]   (thread per (o,i))
+__global__ void linear_bwd_dw_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                     const float* __restrict__ dy, int relu, float* __restrict__ dw,
+                                     float* __restrict__ db, int b, int in, int out) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= (long long)out * in) return;
+  const int i = (int)(t % in), o = (int)(t / in);
+  float acc = 0.f, accb = 0.f;
+  for (int bb = 0; bb < b; ++bb) {
+    float g = dy[(long long)bb * out + o];
+    if (relu && y[(long long)bb * out + o] <= 0.f) g = 0.f;
+    acc = fmaf(g, x[(long long)bb * in + i], acc);
+    accb += g;
+  }
+  dw[t] += acc;
+  if (i == 0 && db) db[o] += accb;
+}
+
+// ------------------------------------------------------------------ GAP / discriminator head / pooling / losses
+__global__ void gap_fwd_kernel(const bf16* __restrict__ y, float* __restrict__ out, int hw, int c) {
+  // block per (n, 32-channel group); threads (32 ch) x (8 rows)
+  const int n = blockIdx.y, c0 = blockIdx.x * 32;
+  const int ch = c0 + (threadIdx.x & 31), r = threadIdx.x >> 5;
+  __shared__ float sh[8][32];
+  float acc = 0.f;
+  if (ch < c)
+    for (int p = r; p < hw; p += 8) acc += __bfloat162float(y[((long long)n * hw + p) * c + ch]);
+  sh[r][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (r == 0 && ch < c) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x & 31];
+    out[(long long)n * c + ch] = t / hw;
+  }
+}
+__global__ void gap_bwd_kernel(const float* __restrict__ g, bf16* __restrict__ dy, int n, int hw, int c) {
+  const long long total = (long long)n * hw * c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c);
+    const int b = (int)(i / ((long long)hw * c));
+    dy[i] = __float2bfloat16(g[(long long)b * c + ch] / hw);
+  }
+}
+
+// warp per pixel
+__global__ void dis_head_fwd_kernel(const bf16* __restrict__ y, const float* __restrict__ w,
+                                    const float* __restrict__ bias, float target, float* __restrict__ out,
+                                    float* __restrict__ loss, float scale, long long npix, int c) {
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  float l = 0.f;
+  if (warp < npix) {
+    float acc = 0.f;
+    for (int i = lane * 8; i < c; i += 256) {
+      const F8 v = load8(y + warp * c + i);
+      const F8 ww = loadf8(w + i);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc = fmaf(v.v[e], ww.v[e], acc);
+    }
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    acc += bias[0];
+    if (lane == 0) {
+      out[warp] = acc;
+      l = (acc - target) * (acc - target);
+    }
+  }
+  // block reduce of l (lane 0 of each warp)
+  __shared__ float sh[32];
+  if (lane == 0) sh[threadIdx.x >> 5] = l;
+  __syncthreads();
+  if (threadIdx.x == 0 && loss) {
+    float t = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t += sh[i];
+    atomicAdd(loss, t * scale / (float)npix);
+  }
+}
+__global__ void dis_head_bwd_kernel(const bf16* __restrict__ y, const float* __restrict__ w,
+                                    const float* __restrict__ out, float target, const float* __restrict__ gscale_dev,
+                                    float gscale, bf16* __restrict__ dy, float* __restrict__ dw, float* __restrict__ db,
+                                    long long npix, int c) {
+  // thread per (pixel, 8-channel group) for dy; dw/db via a second pass below (c threads looping pixels)
+  const int cg = c / 8;
+  const float gs = gscale * (gscale_dev ? gscale_dev[0] : 1.f) * 2.f / (float)npix;
+  const long long total = npix * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    const long long p = i / cg;
+    const float d = gs * (out[p] - target);
+    const F8 ww = loadf8(w + g * 8);
+    F8 r;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r.v[e] = d * ww.v[e];
+    store8(dy + i * 8, r);
+  }
+  if (dw) {
+    // grid-stride over channels: each thread owns one channel and loops all pixels (npix is small: <= B*256)
+    for (long long ch = blockIdx.x * (long long)blockDim.x + threadIdx.x; ch < c; ch += (long long)gridDim.x * blockDim.x) {
+      float acc = 0.f;
+      for (long long p = 0; p < npix; ++p) acc = fmaf(gs * (out[p] - target), __bfloat162float(y[p * c + ch]), acc);
+      dw[ch] += acc;
+    }
+    if (db && blockIdx.x == 0 && threadIdx.x == 0) {
+      float acc = 0.f;
+      for (long long p = 0; p < npix; ++p) acc += gs * (out[p] - target);
+      db[0] += acc;
+    }
+  }
+}
+
+__global__ void avgpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int nc, int h, int w) {
+  const int ho = (h + 1) / 2, wo = (w + 1) / 2;  // floor((h + 2 - 3)/2) + 1
+  const long long total = (long long)nc * ho * wo;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int xo = (int)(i % wo), yo = (int)((i / wo) % ho);
+    const long long pl = i / ((long long)wo * ho);
+    float acc = 0.f;
+    int cnt = 0;
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int yy = 2 * yo + dy, xx = 2 * xo + dx;
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+          acc += x[(pl * h + yy) * w + xx];
+          ++cnt;
+        }
+      }
+    y[i] = acc / cnt;
+  }
+}
+__global__ void avgpool_bwd_kernel(const float* __restrict__ gy, float* __restrict__ gx, int nc, int h, int w) {
+  const int ho = (h + 1) / 2, wo = (w + 1) / 2;
+  const long long total = (long long)nc * h * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % w), yy = (int)((i / w) % h);
+    const long long pl = i / ((long long)w * h);
+    float acc = 0.f;
+    // outputs (yo, xo) whose 3x3 window (centre 2*yo) covers (yy, xx)
+    for (int yo = (yy) / 2; yo <= (yy + 1) / 2; ++yo) {
+      if (yo < 0 || yo >= ho || abs(2 * yo - yy) > 1) continue;
+      const int cy = (2 * yo - 1 >= 0 ? 1 : 0) + 1 + (2 * yo + 1 < h ? 1 : 0);
+      for (int xo = (xx) / 2; xo <= (xx + 1) / 2; ++xo) {
+        if (xo < 0 || xo >= wo || abs(2 * xo - xx) > 1) continue;
+        const int cx = (2 * xo - 1 >= 0 ? 1 : 0) + 1 + (2 * xo + 1 < w ? 1 : 0);
+        acc += gy[(pl * ho + yo) * wo + xo] / (float)(cy * cx);
+      }
+    }
+    gx[i] += acc;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ float to_f(T v);
+template <>
+__device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f(float v);
+template <>
+__device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16(v); }
+
+template <typename T>
+__global__ void l1_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b, float* __restrict__ loss, float scale,
+                              long long n) {
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc += fabsf(to_f<T>(a[i]) - to_f<T>(b[i]));
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  __shared__ float sh[32];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t += sh[i];
+    atomicAdd(loss, t * scale);
+  }
+}
+// ga = g*sign(a-b) ; gb = -ga (either may be NULL); g = scale * gscale_dev[0]
+template <typename T>
+__global__ void l1_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b, const float* __restrict__ gscale_dev,
+                              float scale, T* __restrict__ ga, T* __restrict__ gb, long long n) {
+  const float g = scale * (gscale_dev ? gscale_dev[0] : 1.f);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float d = to_f<T>(a[i]) - to_f<T>(b[i]);
+    const float s = d > 0.f ? g : (d < 0.f ? -g : 0.f);
+    if (ga) ga[i] = from_f<T>(s);
+    if (gb) gb[i] = from_f<T>(-s);
+  }
+}
+
+// ------------------------------------------------------------------ Adam
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, float* __restrict__ p_saved, bf16* __restrict__ p_bf16, long long n,
+                            int mode, int save, float lr, float b1, float b2, float eps, float wd, float bc1,
+                            float bc2, float gscale) {
+  const float sq_bc2 = sqrtf(bc2);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float pv = p[i];
+    float gv = g[i] * gscale;
+    gv = fmaf(wd, pv, gv);                    // coupled L2 (grad += wd * p)
+    const float mv = fmaf(b1, m[i], (1.f - b1) * gv);
+    const float vv = fmaf(b2, v[i], (1.f - b2) * gv * gv);
+    m[i] = mv;
+    v[i] = vv;
+    float np;
+    if (mode == 0) {
+      // torch.optim.Adam (torch 2.x): denom = sqrt(v)/sqrt(bc2) + eps ; p -= lr/bc1 * m/denom
+      const float denom = sqrtf(vv) / sq_bc2 + eps;
+      np = pv - (lr / bc1) * (mv / denom);
+    } else {
+      // ExtraAdam.update (extraadam.py:155-168): denom = sqrt(v)+eps ; u = -lr*sqrt(bc2)/bc1 * m/denom
+      const float u = -(lr * sq_bc2 / bc1) * mv / (sqrtf(vv) + eps);
+      if (mode == 1) {
+        if (save) p_saved[i] = pv;
+        np = pv + u;
+      } else {
+        np = p_saved[i] + u;
+      }
+    }
+    p[i] = np;
+    if (p_bf16) p_bf16[i] = __float2bfloat16(np);
+  }
+}
+
+__global__ void fill_kernel(float* __restrict__ p, float v, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void add_bf16_kernel(bf16* __restrict__ dst, const bf16* __restrict__ src, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    F8 a = load8(dst + i * 8);
+    const F8 b = load8(src + i * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a.v[e] += b.v[e];
+    store8(dst + i * 8, a);
+  }
+}
+
+inline int grid_for(long long work, int threads = 256, int max_blocks = 148 * 16) {
+  long long b = (work + threads - 1) / threads;
+  if (b > max_blocks) b = max_blocks;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+inline int reduce_splits(int hw, int c) {
+  const int rows = 256 / (c / 8);
+  int s = (hw + rows * 16 - 1) / (rows * 16);
+  if (s < 1) s = 1;
+  if (s > 1024) s = 1024;
+  return s;
+}
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define BF(p) reinterpret_cast<bf16*>(p)
+#define CBF(p) reinterpret_cast<const bf16*>(p)
+
+}  // namespace
+
+extern "C" {
+
+int munit_image_to_act(const float* x, void* act, int n, int c, int h, int w, int pad, int cp, void* stream) {
+  if (cp % 8 || c > cp) return mb_fail(MUNIT_ERR_ARG, "image_to_act: cp");
+  if (pad >= h || pad >= w) return mb_fail(MUNIT_ERR_ARG, "image_to_act: reflect pad >= size");
+  const long long total = (long long)n * (h + 2 * pad) * (w + 2 * pad);
+  image_to_act_kernel<<<grid_for(total), 256, 0, ST(stream)>>>(x, BF(act), n, c, h, w, pad, cp);
+  MB_CHECK_LAUNCH("image_to_act");
+  return MUNIT_OK;
+}
+
+int munit_image_to_kwexp(const float* x, void* e, int n, int c, int h, int w, int pad, int kw, int sx, int wo, int kwp,
+                         int cp, void* stream) {
+  if (cp % 8 || c > cp || kw > kwp) return mb_fail(MUNIT_ERR_ARG, "image_to_kwexp: args");
+  const long long total = (long long)n * (h + 2 * pad) * wo * kwp * (cp / 8);
+  image_to_kwexp_kernel<<<grid_for(total), 256, 0, ST(stream)>>>(x, BF(e), n, c, h, w, pad, kw, sx, wo, kwp, cp);
+  MB_CHECK_LAUNCH("image_to_kwexp");
+  return MUNIT_OK;
+}
+
+int munit_kwexp_to_image_grad(const void* de, float* dx, int n, int c, int h, int w, int pad, int kw, int sx, int wo,
+                              int kwp, int cp, void* stream) {
+  if (c > 4) return mb_fail(MUNIT_ERR_ARG, "kwexp_to_image_grad: c > 4");
+  kwexp_to_image_grad_kernel<<<grid_for((long long)n * h * w), 256, 0, ST(stream)>>>(CBF(de), dx, n, c, h, w, pad, kw,
+                                                                                      sx, wo, kwp, cp);
+  MB_CHECK_LAUNCH("kwexp_to_image_grad");
+  return MUNIT_OK;
+}
+
+int munit_act_to_nchw(const void* act, float* y, int n, int c, int h, int w, int pad, int cp, void* stream) {
+  dim3 grid((w + 31) / 32, (c + 31) / 32, n * h), block(32, 8);
+  act_to_nchw_kernel<<<grid, block, 0, ST(stream)>>>(CBF(act), y, n, c, h, w, pad, cp);
+  MB_CHECK_LAUNCH("act_to_nchw");
+  return MUNIT_OK;
+}
+
+int munit_nchw_to_act(const float* x, void* act, int n, int c, int h, int w, int pad, int cp, void* stream) {
+  dim3 grid((w + 31) / 32, (cp + 31) / 32, n * h), block(32, 8);
+  nchw_to_act_kernel<<<grid, block, 0, ST(stream)>>>(x, BF(act), n, c, h, w, pad, cp);
+  MB_CHECK_LAUNCH("nchw_to_act");
+  return MUNIT_OK;
+}
+
+int munit_halo_fill(void* act, int n, int h, int w, int c, int pad, void* stream) {
+  if (pad == 0) return MUNIT_OK;
+  if (c % 8) return mb_fail(MUNIT_ERR_ARG, "halo_fill: c %% 8");
+  if (pad >= h || pad >= w) return mb_fail(MUNIT_ERR_ARG, "halo_fill: reflect pad >= size");
+  const long long total = (long long)n * (h + 2 * pad) * (w + 2 * pad) * (c / 8);
+  halo_fill_kernel<<<grid_for(total), 256, 0, ST(stream)>>>(BF(act), n, h, w, c, pad);
+  MB_CHECK_LAUNCH("halo_fill");
+  return MUNIT_OK;
+}
+
+int munit_norm_stats(const void* y, float* stats, float* shift, int n, int hw, int c, void* stream) {
+  if (c % 8 || c / 8 > 256 || 256 % (c / 8)) return mb_fail(MUNIT_ERR_ARG, "norm_stats: channels %d", c);
+  cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)n * c, ST(stream));
+  const int rows = 256 / (c / 8);
+  dim3 grid(reduce_splits(hw, c), n);
+  norm_stats_kernel<<<grid, 256, sizeof(float) * 2 * rows * c, ST(stream)>>>(CBF(y), stats, shift, hw, c);
+  MB_CHECK_LAUNCH("norm_stats");
+  return MUNIT_OK;
+}
+
+int munit_norm_finalize(const float* stats, const float* shift, int mode, const float* p_w, const float* p_b,
+                        int64_t ldw, float eps, float* mean, float* rinv, float* a, float* b, int n, int hw, int c,
+                        void* stream) {
+  if (mode != MUNIT_NORM_IN && (!p_w || !p_b)) return mb_fail(MUNIT_ERR_ARG, "norm_finalize: missing affine params");
+  norm_finalize_kernel<<<n, 256, 0, ST(stream)>>>(stats, shift, mode, p_w, p_b, ldw, eps, mean, rinv, a, b, hw, c);
+  MB_CHECK_LAUNCH("norm_finalize");
+  return MUNIT_OK;
+}
+
+int munit_norm_apply(const void* y, const float* a, const float* b, int relu, const void* residual, int res_pad,
+                     void* out_act, int out_pad, int upsample, int n, int h, int w, int c, void* stream) {
+  if (c % 8) return mb_fail(MUNIT_ERR_ARG, "norm_apply: c %% 8");
+  const long long total = (long long)n * h * w * (c / 8);
+  if (upsample == 2)
+    norm_apply_kernel<2><<<grid_for(total), 256, 0, ST(stream)>>>(CBF(y), a, b, relu, CBF(residual), res_pad,
+                                                                   BF(out_act), out_pad, n, h, w, c);
+  else if (upsample == 1)
+    norm_apply_kernel<1><<<grid_for(total), 256, 0, ST(stream)>>>(CBF(y), a, b, relu, CBF(residual), res_pad,
+                                                                   BF(out_act), out_pad, n, h, w, c);
+  else
+    return mb_fail(MUNIT_ERR_ARG, "norm_apply: upsample must be 1 or 2");
+  MB_CHECK_LAUNCH("norm_apply");
+  return MUNIT_OK;
+}
+
+int munit_norm_bwd_reduce(const void* g_out, int out_pad, int upsample, const void* y, const float* a, const float* b,
+                          int relu, const float* mean, const float* rinv, float* sums, int n, int h, int w, int c,
+                          void* stream) {
+  if (c % 8 || c / 8 > 256 || 256 % (c / 8)) return mb_fail(MUNIT_ERR_ARG, "norm_bwd_reduce: channels %d", c);
+  cudaMemsetAsync(sums, 0, sizeof(float) * 2 * (size_t)n * c, ST(stream));
+  const int rows = 256 / (c / 8);
+  dim3 grid(reduce_splits(h * w, c), n);
+  const size_t sm = sizeof(float) * 2 * rows * c;
+  if (upsample == 2)
+    norm_bwd_reduce_kernel<2><<<grid, 256, sm, ST(stream)>>>(CBF(g_out), out_pad, CBF(y), a, b, relu, mean, rinv, sums,
+                                                             h, w, c);
+  else
+    norm_bwd_reduce_kernel<1><<<grid, 256, sm, ST(stream)>>>(CBF(g_out), out_pad, CBF(y), a, b, relu, mean, rinv, sums,
+                                                             h, w, c);
+  MB_CHECK_LAUNCH("norm_bwd_reduce");
+  return MUNIT_OK;
+}
+
+int munit_norm_bwd_finalize(const float* sums, int mode, const float* p_w, int64_t ldw, const float* rinv, float eps,
+                            float* ca, float* cb, float* cc, float* g_w, float* g_b, int64_t ldg, int n, int hw, int c,
+                            void* stream) {
+  norm_bwd_finalize_kernel<<<n, 256, 0, ST(stream)>>>(sums, mode, p_w, ldw, rinv, eps, ca, cb, cc, g_w, g_b, ldg, hw,
+                                                      c);
+  MB_CHECK_LAUNCH("norm_bwd_finalize");
+  return MUNIT_OK;
+}
+
+int munit_norm_bwd_apply(const void* g_out, int out_pad, int upsample, const void* y, const float* a, const float* b,
+                         int relu, const float* mean, const float* rinv, const float* ca, const float* cb,
+                         const float* cc, void* dy, void* g_res, int res_pad, int n, int h, int w, int c,
+                         void* stream) {
+  const long long total = (long long)n * h * w * (c / 8);
+  if (upsample == 2)
+    norm_bwd_apply_kernel<2><<<grid_for(total), 256, 0, ST(stream)>>>(CBF(g_out), out_pad, CBF(y), a, b, relu, mean,
+                                                                       rinv, ca, cb, cc, BF(dy), BF(g_res), res_pad, n,
+                                                                       h, w, c);
+  else
+    norm_bwd_apply_kernel<1><<<grid_for(total), 256, 0, ST(stream)>>>(CBF(g_out), out_pad, CBF(y), a, b, relu, mean,
+                                                                       rinv, ca, cb, cc, BF(dy), BF(g_res), res_pad, n,
+                                                                       h, w, c);
+  MB_CHECK_LAUNCH("norm_bwd_apply");
+  return MUNIT_OK;
+}
+
+int munit_act_bwd(const void* g_out, const void* out_act, int pad, int act, void* dy, int n, int h, int w, int c,
+                  void* stream) {
+  if (c % 8) return mb_fail(MUNIT_ERR_ARG, "act_bwd: c %% 8");
+  const long long total = (long long)n * h * w * (c / 8);
+  act_bwd_kernel<<<grid_for(total), 256, 0, ST(stream)>>>(CBF(g_out), CBF(out_act), pad, act, BF(dy), n, h, w, c);
+  MB_CHECK_LAUNCH("act_bwd");
+  return MUNIT_OK;
+}
+
+int munit_colsum(const void* dy, float* dbias, int64_t npix, int c, void* stream) {
+  if (c % 8 || c / 8 > 256 || 256 % (c / 8)) return mb_fail(MUNIT_ERR_ARG, "colsum: channels %d", c);
+  const int rows = 256 / (c / 8);
+  long long splits = (npix + rows * 16 - 1) / (rows * 16);
+  if (splits > 2048) splits = 2048;
+  if (splits < 1) splits = 1;
+  colsum_kernel<<<(int)splits, 256, sizeof(float) * rows * c, ST(stream)>>>(CBF(dy), dbias, npix, c);
+  MB_CHECK_LAUNCH("colsum");
+  return MUNIT_OK;
+}
+
+int munit_gather_cast(const float* src, const int32_t* idx, void* dst, int64_t n, void* stream) {
+  gather_cast_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(src, idx, BF(dst), n);
+  MB_CHECK_LAUNCH("gather_cast");
+  return MUNIT_OK;
+}
+int munit_gather_add(const float* src, const int32_t* idx, float* dst, int64_t n, void* stream) {
+  gather_add_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(src, idx, dst, n);
+  MB_CHECK_LAUNCH("gather_add");
+  return MUNIT_OK;
+}
+int munit_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  cast_bf16_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(src, BF(dst), n);
+  MB_CHECK_LAUNCH("cast_bf16");
+  return MUNIT_OK;
+}
+
+int munit_linear_fwd(const float* x, const float* w, const float* bias, float* y, int b, int in, int out, int relu,
+                     void* stream) {
+  const long long threads = (long long)b * out * 32;
+  linear_fwd_kernel<<<nblocks(threads, 256), 256, 0, ST(stream)>>>(x, w, bias, y, b, in, out, relu);
+  MB_CHECK_LAUNCH("linear_fwd");
+  return MUNIT_OK;
+}
+int munit_linear_bwd(const float* x, const float* w, const float* y, const float* dy, int relu, float* dx, float* dw,
+                     float* db, int b, int in, int out, void* stream) {
+  if (dx) {
+    linear_bwd_dx_kernel<<<nblocks((long long)b * in, 128), 128, 0, ST(stream)>>>(w, y, dy, relu, dx, b, in, out);
+    MB_CHECK_LAUNCH("linear_bwd_dx");
+  }
+  if (dw) {
+    linear_bwd_dw_kernel<<<nblocks((long long)out * in, 128), 128, 0, ST(stream)>>>(x, y, dy, relu, dw, db, b, in, out);
+    MB_CHECK_LAUNCH("linear_bwd_dw");
+  }
+  return MUNIT_OK;
+}
+
+int munit_gap_fwd(const void* y, float* out, int n, int hw, int c, void* stream) {
+  dim3 grid((c + 31) / 32, n);
+  gap_fwd_kernel<<<grid, 256, 0, ST(stream)>>>(CBF(y), out, hw, c);
+  MB_CHECK_LAUNCH("gap_fwd");
+  return MUNIT_OK;
+}
+int munit_gap_bwd(const float* g, void* dy, int n, int hw, int c, void* stream) {
+  gap_bwd_kernel<<<grid_for((long long)n * hw * c), 256, 0, ST(stream)>>>(g, BF(dy), n, hw, c);
+  MB_CHECK_LAUNCH("gap_bwd");
+  return MUNIT_OK;
+}
+
+int munit_dis_head_fwd(const void* y, const float* w, const float* bias, float target, float* out, float* loss,
+                       float scale, int64_t npix, int c, void* stream) {
+  if (c % 8) return mb_fail(MUNIT_ERR_ARG, "dis_head: c %% 8");
+  dis_head_fwd_kernel<<<nblocks(npix * 32, 256), 256, 0, ST(stream)>>>(CBF(y), w, bias, target, out, loss, scale, npix,
+                                                                        c);
+  MB_CHECK_LAUNCH("dis_head_fwd");
+  return MUNIT_OK;
+}
+int munit_dis_head_bwd(const void* y, const float* w, const float* out, float target, const float* gscale_dev,
+                       float gscale, void* dy, float* dw, float* db, int64_t npix, int c, void* stream) {
+  dis_head_bwd_kernel<<<grid_for(npix * (c / 8)), 256, 0, ST(stream)>>>(CBF(y), w, out, target, gscale_dev, gscale,
+                                                                         BF(dy), dw, db, npix, c);
+  MB_CHECK_LAUNCH("dis_head_bwd");
+  return MUNIT_OK;
+}
+
+int munit_avgpool3s2_fwd(const float* x, float* y, int nc, int h, int w, void* stream) {
+  avgpool_fwd_kernel<<<grid_for((long long)nc * ((h + 1) / 2) * ((w + 1) / 2)), 256, 0, ST(stream)>>>(x, y, nc, h, w);
+  MB_CHECK_LAUNCH("avgpool_fwd");
+  return MUNIT_OK;
+}
+int munit_avgpool3s2_bwd(const float* gy, float* gx, int nc, int h, int w, void* stream) {
+  avgpool_bwd_kernel<<<grid_for((long long)nc * h * w), 256, 0, ST(stream)>>>(gy, gx, nc, h, w);
+  MB_CHECK_LAUNCH("avgpool_bwd");
+  return MUNIT_OK;
+}
+
+int munit_l1_fwd(const float* a, const float* b, float* loss, float scale, int64_t n, void* stream) {
+  l1_fwd_kernel<float><<<grid_for(n, 256, 592), 256, 0, ST(stream)>>>(a, b, loss, scale, n);
+  MB_CHECK_LAUNCH("l1_fwd");
+  return MUNIT_OK;
+}
+int munit_l1_bwd(const float* a, const float* b, const float* gscale_dev, float scale, float* ga, float* gb, int64_t n,
+                 void* stream) {
+  l1_bwd_kernel<float><<<grid_for(n), 256, 0, ST(stream)>>>(a, b, gscale_dev, scale, ga, gb, n);
+  MB_CHECK_LAUNCH("l1_bwd");
+  return MUNIT_OK;
+}
+int munit_l1_bf16_fwd(const void* a, const void* b, float* loss, float scale, int64_t n, void* stream) {
+  l1_fwd_kernel<bf16><<<grid_for(n, 256, 592), 256, 0, ST(stream)>>>(CBF(a), CBF(b), loss, scale, n);
+  MB_CHECK_LAUNCH("l1_bf16_fwd");
+  return MUNIT_OK;
+}
+int munit_l1_bf16_bwd(const void* a, const void* b, const float* gscale_dev, float scale, void* ga, void* gb, int64_t n,
+                      void* stream) {
+  l1_bwd_kernel<bf16><<<grid_for(n), 256, 0, ST(stream)>>>(CBF(a), CBF(b), gscale_dev, scale, BF(ga), BF(gb), n);
+  MB_CHECK_LAUNCH("l1_bf16_bwd");
+  return MUNIT_OK;
+}
+
+int munit_adam(float* p, const float* g, float* m, float* v, float* p_saved, void* p_bf16, int64_t n, int mode,
+               int save, float lr, float beta1, float beta2, float eps, float wd, int step, float gscale,
+               void* stream) {
+  if (mode < 0 || mode > 2) return mb_fail(MUNIT_ERR_ARG, "adam: mode");
+  if (mode != 0 && !p_saved) return mb_fail(MUNIT_ERR_ARG, "adam: extragradient modes need p_saved");
+  const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  const float bc2 = (float)(1.0 - pow((double)beta2, (double)step));
+  adam_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(p, g, m, v, p_saved, BF(p_bf16), n, mode, save, lr, beta1, beta2,
+                                                   eps, wd, bc1, bc2, gscale);
+  MB_CHECK_LAUNCH("adam");
+  return MUNIT_OK;
+}
+
+int munit_fill_f32(float* p, float v, int64_t n, void* stream) {
+  fill_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(p, v, n);
+  MB_CHECK_LAUNCH("fill");
+  return MUNIT_OK;
+}
+int munit_add_bf16(void* dst, const void* src, int64_t n, void* stream) {
+  if (n % 8) return mb_fail(MUNIT_ERR_ARG, "add_bf16: n %% 8");
+  add_bf16_kernel<<<grid_for(n / 8), 256, 0, ST(stream)>>>(BF(dst), CBF(src), n / 8);
+  MB_CHECK_LAUNCH("add_bf16");
+  return MUNIT_OK;
+}
+
+}  // extern "C"

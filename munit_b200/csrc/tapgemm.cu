@@ -1,0 +1,569 @@
+// Tap-GEMM: implicit-GEMM convolution core for sm_100a (tcgen05.mma + TMEM + TMA).
+//   forward / dgrad : munit_tapgemm  (K-major A = pixels x channels, K-major B = weights)
+//   wgrad           : munit_wgrad    (MN-major A = dY, MN-major B = X, reduction over pixels)
+// Replaces nn.ReflectionPad2d + nn.Conv2d (networks.py:696) and their autograd backward.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/munit_b200.h"
+#include "common.h"
+#include "ptx.cuh"
+
+using namespace mb;
+
+namespace {
+
+constexpr int kThreads = 192;  // warp0 TMA, warp1 MMA/TMEM, warps2-5 epilogue
+constexpr int kMaxStages = 8;
+constexpr int kABytes = 128 * 128;  // 128 pixels x 64 bf16
+
+struct FwdParams {
+  int tw, th, tn;
+  int tiles_x, tiles_y, tiles_n;
+  int out_w, out_h, n_img;
+  int rank;
+  int mx[5], my[5], mn[5];
+  int num_taps, chunks;
+  int b_k0[MUNIT_MAX_PHASES];
+  int o_yoff[MUNIT_MAX_PHASES], o_xoff[MUNIT_MAX_PHASES];
+  __nv_bfloat16* out;
+  long long o_sn, o_sy, o_sx;
+  int o_ymul, o_xmul;
+  int n_store;
+  const float* bias;
+  int act;
+  int stages;
+  int* err;
+  int tap_off[MUNIT_MAX_TAPS][5];
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == MUNIT_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == MUNIT_ACT_LRELU) return v > 0.f ? v : 0.2f * v;
+  if (act == MUNIT_ACT_TANH) return tanhf(v);
+  return v;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ FwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int kBBytes = BN * 128;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  // dynamic smem is only guaranteed 16B aligned: align to 1024 by hand (SWIZZLE_128B atoms).
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stages = p.stages;
+
+  // tile coordinates
+  int t = blockIdx.x;
+  const int tx = t % p.tiles_x;
+  t /= p.tiles_x;
+  const int ty = t % p.tiles_y;
+  const int tnn = t / p.tiles_y;
+  const int x0 = tx * p.tw, y0 = ty * p.th, n0 = tnn * p.tn;
+  const int n_tile = blockIdx.y;
+  const int phase_id = blockIdx.z;
+  const int num_kb = p.num_taps * p.chunks;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&tmem_full_bar), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_base_slot), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      bool dead = false;
+      int base[5];
+#pragma unroll
+      for (int d = 0; d < 5; ++d) base[d] = x0 * p.mx[d] + y0 * p.my[d] + n0 * p.mn[d];
+      const int bk0 = p.b_k0[phase_id];
+      int stage = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int tap = kb / p.chunks;
+        const int kc = kb - tap * p.chunks;
+        mbar_wait(smem_u32(&empty_bar[stage]), ph ^ 1, dead, p.err);
+        const uint32_t fb = smem_u32(&full_bar[stage]);
+        mbar_arrive_expect_tx(fb, kStageBytes);
+        int c[5];
+#pragma unroll
+        for (int d = 0; d < 5; ++d) c[d] = base[d] + p.tap_off[tap][d];
+        c[0] += kc * 64;
+        const uint32_t sa = smem_base + stage * kStageBytes;
+        tma_load_nd(p.rank, sa, &tmap_a, fb, c);
+        tma_load_2d(sa + kABytes, &tmap_b, fb, bk0 + kb * 64, n_tile * BN);
+        if (++stage == stages) {
+          stage = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      bool dead = false;
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      int stage = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&full_bar[stage]), ph, dead, p.err);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * kStageBytes;
+        const uint32_t sb = sa + kABytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da = umma_desc_sw128(sa + k * 32, 0, 1024);
+          const uint64_t db = umma_desc_sw128(sb + k * 32, 0, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0);
+        }
+        umma_commit(smem_u32(&empty_bar[stage]));
+        if (++stage == stages) {
+          stage = 0;
+          ph ^= 1;
+        }
+      }
+      umma_commit(smem_u32(&tmem_full_bar));
+    }
+  } else {
+    // ===================== epilogue: TMEM -> regs -> global =====================
+    bool dead = false;
+    const int q = warp & 3;        // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane; // pixel within the tile
+    const int dx = row % p.tw;
+    const int dy = (row / p.tw) % p.th;
+    const int dn = row / (p.tw * p.th);
+    const int n = n0 + dn, y = y0 + dy, x = x0 + dx;
+    const bool valid = (n < p.n_img) && (y < p.out_h) && (x < p.out_w);
+    __nv_bfloat16* optr = p.out + (long long)n * p.o_sn + (long long)(y * p.o_ymul + p.o_yoff[phase_id]) * p.o_sy +
+                          (long long)(x * p.o_xmul + p.o_xoff[phase_id]) * p.o_sx + n_tile * BN;
+    mbar_wait(smem_u32(&tmem_full_bar), 0, dead, p.err);
+    tc_fence_after();
+    constexpr int kChunk = BN < 32 ? 16 : 32;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += kChunk) {
+      uint32_t v[kChunk];
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0;
+      if (kChunk == 32) tmem_ld_32x32(taddr, v);
+      else tmem_ld_32x16(taddr, v);
+      tmem_ld_wait();
+      if (valid && !dead) {
+        const int col0 = n_tile * BN + c0;
+#pragma unroll
+        for (int j = 0; j < kChunk; j += 8) {
+          if (col0 + j < p.n_store) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float a = __uint_as_float(v[j + e]);
+              if (p.bias) a += __ldg(p.bias + col0 + j + e);
+              f[e] = apply_act(a, p.act);
+            }
+            uint4 o;
+            o.x = pack_bf16(f[0], f[1]);
+            o.y = pack_bf16(f[2], f[3]);
+            o.z = pack_bf16(f[4], f[5]);
+            o.w = pack_bf16(f[6], f[7]);
+            *reinterpret_cast<uint4*>(optr + c0 + j) = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// =============================================================================================
+// wgrad
+// =============================================================================================
+struct WgParams {
+  int pw, ph, pn;
+  int blocks_x, blocks_y, blocks_n;  // pixel-block grid
+  int a_rank, b_rank;
+  int a_mx[5], a_my[5], a_mn[5];
+  int b_mx[5], b_my[5], b_mn[5];
+  int m_total, n_total;
+  int num_taps;
+  int n_tiles;  // N tiles per tap
+  float* dw;
+  long long s_m, s_t, s_n;
+  int ksplit;
+  int stages;
+  int* err;
+  int tap_off[MUNIT_MAX_TAPS][5];
+};
+
+constexpr int kBoxBytes = 64 * 128;  // 64 pixels x 64 channels bf16
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+             const __grid_constant__ WgParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int kNB = BN / 64;                     // B boxes per stage
+  constexpr int kStageBytes = (2 + kNB) * kBoxBytes;  // A: 2 boxes (M = 128 channels)
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stages = p.stages;
+
+  // blockIdx.x = (tap * n_tiles + n_tile), blockIdx.y = m_tile, blockIdx.z = k split
+  const int tap = blockIdx.x / p.n_tiles;
+  const int n_tile = blockIdx.x - tap * p.n_tiles;
+  const int m_tile = blockIdx.y;
+  const int total_pb = p.blocks_x * p.blocks_y * p.blocks_n;
+  const int pb_begin = (int)(((long long)total_pb * blockIdx.z) / p.ksplit);
+  const int pb_end = (int)(((long long)total_pb * (blockIdx.z + 1)) / p.ksplit);
+  const int num_kb = pb_end - pb_begin;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&tmem_full_bar), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_base_slot), BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (num_kb > 0) {
+    if (warp == 0) {
+      if (elect_one()) {
+        bool dead = false;
+        int stage = 0;
+        uint32_t ph = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          int t = pb_begin + kb;
+          const int bx = t % p.blocks_x;
+          t /= p.blocks_x;
+          const int by = t % p.blocks_y;
+          const int bnn = t / p.blocks_y;
+          const int x0 = bx * p.pw, y0 = by * p.ph, n0 = bnn * p.pn;
+          mbar_wait(smem_u32(&empty_bar[stage]), ph ^ 1, dead, p.err);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_arrive_expect_tx(fb, kStageBytes);
+          const uint32_t sa = smem_base + stage * kStageBytes;
+          int c[5];
+#pragma unroll
+          for (int d = 0; d < 5; ++d) c[d] = x0 * p.a_mx[d] + y0 * p.a_my[d] + n0 * p.a_mn[d];
+          const int ca0 = c[0] + m_tile * 128;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            c[0] = ca0 + i * 64;
+            tma_load_nd(p.a_rank, sa + i * kBoxBytes, &tmap_a, fb, c);
+          }
+#pragma unroll
+          for (int d = 0; d < 5; ++d) c[d] = x0 * p.b_mx[d] + y0 * p.b_my[d] + n0 * p.b_mn[d] + p.tap_off[tap][d];
+          const int cb0 = c[0] + n_tile * BN;
+#pragma unroll
+          for (int i = 0; i < kNB; ++i) {
+            c[0] = cb0 + i * 64;
+            tma_load_nd(p.b_rank, sa + (2 + i) * kBoxBytes, &tmap_b, fb, c);
+          }
+          if (++stage == stages) {
+            stage = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (elect_one()) {
+        bool dead = false;
+        constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);  // both operands MN-major
+        int stage = 0;
+        uint32_t ph = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), ph, dead, p.err);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * kStageBytes;
+          const uint32_t sb = sa + 2 * kBoxBytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // MN-major SW128: 16 K rows (pixels) = 2048 B; 64-channel groups kBoxBytes apart (LBO);
+            // 8-row K groups 1024 B apart (SBO).
+            const uint64_t da = umma_desc_sw128(sa + k * 2048, kBoxBytes, 1024);
+            const uint64_t db = umma_desc_sw128(sb + k * 2048, kBoxBytes, 1024);
+            umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0);
+          }
+          umma_commit(smem_u32(&empty_bar[stage]));
+          if (++stage == stages) {
+            stage = 0;
+            ph ^= 1;
+          }
+        }
+        umma_commit(smem_u32(&tmem_full_bar));
+      }
+    } else {
+      bool dead = false;
+      const int q = warp & 3;
+      const int m = m_tile * 128 + q * 32 + lane;
+      mbar_wait(smem_u32(&tmem_full_bar), 0, dead, p.err);
+      tc_fence_after();
+      float* dst = p.dw + (long long)m * p.s_m + (long long)tap * p.s_t;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+        tmem_ld_wait();
+        if (m < p.m_total && !dead) {
+          const int nb = n_tile * BN + c0;
+          if (p.s_n == 1 && ((p.s_m | p.s_t) & 3) == 0 && (nb + 32 <= p.n_total)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              red_add_v4_f32(dst + nb + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                             __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < p.n_total) red_add_f32(dst + (long long)(nb + j) * p.s_n, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+int make_tmap(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dim, const uint64_t* stride,
+              const uint32_t* box) {
+  if (!g_encode) return mb_fail(MUNIT_ERR_CUDA, "munit_init() not called or cuTensorMapEncodeTiled unavailable");
+  if (rank < 2 || rank > 5) return mb_fail(MUNIT_ERR_ARG, "tensor map rank %d not in 2..5", rank);
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return mb_fail(MUNIT_ERR_ARG, "TMA base not 16B aligned");
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dim[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (box[i] == 0 || box[i] > 256) return mb_fail(MUNIT_ERR_ARG, "TMA box[%d]=%u out of range", i, box[i]);
+    if (i > 0) {
+      gs[i - 1] = stride[i];
+      if (stride[i] % 16) return mb_fail(MUNIT_ERR_ARG, "TMA stride[%d]=%llu not multiple of 16", i,
+                                         (unsigned long long)stride[i]);
+    }
+  }
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gd, gs, bx, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return mb_fail(MUNIT_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
+  return MUNIT_OK;
+}
+
+template <int BN>
+int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, FwdParams& p, dim3 grid, cudaStream_t st) {
+  const int stage_bytes = kABytes + BN * 128;
+  int stages = p.stages;
+  if (stages <= 0) {
+    stages = (200 * 1024) / stage_bytes;
+    if (stages > 6) stages = 6;
+  }
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  tapgemm_kernel<BN><<<grid, kThreads, smem, st>>>(ta, tb, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "tapgemm launch: %s", cudaGetErrorString(e));
+  return MUNIT_OK;
+}
+
+template <int BN>
+int launch_wg(const CUtensorMap& ta, const CUtensorMap& tb, WgParams& p, dim3 grid, cudaStream_t st) {
+  const int stage_bytes = (2 + BN / 64) * kBoxBytes;
+  int stages = p.stages;
+  if (stages <= 0) {
+    stages = (200 * 1024) / stage_bytes;
+    if (stages > 6) stages = 6;
+  }
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  wgrad_kernel<BN><<<grid, kThreads, smem, st>>>(ta, tb, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(e));
+  return MUNIT_OK;
+}
+
+}  // namespace
+
+int mb_tapgemm_init() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+    return mb_fail(MUNIT_ERR_CUDA, "cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: %s",
+                   cudaGetErrorString(e));
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return MUNIT_OK;
+}
+
+extern "C" int munit_tapgemm(const munit_tapgemm_desc* d, void* stream) {
+  if (!d || !d->a || !d->b || !d->out) return mb_fail(MUNIT_ERR_ARG, "tapgemm: null pointer");
+  if (d->a_rank < 3 || d->a_rank > 5) return mb_fail(MUNIT_ERR_ARG, "tapgemm: a_rank %d", d->a_rank);
+  if (d->a_box[0] != 64) return mb_fail(MUNIT_ERR_ARG, "tapgemm: a_box[0] must be 64");
+  uint64_t prod = 1;
+  for (int i = 1; i < d->a_rank; ++i) prod *= d->a_box[i];
+  if (prod != 128 || d->tw * d->th * d->tn != 128) return mb_fail(MUNIT_ERR_ARG, "tapgemm: M tile must be 128 pixels");
+  if (d->num_taps < 1 || d->num_taps > MUNIT_MAX_TAPS || d->chunks < 1)
+    return mb_fail(MUNIT_ERR_ARG, "tapgemm: taps/chunks");
+  if (d->phases < 1 || d->phases > MUNIT_MAX_PHASES) return mb_fail(MUNIT_ERR_ARG, "tapgemm: phases");
+  if (d->b_rows % d->bn) return mb_fail(MUNIT_ERR_ARG, "tapgemm: b_rows %% bn");
+  if ((reinterpret_cast<uintptr_t>(d->out) & 15) || (d->o_sn % 8) || (d->o_sy % 8) || (d->o_sx % 8))
+    return mb_fail(MUNIT_ERR_ARG, "tapgemm: output must be 16B aligned per pixel");
+  if (d->n_store % 8) return mb_fail(MUNIT_ERR_ARG, "tapgemm: n_store must be a multiple of 8");
+  for (int ph = 0; ph < d->phases; ++ph)
+    if ((uint64_t)d->b_k0[ph] + (uint64_t)d->num_taps * d->chunks * 64 > d->b_k)
+      return mb_fail(MUNIT_ERR_ARG, "tapgemm: weight K extent too small");
+  CUtensorMap ta, tb;
+  int rc = make_tmap(&ta, d->a, d->a_rank, d->a_dim, d->a_stride, d->a_box);
+  if (rc) return rc;
+  uint64_t bdim[2] = {d->b_k, d->b_rows};
+  uint64_t bstr[2] = {0, d->b_k * 2};
+  uint32_t bbox[2] = {64, (uint32_t)d->bn};
+  rc = make_tmap(&tb, d->b, 2, bdim, bstr, bbox);
+  if (rc) return rc;
+  FwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.tw = d->tw; p.th = d->th; p.tn = d->tn;
+  p.tiles_x = (d->out_w + d->tw - 1) / d->tw;
+  p.tiles_y = (d->out_h + d->th - 1) / d->th;
+  p.tiles_n = (d->n_img + d->tn - 1) / d->tn;
+  p.out_w = d->out_w; p.out_h = d->out_h; p.n_img = d->n_img;
+  p.rank = d->a_rank;
+  for (int i = 0; i < 5; ++i) { p.mx[i] = d->mx[i]; p.my[i] = d->my[i]; p.mn[i] = d->mn[i]; }
+  p.num_taps = d->num_taps; p.chunks = d->chunks;
+  for (int i = 0; i < MUNIT_MAX_PHASES; ++i) { p.b_k0[i] = d->b_k0[i]; p.o_yoff[i] = d->o_yoff[i]; p.o_xoff[i] = d->o_xoff[i]; }
+  p.out = reinterpret_cast<__nv_bfloat16*>(d->out);
+  p.o_sn = d->o_sn; p.o_sy = d->o_sy; p.o_sx = d->o_sx; p.o_ymul = d->o_ymul; p.o_xmul = d->o_xmul;
+  p.n_store = d->n_store; p.bias = d->bias; p.act = d->act; p.stages = d->stages;
+  p.err = mb_error_flag();
+  memcpy(p.tap_off, d->tap_off, sizeof(p.tap_off));
+  dim3 grid(p.tiles_x * p.tiles_y * p.tiles_n, (unsigned)(d->b_rows / d->bn), d->phases);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (d->bn) {
+    case 16: return launch_fwd<16>(ta, tb, p, grid, st);
+    case 32: return launch_fwd<32>(ta, tb, p, grid, st);
+    case 64: return launch_fwd<64>(ta, tb, p, grid, st);
+    case 128: return launch_fwd<128>(ta, tb, p, grid, st);
+    case 256: return launch_fwd<256>(ta, tb, p, grid, st);
+  }
+  return mb_fail(MUNIT_ERR_ARG, "tapgemm: bn %d unsupported", d->bn);
+}
+
+extern "C" int munit_wgrad(const munit_wgrad_desc* d, void* stream) {
+  if (!d || !d->a || !d->b || !d->dw) return mb_fail(MUNIT_ERR_ARG, "wgrad: null pointer");
+  if (d->a_box[0] != 64 || d->b_box[0] != 64) return mb_fail(MUNIT_ERR_ARG, "wgrad: box[0] must be 64");
+  if (d->pw * d->ph * d->pn != 64) return mb_fail(MUNIT_ERR_ARG, "wgrad: pixel block must be 64");
+  if (d->num_taps < 1 || d->num_taps > MUNIT_MAX_TAPS) return mb_fail(MUNIT_ERR_ARG, "wgrad: taps");
+  CUtensorMap ta, tb;
+  int rc = make_tmap(&ta, d->a, d->a_rank, d->a_dim, d->a_stride, d->a_box);
+  if (rc) return rc;
+  rc = make_tmap(&tb, d->b, d->b_rank, d->b_dim, d->b_stride, d->b_box);
+  if (rc) return rc;
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  p.pw = d->pw; p.ph = d->ph; p.pn = d->pn;
+  p.blocks_x = (d->out_w + d->pw - 1) / d->pw;
+  p.blocks_y = (d->out_h + d->ph - 1) / d->ph;
+  p.blocks_n = (d->n_img + d->pn - 1) / d->pn;
+  p.a_rank = d->a_rank; p.b_rank = d->b_rank;
+  for (int i = 0; i < 5; ++i) {
+    p.a_mx[i] = d->a_mx[i]; p.a_my[i] = d->a_my[i]; p.a_mn[i] = d->a_mn[i];
+    p.b_mx[i] = d->b_mx[i]; p.b_my[i] = d->b_my[i]; p.b_mn[i] = d->b_mn[i];
+  }
+  p.m_total = d->m_total; p.n_total = d->n_total; p.num_taps = d->num_taps;
+  p.n_tiles = (d->n_total + d->bn - 1) / d->bn;
+  p.dw = d->dw; p.s_m = d->s_m; p.s_t = d->s_t; p.s_n = d->s_n;
+  p.stages = d->stages; p.err = mb_error_flag();
+  memcpy(p.tap_off, d->tap_off, sizeof(p.tap_off));
+  const int m_tiles = (d->m_total + 127) / 128;
+  const int total_pb = p.blocks_x * p.blocks_y * p.blocks_n;
+  int ks = d->ksplit;
+  if (ks <= 0) {
+    const int ctas = d->num_taps * p.n_tiles * m_tiles;
+    ks = (2 * 148 + ctas - 1) / ctas;  // ~2 waves
+    const int max_ks = total_pb / 8 > 0 ? total_pb / 8 : 1;  // >= 8 k-blocks per CTA
+    if (ks > max_ks) ks = max_ks;
+  }
+  if (ks > total_pb) ks = total_pb;
+  if (ks < 1) ks = 1;
+  p.ksplit = ks;
+  dim3 grid(d->num_taps * p.n_tiles, m_tiles, ks);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (d->bn) {
+    case 64: return launch_wg<64>(ta, tb, p, grid, st);
+    case 128: return launch_wg<128>(ta, tb, p, grid, st);
+    case 256: return launch_wg<256>(ta, tb, p, grid, st);
+  }
+  return mb_fail(MUNIT_ERR_ARG, "wgrad: bn %d unsupported", d->bn);
+}

@@ -1,0 +1,343 @@
+"""Thin torch-tensor wrappers over the C-ABI (munit_b200/_lib.py).  PyTorch supplies device memory and
+the current CUDA stream only; every call below launches hand-written sm_100a kernels."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ACT, NORM, TapGemmDesc, WgradDesc, check, lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _count(n=1):
+    _lib.launches += n
+
+
+def _fill5(dst, src, fill=0):
+    for i in range(5):
+        dst[i] = src[i] if i < len(src) else fill
+
+
+def tapgemm(plan, a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, bias=None, act="none", stages=0):
+    """out (bf16) <- act(tapconv(a; b) + bias) as described by `plan` (geometry.TapGemmPlan)."""
+    _lib.init()
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
+    assert a.is_cuda and a.is_contiguous() and b.is_contiguous()
+    assert b.numel() == plan.b_rows * plan.b_k, (b.shape, plan.b_rows, plan.b_k)
+    d = TapGemmDesc()
+    d.a, d.a_rank = a.data_ptr(), plan.a_rank
+    _fill5(d.a_dim, plan.a_dim, 1)
+    _fill5(d.a_stride, plan.a_stride, 0)
+    _fill5(d.a_box, plan.a_box, 1)
+    d.b, d.b_rows, d.b_k, d.bn = b.data_ptr(), plan.b_rows, plan.b_k, plan.bn
+    d.tw, d.th, d.tn = plan.tw, plan.th, plan.tn
+    d.out_w, d.out_h, d.n_img = plan.out_w, plan.out_h, plan.n_img
+    _fill5(d.mx, plan.mx)
+    _fill5(d.my, plan.my)
+    _fill5(d.mn, plan.mn)
+    d.num_taps, d.chunks = plan.num_taps, plan.chunks
+    for t, off in enumerate(plan.tap_off):
+        for i in range(5):
+            d.tap_off[t][i] = off[i] if i < len(off) else 0
+    d.phases = plan.phases
+    for i in range(plan.phases):
+        d.b_k0[i], d.o_yoff[i], d.o_xoff[i] = plan.b_k0[i], plan.o_yoff[i], plan.o_xoff[i]
+    d.out = out.data_ptr()
+    d.o_sn, d.o_sy, d.o_sx, d.o_ymul, d.o_xmul = plan.o_sn, plan.o_sy, plan.o_sx, plan.o_ymul, plan.o_xmul
+    d.n_store = plan.n_store
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() >= plan.b_rows
+    d.bias, d.act, d.stages = _ptr(bias), ACT[act], stages
+    check(lib.munit_tapgemm(C.byref(d), _stream()), "munit_tapgemm")
+    _count()
+    return out
+
+
+def wgrad(plan, a: torch.Tensor, b: torch.Tensor, dw: torch.Tensor, ksplit=0, stages=0):
+    """dw (fp32, +=) <- sum_pix a[pix, m] * b[pix@tap, n] as described by `plan` (geometry.WgradPlan)."""
+    _lib.init()
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and dw.dtype == torch.float32
+    d = WgradDesc()
+    d.a, d.a_rank = a.data_ptr(), plan.a_rank
+    _fill5(d.a_dim, plan.a_dim, 1)
+    _fill5(d.a_stride, plan.a_stride, 0)
+    _fill5(d.a_box, plan.a_box, 1)
+    _fill5(d.a_mx, plan.a_mx)
+    _fill5(d.a_my, plan.a_my)
+    _fill5(d.a_mn, plan.a_mn)
+    d.b, d.b_rank = b.data_ptr(), plan.b_rank
+    _fill5(d.b_dim, plan.b_dim, 1)
+    _fill5(d.b_stride, plan.b_stride, 0)
+    _fill5(d.b_box, plan.b_box, 1)
+    _fill5(d.b_mx, plan.b_mx)
+    _fill5(d.b_my, plan.b_my)
+    _fill5(d.b_mn, plan.b_mn)
+    d.pw, d.ph, d.pn = plan.pw, plan.ph, plan.pn
+    d.out_w, d.out_h, d.n_img = plan.out_w, plan.out_h, plan.n_img
+    d.m_total, d.n_total, d.bn, d.num_taps = plan.m_total, plan.n_total, plan.bn, plan.num_taps
+    for t, off in enumerate(plan.tap_off):
+        for i in range(5):
+            d.tap_off[t][i] = off[i] if i < len(off) else 0
+    d.dw, d.s_m, d.s_t, d.s_n = dw.data_ptr(), plan.s_m, plan.s_t, plan.s_n
+    d.ksplit, d.stages = ksplit, stages
+    check(lib.munit_wgrad(C.byref(d), _stream()), "munit_wgrad")
+    _count()
+    return dw
+
+
+# ---------------------------------------------------------------- layout
+def image_to_act(x, pad, cp):
+    n, c, h, w = x.shape
+    act = torch.empty(n, h + 2 * pad, w + 2 * pad, cp, dtype=torch.bfloat16, device=x.device)
+    check(lib.munit_image_to_act(x.data_ptr(), act.data_ptr(), n, c, h, w, pad, cp, _stream()), "image_to_act")
+    _count()
+    return act
+
+
+def image_to_kwexp(x, pad, kw, sx, kwp, cp):
+    n, c, h, w = x.shape
+    wo = (w + 2 * pad - kw) // sx + 1
+    e = torch.empty(n, h + 2 * pad, wo, kwp * cp, dtype=torch.bfloat16, device=x.device)
+    check(lib.munit_image_to_kwexp(x.data_ptr(), e.data_ptr(), n, c, h, w, pad, kw, sx, wo, kwp, cp, _stream()),
+          "image_to_kwexp")
+    _count()
+    return e
+
+
+def kwexp_to_image_grad(de, n, c, h, w, pad, kw, sx, kwp, cp):
+    wo = (w + 2 * pad - kw) // sx + 1
+    dx = torch.empty(n, c, h, w, dtype=torch.float32, device=de.device)
+    check(lib.munit_kwexp_to_image_grad(de.data_ptr(), dx.data_ptr(), n, c, h, w, pad, kw, sx, wo, kwp, cp, _stream()),
+          "kwexp_to_image_grad")
+    _count()
+    return dx
+
+
+def act_to_nchw(act, c, pad):
+    n, hp, wp, cp = act.shape
+    h, w = hp - 2 * pad, wp - 2 * pad
+    y = torch.empty(n, c, h, w, dtype=torch.float32, device=act.device)
+    check(lib.munit_act_to_nchw(act.data_ptr(), y.data_ptr(), n, c, h, w, pad, cp, _stream()), "act_to_nchw")
+    _count()
+    return y
+
+
+def nchw_to_act(x, pad, cp=None, fill_halo=True):
+    n, c, h, w = x.shape
+    cp = cp or c
+    act = torch.empty(n, h + 2 * pad, w + 2 * pad, cp, dtype=torch.bfloat16, device=x.device)
+    check(lib.munit_nchw_to_act(x.data_ptr(), act.data_ptr(), n, c, h, w, pad, cp, _stream()), "nchw_to_act")
+    _count()
+    if fill_halo and pad:
+        halo_fill(act, pad)
+    return act
+
+
+def halo_fill(act, pad):
+    n, hp, wp, c = act.shape
+    if pad:
+        check(lib.munit_halo_fill(act.data_ptr(), n, hp - 2 * pad, wp - 2 * pad, c, pad, _stream()), "halo_fill")
+        _count()
+    return act
+
+
+# ---------------------------------------------------------------- norms
+def norm_stats(y):
+    n, h, w, c = y.shape
+    stats = torch.empty(n, c, 2, dtype=torch.float32, device=y.device)
+    shift = torch.empty(n, c, dtype=torch.float32, device=y.device)
+    check(lib.munit_norm_stats(y.data_ptr(), stats.data_ptr(), shift.data_ptr(), n, h * w, c, _stream()), "norm_stats")
+    _count(2)
+    return stats, shift
+
+
+def norm_finalize(stats, shift, mode, p_w, p_b, ldw, hw, eps=1e-5):
+    n, c = shift.shape
+    o = torch.empty(4, n, c, dtype=torch.float32, device=stats.device)
+    check(lib.munit_norm_finalize(stats.data_ptr(), shift.data_ptr(), NORM[mode], _ptr(p_w), _ptr(p_b), ldw, eps,
+                                  o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), o[3].data_ptr(), n, hw, c,
+                                  _stream()), "norm_finalize")
+    _count()
+    return o  # mean, rinv, a, b
+
+
+def norm_apply(y, a, b, relu, residual, res_pad, out_pad, upsample):
+    n, h, w, c = y.shape
+    out = torch.empty(n, h * upsample + 2 * out_pad, w * upsample + 2 * out_pad, c, dtype=torch.bfloat16,
+                      device=y.device)
+    check(lib.munit_norm_apply(y.data_ptr(), a.data_ptr(), b.data_ptr(), int(relu), _ptr(residual), res_pad,
+                               out.data_ptr(), out_pad, upsample, n, h, w, c, _stream()), "norm_apply")
+    _count()
+    return out
+
+
+def norm_bwd(g_out, out_pad, upsample, y, coef, relu, mode, p_w, ldw, g_w, g_b, ldg, want_res, res_pad, eps=1e-5):
+    """Returns (dy, g_res).  coef = (mean, rinv, a, b) from norm_finalize."""
+    n, h, w, c = y.shape
+    mean, rinv, a, b = coef[0], coef[1], coef[2], coef[3]
+    sums = torch.empty(n, c, 2, dtype=torch.float32, device=y.device)
+    check(lib.munit_norm_bwd_reduce(g_out.data_ptr(), out_pad, upsample, y.data_ptr(), a.data_ptr(), b.data_ptr(),
+                                    int(relu), mean.data_ptr(), rinv.data_ptr(), sums.data_ptr(), n, h, w, c,
+                                    _stream()), "norm_bwd_reduce")
+    k = torch.empty(3, n, c, dtype=torch.float32, device=y.device)
+    check(lib.munit_norm_bwd_finalize(sums.data_ptr(), NORM[mode], _ptr(p_w), ldw, rinv.data_ptr(), eps,
+                                      k[0].data_ptr(), k[1].data_ptr(), k[2].data_ptr(), _ptr(g_w), _ptr(g_b), ldg, n,
+                                      h * w, c, _stream()), "norm_bwd_finalize")
+    dy = torch.empty_like(y)
+    g_res = None
+    if want_res:
+        g_res = torch.zeros(n, h + 2 * res_pad, w + 2 * res_pad, c, dtype=torch.bfloat16, device=y.device)
+    check(lib.munit_norm_bwd_apply(g_out.data_ptr(), out_pad, upsample, y.data_ptr(), a.data_ptr(), b.data_ptr(),
+                                   int(relu), mean.data_ptr(), rinv.data_ptr(), k[0].data_ptr(), k[1].data_ptr(),
+                                   k[2].data_ptr(), dy.data_ptr(), _ptr(g_res), res_pad, n, h, w, c, _stream()),
+          "norm_bwd_apply")
+    _count(4)
+    return dy, g_res
+
+
+def act_bwd(g_out, out_act, pad, act):
+    n, hp, wp, c = out_act.shape
+    h, w = hp - 2 * pad, wp - 2 * pad
+    dy = torch.empty(n, h, w, c, dtype=torch.bfloat16, device=g_out.device)
+    check(lib.munit_act_bwd(g_out.data_ptr(), out_act.data_ptr(), pad, ACT[act], dy.data_ptr(), n, h, w, c, _stream()),
+          "act_bwd")
+    _count()
+    return dy
+
+
+def colsum(dy, out):
+    c = dy.shape[-1]
+    check(lib.munit_colsum(dy.data_ptr(), out.data_ptr(), dy.numel() // c, c, _stream()), "colsum")
+    _count()
+    return out
+
+
+# ---------------------------------------------------------------- weights
+def gather_cast(src, idx, dst):
+    check(lib.munit_gather_cast(src.data_ptr(), idx.data_ptr(), dst.data_ptr(), dst.numel(), _stream()), "gather_cast")
+    _count()
+    return dst
+
+
+def gather_add(src, idx, dst):
+    check(lib.munit_gather_add(src.data_ptr(), idx.data_ptr(), dst.data_ptr(), dst.numel(), _stream()), "gather_add")
+    _count()
+    return dst
+
+
+def cast_bf16(src, dst):
+    check(lib.munit_cast_bf16(src.data_ptr(), dst.data_ptr(), dst.numel(), _stream()), "cast_bf16")
+    _count()
+    return dst
+
+
+# ---------------------------------------------------------------- small fp32 ops
+def linear_fwd(x, w, bias, relu):
+    b, i = x.shape
+    o = w.shape[0]
+    y = torch.empty(b, o, dtype=torch.float32, device=x.device)
+    check(lib.munit_linear_fwd(x.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr(), b, i, o, int(relu), _stream()),
+          "linear_fwd")
+    _count()
+    return y
+
+
+def linear_bwd(x, w, y, dy, relu, need_dx, dw, db):
+    b, i = x.shape
+    o = w.shape[0]
+    dx = torch.empty_like(x) if need_dx else None
+    check(lib.munit_linear_bwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), dy.data_ptr(), int(relu), _ptr(dx), _ptr(dw),
+                               _ptr(db), b, i, o, _stream()), "linear_bwd")
+    _count(2)
+    return dx
+
+
+def gap_fwd(y):
+    n, h, w, c = y.shape
+    out = torch.empty(n, c, dtype=torch.float32, device=y.device)
+    check(lib.munit_gap_fwd(y.data_ptr(), out.data_ptr(), n, h * w, c, _stream()), "gap_fwd")
+    _count()
+    return out
+
+
+def gap_bwd(g, shape):
+    n, h, w, c = shape
+    dy = torch.empty(n, h, w, c, dtype=torch.bfloat16, device=g.device)
+    check(lib.munit_gap_bwd(g.data_ptr(), dy.data_ptr(), n, h * w, c, _stream()), "gap_bwd")
+    _count()
+    return dy
+
+
+def dis_head_fwd(y, w, bias, target, loss, scale):
+    c = y.shape[-1]
+    npix = y.numel() // c
+    out = torch.empty(npix, dtype=torch.float32, device=y.device)
+    check(lib.munit_dis_head_fwd(y.data_ptr(), w.data_ptr(), bias.data_ptr(), float(target), out.data_ptr(), _ptr(loss),
+                                 float(scale), npix, c, _stream()), "dis_head_fwd")
+    _count()
+    return out
+
+
+def dis_head_bwd(y, w, out, target, gscale_dev, gscale, dw, db):
+    c = y.shape[-1]
+    npix = y.numel() // c
+    dy = torch.empty_like(y)
+    check(lib.munit_dis_head_bwd(y.data_ptr(), w.data_ptr(), out.data_ptr(), float(target), _ptr(gscale_dev),
+                                 float(gscale), dy.data_ptr(), _ptr(dw), _ptr(db), npix, c, _stream()), "dis_head_bwd")
+    _count()
+    return dy
+
+
+def avgpool_fwd(x):
+    n, c, h, w = x.shape
+    y = torch.empty(n, c, (h + 1) // 2, (w + 1) // 2, dtype=torch.float32, device=x.device)
+    check(lib.munit_avgpool3s2_fwd(x.data_ptr(), y.data_ptr(), n * c, h, w, _stream()), "avgpool_fwd")
+    _count()
+    return y
+
+
+def avgpool_bwd(gy, gx):
+    n, c, h, w = gx.shape
+    check(lib.munit_avgpool3s2_bwd(gy.data_ptr(), gx.data_ptr(), n * c, h, w, _stream()), "avgpool_bwd")
+    _count()
+    return gx
+
+
+def l1_fwd(a, b, loss, scale):
+    fn = lib.munit_l1_bf16_fwd if a.dtype == torch.bfloat16 else lib.munit_l1_fwd
+    check(fn(a.data_ptr(), b.data_ptr(), loss.data_ptr(), float(scale), a.numel(), _stream()), "l1_fwd")
+    _count()
+
+
+def l1_bwd(a, b, gscale_dev, scale, ga, gb):
+    fn = lib.munit_l1_bf16_bwd if a.dtype == torch.bfloat16 else lib.munit_l1_bwd
+    check(fn(a.data_ptr(), b.data_ptr(), _ptr(gscale_dev), float(scale), _ptr(ga), _ptr(gb), a.numel(), _stream()),
+          "l1_bwd")
+    _count()
+
+
+def adam(p, g, m, v, p_saved, p_bf16, mode, save, lr, b1, b2, eps, wd, step, gscale=1.0):
+    check(lib.munit_adam(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(p_saved), _ptr(p_bf16), p.numel(),
+                         mode, int(save), lr, b1, b2, eps, wd, step, gscale, _stream()), "adam")
+    _count()
+
+
+def fill(t, v):
+    check(lib.munit_fill_f32(t.data_ptr(), float(v), t.numel(), _stream()), "fill")
+    _count()
+    return t
+
+
+def add_bf16(dst, src):
+    check(lib.munit_add_bf16(dst.data_ptr(), src.data_ptr(), dst.numel(), _stream()), "add_bf16")
+    _count()
+    return dst
