@@ -173,8 +173,8 @@ int munit_norm_bwd_apply(const void* g_out, int out_pad, int upsample, const voi
  * (interior of out_act, halo `pad`; g_out has the same padded extent). */
 int munit_act_bwd(const void* g_out, const void* out_act, int pad, int act, void* dy, int n, int h, int w, int c,
                   void* stream);
-/* dbias[c] += sum over pixels of dy [npix][C] bf16. */
-int munit_colsum(const void* dy, float* dbias, int64_t npix, int c, void* stream);
+/* dbias[c] += sum over pixels of dy [npix][C] bf16, for c < c_out (<= C). */
+int munit_colsum(const void* dy, float* dbias, int64_t npix, int c, int c_out, void* stream);
 
 /* Weights: fp32 master (OIHW shape stored channels_last = [Cout][KH][KW][Cin]) -> bf16 GEMM shadows.
  * dst[i] = idx[i] >= 0 ? bf16(src[idx[i]]) : 0 -- the index map (built once per layer on the host) encodes

@@ -77,7 +77,7 @@ _SIGS = {
     "munit_norm_bwd_finalize": ([_vp, _i, _vp, _i64, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp], C.c_int),
     "munit_norm_bwd_apply": ([_vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], C.c_int),
     "munit_act_bwd": ([_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp], C.c_int),
-    "munit_colsum": ([_vp, _vp, _i64, _i, _vp], C.c_int),
+    "munit_colsum": ([_vp, _vp, _i64, _i, _i, _vp], C.c_int),
     "munit_gather_cast": ([_vp, _vp, _vp, _i64, _vp], C.c_int),
     "munit_gather_add": ([_vp, _vp, _vp, _i64, _vp], C.c_int),
     "munit_cast_bf16": ([_vp, _vp, _i64, _vp], C.c_int),

@@ -254,7 +254,7 @@ __global__ void norm_stats_kernel(const bf16* __restrict__ y, float* __restrict_
       shift[(long long)blockIdx.y * c + ch] = __bfloat162float(y[((long long)blockIdx.y * hw) * c + ch]);
 }
 
-__global__ void colsum_kernel(const bf16* __restrict__ dy, float* __restrict__ out, long long npix, int c) {
+__global__ void colsum_kernel(const bf16* __restrict__ dy, float* __restrict__ out, long long npix, int c, int c_out) {
   // grid.x over pixel spans; reuse the (CG x R) mapping with a single "sample".
   extern __shared__ float red[];
   const int cgs = c / 8;
@@ -277,7 +277,7 @@ __global__ void colsum_kernel(const bf16* __restrict__ dy, float* __restrict__ o
     for (int e = 0; e < 8; ++e) red[r * c + cg * 8 + e] = s0[e];
   }
   __syncthreads();
-  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+  for (int ch = threadIdx.x; ch < c_out; ch += blockDim.x) {
     float a = 0.f;
     for (int rr = 0; rr < rows; ++rr) a += red[rr * c + ch];
     atomicAdd(out + ch, a);
@@ -1029,13 +1029,13 @@ int munit_act_bwd(const void* g_out, const void* out_act, int pad, int act, void
   return MUNIT_OK;
 }
 
-int munit_colsum(const void* dy, float* dbias, int64_t npix, int c, void* stream) {
+int munit_colsum(const void* dy, float* dbias, int64_t npix, int c, int c_out, void* stream) {
   if (c % 8 || c / 8 > 256 || 256 % (c / 8)) return mb_fail(MUNIT_ERR_ARG, "colsum: channels %d", c);
   const int rows = 256 / (c / 8);
   long long splits = (npix + rows * 16 - 1) / (rows * 16);
   if (splits > 2048) splits = 2048;
   if (splits < 1) splits = 1;
-  colsum_kernel<<<(int)splits, 256, sizeof(float) * rows * c, ST(stream)>>>(CBF(dy), dbias, npix, c);
+  colsum_kernel<<<(int)splits, 256, sizeof(float) * rows * c, ST(stream)>>>(CBF(dy), dbias, npix, c, c_out < c ? c_out : c);
   MB_CHECK_LAUNCH("colsum");
   return MUNIT_OK;
 }

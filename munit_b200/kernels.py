@@ -214,9 +214,10 @@ def act_bwd(g_out, out_act, pad, act):
     return dy
 
 
-def colsum(dy, out):
+def colsum(dy, out, c_out=None):
     c = dy.shape[-1]
-    check(lib.munit_colsum(dy.data_ptr(), out.data_ptr(), dy.numel() // c, c, _stream()), "colsum")
+    check(lib.munit_colsum(dy.data_ptr(), out.data_ptr(), dy.numel() // c, c, c if c_out is None else c_out,
+                           _stream()), "colsum")
     _count()
     return out
 

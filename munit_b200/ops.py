@@ -1,0 +1,447 @@
+"""Autograd glue: torch.autograd.Function wrappers that sequence the sm_100a kernels (kernels.py).
+
+Internal activation format ("act"): torch bf16 tensor [N, H+2P, W+2P, C], NHWC, with the reflect halo
+of width P that the *consuming* convolution needs already materialised (nn.ReflectionPad2d,
+networks.py:643, is never executed as an op).  `Act` carries the tensor and its P.
+
+Parameter gradients: when a parameter already owns a `.grad` buffer (the trainer pre-allocates them in
+one flat arena) the kernels accumulate straight into it and the Function returns None for that input;
+otherwise a fresh gradient tensor is returned and autograd accumulates as usual.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import geometry as G
+from . import kernels as K
+
+
+@dataclass
+class Act:
+    t: torch.Tensor  # [N, H+2P, W+2P, C] bf16
+    pad: int
+
+    @property
+    def n(self):
+        return self.t.shape[0]
+
+    @property
+    def h(self):
+        return self.t.shape[1] - 2 * self.pad
+
+    @property
+    def w(self):
+        return self.t.shape[2] - 2 * self.pad
+
+    @property
+    def c(self):
+        return self.t.shape[3]
+
+
+def _cl_weight(weight: torch.Tensor) -> torch.Tensor:
+    """Flat view of a conv weight in [Cout][KH][KW][Cin] order (channels_last memory)."""
+    if weight.dim() == 4 and not weight.is_contiguous(memory_format=torch.channels_last):
+        weight = weight.contiguous(memory_format=torch.channels_last)
+    return weight.permute(0, 2, 3, 1).reshape(-1) if weight.dim() == 4 else weight.reshape(-1)
+
+
+def _grad_like_cl(weight: torch.Tensor) -> torch.Tensor:
+    return torch.zeros(weight.shape, dtype=torch.float32, device=weight.device).contiguous(
+        memory_format=torch.channels_last)
+
+
+class ConvLayer:
+    """Per-convolution host state: geometry, bf16 weight shadows, cached plans.  Not an nn.Module --
+    owned by Conv2dBlock next to the nn.Conv2d that holds the fp32 master parameters."""
+
+    def __init__(self, cin, cout, k, stride, pad):
+        self.cin, self.cout, self.k, self.stride, self.pad = cin, cout, k, stride, pad
+        self.first = cin < 64  # image-space layer: kw-expanded GEMM (K = 64 per kh tap)
+        if self.first:
+            assert cin <= 4 and k in (4, 7), "first-layer path supports 7x7 (s1) and 4x4 (s2) RGB convs"
+            self.kwp, self.cp = (8, 8) if k == 7 else (4, 16)
+            self.c_buf = 64
+        else:
+            assert cin % 64 == 0, f"input channels {cin} must be a multiple of 64 (or an image)"
+            self.c_buf = cin
+        self.co_rows = ((cout + 15) // 16) * 16
+        self.ck = max(64, self.co_rows)  # K extent per tap of the dgrad matrix
+        self._ver = None
+        self.w_fwd = self.w_dg = self.bias_p = None
+        self._idx_fwd = self._idx_dg = self._idx_inv = None
+        self._plans = {}
+
+    # ---- weight shadows -------------------------------------------------------------------
+    def _build_maps(self, dev):
+        c, k = self, self.k
+        if c.first:
+            fwd = G.fwd_index_map(c.cout, c.cin, k, k, c.co_rows, 64, c.kwp, c.cp)
+            dg = G.dgrad_index_map(c.cout, c.cin, k, k, c.stride, 1, 64, c.ck, c.kwp, c.cp)
+        else:
+            fwd = G.fwd_index_map(c.cout, c.cin, k, k, c.co_rows, c.cin)
+            dg = G.dgrad_index_map(c.cout, c.cin, k, k, c.stride, c.stride, c.cin, c.ck)
+        self._idx_fwd, self._idx_dg = fwd.to(dev), dg.to(dev)
+        if c.first:  # param element -> position in the padded fwd matrix (for the wgrad scatter-back)
+            inv = torch.full((c.cout * k * k * c.cin,), -1, dtype=torch.int32)
+            m = fwd >= 0
+            inv[fwd[m].long()] = torch.arange(fwd.numel(), dtype=torch.int32)[m]
+            self._idx_inv = inv.to(dev)
+        self._identity_fwd = (not c.first) and c.co_rows == c.cout
+
+    def refresh(self, weight, bias, force=False):
+        """(Re)build the bf16 GEMM operands from the fp32 master weights when they changed."""
+        ver = (weight._version, weight.data_ptr(), None if bias is None else bias._version)
+        if not force and ver == self._ver:
+            return
+        dev = weight.device
+        if self._idx_fwd is None or self._idx_fwd.device != dev:
+            self._build_maps(dev)
+            self.w_fwd = torch.empty(self.co_rows, self._idx_fwd.numel() // self.co_rows, dtype=torch.bfloat16,
+                                     device=dev)
+            rows = 64 if self.first else self.cin
+            self.w_dg = torch.empty(rows, self._idx_dg.numel() // rows, dtype=torch.bfloat16, device=dev)
+            self.bias_p = torch.zeros(self.co_rows, dtype=torch.float32, device=dev)
+        src = _cl_weight(weight.detach())
+        if self._identity_fwd:
+            K.cast_bf16(src, self.w_fwd)
+        else:
+            K.gather_cast(src, self._idx_fwd, self.w_fwd)
+        K.gather_cast(src, self._idx_dg, self.w_dg)
+        if bias is not None:
+            if self.co_rows == self.cout:
+                self.bias_p = bias.detach()
+            else:
+                self.bias_p[: self.cout].copy_(bias.detach())
+        self._ver = ver
+
+    # ---- plans ----------------------------------------------------------------------------
+    def plans(self, n, hp, wp, out_pad):
+        """hp, wp: extents of the GEMM input buffer (padded act, or the kw-expanded image)."""
+        key = (n, hp, wp, out_pad)
+        p = self._plans.get(key)
+        if p is None:
+            k, s = self.k, self.stride
+            if self.first:
+                kh, kw, sy, sx, c = k, 1, s, 1, 64
+            else:
+                kh, kw, sy, sx, c = k, k, s, s, self.cin
+            ho, wo = G.conv_out(hp, kh, sy), G.conv_out(wp, kw, sx)
+            hop, wop = ho + 2 * out_pad, wo + 2 * out_pad
+            fwd = G.plan_fwd(n, hp, wp, c, kh, kw, sy, sx, self.co_rows,
+                             (hop * wop * self.co_rows, wop * self.co_rows, self.co_rows, out_pad, out_pad))
+            dg = G.plan_dgrad(n, hp, wp, c, kh, kw, sy, sx, self.co_rows)
+            if self.first:
+                wg = G.plan_wgrad(n, hp, wp, 64, kh, 1, sy, 1, self.co_rows, self.cout, kh * 64, 64, 1)
+            else:
+                wg = G.plan_wgrad(n, hp, wp, c, kh, kw, sy, sx, self.co_rows, self.cout, kh * kw * c, c, 1)
+            p = (fwd, dg, wg, ho, wo)
+            self._plans[key] = p
+        return p
+
+
+def _param_grad_buf(p: Optional[torch.Tensor]):
+    """The pre-allocated .grad of a leaf parameter, if any (kernels accumulate into it directly)."""
+    if p is None or not isinstance(p, torch.nn.Parameter):
+        return None
+    return p.grad
+
+
+class ConvFn(torch.autograd.Function):
+    """Conv2dBlock with norm='none' (networks.py:695-701): reflect-padded input act -> conv + bias +
+    activation -> output act with the next layer's halo.  Also used with act='none', out_pad=0 to
+    produce the raw conv output that feeds a norm."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, layer: ConvLayer, act: str, out_pad: int, image_pad: int):
+        layer.refresh(weight, bias)
+        if layer.first:  # x is an NCHW fp32 image
+            n, c, h, w = x.shape
+            gemm_in = K.image_to_kwexp(x.detach().contiguous(), image_pad, layer.k, layer.stride, layer.kwp, layer.cp)
+            ctx.img_shape = (n, c, h, w)
+        else:
+            gemm_in = x
+        n, hp, wp, _ = gemm_in.shape
+        fwd, _, _, ho, wo = layer.plans(n, hp, wp, out_pad)
+        out = torch.empty(n, ho + 2 * out_pad, wo + 2 * out_pad, layer.co_rows, dtype=torch.bfloat16, device=x.device)
+        K.tapgemm(fwd, gemm_in, layer.w_fwd, out, layer.bias_p if bias is not None else None, act)
+        K.halo_fill(out, out_pad)
+        ctx.layer, ctx.act, ctx.out_pad, ctx.image_pad = layer, act, out_pad, image_pad
+        ctx.has_bias = bias is not None
+        ctx.wbuf, ctx.bbuf = _param_grad_buf(weight), _param_grad_buf(bias)
+        ctx.save_for_backward(gemm_in, out, weight)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        layer: ConvLayer = ctx.layer
+        gemm_in, out, weight = ctx.saved_tensors
+        n, hp, wp, _ = gemm_in.shape
+        _, dg, wg, ho, wo = layer.plans(n, hp, wp, ctx.out_pad)
+        g_out = g_out.contiguous()
+        if ctx.act != "none" or ctx.out_pad > 0:
+            dy = K.act_bwd(g_out, out, ctx.out_pad, ctx.act)
+        else:
+            dy = g_out
+        gx = gw = gb = None
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            buf = ctx.bbuf
+            tgt = buf if buf is not None else torch.zeros(layer.cout, dtype=torch.float32, device=dy.device)
+            K.colsum(dy, tgt, layer.cout)
+            gb = None if buf is not None else tgt
+        if ctx.needs_input_grad[0]:
+            rows = 64 if layer.first else layer.cin
+            dxp = torch.empty(n, hp, wp, rows, dtype=torch.bfloat16, device=dy.device)
+            K.tapgemm(dg, dy, layer.w_dg, dxp)
+            if layer.first:
+                ni, ci, hi, wi = ctx.img_shape
+                gx = K.kwexp_to_image_grad(dxp, ni, ci, hi, wi, ctx.image_pad, layer.k, layer.stride, layer.kwp,
+                                           layer.cp)
+            else:
+                gx = dxp
+        if ctx.needs_input_grad[1]:
+            buf = ctx.wbuf
+            if layer.first:
+                tmp = torch.zeros(layer.cout * layer.k * 64, dtype=torch.float32, device=dy.device)
+                K.wgrad(wg, dy, gemm_in, tmp)
+                tgt = buf if buf is not None else _grad_like_cl(weight)
+                K.gather_add(tmp, layer._idx_inv, _cl_weight(tgt))
+            else:
+                tgt = buf if buf is not None else _grad_like_cl(weight)
+                K.wgrad(wg, dy, gemm_in, _cl_weight(tgt))
+            gw = None if buf is not None else tgt
+        return gx, gw, gb, None, None, None, None
+
+
+class NormFn(torch.autograd.Function):
+    """InstanceNorm2d / AdaptiveInstanceNorm2d / MUNIT LayerNorm (networks.py:657,810-878) + ReLU +
+    residual add (networks.py:623) + nearest-2x upsample (networks.py:534) + the next conv's reflect
+    halo, as statistics -> finalize -> one apply pass."""
+
+    @staticmethod
+    def forward(ctx, y, p_w, p_b, residual, mode: str, relu: bool, res_pad: int, out_pad: int, upsample: int,
+                eps: float):
+        n, h, w, c = y.shape
+        y = y.contiguous()
+        stats, shift = K.norm_stats(y)
+        ldw = 0
+        if mode == "adain":
+            assert p_w.stride(1) == 1 and p_b.stride(1) == 1 and p_w.stride(0) == p_b.stride(0)
+            ldw = p_w.stride(0)
+        coef = K.norm_finalize(stats, shift, mode, p_w, p_b, ldw, h * w, eps)
+        out = K.norm_apply(y, coef[2], coef[3], relu, residual, res_pad, out_pad, upsample)
+        ctx.cfg = (mode, relu, res_pad, out_pad, upsample, eps, ldw, residual is not None)
+        ctx.wbuf, ctx.bbuf = _param_grad_buf(p_w), _param_grad_buf(p_b)
+        ctx.save_for_backward(y, coef, p_w)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        mode, relu, res_pad, out_pad, upsample, eps, ldw, has_res = ctx.cfg
+        y, coef, p_w = ctx.saved_tensors
+        n, h, w, c = y.shape
+        g_w = g_b = None
+        ret_w = ret_b = None
+        ldg = 0
+        if mode == "adain":
+            g_w = torch.empty(n, c, dtype=torch.float32, device=y.device)
+            g_b = torch.empty(n, c, dtype=torch.float32, device=y.device)
+            ldg, ret_w, ret_b = c, g_w, g_b
+        elif mode == "ln":
+            g_w = ctx.wbuf if ctx.wbuf is not None else torch.zeros(c, dtype=torch.float32, device=y.device)
+            g_b = ctx.bbuf if ctx.bbuf is not None else torch.zeros(c, dtype=torch.float32, device=y.device)
+            ret_w = None if ctx.wbuf is not None else g_w
+            ret_b = None if ctx.bbuf is not None else g_b
+        dy, g_res = K.norm_bwd(g_out.contiguous(), out_pad, upsample, y, coef, relu, mode, p_w, ldw, g_w, g_b, ldg,
+                               has_res and ctx.needs_input_grad[3], res_pad, eps)
+        return dy, ret_w, ret_b, g_res, None, None, None, None, None, None
+
+
+class ToActFn(torch.autograd.Function):
+    """NCHW fp32 (public tensor format) -> act with reflect halo."""
+
+    @staticmethod
+    def forward(ctx, x, pad: int):
+        ctx.pad = pad
+        ctx.c = x.shape[1]
+        return K.nchw_to_act(x.contiguous(), pad)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        folded = K.act_bwd(g, g, ctx.pad, "none") if ctx.pad else g
+        return K.act_to_nchw(folded, ctx.c, 0), None
+
+
+class FromActFn(torch.autograd.Function):
+    """act interior (first `c` channels) -> NCHW fp32."""
+
+    @staticmethod
+    def forward(ctx, t, c: int, pad: int):
+        ctx.pad, ctx.cp = pad, t.shape[3]
+        return K.act_to_nchw(t, c, pad)
+
+    @staticmethod
+    def backward(ctx, g):
+        # halo of the gradient buffer is zero (reads of the halo do not exist in the forward)
+        gt = K.nchw_to_act(g.contiguous(), ctx.pad, ctx.cp, fill_halo=False)
+        if ctx.pad:
+            p = ctx.pad
+            gt[:, :p].zero_(); gt[:, -p:].zero_(); gt[:, :, :p].zero_(); gt[:, :, -p:].zero_()
+        return gt, None, None
+
+
+class RepadFn(torch.autograd.Function):
+    """Change the halo width of an act (rare: only when a caller hands an act to a layer that needs a
+    different pad than its producer assumed)."""
+
+    @staticmethod
+    def forward(ctx, t, pad_in: int, pad_out: int):
+        n, hp, wp, c = t.shape
+        h, w = hp - 2 * pad_in, wp - 2 * pad_in
+        out = torch.empty(n, h + 2 * pad_out, w + 2 * pad_out, c, dtype=t.dtype, device=t.device)
+        out[:, pad_out:pad_out + h, pad_out:pad_out + w] = t[:, pad_in:pad_in + h, pad_in:pad_in + w]
+        K.halo_fill(out, pad_out)
+        ctx.pads = (pad_in, pad_out, h, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pad_in, pad_out, h, w = ctx.pads
+        g = g.contiguous()
+        folded = K.act_bwd(g, g, pad_out, "none") if pad_out else g
+        out = torch.zeros(g.shape[0], h + 2 * pad_in, w + 2 * pad_in, g.shape[3], dtype=g.dtype, device=g.device)
+        out[:, pad_in:pad_in + h, pad_in:pad_in + w] = folded
+        return out, None, None
+
+
+class LinearFn(torch.autograd.Function):
+    """nn.Linear (+ReLU) of the style MLP (networks.py:583-597,704-749), fp32."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu: bool):
+        x = x.contiguous()
+        w2 = weight.reshape(weight.shape[0], -1)
+        y = K.linear_fwd(x, w2.contiguous(), bias, relu)
+        ctx.relu = relu
+        ctx.wbuf, ctx.bbuf = _param_grad_buf(weight), _param_grad_buf(bias)
+        ctx.save_for_backward(x, weight, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight, y = ctx.saved_tensors
+        w2 = weight.reshape(weight.shape[0], -1).contiguous()
+        need_w = ctx.needs_input_grad[1]
+        dw = db = None
+        if need_w:
+            dw = ctx.wbuf if ctx.wbuf is not None else torch.zeros_like(weight)
+            db = ctx.bbuf if ctx.bbuf is not None else torch.zeros(weight.shape[0], dtype=torch.float32,
+                                                                      device=x.device)
+            assert dw.is_contiguous() or dw.dim() == 4
+        dx = K.linear_bwd(x, w2, y, gy.contiguous(), ctx.relu, ctx.needs_input_grad[0],
+                          dw.reshape(-1) if dw is not None and dw.is_contiguous() else _cl_weight(dw) if dw is not None else None,
+                          db)
+        return (dx, None if (not need_w or ctx.wbuf is not None) else dw,
+                None if (not need_w or ctx.bbuf is not None) else db, None)
+
+
+class GapFn(torch.autograd.Function):
+    """nn.AdaptiveAvgPool2d(1) (networks.py:471) on an act with no halo -> fp32 [N, C]."""
+
+    @staticmethod
+    def forward(ctx, t):
+        ctx.shape = tuple(t.shape)
+        return K.gap_fwd(t.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        return K.gap_bwd(g.contiguous(), ctx.shape)
+
+
+class DisHeadFn(torch.autograd.Function):
+    """MsImageDis head: 1x1 conv C->1 (networks.py:68) fused with its LSGAN term
+    scale * mean((out - target)^2) (networks.py:91,109).  Returns (map fp32 [N,1,H,W], loss [1])."""
+
+    @staticmethod
+    def forward(ctx, t, weight, bias, target: float, scale: float):
+        n, h, w, c = t.shape
+        loss = torch.zeros(1, dtype=torch.float32, device=t.device)
+        wv = weight.reshape(-1).contiguous()
+        out = K.dis_head_fwd(t.contiguous(), wv, bias, target, loss, scale)
+        ctx.cfg = (target, scale)
+        ctx.wbuf, ctx.bbuf = _param_grad_buf(weight), _param_grad_buf(bias)
+        ctx.save_for_backward(t, weight, out)
+        omap = out.view(n, 1, h, w)
+        ctx.mark_non_differentiable(omap)
+        return omap, loss
+
+    @staticmethod
+    def backward(ctx, g_map, g_loss):
+        t, weight, out = ctx.saved_tensors
+        target, scale = ctx.cfg
+        need_w = ctx.needs_input_grad[1]
+        dw = db = None
+        if need_w:
+            dw = ctx.wbuf if ctx.wbuf is not None else torch.zeros_like(weight)
+            db = ctx.bbuf if ctx.bbuf is not None else torch.zeros(1, dtype=torch.float32, device=t.device)
+        dy = K.dis_head_bwd(t, weight.reshape(-1).contiguous(), out, target, g_loss.contiguous(), scale,
+                            dw.view(-1) if dw is not None else None, db)
+        return (dy if ctx.needs_input_grad[0] else None,
+                None if (not need_w or ctx.wbuf is not None) else dw,
+                None if (not need_w or ctx.bbuf is not None) else db, None, None)
+
+
+class AvgPoolFn(torch.autograd.Function):
+    """nn.AvgPool2d(3, stride=2, padding=1, count_include_pad=False) (networks.py:32-34) on NCHW fp32."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.shape = tuple(x.shape)
+        return K.avgpool_fwd(x.contiguous())
+
+    @staticmethod
+    def backward(ctx, gy):
+        gx = torch.zeros(ctx.shape, dtype=torch.float32, device=gy.device)
+        return K.avgpool_bwd(gy.contiguous(), gx)
+
+
+class L1Fn(torch.autograd.Function):
+    """recon_criterion (trainer.py:279-290): mean |a - b| over interiors.  a, b: fp32 tensors of the same
+    shape, or acts with the same interior (halo widths pa, pb)."""
+
+    @staticmethod
+    def forward(ctx, a, b, pa: int, pb: int):
+        if a.dtype == torch.bfloat16:
+            n, hp, wp, c = a.shape
+            h, w = hp - 2 * pa, wp - 2 * pa
+            ai = a[:, pa:pa + h, pa:pa + w].contiguous() if pa else a.contiguous()
+            bi = b[:, pb:pb + h, pb:pb + w].contiguous() if pb else b.contiguous()
+        else:
+            ai, bi = a.contiguous(), b.contiguous()
+        loss = torch.zeros(1, dtype=torch.float32, device=a.device)
+        K.l1_fwd(ai, bi, loss, 1.0 / ai.numel())
+        ctx.pads = (pa, pb)
+        ctx.save_for_backward(ai, bi)
+        ctx.shapes = (a.shape, b.shape)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        ai, bi = ctx.saved_tensors
+        pa, pb = ctx.pads
+        need_a, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        ga = torch.empty_like(ai) if need_a else None
+        gb = torch.empty_like(bi) if need_b else None
+        K.l1_bwd(ai, bi, g.contiguous(), 1.0 / ai.numel(), ga, gb)
+
+        def embed(gi, shape, p):
+            if gi is None or p == 0:
+                return gi
+            full = torch.zeros(shape, dtype=gi.dtype, device=gi.device)
+            full[:, p:-p, p:-p] = gi
+            return full
+
+        return embed(ga, ctx.shapes[0], pa), embed(gb, ctx.shapes[1], pb), None, None
