@@ -318,13 +318,14 @@ class RepadFn(torch.autograd.Function):
 
 
 class LinearFn(torch.autograd.Function):
-    """nn.Linear (+ReLU) of the style MLP (networks.py:583-597,704-749), fp32."""
+    """nn.Linear (+ReLU) of the style MLP (networks.py:583-597,704-749) and the 1x1 style head
+    (networks.py:472), fp32.  `weight` is [out, in] or a contiguous [out, in, 1, 1] conv weight."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, relu: bool):
         x = x.contiguous()
-        w2 = weight.reshape(weight.shape[0], -1)
-        y = K.linear_fwd(x, w2.contiguous(), bias, relu)
+        assert weight.is_contiguous()
+        y = K.linear_fwd(x, weight, bias, relu)
         ctx.relu = relu
         ctx.wbuf, ctx.bbuf = _param_grad_buf(weight), _param_grad_buf(bias)
         ctx.save_for_backward(x, weight, y)
@@ -333,17 +334,13 @@ class LinearFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         x, weight, y = ctx.saved_tensors
-        w2 = weight.reshape(weight.shape[0], -1).contiguous()
         need_w = ctx.needs_input_grad[1]
         dw = db = None
         if need_w:
             dw = ctx.wbuf if ctx.wbuf is not None else torch.zeros_like(weight)
             db = ctx.bbuf if ctx.bbuf is not None else torch.zeros(weight.shape[0], dtype=torch.float32,
                                                                       device=x.device)
-            assert dw.is_contiguous() or dw.dim() == 4
-        dx = K.linear_bwd(x, w2, y, gy.contiguous(), ctx.relu, ctx.needs_input_grad[0],
-                          dw.reshape(-1) if dw is not None and dw.is_contiguous() else _cl_weight(dw) if dw is not None else None,
-                          db)
+        dx = K.linear_bwd(x, weight, y, gy.contiguous(), ctx.relu, ctx.needs_input_grad[0], dw, db)
         return (dx, None if (not need_w or ctx.wbuf is not None) else dw,
                 None if (not need_w or ctx.bbuf is not None) else db, None)
 

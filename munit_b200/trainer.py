@@ -1,0 +1,334 @@
+"""B200-native drop-in for cc-ai/MUNIT `scripts/trainer.py::MUNIT_Trainer` (hot path).
+
+Same constructor argument (the config dict), methods and attributes as the reference:
+forward (trainer.py:307-334), gen_update (:336-561), dis_update (:1133-1186), sample (:773-928),
+sample_fid (:1087-1131), update_learning_rate (:1326-1335), save / resume (:1337-1429),
+gen_opt_step / dis_opt_step (:252-268), recon_criterion(_mask) (:279-305); attributes gen | gen_a, gen_b,
+dis_a, dis_b, gen_opt, dis_opt, s_a, s_b, style_dim, iterations, loss_*.
+
+Differences that do not change results: the generator pass of dis_update runs without autograd (the
+reference records it and then .detach()es, trainer.py:1178-1179); gen_update does not compute the
+discriminator weight gradients the reference computes and discards (trainer.py:490-491 vs :1145).
+Out of scope (raise NotImplementedError): semantic_w, domain_adv_w, adaptation heads, vgg_w, synth pairs.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .networks import AdaINGen, AdaINGen_double, MsImageDis
+from .optim import ExtraAdam, FlatAdam
+from .ops import Act
+from .utils import get_model_list, get_scheduler, weights_init
+
+
+def _scalar(t):
+    return t.reshape(())
+
+
+class MUNIT_Trainer(nn.Module):
+    def __init__(self, hyperparameters):
+        super().__init__()
+        lr = hyperparameters["lr"]
+        self.gen_state = hyperparameters["gen_state"]
+        self.guided = hyperparameters["guided"]
+        self.newsize = hyperparameters["crop_image_height"]
+        self.semantic_w = hyperparameters["semantic_w"] > 0
+        self.recon_mask = hyperparameters["recon_mask"] == 1
+        self.dann_scheduler = None
+        self.full_adaptation = hyperparameters["adaptation"]["full_adaptation"] == 1
+        self.hyperparameters = hyperparameters
+        for k, why in (("semantic_w", "needs the Resnet34_8s checkpoint"), ("domain_adv_w", "domainClassifier head"),
+                       ("vgg_w", "load_vgg16 always raises in the reference")):
+            if hyperparameters.get(k, 0) > 0:
+                raise NotImplementedError(f"{k} > 0 is outside the B200 hot path ({why}); see SURVEY.md s2")
+        for k in ("dfeat_lambda", "adv_lambda", "sem_seg_lambda", "output_classifier_lambda", "output_adv_lambda"):
+            if hyperparameters["adaptation"].get(k, 0) > 0:
+                raise NotImplementedError(f"adaptation.{k} > 0 is outside the B200 hot path; see SURVEY.md s8(f)")
+        optimizer = FlatAdam if "extra" not in hyperparameters["optimizer"] else ExtraAdam
+        self.domain_classif_ab = False
+        self.use_classifier_sr = False
+        self.train_seg = False
+        self.use_output_classifier_sr = False
+
+        if self.gen_state == 0:
+            self.gen_a = AdaINGen(hyperparameters["input_dim_a"], hyperparameters["gen"])  # auto-encoder for domain a
+            self.gen_b = AdaINGen(hyperparameters["input_dim_b"], hyperparameters["gen"])  # auto-encoder for domain b
+        elif self.gen_state == 1:
+            self.gen = AdaINGen_double(hyperparameters["input_dim_a"], hyperparameters["gen"])
+        else:
+            print("self.gen_state unknown value:", self.gen_state)
+        self.dis_a = MsImageDis(hyperparameters["input_dim_a"], hyperparameters["dis"])  # discriminator for domain a
+        self.dis_b = MsImageDis(hyperparameters["input_dim_b"], hyperparameters["dis"])  # discriminator for domain b
+        self.instancenorm = nn.InstanceNorm2d(512, affine=False)
+        self.style_dim = hyperparameters["gen"]["style_dim"]
+
+        # fix the noise used in sampling (host RNG, drawn mid-stream exactly like trainer.py:93-95)
+        display_size = int(hyperparameters["display_size"])
+        self.s_a = torch.randn(display_size, self.style_dim, 1, 1)
+        self.s_b = torch.randn(display_size, self.style_dim, 1, 1)
+
+        beta1 = hyperparameters["beta1"]
+        beta2 = hyperparameters["beta2"]
+        dis_params = list(self.dis_a.parameters()) + list(self.dis_b.parameters())
+        if self.gen_state == 0:
+            gen_params = list(self.gen_a.parameters()) + list(self.gen_b.parameters())
+        else:
+            gen_params = list(self.gen.parameters())
+        self.dis_opt = optimizer([p for p in dis_params if p.requires_grad], lr=lr, betas=(beta1, beta2),
+                                 weight_decay=hyperparameters["weight_decay"])
+        self.gen_opt = optimizer([p for p in gen_params if p.requires_grad], lr=lr, betas=(beta1, beta2),
+                                 weight_decay=hyperparameters["weight_decay"])
+        self.dis_scheduler = get_scheduler(self.dis_opt, hyperparameters)
+        self.gen_scheduler = get_scheduler(self.gen_opt, hyperparameters)
+
+        # Network weight initialization (trainer.py:124-127)
+        self.apply(weights_init(hyperparameters["init"]))
+        self.dis_a.apply(weights_init("gaussian"))
+        self.dis_b.apply(weights_init("gaussian"))
+        self.iterations = 0
+
+    # ------------------------------------------------------------------ device
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self.s_a = fn(self.s_a)
+        self.s_b = fn(self.s_b)
+        return out
+
+    # ------------------------------------------------------------------ optimiser steps (trainer.py:252-268)
+    def dis_opt_step(self):
+        if "extra" in self.hyperparameters["optimizer"] and (self.iterations % 2 == 0):
+            self.dis_opt.extrapolation()
+        else:
+            self.dis_opt.step()
+
+    def gen_opt_step(self):
+        if "extra" in self.hyperparameters["optimizer"] and (self.iterations % 2 == 0):
+            self.gen_opt.extrapolation()
+        else:
+            self.gen_opt.step()
+
+    # ------------------------------------------------------------------ losses (trainer.py:279-305)
+    def recon_criterion(self, input, target):
+        """mean |input - target|; accepts NCHW fp32 tensors or Act pairs (content codes)."""
+        if isinstance(input, Act):
+            return _scalar(ops.L1Fn.apply(input.t, target.t, input.pad, target.pad))
+        return _scalar(ops.L1Fn.apply(input.float(), target.float(), 0, 0))
+
+    def recon_criterion_mask(self, input, target, mask):
+        """mean |(input - target) * (1 - mask)| over all elements (trainer.py:292-305)."""
+        keep = 1 - mask
+        return _scalar(ops.L1Fn.apply((input * keep).float(), (target * keep).float(), 0, 0))
+
+    # ------------------------------------------------------------------ generator plumbing
+    def _enc(self, which, x):
+        if self.gen_state == 0:
+            return (self.gen_a if which == "a" else self.gen_b).encode_act(x)
+        return self.gen.encode_act(x, 1 if which == "a" else 2)
+
+    def _dec(self, which, c, s):
+        if self.gen_state == 0:
+            return (self.gen_a if which == "a" else self.gen_b).decode(c, s)
+        return self.gen.decode(c, s, 1 if which == "a" else 2)
+
+    def _style_noise(self, x_a, x_b, s_a, s_b):
+        """Host-generator draws in the reference's order (trainer.py:366-367,1146-1147) unless supplied."""
+        if s_a is None:
+            s_a = torch.randn(x_a.size(0), self.style_dim, 1, 1).to(x_a.device)
+            s_b = torch.randn(x_b.size(0), self.style_dim, 1, 1).to(x_b.device)
+        return s_a, s_b
+
+    def forward(self, x_a, x_b):
+        """Translate x_a -> x_ab and x_b -> x_ba with the fixed display codes (trainer.py:307-334)."""
+        self.eval()
+        with torch.no_grad():
+            c_a, _ = self._enc("a", x_a)
+            c_b, _ = self._enc("b", x_b)
+            x_ba = self._dec("a", c_b, self.s_a)
+            x_ab = self._dec("b", c_a, self.s_b)
+        self.train()
+        return x_ab, x_ba
+
+    # ------------------------------------------------------------------ updates
+    def gen_update(self, x_a, x_b, hyperparameters, mask_a=None, mask_b=None, comet_exp=None, synth=False,
+                   semantic_gt_a=None, semantic_gt_b=None, s_a=None, s_b=None):
+        """One generator update (trainer.py:336-561)."""
+        if synth:
+            raise NotImplementedError("synthetic-pair losses are a 'next' item (SURVEY.md s8(f).4)")
+        self.gen_opt.zero_grad()
+        s_a, s_b = self._style_noise(x_a, x_b, s_a, s_b)
+        # encode
+        c_a, s_a_prime = self._enc("a", x_a)
+        c_b, s_b_prime = self._enc("b", x_b)
+        # decode (within domain)
+        x_a_recon = self._dec("a", c_a, s_a_prime)
+        x_b_recon = self._dec("b", c_b, s_b_prime)
+        # decode (cross domain)
+        if self.guided == 0:
+            x_ba = self._dec("a", c_b, s_a)
+            x_ab = self._dec("b", c_a, s_b)
+        elif self.guided == 1:
+            x_ba = self._dec("a", c_b, s_a_prime)
+            x_ab = self._dec("b", c_a, s_b_prime)
+        else:
+            print("self.guided unknown value:", self.guided)
+        # encode again
+        c_b_recon, s_a_recon = self._enc("a", x_ba)
+        c_a_recon, s_b_recon = self._enc("b", x_ab)
+        # decode again (if needed)
+        cyc = hyperparameters["recon_x_cyc_w"] > 0
+        x_aba = self._dec("a", c_a_recon, s_a_prime) if cyc else None
+        x_bab = self._dec("b", c_b_recon, s_b_prime) if cyc else None
+
+        # reconstruction loss
+        self.loss_gen_recon_x_a = self.recon_criterion(x_a_recon, x_a)
+        self.loss_gen_recon_x_b = self.recon_criterion(x_b_recon, x_b)
+        if self.guided == 0:
+            self.loss_gen_recon_s_a = self.recon_criterion(s_a_recon, s_a)
+            self.loss_gen_recon_s_b = self.recon_criterion(s_b_recon, s_b)
+        else:
+            self.loss_gen_recon_s_a = self.recon_criterion(s_a_recon, s_a_prime)
+            self.loss_gen_recon_s_b = self.recon_criterion(s_b_recon, s_b_prime)
+        self.loss_gen_recon_c_a = self.recon_criterion(c_a_recon, c_a)
+        self.loss_gen_recon_c_b = self.recon_criterion(c_b_recon, c_b)
+        self.loss_gen_recon_synth = 0
+        if self.recon_mask:
+            self.loss_gen_cycrecon_x_a = self.recon_criterion_mask(x_aba, x_a, mask_a) if cyc else 0
+            self.loss_gen_cycrecon_x_b = self.recon_criterion_mask(x_bab, x_b, mask_b) if cyc else 0
+        else:
+            self.loss_gen_cycrecon_x_a = self.recon_criterion(x_aba, x_a) if cyc else 0
+            self.loss_gen_cycrecon_x_b = self.recon_criterion(x_bab, x_b) if cyc else 0
+        # GAN loss (discriminator weights frozen: dgrad only)
+        self.loss_gen_adv_a = self.dis_a.calc_gen_loss(x_ba, frozen=True)
+        self.loss_gen_adv_b = self.dis_b.calc_gen_loss(x_ab, frozen=True)
+        self.loss_gen_vgg_a = 0
+        self.loss_gen_vgg_b = 0
+        self.loss_sem_seg = 0
+        self.domain_adv_loss = 0
+        self.loss_classifier_sr = 0
+        self.loss_output_classifier_sr = 0
+        # total loss (trainer.py:539-558)
+        self.loss_gen_total = (
+            hyperparameters["gan_w"] * self.loss_gen_adv_a
+            + hyperparameters["gan_w"] * self.loss_gen_adv_b
+            + hyperparameters["recon_x_w"] * self.loss_gen_recon_x_a
+            + hyperparameters["recon_s_w"] * self.loss_gen_recon_s_a
+            + hyperparameters["recon_c_w"] * self.loss_gen_recon_c_a
+            + hyperparameters["recon_x_w"] * self.loss_gen_recon_x_b
+            + hyperparameters["recon_s_w"] * self.loss_gen_recon_s_b
+            + hyperparameters["recon_c_w"] * self.loss_gen_recon_c_b
+            + hyperparameters["recon_x_cyc_w"] * self.loss_gen_cycrecon_x_a
+            + hyperparameters["recon_x_cyc_w"] * self.loss_gen_cycrecon_x_b
+        )
+        self.loss_gen_total.backward()
+        self.gen_opt_step()
+        self._last = dict(x_ab=x_ab.detach(), x_ba=x_ba.detach())
+        if comet_exp is not None and self.iterations % 100 == 0:
+            for k in ("loss_gen_adv_a", "loss_gen_adv_b", "loss_gen_recon_x_a", "loss_gen_recon_s_a",
+                      "loss_gen_recon_c_a", "loss_gen_recon_x_b", "loss_gen_recon_s_b", "loss_gen_recon_c_b",
+                      "loss_gen_cycrecon_x_a", "loss_gen_cycrecon_x_b", "loss_gen_total"):
+                comet_exp.log_metric(k, getattr(self, k).cpu().detach())
+
+    def dis_update(self, x_a, x_b, hyperparameters, comet_exp=None, s_a=None, s_b=None):
+        """One discriminator update (trainer.py:1133-1186)."""
+        self.dis_opt.zero_grad()
+        s_a, s_b = self._style_noise(x_a, x_b, s_a, s_b)
+        with torch.no_grad():
+            c_a, s_a_prime = self._enc("a", x_a)
+            c_b, s_b_prime = self._enc("b", x_b)
+            if self.guided == 0:
+                x_ba = self._dec("a", c_b, s_a)
+                x_ab = self._dec("b", c_a, s_b)
+            elif self.guided == 1:
+                x_ba = self._dec("a", c_b, s_a_prime)
+                x_ab = self._dec("b", c_a, s_b_prime)
+            else:
+                print("self.guided unknown value:", self.guided)
+        # D loss
+        self.loss_dis_a = self.dis_a.calc_dis_loss(x_ba.detach(), x_a)
+        self.loss_dis_b = self.dis_b.calc_dis_loss(x_ab.detach(), x_b)
+        self.loss_dis_total = hyperparameters["gan_w"] * self.loss_dis_a + hyperparameters["gan_w"] * self.loss_dis_b
+        self.loss_dis_total.backward()
+        self.dis_opt_step()
+        if comet_exp is not None and self.iterations % 100 == 0:
+            comet_exp.log_metric("loss_dis_b", self.loss_dis_b.cpu().detach())
+            comet_exp.log_metric("loss_dis_a", self.loss_dis_a.cpu().detach())
+
+    # ------------------------------------------------------------------ sampling (trainer.py:773-928,1087-1131)
+    def sample(self, x_a, x_b):
+        """(x_a, x_a_recon, x_ab1, x_ab2, x_b, x_b_recon, x_ba1, x_ba2).  Batched: every norm is
+        per-sample, so this equals the reference's batch-1 loop."""
+        self.eval()
+        n = x_a.size(0)
+        s_a1, s_b1 = self.s_a[:n], self.s_b[:n]
+        s_a2 = torch.randn(x_a.size(0), self.style_dim, 1, 1).to(x_a.device)
+        s_b2 = torch.randn(x_b.size(0), self.style_dim, 1, 1).to(x_b.device)
+        with torch.no_grad():
+            c_a, s_a_fake = self._enc("a", x_a)
+            c_b, s_b_fake = self._enc("b", x_b)
+            x_a_recon = self._dec("a", c_a, s_a_fake)
+            x_b_recon = self._dec("b", c_b, s_b_fake)
+            if self.guided == 0:
+                x_ba1, x_ba2 = self._dec("a", c_b, s_a1), self._dec("a", c_b, s_a2)
+                x_ab1, x_ab2 = self._dec("b", c_a, s_b1), self._dec("b", c_a, s_b2)
+            else:
+                x_ba1 = x_ba2 = self._dec("a", c_b, s_a_fake)
+                x_ab1 = x_ab2 = self._dec("b", c_a, s_b_fake)
+        self.train()
+        return x_a, x_a_recon, x_ab1, x_ab2, x_b, x_b_recon, x_ba1, x_ba2
+
+    def sample_fid(self, x_a, x_b):
+        self.eval()
+        with torch.no_grad():
+            c_a, _ = self._enc("a", x_a)
+            _, s_b_fake = self._enc("b", x_b)
+            if self.guided == 1:
+                x_ab1 = self._dec("b", c_a, s_b_fake)
+            else:
+                print("self.guided unknown value:", self.guided)
+                x_ab1 = None
+        self.train()
+        return x_ab1
+
+    def update_learning_rate(self):
+        """trainer.py:1326-1335."""
+        if self.dis_scheduler is not None:
+            self.dis_scheduler.step()
+        if self.gen_scheduler is not None:
+            self.gen_scheduler.step()
+
+    # ------------------------------------------------------------------ checkpoints (trainer.py:1337-1429)
+    def resume(self, checkpoint_dir, hyperparameters):
+        last_model_name = get_model_list(checkpoint_dir, "gen")
+        state_dict = torch.load(last_model_name, map_location="cpu")
+        if self.gen_state == 0:
+            self.gen_a.load_state_dict(state_dict["a"])
+            self.gen_b.load_state_dict(state_dict["b"])
+        else:
+            self.gen.load_state_dict(state_dict["2"])
+        iterations = int(last_model_name[-11:-3])
+        last_model_name = get_model_list(checkpoint_dir, "dis")
+        state_dict = torch.load(last_model_name, map_location="cpu")
+        self.dis_a.load_state_dict(state_dict["a"])
+        self.dis_b.load_state_dict(state_dict["b"])
+        state_dict = torch.load(os.path.join(checkpoint_dir, "optimizer.pt"), map_location="cpu")
+        self.dis_opt.load_state_dict(state_dict["dis"])
+        self.gen_opt.load_state_dict(state_dict["gen"])
+        self.dis_scheduler = get_scheduler(self.dis_opt, hyperparameters, iterations)
+        self.gen_scheduler = get_scheduler(self.gen_opt, hyperparameters, iterations)
+        print("Resume from iteration %d" % iterations)
+        return iterations
+
+    def save(self, snapshot_dir, iterations):
+        gen_name = os.path.join(snapshot_dir, "gen_%08d.pt" % (iterations + 1))
+        dis_name = os.path.join(snapshot_dir, "dis_%08d.pt" % (iterations + 1))
+        opt_name = os.path.join(snapshot_dir, "optimizer.pt")
+        if self.gen_state == 0:
+            torch.save({"a": self.gen_a.state_dict(), "b": self.gen_b.state_dict()}, gen_name)
+        else:
+            torch.save({"2": self.gen.state_dict()}, gen_name)
+        torch.save({"a": self.dis_a.state_dict(), "b": self.dis_b.state_dict()}, dis_name)
+        torch.save({"gen": self.gen_opt.state_dict(), "dis": self.dis_opt.state_dict()}, opt_name)

@@ -1,0 +1,136 @@
+"""Drop-in modules (munit_b200/networks.py) on the B200 against the CPU oracle / golden fixtures.
+bf16 tensor-core path: rel-L2 <= 1e-2 per layer (BASELINE.json north_star); whole networks stack ~20
+bf16 layers, so their end-to-end outputs are held to 3e-2 and reported."""
+import pytest
+import torch
+
+from oracle import munit_oracle as O
+from tests.gpu_util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+LAYER_TOL = 1e-2
+NET_TOL = 3e-2
+
+
+def _images(seed, b, hw):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(b, 3, hw, hw, generator=g) * 2 - 1, torch.rand(b, 3, hw, hw, generator=g) * 2 - 1
+
+
+BLOCKS = [
+    # cin, cout, k, s, p, norm, act, n, hw
+    (3, 64, 7, 1, 3, "none", "relu", 2, 32),
+    (3, 64, 7, 1, 3, "in", "relu", 2, 32),
+    (3, 64, 4, 2, 1, "none", "lrelu", 2, 32),
+    (64, 128, 4, 2, 1, "in", "relu", 2, 32),
+    (64, 128, 4, 2, 1, "none", "lrelu", 3, 16),
+    (256, 256, 3, 1, 1, "in", "relu", 2, 16),
+    (256, 256, 3, 1, 1, "in", "none", 1, 16),
+    (128, 64, 5, 1, 2, "ln", "relu", 2, 24),
+    (64, 3, 7, 1, 3, "none", "tanh", 2, 32),
+]
+
+
+@pytest.mark.parametrize("cin,cout,k,s,p,norm,act,n,hw", BLOCKS)
+def test_conv2dblock_forward_backward(cin, cout, k, s, p, norm, act, n, hw):
+    from munit_b200.networks import Conv2dBlock
+
+    torch.manual_seed(0)
+    blk = Conv2dBlock(cin, cout, k, s, p, norm=norm, activation=act, pad_type="reflect")
+    torch.nn.init.normal_(blk.conv.bias, 0, 0.1)
+    sd = {k_: v.detach().clone().contiguous().requires_grad_(True) for k_, v in blk.state_dict().items()}
+    x = torch.randn(n, cin, hw, hw)
+    xr = x.clone().requires_grad_(True)
+    y_ref = O.conv_block(sd, "", xr, s, p, norm, act)
+    gy = torch.randn_like(y_ref)
+    y_ref.backward(gy)
+    blk = blk.cuda()
+    xg = x.cuda().requires_grad_(True)
+    y = blk(xg)
+    assert y.shape == y_ref.shape
+    assert rel_l2(y.cpu(), y_ref) < LAYER_TOL, rel_l2(y.cpu(), y_ref)
+    y.backward(gy.cuda())
+    assert rel_l2(xg.grad.cpu(), xr.grad) < 2 * LAYER_TOL, ("dx", rel_l2(xg.grad.cpu(), xr.grad))
+    assert rel_l2(blk.conv.weight.grad.cpu(), sd["conv.weight"].grad) < 2 * LAYER_TOL
+    if norm in ("none", "ln"):
+        assert rel_l2(blk.conv.bias.grad.cpu(), sd["conv.bias"].grad) < 2 * LAYER_TOL
+    if norm == "ln":
+        assert rel_l2(blk.norm.gamma.grad.cpu(), sd["norm.gamma"].grad) < 2 * LAYER_TOL
+        assert rel_l2(blk.norm.beta.grad.cpu(), sd["norm.beta"].grad) < 2 * LAYER_TOL
+
+
+def test_generator_and_discriminator_vs_golden(golden):
+    """AdaINGen_double / AdaINGen / MsImageDis forward on the seeded weights of tests/golden/nets.pt
+    (reference outputs) -- also exercises load_state_dict with the reference's keys."""
+    from munit_b200.networks import AdaINGen, AdaINGen_double, MsImageDis
+
+    fx = golden("nets.pt")
+    cfg = O.config_256_core()
+    gsd = O.init_state_dict(O.gen_spec(cfg["gen"], 3, True), fx["seeds"]["gen"], "kaiming")
+    dsd = O.init_state_dict(O.dis_spec(cfg["dis"], 3), fx["seeds"]["dis"], "gaussian")
+    gen = AdaINGen_double(3, cfg["gen"])
+    gen.load_state_dict(gsd)
+    dis = MsImageDis(3, cfg["dis"])
+    dis.load_state_dict(dsd)
+    gen, dis = gen.cuda(), dis.cuda()
+    x_a, x_b = _images(fx["seeds"]["img"], fx["b"], fx["hw"])
+    x_a, x_b = x_a.cuda(), x_b.cuda()
+    with torch.no_grad():
+        c_a, s_a = gen.encode(x_a, 1)
+        c_b, s_b = gen.encode(x_b, 2)
+        x_ab = gen.decode(c_a, s_b, 2)
+        x_ba = gen.decode(c_b, s_a, 1)
+        ap = gen.get_adain_param(s_b, 2)
+        x_ab_ref = fx["x_ab"].cuda()
+        d_out = dis(x_ab_ref)
+        dl = dis.calc_dis_loss(x_ab_ref, x_b)
+        gl = dis.calc_gen_loss(x_ab_ref)
+    errs = dict(s_a=rel_l2(s_a.cpu(), fx["s_a"]), s_b=rel_l2(s_b.cpu(), fx["s_b"]),
+                x_ab=rel_l2(x_ab.cpu(), fx["x_ab"]), x_ba=rel_l2(x_ba.cpu(), fx["x_ba"]))
+    for i, (o, r) in enumerate(zip(d_out, fx["d_out"])):
+        assert o.shape == r.shape
+        errs[f"d{i}"] = rel_l2(o.cpu(), r)
+    print("whole-network rel-L2:", {k: round(v, 5) for k, v in errs.items()})
+    assert max(errs.values()) < NET_TOL, errs
+    assert c_a.shape == tuple(fx["c_a"]["shape"]) and ap.shape == tuple(fx["adain_params"]["shape"])
+    assert abs(float(dl) - fx["dis_loss"]) < 2e-2 * abs(fx["dis_loss"])
+    assert abs(float(gl) - fx["gen_loss"]) < 2e-2 * abs(fx["gen_loss"])
+    # single generator with sampled style (gen_state 0 / test_batch.py semantics)
+    g0 = AdaINGen(3, cfg["gen"])
+    g0.load_state_dict(O.init_state_dict(O.gen_spec(cfg["gen"], 3, False), fx["seeds"]["gen0"], "kaiming"))
+    g0 = g0.cuda()
+    with torch.no_grad():
+        c0, s0 = g0.encode(x_a)
+        y0 = g0.decode(c0, fx["s_rand"].cuda())
+    assert rel_l2(y0.cpu(), fx["y0"]) < NET_TOL and rel_l2(s0.cpu(), fx["s0"]) < NET_TOL
+
+
+def test_adain_assignment_is_exact():
+    """assign_adain_params slicing (networks.py:230-239) must be bit-exact."""
+    from munit_b200.networks import AdaINGen
+
+    cfg = O.config_256_core()
+    g = AdaINGen(3, cfg["gen"])
+    n_ad = g.get_num_adain_params(g.dec)
+    assert n_ad == 4096
+    p = torch.arange(2 * n_ad, dtype=torch.float32).view(2, n_ad)
+    g.assign_adain_params(p, g.dec)
+    ref = O.split_adain_params(p, 8, 256)
+    mods = [m for m in g.dec.modules() if m.__class__.__name__ == "AdaptiveInstanceNorm2d"]
+    assert len(mods) == 8
+    for m, (b, w) in zip(mods, ref):
+        assert torch.equal(m.bias, b) and torch.equal(m.weight, w)
+
+
+def test_standalone_norm_modules():
+    from munit_b200.networks import AdaptiveInstanceNorm2d, LayerNorm
+
+    x = torch.randn(2, 64, 8, 8)
+    ln = LayerNorm(64)
+    ref = O.layer_norm_munit(x, ln.gamma.detach(), ln.beta.detach())
+    assert rel_l2(ln.cuda()(x.cuda()).cpu(), ref) < LAYER_TOL
+    ad = AdaptiveInstanceNorm2d(64).cuda()
+    w, b = torch.randn(128), torch.randn(128)
+    ad.weight, ad.bias = w.cuda(), b.cuda()
+    assert rel_l2(ad(x.cuda()).cpu(), O.instance_norm(x, w, b)) < LAYER_TOL
