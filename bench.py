@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Benchmark of the MUNIT training hot path on B200 (contract: see the task statement / DESIGN.md s6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # munit_b200 (sm_100a kernels)
+    python bench.py --impl reference [--gpus N] ...                # the reference's CPU path (oracle port)
+
+One step = MUNIT_Trainer.dis_update + gen_update (train.py:182-187) on `--batch` image pairs per GPU,
+config_256-core (configs/config_256.yaml with semantic/adaptation heads off), 256x256, synthetic
+uniform[-1,1] images, seeded kaiming/gaussian weights.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "MUNIT train steps/sec (gen+dis) 256^2"
+UNIT = "steps/s (1 step = dis_update+gen_update on 8 image pairs)"
+
+
+def load_cfg(hd=False):
+    from munit_b200.utils import core_config, get_config
+
+    cfg = core_config(get_config(os.path.join(ROOT, "configs", "config_HD.yaml" if hd else "config_256.yaml")))
+    return cfg
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(tflops=d.get("bf16_tflops_sustained", d.get("bf16_tflops")), tflops_burst=d.get("bf16_tflops"),
+                    hbm=d.get("hbm_gbs"), src="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                          str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower() == "active"})
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+def synthetic_images(batch, hw, seed):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(batch, 3, hw, hw, generator=g) * 2 - 1, torch.rand(batch, 3, hw, hw, generator=g) * 2 - 1)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the reference's algorithm on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_steps(cfg, hw, steps, warmup, batch_equiv, budget_s=150.0):
+    """Times dis_update+gen_update of the reference's CPU path at batch 1 (the reference's own batch size,
+    config_256.yaml:13).  Uses the unmodified reference when /root/reference is present, else the oracle
+    port (oracle/munit_oracle.py, pinned to the reference by tests/golden).  Returns steps/s scaled to
+    `batch_equiv` image pairs per step."""
+    from oracle import munit_oracle as O
+    from oracle import ref_loader
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    x_a, x_b = synthetic_images(1, hw, 1234)
+    kind = "port"
+    if ref_loader.available():
+        torch.manual_seed(0)
+        tr = ref_loader.make_trainer(cfg)
+        kind = "reference"
+
+        def one(it):
+            tr.iterations = it
+            tr.dis_update(x_a, x_b, cfg)
+            tr.gen_update(x_a, x_b, cfg)
+    else:
+        double = cfg["gen_state"] == 1
+        if double:
+            gsd = O.init_state_dict(O.gen_spec(cfg["gen"], 3, True), 21, cfg["init"])
+        else:
+            gsd = {k: O.init_state_dict(O.gen_spec(cfg["gen"], 3, False), s, cfg["init"]) for k, s in (("a", 21), ("b", 22))}
+        tr = O.OracleTrainer(cfg, gsd, O.init_state_dict(O.dis_spec(cfg["dis"], 3), 23, "gaussian"),
+                             O.init_state_dict(O.dis_spec(cfg["dis"], 3), 24, "gaussian"))
+
+        def one(it):
+            tr.iterations = it
+            tr.dis_update(x_a, x_b)
+            tr.gen_update(x_a, x_b)
+    t0 = time.time()
+    times = []
+    for it in range(warmup + steps):
+        t1 = time.time()
+        one(it)
+        if it >= warmup:
+            times.append(time.time() - t1)
+        if time.time() - t0 > budget_s and times:
+            break
+    if not times:
+        times = [time.time() - t0]
+    per_step_b1 = sorted(times)[len(times) // 2]
+    value = 1.0 / (per_step_b1 * batch_equiv)
+    sample = (f"{len(times)} timed step(s) of dis_update+gen_update at batch 1 (the reference's batch size), {hw}x{hw}, "
+              f"fp32, median {per_step_b1:.2f} s/step; steps/s scaled by 1/{batch_equiv} to the batch-{batch_equiv} step")
+    return value, kind, sample, per_step_b1
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    cfg = load_cfg(args.hd)
+    hw = cfg["crop_image_height"]
+    v, kind, sample, per = cpu_reference_steps(cfg, hw, max(1, min(args.steps, 3)), 1, args.batch)
+    world = int(os.environ.get("WORLD_SIZE", args.gpus))
+    line = dict(impl="reference", metric=METRIC, value=v, unit=UNIT, n_gpus=world, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1000.0 / v, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic",
+                config=dict(workload=f"config_256-core train step, batch {args.batch}, {hw}x{hw}", optimizer=cfg["optimizer"]),
+                cpu_baseline=dict(value=v, unit=UNIT, cores=os.cpu_count(), kind=kind, sample=sample),
+                e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def profile_tensor_kernels(runner):
+    """One extra (untimed) eager step with CUDA events around every tap-GEMM / wgrad launch on the launching
+    stream: per-launch device time and direct-form FLOPs of the dominant kernel family."""
+    from munit_b200 import kernels as K
+
+    rec = {"tapgemm": [], "wgrad": []}
+    orig_t, orig_w = K.tapgemm, K.wgrad
+
+    def wrap(name, fn):
+        def inner(plan, *a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(plan, *a, **k)
+            e1.record()
+            rec[name].append((e0, e1, getattr(plan, "alg_flops", 0.0)))
+            return out
+        return inner
+
+    K.tapgemm, K.wgrad = wrap("tapgemm", orig_t), wrap("wgrad", orig_w)
+    try:
+        runner._prepare_host_state()
+        runner._eager_step()
+        runner._advance()
+        torch.cuda.synchronize()
+    finally:
+        K.tapgemm, K.wgrad = orig_t, orig_w
+    out = {}
+    for name, lst in rec.items():
+        ms = sum(a.elapsed_time(b) for a, b, _ in lst)
+        fl = sum(f for _, _, f in lst)
+        out[name] = dict(launches=len(lst), ms=ms, flops=fl)
+    return out
+
+
+def run_b200(args):
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from munit_b200 import _lib
+    from munit_b200.engine import StepRunner
+    from munit_b200.trainer import MUNIT_Trainer
+
+    cfg = load_cfg(args.hd)
+    if args.optimizer:
+        cfg["optimizer"] = args.optimizer
+    hw = args.hw or cfg["crop_image_height"]
+    torch.manual_seed(0)  # identical replicas on every rank
+    trainer = MUNIT_Trainer(cfg).cuda()
+    runner = StepRunner(trainer, cfg, args.batch, hw, use_graph=not args.no_graph, world=world)
+    x_a, x_b = synthetic_images(args.batch, hw, 1234 + rank)
+    x_a_h, x_b_h = x_a.pin_memory(), x_b.pin_memory()
+    sd = trainer.style_dim
+    s_host = [torch.zeros(args.batch, sd, 1, 1).pin_memory() for _ in range(4)]
+
+    def draw_styles():
+        # host-generator draws in the reference's order: dis_update (s_a, s_b) then gen_update (s_a, s_b)
+        for s in s_host:
+            s.copy_(torch.randn(args.batch, sd, 1, 1))
+
+    torch.manual_seed(1000 + rank)
+    draw_styles()
+    runner.load_inputs(x_a_h, x_b_h, *s_host)
+    runner.warmup_and_capture(2)
+    for _ in range(args.warmup):
+        runner.step()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- value: inputs resident in HBM
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        runner.step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    # ---- e2e: host buffers -> H2D every step, loss read back every step
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    last = None
+    for _ in range(args.steps):
+        draw_styles()
+        runner.load_inputs(x_a_h, x_b_h, *s_host)
+        runner.step()
+        ls = runner.losses()
+        last = (float(ls["loss_dis_total"]), float(ls["loss_gen_total"]))  # D2H + sync
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tt = torch.tensor([ms, ms_e2e], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(tt[0]), float(tt[1])
+    prof = profile_tensor_kernels(runner)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = measured_peaks()
+    steps_per_s = args.steps / (ms / 1000.0) * world  # batch-8-equivalent steps, whole job
+    e2e_per_s = args.steps / (ms_e2e / 1000.0) * world
+    tg = prof["tapgemm"]
+    ach = tg["flops"] / (tg["ms"] / 1000.0) / 1e12 if tg["ms"] > 0 else 0.0
+    wg = prof["wgrad"]
+    ach_w = wg["flops"] / (wg["ms"] / 1000.0) / 1e12 if wg["ms"] > 0 else 0.0
+    h2d = 2 * args.batch * 3 * hw * hw * 4 + 4 * args.batch * sd * 4 + 2 * 16
+    algo_tflop_step = 2.790 * args.batch * (hw / 256.0) ** 2  # SURVEY.md s8d, per sample pair at 256^2
+    cpu_v, cpu_kind, cpu_sample, _ = cpu_reference_steps(cfg, hw, 2, 1, args.batch, budget_s=40.0) \
+        if (world == 1 and not args.no_cpu_baseline) else (None, "port", "skipped (N>1 or --no-cpu-baseline)", None)
+    line = dict(
+        metric=METRIC, value=steps_per_s, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+        ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+        data="synthetic",
+        config=dict(workload=f"config_256-core train step (dis_update+gen_update), batch {args.batch}/GPU, {hw}x{hw}",
+                    global_batch=args.batch * world, gen_state=cfg["gen_state"], guided=cfg["guided"],
+                    optimizer=cfg["optimizer"], parallelism=f"dp{world}", cuda_graph=not args.no_graph,
+                    l2="per-step working set (several GB of bf16 activations) >> 126 MB L2; no explicit flush"),
+        e2e=dict(value=e2e_per_s, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=8,
+                 last_losses=dict(dis=last[0], gen=last[1])),
+        gpu_launches=(runner.launches_per_step or 0) * args.steps,
+        clocks=clocks,
+        roofline=dict(bound="tensor", kernel="tapgemm_kernel<BN> (conv fwd + dgrad, tcgen05)", achieved=ach,
+                      peak=peaks["tflops"], unit="TFLOP/s", frac=ach / peaks["tflops"] if peaks["tflops"] else None,
+                      traffic=None, peak_source=peaks["src"], launches_per_step=tg["launches"],
+                      kernel_ms_per_step=tg["ms"],
+                      wgrad=dict(achieved=ach_w, launches_per_step=wg["launches"], kernel_ms_per_step=wg["ms"]),
+                      step_algorithmic_tflop=algo_tflop_step,
+                      step_frac=(algo_tflop_step / (ms / args.steps / 1000.0)) / peaks["tflops"]),
+        cpu_baseline=dict(value=cpu_v, unit=UNIT, cores=os.cpu_count(), kind=cpu_kind, sample=cpu_sample),
+    )
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="image pairs per GPU per step")
+    ap.add_argument("--hw", type=int, default=0, help="override crop size")
+    ap.add_argument("--hd", action="store_true", help="config_HD (512x512, ExtraAdam)")
+    ap.add_argument("--optimizer", default="")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

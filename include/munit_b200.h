@@ -219,10 +219,12 @@ int munit_l1_bf16_bwd(const void* a, const void* b, const float* gscale_dev, flo
 /* Flat multi-tensor Adam over one contiguous fp32 arena (torch.optim.Adam as resolved by trainer.py:41-45,
  * and ExtraAdam.update extraadam.py:119-168).  mode 0: torch Adam; 1: legacy formula, extrapolate
  * (p_saved = p if save; p += u); 2: legacy formula, step (p = p_saved + u).  gscale multiplies the
- * gradient first (1/world for data parallel).  Optionally refreshes a bf16 copy of p. */
+ * gradient first (1/world for data parallel).  Optionally refreshes a bf16 copy of p.  If hyper_dev is
+ * non-NULL the kernel reads {lr, 1-beta1^t, 1-beta2^t} from that device array instead of the host
+ * arguments, so a captured CUDA graph can be replayed with advancing step / learning rate. */
 int munit_adam(float* p, const float* g, float* m, float* v, float* p_saved, void* p_bf16, int64_t n, int mode,
                int save, float lr, float beta1, float beta2, float eps, float wd, int step, float gscale,
-               void* stream);
+               const float* hyper_dev, void* stream);
 
 int munit_fill_f32(float* p, float v, int64_t n, void* stream);
 int munit_add_bf16(void* dst, const void* src, int64_t n, void* stream);

@@ -93,7 +93,7 @@ _SIGS = {
     "munit_l1_bwd": ([_vp, _vp, _vp, _f, _vp, _vp, _i64, _vp], C.c_int),
     "munit_l1_bf16_fwd": ([_vp, _vp, _vp, _f, _i64, _vp], C.c_int),
     "munit_l1_bf16_bwd": ([_vp, _vp, _vp, _f, _vp, _vp, _i64, _vp], C.c_int),
-    "munit_adam": ([_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _f, _f, _f, _f, _f, _i, _f, _vp], C.c_int),
+    "munit_adam": ([_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _f, _f, _f, _f, _f, _i, _f, _vp, _vp], C.c_int),
     "munit_fill_f32": ([_vp, _f, _i64, _vp], C.c_int),
     "munit_add_bf16": ([_vp, _vp, _i64, _vp], C.c_int),
 }

@@ -825,7 +825,12 @@ __global__ void l1_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b, 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, float* __restrict__ p_saved, bf16* __restrict__ p_bf16, long long n,
                             int mode, int save, float lr, float b1, float b2, float eps, float wd, float bc1,
-                            float bc2, float gscale) {
+                            float bc2, float gscale, const float* __restrict__ hyper) {
+  if (hyper) {  // step-dependent scalars read from device memory (CUDA-graph replays)
+    lr = hyper[0];
+    bc1 = hyper[1];
+    bc2 = hyper[2];
+  }
   const float sq_bc2 = sqrtf(bc2);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float pv = p[i];
@@ -1140,13 +1145,13 @@ int munit_l1_bf16_bwd(const void* a, const void* b, const float* gscale_dev, flo
 
 int munit_adam(float* p, const float* g, float* m, float* v, float* p_saved, void* p_bf16, int64_t n, int mode,
                int save, float lr, float beta1, float beta2, float eps, float wd, int step, float gscale,
-               void* stream) {
+               const float* hyper_dev, void* stream) {
   if (mode < 0 || mode > 2) return mb_fail(MUNIT_ERR_ARG, "adam: mode");
   if (mode != 0 && !p_saved) return mb_fail(MUNIT_ERR_ARG, "adam: extragradient modes need p_saved");
   const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
   const float bc2 = (float)(1.0 - pow((double)beta2, (double)step));
   adam_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(p, g, m, v, p_saved, BF(p_bf16), n, mode, save, lr, beta1, beta2,
-                                                   eps, wd, bc1, bc2, gscale);
+                                                   eps, wd, bc1, bc2, gscale, hyper_dev);
   MB_CHECK_LAUNCH("adam");
   return MUNIT_OK;
 }

@@ -1,0 +1,159 @@
+"""Step runner: one MUNIT training step (dis_update + gen_update, train.py:182-187) executed as CUDA
+graph replays -- a step issues ~2000 kernels, so Python launch overhead would otherwise dominate at
+B = 8 -- and batch data parallelism: one process per GPU, replicated weights, gradients of the flat
+arenas summed with NCCL all-reduce (torch.distributed) between the captured segments, the 1/world scale
+fused into the Adam kernel.  All norms are per-sample and every loss is a batch mean, so sharding the
+batch and averaging gradients equals the single-GPU large-batch step."""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+class StepRunner:
+    def __init__(self, trainer, cfg: dict, batch: int, hw: int, use_graph: bool = True, world: int = 1):
+        self.t, self.cfg, self.batch, self.hw = trainer, cfg, batch, hw
+        self.use_graph, self.world = use_graph, world
+        dev = next(trainer.parameters()).device
+        self.dev = dev
+        sd = trainer.style_dim
+        self.x_a = torch.zeros(batch, 3, hw, hw, device=dev)
+        self.x_b = torch.zeros(batch, 3, hw, hw, device=dev)
+        self.s_a = torch.zeros(batch, sd, 1, 1, device=dev)
+        self.s_b = torch.zeros(batch, sd, 1, 1, device=dev)
+        self.s_a2 = torch.zeros(batch, sd, 1, 1, device=dev)
+        self.s_b2 = torch.zeros(batch, sd, 1, 1, device=dev)
+        self.extra = "extra" in cfg["optimizer"]
+        self.graphs: Dict[int, list] = {}
+        self.launches_per_step: Optional[int] = None
+        for opt in (trainer.dis_opt, trainer.gen_opt):
+            opt.build_arena()
+            opt.enable_graph_hyper()
+            opt.grad_scale = 1.0 / world
+        self.iter = 0
+
+    # ------------------------------------------------------------------ pieces of a step
+    def _seg_dis(self):
+        for opt in (self.t.dis_opt, self.t.gen_opt):
+            opt.upload_hyper()
+        self.t._dis_backward(self.x_a, self.x_b, self.cfg, self.s_a, self.s_b)
+
+    def _seg_mid(self):
+        self.t.dis_opt_step()
+        self.t._gen_backward(self.x_a, self.x_b, self.cfg, None, None, False, self.s_a2, self.s_b2)
+
+    def _seg_end(self):
+        self.t.gen_opt_step()
+
+    def _allreduce(self, opt):
+        if self.world > 1:
+            dist.all_reduce(opt.g_arena, op=dist.ReduceOp.SUM)
+
+    def _eager_step(self):
+        self._seg_dis()
+        self._allreduce(self.t.dis_opt)
+        self._seg_mid()
+        self._allreduce(self.t.gen_opt)
+        self._seg_end()
+
+    def _py_state(self):
+        t = self.t
+        return [(o.step_count, getattr(o, "_have_copy", None)) for o in (t.dis_opt, t.gen_opt)]
+
+    def _restore_py_state(self, st):
+        for o, (c, h) in zip((self.t.dis_opt, self.t.gen_opt), st):
+            o.step_count = c
+            if h is not None:
+                o._have_copy = h
+
+    def _capture(self, parity: int):
+        """Capture the step for iterations of the given parity (ExtraAdam alternates extrapolation/step)."""
+        st = self._py_state()
+        if self.extra:  # python-side flag ExtraAdam.step() checks; device state is untouched by capture
+            for o in (self.t.dis_opt, self.t.gen_opt):
+                o._have_copy = parity == 1
+        segs = [self._seg_dis, self._seg_mid, self._seg_end] if self.world > 1 else [self._eager_step]
+        graphs = []
+        pool = None
+        before = _lib.launches
+        for fn in segs:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                fn()
+            pool = g.pool()
+            graphs.append(g)
+        self.launches_per_step = _lib.launches - before
+        self._restore_py_state(st)
+        self.graphs[parity] = graphs
+
+    # ------------------------------------------------------------------ public
+    def warmup_and_capture(self, eager_steps: int = 2):
+        """Eager steps (sets kernel attributes, builds plans/shadows, warms the allocator), then capture."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(eager_steps):
+                self._prepare_host_state()
+                before = _lib.launches
+                self._eager_step()
+                self.launches_per_step = _lib.launches - before
+                self._advance()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        if self.use_graph:
+            n_par = 2 if self.extra else 1
+            assert not self.extra or self.iter % 2 == 0
+            for par in range(n_par):
+                self.t.iterations = self.iter + par
+                self._capture(par)
+            self.t.iterations = self.iter
+            torch.cuda.synchronize()
+
+    def _prepare_host_state(self):
+        t = self.t
+        t.iterations = self.iter
+        for opt in (t.dis_opt, t.gen_opt):
+            opt.stage_hyper(opt.step_count + 1)
+
+    def _advance(self):
+        self.iter += 1
+
+    def step(self):
+        """One dis_update + gen_update on the resident inputs."""
+        self._prepare_host_state()
+        if not self.use_graph:
+            self._eager_step()
+        else:
+            graphs = self.graphs[self.iter % 2 if self.extra else 0]
+            t = self.t
+            if self.world > 1:
+                graphs[0].replay()
+                self._allreduce(t.dis_opt)
+                graphs[1].replay()
+                self._allreduce(t.gen_opt)
+                graphs[2].replay()
+            else:
+                graphs[0].replay()
+            for opt in (t.dis_opt, t.gen_opt):  # python-side bookkeeping the replay does not run
+                opt.step_count += 1
+                if self.extra:
+                    opt._have_copy = (self.iter % 2 == 0)
+        self._advance()
+
+    def load_inputs(self, x_a, x_b, s_a, s_b, s_a2, s_b2):
+        """Host (pinned) -> device copies of one step's inputs: images and the four style-code draws
+        (dis_update then gen_update, trainer.py:1146-1147,366-367)."""
+        self.x_a.copy_(x_a, non_blocking=True)
+        self.x_b.copy_(x_b, non_blocking=True)
+        self.s_a.copy_(s_a, non_blocking=True)
+        self.s_b.copy_(s_b, non_blocking=True)
+        self.s_a2.copy_(s_a2, non_blocking=True)
+        self.s_b2.copy_(s_b2, non_blocking=True)
+
+    def losses(self):
+        t = self.t
+        return dict(loss_dis_total=t.loss_dis_total, loss_gen_total=t.loss_gen_total)

@@ -326,9 +326,9 @@ def l1_bwd(a, b, gscale_dev, scale, ga, gb):
     _count()
 
 
-def adam(p, g, m, v, p_saved, p_bf16, mode, save, lr, b1, b2, eps, wd, step, gscale=1.0):
+def adam(p, g, m, v, p_saved, p_bf16, mode, save, lr, b1, b2, eps, wd, step, gscale=1.0, hyper_dev=None):
     check(lib.munit_adam(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(p_saved), _ptr(p_bf16), p.numel(),
-                         mode, int(save), lr, b1, b2, eps, wd, step, gscale, _stream()), "adam")
+                         mode, int(save), lr, b1, b2, eps, wd, step, gscale, _ptr(hyper_dev), _stream()), "adam")
     _count()
 
 

@@ -137,6 +137,9 @@ class ConvLayer:
                 wg = G.plan_wgrad(n, hp, wp, 64, kh, 1, sy, 1, self.co_rows, self.cout, kh * 64, 64, 1)
             else:
                 wg = G.plan_wgrad(n, hp, wp, c, kh, kw, sy, sx, self.co_rows, self.cout, kh * kw * c, c, 1)
+            # direct-form algorithmic work of this layer instance: 1 MAC = 2 FLOP
+            flops = 2.0 * n * ho * wo * self.cout * self.k * self.k * self.cin
+            fwd.alg_flops = dg.alg_flops = wg.alg_flops = flops
             p = (fwd, dg, wg, ho, wo)
             self._plans[key] = p
         return p

@@ -43,6 +43,9 @@ class FlatAdam(Optimizer):
         self._arena_built = False
         self.step_count = 0
         self.grad_scale = 1.0  # 1/world_size under data parallelism (fused into the update)
+        # CUDA-graph mode: {lr, 1-b1^t, 1-b2^t} live in a device array refreshed from pinned host memory
+        self.hyper_host = None
+        self.hyper_dev = None
 
     # ------------------------------------------------------------------ arena
     def _all_params(self) -> List[torch.nn.Parameter]:
@@ -95,8 +98,28 @@ class FlatAdam(Optimizer):
         if mode != 0 and self.saved_arena is None:
             self.saved_arena = torch.empty_like(self.p_arena)
         K.adam(self.p_arena, self.g_arena, self.m_arena, self.v_arena, self.saved_arena, None, mode, save, g["lr"],
-               g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self.step_count, self.grad_scale)
+               g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self.step_count, self.grad_scale,
+               self.hyper_dev)
         _bump_versions(self._all_params())
+
+    # ------------------------------------------------------------------ CUDA-graph support
+    def enable_graph_hyper(self):
+        """Route lr / bias corrections through device memory so a captured step can be replayed."""
+        if not self._arena_built:
+            self.build_arena()
+        if self.hyper_dev is None:
+            self.hyper_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+            self.hyper_dev = torch.zeros(4, dtype=torch.float32, device=self.p_arena.device)
+
+    def stage_hyper(self, step: int):
+        """Write the scalars for optimiser step `step` (1-based) into the pinned staging buffer."""
+        g = self.param_groups[0]
+        self.hyper_host[0] = g["lr"]
+        self.hyper_host[1] = 1.0 - g["betas"][0] ** step
+        self.hyper_host[2] = 1.0 - g["betas"][1] ** step
+
+    def upload_hyper(self):
+        self.hyper_dev.copy_(self.hyper_host, non_blocking=True)
 
     @torch.no_grad()
     def step(self, closure=None):

@@ -156,6 +156,16 @@ class MUNIT_Trainer(nn.Module):
     def gen_update(self, x_a, x_b, hyperparameters, mask_a=None, mask_b=None, comet_exp=None, synth=False,
                    semantic_gt_a=None, semantic_gt_b=None, s_a=None, s_b=None):
         """One generator update (trainer.py:336-561)."""
+        self._gen_backward(x_a, x_b, hyperparameters, mask_a, mask_b, synth, s_a, s_b)
+        self.gen_opt_step()
+        if comet_exp is not None and self.iterations % 100 == 0:
+            for k in ("loss_gen_adv_a", "loss_gen_adv_b", "loss_gen_recon_x_a", "loss_gen_recon_s_a",
+                      "loss_gen_recon_c_a", "loss_gen_recon_x_b", "loss_gen_recon_s_b", "loss_gen_recon_c_b",
+                      "loss_gen_cycrecon_x_a", "loss_gen_cycrecon_x_b", "loss_gen_total"):
+                comet_exp.log_metric(k, getattr(self, k).cpu().detach())
+
+    def _gen_backward(self, x_a, x_b, hyperparameters, mask_a=None, mask_b=None, synth=False, s_a=None, s_b=None):
+        """Losses + gradients of gen_update (everything up to, not including, the optimiser step)."""
         if synth:
             raise NotImplementedError("synthetic-pair losses are a 'next' item (SURVEY.md s8(f).4)")
         self.gen_opt.zero_grad()
@@ -224,16 +234,18 @@ class MUNIT_Trainer(nn.Module):
             + hyperparameters["recon_x_cyc_w"] * self.loss_gen_cycrecon_x_b
         )
         self.loss_gen_total.backward()
-        self.gen_opt_step()
         self._last = dict(x_ab=x_ab.detach(), x_ba=x_ba.detach())
-        if comet_exp is not None and self.iterations % 100 == 0:
-            for k in ("loss_gen_adv_a", "loss_gen_adv_b", "loss_gen_recon_x_a", "loss_gen_recon_s_a",
-                      "loss_gen_recon_c_a", "loss_gen_recon_x_b", "loss_gen_recon_s_b", "loss_gen_recon_c_b",
-                      "loss_gen_cycrecon_x_a", "loss_gen_cycrecon_x_b", "loss_gen_total"):
-                comet_exp.log_metric(k, getattr(self, k).cpu().detach())
 
     def dis_update(self, x_a, x_b, hyperparameters, comet_exp=None, s_a=None, s_b=None):
         """One discriminator update (trainer.py:1133-1186)."""
+        self._dis_backward(x_a, x_b, hyperparameters, s_a, s_b)
+        self.dis_opt_step()
+        if comet_exp is not None and self.iterations % 100 == 0:
+            comet_exp.log_metric("loss_dis_b", self.loss_dis_b.cpu().detach())
+            comet_exp.log_metric("loss_dis_a", self.loss_dis_a.cpu().detach())
+
+    def _dis_backward(self, x_a, x_b, hyperparameters, s_a=None, s_b=None):
+        """Losses + gradients of dis_update (everything up to, not including, the optimiser step)."""
         self.dis_opt.zero_grad()
         s_a, s_b = self._style_noise(x_a, x_b, s_a, s_b)
         with torch.no_grad():
@@ -252,10 +264,6 @@ class MUNIT_Trainer(nn.Module):
         self.loss_dis_b = self.dis_b.calc_dis_loss(x_ab.detach(), x_b)
         self.loss_dis_total = hyperparameters["gan_w"] * self.loss_dis_a + hyperparameters["gan_w"] * self.loss_dis_b
         self.loss_dis_total.backward()
-        self.dis_opt_step()
-        if comet_exp is not None and self.iterations % 100 == 0:
-            comet_exp.log_metric("loss_dis_b", self.loss_dis_b.cpu().detach())
-            comet_exp.log_metric("loss_dis_a", self.loss_dis_a.cpu().detach())
 
     # ------------------------------------------------------------------ sampling (trainer.py:773-928,1087-1131)
     def sample(self, x_a, x_b):

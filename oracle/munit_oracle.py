@@ -23,6 +23,36 @@ SD = Dict[str, torch.Tensor]
 
 EPS_NORM = 1e-5
 
+# ---------------------------------------------------------------------------------------------
+# Optional "storage-aware" mode (tests only): QUANT = True makes the oracle round, with straight-through
+# gradients, at exactly the points where the B200 path stores bf16 (conv weights, conv outputs before a
+# norm, block outputs, images entering a first layer, gradients flowing through those points).  It
+# separates kernel errors from the ReLU-mask flips that bf16 storage itself causes; the golden fixtures
+# pin the default fp32 mode (QUANT = False), which is the reference's arithmetic.
+# ---------------------------------------------------------------------------------------------
+QUANT = False
+
+
+class _RoundSTE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, round_grad):
+        ctx.round_grad = round_grad
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g.to(torch.bfloat16).to(g.dtype) if ctx.round_grad else g), None
+
+
+def _q(t):
+    """bf16 storage point of an activation (value and incoming gradient rounded)."""
+    return _RoundSTE.apply(t, True) if QUANT else t
+
+
+def _qw(t):
+    """bf16 GEMM operand made from fp32 master data (gradient passes through unrounded)."""
+    return _RoundSTE.apply(t, False) if QUANT else t
+
 
 # --------------------------------------------------------------------------
 # default hyper-parameters (configs/config_256.yaml "core": semantic_w=0,
@@ -226,9 +256,17 @@ def activation(x, kind):
     raise ValueError(kind)
 
 
-def conv_block(sd: SD, p: str, x, stride, pad, norm="none", act="relu", adain=None):
-    """Conv2dBlock.forward networks.py:695-701: pad -> conv(bias) -> norm -> activation."""
-    y = F.conv2d(reflect_pad(x, pad), sd[p + "conv.weight"], sd[p + "conv.bias"], stride=stride)
+def conv_block(sd: SD, p: str, x, stride, pad, norm="none", act="relu", adain=None, residual=None, image=False):
+    """Conv2dBlock.forward networks.py:695-701: pad -> conv(bias) -> norm -> activation
+    (+ the ResBlock residual add of networks.py:623 when `residual` is given)."""
+    if image:
+        x = _qw(x)
+    bias = sd[p + "conv.bias"]
+    if QUANT and norm in ("in", "adain"):
+        bias = None  # cancelled exactly by the mean subtraction; the B200 path skips it
+    y = F.conv2d(reflect_pad(x, pad), _qw(sd[p + "conv.weight"]), bias, stride=stride)
+    if norm != "none":
+        y = _q(y)
     if norm == "in":
         y = instance_norm(y)
     elif norm == "adain":
@@ -237,12 +275,15 @@ def conv_block(sd: SD, p: str, x, stride, pad, norm="none", act="relu", adain=No
         y = layer_norm_munit(y, sd[p + "norm.gamma"], sd[p + "norm.beta"])
     elif norm != "none":
         raise ValueError(norm)
-    return activation(y, act)
+    y = activation(y, act)
+    if residual is not None:
+        y = y + residual
+    return _q(y)
 
 
 def style_encoder(sd: SD, p: str, x, activ="relu", n_downsample=4):
     """StyleEncoder networks.py:442-477: 7x7 -> 4x4s2 x2 (doubling) -> 4x4s2 x(n-2) -> GAP -> 1x1."""
-    y = conv_block(sd, f"{p}model.0.", x, 1, 3, "none", activ)
+    y = conv_block(sd, f"{p}model.0.", x, 1, 3, "none", activ, image=True)
     for i in range(1, n_downsample + 1):
         y = conv_block(sd, f"{p}model.{i}.", y, 2, 1, "none", activ)
     y = y.mean(dim=(2, 3), keepdim=True)
@@ -256,14 +297,13 @@ def res_blocks(sd: SD, p: str, x, n_res, norm, activ, adain_list=None):
         a0 = adain_list[2 * r] if adain_list is not None else None
         a1 = adain_list[2 * r + 1] if adain_list is not None else None
         y = conv_block(sd, f"{p}model.{r}.model.0.", x, 1, 1, norm, activ, a0)
-        y = conv_block(sd, f"{p}model.{r}.model.1.", y, 1, 1, norm, "none", a1)
-        x = y + x
+        x = conv_block(sd, f"{p}model.{r}.model.1.", y, 1, 1, norm, "none", a1, residual=x)
     return x
 
 
 def content_encoder(sd: SD, p: str, x, n_down=2, n_res=4, activ="relu"):
     """ContentEncoder networks.py:480-512."""
-    y = conv_block(sd, f"{p}model.0.", x, 1, 3, "in", activ)
+    y = conv_block(sd, f"{p}model.0.", x, 1, 3, "in", activ, image=True)
     for i in range(1, n_down + 1):
         y = conv_block(sd, f"{p}model.{i}.", y, 2, 1, "in", activ)
     return res_blocks(sd, f"{p}model.{n_down+1}.", y, n_res, "in", activ)
@@ -341,7 +381,7 @@ def dis_forward(sd: SD, dp: dict, x) -> List[torch.Tensor]:
     """MsImageDis.forward networks.py:72-77."""
     outs = []
     for s in range(dp["num_scales"]):
-        y = conv_block(sd, f"cnns.{s}.0.", x, 2, 1, "none", dp["activ"])
+        y = conv_block(sd, f"cnns.{s}.0.", x, 2, 1, "none", dp["activ"], image=True)
         for i in range(1, dp["n_layer"]):
             y = conv_block(sd, f"cnns.{s}.{i}.", y, 2, 1, "none", dp["activ"])
         k = dp["n_layer"]

