@@ -35,6 +35,10 @@ class StepRunner:
             opt.enable_graph_hyper()
             opt.grad_scale = 1.0 / world
         self.iter = 0
+        # Warm-up and capture share ONE side stream: autograd grad-accumulator nodes remember the stream
+        # they were created on, and a node surviving from warm-up on another stream would make the
+        # engine's end-of-backward stream sync reach outside the capture (cudaErrorStreamCaptureIsolation).
+        self.stream = torch.cuda.Stream()
 
     # ------------------------------------------------------------------ pieces of a step
     def _seg_dis(self):
@@ -82,7 +86,7 @@ class StepRunner:
         before = _lib.launches
         for fn in segs:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool):
+            with torch.cuda.graph(g, pool=pool, stream=self.stream):
                 fn()
             pool = g.pool()
             graphs.append(g)
@@ -93,7 +97,7 @@ class StepRunner:
     # ------------------------------------------------------------------ public
     def warmup_and_capture(self, eager_steps: int = 2):
         """Eager steps (sets kernel attributes, builds plans/shadows, warms the allocator), then capture."""
-        s = torch.cuda.Stream()
+        s = self.stream
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(eager_steps):

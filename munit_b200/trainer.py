@@ -235,6 +235,7 @@ class MUNIT_Trainer(nn.Module):
         )
         self.loss_gen_total.backward()
         self._last = dict(x_ab=x_ab.detach(), x_ba=x_ba.detach())
+        self._release_graph()
 
     def dis_update(self, x_a, x_b, hyperparameters, comet_exp=None, s_a=None, s_b=None):
         """One discriminator update (trainer.py:1133-1186)."""
@@ -264,6 +265,17 @@ class MUNIT_Trainer(nn.Module):
         self.loss_dis_b = self.dis_b.calc_dis_loss(x_ab.detach(), x_b)
         self.loss_dis_total = hyperparameters["gan_w"] * self.loss_dis_a + hyperparameters["gan_w"] * self.loss_dis_b
         self.loss_dis_total.backward()
+        self._release_graph()
+
+    def _release_graph(self):
+        """Drop references into the autograd graph of the finished update: the stored loss_* become
+        detached 0-dim tensors and the AdaIN layers forget their (graph-attached) parameter views."""
+        for k, v in list(self.__dict__.items()):
+            if k.startswith("loss_") and torch.is_tensor(v) and v.grad_fn is not None:
+                setattr(self, k, v.detach())
+        for m in self.modules():
+            if m.__class__.__name__ == "AdaptiveInstanceNorm2d" and m._w is not None:
+                m._w, m._b = m._w.detach(), m._b.detach()
 
     # ------------------------------------------------------------------ sampling (trainer.py:773-928,1087-1131)
     def sample(self, x_a, x_b):
