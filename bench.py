@@ -169,7 +169,7 @@ def profile_tensor_kernels(runner):
             e0.record()
             out = fn(plan, *a, **k)
             e1.record()
-            rec[name].append((e0, e1, getattr(plan, "alg_flops", 0.0)))
+            rec[name].append((e0, e1, getattr(plan, "alg_flops", 0.0), plan))
             return out
         return inner
 
@@ -182,10 +182,21 @@ def profile_tensor_kernels(runner):
     finally:
         K.tapgemm, K.wgrad = orig_t, orig_w
     out = {}
+    detail = []
     for name, lst in rec.items():
-        ms = sum(a.elapsed_time(b) for a, b, _ in lst)
-        fl = sum(f for _, _, f in lst)
+        ms = sum(a.elapsed_time(b) for a, b, _, _ in lst)
+        fl = sum(f for _, _, f, _ in lst)
         out[name] = dict(launches=len(lst), ms=ms, flops=fl)
+        for a, b, f, plan in lst:
+            d = dict(kind=name, ms=a.elapsed_time(b), alg_gflop=f / 1e9, n=plan.n_img, oh=plan.out_h, ow=plan.out_w,
+                     taps=plan.num_taps, bn=plan.bn)
+            if name == "tapgemm":
+                d.update(rows=plan.b_rows, chunks=plan.chunks, phases=plan.phases, tile=(plan.tw, plan.th, plan.tn),
+                         exec_gflop=plan.flops() / 1e9)
+            else:
+                d.update(m=plan.m_total, ncols=plan.n_total)
+            detail.append(d)
+    out["detail"] = detail
     return out
 
 
@@ -264,6 +275,8 @@ def run_b200(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(tt[0]), float(tt[1])
     prof = profile_tensor_kernels(runner)
+    if rank == 0 and args.dump_launches:
+        json.dump(prof["detail"], open(args.dump_launches, "w"))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -317,6 +330,7 @@ def main():
     ap.add_argument("--optimizer", default="")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-launches", default="", help="write per-launch tensor-kernel timings (profile pass) to this json")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -47,7 +47,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -226,7 +226,7 @@ struct WgParams {
 constexpr int kBoxBytes = 64 * 128;  // 64 pixels x 64 channels bf16
 
 template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
              const __grid_constant__ WgParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -411,7 +411,9 @@ int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, FwdParams& p, dim3 
   const int stage_bytes = kABytes + BN * 128;
   int stages = p.stages;
   if (stages <= 0) {
-    stages = (200 * 1024) / stage_bytes;
+    // Two CTAs per SM (<= ~113 KB each): a co-resident CTA hides the other's prologue, TMA latency and
+    // epilogue -- measured on B200 to beat a deeper single-CTA pipeline (profiles/r1_stages.md).
+    stages = (112 * 1024) / stage_bytes;
     if (stages > 6) stages = 6;
   }
   if (stages > kMaxStages) stages = kMaxStages;
@@ -435,7 +437,9 @@ int launch_wg(const CUtensorMap& ta, const CUtensorMap& tb, WgParams& p, dim3 gr
   const int stage_bytes = (2 + BN / 64) * kBoxBytes;
   int stages = p.stages;
   if (stages <= 0) {
-    stages = (200 * 1024) / stage_bytes;
+    // Two CTAs per SM (<= ~113 KB each): a co-resident CTA hides the other's prologue, TMA latency and
+    // epilogue -- measured on B200 to beat a deeper single-CTA pipeline (profiles/r1_stages.md).
+    stages = (112 * 1024) / stage_bytes;
     if (stages > 6) stages = 6;
   }
   if (stages > kMaxStages) stages = kMaxStages;
