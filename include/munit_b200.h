@@ -137,8 +137,11 @@ int munit_nchw_to_act(const float* x, void* act, int n, int c, int h, int w, int
 /* In-place reflect halo fill of an act buffer from its interior. */
 int munit_halo_fill(void* act, int n, int h, int w, int c, int pad, void* stream);
 
-/* Per-(n,c) shifted sums over H*W of y [N][H][W][C] bf16 (row stride in elements ldp = C):
- * stats[(n*C+c)*2 + {0,1}] = {sum(x - s), sum((x - s)^2)}, shift[n*C+c] = s = y[n,0,0,c].
+/* Number of pixel splits S the per-(n,c) reductions use for (hw, c); workspaces `stats` / `sums` below hold
+ * N*S*C*2 floats.  Partials are added in a fixed order by the finalize calls (bit-reproducible). */
+int munit_norm_splits(int hw, int c);
+/* Per-(n,c) shifted sums over H*W of y [N][H][W][C] bf16:
+ * stats[((n*S+s)*C+c)*2 + {0,1}] = split-s partial of {sum(x - sh), sum((x - sh)^2)}, shift[n*C+c] = sh = y[n,0,0,c].
  * (first half of nn.InstanceNorm2d networks.py:657 / F.batch_norm networks.py:834 / LayerNorm :865-871) */
 int munit_norm_stats(const void* y, float* stats, float* shift, int n, int hw, int c, void* stream);
 
@@ -175,6 +178,16 @@ int munit_act_bwd(const void* g_out, const void* out_act, int pad, int act, void
                   void* stream);
 /* dbias[c] += sum over pixels of dy [npix][C] bf16, for c < c_out (<= C). */
 int munit_colsum(const void* dy, float* dbias, int64_t npix, int c, int c_out, void* stream);
+
+/* Narrow-output convolutions (Cout <= 4: the 64->3 7x7 tanh layer, networks.py:548-559).  The tap-GEMM
+ * computes the vertical part R[n][y][xp][kw*4+co] = sum_{kh,ci} Xpad[n][y+kh][xp][ci] W[co][kh][kw][ci]
+ * (7 taps, N = 32); combine does out[n][co][y][x] = act(bias[co] + sum_kw R[n][y][x+kw][kw*4+co]) and writes
+ * the public NCHW fp32 image; expand is its adjoint: dR from g = dL/dout (act' applied from `out`),
+ * dbias[co] += sum g*act'. */
+int munit_rspace_combine(const void* r, const float* bias, float* out, int n, int cout, int h, int w, int kw, int act,
+                         void* stream);
+int munit_rspace_expand(const float* g, const float* out, void* dr, float* dbias, int n, int cout, int h, int w, int kw,
+                        int act, void* stream);
 
 /* Weights: fp32 master (OIHW shape stored channels_last = [Cout][KH][KW][Cin]) -> bf16 GEMM shadows.
  * dst[i] = idx[i] >= 0 ? bf16(src[idx[i]]) : 0 -- the index map (built once per layer on the host) encodes

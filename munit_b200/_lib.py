@@ -70,6 +70,7 @@ _SIGS = {
     "munit_act_to_nchw": ([_vp, _vp, _i, _i, _i, _i, _i, _i, _vp], C.c_int),
     "munit_nchw_to_act": ([_vp, _vp, _i, _i, _i, _i, _i, _i, _vp], C.c_int),
     "munit_halo_fill": ([_vp, _i, _i, _i, _i, _i, _vp], C.c_int),
+    "munit_norm_splits": ([_i, _i], C.c_int),
     "munit_norm_stats": ([_vp, _vp, _vp, _i, _i, _i, _vp], C.c_int),
     "munit_norm_finalize": ([_vp, _vp, _i, _vp, _vp, _i64, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp], C.c_int),
     "munit_norm_apply": ([_vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp], C.c_int),
@@ -78,6 +79,8 @@ _SIGS = {
     "munit_norm_bwd_apply": ([_vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], C.c_int),
     "munit_act_bwd": ([_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp], C.c_int),
     "munit_colsum": ([_vp, _vp, _i64, _i, _i, _vp], C.c_int),
+    "munit_rspace_combine": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], C.c_int),
+    "munit_rspace_expand": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], C.c_int),
     "munit_gather_cast": ([_vp, _vp, _vp, _i64, _vp], C.c_int),
     "munit_gather_add": ([_vp, _vp, _vp, _i64, _vp], C.c_int),
     "munit_cast_bf16": ([_vp, _vp, _i64, _vp], C.c_int),

@@ -193,7 +193,9 @@ __global__ void halo_fill_kernel(bf16* __restrict__ act, int n, int h, int w, in
 
 // ------------------------------------------------------------------ per-(n,c) reductions
 // Block = CG column groups x R rows (CG*R = 256); grid = (splits, N).  `Fn(n, pix, cg)` returns the
-// two 8-channel vectors to accumulate.  Partial sums are combined in smem, then atomically added.
+// two 8-channel vectors to accumulate.  Partial sums are combined in smem and written to
+// part[((n*splits + split)*C + c)*2 + {0,1}]; the finalize kernels add the splits in a fixed order, so
+// the statistics (and with them the whole forward pass) are bit-reproducible run to run.
 template <typename Fn>
 __device__ __forceinline__ void reduce_nc(Fn fn, float* __restrict__ out2, int hw, int c) {
   extern __shared__ float red[];  // [R][C][2]
@@ -231,8 +233,19 @@ __device__ __forceinline__ void reduce_nc(Fn fn, float* __restrict__ out2, int h
       a += red[((rr * c) + ch) * 2 + 0];
       b += red[((rr * c) + ch) * 2 + 1];
     }
-    atomicAdd(out2 + ((long long)n * c + ch) * 2 + 0, a);
-    atomicAdd(out2 + ((long long)n * c + ch) * 2 + 1, b);
+    float* dst = out2 + (((long long)n * gridDim.x + blockIdx.x) * c + ch) * 2;
+    dst[0] = a;
+    dst[1] = b;
+  }
+}
+__device__ __forceinline__ void sum_splits(const float* __restrict__ part, int n, int splits, int c, int ch, double& s1,
+                                           double& s2) {
+  s1 = 0.0;
+  s2 = 0.0;
+  for (int s = 0; s < splits; ++s) {
+    const float* p = part + (((long long)n * splits + s) * c + ch) * 2;
+    s1 += (double)p[0];
+    s2 += (double)p[1];
   }
 }
 
@@ -285,7 +298,7 @@ __global__ void colsum_kernel(const bf16* __restrict__ dy, float* __restrict__ o
 }
 
 // one block per sample
-__global__ void norm_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ shift, int mode,
+__global__ void norm_finalize_kernel(const float* __restrict__ stats, int splits, const float* __restrict__ shift, int mode,
                                      const float* __restrict__ p_w, const float* __restrict__ p_b, long long ldw,
                                      float eps, float* __restrict__ mean, float* __restrict__ rinv,
                                      float* __restrict__ a, float* __restrict__ b, int hw, int c) {
@@ -296,8 +309,11 @@ __global__ void norm_finalize_kernel(const float* __restrict__ stats, const floa
   if (mode == MUNIT_NORM_LN) {
     // sample mean
     double s = 0.0;
-    for (int ch = threadIdx.x; ch < c; ch += blockDim.x)
-      s += cnt * (double)shift[(long long)n * c + ch] + (double)stats[((long long)n * c + ch) * 2];
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+      double a1, a2;
+      sum_splits(stats, n, splits, c, ch, a1, a2);
+      s += cnt * (double)shift[(long long)n * c + ch] + a1;
+    }
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0) sh[0][threadIdx.x >> 5] = s;
     __syncthreads();
@@ -311,7 +327,8 @@ __global__ void norm_finalize_kernel(const float* __restrict__ stats, const floa
     double ss = 0.0;
     for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
       const double d = mu - (double)shift[(long long)n * c + ch];
-      const double s1 = stats[((long long)n * c + ch) * 2], s2 = stats[((long long)n * c + ch) * 2 + 1];
+      double s1, s2;
+      sum_splits(stats, n, splits, c, ch, s1, s2);
       ss += s2 - 2.0 * d * s1 + cnt * d * d;
     }
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
@@ -336,8 +353,10 @@ __global__ void norm_finalize_kernel(const float* __restrict__ stats, const floa
   } else {
     for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
       const long long i = (long long)n * c + ch;
-      const double m1 = (double)stats[i * 2] / cnt;
-      double var = (double)stats[i * 2 + 1] / cnt - m1 * m1;  // biased (F.batch_norm / InstanceNorm2d)
+      double a1, a2;
+      sum_splits(stats, n, splits, c, ch, a1, a2);
+      const double m1 = a1 / cnt;
+      double var = a2 / cnt - m1 * m1;  // biased (F.batch_norm / InstanceNorm2d)
       if (var < 0.0) var = 0.0;
       const float mu = (float)((double)shift[i] + m1);
       const float ri = (float)(1.0 / sqrt(var + (double)eps));
@@ -456,7 +475,7 @@ __global__ void norm_bwd_reduce_kernel(const bf16* __restrict__ g_out, int out_p
 }
 
 // one block per sample
-__global__ void norm_bwd_finalize_kernel(const float* __restrict__ sums, int mode, const float* __restrict__ p_w,
+__global__ void norm_bwd_finalize_kernel(const float* __restrict__ sums, int splits, int mode, const float* __restrict__ p_w,
                                          long long ldw, const float* __restrict__ rinv, float eps,
                                          float* __restrict__ ca, float* __restrict__ cb, float* __restrict__ cc,
                                          float* __restrict__ g_w, float* __restrict__ g_b, long long ldg, int hw,
@@ -468,11 +487,12 @@ __global__ void norm_bwd_finalize_kernel(const float* __restrict__ sums, int mod
     __shared__ double tot[2];
     double g1 = 0.0, g2 = 0.0;
     for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-      const long long i = (long long)n * c + ch;
-      g1 += (double)p_w[ch] * sums[i * 2];
-      g2 += (double)p_w[ch] * sums[i * 2 + 1];
-      if (g_w) atomicAdd(g_w + ch, sums[i * 2 + 1]);
-      if (g_b) atomicAdd(g_b + ch, sums[i * 2]);
+      double s1, s2;
+      sum_splits(sums, n, splits, c, ch, s1, s2);
+      g1 += (double)p_w[ch] * s1;
+      g2 += (double)p_w[ch] * s2;
+      if (g_w) atomicAdd(g_w + ch, (float)s2);
+      if (g_b) atomicAdd(g_b + ch, (float)s1);
     }
     for (int o = 16; o > 0; o >>= 1) {
       g1 += __shfl_xor_sync(0xffffffffu, g1, o);
@@ -509,12 +529,14 @@ __global__ void norm_bwd_finalize_kernel(const float* __restrict__ sums, int mod
       const long long i = (long long)n * c + ch;
       const float wv = (mode == MUNIT_NORM_ADAIN) ? p_w[(long long)n * ldw + ch] : 1.f;
       const float A = rinv[i] * wv;
+      double s1, s2;
+      sum_splits(sums, n, splits, c, ch, s1, s2);
       ca[i] = A;
-      cc[i] = (float)(-(double)A * sums[i * 2] / cnt);
-      cb[i] = (float)(-(double)A * sums[i * 2 + 1] / cnt);
+      cc[i] = (float)(-(double)A * s1 / cnt);
+      cb[i] = (float)(-(double)A * s2 / cnt);
       if (mode == MUNIT_NORM_ADAIN) {
-        if (g_w) g_w[(long long)n * ldg + ch] = sums[i * 2 + 1];
-        if (g_b) g_b[(long long)n * ldg + ch] = sums[i * 2];
+        if (g_w) g_w[(long long)n * ldg + ch] = (float)s2;
+        if (g_b) g_b[(long long)n * ldg + ch] = (float)s1;
       }
     }
   }
@@ -575,6 +597,92 @@ __global__ void act_bwd_kernel(const bf16* __restrict__ g_out, const bf16* __res
       }
     }
     store8(dy + i * 8, gr);
+  }
+}
+
+
+// ------------------------------------------------------------------ narrow-output convs (Cout <= 4, e.g. 64->3 7x7)
+// The GEMM produces R[n][y][xp][kw*4+co] = sum_{kh,ci} Xpad[n][y+kh][xp][ci] * W[co][kh][kw][ci] (N = 32 instead
+// of 49 taps of N = 16); these kernels do the cheap horizontal part:
+//   out[n][co][y][x] = act(bias[co] + sum_kw R[n][y][x+kw][kw*4+co])           (NCHW fp32, the public format)
+__global__ void rspace_combine_kernel(const bf16* __restrict__ r, const float* __restrict__ bias,
+                                      float* __restrict__ out, int n, int cout, int h, int w, int kw, int act) {
+  const int wp = w + kw - 1;
+  const long long total = (long long)n * h * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w);
+    const int y = (int)((i / w) % h);
+    const int b = (int)(i / ((long long)w * h));
+    float acc[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[c] = (bias && c < cout) ? bias[c] : 0.f;
+    const bf16* row = r + (((long long)b * h + y) * wp + x) * 32;
+    for (int k = 0; k < kw; ++k) {
+      const uint2 u = *reinterpret_cast<const uint2*>(row + (long long)k * 32 + k * 4);
+      const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+      const float2 a = __bfloat1622float2(hh[0]), c2 = __bfloat1622float2(hh[1]);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += c2.x; acc[3] += c2.y;
+    }
+    for (int c = 0; c < cout; ++c) {
+      float v = acc[c];
+      if (act == MUNIT_ACT_TANH) v = tanhf(v);
+      else if (act == MUNIT_ACT_RELU) v = fmaxf(v, 0.f);
+      else if (act == MUNIT_ACT_LRELU) v = v > 0.f ? v : 0.2f * v;
+      out[(((long long)b * cout + c) * h + y) * w + x] = v;
+    }
+  }
+}
+// Backward: dpre = g * act'(out); dR[n][y][xp][kw*4+co] = dpre[n][co][y][xp-kw] (0 where out of range);
+// dbias[co] += sum dpre.
+__global__ void rspace_expand_kernel(const float* __restrict__ g, const float* __restrict__ out,
+                                     bf16* __restrict__ dr, float* __restrict__ dbias, int n, int cout, int h, int w,
+                                     int kw, int act) {
+  const int wp = w + kw - 1;
+  const long long total = (long long)n * h * wp;
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int xp = (int)(i % wp);
+    const int y = (int)((i / wp) % h);
+    const int b = (int)(i / ((long long)wp * h));
+    uint32_t packed[16];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
+      const int x = xp - k;
+      if (k < kw && x >= 0 && x < w) {
+        for (int c = 0; c < cout; ++c) {
+          const long long o = (((long long)b * cout + c) * h + y) * w + x;
+          float gv = g[o];
+          const float ov = out[o];
+          if (act == MUNIT_ACT_TANH) gv *= (1.f - ov * ov);
+          else if (act == MUNIT_ACT_RELU) gv = ov > 0.f ? gv : 0.f;
+          else if (act == MUNIT_ACT_LRELU) gv = ov > 0.f ? gv : 0.2f * gv;
+          d[c] = gv;
+          if (k == 0) bsum[c] += gv;
+        }
+      }
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(d[0], d[1]), p1 = __floats2bfloat162_rn(d[2], d[3]);
+      packed[2 * k] = *reinterpret_cast<uint32_t*>(&p0);
+      packed[2 * k + 1] = *reinterpret_cast<uint32_t*>(&p1);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(dr + i * 32);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+  }
+  if (dbias) {
+    __shared__ float sh[4][32];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float v = bsum[c];
+      for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+      if ((threadIdx.x & 31) == 0) sh[c][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < cout) {
+      float tsum = 0.f;
+      for (int i = 0; i < (blockDim.x >> 5); ++i) tsum += sh[threadIdx.x][i];
+      atomicAdd(dbias + threadIdx.x, tsum);
+    }
   }
 }
 
@@ -946,9 +1054,13 @@ int munit_halo_fill(void* act, int n, int h, int w, int c, int pad, void* stream
   return MUNIT_OK;
 }
 
+int munit_norm_splits(int hw, int c) {
+  if (c % 8 || c / 8 > 256 || 256 % (c / 8)) return -1;
+  return reduce_splits(hw, c);
+}
+
 int munit_norm_stats(const void* y, float* stats, float* shift, int n, int hw, int c, void* stream) {
   if (c % 8 || c / 8 > 256 || 256 % (c / 8)) return mb_fail(MUNIT_ERR_ARG, "norm_stats: channels %d", c);
-  cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)n * c, ST(stream));
   const int rows = 256 / (c / 8);
   dim3 grid(reduce_splits(hw, c), n);
   norm_stats_kernel<<<grid, 256, sizeof(float) * 2 * rows * c, ST(stream)>>>(CBF(y), stats, shift, hw, c);
@@ -960,7 +1072,8 @@ int munit_norm_finalize(const float* stats, const float* shift, int mode, const 
                         int64_t ldw, float eps, float* mean, float* rinv, float* a, float* b, int n, int hw, int c,
                         void* stream) {
   if (mode != MUNIT_NORM_IN && (!p_w || !p_b)) return mb_fail(MUNIT_ERR_ARG, "norm_finalize: missing affine params");
-  norm_finalize_kernel<<<n, 256, 0, ST(stream)>>>(stats, shift, mode, p_w, p_b, ldw, eps, mean, rinv, a, b, hw, c);
+  norm_finalize_kernel<<<n, 256, 0, ST(stream)>>>(stats, reduce_splits(hw, c), shift, mode, p_w, p_b, ldw, eps, mean,
+                                                  rinv, a, b, hw, c);
   MB_CHECK_LAUNCH("norm_finalize");
   return MUNIT_OK;
 }
@@ -985,7 +1098,6 @@ int munit_norm_bwd_reduce(const void* g_out, int out_pad, int upsample, const vo
                           int relu, const float* mean, const float* rinv, float* sums, int n, int h, int w, int c,
                           void* stream) {
   if (c % 8 || c / 8 > 256 || 256 % (c / 8)) return mb_fail(MUNIT_ERR_ARG, "norm_bwd_reduce: channels %d", c);
-  cudaMemsetAsync(sums, 0, sizeof(float) * 2 * (size_t)n * c, ST(stream));
   const int rows = 256 / (c / 8);
   dim3 grid(reduce_splits(h * w, c), n);
   const size_t sm = sizeof(float) * 2 * rows * c;
@@ -1002,8 +1114,8 @@ int munit_norm_bwd_reduce(const void* g_out, int out_pad, int upsample, const vo
 int munit_norm_bwd_finalize(const float* sums, int mode, const float* p_w, int64_t ldw, const float* rinv, float eps,
                             float* ca, float* cb, float* cc, float* g_w, float* g_b, int64_t ldg, int n, int hw, int c,
                             void* stream) {
-  norm_bwd_finalize_kernel<<<n, 256, 0, ST(stream)>>>(sums, mode, p_w, ldw, rinv, eps, ca, cb, cc, g_w, g_b, ldg, hw,
-                                                      c);
+  norm_bwd_finalize_kernel<<<n, 256, 0, ST(stream)>>>(sums, reduce_splits(hw, c), mode, p_w, ldw, rinv, eps, ca, cb, cc,
+                                                      g_w, g_b, ldg, hw, c);
   MB_CHECK_LAUNCH("norm_bwd_finalize");
   return MUNIT_OK;
 }
@@ -1042,6 +1154,22 @@ int munit_colsum(const void* dy, float* dbias, int64_t npix, int c, int c_out, v
   if (splits < 1) splits = 1;
   colsum_kernel<<<(int)splits, 256, sizeof(float) * rows * c, ST(stream)>>>(CBF(dy), dbias, npix, c, c_out < c ? c_out : c);
   MB_CHECK_LAUNCH("colsum");
+  return MUNIT_OK;
+}
+
+int munit_rspace_combine(const void* r, const float* bias, float* out, int n, int cout, int h, int w, int kw, int act,
+                         void* stream) {
+  if (cout > 4 || kw > 8) return mb_fail(MUNIT_ERR_ARG, "rspace_combine: cout <= 4 and kw <= 8 required");
+  rspace_combine_kernel<<<grid_for((long long)n * h * w), 256, 0, ST(stream)>>>(CBF(r), bias, out, n, cout, h, w, kw, act);
+  MB_CHECK_LAUNCH("rspace_combine");
+  return MUNIT_OK;
+}
+int munit_rspace_expand(const float* g, const float* out, void* dr, float* dbias, int n, int cout, int h, int w, int kw,
+                        int act, void* stream) {
+  if (cout > 4 || kw > 8) return mb_fail(MUNIT_ERR_ARG, "rspace_expand: cout <= 4 and kw <= 8 required");
+  rspace_expand_kernel<<<grid_for((long long)n * h * (w + kw - 1), 256, 148 * 8), 256, 0, ST(stream)>>>(
+      g, out, BF(dr), dbias, n, cout, h, w, kw, act);
+  MB_CHECK_LAUNCH("rspace_expand");
   return MUNIT_OK;
 }
 

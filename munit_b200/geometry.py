@@ -266,3 +266,25 @@ def dgrad_index_map(cout, cin, kh, kw, sy, sx, c_rows, ck, kw_p=None, c_p=None):
                 idx[:kw, :cin, py, a, 0, :cout] = src[:, sy * a + py, :, :].permute(1, 2, 0)
         idx = idx.view(kw_p * c_p, sy, na, 1, ck)
     return idx.reshape(-1)
+
+
+def rspace_index_maps(cout, cin, kh, kw, kwp=8, cop=4, ck=64):
+    """Narrow-output layers (cout <= cop): weight matrices of the vertical (kh x 1) GEMM whose N index is
+    (kw, co) = kw*cop + co.  Returns (fwd, dgrad, inv):
+      fwd   [(kwp*cop)][kh][cin]          <- w[co][kh][kw][ci]
+      dgrad [cin][kh][ck]  (K = (kw,co))  <- w[co][kh][kw][ci]
+      inv   [cout*kh*kw*cin]              position of each parameter element inside `fwd` (wgrad scatter-back)."""
+    import torch
+
+    src = torch.arange(cout * kh * kw * cin, dtype=torch.int32).view(cout, kh, kw, cin)
+    rows = kwp * cop
+    fwd = torch.full((kwp, cop, kh, cin), -1, dtype=torch.int32)
+    fwd[:kw, :cout] = src.permute(2, 0, 1, 3)
+    dg = torch.full((cin, kh, ck), -1, dtype=torch.int32)
+    dgv = dg[:, :, :rows].view(cin, kh, kwp, cop)
+    dgv[:, :, :kw, :cout] = src.permute(3, 1, 2, 0)
+    fwd = fwd.reshape(-1)
+    inv = torch.full((cout * kh * kw * cin,), -1, dtype=torch.int32)
+    m = fwd >= 0
+    inv[fwd[m].long()] = torch.arange(fwd.numel(), dtype=torch.int32)[m]
+    return fwd, dg.reshape(-1), inv

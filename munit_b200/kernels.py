@@ -153,10 +153,12 @@ def halo_fill(act, pad):
 # ---------------------------------------------------------------- norms
 def norm_stats(y):
     n, h, w, c = y.shape
-    stats = torch.empty(n, c, 2, dtype=torch.float32, device=y.device)
+    splits = lib.munit_norm_splits(h * w, c)
+    assert splits > 0, f"unsupported channel count {c}"
+    stats = torch.empty(n, splits, c, 2, dtype=torch.float32, device=y.device)
     shift = torch.empty(n, c, dtype=torch.float32, device=y.device)
     check(lib.munit_norm_stats(y.data_ptr(), stats.data_ptr(), shift.data_ptr(), n, h * w, c, _stream()), "norm_stats")
-    _count(2)
+    _count()
     return stats, shift
 
 
@@ -184,7 +186,7 @@ def norm_bwd(g_out, out_pad, upsample, y, coef, relu, mode, p_w, ldw, g_w, g_b, 
     """Returns (dy, g_res).  coef = (mean, rinv, a, b) from norm_finalize."""
     n, h, w, c = y.shape
     mean, rinv, a, b = coef[0], coef[1], coef[2], coef[3]
-    sums = torch.empty(n, c, 2, dtype=torch.float32, device=y.device)
+    sums = torch.empty(n, lib.munit_norm_splits(h * w, c), c, 2, dtype=torch.float32, device=y.device)
     check(lib.munit_norm_bwd_reduce(g_out.data_ptr(), out_pad, upsample, y.data_ptr(), a.data_ptr(), b.data_ptr(),
                                     int(relu), mean.data_ptr(), rinv.data_ptr(), sums.data_ptr(), n, h, w, c,
                                     _stream()), "norm_bwd_reduce")
@@ -200,7 +202,7 @@ def norm_bwd(g_out, out_pad, upsample, y, coef, relu, mode, p_w, ldw, g_w, g_b, 
                                    int(relu), mean.data_ptr(), rinv.data_ptr(), k[0].data_ptr(), k[1].data_ptr(),
                                    k[2].data_ptr(), dy.data_ptr(), _ptr(g_res), res_pad, n, h, w, c, _stream()),
           "norm_bwd_apply")
-    _count(4)
+    _count(3)
     return dy, g_res
 
 
@@ -220,6 +222,26 @@ def colsum(dy, out, c_out=None):
                            _stream()), "colsum")
     _count()
     return out
+
+
+def rspace_combine(r, bias, cout, kw, act):
+    n, h, wp, c = r.shape
+    assert c == 32
+    w = wp - kw + 1
+    out = torch.empty(n, cout, h, w, dtype=torch.float32, device=r.device)
+    check(lib.munit_rspace_combine(r.data_ptr(), _ptr(bias), out.data_ptr(), n, cout, h, w, kw, ACT[act], _stream()),
+          "rspace_combine")
+    _count()
+    return out
+
+
+def rspace_expand(g, out, kw, act, dbias):
+    n, cout, h, w = out.shape
+    dr = torch.empty(n, h, w + kw - 1, 32, dtype=torch.bfloat16, device=out.device)
+    check(lib.munit_rspace_expand(g.data_ptr(), out.data_ptr(), dr.data_ptr(), _ptr(dbias), n, cout, h, w, kw, ACT[act],
+                                  _stream()), "rspace_expand")
+    _count()
+    return dr
 
 
 # ---------------------------------------------------------------- weights

@@ -168,6 +168,10 @@ class Conv2dBlock(nn.Module):
             xin = ops.ToActFn.apply(x, self.padding)
         w = self.conv.weight.detach() if frozen else self.conv.weight
         b = self.conv.bias.detach() if frozen else self.conv.bias
+        if layer.last and self.norm_type == "none":
+            # narrow-output layer: produces the public NCHW fp32 image directly (must end a chain)
+            assert upsample == 1 and residual is None and out_pad == 0
+            return ops.ConvOutFn.apply(xin, w, b, layer, self.act_type)
         if self.norm_type == "none":
             assert upsample == 1 and residual is None
             out = ops.ConvFn.apply(xin, w, b, layer, self.act_type, out_pad, self.padding)
@@ -191,6 +195,8 @@ class Conv2dBlock(nn.Module):
     # -- public path (tensor in, tensor out) ----------------------------------------------
     def forward(self, x):
         a = self.forward_act(x, 0)
+        if torch.is_tensor(a):
+            return a
         return ops.FromActFn.apply(a.t, self.conv.out_channels, 0)
 
 
@@ -387,6 +393,8 @@ class Decoder(nn.Module):
         if not isinstance(x, Act):
             x = Act(ops.ToActFn.apply(x, 1), 1)
         a = run_chain(list(self.model), x, 0)
+        if torch.is_tensor(a):  # the 7x7 tanh layer wrote the NCHW fp32 image itself
+            return a
         return ops.FromActFn.apply(a.t, self.output_dim, 0)
 
 

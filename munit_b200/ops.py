@@ -60,6 +60,8 @@ class ConvLayer:
     def __init__(self, cin, cout, k, stride, pad):
         self.cin, self.cout, self.k, self.stride, self.pad = cin, cout, k, stride, pad
         self.first = cin < 64  # image-space layer: kw-expanded GEMM (K = 64 per kh tap)
+        # narrow-output layer (64->3 7x7 tanh): vertical GEMM with N = (kw, co) + horizontal combine
+        self.last = (not self.first) and cout <= 4 and k <= 8 and stride == 1
         if self.first:
             assert cin <= 4 and k in (4, 7), "first-layer path supports 7x7 (s1) and 4x4 (s2) RGB convs"
             self.kwp, self.cp = (8, 8) if k == 7 else (4, 16)
@@ -67,7 +69,7 @@ class ConvLayer:
         else:
             assert cin % 64 == 0, f"input channels {cin} must be a multiple of 64 (or an image)"
             self.c_buf = cin
-        self.co_rows = ((cout + 15) // 16) * 16
+        self.co_rows = 32 if self.last else ((cout + 15) // 16) * 16
         self.ck = max(64, self.co_rows)  # K extent per tap of the dgrad matrix
         self._ver = None
         self.w_fwd = self.w_dg = self.bias_p = None
@@ -77,6 +79,11 @@ class ConvLayer:
     # ---- weight shadows -------------------------------------------------------------------
     def _build_maps(self, dev):
         c, k = self, self.k
+        if c.last:
+            fwd, dg, inv = G.rspace_index_maps(c.cout, c.cin, k, k)
+            self._idx_fwd, self._idx_dg, self._idx_inv = fwd.to(dev), dg.to(dev), inv.to(dev)
+            self._identity_fwd = False
+            return
         if c.first:
             fwd = G.fwd_index_map(c.cout, c.cin, k, k, c.co_rows, 64, c.kwp, c.cp)
             dg = G.dgrad_index_map(c.cout, c.cin, k, k, c.stride, 1, 64, c.ck, c.kwp, c.cp)
@@ -110,7 +117,7 @@ class ConvLayer:
         else:
             K.gather_cast(src, self._idx_fwd, self.w_fwd)
         K.gather_cast(src, self._idx_dg, self.w_dg)
-        if bias is not None:
+        if bias is not None and not self.last:
             if self.co_rows == self.cout:
                 self.bias_p = bias.detach()
             else:
@@ -124,7 +131,7 @@ class ConvLayer:
         p = self._plans.get(key)
         if p is None:
             k, s = self.k, self.stride
-            if self.first:
+            if self.first or self.last:
                 kh, kw, sy, sx, c = k, 1, s, 1, 64
             else:
                 kh, kw, sy, sx, c = k, k, s, s, self.cin
@@ -135,6 +142,8 @@ class ConvLayer:
             dg = G.plan_dgrad(n, hp, wp, c, kh, kw, sy, sx, self.co_rows)
             if self.first:
                 wg = G.plan_wgrad(n, hp, wp, 64, kh, 1, sy, 1, self.co_rows, self.cout, kh * 64, 64, 1)
+            elif self.last:
+                wg = G.plan_wgrad(n, hp, wp, 64, kh, 1, 1, 1, 32, 32, kh * 64, 64, 1)
             else:
                 wg = G.plan_wgrad(n, hp, wp, c, kh, kw, sy, sx, self.co_rows, self.cout, kh * kw * c, c, 1)
             # direct-form algorithmic work of this layer instance: 1 MAC = 2 FLOP
@@ -216,6 +225,49 @@ class ConvFn(torch.autograd.Function):
                 K.wgrad(wg, dy, gemm_in, _cl_weight(tgt))
             gw = None if buf is not None else tgt
         return gx, gw, gb, None, None, None, None
+
+
+class ConvOutFn(torch.autograd.Function):
+    """Narrow-output Conv2dBlock (64 -> 3, 7x7, tanh; networks.py:548-559): act with halo -> NCHW fp32 image.
+    Vertical taps on the tensor cores (7 taps, N = (kw, co) = 32), horizontal taps + bias + activation in
+    one bandwidth kernel that writes the public layout directly."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, layer: ConvLayer, act: str):
+        layer.refresh(weight, bias)
+        n, hp, wp, _ = x.shape
+        fwd, _, _, ho, wo = layer.plans(n, hp, wp, 0)
+        r = torch.empty(n, ho, wp, 32, dtype=torch.bfloat16, device=x.device)
+        K.tapgemm(fwd, x, layer.w_fwd, r, None, "none")
+        out = K.rspace_combine(r, bias.detach() if bias is not None else None, layer.cout, layer.k, act)
+        ctx.layer, ctx.act = layer, act
+        ctx.wbuf, ctx.bbuf = _param_grad_buf(weight), _param_grad_buf(bias)
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, out, weight)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        layer: ConvLayer = ctx.layer
+        x, out, weight = ctx.saved_tensors
+        n, hp, wp, _ = x.shape
+        _, dg, wg, ho, wo = layer.plans(n, hp, wp, 0)
+        gb = gw = gx = None
+        db = None
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = ctx.bbuf if ctx.bbuf is not None else torch.zeros(layer.cout, dtype=torch.float32, device=x.device)
+            gb = None if ctx.bbuf is not None else db
+        dr = K.rspace_expand(g.contiguous(), out, layer.k, ctx.act, db)
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty(n, hp, wp, layer.cin, dtype=torch.bfloat16, device=x.device)
+            K.tapgemm(dg, dr, layer.w_dg, gx)
+        if ctx.needs_input_grad[1]:
+            tmp = torch.zeros(32 * layer.k * 64, dtype=torch.float32, device=x.device)
+            K.wgrad(wg, dr, x, tmp)
+            tgt = ctx.wbuf if ctx.wbuf is not None else _grad_like_cl(weight)
+            K.gather_add(tmp, layer._idx_inv, _cl_weight(tgt))
+            gw = None if ctx.wbuf is not None else tgt
+        return gx, gw, gb, None, None
 
 
 class NormFn(torch.autograd.Function):

@@ -122,3 +122,40 @@ def test_pick_tile():
     assert tw * th * tn == 128 and tw <= 4 and th <= 4
     tw, th, tn = G.pick_tile(66, 66, 1, 128)
     assert tw * th * tn == 128
+
+
+def test_rspace_narrow_output_layer():
+    """64 -> 3 7x7 layer as a vertical (7x1) GEMM with N = (kw, co) plus a horizontal combine."""
+    n, cin, cout, k, pad, h, w = 2, 64, 3, 7, 3, 6, 9
+    x = torch.randn(n, cin, h, w)
+    wt = torch.randn(cout, cin, k, k) * 0.1
+    xp = F.pad(x, (pad,) * 4, mode="reflect").requires_grad_(True)
+    wt_r = wt.clone().requires_grad_(True)
+    y = F.conv2d(xp, wt_r)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    hp, wp = h + 2 * pad, w + 2 * pad
+    fwd_i, dg_i, inv_i = G.rspace_index_maps(cout, cin, k, k)
+    wflat = wt.permute(0, 2, 3, 1).reshape(-1)
+    pick = lambda idx: torch.where(idx >= 0, wflat[idx.clamp(min=0).long()], torch.zeros(()))
+    plan = G.plan_fwd(n, hp, wp, 64, k, 1, 1, 1, 32, (h * wp * 32, wp * 32, 32, 0, 0))
+    r = torch.zeros(n * h * wp * 32)
+    E.tapgemm(plan, nhwc(xp.detach()).reshape(-1), pick(fwd_i).view(32, -1), r)
+    r = r.view(n, h, wp, 8, 4)
+    out = torch.zeros(n, cout, h, w)
+    for kw in range(k):
+        out += r[:, :, kw:kw + w, kw, :cout].permute(0, 3, 1, 2)
+    assert torch.allclose(out, y.detach(), atol=1e-3)
+    # backward: expand g -> dR, vertical dgrad, wgrad + scatter-back
+    dr = torch.zeros(n, h, wp, 8, 4)
+    for kw in range(k):
+        dr[:, :, kw:kw + w, kw, :cout] = gy.permute(0, 2, 3, 1)
+    dplan = G.plan_dgrad(n, hp, wp, 64, k, 1, 1, 1, 32)
+    dxp = torch.zeros(n * hp * wp * 64)
+    E.tapgemm(dplan, dr.reshape(-1), pick(dg_i).view(64, -1), dxp)
+    assert torch.allclose(dxp.view(n, hp, wp, 64), nhwc(xp.grad), atol=1e-3)
+    wplan = G.plan_wgrad(n, hp, wp, 64, k, 1, 1, 1, 32, 32, k * 64, 64, 1)
+    tmp = torch.zeros(32 * k * 64)
+    E.wgrad(wplan, dr.reshape(-1), nhwc(xp.detach()).reshape(-1), tmp)
+    dw = torch.where(inv_i >= 0, tmp[inv_i.clamp(min=0).long()], torch.zeros(()))
+    assert torch.allclose(dw.view(cout, k, k, cin), wt_r.grad.permute(0, 2, 3, 1), atol=1e-2, rtol=1e-3)
