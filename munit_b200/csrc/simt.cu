@@ -238,15 +238,28 @@ __device__ __forceinline__ void reduce_nc(Fn fn, float* __restrict__ out2, int h
     dst[1] = b;
   }
 }
-__device__ __forceinline__ void sum_splits(const float* __restrict__ part, int n, int splits, int c, int ch, double& s1,
-                                           double& s2) {
-  s1 = 0.0;
-  s2 = 0.0;
-  for (int s = 0; s < splits; ++s) {
-    const float* p = part + (((long long)n * splits + s) * c + ch) * 2;
-    s1 += (double)p[0];
-    s2 += (double)p[1];
+// Sum the split partials of sample n for every channel into shared memory (sm[ch*2+{0,1}]), one warp per
+// channel, lanes striding over splits, fixed shuffle tree: deterministic.  Ends with __syncthreads().
+__device__ __forceinline__ void sum_splits_to_smem(const float* __restrict__ part, int n, int splits, int c,
+                                                   double* __restrict__ sm) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int ch = warp; ch < c; ch += nwarps) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int s = lane; s < splits; s += 32) {
+      const float2 p = *reinterpret_cast<const float2*>(part + (((long long)n * splits + s) * c + ch) * 2);
+      s1 += (double)p.x;
+      s2 += (double)p.y;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) {
+      sm[ch * 2] = s1;
+      sm[ch * 2 + 1] = s2;
+    }
   }
+  __syncthreads();
 }
 
 __global__ void norm_stats_kernel(const bf16* __restrict__ y, float* __restrict__ stats, float* __restrict__ shift,
@@ -305,15 +318,14 @@ __global__ void norm_finalize_kernel(const float* __restrict__ stats, int splits
   const int n = blockIdx.x;
   __shared__ double sh[2][32];
   __shared__ double tot[2];
+  extern __shared__ double ssum[];  // [c][2]
   const double cnt = (double)hw;
+  sum_splits_to_smem(stats, n, splits, c, ssum);
   if (mode == MUNIT_NORM_LN) {
     // sample mean
     double s = 0.0;
-    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-      double a1, a2;
-      sum_splits(stats, n, splits, c, ch, a1, a2);
-      s += cnt * (double)shift[(long long)n * c + ch] + a1;
-    }
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x)
+      s += cnt * (double)shift[(long long)n * c + ch] + ssum[ch * 2];
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0) sh[0][threadIdx.x >> 5] = s;
     __syncthreads();
@@ -327,8 +339,7 @@ __global__ void norm_finalize_kernel(const float* __restrict__ stats, int splits
     double ss = 0.0;
     for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
       const double d = mu - (double)shift[(long long)n * c + ch];
-      double s1, s2;
-      sum_splits(stats, n, splits, c, ch, s1, s2);
+      const double s1 = ssum[ch * 2], s2 = ssum[ch * 2 + 1];
       ss += s2 - 2.0 * d * s1 + cnt * d * d;
     }
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
@@ -353,8 +364,7 @@ __global__ void norm_finalize_kernel(const float* __restrict__ stats, int splits
   } else {
     for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
       const long long i = (long long)n * c + ch;
-      double a1, a2;
-      sum_splits(stats, n, splits, c, ch, a1, a2);
+      const double a1 = ssum[ch * 2], a2 = ssum[ch * 2 + 1];
       const double m1 = a1 / cnt;
       double var = a2 / cnt - m1 * m1;  // biased (F.batch_norm / InstanceNorm2d)
       if (var < 0.0) var = 0.0;
@@ -482,13 +492,14 @@ __global__ void norm_bwd_finalize_kernel(const float* __restrict__ sums, int spl
                                          int c) {
   const int n = blockIdx.x;
   const double cnt = (double)hw;
+  extern __shared__ double ssum[];  // [c][2]
+  sum_splits_to_smem(sums, n, splits, c, ssum);
   if (mode == MUNIT_NORM_LN) {
     __shared__ double sh[2][32];
     __shared__ double tot[2];
     double g1 = 0.0, g2 = 0.0;
     for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-      double s1, s2;
-      sum_splits(sums, n, splits, c, ch, s1, s2);
+      const double s1 = ssum[ch * 2], s2 = ssum[ch * 2 + 1];
       g1 += (double)p_w[ch] * s1;
       g2 += (double)p_w[ch] * s2;
       if (g_w) atomicAdd(g_w + ch, (float)s2);
@@ -529,8 +540,7 @@ __global__ void norm_bwd_finalize_kernel(const float* __restrict__ sums, int spl
       const long long i = (long long)n * c + ch;
       const float wv = (mode == MUNIT_NORM_ADAIN) ? p_w[(long long)n * ldw + ch] : 1.f;
       const float A = rinv[i] * wv;
-      double s1, s2;
-      sum_splits(sums, n, splits, c, ch, s1, s2);
+      const double s1 = ssum[ch * 2], s2 = ssum[ch * 2 + 1];
       ca[i] = A;
       cc[i] = (float)(-(double)A * s1 / cnt);
       cb[i] = (float)(-(double)A * s2 / cnt);
@@ -723,20 +733,24 @@ __global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __re
     y[(long long)bb * out + o] = relu ? fmaxf(acc, 0.f) : acc;
   }
 }
-// dx[b][i] = sum_o dyp[b][o] w[o][i]   (thread per (b,i))
+// dx[b][i] = sum_o dyp[b][o] w[o][i]: grid (o-chunks of 64, b); threads over i; partial sums via atomicAdd
 __global__ void linear_bwd_dx_kernel(const float* __restrict__ w, const float* __restrict__ y,
                                      const float* __restrict__ dy, int relu, float* __restrict__ dx, int b, int in,
                                      int out) {
-  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (t >= (long long)b * in) return;
-  const int i = (int)(t % in), bb = (int)(t / in);
-  float acc = 0.f;
-  for (int o = 0; o < out; ++o) {
-    float g = dy[(long long)bb * out + o];
-    if (relu && y[(long long)bb * out + o] <= 0.f) g = 0.f;
-    acc = fmaf(g, w[(long long)o * in + i], acc);
+  const int bb = blockIdx.y;
+  const int o0 = blockIdx.x * 64, o1 = min(out, o0 + 64);
+  __shared__ float g[64];
+  for (int o = o0 + threadIdx.x; o < o1; o += blockDim.x) {
+    float v = dy[(long long)bb * out + o];
+    if (relu && y[(long long)bb * out + o] <= 0.f) v = 0.f;
+    g[o - o0] = v;
   }
-  dx[t] = acc;
+  __syncthreads();
+  for (int i = threadIdx.x; i < in; i += blockDim.x) {
+    float acc = 0.f;
+    for (int o = o0; o < o1; ++o) acc = fmaf(g[o - o0], w[(long long)o * in + i], acc);
+    atomicAdd(dx + (long long)bb * in + i, acc);
+  }
 }
 // dw[o][i] += sum_b dyp[b][o] x[b][i]; db[o] += sum_b dyp[b][o]   (thread per (o,i))
 __global__ void linear_bwd_dw_kernel(const float* __restrict__ x, const float* __restrict__ y,
@@ -816,9 +830,8 @@ __global__ void dis_head_fwd_kernel(const bf16* __restrict__ y, const float* __r
 }
 __global__ void dis_head_bwd_kernel(const bf16* __restrict__ y, const float* __restrict__ w,
                                     const float* __restrict__ out, float target, const float* __restrict__ gscale_dev,
-                                    float gscale, bf16* __restrict__ dy, float* __restrict__ dw, float* __restrict__ db,
-                                    long long npix, int c) {
-  // thread per (pixel, 8-channel group) for dy; dw/db via a second pass below (c threads looping pixels)
+                                    float gscale, bf16* __restrict__ dy, long long npix, int c) {
+  // thread per (pixel, 8-channel group)
   const int cg = c / 8;
   const float gs = gscale * (gscale_dev ? gscale_dev[0] : 1.f) * 2.f / (float)npix;
   const long long total = npix * cg;
@@ -832,18 +845,45 @@ __global__ void dis_head_bwd_kernel(const bf16* __restrict__ y, const float* __r
     for (int e = 0; e < 8; ++e) r.v[e] = d * ww.v[e];
     store8(dy + i * 8, r);
   }
-  if (dw) {
-    // grid-stride over channels: each thread owns one channel and loops all pixels (npix is small: <= B*256)
-    for (long long ch = blockIdx.x * (long long)blockDim.x + threadIdx.x; ch < c; ch += (long long)gridDim.x * blockDim.x) {
-      float acc = 0.f;
-      for (long long p = 0; p < npix; ++p) acc = fmaf(gs * (out[p] - target), __bfloat162float(y[p * c + ch]), acc);
-      dw[ch] += acc;
+}
+// dw[c] += sum_p do[p]*y[p][c]; db += sum_p do[p]   (block = CG x R like colsum; atomics per block)
+__global__ void dis_head_wgrad_kernel(const bf16* __restrict__ y, const float* __restrict__ out, float target,
+                                      const float* __restrict__ gscale_dev, float gscale, float* __restrict__ dw,
+                                      float* __restrict__ db, long long npix, int c) {
+  extern __shared__ float red[];
+  const int cgs = c / 8;
+  const int rows = blockDim.x / cgs;
+  const int cg = threadIdx.x % cgs, r = threadIdx.x / cgs;
+  const float gs = gscale * (gscale_dev ? gscale_dev[0] : 1.f) * 2.f / (float)npix;
+  const long long per = (npix + gridDim.x - 1) / gridDim.x;
+  const long long p0 = blockIdx.x * per;
+  const long long p1 = min(npix, p0 + per);
+  float s0[8], sb = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s0[e] = 0.f;
+  if (r < rows)
+    for (long long pix = p0 + r; pix < p1; pix += rows) {
+      const float d = gs * (out[pix] - target);
+      const F8 x = load8(y + pix * c + cg * 8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s0[e] = fmaf(d, x.v[e], s0[e]);
+      if (cg == 0) sb += d;
     }
-    if (db && blockIdx.x == 0 && threadIdx.x == 0) {
-      float acc = 0.f;
-      for (long long p = 0; p < npix; ++p) acc += gs * (out[p] - target);
-      db[0] += acc;
-    }
+  if (r < rows) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[r * c + cg * 8 + e] = s0[e];
+    if (cg == 0) red[rows * c + r] = sb;
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float a = 0.f;
+    for (int rr = 0; rr < rows; ++rr) a += red[rr * c + ch];
+    atomicAdd(dw + ch, a);
+  }
+  if (threadIdx.x == 0 && db) {
+    float a = 0.f;
+    for (int rr = 0; rr < rows; ++rr) a += red[rows * c + rr];
+    atomicAdd(db, a);
   }
 }
 
@@ -1072,7 +1112,7 @@ int munit_norm_finalize(const float* stats, const float* shift, int mode, const 
                         int64_t ldw, float eps, float* mean, float* rinv, float* a, float* b, int n, int hw, int c,
                         void* stream) {
   if (mode != MUNIT_NORM_IN && (!p_w || !p_b)) return mb_fail(MUNIT_ERR_ARG, "norm_finalize: missing affine params");
-  norm_finalize_kernel<<<n, 256, 0, ST(stream)>>>(stats, reduce_splits(hw, c), shift, mode, p_w, p_b, ldw, eps, mean,
+  norm_finalize_kernel<<<n, 256, sizeof(double) * 2 * c, ST(stream)>>>(stats, reduce_splits(hw, c), shift, mode, p_w, p_b, ldw, eps, mean,
                                                   rinv, a, b, hw, c);
   MB_CHECK_LAUNCH("norm_finalize");
   return MUNIT_OK;
@@ -1114,7 +1154,7 @@ int munit_norm_bwd_reduce(const void* g_out, int out_pad, int upsample, const vo
 int munit_norm_bwd_finalize(const float* sums, int mode, const float* p_w, int64_t ldw, const float* rinv, float eps,
                             float* ca, float* cb, float* cc, float* g_w, float* g_b, int64_t ldg, int n, int hw, int c,
                             void* stream) {
-  norm_bwd_finalize_kernel<<<n, 256, 0, ST(stream)>>>(sums, reduce_splits(hw, c), mode, p_w, ldw, rinv, eps, ca, cb, cc,
+  norm_bwd_finalize_kernel<<<n, 256, sizeof(double) * 2 * c, ST(stream)>>>(sums, reduce_splits(hw, c), mode, p_w, ldw, rinv, eps, ca, cb, cc,
                                                       g_w, g_b, ldg, hw, c);
   MB_CHECK_LAUNCH("norm_bwd_finalize");
   return MUNIT_OK;
@@ -1199,7 +1239,9 @@ int munit_linear_fwd(const float* x, const float* w, const float* bias, float* y
 int munit_linear_bwd(const float* x, const float* w, const float* y, const float* dy, int relu, float* dx, float* dw,
                      float* db, int b, int in, int out, void* stream) {
   if (dx) {
-    linear_bwd_dx_kernel<<<nblocks((long long)b * in, 128), 128, 0, ST(stream)>>>(w, y, dy, relu, dx, b, in, out);
+    cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)b * in, ST(stream));
+    dim3 grid((out + 63) / 64, b);
+    linear_bwd_dx_kernel<<<grid, in >= 256 ? 256 : 64, 0, ST(stream)>>>(w, y, dy, relu, dx, b, in, out);
     MB_CHECK_LAUNCH("linear_bwd_dx");
   }
   if (dw) {
@@ -1232,8 +1274,17 @@ int munit_dis_head_fwd(const void* y, const float* w, const float* bias, float t
 int munit_dis_head_bwd(const void* y, const float* w, const float* out, float target, const float* gscale_dev,
                        float gscale, void* dy, float* dw, float* db, int64_t npix, int c, void* stream) {
   dis_head_bwd_kernel<<<grid_for(npix * (c / 8)), 256, 0, ST(stream)>>>(CBF(y), w, out, target, gscale_dev, gscale,
-                                                                         BF(dy), dw, db, npix, c);
+                                                                         BF(dy), npix, c);
   MB_CHECK_LAUNCH("dis_head_bwd");
+  if (dw) {
+    if (c / 8 > 256 || 256 % (c / 8)) return mb_fail(MUNIT_ERR_ARG, "dis_head_bwd: channels %d", c);
+    const int rows = 256 / (c / 8);
+    long long splits = (npix + rows * 8 - 1) / (rows * 8);
+    if (splits > 592) splits = 592;
+    dis_head_wgrad_kernel<<<(int)splits, 256, sizeof(float) * (rows * c + rows), ST(stream)>>>(
+        CBF(y), out, target, gscale_dev, gscale, dw, db, npix, c);
+    MB_CHECK_LAUNCH("dis_head_wgrad");
+  }
   return MUNIT_OK;
 }
 
