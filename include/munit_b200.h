@@ -74,7 +74,8 @@ typedef struct {
   int32_t n_store; /* columns actually stored per pixel (<= b_rows) */
   const float* bias; /* [b_rows] or NULL */
   int32_t act;
-  int32_t stages; /* 0 = auto */
+  int32_t stages;  /* 0 = auto */
+  int32_t cluster; /* CTAs per cluster sharing (multicasting) the weight tile: 0 = auto, 1, 2 or 4 */
 } munit_tapgemm_desc;
 
 int munit_tapgemm(const munit_tapgemm_desc* d, void* stream);

@@ -46,8 +46,10 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
-template <int BN>
-__global__ void __launch_bounds__(kThreads, 2)
+// CS = cluster size along the M-tile index: the CS CTAs of a cluster share the weight tile, each loads
+// BN/CS rows of it and multicasts them to all (cuts L2->SM weight traffic by CS).
+template <int BN, int CS>
+__global__ void __launch_bounds__(kThreads, BN <= 64 ? 4 : 2)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -81,7 +83,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     prefetch_tmap(&tmap_b);
     for (int s = 0; s < stages; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), CS);  // released by the MMA warp of every CTA that multicasts into it
     }
     mbar_init(smem_u32(&tmem_full_bar), 1);
     fence_mbar_init();
@@ -92,8 +94,11 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts / arrives remotely
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t cta_rank = CS > 1 ? cluster_ctarank() : 0;
+  constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -117,7 +122,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         c[0] += kc * 64;
         const uint32_t sa = smem_base + stage * kStageBytes;
         tma_load_nd(p.rank, sa, &tmap_a, fb, c);
-        tma_load_2d(sa + kABytes, &tmap_b, fb, bk0 + kb * 64, n_tile * BN);
+        if (CS == 1) {
+          tma_load_2d(sa + kABytes, &tmap_b, fb, bk0 + kb * 64, n_tile * BN);
+        } else {
+          constexpr int kRows = BN / CS;  // this CTA's slice of the weight tile, broadcast to the cluster
+          tma_load_2d_mcast(sa + kABytes + cta_rank * kRows * 128, &tmap_b, fb, bk0 + kb * 64,
+                            n_tile * BN + cta_rank * kRows, kMask);
+        }
         if (++stage == stages) {
           stage = 0;
           ph ^= 1;
@@ -142,7 +153,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint64_t db = umma_desc_sw128(sb + k * 32, 0, 1024);
           umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0);
         }
-        umma_commit(smem_u32(&empty_bar[stage]));
+        if (CS == 1) umma_commit(smem_u32(&empty_bar[stage]));
+        else umma_commit_mcast(smem_u32(&empty_bar[stage]), kMask);
         if (++stage == stages) {
           stage = 0;
           ph ^= 1;
@@ -197,6 +209,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();  // no CTA exits while a peer can still write its smem / barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -406,27 +419,44 @@ int make_tmap(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dim, c
   return MUNIT_OK;
 }
 
-template <int BN>
+int fwd_stages(int bn, int requested) {
+  // Pipeline depth chosen so that >= 2 CTAs share an SM (<= ~113 KB each): a co-resident CTA hides the
+  // other's prologue, TMA round trip and epilogue (profiles/r1_stages.md).  Measured best: BN=256 -> 2,
+  // BN=128 -> 3, BN<=64 -> 2 (four CTAs per SM).
+  if (requested > 0) return requested > kMaxStages ? kMaxStages : (requested < 2 ? 2 : requested);
+  return bn == 128 ? 3 : 2;
+}
+
+template <int BN, int CS>
 int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, FwdParams& p, dim3 grid, cudaStream_t st) {
   const int stage_bytes = kABytes + BN * 128;
-  int stages = p.stages;
-  if (stages <= 0) {
-    // Two CTAs per SM (<= ~113 KB each): a co-resident CTA hides the other's prologue, TMA latency and
-    // epilogue -- measured on B200 to beat a deeper single-CTA pipeline (profiles/r1_stages.md).
-    stages = (112 * 1024) / stage_bytes;
-    if (stages > 6) stages = 6;
-  }
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) stages = 2;
-  p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  p.stages = fwd_stages(BN, p.stages);
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BN, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
     attr_smem = smem;
   }
-  tapgemm_kernel<BN><<<grid, kThreads, smem, st>>>(ta, tb, p);
+  if (CS == 1) {
+    tapgemm_kernel<BN, CS><<<grid, kThreads, smem, st>>>(ta, tb, p);
+  } else {
+    grid.x = (grid.x + CS - 1) / CS * CS;  // padding CTAs map to out-of-range tiles: loads zero-fill, stores masked
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tapgemm_kernel<BN, CS>, ta, tb, p);
+    if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "tapgemm cluster launch: %s", cudaGetErrorString(e));
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "tapgemm launch: %s", cudaGetErrorString(e));
   return MUNIT_OK;
@@ -437,8 +467,7 @@ int launch_wg(const CUtensorMap& ta, const CUtensorMap& tb, WgParams& p, dim3 gr
   const int stage_bytes = (2 + BN / 64) * kBoxBytes;
   int stages = p.stages;
   if (stages <= 0) {
-    // Two CTAs per SM (<= ~113 KB each): a co-resident CTA hides the other's prologue, TMA latency and
-    // epilogue -- measured on B200 to beat a deeper single-CTA pipeline (profiles/r1_stages.md).
+    // two CTAs per SM (<= ~113 KB each), see fwd_stages()
     stages = (112 * 1024) / stage_bytes;
     if (stages > 6) stages = 6;
   }
@@ -491,11 +520,6 @@ extern "C" int munit_tapgemm(const munit_tapgemm_desc* d, void* stream) {
   CUtensorMap ta, tb;
   int rc = make_tmap(&ta, d->a, d->a_rank, d->a_dim, d->a_stride, d->a_box);
   if (rc) return rc;
-  uint64_t bdim[2] = {d->b_k, d->b_rows};
-  uint64_t bstr[2] = {0, d->b_k * 2};
-  uint32_t bbox[2] = {64, (uint32_t)d->bn};
-  rc = make_tmap(&tb, d->b, 2, bdim, bstr, bbox);
-  if (rc) return rc;
   FwdParams p;
   memset(&p, 0, sizeof(p));
   p.tw = d->tw; p.th = d->th; p.tn = d->tn;
@@ -514,13 +538,31 @@ extern "C" int munit_tapgemm(const munit_tapgemm_desc* d, void* stream) {
   memcpy(p.tap_off, d->tap_off, sizeof(p.tap_off));
   dim3 grid(p.tiles_x * p.tiles_y * p.tiles_n, (unsigned)(d->b_rows / d->bn), d->phases);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // Weight-tile multicast across a cluster of M tiles (d->cluster: 0 = auto, 1/2/4 forced).  Measured on
+  // B200 (profiles/r1_multicast.md): the kernel is bound by bytes in flight per SM (smem capacity / TMA round
+  // trip), not by L2->SM bandwidth, so multicast only adds lock-step coupling -- auto therefore picks 1.
+  int cs = d->cluster;
+  if (cs <= 0) cs = 1;
+  if (cs != 1 && cs != 2 && cs != 4) return mb_fail(MUNIT_ERR_ARG, "tapgemm: cluster must be 1, 2 or 4");
+  if (d->bn < 64) cs = 1;
+  uint64_t bdim[2] = {d->b_k, d->b_rows};
+  uint64_t bstr[2] = {0, d->b_k * 2};
+  uint32_t bbox[2] = {64, (uint32_t)(d->bn / cs)};
+  rc = make_tmap(&tb, d->b, 2, bdim, bstr, bbox);
+  if (rc) return rc;
+#define MB_FWD(BN_)                                                   \
+  case BN_:                                                           \
+    if (cs == 4) return launch_fwd<BN_, 4>(ta, tb, p, grid, st);      \
+    if (cs == 2) return launch_fwd<BN_, 2>(ta, tb, p, grid, st);      \
+    return launch_fwd<BN_, 1>(ta, tb, p, grid, st);
   switch (d->bn) {
-    case 16: return launch_fwd<16>(ta, tb, p, grid, st);
-    case 32: return launch_fwd<32>(ta, tb, p, grid, st);
-    case 64: return launch_fwd<64>(ta, tb, p, grid, st);
-    case 128: return launch_fwd<128>(ta, tb, p, grid, st);
-    case 256: return launch_fwd<256>(ta, tb, p, grid, st);
+    case 16: return launch_fwd<16, 1>(ta, tb, p, grid, st);
+    case 32: return launch_fwd<32, 1>(ta, tb, p, grid, st);
+    MB_FWD(64)
+    MB_FWD(128)
+    MB_FWD(256)
   }
+#undef MB_FWD
   return mb_fail(MUNIT_ERR_ARG, "tapgemm: bn %d unsupported", d->bn);
 }
 

@@ -27,7 +27,7 @@ def _fill5(dst, src, fill=0):
         dst[i] = src[i] if i < len(src) else fill
 
 
-def tapgemm(plan, a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, bias=None, act="none", stages=0):
+def tapgemm(plan, a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, bias=None, act="none", stages=0, cluster=0):
     """out (bf16) <- act(tapconv(a; b) + bias) as described by `plan` (geometry.TapGemmPlan)."""
     _lib.init()
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
@@ -56,7 +56,7 @@ def tapgemm(plan, a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, bias=None
     d.n_store = plan.n_store
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() >= plan.b_rows
-    d.bias, d.act, d.stages = _ptr(bias), ACT[act], stages
+    d.bias, d.act, d.stages, d.cluster = _ptr(bias), ACT[act], stages, cluster
     check(lib.munit_tapgemm(C.byref(d), _stream()), "munit_tapgemm")
     _count()
     return out

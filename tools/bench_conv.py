@@ -29,6 +29,7 @@ def run(name, iters=20, nbuf=4):
     if os.environ.get("BN"):
         fwd.bn = int(os.environ["BN"])
     stages = int(os.environ.get("STAGES", 0))
+    cluster = int(os.environ.get("CLUSTER", 0))
     dg = G.plan_dgrad(n, hp, wp, cin, k, k, s, s, cout)
     ck = max(64, cout)
     wd = (torch.randn(cin, dg.b_k, device="cuda") * 0.05).to(torch.bfloat16)
@@ -36,8 +37,8 @@ def run(name, iters=20, nbuf=4):
     wg = G.plan_wgrad(n, hp, wp, cin, k, k, s, s, cout, cout, k * k * cin, cin, 1)
     dw = torch.zeros(cout, k, k, cin, device="cuda")
     res = {}
-    for label, fn in (("fwd", lambda i: K.tapgemm(fwd, xs[i % nbuf], wf, ys[i % nbuf], stages=stages)),
-                      ("dgrad", lambda i: K.tapgemm(dg, ys[i % nbuf], wd, dxs[i % nbuf])),
+    for label, fn in (("fwd", lambda i: K.tapgemm(fwd, xs[i % nbuf], wf, ys[i % nbuf], stages=stages, cluster=cluster)),
+                      ("dgrad", lambda i: K.tapgemm(dg, ys[i % nbuf], wd, dxs[i % nbuf], cluster=cluster)),
                       ("wgrad", lambda i: K.wgrad(wg, ys[i % nbuf], xs[i % nbuf], dw))):
         for i in range(3):
             fn(i)
