@@ -11,7 +11,7 @@ from typing import Dict, Optional
 import torch
 import torch.distributed as dist
 
-from . import _lib
+from . import _lib, dp
 
 
 class StepRunner:
@@ -55,7 +55,7 @@ class StepRunner:
 
     def _allreduce(self, opt):
         if self.world > 1:
-            dist.all_reduce(opt.g_arena, op=dist.ReduceOp.SUM)
+            dp.allreduce_arena(opt.g_arena)
 
     def _eager_step(self):
         self._seg_dis()
