@@ -322,6 +322,80 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_infer(args):
+    """test_batch.py semantics (BASELINE.json configs[3]): 32 content images x 10 random style codes at 256^2,
+    gen_state 0: one content-encode + 10 (MLP + decoder) passes per step -> output images / s."""
+    torch.cuda.set_device(0)
+    from munit_b200 import _lib
+    from munit_b200.trainer import MUNIT_Trainer
+
+    cfg = load_cfg(args.hd)
+    cfg["gen_state"], cfg["guided"] = 0, 0
+    hw = args.hw or cfg["crop_image_height"]
+    nimg, nstyle = args.batch if args.batch != 8 else 32, 10
+    torch.manual_seed(0)
+    t = MUNIT_Trainer(cfg).cuda().eval()
+    x, _ = synthetic_images(nimg, hw, 1234)
+    x_h = x.pin_memory()
+    x_d = torch.empty_like(x, device="cuda")
+    styles_h = torch.randn(nstyle, t.style_dim, 1, 1).pin_memory()
+    styles_d = torch.empty(nstyle, t.style_dim, 1, 1, device="cuda")
+    outs = [None] * nstyle
+
+    def step():
+        with torch.no_grad():
+            c, _ = t.gen_a.encode_act(x_d)
+            for j in range(nstyle):
+                outs[j] = t.gen_b.decode(c, styles_d[j:j + 1].expand(nimg, -1, -1, -1).contiguous())
+
+    x_d.copy_(x_h); styles_d.copy_(styles_h)
+    s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        before = _lib.launches
+        step(); step()
+        launches = (_lib.launches - before) // 2
+    torch.cuda.current_stream().wait_stream(s); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        step()
+    for _ in range(max(args.warmup, 3)):
+        g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        g.replay()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    host_out = torch.empty(nstyle, nimg, 3, hw, hw).pin_memory()
+    f0.record()
+    for _ in range(args.steps):
+        styles_h.copy_(torch.randn(nstyle, t.style_dim, 1, 1))
+        x_d.copy_(x_h, non_blocking=True); styles_d.copy_(styles_h, non_blocking=True)
+        g.replay()
+        for j in range(nstyle):
+            host_out[j].copy_(outs[j], non_blocking=True)
+        torch.cuda.synchronize()
+    f1.record(); torch.cuda.synchronize()
+    ms_e2e = f0.elapsed_time(f1) / args.steps
+    peaks = measured_peaks()
+    n_out = nimg * nstyle
+    tflop = 0.9842 * nimg * (hw / 256.0) ** 2  # 492.1 GMAC per content image with 10 styles (SURVEY.md s8d)
+    line = dict(metric="MUNIT style-sampled inference output imgs/sec 256^2", value=n_out / (ms / 1000.0), unit="images/s",
+                n_gpus=1, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                config=dict(workload=f"test_batch: {nimg} content images x {nstyle} random styles, {hw}x{hw}, gen_state 0",
+                            cuda_graph=True, l2="activations per step >> 126 MB L2; no explicit flush"),
+                e2e=dict(value=n_out / (ms_e2e / 1000.0), unit="images/s", h2d_bytes_per_step=int(x.numel() * 4 + styles_h.numel() * 4),
+                         d2h_bytes_per_step=int(host_out.numel() * 4)),
+                gpu_launches=launches * args.steps,
+                roofline=dict(bound="tensor", achieved=tflop / (ms / 1000.0), peak=peaks["tflops"], unit="TFLOP/s",
+                              frac=tflop / (ms / 1000.0) / peaks["tflops"], traffic=None, peak_source=peaks["src"],
+                              note="whole-step direct-form FLOPs / step time"))
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -334,11 +408,14 @@ def main():
     ap.add_argument("--optimizer", default="")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="train", choices=["train", "infer"])
     ap.add_argument("--dump-launches", default="", help="write per-launch tensor-kernel timings (profile pass) to this json")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "infer":
+        run_infer(args)
     else:
         run_b200(args)
 

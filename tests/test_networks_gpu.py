@@ -145,3 +145,37 @@ def test_standalone_norm_modules():
     w, b = torch.randn(128), torch.randn(128)
     ad.weight, ad.bias = w.cuda(), b.cuda()
     assert rel_l2(ad(x.cuda()).cpu(), O.instance_norm(x, w, b)) < LAYER_TOL
+
+
+def test_style_sampled_inference_matches_oracle():
+    """test_batch.py semantics (encode once, decode per random style) vs the oracle, batched over images."""
+    from munit_b200.networks import AdaINGen
+
+    cfg = O.config_256_core()
+    sd_a = O.init_state_dict(O.gen_spec(cfg["gen"], 3, False), 31, "kaiming")
+    sd_b = O.init_state_dict(O.gen_spec(cfg["gen"], 3, False), 32, "kaiming")
+    ga, gb = AdaINGen(3, cfg["gen"]), AdaINGen(3, cfg["gen"])
+    ga.load_state_dict(sd_a)
+    gb.load_state_dict(sd_b)
+    ga, gb = ga.cuda().eval(), gb.cuda().eval()
+    x, _ = _images(9, 3, 64)
+    torch.manual_seed(4)
+    styles = torch.randn(2, cfg["gen"]["style_dim"], 1, 1)
+    oa, ob = O.Gen(sd_a, cfg["gen"], False), O.Gen(sd_b, cfg["gen"], False)
+    with torch.no_grad():
+        c_ref, _ = oa.encode(x)
+        c, _ = ga.encode_act(x.cuda())
+        for j in range(2):
+            s = styles[j:j + 1].expand(3, -1, -1, -1).contiguous()
+            y_ref = ob.decode(c_ref, s)
+            y = gb.decode(c, s.cuda())
+            # batched decode == per-image decode (all norms are per-sample)
+            y1 = gb.decode(ops_act_slice(c, 1), s[:1].cuda())
+            assert rel_l2(y.cpu(), y_ref) < NET_TOL, rel_l2(y.cpu(), y_ref)
+            assert torch.equal(y[1:2], y1)
+
+
+def ops_act_slice(a, i):
+    from munit_b200.ops import Act
+
+    return Act(a.t[i:i + 1].contiguous(), a.pad)
