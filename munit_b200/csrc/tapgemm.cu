@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/munit_b200.h"
@@ -35,15 +36,46 @@ struct FwdParams {
   const float* bias;
   int act;
   int stages;
+  int dbg;  // profiling knobs (env MUNIT_DBG): 1 skip A loads, 2 skip B loads, 4 skip MMA, 8 skip stores
   int* err;
   int tap_off[MUNIT_MAX_TAPS][5];
 };
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == MUNIT_ACT_RELU) return fmaxf(v, 0.f);
-  if (act == MUNIT_ACT_LRELU) return v > 0.f ? v : 0.2f * v;
-  if (act == MUNIT_ACT_TANH) return tanhf(v);
-  return v;
+struct OutMaps {
+  CUtensorMap m[MUNIT_MAX_PHASES];  // one output view per phase: (C, out_w, out_h, n) with the phase offset/strides
+};
+
+// Branch-free activations keep the epilogue small enough to stay in the instruction cache (a fully
+// unrolled tanhf/branch epilogue was 46 KB of SASS and cost ~15 us per tile in fetch stalls):
+// none / relu / lrelu are max(v, slope*v) with slope 1 / 0 / 0.2; tanh is one MUFU (tanh.approx, ~2^-11 rel).
+__device__ __forceinline__ float act_slope(int act) {
+  return act == MUNIT_ACT_RELU ? 0.f : (act == MUNIT_ACT_LRELU ? 0.2f : 1.f);
+}
+__device__ __forceinline__ float tanh_approx(float v) {
+  float r;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+// 8 accumulators -> (+bias) -> activation -> 4 packed bf16x2 words
+__device__ __forceinline__ void epi8(const uint32_t* v, const float* __restrict__ bias, float slope, bool is_tanh,
+                                     uint32_t* out) {
+  float f[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[e]);
+  if (bias) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias) + 1);
+    f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+    f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], slope * f[e]);
+  if (is_tanh) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = tanh_approx(f[e]);
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) out[e] = pack_bf16(f[2 * e], f[2 * e + 1]);
 }
 
 // CS = cluster size along the M-tile index: the CS CTAs of a cluster share the weight tile, each loads
@@ -51,7 +83,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 template <int BN, int CS>
 __global__ void __launch_bounds__(kThreads, BN <= 64 ? 4 : 2)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const __grid_constant__ FwdParams p) {
+               const __grid_constant__ OutMaps tmap_out, const __grid_constant__ FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int kBBytes = BN * 128;
   constexpr int kStageBytes = kABytes + kBBytes;
@@ -115,14 +147,15 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int kc = kb - tap * p.chunks;
         mbar_wait(smem_u32(&empty_bar[stage]), ph ^ 1, dead, p.err);
         const uint32_t fb = smem_u32(&full_bar[stage]);
-        mbar_arrive_expect_tx(fb, kStageBytes);
+        mbar_arrive_expect_tx(fb, ((p.dbg & 1) ? 0 : kABytes) + ((p.dbg & 2) ? 0 : kBBytes));
         int c[5];
 #pragma unroll
         for (int d = 0; d < 5; ++d) c[d] = base[d] + p.tap_off[tap][d];
         c[0] += kc * 64;
         const uint32_t sa = smem_base + stage * kStageBytes;
-        tma_load_nd(p.rank, sa, &tmap_a, fb, c);
-        if (CS == 1) {
+        if (!(p.dbg & 1)) tma_load_nd(p.rank, sa, &tmap_a, fb, c);
+        if (p.dbg & 2) {
+        } else if (CS == 1) {
           tma_load_2d(sa + kABytes, &tmap_b, fb, bk0 + kb * 64, n_tile * BN);
         } else {
           constexpr int kRows = BN / CS;  // this CTA's slice of the weight tile, broadcast to the cluster
@@ -147,11 +180,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tc_fence_after();
         const uint32_t sa = smem_base + stage * kStageBytes;
         const uint32_t sb = sa + kABytes;
+        if (!(p.dbg & 4)) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t da = umma_desc_sw128(sa + k * 32, 0, 1024);
-          const uint64_t db = umma_desc_sw128(sb + k * 32, 0, 1024);
-          umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = umma_desc_sw128(sa + k * 32, 0, 1024);
+            const uint64_t db = umma_desc_sw128(sb + k * 32, 0, 1024);
+            umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0);
+          }
         }
         if (CS == 1) umma_commit(smem_u32(&empty_bar[stage]));
         else umma_commit_mcast(smem_u32(&empty_bar[stage]), kMask);
@@ -163,45 +198,76 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       umma_commit(smem_u32(&tmem_full_bar));
     }
   } else {
-    // ===================== epilogue: TMEM -> regs -> global =====================
+    // ===================== epilogue: TMEM -> regs -> (smem -> TMA store | global) =====================
     bool dead = false;
     const int q = warp & 3;        // TMEM lane quarter this warp may access
     const int row = q * 32 + lane; // pixel within the tile
-    const int dx = row % p.tw;
-    const int dy = (row / p.tw) % p.th;
-    const int dn = row / (p.tw * p.th);
-    const int n = n0 + dn, y = y0 + dy, x = x0 + dx;
-    const bool valid = (n < p.n_img) && (y < p.out_h) && (x < p.out_w);
-    __nv_bfloat16* optr = p.out + (long long)n * p.o_sn + (long long)(y * p.o_ymul + p.o_yoff[phase_id]) * p.o_sy +
-                          (long long)(x * p.o_xmul + p.o_xoff[phase_id]) * p.o_sx + n_tile * BN;
     mbar_wait(smem_u32(&tmem_full_bar), 0, dead, p.err);
     tc_fence_after();
-    constexpr int kChunk = BN < 32 ? 16 : 32;
+    const float slope = act_slope(p.act);
+    const bool is_tanh = p.act == MUNIT_ACT_TANH;
+    if constexpr (BN >= 64) {
+      // The pipeline stages are idle now (every MMA has completed): stage the bf16 tile there, one
+      // [128 px x 64 ch] SWIZZLE_128B box per 64-channel group, and let TMA write full lines.
+      constexpr int kGroups = BN / 64;
+      const bool issuer = (warp == 2 && lane == 0);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += kChunk) {
-      uint32_t v[kChunk];
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0;
-      if (kChunk == 32) tmem_ld_32x32(taddr, v);
-      else tmem_ld_32x16(taddr, v);
-      tmem_ld_wait();
-      if (valid && !dead) {
-        const int col0 = n_tile * BN + c0;
+      for (int g = 0; g < kGroups; ++g) {
+        if (p.dbg & 16) break;
+        const uint32_t buf = smem_base + g * kABytes;
+        const int col0 = n_tile * BN + g * 64;
+        const bool store_group = col0 < p.n_store;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * 64 + h * 32, v);
+          tmem_ld_wait();
+          if (store_group && !(p.dbg & 32)) {
 #pragma unroll
-        for (int j = 0; j < kChunk; j += 8) {
-          if (col0 + j < p.n_store) {
-            float f[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float a = __uint_as_float(v[j + e]);
-              if (p.bias) a += __ldg(p.bias + col0 + j + e);
-              f[e] = apply_act(a, p.act);
+            for (int j = 0; j < 32; j += 8) {
+              uint32_t o[4];
+              epi8(v + j, p.bias ? p.bias + col0 + h * 32 + j : nullptr, slope, is_tanh, o);
+              const int chunk = (h * 4 + (j >> 3)) ^ (row & 7);  // SWIZZLE_128B: 16B chunk index ^ (row % 8)
+              const uint32_t dst = buf + row * 128 + chunk * 16;
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]),
+                           "r"(o[3])
+                           : "memory");
             }
-            uint4 o;
-            o.x = pack_bf16(f[0], f[1]);
-            o.y = pack_bf16(f[2], f[3]);
-            o.z = pack_bf16(f[4], f[5]);
-            o.w = pack_bf16(f[6], f[7]);
-            *reinterpret_cast<uint4*>(optr + c0 + j) = o;
+          }
+        }
+        fence_proxy_async();
+        named_bar_sync(1, 128);  // the four epilogue warps
+        if (issuer && store_group && !dead && !(p.dbg & 8)) {
+          tma_store_4d(&tmap_out.m[phase_id], buf, col0, x0, y0, n0);
+          tma_store_commit();
+        }
+      }
+      if (issuer) tma_store_wait_read0();
+    } else {
+      const int dx = row % p.tw;
+      const int dy = (row / p.tw) % p.th;
+      const int dn = row / (p.tw * p.th);
+      const int n = n0 + dn, y = y0 + dy, x = x0 + dx;
+      const bool valid = (n < p.n_img) && (y < p.out_h) && (x < p.out_w);
+      __nv_bfloat16* optr = p.out + (long long)n * p.o_sn + (long long)(y * p.o_ymul + p.o_yoff[phase_id]) * p.o_sy +
+                            (long long)(x * p.o_xmul + p.o_xoff[phase_id]) * p.o_sx + n_tile * BN;
+      constexpr int kChunk = BN < 32 ? 16 : 32;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += kChunk) {
+        uint32_t v[kChunk];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0;
+        if (kChunk == 32) tmem_ld_32x32(taddr, v);
+        else tmem_ld_32x16(taddr, v);
+        tmem_ld_wait();
+        if (valid && !dead && !(p.dbg & 8)) {
+          const int col0 = n_tile * BN + c0;
+#pragma unroll
+          for (int j = 0; j < kChunk; j += 8) {
+            if (col0 + j < p.n_store) {
+              uint32_t w[4];
+              epi8(v + j, p.bias ? p.bias + col0 + j : nullptr, slope, is_tanh, w);
+              *reinterpret_cast<uint4*>(optr + c0 + j) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
           }
         }
       }
@@ -428,7 +494,8 @@ int fwd_stages(int bn, int requested) {
 }
 
 template <int BN, int CS>
-int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, FwdParams& p, dim3 grid, cudaStream_t st) {
+int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, const OutMaps& to, FwdParams& p, dim3 grid,
+               cudaStream_t st) {
   const int stage_bytes = kABytes + BN * 128;
   p.stages = fwd_stages(BN, p.stages);
   const size_t smem = (size_t)p.stages * stage_bytes + 1024;
@@ -439,7 +506,7 @@ int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, FwdParams& p, dim3 
     attr_smem = smem;
   }
   if (CS == 1) {
-    tapgemm_kernel<BN, CS><<<grid, kThreads, smem, st>>>(ta, tb, p);
+    tapgemm_kernel<BN, CS><<<grid, kThreads, smem, st>>>(ta, tb, to, p);
   } else {
     grid.x = (grid.x + CS - 1) / CS * CS;  // padding CTAs map to out-of-range tiles: loads zero-fill, stores masked
     cudaLaunchConfig_t cfg = {};
@@ -454,7 +521,7 @@ int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, FwdParams& p, dim3 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tapgemm_kernel<BN, CS>, ta, tb, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tapgemm_kernel<BN, CS>, ta, tb, to, p);
     if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "tapgemm cluster launch: %s", cudaGetErrorString(e));
   }
   cudaError_t e = cudaGetLastError();
@@ -535,6 +602,14 @@ extern "C" int munit_tapgemm(const munit_tapgemm_desc* d, void* stream) {
   p.o_sn = d->o_sn; p.o_sy = d->o_sy; p.o_sx = d->o_sx; p.o_ymul = d->o_ymul; p.o_xmul = d->o_xmul;
   p.n_store = d->n_store; p.bias = d->bias; p.act = d->act; p.stages = d->stages;
   p.err = mb_error_flag();
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("MUNIT_DBG");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.dbg = dbg;
+  }
   memcpy(p.tap_off, d->tap_off, sizeof(p.tap_off));
   dim3 grid(p.tiles_x * p.tiles_y * p.tiles_n, (unsigned)(d->b_rows / d->bn), d->phases);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -550,14 +625,29 @@ extern "C" int munit_tapgemm(const munit_tapgemm_desc* d, void* stream) {
   uint32_t bbox[2] = {64, (uint32_t)(d->bn / cs)};
   rc = make_tmap(&tb, d->b, 2, bdim, bstr, bbox);
   if (rc) return rc;
-#define MB_FWD(BN_)                                                   \
-  case BN_:                                                           \
-    if (cs == 4) return launch_fwd<BN_, 4>(ta, tb, p, grid, st);      \
-    if (cs == 2) return launch_fwd<BN_, 2>(ta, tb, p, grid, st);      \
-    return launch_fwd<BN_, 1>(ta, tb, p, grid, st);
+  // output views for the TMA-store epilogue (BN >= 64): one per phase, clipped to the valid extents
+  OutMaps to;
+  memset(&to, 0, sizeof(to));
+  if (d->bn >= 64) {
+    for (int ph = 0; ph < d->phases; ++ph) {
+      const char* base = reinterpret_cast<const char*>(d->out) +
+                         2 * ((int64_t)d->o_yoff[ph] * d->o_sy + (int64_t)d->o_xoff[ph] * d->o_sx);
+      uint64_t odim[4] = {(uint64_t)d->n_store, (uint64_t)d->out_w, (uint64_t)d->out_h, (uint64_t)d->n_img};
+      uint64_t ostr[4] = {0, (uint64_t)(2 * d->o_sx * d->o_xmul), (uint64_t)(2 * d->o_sy * d->o_ymul),
+                          (uint64_t)(2 * d->o_sn)};
+      uint32_t obox[4] = {64, (uint32_t)d->tw, (uint32_t)d->th, (uint32_t)d->tn};
+      rc = make_tmap(&to.m[ph], base, 4, odim, ostr, obox);
+      if (rc) return rc;
+    }
+  }
+#define MB_FWD(BN_)                                                       \
+  case BN_:                                                               \
+    if (cs == 4) return launch_fwd<BN_, 4>(ta, tb, to, p, grid, st);      \
+    if (cs == 2) return launch_fwd<BN_, 2>(ta, tb, to, p, grid, st);      \
+    return launch_fwd<BN_, 1>(ta, tb, to, p, grid, st);
   switch (d->bn) {
-    case 16: return launch_fwd<16, 1>(ta, tb, p, grid, st);
-    case 32: return launch_fwd<32, 1>(ta, tb, p, grid, st);
+    case 16: return launch_fwd<16, 1>(ta, tb, to, p, grid, st);
+    case 32: return launch_fwd<32, 1>(ta, tb, to, p, grid, st);
     MB_FWD(64)
     MB_FWD(128)
     MB_FWD(256)
