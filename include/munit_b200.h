@@ -84,6 +84,7 @@ int munit_tapgemm(const munit_tapgemm_desc* d, void* stream);
  * Weight-gradient GEMM (replaces cudnn_convolution_backward_weight):
  *
  *   dw[m*s_m + tap*s_t + n*s_n] += sum_{pix} A[pix, m] * B[coordB(pix) + tap_off[tap], n]
+ *   (tap_on_a = 1: the offsets shift A instead, so the wider of Cout / Cin can be the 128-row M operand)
  *
  * A (dY) and B (X) are bf16 activation tensors as TMA views; the reduction runs over pixel blocks of
  * 64 positions (pw x ph x pn), split over `ksplit` CTAs that accumulate into fp32 `dw` with
@@ -110,8 +111,9 @@ typedef struct {
   int32_t tap_off[MUNIT_MAX_TAPS][5]; /* added to B coordinates */
   float* dw;
   int64_t s_m, s_t, s_n;
-  int32_t ksplit; /* 0 = auto */
-  int32_t stages; /* 0 = auto */
+  int32_t ksplit;   /* 0 = auto */
+  int32_t stages;   /* 0 = auto */
+  int32_t tap_on_a; /* 1: tap offsets shift A instead of B (swapped orientation A = X, B = dY) */
 } munit_wgrad_desc;
 
 int munit_wgrad(const munit_wgrad_desc* d, void* stream);

@@ -298,6 +298,7 @@ struct WgParams {
   long long s_m, s_t, s_n;
   int ksplit;
   int stages;
+  int tap_on_a;  // tap offsets shift the A operand (swapped orientation: A = X, B = dY) instead of B
   int* err;
   int tap_off[MUNIT_MAX_TAPS][5];
 };
@@ -305,7 +306,7 @@ struct WgParams {
 constexpr int kBoxBytes = 64 * 128;  // 64 pixels x 64 channels bf16
 
 template <int BN>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, BN == 256 ? 2 : (BN == 128 ? 3 : 4))
 wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
              const __grid_constant__ WgParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -368,7 +369,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           const uint32_t sa = smem_base + stage * kStageBytes;
           int c[5];
 #pragma unroll
-          for (int d = 0; d < 5; ++d) c[d] = x0 * p.a_mx[d] + y0 * p.a_my[d] + n0 * p.a_mn[d];
+          for (int d = 0; d < 5; ++d)
+            c[d] = x0 * p.a_mx[d] + y0 * p.a_my[d] + n0 * p.a_mn[d] + (p.tap_on_a ? p.tap_off[tap][d] : 0);
           const int ca0 = c[0] + m_tile * 128;
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
@@ -376,7 +378,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             tma_load_nd(p.a_rank, sa + i * kBoxBytes, &tmap_a, fb, c);
           }
 #pragma unroll
-          for (int d = 0; d < 5; ++d) c[d] = x0 * p.b_mx[d] + y0 * p.b_my[d] + n0 * p.b_mn[d] + p.tap_off[tap][d];
+          for (int d = 0; d < 5; ++d)
+            c[d] = x0 * p.b_mx[d] + y0 * p.b_my[d] + n0 * p.b_mn[d] + (p.tap_on_a ? 0 : p.tap_off[tap][d]);
           const int cb0 = c[0] + n_tile * BN;
 #pragma unroll
           for (int i = 0; i < kNB; ++i) {
@@ -533,11 +536,7 @@ template <int BN>
 int launch_wg(const CUtensorMap& ta, const CUtensorMap& tb, WgParams& p, dim3 grid, cudaStream_t st) {
   const int stage_bytes = (2 + BN / 64) * kBoxBytes;
   int stages = p.stages;
-  if (stages <= 0) {
-    // two CTAs per SM (<= ~113 KB each), see fwd_stages()
-    stages = (112 * 1024) / stage_bytes;
-    if (stages > 6) stages = 6;
-  }
+  if (stages <= 0) stages = 2;  // shallow pipeline, as many co-resident CTAs as possible (profiles/r1_wgrad.md)
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
   p.stages = stages;
@@ -681,14 +680,22 @@ extern "C" int munit_wgrad(const munit_wgrad_desc* d, void* stream) {
   p.n_tiles = (d->n_total + d->bn - 1) / d->bn;
   p.dw = d->dw; p.s_m = d->s_m; p.s_t = d->s_t; p.s_n = d->s_n;
   p.stages = d->stages; p.err = mb_error_flag();
+  p.tap_on_a = d->tap_on_a;
   memcpy(p.tap_off, d->tap_off, sizeof(p.tap_off));
   const int m_tiles = (d->m_total + 127) / 128;
   const int total_pb = p.blocks_x * p.blocks_y * p.blocks_n;
   int ks = d->ksplit;
   if (ks <= 0) {
+    // The main loop is latency-bound per CTA, so fill every CTA slot of the chip (2 stages -> 2/3/4 CTAs
+    // per SM for BN 256/128/64) with a whole number of waves; keep >= 4 pixel blocks per CTA.
     const int ctas = d->num_taps * p.n_tiles * m_tiles;
-    ks = (2 * 148 + ctas - 1) / ctas;  // ~2 waves
-    const int max_ks = total_pb / 8 > 0 ? total_pb / 8 : 1;  // >= 8 k-blocks per CTA
+    const int per_sm = d->bn == 256 ? 2 : (d->bn == 128 ? 3 : 4);
+    const int slots = 148 * per_sm;
+    int waves = (ctas + slots - 1) / slots;
+    if (waves < 1) waves = 1;
+    ks = (waves * slots) / ctas;
+    if (ks < 1) ks = 1;
+    const int max_ks = total_pb / 4 > 0 ? total_pb / 4 : 1;
     if (ks > max_ks) ks = max_ks;
   }
   if (ks > total_pb) ks = total_pb;

@@ -124,6 +124,7 @@ class WgradPlan:
     s_m: int
     s_t: int
     s_n: int
+    tap_on_a: int = 0
 
 
 def _pad5(v, fill=0):
@@ -207,7 +208,7 @@ def plan_dgrad(n, hp, wp, c_rows, kh, kw, sy, sx, co_c) -> TapGemmPlan:
         o_xmul=sx, n_store=c_rows)
 
 
-def plan_wgrad(n, hp, wp, c, kh, kw, sy, sx, co_c, m_total, s_m, s_t, s_n, n_total=None) -> WgradPlan:
+def plan_wgrad(n, hp, wp, c, kh, kw, sy, sx, co_c, m_total, s_m, s_t, s_n, n_total=None, swap=None) -> WgradPlan:
     """Weight gradient: dw[m, tap, cin] += sum_pix dy[pix, m] * x[pix@tap, cin]."""
     ho, wo = conv_out(hp, kh, sy), conv_out(wp, kw, sx)
     e = 2
@@ -215,7 +216,18 @@ def plan_wgrad(n, hp, wp, c, kh, kw, sy, sx, co_c, m_total, s_m, s_t, s_n, n_tot
     pw, ph, pn = pick_tile(wo, ho, n, 64)
     taps = [off(i, j) for i in range(kh) for j in range(kw)]
     n_total = c if n_total is None else n_total
-    bn = 256 if n_total % 256 == 0 else (128 if n_total % 128 == 0 else 64)
+    if swap is None:  # put the wider channel count on the 128-row M operand
+        swap = m_total <= 64 and n_total >= 128
+    if swap:
+        # A = x (M = input channels, shifted per tap), B = dy (N = output channels): dw[ci*s_n + tap*s_t + co*s_m]
+        bn = 128 if m_total > 64 else 64
+        return WgradPlan(
+            a_rank=rank, a_dim=dims, a_stride=strides, a_box=box(pw, ph, pn), a_mx=mx, a_my=my, a_mn=mn,
+            b_rank=4, b_dim=[co_c, wo, ho, n], b_stride=[e, co_c * e, wo * co_c * e, ho * wo * co_c * e],
+            b_box=[64, pw, ph, pn], b_mx=[0, 1, 0, 0], b_my=[0, 0, 1, 0], b_mn=[0, 0, 0, 1],
+            pw=pw, ph=ph, pn=pn, out_w=wo, out_h=ho, n_img=n, m_total=n_total, n_total=m_total, bn=bn,
+            num_taps=len(taps), tap_off=taps, s_m=s_n, s_t=s_t, s_n=s_m, tap_on_a=1)
+    bn = 128 if n_total % 128 == 0 else 64
     return WgradPlan(
         a_rank=4, a_dim=[co_c, wo, ho, n], a_stride=[e, co_c * e, wo * co_c * e, ho * wo * co_c * e],
         a_box=[64, pw, ph, pn], a_mx=[0, 1, 0, 0], a_my=[0, 0, 1, 0], a_mn=[0, 0, 0, 1],

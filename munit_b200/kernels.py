@@ -62,9 +62,11 @@ def tapgemm(plan, a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, bias=None
     return out
 
 
-def wgrad(plan, a: torch.Tensor, b: torch.Tensor, dw: torch.Tensor, ksplit=0, stages=0):
-    """dw (fp32, +=) <- sum_pix a[pix, m] * b[pix@tap, n] as described by `plan` (geometry.WgradPlan)."""
+def wgrad(plan, dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, ksplit=0, stages=0):
+    """dw (fp32, +=) <- sum_pix dy[pix, co] * x[pix@tap, ci] as described by `plan` (geometry.WgradPlan).
+    A swapped plan (tap_on_a) feeds x as the 128-row A operand and dy as B."""
     _lib.init()
+    a, b = (x, dy) if getattr(plan, "tap_on_a", 0) else (dy, x)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and dw.dtype == torch.float32
     d = WgradDesc()
     d.a, d.a_rank = a.data_ptr(), plan.a_rank
@@ -88,7 +90,7 @@ def wgrad(plan, a: torch.Tensor, b: torch.Tensor, dw: torch.Tensor, ksplit=0, st
         for i in range(5):
             d.tap_off[t][i] = off[i] if i < len(off) else 0
     d.dw, d.s_m, d.s_t, d.s_n = dw.data_ptr(), plan.s_m, plan.s_t, plan.s_n
-    d.ksplit, d.stages = ksplit, stages
+    d.ksplit, d.stages, d.tap_on_a = ksplit, stages, int(getattr(plan, "tap_on_a", 0))
     check(lib.munit_wgrad(C.byref(d), _stream()), "munit_wgrad")
     _count()
     return dw

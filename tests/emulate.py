@@ -47,18 +47,23 @@ def tapgemm(plan, a_flat, b_mat, out_flat, bias=None, act="none"):
     return out_flat
 
 
-def wgrad(plan, a_flat, b_flat, dw_flat):
+def wgrad(plan, dy_flat, x_flat, dw_flat):
+    """(dy, x) as in kernels.wgrad: a swapped plan (tap_on_a) uses x as the A operand and dy as B."""
     p = plan
+    a_flat, b_flat = (x_flat, dy_flat) if getattr(p, "tap_on_a", 0) else (dy_flat, x_flat)
     n_i, y_i, x_i = torch.meshgrid(torch.arange(p.n_img), torch.arange(p.out_h), torch.arange(p.out_w), indexing="ij")
     n_i, y_i, x_i = n_i.reshape(-1), y_i.reshape(-1), x_i.reshape(-1)
-    ca = [x_i * p.a_mx[d] + y_i * p.a_my[d] + n_i * p.a_mn[d] for d in range(1, p.a_rank)]
     m_pad = ((p.m_total + 127) // 128) * 128
-    A = _gather_a(a_flat, p.a_rank, p.a_dim, p.a_stride, ca, 0, m_pad)  # [P, M]
     n_pad = ((p.n_total + p.bn - 1) // p.bn) * p.bn
+    on_a = getattr(p, "tap_on_a", 0)
     for t in range(p.num_taps):
         off = p.tap_off[t]
-        cb = [x_i * p.b_mx[d] + y_i * p.b_my[d] + n_i * p.b_mn[d] + off[d] for d in range(1, p.b_rank)]
-        B = _gather_a(b_flat, p.b_rank, p.b_dim, p.b_stride, cb, off[0], n_pad)  # [P, N]
+        oa = off if on_a else [0] * 5
+        ob = [0] * 5 if on_a else off
+        ca = [x_i * p.a_mx[d] + y_i * p.a_my[d] + n_i * p.a_mn[d] + oa[d] for d in range(1, p.a_rank)]
+        A = _gather_a(a_flat, p.a_rank, p.a_dim, p.a_stride, ca, oa[0], m_pad)  # [P, M]
+        cb = [x_i * p.b_mx[d] + y_i * p.b_my[d] + n_i * p.b_mn[d] + ob[d] for d in range(1, p.b_rank)]
+        B = _gather_a(b_flat, p.b_rank, p.b_dim, p.b_stride, cb, ob[0], n_pad)  # [P, N]
         G = A.t() @ B  # [M, N]
         m = torch.arange(p.m_total)
         nn_ = torch.arange(p.n_total)

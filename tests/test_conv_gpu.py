@@ -21,6 +21,8 @@ CASES = [
     (1, 20, 12, 64, 16, 7, 1, 3),
     (5, 4, 4, 512, 64, 1, 1, 0),
     (8, 64, 64, 256, 256, 3, 1, 1),
+    (2, 24, 24, 128, 64, 5, 1, 2),  # swapped wgrad orientation (cout < 128 <= cin)
+    (2, 16, 16, 256, 64, 4, 2, 1),
 ]
 
 

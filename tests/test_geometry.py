@@ -15,6 +15,8 @@ CASES = [
     (1, 4, 4, 128, 64, 4, 2, 1),
     (1, 9, 7, 64, 16, 7, 1, 3),
     (3, 4, 4, 64, 64, 1, 1, 0),
+    (1, 6, 6, 128, 64, 5, 1, 2),  # cout < 128 <= cin: swapped wgrad orientation
+    (1, 8, 8, 128, 64, 4, 2, 1),
 ]
 
 
