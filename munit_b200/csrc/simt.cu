@@ -210,6 +210,7 @@ __device__ __forceinline__ void reduce_nc(Fn fn, float* __restrict__ out2, int h
 #pragma unroll
   for (int e = 0; e < 8; ++e) s0[e] = s1[e] = 0.f;
   if (r < rows)
+#pragma unroll 4
     for (int pix = p0 + r; pix < p1; pix += rows) {
       F8 u, v;
       fn(n, pix, cg, u, v);
@@ -264,8 +265,9 @@ __device__ __forceinline__ void sum_splits_to_smem(const float* __restrict__ par
 
 __global__ void norm_stats_kernel(const bf16* __restrict__ y, float* __restrict__ stats, float* __restrict__ shift,
                                   int hw, int c) {
+  const int cg_own = threadIdx.x % (c / 8);
+  const F8 s = load8(y + ((long long)blockIdx.y * hw) * c + cg_own * 8);  // per-thread constant: hoisted
   auto fn = [&](int n, int pix, int cg, F8& u, F8& v) {
-    const F8 s = load8(y + ((long long)n * hw) * c + cg * 8);
     const F8 x = load8(y + ((long long)n * hw + pix) * c + cg * 8);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -384,22 +386,27 @@ __global__ void norm_finalize_kernel(const float* __restrict__ stats, int splits
   }
 }
 
+// Block = CG channel groups x R rows (256 threads), grid = (pixel splits, N): a thread keeps its (n, channel
+// group) coefficients in registers and walks pixels, so the per-(n,c) vectors are read once per thread.
 template <int UP>
 __global__ void norm_apply_kernel(const bf16* __restrict__ y, const float* __restrict__ a, const float* __restrict__ b,
                                   int relu, const bf16* __restrict__ res, int res_pad, bf16* __restrict__ out,
                                   int out_pad, int n, int h, int w, int c) {
-  const int cg = c / 8;
-  const long long total = (long long)n * h * w * cg;
+  const int cgs = c / 8;
+  const int rows = blockDim.x / cgs;
+  const int g = threadIdx.x % cgs, r = threadIdx.x / cgs;
+  if (r >= rows) return;
+  const int bb = blockIdx.y;
+  const int hw = h * w;
+  const int per = (hw + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * per, p1 = min(hw, p0 + per);
   const int ho = h * UP, wo = w * UP;
   const int hop = ho + 2 * out_pad, wop = wo + 2 * out_pad;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long t = i;
-    const int g = (int)(t % cg); t /= cg;
-    const int x = (int)(t % w); t /= w;
-    const int yy = (int)(t % h);
-    const int bb = (int)(t / h);
-    F8 v = load8(y + i * 8);
-    const F8 fa = loadf8(a + (long long)bb * c + g * 8), fb = loadf8(b + (long long)bb * c + g * 8);
+  const F8 fa = loadf8(a + (long long)bb * c + g * 8), fb = loadf8(b + (long long)bb * c + g * 8);
+#pragma unroll 4
+  for (int pix = p0 + r; pix < p1; pix += rows) {
+    const int yy = pix / w, x = pix - yy * w;
+    F8 v = load8(y + ((long long)bb * hw + pix) * c + g * 8);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float o = fmaf(v.v[e], fa.v[e], fb.v[e]);
@@ -407,9 +414,9 @@ __global__ void norm_apply_kernel(const bf16* __restrict__ y, const float* __res
       v.v[e] = o;
     }
     if (res) {
-      const F8 r = load8(res + (((long long)bb * (h + 2 * res_pad) + yy + res_pad) * (w + 2 * res_pad) + x + res_pad) * c + g * 8);
+      const F8 rr = load8(res + (((long long)bb * (h + 2 * res_pad) + yy + res_pad) * (w + 2 * res_pad) + x + res_pad) * c + g * 8);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v.v[e] += r.v[e];
+      for (int e = 0; e < 8; ++e) v.v[e] += rr.v[e];
     }
     uint4 packed;
     {
@@ -419,15 +426,15 @@ __global__ void norm_apply_kernel(const bf16* __restrict__ y, const float* __res
     }
 #pragma unroll
     for (int uy = 0; uy < UP; ++uy) {
-      int rows[3];
-      const int nr = pad_positions(yy * UP + uy, ho, out_pad, rows);
+      int prow[3];
+      const int nr = pad_positions(yy * UP + uy, ho, out_pad, prow);
 #pragma unroll
       for (int ux = 0; ux < UP; ++ux) {
-        int cols[3];
-        const int nc = pad_positions(x * UP + ux, wo, out_pad, cols);
-        for (int r = 0; r < nr; ++r)
+        int pcol[3];
+        const int nc = pad_positions(x * UP + ux, wo, out_pad, pcol);
+        for (int i = 0; i < nr; ++i)
           for (int q = 0; q < nc; ++q)
-            *reinterpret_cast<uint4*>(out + (((long long)bb * hop + rows[r]) * wop + cols[q]) * c + g * 8) = packed;
+            *reinterpret_cast<uint4*>(out + (((long long)bb * hop + prow[i]) * wop + pcol[q]) * c + g * 8) = packed;
       }
     }
   }
@@ -467,12 +474,12 @@ __global__ void norm_bwd_reduce_kernel(const bf16* __restrict__ g_out, int out_p
                                        const float* __restrict__ mean, const float* __restrict__ rinv,
                                        float* __restrict__ sums, int h, int w, int c) {
   const int hw = h * w;
+  const long long co = (long long)blockIdx.y * c + (threadIdx.x % (c / 8)) * 8;  // this thread's (n, channel group)
+  const F8 fa = loadf8(a + co), fb = loadf8(b + co), fm = loadf8(mean + co), fr = loadf8(rinv + co);
   auto fn = [&](int n, int pix, int cg, F8& u, F8& v) {
     const int yy = pix / w, x = pix - yy * w;
     const F8 g = fold_grad<UP>(g_out, n, yy, x, cg, h, w, c, out_pad);
     const F8 xv = load8(y + ((long long)n * hw + pix) * c + cg * 8);
-    const F8 fa = loadf8(a + (long long)n * c + cg * 8), fb = loadf8(b + (long long)n * c + cg * 8);
-    const F8 fm = loadf8(mean + (long long)n * c + cg * 8), fr = loadf8(rinv + (long long)n * c + cg * 8);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float dz = g.v[e];
@@ -559,19 +566,23 @@ __global__ void norm_bwd_apply_kernel(const bf16* __restrict__ g_out, int out_pa
                                       const float* __restrict__ ca, const float* __restrict__ cb,
                                       const float* __restrict__ cc, bf16* __restrict__ dy, bf16* __restrict__ g_res,
                                       int res_pad, int n, int h, int w, int c) {
-  const int cg = c / 8;
-  const long long total = (long long)n * h * w * cg;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long t = i;
-    const int g = (int)(t % cg); t /= cg;
-    const int x = (int)(t % w); t /= w;
-    const int yy = (int)(t % h);
-    const int bb = (int)(t / h);
+  const int cgs = c / 8;
+  const int rows = blockDim.x / cgs;
+  const int g = threadIdx.x % cgs, r = threadIdx.x / cgs;
+  if (r >= rows) return;
+  const int bb = blockIdx.y;
+  const int hw = h * w;
+  const int per = (hw + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * per, p1 = min(hw, p0 + per);
+  const long long o = (long long)bb * c + g * 8;
+  const F8 fa = loadf8(a + o), fb = loadf8(b + o), fm = loadf8(mean + o), fr = loadf8(rinv + o);
+  const F8 fca = loadf8(ca + o), fcb = loadf8(cb + o), fcc = loadf8(cc + o);
+#pragma unroll 4
+  for (int pix = p0 + r; pix < p1; pix += rows) {
+    const int yy = pix / w, x = pix - yy * w;
     const F8 gr = fold_grad<UP>(g_out, bb, yy, x, g, h, w, c, out_pad);
-    const F8 xv = load8(y + i * 8);
-    const long long o = (long long)bb * c + g * 8;
-    const F8 fa = loadf8(a + o), fb = loadf8(b + o), fm = loadf8(mean + o), fr = loadf8(rinv + o);
-    const F8 fca = loadf8(ca + o), fcb = loadf8(cb + o), fcc = loadf8(cc + o);
+    const long long i8 = ((long long)bb * hw + pix) * c + g * 8;
+    const F8 xv = load8(y + i8);
     F8 d;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -580,7 +591,7 @@ __global__ void norm_bwd_apply_kernel(const bf16* __restrict__ g_out, int out_pa
       const float xh = (xv.v[e] - fm.v[e]) * fr.v[e];
       d.v[e] = fmaf(fca.v[e], dz, fmaf(fcb.v[e], xh, fcc.v[e]));
     }
-    store8(dy + i * 8, d);
+    store8(dy + i8, d);
     if (g_res) store8(g_res + (((long long)bb * (h + 2 * res_pad) + yy + res_pad) * (w + 2 * res_pad) + x + res_pad) * c + g * 8, gr);
   }
 }
@@ -1035,6 +1046,16 @@ inline int reduce_splits(int hw, int c) {
   return s;
 }
 
+// pixel splits for the elementwise norm kernels: ~8 pixels per thread, at most ~8 waves of blocks
+inline int apply_splits(int hw, int c, int n) {
+  const int rows = 256 / (c / 8);
+  int s = (hw + rows * 8 - 1) / (rows * 8);
+  const int cap = (148 * 16 + n - 1) / n;
+  if (s > cap) s = cap;
+  if (s < 1) s = 1;
+  return s;
+}
+
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 #define BF(p) reinterpret_cast<bf16*>(p)
 #define CBF(p) reinterpret_cast<const bf16*>(p)
@@ -1120,14 +1141,14 @@ int munit_norm_finalize(const float* stats, const float* shift, int mode, const 
 
 int munit_norm_apply(const void* y, const float* a, const float* b, int relu, const void* residual, int res_pad,
                      void* out_act, int out_pad, int upsample, int n, int h, int w, int c, void* stream) {
-  if (c % 8) return mb_fail(MUNIT_ERR_ARG, "norm_apply: c %% 8");
-  const long long total = (long long)n * h * w * (c / 8);
+  if (c % 8 || c / 8 > 256 || 256 % (c / 8)) return mb_fail(MUNIT_ERR_ARG, "norm_apply: channels %d", c);
+  dim3 grid(apply_splits(h * w, c, n), n);
   if (upsample == 2)
-    norm_apply_kernel<2><<<grid_for(total), 256, 0, ST(stream)>>>(CBF(y), a, b, relu, CBF(residual), res_pad,
-                                                                   BF(out_act), out_pad, n, h, w, c);
+    norm_apply_kernel<2><<<grid, 256, 0, ST(stream)>>>(CBF(y), a, b, relu, CBF(residual), res_pad, BF(out_act),
+                                                        out_pad, n, h, w, c);
   else if (upsample == 1)
-    norm_apply_kernel<1><<<grid_for(total), 256, 0, ST(stream)>>>(CBF(y), a, b, relu, CBF(residual), res_pad,
-                                                                   BF(out_act), out_pad, n, h, w, c);
+    norm_apply_kernel<1><<<grid, 256, 0, ST(stream)>>>(CBF(y), a, b, relu, CBF(residual), res_pad, BF(out_act),
+                                                        out_pad, n, h, w, c);
   else
     return mb_fail(MUNIT_ERR_ARG, "norm_apply: upsample must be 1 or 2");
   MB_CHECK_LAUNCH("norm_apply");
@@ -1164,15 +1185,14 @@ int munit_norm_bwd_apply(const void* g_out, int out_pad, int upsample, const voi
                          int relu, const float* mean, const float* rinv, const float* ca, const float* cb,
                          const float* cc, void* dy, void* g_res, int res_pad, int n, int h, int w, int c,
                          void* stream) {
-  const long long total = (long long)n * h * w * (c / 8);
+  if (c % 8 || c / 8 > 256 || 256 % (c / 8)) return mb_fail(MUNIT_ERR_ARG, "norm_bwd_apply: channels %d", c);
+  dim3 grid(apply_splits(h * w, c, n), n);
   if (upsample == 2)
-    norm_bwd_apply_kernel<2><<<grid_for(total), 256, 0, ST(stream)>>>(CBF(g_out), out_pad, CBF(y), a, b, relu, mean,
-                                                                       rinv, ca, cb, cc, BF(dy), BF(g_res), res_pad, n,
-                                                                       h, w, c);
+    norm_bwd_apply_kernel<2><<<grid, 256, 0, ST(stream)>>>(CBF(g_out), out_pad, CBF(y), a, b, relu, mean, rinv, ca, cb,
+                                                            cc, BF(dy), BF(g_res), res_pad, n, h, w, c);
   else
-    norm_bwd_apply_kernel<1><<<grid_for(total), 256, 0, ST(stream)>>>(CBF(g_out), out_pad, CBF(y), a, b, relu, mean,
-                                                                       rinv, ca, cb, cc, BF(dy), BF(g_res), res_pad, n,
-                                                                       h, w, c);
+    norm_bwd_apply_kernel<1><<<grid, 256, 0, ST(stream)>>>(CBF(g_out), out_pad, CBF(y), a, b, relu, mean, rinv, ca, cb,
+                                                            cc, BF(dy), BF(g_res), res_pad, n, h, w, c);
   MB_CHECK_LAUNCH("norm_bwd_apply");
   return MUNIT_OK;
 }
