@@ -239,26 +239,28 @@ __device__ __forceinline__ void reduce_nc(Fn fn, float* __restrict__ out2, int h
     dst[1] = b;
   }
 }
-// Sum the split partials of sample n for every channel into shared memory (sm[ch*2+{0,1}]), one warp per
-// channel, lanes striding over splits, fixed shuffle tree: deterministic.  Ends with __syncthreads().
+// Sum the split partials of sample n for every channel into shared memory (sm[ch*2+{0,1}]): one thread per
+// channel (coalesced float2 reads), splits added in index order -> deterministic.  Ends with __syncthreads().
 __device__ __forceinline__ void sum_splits_to_smem(const float* __restrict__ part, int n, int splits, int c,
                                                    double* __restrict__ sm) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int ch = warp; ch < c; ch += nwarps) {
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    const float2* p = reinterpret_cast<const float2*>(part) + (long long)n * splits * c + ch;
     double s1 = 0.0, s2 = 0.0;
-    for (int s = lane; s < splits; s += 32) {
-      const float2 p = *reinterpret_cast<const float2*>(part + (((long long)n * splits + s) * c + ch) * 2);
-      s1 += (double)p.x;
-      s2 += (double)p.y;
+    int s = 0;
+    for (; s + 4 <= splits; s += 4) {
+      const float2 v0 = p[(long long)(s + 0) * c], v1 = p[(long long)(s + 1) * c];
+      const float2 v2 = p[(long long)(s + 2) * c], v3 = p[(long long)(s + 3) * c];
+      s1 += (double)v0.x; s2 += (double)v0.y;
+      s1 += (double)v1.x; s2 += (double)v1.y;
+      s1 += (double)v2.x; s2 += (double)v2.y;
+      s1 += (double)v3.x; s2 += (double)v3.y;
     }
-    for (int o = 16; o > 0; o >>= 1) {
-      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    for (; s < splits; ++s) {
+      const float2 v = p[(long long)s * c];
+      s1 += (double)v.x; s2 += (double)v.y;
     }
-    if (lane == 0) {
-      sm[ch * 2] = s1;
-      sm[ch * 2 + 1] = s2;
-    }
+    sm[ch * 2] = s1;
+    sm[ch * 2 + 1] = s2;
   }
   __syncthreads();
 }
@@ -440,29 +442,42 @@ __global__ void norm_apply_kernel(const bf16* __restrict__ y, const float* __res
   }
 }
 
-// gradient w.r.t. the unpadded, un-upsampled pixel: sum of g_out over every position that copied it
+// gradient w.r.t. the unpadded, un-upsampled pixel: sum of g_out over every position that copied it.
+// Fast path: the UP x UP interior positions (always present, branch-free loads the compiler can pipeline);
+// only pixels within `pad` of the border additionally gather their mirrored halo copies.
 template <int UP>
 __device__ __forceinline__ F8 fold_grad(const bf16* __restrict__ g_out, int bb, int yy, int x, int g, int h, int w,
                                         int c, int pad) {
   const int ho = h * UP, wo = w * UP;
   const int hop = ho + 2 * pad, wop = wo + 2 * pad;
-  F8 acc;
+  const bf16* base = g_out + (long long)bb * hop * wop * c + g * 8;
+  F8 acc = load8(base + ((long long)(yy * UP + pad) * wop + x * UP + pad) * c);
+  if (UP == 2) {
+    const F8 t1 = load8(base + ((long long)(yy * 2 + pad) * wop + x * 2 + 1 + pad) * c);
+    const F8 t2 = load8(base + ((long long)(yy * 2 + 1 + pad) * wop + x * 2 + pad) * c);
+    const F8 t3 = load8(base + ((long long)(yy * 2 + 1 + pad) * wop + x * 2 + 1 + pad) * c);
 #pragma unroll
-  for (int e = 0; e < 8; ++e) acc.v[e] = 0.f;
+    for (int e = 0; e < 8; ++e) acc.v[e] += t1.v[e] + t2.v[e] + t3.v[e];
+  }
+  const int r0 = yy * UP, c0 = x * UP;
+  const bool border = pad > 0 && (r0 <= pad || c0 <= pad || r0 + UP - 1 >= ho - 1 - pad || c0 + UP - 1 >= wo - 1 - pad);
+  if (border) {
 #pragma unroll
-  for (int uy = 0; uy < UP; ++uy) {
-    int rows[3];
-    const int nr = pad_positions(yy * UP + uy, ho, pad, rows);
+    for (int uy = 0; uy < UP; ++uy) {
+      int rows[3];
+      const int nr = pad_positions(r0 + uy, ho, pad, rows);
 #pragma unroll
-    for (int ux = 0; ux < UP; ++ux) {
-      int cols[3];
-      const int nc = pad_positions(x * UP + ux, wo, pad, cols);
-      for (int r = 0; r < nr; ++r)
-        for (int q = 0; q < nc; ++q) {
-          const F8 t = load8(g_out + (((long long)bb * hop + rows[r]) * wop + cols[q]) * c + g * 8);
+      for (int ux = 0; ux < UP; ++ux) {
+        int cols[3];
+        const int nc = pad_positions(c0 + ux, wo, pad, cols);
+        for (int r = 0; r < nr; ++r)
+          for (int q = 0; q < nc; ++q) {
+            if (r == 0 && q == 0) continue;  // the interior copy is already in acc
+            const F8 t = load8(base + ((long long)rows[r] * wop + cols[q]) * c);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc.v[e] += t.v[e];
-        }
+            for (int e = 0; e < 8; ++e) acc.v[e] += t.v[e];
+          }
+      }
     }
   }
   return acc;
