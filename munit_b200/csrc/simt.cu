@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/munit_b200.h"
 #include "common.h"
@@ -311,6 +312,95 @@ __global__ void colsum_kernel(const bf16* __restrict__ dy, float* __restrict__ o
     float a = 0.f;
     for (int rr = 0; rr < rows; ++rr) a += red[rr * c + ch];
     atomicAdd(out + ch, a);
+  }
+}
+
+// IN / AdaIN finalize, parallel over channels: grid (C/32, N), 256 threads = 32 channels x 8 split lanes; the 8
+// lane partials are added in lane order (deterministic).
+__global__ void norm_finalize_nc_kernel(const float* __restrict__ stats, int splits, const float* __restrict__ shift,
+                                        int adain, const float* __restrict__ p_w, const float* __restrict__ p_b,
+                                        long long ldw, float eps, float* __restrict__ mean, float* __restrict__ rinv,
+                                        float* __restrict__ a, float* __restrict__ b, int hw, int c) {
+  __shared__ double sh[8][32][2];
+  const int n = blockIdx.y;
+  const int ch = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int lane = threadIdx.x >> 5;  // split lane 0..7
+  double s1 = 0.0, s2 = 0.0;
+  if (ch < c) {
+    const float2* p = reinterpret_cast<const float2*>(stats) + (long long)n * splits * c + ch;
+    for (int s = lane; s < splits; s += 8) {
+      const float2 v = p[(long long)s * c];
+      s1 += (double)v.x;
+      s2 += (double)v.y;
+    }
+  }
+  sh[lane][threadIdx.x & 31][0] = s1;
+  sh[lane][threadIdx.x & 31][1] = s2;
+  __syncthreads();
+  if (lane == 0 && ch < c) {
+    double a1 = 0.0, a2 = 0.0;
+    for (int l = 0; l < 8; ++l) {
+      a1 += sh[l][threadIdx.x][0];
+      a2 += sh[l][threadIdx.x][1];
+    }
+    const double cnt = (double)hw;
+    const long long i = (long long)n * c + ch;
+    const double m1 = a1 / cnt;
+    double var = a2 / cnt - m1 * m1;  // biased (F.batch_norm / InstanceNorm2d)
+    if (var < 0.0) var = 0.0;
+    const float mu = (float)((double)shift[i] + m1);
+    const float ri = (float)(1.0 / sqrt(var + (double)eps));
+    float wv = 1.f, bv = 0.f;
+    if (adain) {
+      wv = p_w[(long long)n * ldw + ch];
+      bv = p_b[(long long)n * ldw + ch];
+    }
+    const float aa = ri * wv;
+    mean[i] = mu;
+    rinv[i] = ri;
+    a[i] = aa;
+    b[i] = bv - mu * aa;
+  }
+}
+// IN / AdaIN backward finalize, same mapping.
+__global__ void norm_bwd_finalize_nc_kernel(const float* __restrict__ sums, int splits, int adain,
+                                            const float* __restrict__ p_w, long long ldw,
+                                            const float* __restrict__ rinv, float* __restrict__ ca,
+                                            float* __restrict__ cb, float* __restrict__ cc, float* __restrict__ g_w,
+                                            float* __restrict__ g_b, long long ldg, int hw, int c) {
+  __shared__ double sh[8][32][2];
+  const int n = blockIdx.y;
+  const int ch = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int lane = threadIdx.x >> 5;
+  double s1 = 0.0, s2 = 0.0;
+  if (ch < c) {
+    const float2* p = reinterpret_cast<const float2*>(sums) + (long long)n * splits * c + ch;
+    for (int s = lane; s < splits; s += 8) {
+      const float2 v = p[(long long)s * c];
+      s1 += (double)v.x;
+      s2 += (double)v.y;
+    }
+  }
+  sh[lane][threadIdx.x & 31][0] = s1;
+  sh[lane][threadIdx.x & 31][1] = s2;
+  __syncthreads();
+  if (lane == 0 && ch < c) {
+    double a1 = 0.0, a2 = 0.0;
+    for (int l = 0; l < 8; ++l) {
+      a1 += sh[l][threadIdx.x][0];
+      a2 += sh[l][threadIdx.x][1];
+    }
+    const double cnt = (double)hw;
+    const long long i = (long long)n * c + ch;
+    const float wv = adain ? p_w[(long long)n * ldw + ch] : 1.f;
+    const float A = rinv[i] * wv;
+    ca[i] = A;
+    cc[i] = (float)(-(double)A * a1 / cnt);
+    cb[i] = (float)(-(double)A * a2 / cnt);
+    if (adain) {
+      if (g_w) g_w[(long long)n * ldg + ch] = (float)a2;
+      if (g_b) g_b[(long long)n * ldg + ch] = (float)a1;
+    }
   }
 }
 
@@ -1054,18 +1144,29 @@ inline int grid_for(long long work, int threads = 256, int max_blocks = 148 * 16
   return (int)b;
 }
 inline int reduce_splits(int hw, int c) {
+  // ~4 pixels per thread: these layers are small (16 MB), parallelism beats per-thread amortisation
   const int rows = 256 / (c / 8);
-  int s = (hw + rows * 16 - 1) / (rows * 16);
+  static int ppt = 0;
+  if (!ppt) {
+    const char* e = getenv("MUNIT_RSPLIT");
+    ppt = e ? atoi(e) : 16;  // A/B on the full step: 16 px/thread beats 4/8/32 (profiles/r1_simt.md)
+  }
+  int s = (hw + rows * ppt - 1) / (rows * ppt);
   if (s < 1) s = 1;
-  if (s > 1024) s = 1024;
+  if (s > 512) s = 512;
   return s;
 }
 
 // pixel splits for the elementwise norm kernels: ~8 pixels per thread, at most ~8 waves of blocks
 inline int apply_splits(int hw, int c, int n) {
   const int rows = 256 / (c / 8);
-  int s = (hw + rows * 8 - 1) / (rows * 8);
-  const int cap = (148 * 16 + n - 1) / n;
+  static int ppt = 0;
+  if (!ppt) {
+    const char* e = getenv("MUNIT_ASPLIT");
+    ppt = e ? atoi(e) : 8;
+  }
+  int s = (hw + rows * ppt - 1) / (rows * ppt);
+  const int cap = (148 * 24 + n - 1) / n;
   if (s > cap) s = cap;
   if (s < 1) s = 1;
   return s;
@@ -1148,6 +1249,13 @@ int munit_norm_finalize(const float* stats, const float* shift, int mode, const 
                         int64_t ldw, float eps, float* mean, float* rinv, float* a, float* b, int n, int hw, int c,
                         void* stream) {
   if (mode != MUNIT_NORM_IN && (!p_w || !p_b)) return mb_fail(MUNIT_ERR_ARG, "norm_finalize: missing affine params");
+  if (mode != MUNIT_NORM_LN) {
+    dim3 grid((c + 31) / 32, n);
+    norm_finalize_nc_kernel<<<grid, 256, 0, ST(stream)>>>(stats, reduce_splits(hw, c), shift, mode == MUNIT_NORM_ADAIN,
+                                                          p_w, p_b, ldw, eps, mean, rinv, a, b, hw, c);
+    MB_CHECK_LAUNCH("norm_finalize_nc");
+    return MUNIT_OK;
+  }
   norm_finalize_kernel<<<n, 256, sizeof(double) * 2 * c, ST(stream)>>>(stats, reduce_splits(hw, c), shift, mode, p_w, p_b, ldw, eps, mean,
                                                   rinv, a, b, hw, c);
   MB_CHECK_LAUNCH("norm_finalize");
@@ -1190,6 +1298,13 @@ int munit_norm_bwd_reduce(const void* g_out, int out_pad, int upsample, const vo
 int munit_norm_bwd_finalize(const float* sums, int mode, const float* p_w, int64_t ldw, const float* rinv, float eps,
                             float* ca, float* cb, float* cc, float* g_w, float* g_b, int64_t ldg, int n, int hw, int c,
                             void* stream) {
+  if (mode != MUNIT_NORM_LN) {
+    dim3 grid((c + 31) / 32, n);
+    norm_bwd_finalize_nc_kernel<<<grid, 256, 0, ST(stream)>>>(sums, reduce_splits(hw, c), mode == MUNIT_NORM_ADAIN, p_w,
+                                                              ldw, rinv, ca, cb, cc, g_w, g_b, ldg, hw, c);
+    MB_CHECK_LAUNCH("norm_bwd_finalize_nc");
+    return MUNIT_OK;
+  }
   norm_bwd_finalize_kernel<<<n, 256, sizeof(double) * 2 * c, ST(stream)>>>(sums, reduce_splits(hw, c), mode, p_w, ldw, rinv, eps, ca, cb, cc,
                                                       g_w, g_b, ldg, hw, c);
   MB_CHECK_LAUNCH("norm_bwd_finalize");
