@@ -27,8 +27,8 @@ METRIC = "MUNIT train steps/sec (gen+dis) 256^2"
 UNIT = "steps/s (1 step = dis_update+gen_update on 8 image pairs)"
 
 
-def workload_name(batch, hw):
-    return f"config_256-core train step (dis_update+gen_update), batch {batch}/GPU, {hw}x{hw}"
+def workload_name(batch, hw, hd=False):
+    return f"config_{'HD' if hd else '256'}-core train step (dis_update+gen_update), batch {batch}/GPU, {hw}x{hw}"
 
 
 def load_cfg(hd=False):
@@ -150,7 +150,7 @@ def run_reference_arm(args):
     line = dict(impl="reference", metric=METRIC, value=v, unit=UNIT, n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1000.0 / v, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32", data="synthetic",
-                config=dict(workload=workload_name(args.batch, hw), optimizer=cfg["optimizer"]),
+                config=dict(workload=workload_name(args.batch, hw, args.hd), optimizer=cfg["optimizer"]),
                 cpu_baseline=dict(value=v, unit=UNIT, cores=os.cpu_count(), kind=kind, sample=sample),
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
@@ -300,7 +300,7 @@ def run_b200(args):
         metric=METRIC, value=steps_per_s, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
         data="synthetic",
-        config=dict(workload=workload_name(args.batch, hw),
+        config=dict(workload=workload_name(args.batch, hw, args.hd),
                     global_batch=args.batch * world, gen_state=cfg["gen_state"], guided=cfg["guided"],
                     optimizer=cfg["optimizer"], parallelism=f"dp{world}", cuda_graph=not args.no_graph,
                     l2="per-step working set (several GB of bf16 activations) >> 126 MB L2; no explicit flush"),

@@ -583,10 +583,26 @@ class MsImageDis(nn.Module):
         return self._run(x, 0.0)[0]
 
     def calc_dis_loss(self, input_fake, input_real):
-        """networks.py:79-101 (lsgan): sum_scales mean(out_fake^2) + mean((out_real-1)^2)."""
-        _, l0 = self._run(input_fake, 0.0)
-        _, l1 = self._run(input_real, 1.0)
-        return (l0 + l1).squeeze(0)
+        """networks.py:79-101 (lsgan): sum_scales mean(out_fake^2) + mean((out_real-1)^2).
+        Fake and real share the weights, so they run as ONE batch of 2B through every scale (half the launches,
+        twice the rows per GEMM); only the LSGAN heads see the two halves with their own targets."""
+        if input_fake.shape != input_real.shape:
+            _, l0 = self._run(input_fake, 0.0)
+            _, l1 = self._run(input_real, 1.0)
+            return (l0 + l1).squeeze(0)
+        b = input_fake.shape[0]
+        x = torch.cat([input_fake, input_real], 0)
+        loss = None
+        for s, model in enumerate(self.cnns):
+            mods = list(model)
+            a = run_chain(mods[:-1], x, 0)
+            head = mods[-1]
+            for half, target in ((a.t[:b], 0.0), (a.t[b:], 1.0)):
+                _, l = ops.DisHeadFn.apply(half, head.weight, head.bias, target, 1.0)
+                loss = l if loss is None else loss + l
+            if s + 1 < len(self.cnns):
+                x = ops.AvgPoolFn.apply(x)
+        return loss.squeeze(0)
 
     def calc_gen_loss(self, input_fake, frozen: bool = False):
         """networks.py:103-115 (lsgan): sum_scales mean((out_fake-1)^2).  `frozen` skips the (wasted)
