@@ -134,6 +134,34 @@ class MUNIT_Trainer(nn.Module):
             return (self.gen_a if which == "a" else self.gen_b).decode(c, s)
         return self.gen.decode(c, s, 1 if which == "a" else 2)
 
+    def _gen_forward_batched(self, x_a, x_b, s_a, s_b):
+        """The first three stages of gen_update (trainer.py:400-419) for the shared-style generator, with calls
+        that use the SAME weights on independent inputs merged into one batch: the style encoder sees [x_a; x_b]
+        and [x_ba; x_ab], each decoder sees its within-domain and cross-domain pair together.  Every norm is per
+        sample, so the results are those of the reference's one-call-per-tensor sequence."""
+        g = self.gen
+        b = x_a.shape[0]
+
+        def cat_act(u, v):
+            return Act(torch.cat([u.t, v.t], 0), u.pad)
+
+        c_a = g.enc1_content.forward_act(x_a, 1)
+        c_b = g.enc2_content.forward_act(x_b, 1)
+        s_both = g.enc_style(torch.cat([x_a, x_b], 0))
+        s_a_prime, s_b_prime = s_both[:b], s_both[b:]
+        sty_a = s_a if self.guided == 0 else s_a_prime   # style used for the cross-domain decode into a
+        sty_b = s_b if self.guided == 0 else s_b_prime
+        out1 = g.decode(cat_act(c_a, c_b), torch.cat([s_a_prime, sty_a], 0), 1)   # [x_a_recon; x_ba]
+        out2 = g.decode(cat_act(c_b, c_a), torch.cat([s_b_prime, sty_b], 0), 2)   # [x_b_recon; x_ab]
+        x_a_recon, x_ba = out1[:b], out1[b:]
+        x_b_recon, x_ab = out2[:b], out2[b:]
+        c_b_recon = g.enc1_content.forward_act(x_ba, 1)
+        c_a_recon = g.enc2_content.forward_act(x_ab, 1)
+        s_re = g.enc_style(torch.cat([x_ba, x_ab], 0))
+        s_a_recon, s_b_recon = s_re[:b], s_re[b:]
+        return (c_a, s_a_prime, c_b, s_b_prime, x_a_recon, x_b_recon, x_ba, x_ab, c_b_recon, s_a_recon, c_a_recon,
+                s_b_recon)
+
     def _style_noise(self, x_a, x_b, s_a, s_b):
         """Host-generator draws in the reference's order (trainer.py:366-367,1146-1147) unless supplied."""
         if s_a is None:
@@ -170,26 +198,30 @@ class MUNIT_Trainer(nn.Module):
             raise NotImplementedError("synthetic-pair losses are a 'next' item (SURVEY.md s8(f).4)")
         self.gen_opt.zero_grad()
         s_a, s_b = self._style_noise(x_a, x_b, s_a, s_b)
-        # encode
-        c_a, s_a_prime = self._enc("a", x_a)
-        c_b, s_b_prime = self._enc("b", x_b)
-        # decode (within domain)
-        x_a_recon = self._dec("a", c_a, s_a_prime)
-        x_b_recon = self._dec("b", c_b, s_b_prime)
-        # decode (cross domain)
-        if self.guided == 0:
-            x_ba = self._dec("a", c_b, s_a)
-            x_ab = self._dec("b", c_a, s_b)
-        elif self.guided == 1:
-            x_ba = self._dec("a", c_b, s_a_prime)
-            x_ab = self._dec("b", c_a, s_b_prime)
-        else:
-            print("self.guided unknown value:", self.guided)
-        # encode again
-        c_b_recon, s_a_recon = self._enc("a", x_ba)
-        c_a_recon, s_b_recon = self._enc("b", x_ab)
-        # decode again (if needed)
         cyc = hyperparameters["recon_x_cyc_w"] > 0
+        if self.gen_state == 1 and x_a.shape == x_b.shape:
+            (c_a, s_a_prime, c_b, s_b_prime, x_a_recon, x_b_recon, x_ba, x_ab, c_b_recon, s_a_recon, c_a_recon,
+             s_b_recon) = self._gen_forward_batched(x_a, x_b, s_a, s_b)
+        else:
+            # encode
+            c_a, s_a_prime = self._enc("a", x_a)
+            c_b, s_b_prime = self._enc("b", x_b)
+            # decode (within domain)
+            x_a_recon = self._dec("a", c_a, s_a_prime)
+            x_b_recon = self._dec("b", c_b, s_b_prime)
+            # decode (cross domain)
+            if self.guided == 0:
+                x_ba = self._dec("a", c_b, s_a)
+                x_ab = self._dec("b", c_a, s_b)
+            elif self.guided == 1:
+                x_ba = self._dec("a", c_b, s_a_prime)
+                x_ab = self._dec("b", c_a, s_b_prime)
+            else:
+                print("self.guided unknown value:", self.guided)
+            # encode again
+            c_b_recon, s_a_recon = self._enc("a", x_ba)
+            c_a_recon, s_b_recon = self._enc("b", x_ab)
+        # decode again (if needed)
         x_aba = self._dec("a", c_a_recon, s_a_prime) if cyc else None
         x_bab = self._dec("b", c_b_recon, s_b_prime) if cyc else None
 
