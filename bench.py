@@ -38,6 +38,15 @@ def load_cfg(hd=False):
     return cfg
 
 
+def profiled_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return d["dram_bytes_read_per_launch"] + d["dram_bytes_write_per_launch"], d["kernel"]
+    return None, None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -310,7 +319,8 @@ def run_b200(args):
         clocks=clocks,
         roofline=dict(bound="tensor", kernel="tapgemm_kernel<BN> (conv fwd + dgrad, tcgen05)", achieved=ach,
                       peak=peaks["tflops"], unit="TFLOP/s", frac=ach / peaks["tflops"] if peaks["tflops"] else None,
-                      traffic=None, peak_source=peaks["src"], launches_per_step=tg["launches"],
+                      traffic=profiled_traffic()[0], traffic_kernel=profiled_traffic()[1],
+                      peak_source=peaks["src"], launches_per_step=tg["launches"],
                       kernel_ms_per_step=tg["ms"],
                       wgrad=dict(achieved=ach_w, launches_per_step=wg["launches"], kernel_ms_per_step=wg["ms"]),
                       step_algorithmic_tflop=algo_tflop_step,

@@ -211,7 +211,7 @@ __device__ __forceinline__ void reduce_nc(Fn fn, float* __restrict__ out2, int h
 #pragma unroll
   for (int e = 0; e < 8; ++e) s0[e] = s1[e] = 0.f;
   if (r < rows)
-#pragma unroll 4
+#pragma unroll 2
     for (int pix = p0 + r; pix < p1; pix += rows) {
       F8 u, v;
       fn(n, pix, cg, u, v);
@@ -394,6 +394,7 @@ __global__ void norm_bwd_finalize_nc_kernel(const float* __restrict__ sums, int 
     const long long i = (long long)n * c + ch;
     const float wv = adain ? p_w[(long long)n * ldw + ch] : 1.f;
     const float A = rinv[i] * wv;
+    a2 *= (double)rinv[i];  // sum dz*(x-mean) -> sum dz*xhat
     ca[i] = A;
     cc[i] = (float)(-(double)A * a1 / cnt);
     cb[i] = (float)(-(double)A * a2 / cnt);
@@ -495,7 +496,7 @@ __global__ void norm_apply_kernel(const bf16* __restrict__ y, const float* __res
   const int ho = h * UP, wo = w * UP;
   const int hop = ho + 2 * out_pad, wop = wo + 2 * out_pad;
   const F8 fa = loadf8(a + (long long)bb * c + g * 8), fb = loadf8(b + (long long)bb * c + g * 8);
-#pragma unroll 4
+#pragma unroll 2
   for (int pix = p0 + r; pix < p1; pix += rows) {
     const int yy = pix / w, x = pix - yy * w;
     F8 v = load8(y + ((long long)bb * hw + pix) * c + g * 8);
@@ -573,14 +574,17 @@ __device__ __forceinline__ F8 fold_grad(const bf16* __restrict__ g_out, int bb, 
   return acc;
 }
 
+// sums = {sum dz, sum dz*(x - mean)}; the finalize kernels multiply the second by rinv (keeps this loop at 3
+// coefficient vectors so that four blocks fit per SM).
 template <int UP>
-__global__ void norm_bwd_reduce_kernel(const bf16* __restrict__ g_out, int out_pad, const bf16* __restrict__ y,
+__global__ void __launch_bounds__(256, 3)
+norm_bwd_reduce_kernel(const bf16* __restrict__ g_out, int out_pad, const bf16* __restrict__ y,
                                        const float* __restrict__ a, const float* __restrict__ b, int relu,
                                        const float* __restrict__ mean, const float* __restrict__ rinv,
                                        float* __restrict__ sums, int h, int w, int c) {
   const int hw = h * w;
   const long long co = (long long)blockIdx.y * c + (threadIdx.x % (c / 8)) * 8;  // this thread's (n, channel group)
-  const F8 fa = loadf8(a + co), fb = loadf8(b + co), fm = loadf8(mean + co), fr = loadf8(rinv + co);
+  const F8 fa = loadf8(a + co), fb = loadf8(b + co), fm = loadf8(mean + co);
   auto fn = [&](int n, int pix, int cg, F8& u, F8& v) {
     const int yy = pix / w, x = pix - yy * w;
     const F8 g = fold_grad<UP>(g_out, n, yy, x, cg, h, w, c, out_pad);
@@ -590,7 +594,7 @@ __global__ void norm_bwd_reduce_kernel(const bf16* __restrict__ g_out, int out_p
       float dz = g.v[e];
       if (relu && fmaf(xv.v[e], fa.v[e], fb.v[e]) <= 0.f) dz = 0.f;
       u.v[e] = dz;
-      v.v[e] = dz * (xv.v[e] - fm.v[e]) * fr.v[e];
+      v.v[e] = dz * (xv.v[e] - fm.v[e]);
     }
   };
   reduce_nc(fn, sums, hw, c);
@@ -606,6 +610,8 @@ __global__ void norm_bwd_finalize_kernel(const float* __restrict__ sums, int spl
   const double cnt = (double)hw;
   extern __shared__ double ssum[];  // [c][2]
   sum_splits_to_smem(sums, n, splits, c, ssum);
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) ssum[ch * 2 + 1] *= (double)rinv[(long long)n * c + ch];
+  __syncthreads();
   if (mode == MUNIT_NORM_LN) {
     __shared__ double sh[2][32];
     __shared__ double tot[2];
@@ -665,7 +671,8 @@ __global__ void norm_bwd_finalize_kernel(const float* __restrict__ sums, int spl
 }
 
 template <int UP>
-__global__ void norm_bwd_apply_kernel(const bf16* __restrict__ g_out, int out_pad, const bf16* __restrict__ y,
+__global__ void __launch_bounds__(256, 3)
+norm_bwd_apply_kernel(const bf16* __restrict__ g_out, int out_pad, const bf16* __restrict__ y,
                                       const float* __restrict__ a, const float* __restrict__ b, int relu,
                                       const float* __restrict__ mean, const float* __restrict__ rinv,
                                       const float* __restrict__ ca, const float* __restrict__ cb,
@@ -680,9 +687,17 @@ __global__ void norm_bwd_apply_kernel(const bf16* __restrict__ g_out, int out_pa
   const int per = (hw + gridDim.x - 1) / gridDim.x;
   const int p0 = blockIdx.x * per, p1 = min(hw, p0 + per);
   const long long o = (long long)bb * c + g * 8;
-  const F8 fa = loadf8(a + o), fb = loadf8(b + o), fm = loadf8(mean + o), fr = loadf8(rinv + o);
-  const F8 fca = loadf8(ca + o), fcb = loadf8(cb + o), fcc = loadf8(cc + o);
-#pragma unroll 4
+  const F8 fa = loadf8(a + o), fb = loadf8(b + o), fca = loadf8(ca + o);
+  F8 k1, k0;  // dx = ca*dz + cb*xhat + cc = ca*dz + k1*x + k0 with k1 = cb*rinv, k0 = cc - k1*mean
+  {
+    const F8 fm = loadf8(mean + o), fr = loadf8(rinv + o), fcb = loadf8(cb + o), fcc = loadf8(cc + o);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      k1.v[e] = fcb.v[e] * fr.v[e];
+      k0.v[e] = fcc.v[e] - k1.v[e] * fm.v[e];
+    }
+  }
+#pragma unroll 2
   for (int pix = p0 + r; pix < p1; pix += rows) {
     const int yy = pix / w, x = pix - yy * w;
     const F8 gr = fold_grad<UP>(g_out, bb, yy, x, g, h, w, c, out_pad);
@@ -693,8 +708,7 @@ __global__ void norm_bwd_apply_kernel(const bf16* __restrict__ g_out, int out_pa
     for (int e = 0; e < 8; ++e) {
       float dz = gr.v[e];
       if (relu && fmaf(xv.v[e], fa.v[e], fb.v[e]) <= 0.f) dz = 0.f;
-      const float xh = (xv.v[e] - fm.v[e]) * fr.v[e];
-      d.v[e] = fmaf(fca.v[e], dz, fmaf(fcb.v[e], xh, fcc.v[e]));
+      d.v[e] = fmaf(fca.v[e], dz, fmaf(k1.v[e], xv.v[e], k0.v[e]));
     }
     store8(dy + i8, d);
     if (g_res) store8(g_res + (((long long)bb * (h + 2 * res_pad) + yy + res_pad) * (w + 2 * res_pad) + x + res_pad) * c + g * 8, gr);
