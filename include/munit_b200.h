@@ -76,6 +76,9 @@ typedef struct {
   int32_t act;
   int32_t stages;  /* 0 = auto */
   int32_t cluster; /* CTAs per cluster sharing (multicasting) the weight tile: 0 = auto, 1, 2 or 4 */
+  int32_t halo;    /* 1: halo-resident variant (stride-1 rank-4 view, one phase, tw x th x tn = 8 x 16 x 1, taps on a
+                      full KH x KW grid, KW <= 9): the activation tile + halo is loaded once per 64-channel chunk and
+                      every tap reads it through a shifted UMMA descriptor.  0: one TMA box per tap. */
 } munit_tapgemm_desc;
 
 int munit_tapgemm(const munit_tapgemm_desc* d, void* stream);

@@ -30,7 +30,7 @@ class TapGemmDesc(C.Structure):
         ("o_yoff", C.c_int32 * MAX_PHASES), ("o_xoff", C.c_int32 * MAX_PHASES),
         ("out", C.c_void_p), ("o_sn", C.c_int64), ("o_sy", C.c_int64), ("o_sx", C.c_int64),
         ("o_ymul", C.c_int32), ("o_xmul", C.c_int32), ("n_store", C.c_int32),
-        ("bias", C.c_void_p), ("act", C.c_int32), ("stages", C.c_int32), ("cluster", C.c_int32),
+        ("bias", C.c_void_p), ("act", C.c_int32), ("stages", C.c_int32), ("cluster", C.c_int32), ("halo", C.c_int32),
     ]
 
 

@@ -203,8 +203,9 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t* v) {
 // ---------------------------------------------------------------- UMMA descriptors
 // Shared-memory matrix descriptor (sm_100): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
 // version=1 [46,48) | layout [61,64) (2 = SWIZZLE_128B).
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                    uint32_t base_offset = 0) {
+  uint64_t d = static_cast<uint64_t>(base_offset & 7) << 49;  // row phase of the start inside the 1024 B swizzle atom
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;

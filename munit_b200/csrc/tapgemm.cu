@@ -37,6 +37,8 @@ struct FwdParams {
   int act;
   int stages;
   int dbg;  // profiling knobs (env MUNIT_DBG): 1 skip A loads, 2 skip B loads, 4 skip MMA, 8 skip stores
+  // halo-resident variant: window origin (tap offset minimum), box width / rows, descriptor base-offset mode
+  int halo_ox, halo_oy, halo_wb, halo_rb, halo_mode;
   int* err;
   int tap_off[MUNIT_MAX_TAPS][5];
 };
@@ -276,6 +278,167 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   tc_fence_before();
   __syncthreads();
   if (CS > 1) cluster_sync_all();  // no CTA exits while a peer can still write its smem / barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// =============================================================================================
+// Halo-resident variant for stride-1 convolutions (3x3 / 5x5 / 7x1 ...): per 64-channel chunk ONE TMA box
+// [RB rows x WB cols x 64 ch] covering the 8 x 16 pixel tile plus its (KH-1, KW-1) halo lands in shared memory and
+// every tap's A operand is a shifted UMMA descriptor into it (start += (wy*WB + wx)*128 B, 8-row groups = one
+// 8-pixel image-row segment, SBO = WB*128 B).  Shared-memory bytes per tap drop from 16 KB to box/taps
+// (3x3: 4.1 KB, 5x5: 1.6 KB), which is what bounds the plain kernel (profiles/r1_multicast.md).
+// =============================================================================================
+template <int BN>
+__global__ void __launch_bounds__(kThreads, BN <= 64 ? 3 : 2)
+tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ OutMaps tmap_out, const __grid_constant__ FwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int kBBytes = BN * 128;
+  constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_bytes = (uint32_t)(p.halo_wb * p.halo_rb * 128);
+  const uint32_t b_base = smem_base + ((a_bytes + 1023u) & ~1023u);
+  __shared__ __align__(8) uint64_t b_full[kMaxStages];
+  __shared__ __align__(8) uint64_t b_empty[kMaxStages];
+  __shared__ __align__(8) uint64_t a_full, a_empty, tmem_full_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stages = p.stages;
+  int t = blockIdx.x;
+  const int tx = t % p.tiles_x;
+  t /= p.tiles_x;
+  const int ty = t % p.tiles_y;
+  const int n0 = t / p.tiles_y;
+  const int x0 = tx * 8, y0 = ty * 16;
+  const int n_tile = blockIdx.y;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(smem_u32(&b_full[s]), 1);
+      mbar_init(smem_u32(&b_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&a_full), 1);
+    mbar_init(smem_u32(&a_empty), 1);
+    mbar_init(smem_u32(&tmem_full_bar), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_base_slot), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      bool dead = false;
+      int stage = 0;
+      uint32_t ph = 0, aph = 0;
+      for (int kc = 0; kc < p.chunks; ++kc) {
+        mbar_wait(smem_u32(&a_empty), aph ^ 1, dead, p.err);  // every MMA of the previous chunk has read A
+        mbar_arrive_expect_tx(smem_u32(&a_full), a_bytes);
+        tma_load_4d(smem_base, &tmap_a, smem_u32(&a_full), kc * 64, x0 + p.halo_ox, y0 + p.halo_oy, n0);
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+          mbar_wait(smem_u32(&b_empty[stage]), ph ^ 1, dead, p.err);
+          const uint32_t fb = smem_u32(&b_full[stage]);
+          mbar_arrive_expect_tx(fb, kBBytes);
+          tma_load_2d(b_base + stage * kBBytes, &tmap_b, fb, p.b_k0[0] + (tap * p.chunks + kc) * 64, n_tile * BN);
+          if (++stage == stages) {
+            stage = 0;
+            ph ^= 1;
+          }
+        }
+        aph ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      bool dead = false;
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      const uint32_t sbo = (uint32_t)p.halo_wb * 128u;
+      int stage = 0;
+      uint32_t ph = 0, aph = 0;
+      for (int kc = 0; kc < p.chunks; ++kc) {
+        mbar_wait(smem_u32(&a_full), aph, dead, p.err);
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+          mbar_wait(smem_u32(&b_full[stage]), ph, dead, p.err);
+          tc_fence_after();
+          const int wx = p.tap_off[tap][1] - p.halo_ox, wy = p.tap_off[tap][2] - p.halo_oy;
+          const uint32_t sa = smem_base + (uint32_t)(wy * p.halo_wb + wx) * 128u;
+          // base_offset stays 0: the 128B swizzle is applied on absolute smem address bits (probed on B200,
+          // profiles/r1_halo.md); halo_mode == 3 keeps the rejected (addr >> 7) & 7 variant reachable for the probe.
+          const uint32_t boff = p.halo_mode == 3 ? ((sa >> 7) & 7u) : 0u;
+          const uint32_t sb = b_base + stage * kBBytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = umma_desc_sw128(sa + k * 32, 0, sbo, boff);
+            const uint64_t db = umma_desc_sw128(sb + k * 32, 0, 1024);
+            umma_bf16(tmem_base, da, db, idesc, (kc | tap | k) != 0);
+          }
+          umma_commit(smem_u32(&b_empty[stage]));
+          if (++stage == stages) {
+            stage = 0;
+            ph ^= 1;
+          }
+        }
+        umma_commit(smem_u32(&a_empty));
+        aph ^= 1;
+      }
+      umma_commit(smem_u32(&tmem_full_bar));
+    }
+  } else {
+    bool dead = false;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    mbar_wait(smem_u32(&tmem_full_bar), 0, dead, p.err);
+    tc_fence_after();
+    const float slope = act_slope(p.act);
+    const bool is_tanh = p.act == MUNIT_ACT_TANH;
+    constexpr int kGroups = BN / 64;
+    const bool issuer = (warp == 2 && lane == 0);
+#pragma unroll 1
+    for (int g = 0; g < kGroups; ++g) {
+      const uint32_t buf = smem_base + g * kABytes;  // A + B regions are idle now
+      const int col0 = n_tile * BN + g * 64;
+      const bool store_group = col0 < p.n_store;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * 64 + h * 32, v);
+        tmem_ld_wait();
+        if (store_group) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t o[4];
+            epi8(v + j, p.bias ? p.bias + col0 + h * 32 + j : nullptr, slope, is_tanh, o);
+            const int chunk = (h * 4 + (j >> 3)) ^ (row & 7);
+            const uint32_t dst = buf + row * 128 + chunk * 16;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]),
+                         "r"(o[3])
+                         : "memory");
+          }
+        }
+      }
+      fence_proxy_async();
+      named_bar_sync(1, 128);
+      if (issuer && store_group && !dead) {
+        tma_store_4d(&tmap_out.m[0], buf, col0, x0, y0, n0);
+        tma_store_commit();
+      }
+    }
+    if (issuer) tma_store_wait_read0();
+  }
+  tc_fence_before();
+  __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -533,6 +696,33 @@ int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, const OutMaps& to, 
 }
 
 template <int BN>
+int launch_halo(const CUtensorMap& ta, const CUtensorMap& tb, const OutMaps& to, FwdParams& p, dim3 grid,
+                cudaStream_t st) {
+  const size_t a_bytes = ((size_t)p.halo_wb * p.halo_rb * 128 + 1023) & ~(size_t)1023;
+  if (p.stages <= 0) {
+    // fill what is left of a two-CTA (three for BN 64) smem budget with weight stages
+    const size_t budget = (BN <= 64 ? 74 : 112) * 1024;
+    int st_ = (int)((budget > a_bytes ? budget - a_bytes : 0) / (BN * 128));
+    if (st_ > kMaxStages) st_ = kMaxStages;
+    if (st_ < 2) st_ = 2;
+    p.stages = st_;
+  }
+  size_t smem = a_bytes + (size_t)p.stages * BN * 128 + 1024;
+  const size_t need_epi = (size_t)(BN / 64) * kABytes + 1024;
+  if (smem < need_epi) smem = need_epi;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+    attr_smem = smem;
+  }
+  tapgemm_halo_kernel<BN><<<grid, kThreads, smem, st>>>(ta, tb, to, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "tapgemm_halo launch: %s", cudaGetErrorString(e));
+  return MUNIT_OK;
+}
+
+template <int BN>
 int launch_wg(const CUtensorMap& ta, const CUtensorMap& tb, WgParams& p, dim3 grid, cudaStream_t st) {
   const int stage_bytes = (2 + BN / 64) * kBoxBytes;
   int stages = p.stages;
@@ -572,7 +762,8 @@ extern "C" int munit_tapgemm(const munit_tapgemm_desc* d, void* stream) {
   if (d->a_box[0] != 64) return mb_fail(MUNIT_ERR_ARG, "tapgemm: a_box[0] must be 64");
   uint64_t prod = 1;
   for (int i = 1; i < d->a_rank; ++i) prod *= d->a_box[i];
-  if (prod != 128 || d->tw * d->th * d->tn != 128) return mb_fail(MUNIT_ERR_ARG, "tapgemm: M tile must be 128 pixels");
+  if (!d->halo && prod != 128) return mb_fail(MUNIT_ERR_ARG, "tapgemm: A box must cover 128 pixels");
+  if (d->tw * d->th * d->tn != 128) return mb_fail(MUNIT_ERR_ARG, "tapgemm: M tile must be 128 pixels");
   if (d->num_taps < 1 || d->num_taps > MUNIT_MAX_TAPS || d->chunks < 1)
     return mb_fail(MUNIT_ERR_ARG, "tapgemm: taps/chunks");
   if (d->phases < 1 || d->phases > MUNIT_MAX_PHASES) return mb_fail(MUNIT_ERR_ARG, "tapgemm: phases");
@@ -584,8 +775,11 @@ extern "C" int munit_tapgemm(const munit_tapgemm_desc* d, void* stream) {
     if ((uint64_t)d->b_k0[ph] + (uint64_t)d->num_taps * d->chunks * 64 > d->b_k)
       return mb_fail(MUNIT_ERR_ARG, "tapgemm: weight K extent too small");
   CUtensorMap ta, tb;
-  int rc = make_tmap(&ta, d->a, d->a_rank, d->a_dim, d->a_stride, d->a_box);
-  if (rc) return rc;
+  int rc = 0;
+  if (!d->halo) {
+    rc = make_tmap(&ta, d->a, d->a_rank, d->a_dim, d->a_stride, d->a_box);
+    if (rc) return rc;
+  }
   FwdParams p;
   memset(&p, 0, sizeof(p));
   p.tw = d->tw; p.th = d->th; p.tn = d->tn;
@@ -612,6 +806,48 @@ extern "C" int munit_tapgemm(const munit_tapgemm_desc* d, void* stream) {
   memcpy(p.tap_off, d->tap_off, sizeof(p.tap_off));
   dim3 grid(p.tiles_x * p.tiles_y * p.tiles_n, (unsigned)(d->b_rows / d->bn), d->phases);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (d->halo) {
+    // halo-resident variant: validated stride-1 geometry (see include/munit_b200.h)
+    if (d->a_rank != 4 || d->phases != 1 || d->tw != 8 || d->th != 16 || d->tn != 1 || d->bn < 64)
+      return mb_fail(MUNIT_ERR_ARG, "tapgemm halo: needs rank-4 stride-1 view, one phase, 8x16x1 tile, bn >= 64");
+    int ox = d->tap_off[0][1], oy = d->tap_off[0][2], mx_ = ox, my_ = oy;
+    for (int t2 = 0; t2 < d->num_taps; ++t2) {
+      if (d->tap_off[t2][0] != 0 || d->tap_off[t2][3] != 0) return mb_fail(MUNIT_ERR_ARG, "tapgemm halo: tap offsets");
+      ox = d->tap_off[t2][1] < ox ? d->tap_off[t2][1] : ox;
+      oy = d->tap_off[t2][2] < oy ? d->tap_off[t2][2] : oy;
+      mx_ = d->tap_off[t2][1] > mx_ ? d->tap_off[t2][1] : mx_;
+      my_ = d->tap_off[t2][2] > my_ ? d->tap_off[t2][2] : my_;
+    }
+    const int kw_ = mx_ - ox + 1, kh_ = my_ - oy + 1;
+    if (kw_ > 9) return mb_fail(MUNIT_ERR_ARG, "tapgemm halo: kernel width %d > 9", kw_);
+    p.halo_ox = ox; p.halo_oy = oy;
+    p.halo_wb = kw_ > 1 ? 16 : 8;
+    p.halo_rb = 16 + kh_ - 1;
+    p.halo_mode = d->halo;
+    uint32_t abox[4] = {64, (uint32_t)p.halo_wb, (uint32_t)p.halo_rb, 1};
+    rc = make_tmap(&ta, d->a, 4, d->a_dim, d->a_stride, abox);
+    if (rc) return rc;
+    uint64_t bdim[2] = {d->b_k, d->b_rows};
+    uint64_t bstr[2] = {0, d->b_k * 2};
+    uint32_t bbox[2] = {64, (uint32_t)d->bn};
+    rc = make_tmap(&tb, d->b, 2, bdim, bstr, bbox);
+    if (rc) return rc;
+    OutMaps to;
+    memset(&to, 0, sizeof(to));
+    const char* base = reinterpret_cast<const char*>(d->out) +
+                       2 * ((int64_t)d->o_yoff[0] * d->o_sy + (int64_t)d->o_xoff[0] * d->o_sx);
+    uint64_t odim[4] = {(uint64_t)d->n_store, (uint64_t)d->out_w, (uint64_t)d->out_h, (uint64_t)d->n_img};
+    uint64_t ostr[4] = {0, (uint64_t)(2 * d->o_sx * d->o_xmul), (uint64_t)(2 * d->o_sy * d->o_ymul), (uint64_t)(2 * d->o_sn)};
+    uint32_t obox[4] = {64, 8, 16, 1};
+    rc = make_tmap(&to.m[0], base, 4, odim, ostr, obox);
+    if (rc) return rc;
+    switch (d->bn) {
+      case 64: return launch_halo<64>(ta, tb, to, p, grid, st);
+      case 128: return launch_halo<128>(ta, tb, to, p, grid, st);
+      case 256: return launch_halo<256>(ta, tb, to, p, grid, st);
+    }
+    return mb_fail(MUNIT_ERR_ARG, "tapgemm halo: bn %d unsupported", d->bn);
+  }
   // Weight-tile multicast across a cluster of M tiles (d->cluster: 0 = auto, 1/2/4 forced).  Measured on
   // B200 (profiles/r1_multicast.md): the kernel is bound by bytes in flight per SM (smem capacity / TMA round
   // trip), not by L2->SM bandwidth, so multicast only adds lock-step coupling -- auto therefore picks 1.

@@ -82,6 +82,7 @@ class TapGemmPlan:
     o_ymul: int
     o_xmul: int
     n_store: int
+    halo: int = 0  # 1/2: halo-resident kernel variant (stride-1 only, 8x16 tiles)
 
     @property
     def grid(self):
@@ -165,7 +166,12 @@ def conv_out(hp, k, s):
     return (hp - k) // s + 1
 
 
-def plan_fwd(n, hp, wp, c, kh, kw, sy, sx, co_rows, out_geom, n_store=None) -> TapGemmPlan:
+def halo_ok(kh, kw, sy, sx, out_h, out_w, bn) -> bool:
+    """Geometry the halo-resident kernel variant accepts."""
+    return sy == 1 and sx == 1 and kw <= 9 and kh * kw > 1 and bn >= 64 and out_h >= 8 and out_w >= 8
+
+
+def plan_fwd(n, hp, wp, c, kh, kw, sy, sx, co_rows, out_geom, n_store=None, halo=0) -> TapGemmPlan:
     """Forward conv: x [n,hp,wp,c] -> out.  out_geom = (o_sn, o_sy, o_sx, y_off, x_off) in elements:
     pixel (b, y, x) is stored at out + b*o_sn + (y+y_off)*o_sy + (x+x_off)*o_sx."""
     assert c % 64 == 0, "input channels must be a multiple of 64"
@@ -175,14 +181,18 @@ def plan_fwd(n, hp, wp, c, kh, kw, sy, sx, co_rows, out_geom, n_store=None) -> T
     taps = [off(i, j) for i in range(kh) for j in range(kw)]
     o_sn, o_sy, o_sx, y_off, x_off = out_geom
     bn = pick_bn(co_rows)
+    halo = halo if halo_ok(kh, kw, sy, sx, ho, wo, bn) else 0
+    if halo:
+        tw, th, tn = 8, 16, 1
     return TapGemmPlan(
+        halo=halo,
         a_rank=rank, a_dim=dims, a_stride=strides, a_box=box(tw, th, tn), b_rows=co_rows, b_k=kh * kw * c, bn=bn,
         tw=tw, th=th, tn=tn, out_w=wo, out_h=ho, n_img=n, mx=mx, my=my, mn=mn, num_taps=len(taps), chunks=c // 64,
         tap_off=taps, phases=1, b_k0=[0], o_yoff=[y_off], o_xoff=[x_off], o_sn=o_sn, o_sy=o_sy, o_sx=o_sx, o_ymul=1,
         o_xmul=1, n_store=co_rows if n_store is None else n_store)
 
 
-def plan_dgrad(n, hp, wp, c_rows, kh, kw, sy, sx, co_c) -> TapGemmPlan:
+def plan_dgrad(n, hp, wp, c_rows, kh, kw, sy, sx, co_c, halo=0) -> TapGemmPlan:
     """Input gradient: dy [n,ho,wo,co_c] (unpadded; out-of-range taps read zero through TMA) ->
     dxp [n,hp,wp,c_rows] (gradient w.r.t. the *padded* conv input, every position written)."""
     ho, wo = conv_out(hp, kh, sy), conv_out(wp, kw, sx)
@@ -199,7 +209,11 @@ def plan_dgrad(n, hp, wp, c_rows, kh, kw, sy, sx, co_c) -> TapGemmPlan:
     taps = [[0, -b, -a, 0] for a in range(na) for b in range(nb)]
     phases = sy * sx
     kper = na * nb * ck
+    halo = halo if halo_ok(kh, kw, sy, sx, oh, ow, pick_bn(c_rows)) else 0
+    if halo:
+        tw, th, tn = 8, 16, 1
     return TapGemmPlan(
+        halo=halo,
         a_rank=4, a_dim=dims, a_stride=strides, a_box=[64, tw, th, tn], b_rows=c_rows, b_k=phases * kper,
         bn=pick_bn(c_rows), tw=tw, th=th, tn=tn, out_w=ow, out_h=oh, n_img=n, mx=[0, 1, 0, 0], my=[0, 0, 1, 0],
         mn=[0, 0, 0, 1], num_taps=len(taps), chunks=ck // 64, tap_off=taps, phases=phases,

@@ -78,6 +78,7 @@ def tapgemm(plan, a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, bias=None
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() >= plan.b_rows
     d.bias, d.act, d.stages, d.cluster = _ptr(bias), ACT[act], stages, cluster
+    d.halo = int(getattr(plan, "halo", 0))
     check(lib.munit_tapgemm(C.byref(d), _stream()), "munit_tapgemm")
     _count()
     return out

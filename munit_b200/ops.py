@@ -138,8 +138,9 @@ class ConvLayer:
             ho, wo = G.conv_out(hp, kh, sy), G.conv_out(wp, kw, sx)
             hop, wop = ho + 2 * out_pad, wo + 2 * out_pad
             fwd = G.plan_fwd(n, hp, wp, c, kh, kw, sy, sx, self.co_rows,
-                             (hop * wop * self.co_rows, wop * self.co_rows, self.co_rows, out_pad, out_pad))
-            dg = G.plan_dgrad(n, hp, wp, c, kh, kw, sy, sx, self.co_rows)
+                             (hop * wop * self.co_rows, wop * self.co_rows, self.co_rows, out_pad, out_pad),
+                             halo=_want_halo(kh, kw, ho, wo))
+            dg = G.plan_dgrad(n, hp, wp, c, kh, kw, sy, sx, self.co_rows, halo=_want_halo(kh, kw, hp, wp))
             if self.first:
                 wg = G.plan_wgrad(n, hp, wp, 64, kh, 1, sy, 1, self.co_rows, self.cout, kh * 64, 64, 1)
             elif self.last:
@@ -152,6 +153,16 @@ class ConvLayer:
             p = (fwd, dg, wg, ho, wo)
             self._plans[key] = p
         return p
+
+
+def _want_halo(kh, kw, out_h, out_w) -> int:
+    """Use the halo-resident tap-GEMM variant where it measured faster (profiles/r1_halo.md): many taps (5x5 and
+    up) and an output extent that 8 x 16 tiles cover with <= 10 % waste.  (The UMMA descriptor base offset stays 0:
+    the 128B swizzle is a function of the absolute shared-memory address.)"""
+    if kh * kw < 25:
+        return 0
+    cover = (-(-out_w // 8) * 8) * (-(-out_h // 16) * 16)
+    return 1 if out_w * out_h >= 0.9 * cover else 0
 
 
 def _param_grad_buf(p: Optional[torch.Tensor]):

@@ -115,3 +115,46 @@ def test_forward_into_padded_buffer_and_halo():
     torch.cuda.synchronize()
     ref = nhwc(F.pad(y, (po,) * 4, mode="reflect"))
     assert rel_l2(out, ref) < TOL
+
+
+HALO_CASES = [
+    (2, 16, 16, 64, 64, 3, 1, 1),
+    (8, 64, 64, 256, 256, 3, 1, 1),
+    (1, 24, 40, 128, 128, 5, 1, 2),
+    (2, 32, 32, 128, 64, 5, 1, 2),
+    (1, 20, 28, 64, 64, 7, 1, 3),
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,k,s,pad", HALO_CASES)
+def test_tapgemm_halo_variant(n, h, w, cin, cout, k, s, pad):
+    """Halo-resident kernel variant (one activation box per channel chunk, shifted UMMA descriptors per tap):
+    forward and input-gradient against torch conv2d."""
+    from munit_b200 import geometry as G, kernels as K
+
+    xp, wt, bias = _setup(n, h, w, cin, cout, k, s, pad, 5)
+    xp = xp.requires_grad_(True)
+    y_ref = F.conv2d(xp, wt, bias, stride=s)
+    gy = bf16_round(torch.randn_like(y_ref))
+    y_ref.backward(gy)
+    hp, wp = xp.shape[2:]
+    ho, wo = y_ref.shape[2:]
+    plan = G.plan_fwd(n, hp, wp, cin, k, k, s, s, cout, (ho * wo * cout, wo * cout, cout, 0, 0), halo=1)
+    assert plan.halo == 1
+    a = nhwc(xp.detach()).to(torch.bfloat16)
+    b = wt.permute(0, 2, 3, 1).reshape(cout, -1).contiguous().to(torch.bfloat16)
+    out = torch.zeros(n, ho, wo, cout, dtype=torch.bfloat16, device="cuda")
+    K.tapgemm(plan, a, b, out, bias, "none")
+    torch.cuda.synchronize()
+    assert error_flag() == 0
+    assert rel_l2(out, nhwc(y_ref.detach())) < TOL, rel_l2(out, nhwc(y_ref.detach()))
+    dplan = G.plan_dgrad(n, hp, wp, cin, k, k, s, s, cout, halo=1)
+    assert dplan.halo == 1
+    idx = G.dgrad_index_map(cout, cin, k, k, s, s, cin, max(64, cout)).cuda()
+    wd = torch.empty(cin, idx.numel() // cin, dtype=torch.bfloat16, device="cuda")
+    K.gather_cast(wt.permute(0, 2, 3, 1).contiguous().reshape(-1), idx, wd)
+    dxp = torch.full((n, hp, wp, cin), float("nan"), dtype=torch.bfloat16, device="cuda")
+    K.tapgemm(dplan, nhwc(gy).to(torch.bfloat16), wd, dxp)
+    torch.cuda.synchronize()
+    assert error_flag() == 0
+    assert rel_l2(dxp, nhwc(xp.grad)) < TOL, rel_l2(dxp, nhwc(xp.grad))

@@ -66,12 +66,13 @@ def run(name, iters=20, nbuf=4):
     xs = [torch.randn(n, hp, wp, cin, device="cuda").to(torch.bfloat16) for _ in range(nbuf)]
     wf = (torch.randn(cout, k * k * cin, device="cuda") * 0.05).to(torch.bfloat16)
     ys = [torch.empty(n, ho, wo, cout, dtype=torch.bfloat16, device="cuda") for _ in range(nbuf)]
-    fwd = G.plan_fwd(n, hp, wp, cin, k, k, s, s, cout, (ho * wo * cout, wo * cout, cout, 0, 0))
+    halo = int(os.environ.get("HALO", 0))
+    fwd = G.plan_fwd(n, hp, wp, cin, k, k, s, s, cout, (ho * wo * cout, wo * cout, cout, 0, 0), halo=halo)
     if os.environ.get("BN"):
         fwd.bn = int(os.environ["BN"])
     stages = int(os.environ.get("STAGES", 0))
     cluster = int(os.environ.get("CLUSTER", 0))
-    dg = G.plan_dgrad(n, hp, wp, cin, k, k, s, s, cout)
+    dg = G.plan_dgrad(n, hp, wp, cin, k, k, s, s, cout, halo=halo)
     ck = max(64, cout)
     wd = (torch.randn(cin, dg.b_k, device="cuda") * 0.05).to(torch.bfloat16)
     dxs = [torch.empty(n, hp, wp, cin, dtype=torch.bfloat16, device="cuda") for _ in range(nbuf)]
