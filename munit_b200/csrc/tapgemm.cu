@@ -821,7 +821,11 @@ extern "C" int munit_tapgemm(const munit_tapgemm_desc* d, void* stream) {
     const int kw_ = mx_ - ox + 1, kh_ = my_ - oy + 1;
     if (kw_ > 9) return mb_fail(MUNIT_ERR_ARG, "tapgemm halo: kernel width %d > 9", kw_);
     p.halo_ox = ox; p.halo_oy = oy;
-    p.halo_wb = kw_ > 1 ? 16 : 8;
+    // box width = tile width + halo; no rounding needed (the swizzle is address based, any 128 B row offset works)
+    {
+      const char* e = getenv("MUNIT_HALO_WB16");
+      p.halo_wb = (e && atoi(e)) ? (kw_ > 1 ? 16 : 8) : 8 + kw_ - 1;
+    }
     p.halo_rb = 16 + kh_ - 1;
     p.halo_mode = d->halo;
     uint32_t abox[4] = {64, (uint32_t)p.halo_wb, (uint32_t)p.halo_rb, 1};
