@@ -117,6 +117,9 @@ typedef struct {
   int32_t ksplit;   /* 0 = auto */
   int32_t stages;   /* 0 = auto */
   int32_t tap_on_a; /* 1: tap offsets shift A instead of B (swapped orientation A = X, B = dY) */
+  int32_t row_taps; /* > 0: row-sharing variant for stride-1 convs -- one CTA owns `row_taps` consecutive taps (a kernel
+                       row), loads dY and one widened X box per 8x8 pixel block and feeds each tap through a shifted
+                       UMMA descriptor into its own TMEM accumulator (row_taps * bn <= 512, bn <= 128) */
 } munit_wgrad_desc;
 
 int munit_wgrad(const munit_wgrad_desc* d, void* stream);

@@ -45,7 +45,7 @@ class WgradDesc(C.Structure):
         ("m_total", C.c_int32), ("n_total", C.c_int32), ("bn", C.c_int32), ("num_taps", C.c_int32),
         ("tap_off", (C.c_int32 * 5) * MAX_TAPS),
         ("dw", C.c_void_p), ("s_m", C.c_int64), ("s_t", C.c_int64), ("s_n", C.c_int64),
-        ("ksplit", C.c_int32), ("stages", C.c_int32), ("tap_on_a", C.c_int32),
+        ("ksplit", C.c_int32), ("stages", C.c_int32), ("tap_on_a", C.c_int32), ("row_taps", C.c_int32),
     ]
 
 

@@ -462,6 +462,8 @@ struct WgParams {
   int ksplit;
   int stages;
   int tap_on_a;  // tap offsets shift the A operand (swapped orientation: A = X, B = dY) instead of B
+  int row_taps;  // row-sharing variant: taps per group (one kernel row); 0 = one tap per CTA
+  int wb;        // row-sharing variant: B box width in pixels (8 + KW - 1)
   int* err;
   int tap_off[MUNIT_MAX_TAPS][5];
 };
@@ -619,6 +621,156 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 }
 
 // =============================================================================================
+// Row-sharing wgrad variant (stride-1 convolutions): one CTA owns a whole kernel ROW of taps (KW taps) for its
+// (Cout tile, Cin tile, pixel slice).  Per 8x8-pixel block it loads dY once and ONE [8 rows x (8+KW-1) cols x 64 ch]
+// box of X per channel group; each tap's B operand is a UMMA descriptor shifted by `tap * 128 B` into that box and
+// accumulates into its own TMEM column range (KW x BN <= 512 columns).  Shared-memory bytes per tap-MMA drop ~2-4x.
+// =============================================================================================
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_row_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ WgParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int kNB = BN / 64;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_box_bytes = ((uint32_t)p.wb * 8u * 128u + 1023u) & ~1023u;  // boxes stay 1024 B aligned
+  const uint32_t stage_bytes = 2 * kBoxBytes + kNB * b_box_bytes;
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stages = p.stages;
+  const int kw = p.row_taps;
+  const int grp = blockIdx.x / p.n_tiles;            // kernel row
+  const int n_tile = blockIdx.x - grp * p.n_tiles;
+  const int m_tile = blockIdx.y;
+  const int total_pb = p.blocks_x * p.blocks_y * p.blocks_n;
+  const int pb_begin = (int)(((long long)total_pb * blockIdx.z) / p.ksplit);
+  const int pb_end = (int)(((long long)total_pb * (blockIdx.z + 1)) / p.ksplit);
+  const int num_kb = pb_end - pb_begin;
+  const int tap0 = grp * kw;
+  const int ox = p.tap_off[tap0][1], oy = p.tap_off[tap0][2];  // window origin (taps of a row are ordered by dx)
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&tmem_full_bar), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_base_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (num_kb > 0) {
+    if (warp == 0) {
+      if (elect_one()) {
+        bool dead = false;
+        int stage = 0;
+        uint32_t ph = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          int t = pb_begin + kb;
+          const int bx = t % p.blocks_x;
+          t /= p.blocks_x;
+          const int by = t % p.blocks_y;
+          const int n0 = t / p.blocks_y;
+          const int x0 = bx * 8, y0 = by * 8;
+          mbar_wait(smem_u32(&empty_bar[stage]), ph ^ 1, dead, p.err);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_arrive_expect_tx(fb, 2 * kBoxBytes + kNB * (uint32_t)p.wb * 8u * 128u);
+          const uint32_t sa = smem_base + stage * stage_bytes;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) tma_load_4d(sa + i * kBoxBytes, &tmap_a, fb, m_tile * 128 + i * 64, x0, y0, n0);
+#pragma unroll
+          for (int i = 0; i < kNB; ++i)
+            tma_load_4d(sa + 2 * kBoxBytes + i * b_box_bytes, &tmap_b, fb, n_tile * BN + i * 64, x0 + ox, y0 + oy, n0);
+          if (++stage == stages) {
+            stage = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (elect_one()) {
+        bool dead = false;
+        constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
+        const uint32_t sbo_b = (uint32_t)p.wb * 128u;
+        int stage = 0;
+        uint32_t ph = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), ph, dead, p.err);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          const uint32_t sb = sa + 2 * kBoxBytes;
+          for (int j = 0; j < kw; ++j) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              // A (dY): 16 pixels = 2 patch rows of 8 -> 2048 B per K step, 8-row groups 1024 B apart.
+              // B (X): same 2 patch rows inside the wider box, shifted by tap j: groups wb*128 B apart.
+              const uint64_t da = umma_desc_sw128(sa + k * 2048, kBoxBytes, 1024);
+              const uint64_t db = umma_desc_sw128(sb + (uint32_t)((2 * k) * p.wb + j) * 128u, b_box_bytes, sbo_b);
+              umma_bf16(tmem_base + j * BN, da, db, idesc, (kb | k) != 0);
+            }
+          }
+          umma_commit(smem_u32(&empty_bar[stage]));
+          if (++stage == stages) {
+            stage = 0;
+            ph ^= 1;
+          }
+        }
+        umma_commit(smem_u32(&tmem_full_bar));
+      }
+    } else {
+      bool dead = false;
+      const int q = warp & 3;
+      const int m = m_tile * 128 + q * 32 + lane;
+      mbar_wait(smem_u32(&tmem_full_bar), 0, dead, p.err);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < kw; ++j) {
+        float* dst = p.dw + (long long)m * p.s_m + (long long)(tap0 + j) * p.s_t;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + j * BN + c0, v);
+          tmem_ld_wait();
+          if (m < p.m_total && !dead) {
+            const int nb = n_tile * BN + c0;
+            if (p.s_n == 1 && ((p.s_m | p.s_t) & 3) == 0 && (nb + 32 <= p.n_total)) {
+#pragma unroll
+              for (int e = 0; e < 32; e += 4)
+                red_add_v4_f32(dst + nb + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                               __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e)
+                if (nb + e < p.n_total) red_add_f32(dst + (long long)(nb + e) * p.s_n, __uint_as_float(v[e]));
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =============================================================================================
 // host side
 // =============================================================================================
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -740,6 +892,28 @@ int launch_wg(const CUtensorMap& ta, const CUtensorMap& tb, WgParams& p, dim3 gr
   wgrad_kernel<BN><<<grid, kThreads, smem, st>>>(ta, tb, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(e));
+  return MUNIT_OK;
+}
+
+template <int BN>
+int launch_wg_row(const CUtensorMap& ta, const CUtensorMap& tb, WgParams& p, dim3 grid, cudaStream_t st) {
+  const size_t b_box = ((size_t)p.wb * 8 * 128 + 1023) & ~(size_t)1023;
+  const size_t stage_bytes = 2 * kBoxBytes + (BN / 64) * b_box;
+  int stages = p.stages;
+  if (stages <= 0) stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_row_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+    attr_smem = smem;
+  }
+  wgrad_row_kernel<BN><<<grid, kThreads, smem, st>>>(ta, tb, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "wgrad_row launch: %s", cudaGetErrorString(e));
   return MUNIT_OK;
 }
 
@@ -897,11 +1071,58 @@ extern "C" int munit_tapgemm(const munit_tapgemm_desc* d, void* stream) {
 
 extern "C" int munit_wgrad(const munit_wgrad_desc* d, void* stream) {
   if (!d || !d->a || !d->b || !d->dw) return mb_fail(MUNIT_ERR_ARG, "wgrad: null pointer");
-  if (d->a_box[0] != 64 || d->b_box[0] != 64) return mb_fail(MUNIT_ERR_ARG, "wgrad: box[0] must be 64");
-  if (d->pw * d->ph * d->pn != 64) return mb_fail(MUNIT_ERR_ARG, "wgrad: pixel block must be 64");
+  if (!d->row_taps) {
+    if (d->a_box[0] != 64 || d->b_box[0] != 64) return mb_fail(MUNIT_ERR_ARG, "wgrad: box[0] must be 64");
+    if (d->pw * d->ph * d->pn != 64) return mb_fail(MUNIT_ERR_ARG, "wgrad: pixel block must be 64");
+  }
   if (d->num_taps < 1 || d->num_taps > MUNIT_MAX_TAPS) return mb_fail(MUNIT_ERR_ARG, "wgrad: taps");
   CUtensorMap ta, tb;
-  int rc = make_tmap(&ta, d->a, d->a_rank, d->a_dim, d->a_stride, d->a_box);
+  int rc = 0;
+  if (d->row_taps > 0) {
+    // row-sharing variant: 8x8 pixel blocks, dY box [64 x 8 x 8], X box [64 x (8+KW-1) x 8]
+    if (d->a_rank != 4 || d->b_rank != 4 || d->tap_on_a || d->num_taps % d->row_taps || d->row_taps * d->bn > 512 ||
+        d->bn > 128)
+      return mb_fail(MUNIT_ERR_ARG, "wgrad row: needs rank-4 stride-1 views, taps %% row_taps == 0, row_taps*bn <= 512");
+    uint32_t abox[4] = {64, 8, 8, 1};
+    uint32_t bbox[4] = {64, (uint32_t)(8 + d->row_taps - 1), 8, 1};
+    rc = make_tmap(&ta, d->a, 4, d->a_dim, d->a_stride, abox);
+    if (rc) return rc;
+    rc = make_tmap(&tb, d->b, 4, d->b_dim, d->b_stride, bbox);
+    if (rc) return rc;
+    WgParams p;
+    memset(&p, 0, sizeof(p));
+    p.pw = 8; p.ph = 8; p.pn = 1;
+    p.blocks_x = (d->out_w + 7) / 8;
+    p.blocks_y = (d->out_h + 7) / 8;
+    p.blocks_n = d->n_img;
+    p.a_rank = p.b_rank = 4;
+    p.m_total = d->m_total; p.n_total = d->n_total; p.num_taps = d->num_taps;
+    p.n_tiles = (d->n_total + d->bn - 1) / d->bn;
+    p.dw = d->dw; p.s_m = d->s_m; p.s_t = d->s_t; p.s_n = d->s_n;
+    p.stages = d->stages; p.err = mb_error_flag();
+    p.row_taps = d->row_taps;
+    p.wb = 8 + d->row_taps - 1;
+    memcpy(p.tap_off, d->tap_off, sizeof(p.tap_off));
+    const int m_tiles = (d->m_total + 127) / 128;
+    const int groups = d->num_taps / d->row_taps;
+    const int total_pb = p.blocks_x * p.blocks_y * p.blocks_n;
+    int ks = d->ksplit;
+    if (ks <= 0) {
+      const int ctas = groups * p.n_tiles * m_tiles;  // one CTA per SM (512 TMEM columns): fill whole waves of 148
+      int waves = (ctas + 147) / 148;
+      ks = (waves * 148) / ctas;
+      const int max_ks = total_pb / 4 > 0 ? total_pb / 4 : 1;
+      if (ks > max_ks) ks = max_ks;
+    }
+    if (ks > total_pb) ks = total_pb;
+    if (ks < 1) ks = 1;
+    p.ksplit = ks;
+    dim3 grid(groups * p.n_tiles, m_tiles, ks);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (d->bn == 64) return launch_wg_row<64>(ta, tb, p, grid, st);
+    return launch_wg_row<128>(ta, tb, p, grid, st);
+  }
+  rc = make_tmap(&ta, d->a, d->a_rank, d->a_dim, d->a_stride, d->a_box);
   if (rc) return rc;
   rc = make_tmap(&tb, d->b, d->b_rank, d->b_dim, d->b_stride, d->b_box);
   if (rc) return rc;

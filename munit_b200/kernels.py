@@ -113,6 +113,7 @@ def wgrad(plan, dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, ksplit=0, s
             d.tap_off[t][i] = off[i] if i < len(off) else 0
     d.dw, d.s_m, d.s_t, d.s_n = dw.data_ptr(), plan.s_m, plan.s_t, plan.s_n
     d.ksplit, d.stages, d.tap_on_a = ksplit, stages, int(getattr(plan, "tap_on_a", 0))
+    d.row_taps = int(getattr(plan, "row_taps", 0))
     check(lib.munit_wgrad(C.byref(d), _stream()), "munit_wgrad")
     _count()
     return dw

@@ -79,6 +79,8 @@ def run(name, iters=20, nbuf=4):
     wg = G.plan_wgrad(n, hp, wp, cin, k, k, s, s, cout, cout, k * k * cin, cin, 1)
     if int(os.environ.get("WBN", 0)):
         wg.bn = int(os.environ["WBN"])
+    if os.environ.get("ROWSHARE"):
+        wg = G.plan_wgrad(n, hp, wp, cin, k, k, s, s, cout, cout, k * k * cin, cin, 1, swap=False, row_share=True)
     if os.environ.get("NOSWAP"):
         wg = G.plan_wgrad(n, hp, wp, cin, k, k, s, s, cout, cout, k * k * cin, cin, 1, swap=False)
     ksplit, wstages = int(os.environ.get("KSPLIT", 0)), int(os.environ.get("WSTAGES", 0))
