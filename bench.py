@@ -232,7 +232,8 @@ def run_b200(args):
     hw = args.hw or cfg["crop_image_height"]
     torch.manual_seed(0)  # identical replicas on every rank
     trainer = MUNIT_Trainer(cfg).cuda()
-    runner = StepRunner(trainer, cfg, args.batch, hw, use_graph=not args.no_graph, world=world)
+    runner = StepRunner(trainer, cfg, args.batch, hw, use_graph=not args.no_graph, world=world,
+                        two_streams=args.two_streams)
     x_a, x_b = synthetic_images(args.batch, hw, 1234 + rank)
     x_a_h, x_b_h = x_a.pin_memory(), x_b.pin_memory()
     sd = trainer.style_dim
@@ -311,7 +312,7 @@ def run_b200(args):
         data="synthetic",
         config=dict(workload=workload_name(args.batch, hw, args.hd),
                     global_batch=args.batch * world, gen_state=cfg["gen_state"], guided=cfg["guided"],
-                    optimizer=cfg["optimizer"], parallelism=f"dp{world}", cuda_graph=not args.no_graph,
+                    optimizer=cfg["optimizer"], parallelism=f"dp{world}", cuda_graph=not args.no_graph, two_streams=bool(args.two_streams),
                     l2="per-step working set (several GB of bf16 activations) >> 126 MB L2; no explicit flush"),
         e2e=dict(value=e2e_per_s, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=8,
                  last_losses=dict(dis=last[0], gen=last[1])),
@@ -417,6 +418,7 @@ def main():
     ap.add_argument("--hd", action="store_true", help="config_HD (512x512, ExtraAdam)")
     ap.add_argument("--optimizer", default="")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--two-streams", type=int, default=0, help="fork the domain-a / domain-b branches onto two streams")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="train", choices=["train", "infer"])
     ap.add_argument("--dump-launches", default="", help="write per-launch tensor-kernel timings (profile pass) to this json")

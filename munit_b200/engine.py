@@ -15,8 +15,10 @@ from . import _lib, dp
 
 
 class StepRunner:
-    def __init__(self, trainer, cfg: dict, batch: int, hw: int, use_graph: bool = True, world: int = 1):
+    def __init__(self, trainer, cfg: dict, batch: int, hw: int, use_graph: bool = True, world: int = 1,
+                 two_streams: bool = False):
         self.t, self.cfg, self.batch, self.hw = trainer, cfg, batch, hw
+        trainer.parallel_streams = bool(two_streams and use_graph)
         self.use_graph, self.world = use_graph, world
         dev = next(trainer.parameters()).device
         self.dev = dev
@@ -29,6 +31,7 @@ class StepRunner:
         self.s_b2 = torch.zeros(batch, sd, 1, 1, device=dev)
         self.extra = "extra" in cfg["optimizer"]
         self.graphs: Dict[int, list] = {}
+        self.loss_refs: Dict[int, dict] = {}
         self.launches_per_step: Optional[int] = None
         for opt in (trainer.dis_opt, trainer.gen_opt):
             opt.build_arena()
@@ -93,9 +96,14 @@ class StepRunner:
         self.launches_per_step = _lib.launches - before
         self._restore_py_state(st)
         self.graphs[parity] = graphs
+        # the loss_* tensors this graph writes (static outputs); re-published on the trainer after each replay
+        self.loss_refs[parity] = {k: v for k, v in self.t.__dict__.items() if k.startswith("loss_") and torch.is_tensor(v)}
 
     # ------------------------------------------------------------------ public
     def warmup_and_capture(self, eager_steps: int = 2):
+        eager_steps = max(eager_steps, 1)  # the first eager step sets kernel attributes / builds plans and shadows
+        if self.extra and (self.iter + eager_steps) % 2:
+            eager_steps += 1  # ExtraAdam: capture starts on an extrapolation (even) iteration
         """Eager steps (sets kernel attributes, builds plans/shadows, warms the allocator), then capture."""
         s = self.stream
         s.wait_stream(torch.cuda.current_stream())
@@ -142,6 +150,8 @@ class StepRunner:
                 graphs[2].replay()
             else:
                 graphs[0].replay()
+            for k, v in self.loss_refs[self.iter % 2 if self.extra else 0].items():
+                setattr(t, k, v)
             for opt in (t.dis_opt, t.gen_opt):  # python-side bookkeeping the replay does not run
                 opt.step_count += 1
                 if self.extra:

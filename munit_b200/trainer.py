@@ -90,6 +90,31 @@ class MUNIT_Trainer(nn.Module):
         self.dis_a.apply(weights_init("gaussian"))
         self.dis_b.apply(weights_init("gaussian"))
         self.iterations = 0
+        # Two-stream mode (set by engine.StepRunner under CUDA-graph capture): the domain-a and domain-b branches
+        # of a step are independent for long stretches; forking them onto two streams gives the captured graph
+        # parallel branches, which fills partial waves and hides launch latency of the many small kernels.
+        self.parallel_streams = False
+        self._side = None
+
+    def _fork_join(self, fa, fb):
+        """fa() on the current stream, fb() on the side stream, then join.  Fork/join discipline keeps the
+        caching allocator safe: every side-stream region starts after all earlier work of the main stream."""
+        if not self.parallel_streams:
+            return fa(), fb()
+        cur = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        side = self._side
+        side.wait_stream(cur)
+        ra = fa()
+        with torch.cuda.stream(side):
+            rb = fb()
+        cur.wait_stream(side)
+        return ra, rb
+
+    def _join_side(self):
+        if self.parallel_streams and self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
 
     # ------------------------------------------------------------------ device
     def _apply(self, fn, *a, **k):
@@ -145,8 +170,8 @@ class MUNIT_Trainer(nn.Module):
         def cat_act(u, v):
             return Act(torch.cat([u.t, v.t], 0), u.pad)
 
-        c_a = g.enc1_content.forward_act(x_a, 1)
-        c_b = g.enc2_content.forward_act(x_b, 1)
+        c_a, c_b = self._fork_join(lambda: g.enc1_content.forward_act(x_a, 1),
+                                   lambda: g.enc2_content.forward_act(x_b, 1))
         s_both = g.enc_style(torch.cat([x_a, x_b], 0))
         s_a_prime, s_b_prime = s_both[:b], s_both[b:]
         sty_a = s_a if self.guided == 0 else s_a_prime   # style used for the cross-domain decode into a
@@ -155,8 +180,8 @@ class MUNIT_Trainer(nn.Module):
         out2 = g.decode(cat_act(c_b, c_a), torch.cat([s_b_prime, sty_b], 0), 2)   # [x_b_recon; x_ab]
         x_a_recon, x_ba = out1[:b], out1[b:]
         x_b_recon, x_ab = out2[:b], out2[b:]
-        c_b_recon = g.enc1_content.forward_act(x_ba, 1)
-        c_a_recon = g.enc2_content.forward_act(x_ab, 1)
+        c_b_recon, c_a_recon = self._fork_join(lambda: g.enc1_content.forward_act(x_ba, 1),
+                                               lambda: g.enc2_content.forward_act(x_ab, 1))
         s_re = g.enc_style(torch.cat([x_ba, x_ab], 0))
         s_a_recon, s_b_recon = s_re[:b], s_re[b:]
         return (c_a, s_a_prime, c_b, s_b_prime, x_a_recon, x_b_recon, x_ba, x_ab, c_b_recon, s_a_recon, c_a_recon,
@@ -222,8 +247,11 @@ class MUNIT_Trainer(nn.Module):
             c_b_recon, s_a_recon = self._enc("a", x_ba)
             c_a_recon, s_b_recon = self._enc("b", x_ab)
         # decode again (if needed)
-        x_aba = self._dec("a", c_a_recon, s_a_prime) if cyc else None
-        x_bab = self._dec("b", c_b_recon, s_b_prime) if cyc else None
+        if cyc:
+            x_aba, x_bab = self._fork_join(lambda: self._dec("a", c_a_recon, s_a_prime),
+                                           lambda: self._dec("b", c_b_recon, s_b_prime))
+        else:
+            x_aba = x_bab = None
 
         # reconstruction loss
         self.loss_gen_recon_x_a = self.recon_criterion(x_a_recon, x_a)
@@ -244,8 +272,8 @@ class MUNIT_Trainer(nn.Module):
             self.loss_gen_cycrecon_x_a = self.recon_criterion(x_aba, x_a) if cyc else 0
             self.loss_gen_cycrecon_x_b = self.recon_criterion(x_bab, x_b) if cyc else 0
         # GAN loss (discriminator weights frozen: dgrad only)
-        self.loss_gen_adv_a = self.dis_a.calc_gen_loss(x_ba, frozen=True)
-        self.loss_gen_adv_b = self.dis_b.calc_gen_loss(x_ab, frozen=True)
+        self.loss_gen_adv_a, self.loss_gen_adv_b = self._fork_join(
+            lambda: self.dis_a.calc_gen_loss(x_ba, frozen=True), lambda: self.dis_b.calc_gen_loss(x_ab, frozen=True))
         self.loss_gen_vgg_a = 0
         self.loss_gen_vgg_b = 0
         self.loss_sem_seg = 0
@@ -266,6 +294,7 @@ class MUNIT_Trainer(nn.Module):
             + hyperparameters["recon_x_cyc_w"] * self.loss_gen_cycrecon_x_b
         )
         self.loss_gen_total.backward()
+        self._join_side()  # backward nodes ran on their forward streams; the optimiser step waits for both
         self._last = dict(x_ab=x_ab.detach(), x_ba=x_ba.detach())
         self._release_graph()
 
@@ -282,21 +311,20 @@ class MUNIT_Trainer(nn.Module):
         self.dis_opt.zero_grad()
         s_a, s_b = self._style_noise(x_a, x_b, s_a, s_b)
         with torch.no_grad():
-            c_a, s_a_prime = self._enc("a", x_a)
-            c_b, s_b_prime = self._enc("b", x_b)
+            (c_a, s_a_prime), (c_b, s_b_prime) = self._fork_join(lambda: self._enc("a", x_a), lambda: self._enc("b", x_b))
             if self.guided == 0:
-                x_ba = self._dec("a", c_b, s_a)
-                x_ab = self._dec("b", c_a, s_b)
+                sty_a, sty_b = s_a, s_b
             elif self.guided == 1:
-                x_ba = self._dec("a", c_b, s_a_prime)
-                x_ab = self._dec("b", c_a, s_b_prime)
+                sty_a, sty_b = s_a_prime, s_b_prime
             else:
                 print("self.guided unknown value:", self.guided)
+            x_ba, x_ab = self._fork_join(lambda: self._dec("a", c_b, sty_a), lambda: self._dec("b", c_a, sty_b))
         # D loss
-        self.loss_dis_a = self.dis_a.calc_dis_loss(x_ba.detach(), x_a)
-        self.loss_dis_b = self.dis_b.calc_dis_loss(x_ab.detach(), x_b)
+        self.loss_dis_a, self.loss_dis_b = self._fork_join(lambda: self.dis_a.calc_dis_loss(x_ba.detach(), x_a),
+                                                           lambda: self.dis_b.calc_dis_loss(x_ab.detach(), x_b))
         self.loss_dis_total = hyperparameters["gan_w"] * self.loss_dis_a + hyperparameters["gan_w"] * self.loss_dis_b
         self.loss_dis_total.backward()
+        self._join_side()
         self._release_graph()
 
     def _release_graph(self):
