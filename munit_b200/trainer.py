@@ -170,19 +170,22 @@ class MUNIT_Trainer(nn.Module):
         def cat_act(u, v):
             return Act(torch.cat([u.t, v.t], 0), u.pad)
 
-        c_a, c_b = self._fork_join(lambda: g.enc1_content.forward_act(x_a, 1),
-                                   lambda: g.enc2_content.forward_act(x_b, 1))
-        s_both = g.enc_style(torch.cat([x_a, x_b], 0))
+        xab_cat = torch.cat([x_a, x_b], 0)
+        (c_a, s_both), c_b = self._fork_join(lambda: (g.enc1_content.forward_act(x_a, 1), g.enc_style(xab_cat)),
+                                             lambda: g.enc2_content.forward_act(x_b, 1))
         s_a_prime, s_b_prime = s_both[:b], s_both[b:]
         sty_a = s_a if self.guided == 0 else s_a_prime   # style used for the cross-domain decode into a
         sty_b = s_b if self.guided == 0 else s_b_prime
-        out1 = g.decode(cat_act(c_a, c_b), torch.cat([s_a_prime, sty_a], 0), 1)   # [x_a_recon; x_ba]
-        out2 = g.decode(cat_act(c_b, c_a), torch.cat([s_b_prime, sty_b], 0), 2)   # [x_b_recon; x_ab]
+        in1, st1 = cat_act(c_a, c_b), torch.cat([s_a_prime, sty_a], 0)
+        in2, st2 = cat_act(c_b, c_a), torch.cat([s_b_prime, sty_b], 0)
+        out1, out2 = self._fork_join(lambda: g.decode(in1, st1, 1),    # [x_a_recon; x_ba]
+                                     lambda: g.decode(in2, st2, 2))    # [x_b_recon; x_ab]
         x_a_recon, x_ba = out1[:b], out1[b:]
         x_b_recon, x_ab = out2[:b], out2[b:]
-        c_b_recon, c_a_recon = self._fork_join(lambda: g.enc1_content.forward_act(x_ba, 1),
-                                               lambda: g.enc2_content.forward_act(x_ab, 1))
-        s_re = g.enc_style(torch.cat([x_ba, x_ab], 0))
+        xre_cat = torch.cat([x_ba, x_ab], 0)
+        (c_b_recon, s_re), c_a_recon = self._fork_join(
+            lambda: (g.enc1_content.forward_act(x_ba, 1), g.enc_style(xre_cat)),
+            lambda: g.enc2_content.forward_act(x_ab, 1))
         s_a_recon, s_b_recon = s_re[:b], s_re[b:]
         return (c_a, s_a_prime, c_b, s_b_prime, x_a_recon, x_b_recon, x_ba, x_ab, c_b_recon, s_a_recon, c_a_recon,
                 s_b_recon)
