@@ -79,6 +79,15 @@ typedef struct {
   int32_t halo;    /* 1: halo-resident variant (stride-1 rank-4 view, one phase, tw x th x tn = 8 x 16 x 1, taps on a
                       full KH x KW grid, KW <= 9): the activation tile + halo is loaded once per 64-channel chunk and
                       every tap reads it through a shifted UMMA descriptor.  0: one TMA box per tap. */
+  float* stats;    /* NULL, or where the epilogue leaves the normalisation statistics of the stored (bf16-rounded)
+                      output, so that no separate statistics pass re-reads it (first half of nn.InstanceNorm2d
+                      networks.py:657 / F.batch_norm networks.py:834 / LayerNorm networks.py:865-871).  Needs
+                      bn >= 64, phases == 1, tn == 1, full tiles, n_store == b_rows == C.  With T = tiles per image
+                      and q = 32-row quarter of a tile:
+                      stats_kind 1: stats[((n*4T + tile*4 + q)*C + c)*2 + {0,1}] = {sum x, sum x^2}  (per channel)
+                      stats_kind 2: stats[((n*4T + tile*4 + q)*(C/64) + c/64)*2 + {0,1}]             (channel-reduced)
+                      -> munit_norm_finalize_parts. */
+  int32_t stats_kind;
 } munit_tapgemm_desc;
 
 int munit_tapgemm(const munit_tapgemm_desc* d, void* stream);
@@ -161,6 +170,12 @@ enum { MUNIT_NORM_IN = 0, MUNIT_NORM_ADAIN = 1, MUNIT_NORM_LN = 2 };
 int munit_norm_finalize(const float* stats, const float* shift, int mode, const float* p_w, const float* p_b,
                         int64_t ldw, float eps, float* mean, float* rinv, float* a, float* b, int n, int hw, int c,
                         void* stream);
+/* Same, from the split partials a convolution epilogue left (munit_tapgemm_desc.stats): `splits` partials per
+ * sample, unshifted sums.  kind 1: per-channel partials [N][splits][C][2], mode IN or ADAIN; kind 2: channel-reduced
+ * partials [N][splits][2], mode LN. */
+int munit_norm_finalize_parts(const float* stats, int splits, int kind, int mode, const float* p_w, const float* p_b,
+                              int64_t ldw, float eps, float* mean, float* rinv, float* a, float* b, int n, int hw,
+                              int c, void* stream);
 /* out_act[interior (+halo) (+2x nearest upsample)] = relu?(a*y + b) (+ residual interior).
  * residual (may be NULL) is an act buffer with halo res_pad and the same H, W, C. */
 int munit_norm_apply(const void* y, const float* a, const float* b, int relu, const void* residual, int res_pad,
@@ -180,6 +195,37 @@ int munit_norm_bwd_finalize(const float* sums, int mode, const float* p_w, int64
 int munit_norm_bwd_apply(const void* g_out, int out_pad, int upsample, const void* y, const float* a, const float* b,
                          int relu, const float* mean, const float* rinv, const float* ca, const float* cb,
                          const float* cc, void* dy, void* g_res, int res_pad, int n, int h, int w, int c, void* stream);
+
+/* Fused variants: ONE cooperative launch runs statistics -> finalize -> apply (forward) or reduce -> finalize ->
+ * apply (backward) with grid-wide barriers in between, so the second read of y / g_out is served by L2 when the
+ * caller keeps n*(bytes per sample) within it (munit_b200/kernels.py chunks the batch) and two kernel boundaries
+ * per normalisation disappear.  Arguments mean what they mean in the three stand-alone calls above; `part` is the
+ * split-partial workspace of N*S*C*2 floats with S = munit_norm_fused_splits(...).  That call returns 0 when the
+ * shape cannot be co-resident on the device (caller falls back to the three-call sequence). */
+int munit_norm_fused_splits(int n, int hw, int c, int mode, int backward, int upsample);
+int munit_norm_fwd_fused(const void* y, float* part, float* shift, int mode, const float* p_w, const float* p_b,
+                         int64_t ldw, float eps, float* mean, float* rinv, float* a, float* b, int relu,
+                         const void* residual, int res_pad, void* out_act, int out_pad, int upsample, int n, int h, int w,
+                         int c, void* stream);
+int munit_norm_bwd_fused(const void* g_out, int out_pad, int upsample, const void* y, const float* a, const float* b,
+                         int relu, const float* mean, const float* rinv, float* part, int mode, const float* p_w,
+                         int64_t ldw, float eps, float* ca, float* cb, float* cc, float* g_w, float* g_b, int64_t ldg,
+                         void* dy, void* g_res, int res_pad, int n, int h, int w, int c, void* stream);
+
+/* Slab-resident InstanceNorm / AdaIN: a thread-block cluster owns (sample, 16 channels), keeps its part of the slab
+ * in shared memory between the statistics and the apply pass and combines the per-CTA sums over distributed
+ * shared memory - one launch and one DRAM pass over the inputs instead of three launches and two passes.
+ * munit_norm_slab_ok returns the cluster size (> 0) when (mode, upsample, hw, c) can run this way (IN / ADAIN,
+ * upsample 1, c % 16 == 0, hw <= 16384 forward / backward), else 0.  Arguments as in the stand-alone calls; the
+ * forward also writes mean / rinv / a / b for the backward. */
+int munit_norm_slab_ok(int mode, int upsample, int hw, int c, int backward);
+int munit_norm_fwd_slab(const void* y, int mode, const float* p_w, const float* p_b, int64_t ldw, float eps,
+                        float* mean, float* rinv, float* a, float* b, int relu, const void* residual, int res_pad,
+                        void* out_act, int out_pad, int n, int h, int w, int c, void* stream);
+int munit_norm_bwd_slab(const void* g_out, int out_pad, const void* y, const float* a, const float* b, int relu,
+                        const float* mean, const float* rinv, int mode, const float* p_w, int64_t ldw, float* g_w,
+                        float* g_b, int64_t ldg, void* dy, void* g_res, int res_pad, int n, int h, int w, int c,
+                        void* stream);
 
 /* No-norm conv blocks: dy [N][H][W][C] = fold(g_out_act) * act'(out) where out is the forward output
  * (interior of out_act, halo `pad`; g_out has the same padded extent). */

@@ -31,6 +31,7 @@ class TapGemmDesc(C.Structure):
         ("out", C.c_void_p), ("o_sn", C.c_int64), ("o_sy", C.c_int64), ("o_sx", C.c_int64),
         ("o_ymul", C.c_int32), ("o_xmul", C.c_int32), ("n_store", C.c_int32),
         ("bias", C.c_void_p), ("act", C.c_int32), ("stages", C.c_int32), ("cluster", C.c_int32), ("halo", C.c_int32),
+        ("stats", C.c_void_p), ("stats_kind", C.c_int32),
     ]
 
 
@@ -73,10 +74,21 @@ _SIGS = {
     "munit_norm_splits": ([_i, _i], C.c_int),
     "munit_norm_stats": ([_vp, _vp, _vp, _i, _i, _i, _vp], C.c_int),
     "munit_norm_finalize": ([_vp, _vp, _i, _vp, _vp, _i64, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp], C.c_int),
+    "munit_norm_finalize_parts": ([_vp, _i, _i, _i, _vp, _vp, _i64, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp], C.c_int),
     "munit_norm_apply": ([_vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp], C.c_int),
     "munit_norm_bwd_reduce": ([_vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp], C.c_int),
     "munit_norm_bwd_finalize": ([_vp, _i, _vp, _i64, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp], C.c_int),
     "munit_norm_bwd_apply": ([_vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], C.c_int),
+    "munit_norm_fused_splits": ([_i, _i, _i, _i, _i, _i], C.c_int),
+    "munit_norm_fwd_fused": ([_vp, _vp, _vp, _i, _vp, _vp, _i64, _f, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i,
+                              _i, _i, _vp], C.c_int),
+    "munit_norm_bwd_fused": ([_vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i64, _f, _vp, _vp, _vp, _vp, _vp,
+                              _i64, _vp, _vp, _i, _i, _i, _i, _i, _vp], C.c_int),
+    "munit_norm_slab_ok": ([_i, _i, _i, _i, _i], C.c_int),
+    "munit_norm_fwd_slab": ([_vp, _i, _vp, _vp, _i64, _f, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
+                            C.c_int),
+    "munit_norm_bwd_slab": ([_vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i,
+                             _i, _vp], C.c_int),
     "munit_act_bwd": ([_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp], C.c_int),
     "munit_colsum": ([_vp, _vp, _i64, _i, _i, _vp], C.c_int),
     "munit_rspace_combine": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], C.c_int),

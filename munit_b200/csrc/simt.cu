@@ -1,6 +1,7 @@
 // Bandwidth-bound SIMT kernels of the MUNIT hot path (sm_100a): layout conversion, reflect halo,
 // InstanceNorm / AdaIN / LayerNorm forward+backward, activations, pooling, losses, MLP, Adam.
 // All activations are NHWC bf16 accessed as 128-bit (8-channel) vectors; statistics are fp32.
+#include <cooperative_groups.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -8,6 +9,8 @@
 
 #include "../../include/munit_b200.h"
 #include "common.h"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -197,15 +200,22 @@ __global__ void halo_fill_kernel(bf16* __restrict__ act, int n, int h, int w, in
 // two 8-channel vectors to accumulate.  Partial sums are combined in smem and written to
 // part[((n*splits + split)*C + c)*2 + {0,1}]; the finalize kernels add the splits in a fixed order, so
 // the statistics (and with them the whole forward pass) are bit-reproducible run to run.
+// Which (pixel split, sample) a block works on.  The stand-alone kernels take it from the launch grid; the fused
+// cooperative kernels (one launch = reduce -> finalize -> apply) pass the same triple to every phase.
+struct Blk {
+  int bx, nbx, by;
+};
+__device__ __forceinline__ Blk launch_blk() { return Blk{(int)blockIdx.x, (int)gridDim.x, (int)blockIdx.y}; }
+
 template <typename Fn>
-__device__ __forceinline__ void reduce_nc(Fn fn, float* __restrict__ out2, int hw, int c) {
+__device__ __forceinline__ void reduce_nc(Blk blk, Fn fn, float* __restrict__ out2, int hw, int c) {
   extern __shared__ float red[];  // [R][C][2]
   const int cgs = c / 8;
   const int rows = blockDim.x / cgs;
   const int cg = threadIdx.x % cgs, r = threadIdx.x / cgs;
-  const int n = blockIdx.y;
-  const int per = (hw + gridDim.x - 1) / gridDim.x;
-  const int p0 = blockIdx.x * per;
+  const int n = blk.by;
+  const int per = (hw + blk.nbx - 1) / blk.nbx;
+  const int p0 = blk.bx * per;
   const int p1 = min(hw, p0 + per);
   float s0[8], s1[8];
 #pragma unroll
@@ -235,7 +245,7 @@ __device__ __forceinline__ void reduce_nc(Fn fn, float* __restrict__ out2, int h
       a += red[((rr * c) + ch) * 2 + 0];
       b += red[((rr * c) + ch) * 2 + 1];
     }
-    float* dst = out2 + (((long long)n * gridDim.x + blockIdx.x) * c + ch) * 2;
+    float* dst = out2 + (((long long)n * blk.nbx + blk.bx) * c + ch) * 2;
     dst[0] = a;
     dst[1] = b;
   }
@@ -266,10 +276,10 @@ __device__ __forceinline__ void sum_splits_to_smem(const float* __restrict__ par
   __syncthreads();
 }
 
-__global__ void norm_stats_kernel(const bf16* __restrict__ y, float* __restrict__ stats, float* __restrict__ shift,
-                                  int hw, int c) {
+__device__ __forceinline__ void norm_stats_body(Blk blk, const bf16* __restrict__ y, float* __restrict__ stats,
+                                                float* __restrict__ shift, int hw, int c) {
   const int cg_own = threadIdx.x % (c / 8);
-  const F8 s = load8(y + ((long long)blockIdx.y * hw) * c + cg_own * 8);  // per-thread constant: hoisted
+  const F8 s = load8(y + ((long long)blk.by * hw) * c + cg_own * 8);  // per-thread constant: hoisted
   auto fn = [&](int n, int pix, int cg, F8& u, F8& v) {
     const F8 x = load8(y + ((long long)n * hw + pix) * c + cg * 8);
 #pragma unroll
@@ -279,10 +289,14 @@ __global__ void norm_stats_kernel(const bf16* __restrict__ y, float* __restrict_
       v.v[e] = d * d;
     }
   };
-  reduce_nc(fn, stats, hw, c);
-  if (blockIdx.x == 0)
+  reduce_nc(blk, fn, stats, hw, c);
+  if (blk.bx == 0)
     for (int ch = threadIdx.x; ch < c; ch += blockDim.x)
-      shift[(long long)blockIdx.y * c + ch] = __bfloat162float(y[((long long)blockIdx.y * hw) * c + ch]);
+      shift[(long long)blk.by * c + ch] = __bfloat162float(y[((long long)blk.by * hw) * c + ch]);
+}
+__global__ void norm_stats_kernel(const bf16* __restrict__ y, float* __restrict__ stats, float* __restrict__ shift,
+                                  int hw, int c) {
+  norm_stats_body(launch_blk(), y, stats, shift, hw, c);
 }
 
 __global__ void colsum_kernel(const bf16* __restrict__ dy, float* __restrict__ out, long long npix, int c, int c_out) {
@@ -317,13 +331,14 @@ __global__ void colsum_kernel(const bf16* __restrict__ dy, float* __restrict__ o
 
 // IN / AdaIN finalize, parallel over channels: grid (C/32, N), 256 threads = 32 channels x 8 split lanes; the 8
 // lane partials are added in lane order (deterministic).
-__global__ void norm_finalize_nc_kernel(const float* __restrict__ stats, int splits, const float* __restrict__ shift,
-                                        int adain, const float* __restrict__ p_w, const float* __restrict__ p_b,
-                                        long long ldw, float eps, float* __restrict__ mean, float* __restrict__ rinv,
-                                        float* __restrict__ a, float* __restrict__ b, int hw, int c) {
+__device__ __forceinline__ void norm_finalize_nc_body(int bx, int n, const float* __restrict__ stats, int splits,
+                                                      const float* __restrict__ shift, int adain,
+                                                      const float* __restrict__ p_w, const float* __restrict__ p_b,
+                                                      long long ldw, float eps, float* __restrict__ mean,
+                                                      float* __restrict__ rinv, float* __restrict__ a,
+                                                      float* __restrict__ b, int hw, int c) {
   __shared__ double sh[8][32][2];
-  const int n = blockIdx.y;
-  const int ch = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ch = bx * 32 + (threadIdx.x & 31);
   const int lane = threadIdx.x >> 5;  // split lane 0..7
   double s1 = 0.0, s2 = 0.0;
   if (ch < c) {
@@ -348,7 +363,7 @@ __global__ void norm_finalize_nc_kernel(const float* __restrict__ stats, int spl
     const double m1 = a1 / cnt;
     double var = a2 / cnt - m1 * m1;  // biased (F.batch_norm / InstanceNorm2d)
     if (var < 0.0) var = 0.0;
-    const float mu = (float)((double)shift[i] + m1);
+    const float mu = (float)((shift ? (double)shift[i] : 0.0) + m1);
     const float ri = (float)(1.0 / sqrt(var + (double)eps));
     float wv = 1.f, bv = 0.f;
     if (adain) {
@@ -362,15 +377,21 @@ __global__ void norm_finalize_nc_kernel(const float* __restrict__ stats, int spl
     b[i] = bv - mu * aa;
   }
 }
+__global__ void norm_finalize_nc_kernel(const float* __restrict__ stats, int splits, const float* __restrict__ shift,
+                                        int adain, const float* __restrict__ p_w, const float* __restrict__ p_b,
+                                        long long ldw, float eps, float* __restrict__ mean, float* __restrict__ rinv,
+                                        float* __restrict__ a, float* __restrict__ b, int hw, int c) {
+  norm_finalize_nc_body(blockIdx.x, blockIdx.y, stats, splits, shift, adain, p_w, p_b, ldw, eps, mean, rinv, a, b, hw, c);
+}
 // IN / AdaIN backward finalize, same mapping.
-__global__ void norm_bwd_finalize_nc_kernel(const float* __restrict__ sums, int splits, int adain,
-                                            const float* __restrict__ p_w, long long ldw,
-                                            const float* __restrict__ rinv, float* __restrict__ ca,
-                                            float* __restrict__ cb, float* __restrict__ cc, float* __restrict__ g_w,
-                                            float* __restrict__ g_b, long long ldg, int hw, int c) {
+__device__ __forceinline__ void norm_bwd_finalize_nc_body(int bx, int n, const float* __restrict__ sums, int splits,
+                                                          int adain, const float* __restrict__ p_w, long long ldw,
+                                                          const float* __restrict__ rinv, float* __restrict__ ca,
+                                                          float* __restrict__ cb, float* __restrict__ cc,
+                                                          float* __restrict__ g_w, float* __restrict__ g_b,
+                                                          long long ldg, int hw, int c) {
   __shared__ double sh[8][32][2];
-  const int n = blockIdx.y;
-  const int ch = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ch = bx * 32 + (threadIdx.x & 31);
   const int lane = threadIdx.x >> 5;
   double s1 = 0.0, s2 = 0.0;
   if (ch < c) {
@@ -404,13 +425,21 @@ __global__ void norm_bwd_finalize_nc_kernel(const float* __restrict__ sums, int 
     }
   }
 }
+__global__ void norm_bwd_finalize_nc_kernel(const float* __restrict__ sums, int splits, int adain,
+                                            const float* __restrict__ p_w, long long ldw,
+                                            const float* __restrict__ rinv, float* __restrict__ ca,
+                                            float* __restrict__ cb, float* __restrict__ cc, float* __restrict__ g_w,
+                                            float* __restrict__ g_b, long long ldg, int hw, int c) {
+  norm_bwd_finalize_nc_body(blockIdx.x, blockIdx.y, sums, splits, adain, p_w, ldw, rinv, ca, cb, cc, g_w, g_b, ldg, hw, c);
+}
 
 // one block per sample
-__global__ void norm_finalize_kernel(const float* __restrict__ stats, int splits, const float* __restrict__ shift, int mode,
-                                     const float* __restrict__ p_w, const float* __restrict__ p_b, long long ldw,
-                                     float eps, float* __restrict__ mean, float* __restrict__ rinv,
-                                     float* __restrict__ a, float* __restrict__ b, int hw, int c) {
-  const int n = blockIdx.x;
+__device__ __forceinline__ void norm_finalize_body(int n, const float* __restrict__ stats, int splits,
+                                                   const float* __restrict__ shift, int mode,
+                                                   const float* __restrict__ p_w, const float* __restrict__ p_b,
+                                                   long long ldw, float eps, float* __restrict__ mean,
+                                                   float* __restrict__ rinv, float* __restrict__ a,
+                                                   float* __restrict__ b, int hw, int c) {
   __shared__ double sh[2][32];
   __shared__ double tot[2];
   extern __shared__ double ssum[];  // [c][2]
@@ -478,21 +507,66 @@ __global__ void norm_finalize_kernel(const float* __restrict__ stats, int splits
     }
   }
 }
+__global__ void norm_finalize_kernel(const float* __restrict__ stats, int splits, const float* __restrict__ shift, int mode,
+                                     const float* __restrict__ p_w, const float* __restrict__ p_b, long long ldw,
+                                     float eps, float* __restrict__ mean, float* __restrict__ rinv,
+                                     float* __restrict__ a, float* __restrict__ b, int hw, int c) {
+  norm_finalize_body(blockIdx.x, stats, splits, shift, mode, p_w, p_b, ldw, eps, mean, rinv, a, b, hw, c);
+}
+
+// LayerNorm finalize from channel-reduced, unshifted partials [N][splits][2] (convolution epilogue statistics):
+// one block per sample, partials added in a fixed order in double.
+__global__ void norm_finalize_ln_total_kernel(const float* __restrict__ part, int splits, const float* __restrict__ p_w,
+                                              const float* __restrict__ p_b, float eps, float* __restrict__ mean,
+                                              float* __restrict__ rinv, float* __restrict__ a, float* __restrict__ b,
+                                              int hw, int c) {
+  __shared__ double sh[2][256];
+  const int n = blockIdx.x;
+  const float2* p = reinterpret_cast<const float2*>(part) + (long long)n * splits;
+  double s1 = 0.0, s2 = 0.0;
+  for (int s = threadIdx.x; s < splits; s += blockDim.x) {
+    const float2 v = p[s];
+    s1 += (double)v.x;
+    s2 += (double)v.y;
+  }
+  sh[0][threadIdx.x] = s1;
+  sh[1][threadIdx.x] = s2;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
+      sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  const double nel = (double)hw * c;
+  const double mu = sh[0][0] / nel;
+  const double var = fmax(sh[1][0] - nel * mu * mu, 0.0) / (nel - 1.0);  // unbiased (networks.py:868,871)
+  const float ri = (float)(1.0 / (sqrt(var) + (double)eps));              // eps outside the sqrt (networks.py:873)
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    const float aa = p_w[ch] * ri;
+    mean[(long long)n * c + ch] = (float)mu;
+    rinv[(long long)n * c + ch] = ri;
+    a[(long long)n * c + ch] = aa;
+    b[(long long)n * c + ch] = p_b[ch] - (float)mu * aa;
+  }
+}
 
 // Block = CG channel groups x R rows (256 threads), grid = (pixel splits, N): a thread keeps its (n, channel
 // group) coefficients in registers and walks pixels, so the per-(n,c) vectors are read once per thread.
 template <int UP>
-__global__ void norm_apply_kernel(const bf16* __restrict__ y, const float* __restrict__ a, const float* __restrict__ b,
-                                  int relu, const bf16* __restrict__ res, int res_pad, bf16* __restrict__ out,
-                                  int out_pad, int n, int h, int w, int c) {
+__device__ __forceinline__ void norm_apply_body(Blk blk, const bf16* __restrict__ y, const float* __restrict__ a,
+                                                const float* __restrict__ b, int relu, const bf16* __restrict__ res,
+                                                int res_pad, bf16* __restrict__ out, int out_pad, int n, int h, int w,
+                                                int c) {
   const int cgs = c / 8;
   const int rows = blockDim.x / cgs;
   const int g = threadIdx.x % cgs, r = threadIdx.x / cgs;
   if (r >= rows) return;
-  const int bb = blockIdx.y;
+  const int bb = blk.by;
   const int hw = h * w;
-  const int per = (hw + gridDim.x - 1) / gridDim.x;
-  const int p0 = blockIdx.x * per, p1 = min(hw, p0 + per);
+  const int per = (hw + blk.nbx - 1) / blk.nbx;
+  const int p0 = blk.bx * per, p1 = min(hw, p0 + per);
   const int ho = h * UP, wo = w * UP;
   const int hop = ho + 2 * out_pad, wop = wo + 2 * out_pad;
   const F8 fa = loadf8(a + (long long)bb * c + g * 8), fb = loadf8(b + (long long)bb * c + g * 8);
@@ -531,6 +605,12 @@ __global__ void norm_apply_kernel(const bf16* __restrict__ y, const float* __res
       }
     }
   }
+}
+template <int UP>
+__global__ void norm_apply_kernel(const bf16* __restrict__ y, const float* __restrict__ a, const float* __restrict__ b,
+                                  int relu, const bf16* __restrict__ res, int res_pad, bf16* __restrict__ out,
+                                  int out_pad, int n, int h, int w, int c) {
+  norm_apply_body<UP>(launch_blk(), y, a, b, relu, res, res_pad, out, out_pad, n, h, w, c);
 }
 
 // gradient w.r.t. the unpadded, un-upsampled pixel: sum of g_out over every position that copied it.
@@ -577,13 +657,13 @@ __device__ __forceinline__ F8 fold_grad(const bf16* __restrict__ g_out, int bb, 
 // sums = {sum dz, sum dz*(x - mean)}; the finalize kernels multiply the second by rinv (keeps this loop at 3
 // coefficient vectors so that four blocks fit per SM).
 template <int UP>
-__global__ void __launch_bounds__(256, 3)
-norm_bwd_reduce_kernel(const bf16* __restrict__ g_out, int out_pad, const bf16* __restrict__ y,
-                                       const float* __restrict__ a, const float* __restrict__ b, int relu,
-                                       const float* __restrict__ mean, const float* __restrict__ rinv,
-                                       float* __restrict__ sums, int h, int w, int c) {
+__device__ __forceinline__ void norm_bwd_reduce_body(Blk blk, const bf16* __restrict__ g_out, int out_pad,
+                                                     const bf16* __restrict__ y, const float* __restrict__ a,
+                                                     const float* __restrict__ b, int relu,
+                                                     const float* __restrict__ mean, float* __restrict__ sums, int h,
+                                                     int w, int c) {
   const int hw = h * w;
-  const long long co = (long long)blockIdx.y * c + (threadIdx.x % (c / 8)) * 8;  // this thread's (n, channel group)
+  const long long co = (long long)blk.by * c + (threadIdx.x % (c / 8)) * 8;  // this thread's (n, channel group)
   const F8 fa = loadf8(a + co), fb = loadf8(b + co), fm = loadf8(mean + co);
   auto fn = [&](int n, int pix, int cg, F8& u, F8& v) {
     const int yy = pix / w, x = pix - yy * w;
@@ -597,16 +677,24 @@ norm_bwd_reduce_kernel(const bf16* __restrict__ g_out, int out_pad, const bf16* 
       v.v[e] = dz * (xv.v[e] - fm.v[e]);
     }
   };
-  reduce_nc(fn, sums, hw, c);
+  reduce_nc(blk, fn, sums, hw, c);
+}
+template <int UP>
+__global__ void __launch_bounds__(256, 3)
+norm_bwd_reduce_kernel(const bf16* __restrict__ g_out, int out_pad, const bf16* __restrict__ y,
+                                       const float* __restrict__ a, const float* __restrict__ b, int relu,
+                                       const float* __restrict__ mean, const float* __restrict__ rinv,
+                                       float* __restrict__ sums, int h, int w, int c) {
+  norm_bwd_reduce_body<UP>(launch_blk(), g_out, out_pad, y, a, b, relu, mean, sums, h, w, c);
 }
 
 // one block per sample
-__global__ void norm_bwd_finalize_kernel(const float* __restrict__ sums, int splits, int mode, const float* __restrict__ p_w,
-                                         long long ldw, const float* __restrict__ rinv, float eps,
-                                         float* __restrict__ ca, float* __restrict__ cb, float* __restrict__ cc,
-                                         float* __restrict__ g_w, float* __restrict__ g_b, long long ldg, int hw,
-                                         int c) {
-  const int n = blockIdx.x;
+__device__ __forceinline__ void norm_bwd_finalize_body(int n, const float* __restrict__ sums, int splits, int mode,
+                                                       const float* __restrict__ p_w, long long ldw,
+                                                       const float* __restrict__ rinv, float eps,
+                                                       float* __restrict__ ca, float* __restrict__ cb,
+                                                       float* __restrict__ cc, float* __restrict__ g_w,
+                                                       float* __restrict__ g_b, long long ldg, int hw, int c) {
   const double cnt = (double)hw;
   extern __shared__ double ssum[];  // [c][2]
   sum_splits_to_smem(sums, n, splits, c, ssum);
@@ -669,23 +757,30 @@ __global__ void norm_bwd_finalize_kernel(const float* __restrict__ sums, int spl
     }
   }
 }
+__global__ void norm_bwd_finalize_kernel(const float* __restrict__ sums, int splits, int mode, const float* __restrict__ p_w,
+                                         long long ldw, const float* __restrict__ rinv, float eps,
+                                         float* __restrict__ ca, float* __restrict__ cb, float* __restrict__ cc,
+                                         float* __restrict__ g_w, float* __restrict__ g_b, long long ldg, int hw,
+                                         int c) {
+  norm_bwd_finalize_body(blockIdx.x, sums, splits, mode, p_w, ldw, rinv, eps, ca, cb, cc, g_w, g_b, ldg, hw, c);
+}
 
 template <int UP>
-__global__ void __launch_bounds__(256, 3)
-norm_bwd_apply_kernel(const bf16* __restrict__ g_out, int out_pad, const bf16* __restrict__ y,
-                                      const float* __restrict__ a, const float* __restrict__ b, int relu,
-                                      const float* __restrict__ mean, const float* __restrict__ rinv,
-                                      const float* __restrict__ ca, const float* __restrict__ cb,
-                                      const float* __restrict__ cc, bf16* __restrict__ dy, bf16* __restrict__ g_res,
-                                      int res_pad, int n, int h, int w, int c) {
+__device__ __forceinline__ void norm_bwd_apply_body(Blk blk, const bf16* __restrict__ g_out, int out_pad,
+                                                    const bf16* __restrict__ y, const float* __restrict__ a,
+                                                    const float* __restrict__ b, int relu,
+                                                    const float* __restrict__ mean, const float* __restrict__ rinv,
+                                                    const float* __restrict__ ca, const float* __restrict__ cb,
+                                                    const float* __restrict__ cc, bf16* __restrict__ dy,
+                                                    bf16* __restrict__ g_res, int res_pad, int n, int h, int w, int c) {
   const int cgs = c / 8;
   const int rows = blockDim.x / cgs;
   const int g = threadIdx.x % cgs, r = threadIdx.x / cgs;
   if (r >= rows) return;
-  const int bb = blockIdx.y;
+  const int bb = blk.by;
   const int hw = h * w;
-  const int per = (hw + gridDim.x - 1) / gridDim.x;
-  const int p0 = blockIdx.x * per, p1 = min(hw, p0 + per);
+  const int per = (hw + blk.nbx - 1) / blk.nbx;
+  const int p0 = blk.bx * per, p1 = min(hw, p0 + per);
   const long long o = (long long)bb * c + g * 8;
   const F8 fa = loadf8(a + o), fb = loadf8(b + o), fca = loadf8(ca + o);
   F8 k1, k0;  // dx = ca*dz + cb*xhat + cc = ca*dz + k1*x + k0 with k1 = cb*rinv, k0 = cc - k1*mean
@@ -713,6 +808,83 @@ norm_bwd_apply_kernel(const bf16* __restrict__ g_out, int out_pad, const bf16* _
     store8(dy + i8, d);
     if (g_res) store8(g_res + (((long long)bb * (h + 2 * res_pad) + yy + res_pad) * (w + 2 * res_pad) + x + res_pad) * c + g * 8, gr);
   }
+}
+template <int UP>
+__global__ void __launch_bounds__(256, 3)
+norm_bwd_apply_kernel(const bf16* __restrict__ g_out, int out_pad, const bf16* __restrict__ y,
+                                      const float* __restrict__ a, const float* __restrict__ b, int relu,
+                                      const float* __restrict__ mean, const float* __restrict__ rinv,
+                                      const float* __restrict__ ca, const float* __restrict__ cb,
+                                      const float* __restrict__ cc, bf16* __restrict__ dy, bf16* __restrict__ g_res,
+                                      int res_pad, int n, int h, int w, int c) {
+  norm_bwd_apply_body<UP>(launch_blk(), g_out, out_pad, y, a, b, relu, mean, rinv, ca, cb, cc, dy, g_res, res_pad, n, h, w, c);
+}
+
+// ---- fused cooperative norm kernels: reduce -> grid sync -> finalize -> grid sync -> apply in ONE launch.  The
+// second read of y / g_out then comes from L2 (the host side sizes the sample chunk of a launch to fit), and two
+// kernel boundaries per normalisation disappear.  The phases are the bodies of the stand-alone kernels above, so
+// the arithmetic is identical up to the number of pixel splits.
+struct NormFusedArgs {
+  const bf16* y;
+  float* part;  // [n][splits][c][2] split partials (stats in the forward, sums in the backward)
+  float* shift;
+  int mode;
+  const float* p_w;
+  const float* p_b;
+  long long ldw;
+  float eps;
+  float *mean, *rinv, *a, *b;
+  int relu;
+  const bf16* res;  // fwd: residual input; bwd: unused
+  int res_pad;
+  bf16* out;  // fwd: output act
+  int out_pad;
+  // backward only
+  const bf16* g_out;
+  float *ca, *cb, *cc, *g_w, *g_b;
+  long long ldg;
+  bf16* dy;
+  bf16* g_res;
+  int n, h, w, c;
+};
+
+template <int UP>
+__global__ void __launch_bounds__(256, 3) norm_fwd_fused_kernel(const NormFusedArgs p) {
+  cg::grid_group grid = cg::this_grid();
+  const Blk blk = launch_blk();
+  const int hw = p.h * p.w;
+  norm_stats_body(blk, p.y, p.part, p.shift, hw, p.c);
+  grid.sync();
+  if (p.mode != MUNIT_NORM_LN) {
+    if (blk.bx < (p.c + 31) / 32)
+      norm_finalize_nc_body(blk.bx, blk.by, p.part, blk.nbx, p.shift, p.mode == MUNIT_NORM_ADAIN, p.p_w, p.p_b, p.ldw,
+                            p.eps, p.mean, p.rinv, p.a, p.b, hw, p.c);
+  } else if (blk.bx == 0) {
+    norm_finalize_body(blk.by, p.part, blk.nbx, p.shift, p.mode, p.p_w, p.p_b, p.ldw, p.eps, p.mean, p.rinv, p.a, p.b,
+                       hw, p.c);
+  }
+  grid.sync();
+  norm_apply_body<UP>(blk, p.y, p.a, p.b, p.relu, p.res, p.res_pad, p.out, p.out_pad, p.n, p.h, p.w, p.c);
+}
+
+template <int UP>
+__global__ void __launch_bounds__(256, 2) norm_bwd_fused_kernel(const NormFusedArgs p) {
+  cg::grid_group grid = cg::this_grid();
+  const Blk blk = launch_blk();
+  const int hw = p.h * p.w;
+  norm_bwd_reduce_body<UP>(blk, p.g_out, p.out_pad, p.y, p.a, p.b, p.relu, p.mean, p.part, p.h, p.w, p.c);
+  grid.sync();
+  if (p.mode != MUNIT_NORM_LN) {
+    if (blk.bx < (p.c + 31) / 32)
+      norm_bwd_finalize_nc_body(blk.bx, blk.by, p.part, blk.nbx, p.mode == MUNIT_NORM_ADAIN, p.p_w, p.ldw, p.rinv,
+                                p.ca, p.cb, p.cc, p.g_w, p.g_b, p.ldg, hw, p.c);
+  } else if (blk.bx == 0) {
+    norm_bwd_finalize_body(blk.by, p.part, blk.nbx, p.mode, p.p_w, p.ldw, p.rinv, p.eps, p.ca, p.cb, p.cc, p.g_w,
+                           p.g_b, p.ldg, hw, p.c);
+  }
+  grid.sync();
+  norm_bwd_apply_body<UP>(blk, p.g_out, p.out_pad, p.y, p.a, p.b, p.relu, p.mean, p.rinv, p.ca, p.cb, p.cc, p.dy,
+                          p.g_res, p.res_pad, p.n, p.h, p.w, p.c);
 }
 
 __global__ void act_bwd_kernel(const bf16* __restrict__ g_out, const bf16* __restrict__ out_act, int pad, int act,
@@ -1151,6 +1323,299 @@ __global__ void add_bf16_kernel(bf16* __restrict__ dst, const bf16* __restrict__
   }
 }
 
+
+// ---- slab-resident InstanceNorm / AdaIN (one launch, one DRAM pass over the inputs) ---------------------------
+// IN / AdaIN statistics are independent per (sample, channel), so a thread-block cluster can own the slab
+// (sample n, 16 channels): each CTA of the cluster takes a pixel range, parks its part of the slab in shared memory
+// while it accumulates the sums, the per-CTA sums are combined over distributed shared memory in rank order
+// (deterministic), and the apply pass then reads shared memory instead of DRAM / L2.  No grid-wide barrier, 32 B
+// (full-sector) accesses per pixel.  Shapes whose slab does not fit (hw / 16 > the per-CTA pixel budget), LayerNorm
+// and the up-sampling apply use the three-kernel path.
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t slab_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t slab_cluster_size() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void slab_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem_f32(const float* local, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_addr_u32(local)), "r"(rank));
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+  return v;
+}
+__device__ __forceinline__ F8 unpack8(const uint4& u) {
+  F8 r;
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    r.v[2 * i] = f.x;
+    r.v[2 * i + 1] = f.y;
+  }
+  return r;
+}
+__device__ __forceinline__ uint4 pack8(const F8& r) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(r.v[2 * i], r.v[2 * i + 1]);
+  return u;
+}
+// Sum this block's per-thread {u, v} 8-channel vectors (thread parity = which 8-channel half of the 16-channel
+// slab) into cpart[16][2] in a fixed order: xor-shuffles over equal-parity lanes, then the 8 warps in index order.
+__device__ __forceinline__ void slab_block_reduce(const float* s0, const float* s1, float (*wred)[2][8][2],
+                                                  float (*cpart)[2]) {
+  float a[8], b[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    a[e] = s0[e];
+    b[e] = s1[e];
+  }
+#pragma unroll
+  for (int o = 2; o < 32; o <<= 1) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      a[e] += __shfl_xor_sync(0xffffffffu, a[e], o);
+      b[e] += __shfl_xor_sync(0xffffffffu, b[e], o);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane < 2) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      wred[warp][lane][e][0] = a[e];
+      wred[warp][lane][e][1] = b[e];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int ch = threadIdx.x >> 1, k = threadIdx.x & 1;
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += wred[w][ch >> 3][ch & 7][k];
+    cpart[ch][k] = t;
+  }
+}
+
+struct NormSlabArgs {
+  const bf16* y;
+  int mode;  // MUNIT_NORM_IN or MUNIT_NORM_ADAIN
+  const float* p_w;
+  const float* p_b;
+  long long ldw;
+  float eps;
+  float *mean, *rinv, *a, *b;
+  int relu;
+  const bf16* res;
+  int res_pad;
+  bf16* out;
+  int out_pad;
+  // backward
+  const bf16* g_out;
+  float *g_w, *g_b;
+  long long ldg;
+  bf16* dy;
+  bf16* g_res;
+  int n, h, w, c;
+  int per;  // pixels per CTA
+};
+
+__global__ void __launch_bounds__(256, 4) norm_fwd_slab_kernel(const NormSlabArgs p) {
+  extern __shared__ __align__(16) uint8_t slab_raw[];
+  uint4* slab = reinterpret_cast<uint4*>(slab_raw);  // [per][2] 8-channel chunks of y
+  __shared__ float wred[8][2][8][2];
+  __shared__ float cpart[16][2];
+  __shared__ float coef[16][2];
+  const uint32_t rank = slab_cluster_rank(), csize = slab_cluster_size();
+  const int cg16 = blockIdx.x / csize, n = blockIdx.y;
+  const int hw = p.h * p.w, c = p.c;
+  const int p0 = rank * p.per, p1 = min(hw, p0 + p.per);
+  const int half = threadIdx.x & 1, pr = threadIdx.x >> 1;
+  const int ch0 = cg16 * 16 + half * 8;
+  const bf16* ybase = p.y + (long long)n * hw * c + ch0;
+  const F8 sh = load8(ybase);  // shift = the sample's first pixel (same value in every CTA of the slab)
+  float s0[8], s1[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s0[e] = s1[e] = 0.f;
+#pragma unroll 4
+  for (int pix = p0 + pr; pix < p1; pix += 128) {
+    const uint4 u = *reinterpret_cast<const uint4*>(ybase + (long long)pix * c);
+    slab[(pix - p0) * 2 + half] = u;
+    const F8 x = unpack8(u);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float d = x.v[e] - sh.v[e];
+      s0[e] += d;
+      s1[e] = fmaf(d, d, s1[e]);
+    }
+  }
+  slab_block_reduce(s0, s1, wred, cpart);
+  slab_cluster_sync();  // every CTA's cpart is complete and visible cluster-wide
+  if (threadIdx.x < 16) {
+    const int ch = cg16 * 16 + threadIdx.x;
+    double a1 = 0.0, a2 = 0.0;
+    for (uint32_t r = 0; r < csize; ++r) {
+      a1 += (double)ld_dsmem_f32(&cpart[threadIdx.x][0], r);
+      a2 += (double)ld_dsmem_f32(&cpart[threadIdx.x][1], r);
+    }
+    const double cnt = (double)hw;
+    const double m1 = a1 / cnt;
+    double var = a2 / cnt - m1 * m1;  // biased (F.batch_norm / InstanceNorm2d)
+    if (var < 0.0) var = 0.0;
+    const float shv = __bfloat162float(p.y[(long long)n * hw * c + ch]);
+    const float mu = (float)((double)shv + m1);
+    const float ri = (float)(1.0 / sqrt(var + (double)p.eps));
+    float wv = 1.f, bv = 0.f;
+    if (p.mode == MUNIT_NORM_ADAIN) {
+      wv = p.p_w[(long long)n * p.ldw + ch];
+      bv = p.p_b[(long long)n * p.ldw + ch];
+    }
+    const float aa = ri * wv, bb = bv - mu * aa;
+    coef[threadIdx.x][0] = aa;
+    coef[threadIdx.x][1] = bb;
+    if (rank == 0) {
+      const long long i = (long long)n * c + ch;
+      p.mean[i] = mu;
+      p.rinv[i] = ri;
+      p.a[i] = aa;
+      p.b[i] = bb;
+    }
+  }
+  __syncthreads();
+  float fa[8], fb[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    fa[e] = coef[half * 8 + e][0];
+    fb[e] = coef[half * 8 + e][1];
+  }
+  const int h = p.h, w = p.w, out_pad = p.out_pad, res_pad = p.res_pad;
+  const int hop = h + 2 * out_pad, wop = w + 2 * out_pad;
+#pragma unroll 2
+  for (int pix = p0 + pr; pix < p1; pix += 128) {
+    const int yy = pix / w, x = pix - yy * w;
+    F8 v = unpack8(slab[(pix - p0) * 2 + half]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float o = fmaf(v.v[e], fa[e], fb[e]);
+      if (p.relu) o = fmaxf(o, 0.f);
+      v.v[e] = o;
+    }
+    if (p.res) {
+      const F8 rr = load8(p.res + (((long long)n * (h + 2 * res_pad) + yy + res_pad) * (w + 2 * res_pad) + x + res_pad) * c + ch0);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v.v[e] += rr.v[e];
+    }
+    const uint4 packed = pack8(v);
+    int prow[3], pcol[3];
+    const int nr = pad_positions(yy, h, out_pad, prow);
+    const int nc = pad_positions(x, w, out_pad, pcol);
+    for (int i = 0; i < nr; ++i)
+      for (int q = 0; q < nc; ++q)
+        *reinterpret_cast<uint4*>(p.out + (((long long)n * hop + prow[i]) * wop + pcol[q]) * c + ch0) = packed;
+  }
+  slab_cluster_sync();  // no CTA exits while a peer may still read its cpart
+}
+
+__global__ void __launch_bounds__(256, 3) norm_bwd_slab_kernel(const NormSlabArgs p) {
+  extern __shared__ __align__(16) uint8_t slab_raw[];
+  uint4* slab = reinterpret_cast<uint4*>(slab_raw);  // [per][2][2]: y chunk, folded-gradient chunk
+  __shared__ float wred[8][2][8][2];
+  __shared__ float cpart[16][2];
+  __shared__ float coef[16][3];
+  const uint32_t rank = slab_cluster_rank(), csize = slab_cluster_size();
+  const int cg16 = blockIdx.x / csize, n = blockIdx.y;
+  const int h = p.h, w = p.w, hw = h * w, c = p.c;
+  const int p0 = rank * p.per, p1 = min(hw, p0 + p.per);
+  const int half = threadIdx.x & 1, pr = threadIdx.x >> 1;
+  const int ch0 = cg16 * 16 + half * 8;
+  const long long co = (long long)n * c + ch0;
+  const F8 fa = loadf8(p.a + co), fb = loadf8(p.b + co), fm = loadf8(p.mean + co);
+  const bf16* ybase = p.y + (long long)n * hw * c + ch0;
+  float s0[8], s1[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s0[e] = s1[e] = 0.f;
+#pragma unroll 2
+  for (int pix = p0 + pr; pix < p1; pix += 128) {
+    const int yy = pix / w, x = pix - yy * w;
+    const F8 g = fold_grad<1>(p.g_out, n, yy, x, ch0 >> 3, h, w, c, p.out_pad);
+    const uint4 u = *reinterpret_cast<const uint4*>(ybase + (long long)pix * c);
+    const uint4 gp = pack8(g);
+    slab[((pix - p0) * 2 + half) * 2] = u;
+    slab[((pix - p0) * 2 + half) * 2 + 1] = gp;
+    const F8 xv = unpack8(u);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float dz = g.v[e];  // sums from the unrounded fold; only the parked copy is bf16
+      if (p.relu && fmaf(xv.v[e], fa.v[e], fb.v[e]) <= 0.f) dz = 0.f;
+      s0[e] += dz;
+      s1[e] = fmaf(dz, xv.v[e] - fm.v[e], s1[e]);
+    }
+  }
+  slab_block_reduce(s0, s1, wred, cpart);
+  slab_cluster_sync();
+  if (threadIdx.x < 16) {
+    const int ch = cg16 * 16 + threadIdx.x;
+    const long long i = (long long)n * c + ch;
+    double a1 = 0.0, a2 = 0.0;
+    for (uint32_t r = 0; r < csize; ++r) {
+      a1 += (double)ld_dsmem_f32(&cpart[threadIdx.x][0], r);
+      a2 += (double)ld_dsmem_f32(&cpart[threadIdx.x][1], r);
+    }
+    const double cnt = (double)hw;
+    const float ri = p.rinv[i];
+    const float wv = p.mode == MUNIT_NORM_ADAIN ? p.p_w[(long long)n * p.ldw + ch] : 1.f;
+    const float A = ri * wv;
+    a2 *= (double)ri;  // sum dz*(x-mean) -> sum dz*xhat
+    const float cc = (float)(-(double)A * a1 / cnt);
+    const float cb = (float)(-(double)A * a2 / cnt);
+    const float k1 = cb * ri;
+    coef[threadIdx.x][0] = A;
+    coef[threadIdx.x][1] = k1;
+    coef[threadIdx.x][2] = cc - k1 * p.mean[i];
+    if (rank == 0 && p.mode == MUNIT_NORM_ADAIN) {
+      if (p.g_w) p.g_w[(long long)n * p.ldg + ch] = (float)a2;
+      if (p.g_b) p.g_b[(long long)n * p.ldg + ch] = (float)a1;
+    }
+  }
+  __syncthreads();
+  float fca[8], k1[8], k0[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    fca[e] = coef[half * 8 + e][0];
+    k1[e] = coef[half * 8 + e][1];
+    k0[e] = coef[half * 8 + e][2];
+  }
+  const int res_pad = p.res_pad;
+#pragma unroll 2
+  for (int pix = p0 + pr; pix < p1; pix += 128) {
+    const uint4 u = slab[((pix - p0) * 2 + half) * 2];
+    const uint4 gp = slab[((pix - p0) * 2 + half) * 2 + 1];
+    const F8 xv = unpack8(u), gq = unpack8(gp);
+    F8 d;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float dz = gq.v[e];
+      if (p.relu && fmaf(xv.v[e], fa.v[e], fb.v[e]) <= 0.f) dz = 0.f;
+      d.v[e] = fmaf(fca[e], dz, fmaf(k1[e], xv.v[e], k0[e]));
+    }
+    *reinterpret_cast<uint4*>(p.dy + ((long long)n * hw + pix) * c + ch0) = pack8(d);
+    if (p.g_res) {
+      const int yy = pix / w, x = pix - yy * w;
+      *reinterpret_cast<uint4*>(p.g_res + (((long long)n * (h + 2 * res_pad) + yy + res_pad) * (w + 2 * res_pad) + x + res_pad) * c + ch0) = gp;
+    }
+  }
+  slab_cluster_sync();
+}
+
 inline int grid_for(long long work, int threads = 256, int max_blocks = 148 * 16) {
   long long b = (work + threads - 1) / threads;
   if (b > max_blocks) b = max_blocks;
@@ -1185,6 +1650,83 @@ inline int apply_splits(int hw, int c, int n) {
   if (s < 1) s = 1;
   return s;
 }
+
+// Fused (cooperative) norm launches: every block of the grid must be resident at once.
+inline size_t fused_smem(int c) {
+  const int rows = 256 / (c / 8);
+  const size_t a = sizeof(float) * 2 * rows * c, b = sizeof(double) * 2 * c;
+  return a > b ? a : b;
+}
+inline int fused_capacity(int which) {  // 0: fwd<1>, 1: fwd<2>, 2: bwd<1>, 3: bwd<2>
+  static int cap[4] = {0, 0, 0, 0};
+  if (cap[which]) return cap[which];
+  int dev = 0, sms = 0, coop = 0, occ = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  if (!coop) return cap[which] = -1;
+  const size_t sm = 16384;
+  cudaError_t e;
+  switch (which) {
+    case 0: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, norm_fwd_fused_kernel<1>, 256, sm); break;
+    case 1: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, norm_fwd_fused_kernel<2>, 256, sm); break;
+    case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, norm_bwd_fused_kernel<1>, 256, sm); break;
+    default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, norm_bwd_fused_kernel<2>, 256, sm); break;
+  }
+  if (e != cudaSuccess || occ < 1) return cap[which] = -1;
+  return cap[which] = occ * sms;
+}
+// pixel splits of a fused launch over n samples, or 0 when the shape cannot run fused
+inline int fused_splits(int which, int n, int hw, int c, int mode) {
+  if (c % 8 || c / 8 > 256 || 256 % (c / 8) || n < 1) return 0;
+  const int cap = fused_capacity(which);
+  if (cap < n) return 0;
+  const int rows = 256 / (c / 8);
+  int s = cap / n;
+  const int smax = (hw + rows - 1) / rows;  // at least one pixel per thread row
+  if (s > smax) s = smax;
+  if (s > 512) s = 512;
+  if (mode != MUNIT_NORM_LN && s < (c + 31) / 32) return 0;  // the channel-parallel finalize needs C/32 blocks per sample
+  return s < 1 ? 0 : s;
+}
+
+
+// Cluster size / pixels per CTA of a slab launch: smallest power-of-two cluster that keeps a CTA's pixel range
+// within `per_max`; 0 when the shape needs more than 16 CTAs per slab (caller uses the three-kernel path).
+inline int slab_cluster(int hw, int per_max, int* per) {
+  int cl = 1;
+  while (cl <= 16 && (hw + cl - 1) / cl > per_max) cl <<= 1;
+  if (cl > 16) return 0;
+  *per = (hw + cl - 1) / cl;
+  return cl;
+}
+inline int slab_launch(const void* fn, const NormSlabArgs& p, int cl, size_t smem, cudaStream_t st, const char* what) {
+  static bool attr_done[2] = {false, false};
+  const int which = fn == (const void*)norm_fwd_slab_kernel ? 0 : 1;
+  if (!attr_done[which]) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "%s: attributes: %s", what, cudaGetErrorString(e));
+    attr_done[which] = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cl * (p.c / 16), p.n);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = which == 0 ? cudaLaunchKernelEx(&cfg, norm_fwd_slab_kernel, p) : cudaLaunchKernelEx(&cfg, norm_bwd_slab_kernel, p);
+  if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return MUNIT_OK;
+}
+constexpr int kSlabFwdPer = 1024;  // pixels per CTA: 32 B/px forward (32 KB), 64 B/px backward (64 KB at most)
+constexpr int kSlabBwdPer = 512;
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 #define BF(p) reinterpret_cast<bf16*>(p)
@@ -1276,6 +1818,27 @@ int munit_norm_finalize(const float* stats, const float* shift, int mode, const 
   return MUNIT_OK;
 }
 
+int munit_norm_finalize_parts(const float* stats, int splits, int kind, int mode, const float* p_w, const float* p_b,
+                              int64_t ldw, float eps, float* mean, float* rinv, float* a, float* b, int n, int hw,
+                              int c, void* stream) {
+  if (splits < 1) return mb_fail(MUNIT_ERR_ARG, "norm_finalize_parts: splits");
+  if (kind == 1 && mode != MUNIT_NORM_LN) {
+    if (mode == MUNIT_NORM_ADAIN && (!p_w || !p_b)) return mb_fail(MUNIT_ERR_ARG, "norm_finalize_parts: missing affine params");
+    dim3 grid((c + 31) / 32, n);
+    norm_finalize_nc_kernel<<<grid, 256, 0, ST(stream)>>>(stats, splits, nullptr, mode == MUNIT_NORM_ADAIN, p_w, p_b, ldw,
+                                                          eps, mean, rinv, a, b, hw, c);
+    MB_CHECK_LAUNCH("norm_finalize_parts(nc)");
+    return MUNIT_OK;
+  }
+  if (kind == 2 && mode == MUNIT_NORM_LN) {
+    if (!p_w || !p_b) return mb_fail(MUNIT_ERR_ARG, "norm_finalize_parts: missing affine params");
+    norm_finalize_ln_total_kernel<<<n, 256, 0, ST(stream)>>>(stats, splits, p_w, p_b, eps, mean, rinv, a, b, hw, c);
+    MB_CHECK_LAUNCH("norm_finalize_parts(ln)");
+    return MUNIT_OK;
+  }
+  return mb_fail(MUNIT_ERR_ARG, "norm_finalize_parts: kind %d does not match mode %d", kind, mode);
+}
+
 int munit_norm_apply(const void* y, const float* a, const float* b, int relu, const void* residual, int res_pad,
                      void* out_act, int out_pad, int upsample, int n, int h, int w, int c, void* stream) {
   if (c % 8 || c / 8 > 256 || 256 % (c / 8)) return mb_fail(MUNIT_ERR_ARG, "norm_apply: channels %d", c);
@@ -1339,6 +1902,95 @@ int munit_norm_bwd_apply(const void* g_out, int out_pad, int upsample, const voi
                                                             cc, BF(dy), BF(g_res), res_pad, n, h, w, c);
   MB_CHECK_LAUNCH("norm_bwd_apply");
   return MUNIT_OK;
+}
+
+int munit_norm_fused_splits(int n, int hw, int c, int mode, int backward, int upsample) {
+  if (upsample != 1 && upsample != 2) return 0;
+  return fused_splits((backward ? 2 : 0) + (upsample == 2 ? 1 : 0), n, hw, c, mode);
+}
+
+int munit_norm_fwd_fused(const void* y, float* part, float* shift, int mode, const float* p_w, const float* p_b,
+                         int64_t ldw, float eps, float* mean, float* rinv, float* a, float* b, int relu,
+                         const void* residual, int res_pad, void* out_act, int out_pad, int upsample, int n, int h, int w,
+                         int c, void* stream) {
+  if (upsample != 1 && upsample != 2) return mb_fail(MUNIT_ERR_ARG, "norm_fwd_fused: upsample must be 1 or 2");
+  if (mode != MUNIT_NORM_IN && (!p_w || !p_b)) return mb_fail(MUNIT_ERR_ARG, "norm_fwd_fused: missing affine params");
+  const int which = upsample == 2 ? 1 : 0;
+  const int splits = fused_splits(which, n, h * w, c, mode);
+  if (splits < 1) return mb_fail(MUNIT_ERR_ARG, "norm_fwd_fused: shape n=%d hw=%d c=%d cannot run as one cooperative launch", n, h * w, c);
+  NormFusedArgs p{};
+  p.y = CBF(y); p.part = part; p.shift = shift; p.mode = mode; p.p_w = p_w; p.p_b = p_b; p.ldw = ldw; p.eps = eps;
+  p.mean = mean; p.rinv = rinv; p.a = a; p.b = b; p.relu = relu; p.res = CBF(residual); p.res_pad = res_pad;
+  p.out = BF(out_act); p.out_pad = out_pad; p.n = n; p.h = h; p.w = w; p.c = c;
+  void* args[] = {&p};
+  const void* fn = which ? (const void*)norm_fwd_fused_kernel<2> : (const void*)norm_fwd_fused_kernel<1>;
+  const cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(splits, n), dim3(256), args, fused_smem(c), ST(stream));
+  if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "norm_fwd_fused: %s", cudaGetErrorString(e));
+  MB_CHECK_LAUNCH("norm_fwd_fused");
+  return MUNIT_OK;
+}
+
+int munit_norm_bwd_fused(const void* g_out, int out_pad, int upsample, const void* y, const float* a, const float* b,
+                         int relu, const float* mean, const float* rinv, float* part, int mode, const float* p_w,
+                         int64_t ldw, float eps, float* ca, float* cb, float* cc, float* g_w, float* g_b, int64_t ldg,
+                         void* dy, void* g_res, int res_pad, int n, int h, int w, int c, void* stream) {
+  if (upsample != 1 && upsample != 2) return mb_fail(MUNIT_ERR_ARG, "norm_bwd_fused: upsample must be 1 or 2");
+  const int which = 2 + (upsample == 2 ? 1 : 0);
+  const int splits = fused_splits(which, n, h * w, c, mode);
+  if (splits < 1) return mb_fail(MUNIT_ERR_ARG, "norm_bwd_fused: shape n=%d hw=%d c=%d cannot run as one cooperative launch", n, h * w, c);
+  NormFusedArgs p{};
+  p.y = CBF(y); p.part = part; p.mode = mode; p.p_w = p_w; p.ldw = ldw; p.eps = eps;
+  p.mean = const_cast<float*>(mean); p.rinv = const_cast<float*>(rinv); p.a = const_cast<float*>(a);
+  p.b = const_cast<float*>(b); p.relu = relu; p.res_pad = res_pad; p.out_pad = out_pad; p.g_out = CBF(g_out);
+  p.ca = ca; p.cb = cb; p.cc = cc; p.g_w = g_w; p.g_b = g_b; p.ldg = ldg; p.dy = BF(dy); p.g_res = BF(g_res);
+  p.n = n; p.h = h; p.w = w; p.c = c;
+  void* args[] = {&p};
+  const void* fn = upsample == 2 ? (const void*)norm_bwd_fused_kernel<2> : (const void*)norm_bwd_fused_kernel<1>;
+  const cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(splits, n), dim3(256), args, fused_smem(c), ST(stream));
+  if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "norm_bwd_fused: %s", cudaGetErrorString(e));
+  MB_CHECK_LAUNCH("norm_bwd_fused");
+  return MUNIT_OK;
+}
+
+
+int munit_norm_slab_ok(int mode, int upsample, int hw, int c, int backward) {
+  if (mode == MUNIT_NORM_LN || upsample != 1 || c % 16 || hw < 1) return 0;
+  int per = 0;
+  int cl = slab_cluster(hw, backward ? kSlabBwdPer : kSlabFwdPer, &per);
+  if (!cl && backward) cl = slab_cluster(hw, 2 * kSlabBwdPer, &per);  // 64 KB slabs
+  return cl;
+}
+
+int munit_norm_fwd_slab(const void* y, int mode, const float* p_w, const float* p_b, int64_t ldw, float eps,
+                        float* mean, float* rinv, float* a, float* b, int relu, const void* residual, int res_pad,
+                        void* out_act, int out_pad, int n, int h, int w, int c, void* stream) {
+  if (mode == MUNIT_NORM_ADAIN && (!p_w || !p_b)) return mb_fail(MUNIT_ERR_ARG, "norm_fwd_slab: missing affine params");
+  int per = 0;
+  const int cl = (mode == MUNIT_NORM_LN || c % 16) ? 0 : slab_cluster(h * w, kSlabFwdPer, &per);
+  if (!cl) return mb_fail(MUNIT_ERR_ARG, "norm_fwd_slab: unsupported shape hw=%d c=%d mode=%d", h * w, c, mode);
+  if (out_pad >= h || out_pad >= w) return mb_fail(MUNIT_ERR_ARG, "norm_fwd_slab: reflect pad >= size");
+  NormSlabArgs p{};
+  p.y = CBF(y); p.mode = mode; p.p_w = p_w; p.p_b = p_b; p.ldw = ldw; p.eps = eps;
+  p.mean = mean; p.rinv = rinv; p.a = a; p.b = b; p.relu = relu; p.res = CBF(residual); p.res_pad = res_pad;
+  p.out = BF(out_act); p.out_pad = out_pad; p.n = n; p.h = h; p.w = w; p.c = c; p.per = per;
+  return slab_launch((const void*)norm_fwd_slab_kernel, p, cl, (size_t)per * 32, ST(stream), "norm_fwd_slab");
+}
+
+int munit_norm_bwd_slab(const void* g_out, int out_pad, const void* y, const float* a, const float* b, int relu,
+                        const float* mean, const float* rinv, int mode, const float* p_w, int64_t ldw, float* g_w,
+                        float* g_b, int64_t ldg, void* dy, void* g_res, int res_pad, int n, int h, int w, int c,
+                        void* stream) {
+  int per = 0;
+  int cl = (mode == MUNIT_NORM_LN || c % 16) ? 0 : slab_cluster(h * w, kSlabBwdPer, &per);
+  if (!cl && mode != MUNIT_NORM_LN && c % 16 == 0) cl = slab_cluster(h * w, 2 * kSlabBwdPer, &per);
+  if (!cl) return mb_fail(MUNIT_ERR_ARG, "norm_bwd_slab: unsupported shape hw=%d c=%d mode=%d", h * w, c, mode);
+  NormSlabArgs p{};
+  p.y = CBF(y); p.mode = mode; p.p_w = p_w; p.ldw = ldw;
+  p.mean = const_cast<float*>(mean); p.rinv = const_cast<float*>(rinv); p.a = const_cast<float*>(a);
+  p.b = const_cast<float*>(b); p.relu = relu; p.res_pad = res_pad; p.out_pad = out_pad; p.g_out = CBF(g_out);
+  p.g_w = g_w; p.g_b = g_b; p.ldg = ldg; p.dy = BF(dy); p.g_res = BF(g_res);
+  p.n = n; p.h = h; p.w = w; p.c = c; p.per = per;
+  return slab_launch((const void*)norm_bwd_slab_kernel, p, cl, (size_t)per * 64, ST(stream), "norm_bwd_slab");
 }
 
 int munit_act_bwd(const void* g_out, const void* out_act, int pad, int act, void* dy, int n, int h, int w, int c,

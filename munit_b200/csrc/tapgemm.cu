@@ -39,6 +39,9 @@ struct FwdParams {
   int dbg;  // profiling knobs (env MUNIT_DBG): 1 skip A loads, 2 skip B loads, 4 skip MMA, 8 skip stores
   // halo-resident variant: window origin (tap offset minimum), box width / rows, descriptor base-offset mode
   int halo_ox, halo_oy, halo_wb, halo_rb, halo_mode;
+  // normalisation statistics of the stored tile, written by the epilogue (munit_tapgemm_desc.stats)
+  float* stats;
+  int stats_kind, stats_c;
   int* err;
   int tap_off[MUNIT_MAX_TAPS][5];
 };
@@ -58,6 +61,44 @@ __device__ __forceinline__ float tanh_approx(float v) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
   return r;
 }
+// Column sums of one staged [128 px][64 ch] SWIZZLE_128B group over this warp's 32 rows (q = row quarter): lane l
+// owns the channel pair (2l, 2l+1), one conflict-free LDS.32 per row.  Sums are of the bf16 values that go to
+// memory, i.e. exactly what the apply pass will read back.
+//   kind 1 (IN / AdaIN): stats[((n*S + s)*C + c)*2 + {0,1}] = {sum x, sum x^2}, s = tile*4 + q, S = 4*tiles/image
+//   kind 2 (LayerNorm):  stats[(n*S + s)*2 + {0,1}] channel-reduced, s = (tile*4 + q)*(C/64) + c/64, S = 4*tiles*C/64
+__device__ __forceinline__ void staged_stats(uint32_t buf, int q, int lane, float* __restrict__ stats, int kind,
+                                             int c_total, int n, int tile, int tiles, int col0) {
+  float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
+#pragma unroll 8
+  for (int r = 0; r < 32; ++r) {
+    const int row = q * 32 + r;
+    const uint32_t addr = buf + row * 128 + (((lane >> 2) ^ (row & 7)) << 4) + ((lane & 3) << 2);
+    uint32_t w;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(addr));
+    const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
+    s1a += lo;
+    s2a = fmaf(lo, lo, s2a);
+    s1b += hi;
+    s2b = fmaf(hi, hi, s2b);
+  }
+  if (kind == 1) {
+    const long long s_idx = (long long)n * (4 * tiles) + tile * 4 + q;
+    *reinterpret_cast<float4*>(stats + (s_idx * c_total + col0 + 2 * lane) * 2) = make_float4(s1a, s2a, s1b, s2b);
+  } else {
+    float s1 = s1a + s1b, s2 = s2a + s2b;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const int groups = c_total / 64;
+    if (lane == 0) {
+      const long long s_idx = ((long long)n * (4 * tiles) + tile * 4 + q) * groups + col0 / 64;
+      *reinterpret_cast<float2*>(stats + s_idx * 2) = make_float2(s1, s2);
+    }
+  }
+}
+
 // 8 accumulators -> (+bias) -> activation -> 4 packed bf16x2 words
 __device__ __forceinline__ void epi8(const uint32_t* v, const float* __restrict__ bias, float slope, bool is_tanh,
                                      uint32_t* out) {
@@ -243,6 +284,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           tma_store_4d(&tmap_out.m[phase_id], buf, col0, x0, y0, n0);
           tma_store_commit();
         }
+        if (p.stats && store_group && !dead)
+          staged_stats(buf, q, lane, p.stats, p.stats_kind, p.stats_c, n0, ty * p.tiles_x + tx,
+                       p.tiles_x * p.tiles_y, col0);
       }
       if (issuer) tma_store_wait_read0();
     } else {
@@ -434,6 +478,9 @@ tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tma_store_4d(&tmap_out.m[0], buf, col0, x0, y0, n0);
         tma_store_commit();
       }
+      if (p.stats && store_group && !dead)
+        staged_stats(buf, q, lane, p.stats, p.stats_kind, p.stats_c, n0, ty * p.tiles_x + tx, p.tiles_x * p.tiles_y,
+                     col0);
     }
     if (issuer) tma_store_wait_read0();
   }
@@ -969,6 +1016,15 @@ extern "C" int munit_tapgemm(const munit_tapgemm_desc* d, void* stream) {
   p.o_sn = d->o_sn; p.o_sy = d->o_sy; p.o_sx = d->o_sx; p.o_ymul = d->o_ymul; p.o_xmul = d->o_xmul;
   p.n_store = d->n_store; p.bias = d->bias; p.act = d->act; p.stages = d->stages;
   p.err = mb_error_flag();
+  p.stats = d->stats; p.stats_kind = d->stats_kind; p.stats_c = d->b_rows;
+  if (d->stats) {
+    // every tile must be a full tile of ONE image and every channel must be stored, so that 4 row quarters x
+    // tiles partition each image's pixels
+    if (d->stats_kind != 1 && d->stats_kind != 2) return mb_fail(MUNIT_ERR_ARG, "tapgemm: stats_kind must be 1 or 2");
+    if (d->bn < 64 || d->phases != 1 || d->tn != 1 || d->out_w % d->tw || d->out_h % d->th || d->n_store < d->b_rows ||
+        d->b_rows % 64)
+      return mb_fail(MUNIT_ERR_ARG, "tapgemm: epilogue statistics need bn >= 64, one phase, tn == 1, full tiles and all channels stored");
+  }
   {
     static int dbg = -1;
     if (dbg < 0) {

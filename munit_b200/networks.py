@@ -178,7 +178,7 @@ class Conv2dBlock(nn.Module):
             return Act(out, out_pad)
         # a per-channel bias is cancelled exactly by the mean subtraction of IN / AdaIN: skip it
         bias = b if self.norm_type == "ln" else None
-        y = ops.ConvFn.apply(xin, w, bias, layer, "none", 0, self.padding)
+        y, part = ops.ConvFn.apply(xin, w, bias, layer, "none", 0, self.padding, 2 if self.norm_type == "ln" else 1)
         n = y.shape[0]
         if self.norm_type == "in":
             p_w = p_b = None
@@ -189,7 +189,7 @@ class Conv2dBlock(nn.Module):
         res_t = residual.t if residual is not None else None
         res_pad = residual.pad if residual is not None else 0
         out = ops.NormFn.apply(y, p_w, p_b, res_t, self.norm_type, self.act_type == "relu", res_pad, out_pad,
-                               upsample, self.norm.eps if self.norm_type != "in" else 1e-5)
+                               upsample, self.norm.eps if self.norm_type != "in" else 1e-5, part)
         return Act(out, out_pad)
 
     # -- public path (tensor in, tensor out) ----------------------------------------------

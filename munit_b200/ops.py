@@ -15,8 +15,14 @@ from typing import Optional
 
 import torch
 
+import os
+
 from . import geometry as G
 from . import kernels as K
+
+# Normalisation statistics in the conv epilogue (no separate pass over the conv output); MUNIT_EPI_STATS=0 restores
+# the stand-alone statistics kernel.
+EPI_STATS = os.environ.get("MUNIT_EPI_STATS", "0") != "0"
 
 
 @dataclass
@@ -178,7 +184,9 @@ class ConvFn(torch.autograd.Function):
     produce the raw conv output that feeds a norm."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, layer: ConvLayer, act: str, out_pad: int, image_pad: int):
+    def forward(ctx, x, weight, bias, layer: ConvLayer, act: str, out_pad: int, image_pad: int, stats_kind: int = 0):
+        """stats_kind 1 (IN / AdaIN) or 2 (LayerNorm): also return the normalisation partials the epilogue
+        computed from the stored tile (an empty tensor when this plan cannot produce them)."""
         layer.refresh(weight, bias)
         if layer.first:  # x is an NCHW fp32 image
             n, c, h, w = x.shape
@@ -189,16 +197,25 @@ class ConvFn(torch.autograd.Function):
         n, hp, wp, _ = gemm_in.shape
         fwd, _, _, ho, wo = layer.plans(n, hp, wp, out_pad)
         out = torch.empty(n, ho + 2 * out_pad, wo + 2 * out_pad, layer.co_rows, dtype=torch.bfloat16, device=x.device)
-        K.tapgemm(fwd, gemm_in, layer.w_fwd, out, layer.bias_p if bias is not None else None, act)
+        part = None
+        if stats_kind:
+            splits = K.stats_splits(fwd, stats_kind) if (EPI_STATS and out_pad == 0 and act == "none") else 0
+            part = torch.empty(n * splits * (layer.co_rows if stats_kind == 1 else 1) * 2, dtype=torch.float32,
+                               device=x.device)
+        K.tapgemm(fwd, gemm_in, layer.w_fwd, out, layer.bias_p if bias is not None else None, act,
+                  stats=part if (part is not None and part.numel()) else None, stats_kind=stats_kind)
         K.halo_fill(out, out_pad)
         ctx.layer, ctx.act, ctx.out_pad, ctx.image_pad = layer, act, out_pad, image_pad
         ctx.has_bias = bias is not None
         ctx.wbuf, ctx.bbuf = _param_grad_buf(weight), _param_grad_buf(bias)
         ctx.save_for_backward(gemm_in, out, weight)
+        if stats_kind:
+            ctx.mark_non_differentiable(part)
+            return out, part
         return out
 
     @staticmethod
-    def backward(ctx, g_out):
+    def backward(ctx, g_out, g_part=None):
         layer: ConvLayer = ctx.layer
         gemm_in, out, weight = ctx.saved_tensors
         n, hp, wp, _ = gemm_in.shape
@@ -235,7 +252,7 @@ class ConvFn(torch.autograd.Function):
                 tgt = buf if buf is not None else _grad_like_cl(weight)
                 K.wgrad(wg, dy, gemm_in, _cl_weight(tgt))
             gw = None if buf is not None else tgt
-        return gx, gw, gb, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None
 
 
 class ConvOutFn(torch.autograd.Function):
@@ -288,16 +305,14 @@ class NormFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, y, p_w, p_b, residual, mode: str, relu: bool, res_pad: int, out_pad: int, upsample: int,
-                eps: float):
+                eps: float, part=None):
         n, h, w, c = y.shape
         y = y.contiguous()
-        stats, shift = K.norm_stats(y)
         ldw = 0
         if mode == "adain":
             assert p_w.stride(1) == 1 and p_b.stride(1) == 1 and p_w.stride(0) == p_b.stride(0)
             ldw = p_w.stride(0)
-        coef = K.norm_finalize(stats, shift, mode, p_w, p_b, ldw, h * w, eps)
-        out = K.norm_apply(y, coef[2], coef[3], relu, residual, res_pad, out_pad, upsample)
+        out, coef = K.norm_fwd(y, mode, p_w, p_b, ldw, eps, relu, residual, res_pad, out_pad, upsample, part)
         ctx.cfg = (mode, relu, res_pad, out_pad, upsample, eps, ldw, residual is not None)
         ctx.wbuf, ctx.bbuf = _param_grad_buf(p_w), _param_grad_buf(p_b)
         ctx.save_for_backward(y, coef, p_w)
@@ -322,7 +337,7 @@ class NormFn(torch.autograd.Function):
             ret_b = None if ctx.bbuf is not None else g_b
         dy, g_res = K.norm_bwd(g_out.contiguous(), out_pad, upsample, y, coef, relu, mode, p_w, ldw, g_w, g_b, ldg,
                                has_res and ctx.needs_input_grad[3], res_pad, eps)
-        return dy, ret_w, ret_b, g_res, None, None, None, None, None, None
+        return dy, ret_w, ret_b, g_res, None, None, None, None, None, None, None
 
 
 class ToActFn(torch.autograd.Function):

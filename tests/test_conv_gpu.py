@@ -180,3 +180,50 @@ def test_wgrad_row_sharing_variant(n, h, w, cin, cout, k, s, pad):
     assert error_flag() == 0
     err = rel_l2(dw, wt.grad.permute(0, 2, 3, 1))
     assert err < TOL, err
+
+
+STATS_CASES = [
+    # n, h, w, cin, cout, k, s, pad, halo
+    (2, 64, 64, 256, 256, 3, 1, 1, 0),   # residual-block conv: tile (64, 2, 1)
+    (3, 32, 32, 64, 128, 4, 2, 1, 0),    # stride-2 down-sampling conv
+    (2, 32, 64, 128, 64, 5, 1, 2, 1),    # halo-resident 5x5 (8 x 16 tiles), BN = 64
+    (2, 16, 32, 256, 128, 5, 1, 2, 1),   # halo-resident, BN = 128
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,k,s,pad,halo", STATS_CASES)
+@pytest.mark.parametrize("mode", ["in", "adain", "ln"])
+def test_epilogue_statistics(n, h, w, cin, cout, k, s, pad, halo, mode):
+    """Normalisation partials written by the conv epilogue -> munit_norm_finalize_parts must equal the
+    statistics of the stored bf16 output (what the stand-alone statistics pass would have computed)."""
+    from munit_b200 import geometry as G, kernels as K
+
+    xp, wt, bias = _setup(n, h, w, cin, cout, k, s, pad, 11)
+    bias = bias * 3 + 2  # a mean well away from zero: the unshifted sums must still give the variance
+    hp, wp = xp.shape[2:]
+    ho, wo = (hp - k) // s + 1, (wp - k) // s + 1
+    plan = G.plan_fwd(n, hp, wp, cin, k, k, s, s, cout, (ho * wo * cout, wo * cout, cout, 0, 0), halo=halo)
+    assert plan.halo == halo
+    kind = 2 if mode == "ln" else 1
+    splits = K.stats_splits(plan, kind)
+    assert splits > 0
+    a = nhwc(xp).to(torch.bfloat16)
+    b = wt.permute(0, 2, 3, 1).reshape(cout, -1).contiguous().to(torch.bfloat16)
+    out = torch.zeros(n, ho, wo, cout, dtype=torch.bfloat16, device="cuda")
+    part = torch.full((n * splits * (cout if kind == 1 else 1) * 2,), float("nan"), device="cuda")
+    K.tapgemm(plan, a, b, out, bias, "none", stats=part, stats_kind=kind)
+    torch.cuda.synchronize()
+    assert error_flag() == 0
+    assert rel_l2(out, nhwc(F.conv2d(xp, wt, bias, stride=s))) < TOL
+    g = torch.Generator(device="cuda").manual_seed(3)
+    p_w = p_b = None
+    ldw = 0
+    if mode == "adain":
+        p_w, p_b, ldw = torch.randn(n, cout, device="cuda", generator=g), torch.randn(n, cout, device="cuda", generator=g), cout
+    elif mode == "ln":
+        p_w, p_b = torch.rand(cout, device="cuda", generator=g), torch.randn(cout, device="cuda", generator=g)
+    coef = K.norm_finalize_parts(part, kind, mode, p_w, p_b, ldw, n, ho * wo, cout)
+    stats, shift = K.norm_stats(out)
+    ref = K.norm_finalize(stats, shift, mode, p_w, p_b, ldw, ho * wo)
+    for i, name in enumerate(("mean", "rinv", "a", "b")):
+        assert rel_l2(coef[i], ref[i]) < 2e-5, (name, rel_l2(coef[i], ref[i]))
