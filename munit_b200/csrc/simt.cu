@@ -32,6 +32,24 @@ __device__ __forceinline__ F8 load8(const bf16* p) {
   }
   return r;
 }
+__device__ __forceinline__ F8 unpack8(const uint4& u) {
+  F8 r;
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    r.v[2 * i] = f.x;
+    r.v[2 * i + 1] = f.y;
+  }
+  return r;
+}
+__device__ __forceinline__ uint4 pack8(const F8& r) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(r.v[2 * i], r.v[2 * i + 1]);
+  return u;
+}
 __device__ __forceinline__ void store8(bf16* p, const F8& r) {
   uint4 u;
   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
@@ -68,6 +86,8 @@ inline int nblocks(long long n, int threads) { return (int)((n + threads - 1) / 
 // ------------------------------------------------------------------ layout
 __global__ void image_to_act_kernel(const float* __restrict__ x, bf16* __restrict__ act, int n, int c, int h, int w,
                                     int pad, int cp) {
+  pdl_wait();
+  pdl_trigger();
   const int hp = h + 2 * pad, wp = w + 2 * pad;
   const long long total = (long long)n * hp * wp;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -90,6 +110,8 @@ __global__ void image_to_act_kernel(const float* __restrict__ x, bf16* __restric
 
 __global__ void image_to_kwexp_kernel(const float* __restrict__ x, bf16* __restrict__ e, int n, int c, int h, int w,
                                       int pad, int kw, int sx, int wo, int kwp, int cp) {
+  pdl_wait();
+  pdl_trigger();
   const int hp = h + 2 * pad;
   const int vec_per_tap = cp / 8;
   const long long total = (long long)n * hp * wo * kwp * vec_per_tap;
@@ -114,6 +136,8 @@ __global__ void image_to_kwexp_kernel(const float* __restrict__ x, bf16* __restr
 
 __global__ void kwexp_to_image_grad_kernel(const bf16* __restrict__ de, float* __restrict__ dx, int n, int c, int h,
                                            int w, int pad, int kw, int sx, int wo, int kwp, int cp) {
+  pdl_wait();
+  pdl_trigger();
   const int hp = h + 2 * pad;
   const long long total = (long long)n * h * w;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -143,6 +167,8 @@ __global__ void kwexp_to_image_grad_kernel(const bf16* __restrict__ de, float* _
 // act interior [N][H+2P][W+2P][CP] (channels < C) -> NCHW fp32, 32x32 (x, c) smem transpose tiles
 __global__ void act_to_nchw_kernel(const bf16* __restrict__ act, float* __restrict__ out, int n, int c, int h, int w,
                                    int pad, int cp) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float tile[32][33];
   const int x0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int y = blockIdx.z % h, b = blockIdx.z / h;
@@ -163,6 +189,8 @@ __global__ void act_to_nchw_kernel(const bf16* __restrict__ act, float* __restri
 // NCHW fp32 -> act interior (channels < C; C..CP zero-filled when the block covers them)
 __global__ void nchw_to_act_kernel(const float* __restrict__ in, bf16* __restrict__ act, int n, int c, int h, int w,
                                    int pad, int cp) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float tile[32][33];
   const int x0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int y = blockIdx.z % h, b = blockIdx.z / h;
@@ -179,6 +207,8 @@ __global__ void nchw_to_act_kernel(const float* __restrict__ in, bf16* __restric
 }
 
 __global__ void halo_fill_kernel(bf16* __restrict__ act, int n, int h, int w, int c, int pad) {
+  pdl_wait();
+  pdl_trigger();
   const int hp = h + 2 * pad, wp = w + 2 * pad, cg = c / 8;
   const long long total = (long long)n * hp * wp * cg;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -207,6 +237,33 @@ struct Blk {
 };
 __device__ __forceinline__ Blk launch_blk() { return Blk{(int)blockIdx.x, (int)gridDim.x, (int)blockIdx.y}; }
 
+// Block-level tail of the per-(n,c) reductions: the R row-threads of each channel are added in row order.
+__device__ __forceinline__ void reduce_nc_tail(Blk blk, const float* s0, const float* s1, float* __restrict__ out2,
+                                               int c) {
+  extern __shared__ float red[];  // [R][C][2]
+  const int cgs = c / 8;
+  const int rows = blockDim.x / cgs;
+  const int cg = threadIdx.x % cgs, r = threadIdx.x / cgs;
+  if (r < rows) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      red[((r * c) + cg * 8 + e) * 2 + 0] = s0[e];
+      red[((r * c) + cg * 8 + e) * 2 + 1] = s1[e];
+    }
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int rr = 0; rr < rows; ++rr) {
+      a += red[((rr * c) + ch) * 2 + 0];
+      b += red[((rr * c) + ch) * 2 + 1];
+    }
+    float* dst = out2 + (((long long)blk.by * blk.nbx + blk.bx) * c + ch) * 2;
+    dst[0] = a;
+    dst[1] = b;
+  }
+}
+
 template <typename Fn>
 __device__ __forceinline__ void reduce_nc(Blk blk, Fn fn, float* __restrict__ out2, int hw, int c) {
   extern __shared__ float red[];  // [R][C][2]
@@ -231,24 +288,7 @@ __device__ __forceinline__ void reduce_nc(Blk blk, Fn fn, float* __restrict__ ou
         s1[e] += v.v[e];
       }
     }
-  if (r < rows) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      red[((r * c) + cg * 8 + e) * 2 + 0] = s0[e];
-      red[((r * c) + cg * 8 + e) * 2 + 1] = s1[e];
-    }
-  }
-  __syncthreads();
-  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-    float a = 0.f, b = 0.f;
-    for (int rr = 0; rr < rows; ++rr) {
-      a += red[((rr * c) + ch) * 2 + 0];
-      b += red[((rr * c) + ch) * 2 + 1];
-    }
-    float* dst = out2 + (((long long)n * blk.nbx + blk.bx) * c + ch) * 2;
-    dst[0] = a;
-    dst[1] = b;
-  }
+  reduce_nc_tail(blk, s0, s1, out2, c);
 }
 // Sum the split partials of sample n for every channel into shared memory (sm[ch*2+{0,1}]): one thread per
 // channel (coalesced float2 reads), splits added in index order -> deterministic.  Ends with __syncthreads().
@@ -296,10 +336,14 @@ __device__ __forceinline__ void norm_stats_body(Blk blk, const bf16* __restrict_
 }
 __global__ void norm_stats_kernel(const bf16* __restrict__ y, float* __restrict__ stats, float* __restrict__ shift,
                                   int hw, int c) {
+  pdl_wait();
+  pdl_trigger();
   norm_stats_body(launch_blk(), y, stats, shift, hw, c);
 }
 
 __global__ void colsum_kernel(const bf16* __restrict__ dy, float* __restrict__ out, long long npix, int c, int c_out) {
+  pdl_wait();
+  pdl_trigger();
   // grid.x over pixel spans; reuse the (CG x R) mapping with a single "sample".
   extern __shared__ float red[];
   const int cgs = c / 8;
@@ -381,6 +425,8 @@ __global__ void norm_finalize_nc_kernel(const float* __restrict__ stats, int spl
                                         int adain, const float* __restrict__ p_w, const float* __restrict__ p_b,
                                         long long ldw, float eps, float* __restrict__ mean, float* __restrict__ rinv,
                                         float* __restrict__ a, float* __restrict__ b, int hw, int c) {
+  pdl_wait();
+  pdl_trigger();
   norm_finalize_nc_body(blockIdx.x, blockIdx.y, stats, splits, shift, adain, p_w, p_b, ldw, eps, mean, rinv, a, b, hw, c);
 }
 // IN / AdaIN backward finalize, same mapping.
@@ -430,6 +476,8 @@ __global__ void norm_bwd_finalize_nc_kernel(const float* __restrict__ sums, int 
                                             const float* __restrict__ rinv, float* __restrict__ ca,
                                             float* __restrict__ cb, float* __restrict__ cc, float* __restrict__ g_w,
                                             float* __restrict__ g_b, long long ldg, int hw, int c) {
+  pdl_wait();
+  pdl_trigger();
   norm_bwd_finalize_nc_body(blockIdx.x, blockIdx.y, sums, splits, adain, p_w, ldw, rinv, ca, cb, cc, g_w, g_b, ldg, hw, c);
 }
 
@@ -511,6 +559,8 @@ __global__ void norm_finalize_kernel(const float* __restrict__ stats, int splits
                                      const float* __restrict__ p_w, const float* __restrict__ p_b, long long ldw,
                                      float eps, float* __restrict__ mean, float* __restrict__ rinv,
                                      float* __restrict__ a, float* __restrict__ b, int hw, int c) {
+  pdl_wait();
+  pdl_trigger();
   norm_finalize_body(blockIdx.x, stats, splits, shift, mode, p_w, p_b, ldw, eps, mean, rinv, a, b, hw, c);
 }
 
@@ -520,6 +570,8 @@ __global__ void norm_finalize_ln_total_kernel(const float* __restrict__ part, in
                                               const float* __restrict__ p_b, float eps, float* __restrict__ mean,
                                               float* __restrict__ rinv, float* __restrict__ a, float* __restrict__ b,
                                               int hw, int c) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ double sh[2][256];
   const int n = blockIdx.x;
   const float2* p = reinterpret_cast<const float2*>(part) + (long long)n * splits;
@@ -610,6 +662,8 @@ template <int UP>
 __global__ void norm_apply_kernel(const bf16* __restrict__ y, const float* __restrict__ a, const float* __restrict__ b,
                                   int relu, const bf16* __restrict__ res, int res_pad, bf16* __restrict__ out,
                                   int out_pad, int n, int h, int w, int c) {
+  pdl_wait();
+  pdl_trigger();
   norm_apply_body<UP>(launch_blk(), y, a, b, relu, res, res_pad, out, out_pad, n, h, w, c);
 }
 
@@ -654,6 +708,63 @@ __device__ __forceinline__ F8 fold_grad(const bf16* __restrict__ g_out, int bb, 
   return acc;
 }
 
+// The same fold split in two so that a thread can issue the loads of several pixels back to back before it
+// consumes any of them (memory-level parallelism is what bounds these kernels): fold_load fetches the UP x UP
+// interior copies, fold_finish adds them up and, for border pixels only, gathers the mirrored halo copies.
+template <int UP>
+struct FoldRaw {
+  uint4 v[UP * UP];
+};
+template <int UP>
+__device__ __forceinline__ void fold_load(FoldRaw<UP>& o, const bf16* __restrict__ base, int yy, int x, int wop, int c,
+                                          int pad) {
+#pragma unroll
+  for (int uy = 0; uy < UP; ++uy)
+#pragma unroll
+    for (int ux = 0; ux < UP; ++ux)
+      o.v[uy * UP + ux] =
+          *reinterpret_cast<const uint4*>(base + ((long long)(yy * UP + uy + pad) * wop + x * UP + ux + pad) * c);
+}
+template <int UP>
+__device__ __forceinline__ F8 fold_finish(const FoldRaw<UP>& o, const bf16* __restrict__ base, int yy, int x, int h,
+                                          int w, int c, int pad) {
+  const int ho = h * UP, wo = w * UP, wop = wo + 2 * pad;
+  F8 acc = unpack8(o.v[0]);
+#pragma unroll
+  for (int i = 1; i < UP * UP; ++i) {
+    const F8 t = unpack8(o.v[i]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc.v[e] += t.v[e];
+  }
+  const int r0 = yy * UP, c0 = x * UP;
+  const bool border = pad > 0 && (r0 <= pad || c0 <= pad || r0 + UP - 1 >= ho - 1 - pad || c0 + UP - 1 >= wo - 1 - pad);
+  if (border) {
+#pragma unroll
+    for (int uy = 0; uy < UP; ++uy) {
+      int rows[3];
+      const int nr = pad_positions(r0 + uy, ho, pad, rows);
+#pragma unroll
+      for (int ux = 0; ux < UP; ++ux) {
+        int cols[3];
+        const int nc = pad_positions(c0 + ux, wo, pad, cols);
+        for (int r = 0; r < nr; ++r)
+          for (int q = 0; q < nc; ++q) {
+            if (r == 0 && q == 0) continue;  // the interior copy is already in acc
+            const F8 t = load8(base + ((long long)rows[r] * wop + cols[q]) * c);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc.v[e] += t.v[e];
+          }
+      }
+    }
+  }
+  return acc;
+}
+// pixels a thread keeps in flight per batch
+template <int UP>
+struct FoldBatch {
+  static constexpr int U = UP == 1 ? 8 : 2;
+};
+
 // sums = {sum dz, sum dz*(x - mean)}; the finalize kernels multiply the second by rinv (keeps this loop at 3
 // coefficient vectors so that four blocks fit per SM).
 template <int UP>
@@ -662,29 +773,60 @@ __device__ __forceinline__ void norm_bwd_reduce_body(Blk blk, const bf16* __rest
                                                      const float* __restrict__ b, int relu,
                                                      const float* __restrict__ mean, float* __restrict__ sums, int h,
                                                      int w, int c) {
+  constexpr int U = FoldBatch<UP>::U;
   const int hw = h * w;
-  const long long co = (long long)blk.by * c + (threadIdx.x % (c / 8)) * 8;  // this thread's (n, channel group)
+  const int cgs = c / 8;
+  const int rows = blockDim.x / cgs;
+  const int cg = threadIdx.x % cgs, r = threadIdx.x / cgs;
+  const int n = blk.by;
+  const int per = (hw + blk.nbx - 1) / blk.nbx;
+  const int p0 = blk.bx * per, p1 = min(hw, p0 + per);
+  const long long co = (long long)n * c + cg * 8;  // this thread's (n, channel group)
   const F8 fa = loadf8(a + co), fb = loadf8(b + co), fm = loadf8(mean + co);
-  auto fn = [&](int n, int pix, int cg, F8& u, F8& v) {
-    const int yy = pix / w, x = pix - yy * w;
-    const F8 g = fold_grad<UP>(g_out, n, yy, x, cg, h, w, c, out_pad);
-    const F8 xv = load8(y + ((long long)n * hw + pix) * c + cg * 8);
+  const int wop = w * UP + 2 * out_pad;
+  const bf16* gbase = g_out + (long long)n * (h * UP + 2 * out_pad) * wop * c + cg * 8;
+  const bf16* ybase = y + (long long)n * hw * c + cg * 8;
+  float s0[8], s1[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float dz = g.v[e];
-      if (relu && fmaf(xv.v[e], fa.v[e], fb.v[e]) <= 0.f) dz = 0.f;
-      u.v[e] = dz;
-      v.v[e] = dz * (xv.v[e] - fm.v[e]);
+  for (int e = 0; e < 8; ++e) s0[e] = s1[e] = 0.f;
+  if (r < rows)
+    for (int pb = p0 + r; pb < p1; pb += rows * U) {
+      FoldRaw<UP> gr[U];
+      uint4 yv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int pix = min(pb + u * rows, p1 - 1);  // tail: harmless duplicate loads, masked below
+        const int yy = pix / w, x = pix - yy * w;
+        fold_load<UP>(gr[u], gbase, yy, x, wop, c, out_pad);
+        yv[u] = *reinterpret_cast<const uint4*>(ybase + (long long)pix * c);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int pix = pb + u * rows;
+        if (pix < p1) {
+          const int yy = pix / w, x = pix - yy * w;
+          const F8 g = fold_finish<UP>(gr[u], gbase, yy, x, h, w, c, out_pad);
+          const F8 xv = unpack8(yv[u]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float dz = g.v[e];
+            if (relu && fmaf(xv.v[e], fa.v[e], fb.v[e]) <= 0.f) dz = 0.f;
+            s0[e] += dz;
+            s1[e] = fmaf(dz, xv.v[e] - fm.v[e], s1[e]);
+          }
+        }
+      }
     }
-  };
-  reduce_nc(blk, fn, sums, hw, c);
+  reduce_nc_tail(blk, s0, s1, sums, c);
 }
 template <int UP>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 norm_bwd_reduce_kernel(const bf16* __restrict__ g_out, int out_pad, const bf16* __restrict__ y,
                                        const float* __restrict__ a, const float* __restrict__ b, int relu,
                                        const float* __restrict__ mean, const float* __restrict__ rinv,
                                        float* __restrict__ sums, int h, int w, int c) {
+  pdl_wait();
+  pdl_trigger();
   norm_bwd_reduce_body<UP>(launch_blk(), g_out, out_pad, y, a, b, relu, mean, sums, h, w, c);
 }
 
@@ -762,6 +904,8 @@ __global__ void norm_bwd_finalize_kernel(const float* __restrict__ sums, int spl
                                          float* __restrict__ ca, float* __restrict__ cb, float* __restrict__ cc,
                                          float* __restrict__ g_w, float* __restrict__ g_b, long long ldg, int hw,
                                          int c) {
+  pdl_wait();
+  pdl_trigger();
   norm_bwd_finalize_body(blockIdx.x, sums, splits, mode, p_w, ldw, rinv, eps, ca, cb, cc, g_w, g_b, ldg, hw, c);
 }
 
@@ -792,31 +936,50 @@ __device__ __forceinline__ void norm_bwd_apply_body(Blk blk, const bf16* __restr
       k0.v[e] = fcc.v[e] - k1.v[e] * fm.v[e];
     }
   }
-#pragma unroll 2
-  for (int pix = p0 + r; pix < p1; pix += rows) {
-    const int yy = pix / w, x = pix - yy * w;
-    const F8 gr = fold_grad<UP>(g_out, bb, yy, x, g, h, w, c, out_pad);
-    const long long i8 = ((long long)bb * hw + pix) * c + g * 8;
-    const F8 xv = load8(y + i8);
-    F8 d;
+  constexpr int U = FoldBatch<UP>::U;
+  const int wop = w * UP + 2 * out_pad;
+  const bf16* gbase = g_out + (long long)bb * (h * UP + 2 * out_pad) * wop * c + g * 8;
+  const bf16* ybase = y + (long long)bb * hw * c + g * 8;
+  for (int pb = p0 + r; pb < p1; pb += rows * U) {
+    FoldRaw<UP> graw[U];
+    uint4 yv[U];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float dz = gr.v[e];
-      if (relu && fmaf(xv.v[e], fa.v[e], fb.v[e]) <= 0.f) dz = 0.f;
-      d.v[e] = fmaf(fca.v[e], dz, fmaf(k1.v[e], xv.v[e], k0.v[e]));
+    for (int u = 0; u < U; ++u) {
+      const int pix = min(pb + u * rows, p1 - 1);  // tail: harmless duplicate loads, masked below
+      const int yy = pix / w, x = pix - yy * w;
+      fold_load<UP>(graw[u], gbase, yy, x, wop, c, out_pad);
+      yv[u] = *reinterpret_cast<const uint4*>(ybase + (long long)pix * c);
     }
-    store8(dy + i8, d);
-    if (g_res) store8(g_res + (((long long)bb * (h + 2 * res_pad) + yy + res_pad) * (w + 2 * res_pad) + x + res_pad) * c + g * 8, gr);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pix = pb + u * rows;
+      if (pix < p1) {
+        const int yy = pix / w, x = pix - yy * w;
+        const F8 gr = fold_finish<UP>(graw[u], gbase, yy, x, h, w, c, out_pad);
+        const F8 xv = unpack8(yv[u]);
+        F8 d;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float dz = gr.v[e];
+          if (relu && fmaf(xv.v[e], fa.v[e], fb.v[e]) <= 0.f) dz = 0.f;
+          d.v[e] = fmaf(fca.v[e], dz, fmaf(k1.v[e], xv.v[e], k0.v[e]));
+        }
+        store8(dy + ((long long)bb * hw + pix) * c + g * 8, d);
+        if (g_res) store8(g_res + (((long long)bb * (h + 2 * res_pad) + yy + res_pad) * (w + 2 * res_pad) + x + res_pad) * c + g * 8, gr);
+      }
+    }
   }
 }
 template <int UP>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 norm_bwd_apply_kernel(const bf16* __restrict__ g_out, int out_pad, const bf16* __restrict__ y,
                                       const float* __restrict__ a, const float* __restrict__ b, int relu,
                                       const float* __restrict__ mean, const float* __restrict__ rinv,
                                       const float* __restrict__ ca, const float* __restrict__ cb,
                                       const float* __restrict__ cc, bf16* __restrict__ dy, bf16* __restrict__ g_res,
                                       int res_pad, int n, int h, int w, int c) {
+  pdl_wait();
+  pdl_trigger();
   norm_bwd_apply_body<UP>(launch_blk(), g_out, out_pad, y, a, b, relu, mean, rinv, ca, cb, cc, dy, g_res, res_pad, n, h, w, c);
 }
 
@@ -850,6 +1013,8 @@ struct NormFusedArgs {
 
 template <int UP>
 __global__ void __launch_bounds__(256, 3) norm_fwd_fused_kernel(const NormFusedArgs p) {
+  pdl_wait();
+  pdl_trigger();
   cg::grid_group grid = cg::this_grid();
   const Blk blk = launch_blk();
   const int hw = p.h * p.w;
@@ -869,6 +1034,8 @@ __global__ void __launch_bounds__(256, 3) norm_fwd_fused_kernel(const NormFusedA
 
 template <int UP>
 __global__ void __launch_bounds__(256, 2) norm_bwd_fused_kernel(const NormFusedArgs p) {
+  pdl_wait();
+  pdl_trigger();
   cg::grid_group grid = cg::this_grid();
   const Blk blk = launch_blk();
   const int hw = p.h * p.w;
@@ -889,6 +1056,8 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_fused_kernel(const NormFusedA
 
 __global__ void act_bwd_kernel(const bf16* __restrict__ g_out, const bf16* __restrict__ out_act, int pad, int act,
                                bf16* __restrict__ dy, int n, int h, int w, int c) {
+  pdl_wait();
+  pdl_trigger();
   const int cg = c / 8;
   const long long total = (long long)n * h * w * cg;
   const int hp = h + 2 * pad, wp = w + 2 * pad;
@@ -919,6 +1088,8 @@ __global__ void act_bwd_kernel(const bf16* __restrict__ g_out, const bf16* __res
 //   out[n][co][y][x] = act(bias[co] + sum_kw R[n][y][x+kw][kw*4+co])           (NCHW fp32, the public format)
 __global__ void rspace_combine_kernel(const bf16* __restrict__ r, const float* __restrict__ bias,
                                       float* __restrict__ out, int n, int cout, int h, int w, int kw, int act) {
+  pdl_wait();
+  pdl_trigger();
   const int wp = w + kw - 1;
   const long long total = (long long)n * h * w;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -949,6 +1120,8 @@ __global__ void rspace_combine_kernel(const bf16* __restrict__ r, const float* _
 __global__ void rspace_expand_kernel(const float* __restrict__ g, const float* __restrict__ out,
                                      bf16* __restrict__ dr, float* __restrict__ dbias, int n, int cout, int h, int w,
                                      int kw, int act) {
+  pdl_wait();
+  pdl_trigger();
   const int wp = w + kw - 1;
   const long long total = (long long)n * h * wp;
   float bsum[4] = {0.f, 0.f, 0.f, 0.f};
@@ -1001,6 +1174,8 @@ __global__ void rspace_expand_kernel(const float* __restrict__ g, const float* _
 // ------------------------------------------------------------------ weights
 __global__ void gather_cast_kernel(const float* __restrict__ src, const int* __restrict__ idx, bf16* __restrict__ dst,
                                    long long n) {
+  pdl_wait();
+  pdl_trigger();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int j = idx[i];
     dst[i] = __float2bfloat16(j >= 0 ? src[j] : 0.f);
@@ -1008,12 +1183,16 @@ __global__ void gather_cast_kernel(const float* __restrict__ src, const int* __r
 }
 __global__ void gather_add_kernel(const float* __restrict__ src, const int* __restrict__ idx, float* __restrict__ dst,
                                   long long n) {
+  pdl_wait();
+  pdl_trigger();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int j = idx[i];
     if (j >= 0) dst[i] += src[j];
   }
 }
 __global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  pdl_wait();
+  pdl_trigger();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = __float2bfloat16(src[i]);
 }
@@ -1023,6 +1202,8 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict
 __global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                   const float* __restrict__ bias, float* __restrict__ y, int b, int in, int out,
                                   int relu) {
+  pdl_wait();
+  pdl_trigger();
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= (long long)b * out) return;
@@ -1039,6 +1220,8 @@ __global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __re
 __global__ void linear_bwd_dx_kernel(const float* __restrict__ w, const float* __restrict__ y,
                                      const float* __restrict__ dy, int relu, float* __restrict__ dx, int b, int in,
                                      int out) {
+  pdl_wait();
+  pdl_trigger();
   const int bb = blockIdx.y;
   const int o0 = blockIdx.x * 64, o1 = min(out, o0 + 64);
   __shared__ float g[64];
@@ -1058,6 +1241,8 @@ __global__ void linear_bwd_dx_kernel(const float* __restrict__ w, const float* _
 __global__ void linear_bwd_dw_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                      const float* __restrict__ dy, int relu, float* __restrict__ dw,
                                      float* __restrict__ db, int b, int in, int out) {
+  pdl_wait();
+  pdl_trigger();
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= (long long)out * in) return;
   const int i = (int)(t % in), o = (int)(t / in);
@@ -1074,6 +1259,8 @@ __global__ void linear_bwd_dw_kernel(const float* __restrict__ x, const float* _
 
 // ------------------------------------------------------------------ GAP / discriminator head / pooling / losses
 __global__ void gap_fwd_kernel(const bf16* __restrict__ y, float* __restrict__ out, int hw, int c) {
+  pdl_wait();
+  pdl_trigger();
   // block per (n, 32-channel group); threads (32 ch) x (8 rows)
   const int n = blockIdx.y, c0 = blockIdx.x * 32;
   const int ch = c0 + (threadIdx.x & 31), r = threadIdx.x >> 5;
@@ -1090,6 +1277,8 @@ __global__ void gap_fwd_kernel(const bf16* __restrict__ y, float* __restrict__ o
   }
 }
 __global__ void gap_bwd_kernel(const float* __restrict__ g, bf16* __restrict__ dy, int n, int hw, int c) {
+  pdl_wait();
+  pdl_trigger();
   const long long total = (long long)n * hw * c;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int ch = (int)(i % c);
@@ -1102,6 +1291,8 @@ __global__ void gap_bwd_kernel(const float* __restrict__ g, bf16* __restrict__ d
 __global__ void dis_head_fwd_kernel(const bf16* __restrict__ y, const float* __restrict__ w,
                                     const float* __restrict__ bias, float target, float* __restrict__ out,
                                     float* __restrict__ loss, float scale, long long npix, int c) {
+  pdl_wait();
+  pdl_trigger();
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   float l = 0.f;
@@ -1133,6 +1324,8 @@ __global__ void dis_head_fwd_kernel(const bf16* __restrict__ y, const float* __r
 __global__ void dis_head_bwd_kernel(const bf16* __restrict__ y, const float* __restrict__ w,
                                     const float* __restrict__ out, float target, const float* __restrict__ gscale_dev,
                                     float gscale, bf16* __restrict__ dy, long long npix, int c) {
+  pdl_wait();
+  pdl_trigger();
   // thread per (pixel, 8-channel group)
   const int cg = c / 8;
   const float gs = gscale * (gscale_dev ? gscale_dev[0] : 1.f) * 2.f / (float)npix;
@@ -1152,6 +1345,8 @@ __global__ void dis_head_bwd_kernel(const bf16* __restrict__ y, const float* __r
 __global__ void dis_head_wgrad_kernel(const bf16* __restrict__ y, const float* __restrict__ out, float target,
                                       const float* __restrict__ gscale_dev, float gscale, float* __restrict__ dw,
                                       float* __restrict__ db, long long npix, int c) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float red[];
   const int cgs = c / 8;
   const int rows = blockDim.x / cgs;
@@ -1190,6 +1385,8 @@ __global__ void dis_head_wgrad_kernel(const bf16* __restrict__ y, const float* _
 }
 
 __global__ void avgpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int nc, int h, int w) {
+  pdl_wait();
+  pdl_trigger();
   const int ho = (h + 1) / 2, wo = (w + 1) / 2;  // floor((h + 2 - 3)/2) + 1
   const long long total = (long long)nc * ho * wo;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -1209,6 +1406,8 @@ __global__ void avgpool_fwd_kernel(const float* __restrict__ x, float* __restric
   }
 }
 __global__ void avgpool_bwd_kernel(const float* __restrict__ gy, float* __restrict__ gx, int nc, int h, int w) {
+  pdl_wait();
+  pdl_trigger();
   const int ho = (h + 1) / 2, wo = (w + 1) / 2;
   const long long total = (long long)nc * h * w;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -1245,6 +1444,8 @@ __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16(
 template <typename T>
 __global__ void l1_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b, float* __restrict__ loss, float scale,
                               long long n) {
+  pdl_wait();
+  pdl_trigger();
   float acc = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     acc += fabsf(to_f<T>(a[i]) - to_f<T>(b[i]));
@@ -1262,6 +1463,8 @@ __global__ void l1_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b, 
 template <typename T>
 __global__ void l1_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b, const float* __restrict__ gscale_dev,
                               float scale, T* __restrict__ ga, T* __restrict__ gb, long long n) {
+  pdl_wait();
+  pdl_trigger();
   const float g = scale * (gscale_dev ? gscale_dev[0] : 1.f);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float d = to_f<T>(a[i]) - to_f<T>(b[i]);
@@ -1276,6 +1479,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
                             float* __restrict__ v, float* __restrict__ p_saved, bf16* __restrict__ p_bf16, long long n,
                             int mode, int save, float lr, float b1, float b2, float eps, float wd, float bc1,
                             float bc2, float gscale, const float* __restrict__ hyper) {
+  pdl_wait();
+  pdl_trigger();
   if (hyper) {  // step-dependent scalars read from device memory (CUDA-graph replays)
     lr = hyper[0];
     bc1 = hyper[1];
@@ -1311,9 +1516,13 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 }
 
 __global__ void fill_kernel(float* __restrict__ p, float v, long long n) {
+  pdl_wait();
+  pdl_trigger();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
 __global__ void add_bf16_kernel(bf16* __restrict__ dst, const bf16* __restrict__ src, long long n8) {
+  pdl_wait();
+  pdl_trigger();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     F8 a = load8(dst + i * 8);
     const F8 b = load8(src + i * 8);
@@ -1352,24 +1561,6 @@ __device__ __forceinline__ float ld_dsmem_f32(const float* local, uint32_t rank)
   float v;
   asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
   return v;
-}
-__device__ __forceinline__ F8 unpack8(const uint4& u) {
-  F8 r;
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 f = __bfloat1622float2(h[i]);
-    r.v[2 * i] = f.x;
-    r.v[2 * i + 1] = f.y;
-  }
-  return r;
-}
-__device__ __forceinline__ uint4 pack8(const F8& r) {
-  uint4 u;
-  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(r.v[2 * i], r.v[2 * i + 1]);
-  return u;
 }
 // Sum this block's per-thread {u, v} 8-channel vectors (thread parity = which 8-channel half of the 16-channel
 // slab) into cpart[16][2] in a fixed order: xor-shuffles over equal-parity lanes, then the 8 warps in index order.
@@ -1430,6 +1621,8 @@ struct NormSlabArgs {
 };
 
 __global__ void __launch_bounds__(256, 4) norm_fwd_slab_kernel(const NormSlabArgs p) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(16) uint8_t slab_raw[];
   uint4* slab = reinterpret_cast<uint4*>(slab_raw);  // [per][2] 8-channel chunks of y
   __shared__ float wred[8][2][8][2];
@@ -1526,6 +1719,8 @@ __global__ void __launch_bounds__(256, 4) norm_fwd_slab_kernel(const NormSlabArg
 }
 
 __global__ void __launch_bounds__(256, 3) norm_bwd_slab_kernel(const NormSlabArgs p) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(16) uint8_t slab_raw[];
   uint4* slab = reinterpret_cast<uint4*>(slab_raw);  // [per][2][2]: y chunk, folded-gradient chunk
   __shared__ float wred[8][2][8][2];
@@ -1740,7 +1935,7 @@ int munit_image_to_act(const float* x, void* act, int n, int c, int h, int w, in
   if (cp % 8 || c > cp) return mb_fail(MUNIT_ERR_ARG, "image_to_act: cp");
   if (pad >= h || pad >= w) return mb_fail(MUNIT_ERR_ARG, "image_to_act: reflect pad >= size");
   const long long total = (long long)n * (h + 2 * pad) * (w + 2 * pad);
-  image_to_act_kernel<<<grid_for(total), 256, 0, ST(stream)>>>(x, BF(act), n, c, h, w, pad, cp);
+  mb_launch(image_to_act_kernel, dim3(grid_for(total)), dim3(256), 0, ST(stream), x, BF(act), n, c, h, w, pad, cp);
   MB_CHECK_LAUNCH("image_to_act");
   return MUNIT_OK;
 }
@@ -1749,7 +1944,7 @@ int munit_image_to_kwexp(const float* x, void* e, int n, int c, int h, int w, in
                          int cp, void* stream) {
   if (cp % 8 || c > cp || kw > kwp) return mb_fail(MUNIT_ERR_ARG, "image_to_kwexp: args");
   const long long total = (long long)n * (h + 2 * pad) * wo * kwp * (cp / 8);
-  image_to_kwexp_kernel<<<grid_for(total), 256, 0, ST(stream)>>>(x, BF(e), n, c, h, w, pad, kw, sx, wo, kwp, cp);
+  mb_launch(image_to_kwexp_kernel, dim3(grid_for(total)), dim3(256), 0, ST(stream), x, BF(e), n, c, h, w, pad, kw, sx, wo, kwp, cp);
   MB_CHECK_LAUNCH("image_to_kwexp");
   return MUNIT_OK;
 }
@@ -1757,7 +1952,7 @@ int munit_image_to_kwexp(const float* x, void* e, int n, int c, int h, int w, in
 int munit_kwexp_to_image_grad(const void* de, float* dx, int n, int c, int h, int w, int pad, int kw, int sx, int wo,
                               int kwp, int cp, void* stream) {
   if (c > 4) return mb_fail(MUNIT_ERR_ARG, "kwexp_to_image_grad: c > 4");
-  kwexp_to_image_grad_kernel<<<grid_for((long long)n * h * w), 256, 0, ST(stream)>>>(CBF(de), dx, n, c, h, w, pad, kw,
+  mb_launch(kwexp_to_image_grad_kernel, dim3(grid_for((long long)n * h * w)), dim3(256), 0, ST(stream), CBF(de), dx, n, c, h, w, pad, kw,
                                                                                       sx, wo, kwp, cp);
   MB_CHECK_LAUNCH("kwexp_to_image_grad");
   return MUNIT_OK;
@@ -1765,14 +1960,14 @@ int munit_kwexp_to_image_grad(const void* de, float* dx, int n, int c, int h, in
 
 int munit_act_to_nchw(const void* act, float* y, int n, int c, int h, int w, int pad, int cp, void* stream) {
   dim3 grid((w + 31) / 32, (c + 31) / 32, n * h), block(32, 8);
-  act_to_nchw_kernel<<<grid, block, 0, ST(stream)>>>(CBF(act), y, n, c, h, w, pad, cp);
+  mb_launch(act_to_nchw_kernel, dim3(grid), dim3(block), 0, ST(stream), CBF(act), y, n, c, h, w, pad, cp);
   MB_CHECK_LAUNCH("act_to_nchw");
   return MUNIT_OK;
 }
 
 int munit_nchw_to_act(const float* x, void* act, int n, int c, int h, int w, int pad, int cp, void* stream) {
   dim3 grid((w + 31) / 32, (cp + 31) / 32, n * h), block(32, 8);
-  nchw_to_act_kernel<<<grid, block, 0, ST(stream)>>>(x, BF(act), n, c, h, w, pad, cp);
+  mb_launch(nchw_to_act_kernel, dim3(grid), dim3(block), 0, ST(stream), x, BF(act), n, c, h, w, pad, cp);
   MB_CHECK_LAUNCH("nchw_to_act");
   return MUNIT_OK;
 }
@@ -1782,7 +1977,7 @@ int munit_halo_fill(void* act, int n, int h, int w, int c, int pad, void* stream
   if (c % 8) return mb_fail(MUNIT_ERR_ARG, "halo_fill: c %% 8");
   if (pad >= h || pad >= w) return mb_fail(MUNIT_ERR_ARG, "halo_fill: reflect pad >= size");
   const long long total = (long long)n * (h + 2 * pad) * (w + 2 * pad) * (c / 8);
-  halo_fill_kernel<<<grid_for(total), 256, 0, ST(stream)>>>(BF(act), n, h, w, c, pad);
+  mb_launch(halo_fill_kernel, dim3(grid_for(total)), dim3(256), 0, ST(stream), BF(act), n, h, w, c, pad);
   MB_CHECK_LAUNCH("halo_fill");
   return MUNIT_OK;
 }
@@ -1796,7 +1991,7 @@ int munit_norm_stats(const void* y, float* stats, float* shift, int n, int hw, i
   if (c % 8 || c / 8 > 256 || 256 % (c / 8)) return mb_fail(MUNIT_ERR_ARG, "norm_stats: channels %d", c);
   const int rows = 256 / (c / 8);
   dim3 grid(reduce_splits(hw, c), n);
-  norm_stats_kernel<<<grid, 256, sizeof(float) * 2 * rows * c, ST(stream)>>>(CBF(y), stats, shift, hw, c);
+  mb_launch(norm_stats_kernel, dim3(grid), dim3(256), sizeof(float) * 2 * rows * c, ST(stream), CBF(y), stats, shift, hw, c);
   MB_CHECK_LAUNCH("norm_stats");
   return MUNIT_OK;
 }
@@ -1807,12 +2002,12 @@ int munit_norm_finalize(const float* stats, const float* shift, int mode, const 
   if (mode != MUNIT_NORM_IN && (!p_w || !p_b)) return mb_fail(MUNIT_ERR_ARG, "norm_finalize: missing affine params");
   if (mode != MUNIT_NORM_LN) {
     dim3 grid((c + 31) / 32, n);
-    norm_finalize_nc_kernel<<<grid, 256, 0, ST(stream)>>>(stats, reduce_splits(hw, c), shift, mode == MUNIT_NORM_ADAIN,
+    mb_launch(norm_finalize_nc_kernel, dim3(grid), dim3(256), 0, ST(stream), stats, reduce_splits(hw, c), shift, mode == MUNIT_NORM_ADAIN,
                                                           p_w, p_b, ldw, eps, mean, rinv, a, b, hw, c);
     MB_CHECK_LAUNCH("norm_finalize_nc");
     return MUNIT_OK;
   }
-  norm_finalize_kernel<<<n, 256, sizeof(double) * 2 * c, ST(stream)>>>(stats, reduce_splits(hw, c), shift, mode, p_w, p_b, ldw, eps, mean,
+  mb_launch(norm_finalize_kernel, dim3(n), dim3(256), sizeof(double) * 2 * c, ST(stream), stats, reduce_splits(hw, c), shift, mode, p_w, p_b, ldw, eps, mean,
                                                   rinv, a, b, hw, c);
   MB_CHECK_LAUNCH("norm_finalize");
   return MUNIT_OK;
@@ -1825,14 +2020,14 @@ int munit_norm_finalize_parts(const float* stats, int splits, int kind, int mode
   if (kind == 1 && mode != MUNIT_NORM_LN) {
     if (mode == MUNIT_NORM_ADAIN && (!p_w || !p_b)) return mb_fail(MUNIT_ERR_ARG, "norm_finalize_parts: missing affine params");
     dim3 grid((c + 31) / 32, n);
-    norm_finalize_nc_kernel<<<grid, 256, 0, ST(stream)>>>(stats, splits, nullptr, mode == MUNIT_NORM_ADAIN, p_w, p_b, ldw,
+    mb_launch(norm_finalize_nc_kernel, dim3(grid), dim3(256), 0, ST(stream), stats, splits, nullptr, mode == MUNIT_NORM_ADAIN, p_w, p_b, ldw,
                                                           eps, mean, rinv, a, b, hw, c);
     MB_CHECK_LAUNCH("norm_finalize_parts(nc)");
     return MUNIT_OK;
   }
   if (kind == 2 && mode == MUNIT_NORM_LN) {
     if (!p_w || !p_b) return mb_fail(MUNIT_ERR_ARG, "norm_finalize_parts: missing affine params");
-    norm_finalize_ln_total_kernel<<<n, 256, 0, ST(stream)>>>(stats, splits, p_w, p_b, eps, mean, rinv, a, b, hw, c);
+    mb_launch(norm_finalize_ln_total_kernel, dim3(n), dim3(256), 0, ST(stream), stats, splits, p_w, p_b, eps, mean, rinv, a, b, hw, c);
     MB_CHECK_LAUNCH("norm_finalize_parts(ln)");
     return MUNIT_OK;
   }
@@ -1844,10 +2039,10 @@ int munit_norm_apply(const void* y, const float* a, const float* b, int relu, co
   if (c % 8 || c / 8 > 256 || 256 % (c / 8)) return mb_fail(MUNIT_ERR_ARG, "norm_apply: channels %d", c);
   dim3 grid(apply_splits(h * w, c, n), n);
   if (upsample == 2)
-    norm_apply_kernel<2><<<grid, 256, 0, ST(stream)>>>(CBF(y), a, b, relu, CBF(residual), res_pad, BF(out_act),
+    mb_launch(norm_apply_kernel<2>, dim3(grid), dim3(256), 0, ST(stream), CBF(y), a, b, relu, CBF(residual), res_pad, BF(out_act),
                                                         out_pad, n, h, w, c);
   else if (upsample == 1)
-    norm_apply_kernel<1><<<grid, 256, 0, ST(stream)>>>(CBF(y), a, b, relu, CBF(residual), res_pad, BF(out_act),
+    mb_launch(norm_apply_kernel<1>, dim3(grid), dim3(256), 0, ST(stream), CBF(y), a, b, relu, CBF(residual), res_pad, BF(out_act),
                                                         out_pad, n, h, w, c);
   else
     return mb_fail(MUNIT_ERR_ARG, "norm_apply: upsample must be 1 or 2");
@@ -1863,10 +2058,10 @@ int munit_norm_bwd_reduce(const void* g_out, int out_pad, int upsample, const vo
   dim3 grid(reduce_splits(h * w, c), n);
   const size_t sm = sizeof(float) * 2 * rows * c;
   if (upsample == 2)
-    norm_bwd_reduce_kernel<2><<<grid, 256, sm, ST(stream)>>>(CBF(g_out), out_pad, CBF(y), a, b, relu, mean, rinv, sums,
+    mb_launch(norm_bwd_reduce_kernel<2>, dim3(grid), dim3(256), sm, ST(stream), CBF(g_out), out_pad, CBF(y), a, b, relu, mean, rinv, sums,
                                                              h, w, c);
   else
-    norm_bwd_reduce_kernel<1><<<grid, 256, sm, ST(stream)>>>(CBF(g_out), out_pad, CBF(y), a, b, relu, mean, rinv, sums,
+    mb_launch(norm_bwd_reduce_kernel<1>, dim3(grid), dim3(256), sm, ST(stream), CBF(g_out), out_pad, CBF(y), a, b, relu, mean, rinv, sums,
                                                              h, w, c);
   MB_CHECK_LAUNCH("norm_bwd_reduce");
   return MUNIT_OK;
@@ -1877,12 +2072,12 @@ int munit_norm_bwd_finalize(const float* sums, int mode, const float* p_w, int64
                             void* stream) {
   if (mode != MUNIT_NORM_LN) {
     dim3 grid((c + 31) / 32, n);
-    norm_bwd_finalize_nc_kernel<<<grid, 256, 0, ST(stream)>>>(sums, reduce_splits(hw, c), mode == MUNIT_NORM_ADAIN, p_w,
+    mb_launch(norm_bwd_finalize_nc_kernel, dim3(grid), dim3(256), 0, ST(stream), sums, reduce_splits(hw, c), mode == MUNIT_NORM_ADAIN, p_w,
                                                               ldw, rinv, ca, cb, cc, g_w, g_b, ldg, hw, c);
     MB_CHECK_LAUNCH("norm_bwd_finalize_nc");
     return MUNIT_OK;
   }
-  norm_bwd_finalize_kernel<<<n, 256, sizeof(double) * 2 * c, ST(stream)>>>(sums, reduce_splits(hw, c), mode, p_w, ldw, rinv, eps, ca, cb, cc,
+  mb_launch(norm_bwd_finalize_kernel, dim3(n), dim3(256), sizeof(double) * 2 * c, ST(stream), sums, reduce_splits(hw, c), mode, p_w, ldw, rinv, eps, ca, cb, cc,
                                                       g_w, g_b, ldg, hw, c);
   MB_CHECK_LAUNCH("norm_bwd_finalize");
   return MUNIT_OK;
@@ -1895,10 +2090,10 @@ int munit_norm_bwd_apply(const void* g_out, int out_pad, int upsample, const voi
   if (c % 8 || c / 8 > 256 || 256 % (c / 8)) return mb_fail(MUNIT_ERR_ARG, "norm_bwd_apply: channels %d", c);
   dim3 grid(apply_splits(h * w, c, n), n);
   if (upsample == 2)
-    norm_bwd_apply_kernel<2><<<grid, 256, 0, ST(stream)>>>(CBF(g_out), out_pad, CBF(y), a, b, relu, mean, rinv, ca, cb,
+    mb_launch(norm_bwd_apply_kernel<2>, dim3(grid), dim3(256), 0, ST(stream), CBF(g_out), out_pad, CBF(y), a, b, relu, mean, rinv, ca, cb,
                                                             cc, BF(dy), BF(g_res), res_pad, n, h, w, c);
   else
-    norm_bwd_apply_kernel<1><<<grid, 256, 0, ST(stream)>>>(CBF(g_out), out_pad, CBF(y), a, b, relu, mean, rinv, ca, cb,
+    mb_launch(norm_bwd_apply_kernel<1>, dim3(grid), dim3(256), 0, ST(stream), CBF(g_out), out_pad, CBF(y), a, b, relu, mean, rinv, ca, cb,
                                                             cc, BF(dy), BF(g_res), res_pad, n, h, w, c);
   MB_CHECK_LAUNCH("norm_bwd_apply");
   return MUNIT_OK;
@@ -1997,7 +2192,7 @@ int munit_act_bwd(const void* g_out, const void* out_act, int pad, int act, void
                   void* stream) {
   if (c % 8) return mb_fail(MUNIT_ERR_ARG, "act_bwd: c %% 8");
   const long long total = (long long)n * h * w * (c / 8);
-  act_bwd_kernel<<<grid_for(total), 256, 0, ST(stream)>>>(CBF(g_out), CBF(out_act), pad, act, BF(dy), n, h, w, c);
+  mb_launch(act_bwd_kernel, dim3(grid_for(total)), dim3(256), 0, ST(stream), CBF(g_out), CBF(out_act), pad, act, BF(dy), n, h, w, c);
   MB_CHECK_LAUNCH("act_bwd");
   return MUNIT_OK;
 }
@@ -2008,7 +2203,7 @@ int munit_colsum(const void* dy, float* dbias, int64_t npix, int c, int c_out, v
   long long splits = (npix + rows * 16 - 1) / (rows * 16);
   if (splits > 2048) splits = 2048;
   if (splits < 1) splits = 1;
-  colsum_kernel<<<(int)splits, 256, sizeof(float) * rows * c, ST(stream)>>>(CBF(dy), dbias, npix, c, c_out < c ? c_out : c);
+  mb_launch(colsum_kernel, dim3((int)splits), dim3(256), sizeof(float) * rows * c, ST(stream), CBF(dy), dbias, npix, c, c_out < c ? c_out : c);
   MB_CHECK_LAUNCH("colsum");
   return MUNIT_OK;
 }
@@ -2016,31 +2211,31 @@ int munit_colsum(const void* dy, float* dbias, int64_t npix, int c, int c_out, v
 int munit_rspace_combine(const void* r, const float* bias, float* out, int n, int cout, int h, int w, int kw, int act,
                          void* stream) {
   if (cout > 4 || kw > 8) return mb_fail(MUNIT_ERR_ARG, "rspace_combine: cout <= 4 and kw <= 8 required");
-  rspace_combine_kernel<<<grid_for((long long)n * h * w), 256, 0, ST(stream)>>>(CBF(r), bias, out, n, cout, h, w, kw, act);
+  mb_launch(rspace_combine_kernel, dim3(grid_for((long long)n * h * w)), dim3(256), 0, ST(stream), CBF(r), bias, out, n, cout, h, w, kw, act);
   MB_CHECK_LAUNCH("rspace_combine");
   return MUNIT_OK;
 }
 int munit_rspace_expand(const float* g, const float* out, void* dr, float* dbias, int n, int cout, int h, int w, int kw,
                         int act, void* stream) {
   if (cout > 4 || kw > 8) return mb_fail(MUNIT_ERR_ARG, "rspace_expand: cout <= 4 and kw <= 8 required");
-  rspace_expand_kernel<<<grid_for((long long)n * h * (w + kw - 1), 256, 148 * 8), 256, 0, ST(stream)>>>(
+  mb_launch(rspace_expand_kernel, dim3(grid_for((long long)n * h * (w + kw - 1), 256, 148 * 8)), dim3(256), 0, ST(stream), 
       g, out, BF(dr), dbias, n, cout, h, w, kw, act);
   MB_CHECK_LAUNCH("rspace_expand");
   return MUNIT_OK;
 }
 
 int munit_gather_cast(const float* src, const int32_t* idx, void* dst, int64_t n, void* stream) {
-  gather_cast_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(src, idx, BF(dst), n);
+  mb_launch(gather_cast_kernel, dim3(grid_for(n)), dim3(256), 0, ST(stream), src, idx, BF(dst), n);
   MB_CHECK_LAUNCH("gather_cast");
   return MUNIT_OK;
 }
 int munit_gather_add(const float* src, const int32_t* idx, float* dst, int64_t n, void* stream) {
-  gather_add_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(src, idx, dst, n);
+  mb_launch(gather_add_kernel, dim3(grid_for(n)), dim3(256), 0, ST(stream), src, idx, dst, n);
   MB_CHECK_LAUNCH("gather_add");
   return MUNIT_OK;
 }
 int munit_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
-  cast_bf16_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(src, BF(dst), n);
+  mb_launch(cast_bf16_kernel, dim3(grid_for(n)), dim3(256), 0, ST(stream), src, BF(dst), n);
   MB_CHECK_LAUNCH("cast_bf16");
   return MUNIT_OK;
 }
@@ -2048,7 +2243,7 @@ int munit_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
 int munit_linear_fwd(const float* x, const float* w, const float* bias, float* y, int b, int in, int out, int relu,
                      void* stream) {
   const long long threads = (long long)b * out * 32;
-  linear_fwd_kernel<<<nblocks(threads, 256), 256, 0, ST(stream)>>>(x, w, bias, y, b, in, out, relu);
+  mb_launch(linear_fwd_kernel, dim3(nblocks(threads, 256)), dim3(256), 0, ST(stream), x, w, bias, y, b, in, out, relu);
   MB_CHECK_LAUNCH("linear_fwd");
   return MUNIT_OK;
 }
@@ -2057,11 +2252,11 @@ int munit_linear_bwd(const float* x, const float* w, const float* y, const float
   if (dx) {
     cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)b * in, ST(stream));
     dim3 grid((out + 63) / 64, b);
-    linear_bwd_dx_kernel<<<grid, in >= 256 ? 256 : 64, 0, ST(stream)>>>(w, y, dy, relu, dx, b, in, out);
+    mb_launch(linear_bwd_dx_kernel, dim3(grid), dim3(in >= 256 ? 256 : 64), 0, ST(stream), w, y, dy, relu, dx, b, in, out);
     MB_CHECK_LAUNCH("linear_bwd_dx");
   }
   if (dw) {
-    linear_bwd_dw_kernel<<<nblocks((long long)out * in, 128), 128, 0, ST(stream)>>>(x, y, dy, relu, dw, db, b, in, out);
+    mb_launch(linear_bwd_dw_kernel, dim3(nblocks((long long)out * in, 128)), dim3(128), 0, ST(stream), x, y, dy, relu, dw, db, b, in, out);
     MB_CHECK_LAUNCH("linear_bwd_dw");
   }
   return MUNIT_OK;
@@ -2069,12 +2264,12 @@ int munit_linear_bwd(const float* x, const float* w, const float* y, const float
 
 int munit_gap_fwd(const void* y, float* out, int n, int hw, int c, void* stream) {
   dim3 grid((c + 31) / 32, n);
-  gap_fwd_kernel<<<grid, 256, 0, ST(stream)>>>(CBF(y), out, hw, c);
+  mb_launch(gap_fwd_kernel, dim3(grid), dim3(256), 0, ST(stream), CBF(y), out, hw, c);
   MB_CHECK_LAUNCH("gap_fwd");
   return MUNIT_OK;
 }
 int munit_gap_bwd(const float* g, void* dy, int n, int hw, int c, void* stream) {
-  gap_bwd_kernel<<<grid_for((long long)n * hw * c), 256, 0, ST(stream)>>>(g, BF(dy), n, hw, c);
+  mb_launch(gap_bwd_kernel, dim3(grid_for((long long)n * hw * c)), dim3(256), 0, ST(stream), g, BF(dy), n, hw, c);
   MB_CHECK_LAUNCH("gap_bwd");
   return MUNIT_OK;
 }
@@ -2082,14 +2277,14 @@ int munit_gap_bwd(const float* g, void* dy, int n, int hw, int c, void* stream) 
 int munit_dis_head_fwd(const void* y, const float* w, const float* bias, float target, float* out, float* loss,
                        float scale, int64_t npix, int c, void* stream) {
   if (c % 8) return mb_fail(MUNIT_ERR_ARG, "dis_head: c %% 8");
-  dis_head_fwd_kernel<<<nblocks(npix * 32, 256), 256, 0, ST(stream)>>>(CBF(y), w, bias, target, out, loss, scale, npix,
+  mb_launch(dis_head_fwd_kernel, dim3(nblocks(npix * 32, 256)), dim3(256), 0, ST(stream), CBF(y), w, bias, target, out, loss, scale, npix,
                                                                         c);
   MB_CHECK_LAUNCH("dis_head_fwd");
   return MUNIT_OK;
 }
 int munit_dis_head_bwd(const void* y, const float* w, const float* out, float target, const float* gscale_dev,
                        float gscale, void* dy, float* dw, float* db, int64_t npix, int c, void* stream) {
-  dis_head_bwd_kernel<<<grid_for(npix * (c / 8)), 256, 0, ST(stream)>>>(CBF(y), w, out, target, gscale_dev, gscale,
+  mb_launch(dis_head_bwd_kernel, dim3(grid_for(npix * (c / 8))), dim3(256), 0, ST(stream), CBF(y), w, out, target, gscale_dev, gscale,
                                                                          BF(dy), npix, c);
   MB_CHECK_LAUNCH("dis_head_bwd");
   if (dw) {
@@ -2097,7 +2292,7 @@ int munit_dis_head_bwd(const void* y, const float* w, const float* out, float ta
     const int rows = 256 / (c / 8);
     long long splits = (npix + rows * 8 - 1) / (rows * 8);
     if (splits > 592) splits = 592;
-    dis_head_wgrad_kernel<<<(int)splits, 256, sizeof(float) * (rows * c + rows), ST(stream)>>>(
+    mb_launch(dis_head_wgrad_kernel, dim3((int)splits), dim3(256), sizeof(float) * (rows * c + rows), ST(stream), 
         CBF(y), out, target, gscale_dev, gscale, dw, db, npix, c);
     MB_CHECK_LAUNCH("dis_head_wgrad");
   }
@@ -2105,35 +2300,35 @@ int munit_dis_head_bwd(const void* y, const float* w, const float* out, float ta
 }
 
 int munit_avgpool3s2_fwd(const float* x, float* y, int nc, int h, int w, void* stream) {
-  avgpool_fwd_kernel<<<grid_for((long long)nc * ((h + 1) / 2) * ((w + 1) / 2)), 256, 0, ST(stream)>>>(x, y, nc, h, w);
+  mb_launch(avgpool_fwd_kernel, dim3(grid_for((long long)nc * ((h + 1) / 2) * ((w + 1) / 2))), dim3(256), 0, ST(stream), x, y, nc, h, w);
   MB_CHECK_LAUNCH("avgpool_fwd");
   return MUNIT_OK;
 }
 int munit_avgpool3s2_bwd(const float* gy, float* gx, int nc, int h, int w, void* stream) {
-  avgpool_bwd_kernel<<<grid_for((long long)nc * h * w), 256, 0, ST(stream)>>>(gy, gx, nc, h, w);
+  mb_launch(avgpool_bwd_kernel, dim3(grid_for((long long)nc * h * w)), dim3(256), 0, ST(stream), gy, gx, nc, h, w);
   MB_CHECK_LAUNCH("avgpool_bwd");
   return MUNIT_OK;
 }
 
 int munit_l1_fwd(const float* a, const float* b, float* loss, float scale, int64_t n, void* stream) {
-  l1_fwd_kernel<float><<<grid_for(n, 256, 592), 256, 0, ST(stream)>>>(a, b, loss, scale, n);
+  mb_launch(l1_fwd_kernel<float>, dim3(grid_for(n, 256, 592)), dim3(256), 0, ST(stream), a, b, loss, scale, n);
   MB_CHECK_LAUNCH("l1_fwd");
   return MUNIT_OK;
 }
 int munit_l1_bwd(const float* a, const float* b, const float* gscale_dev, float scale, float* ga, float* gb, int64_t n,
                  void* stream) {
-  l1_bwd_kernel<float><<<grid_for(n), 256, 0, ST(stream)>>>(a, b, gscale_dev, scale, ga, gb, n);
+  mb_launch(l1_bwd_kernel<float>, dim3(grid_for(n)), dim3(256), 0, ST(stream), a, b, gscale_dev, scale, ga, gb, n);
   MB_CHECK_LAUNCH("l1_bwd");
   return MUNIT_OK;
 }
 int munit_l1_bf16_fwd(const void* a, const void* b, float* loss, float scale, int64_t n, void* stream) {
-  l1_fwd_kernel<bf16><<<grid_for(n, 256, 592), 256, 0, ST(stream)>>>(CBF(a), CBF(b), loss, scale, n);
+  mb_launch(l1_fwd_kernel<bf16>, dim3(grid_for(n, 256, 592)), dim3(256), 0, ST(stream), CBF(a), CBF(b), loss, scale, n);
   MB_CHECK_LAUNCH("l1_bf16_fwd");
   return MUNIT_OK;
 }
 int munit_l1_bf16_bwd(const void* a, const void* b, const float* gscale_dev, float scale, void* ga, void* gb, int64_t n,
                       void* stream) {
-  l1_bwd_kernel<bf16><<<grid_for(n), 256, 0, ST(stream)>>>(CBF(a), CBF(b), gscale_dev, scale, BF(ga), BF(gb), n);
+  mb_launch(l1_bwd_kernel<bf16>, dim3(grid_for(n)), dim3(256), 0, ST(stream), CBF(a), CBF(b), gscale_dev, scale, BF(ga), BF(gb), n);
   MB_CHECK_LAUNCH("l1_bf16_bwd");
   return MUNIT_OK;
 }
@@ -2145,20 +2340,20 @@ int munit_adam(float* p, const float* g, float* m, float* v, float* p_saved, voi
   if (mode != 0 && !p_saved) return mb_fail(MUNIT_ERR_ARG, "adam: extragradient modes need p_saved");
   const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
   const float bc2 = (float)(1.0 - pow((double)beta2, (double)step));
-  adam_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(p, g, m, v, p_saved, BF(p_bf16), n, mode, save, lr, beta1, beta2,
+  mb_launch(adam_kernel, dim3(grid_for(n)), dim3(256), 0, ST(stream), p, g, m, v, p_saved, BF(p_bf16), n, mode, save, lr, beta1, beta2,
                                                    eps, wd, bc1, bc2, gscale, hyper_dev);
   MB_CHECK_LAUNCH("adam");
   return MUNIT_OK;
 }
 
 int munit_fill_f32(float* p, float v, int64_t n, void* stream) {
-  fill_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(p, v, n);
+  mb_launch(fill_kernel, dim3(grid_for(n)), dim3(256), 0, ST(stream), p, v, n);
   MB_CHECK_LAUNCH("fill");
   return MUNIT_OK;
 }
 int munit_add_bf16(void* dst, const void* src, int64_t n, void* stream) {
   if (n % 8) return mb_fail(MUNIT_ERR_ARG, "add_bf16: n %% 8");
-  add_bf16_kernel<<<grid_for(n / 8), 256, 0, ST(stream)>>>(BF(dst), CBF(src), n / 8);
+  mb_launch(add_bf16_kernel, dim3(grid_for(n / 8)), dim3(256), 0, ST(stream), BF(dst), CBF(src), n / 8);
   MB_CHECK_LAUNCH("add_bf16");
   return MUNIT_OK;
 }

@@ -171,6 +171,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   if (CS > 1) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts / arrives remotely
   tc_fence_after();
+  // PDL: barriers, tensor-map prefetch and the TMEM allocation above overlapped the previous kernel's tail; nothing
+  // before this point touched memory another kernel writes.
+  pdl_wait();
+  pdl_trigger();
   const uint32_t tmem_base = tmem_base_slot;
   const uint32_t cta_rank = CS > 1 ? cluster_ctarank() : 0;
   constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1);
@@ -380,6 +384,10 @@ tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // PDL: barriers, tensor-map prefetch and the TMEM allocation above overlapped the previous kernel's tail; nothing
+  // before this point touched memory another kernel writes.
+  pdl_wait();
+  pdl_trigger();
   const uint32_t tmem_base = tmem_base_slot;
 
   if (warp == 0) {
@@ -560,6 +568,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // PDL: barriers, tensor-map prefetch and the TMEM allocation above overlapped the previous kernel's tail; nothing
+  // before this point touched memory another kernel writes.
+  pdl_wait();
+  pdl_trigger();
   const uint32_t tmem_base = tmem_base_slot;
 
   if (num_kb > 0) {
@@ -718,6 +730,10 @@ wgrad_row_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // PDL: barriers, tensor-map prefetch and the TMEM allocation above overlapped the previous kernel's tail; nothing
+  // before this point touched memory another kernel writes.
+  pdl_wait();
+  pdl_trigger();
   const uint32_t tmem_base = tmem_base_slot;
 
   if (num_kb > 0) {
@@ -871,7 +887,7 @@ int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, const OutMaps& to, 
     attr_smem = smem;
   }
   if (CS == 1) {
-    tapgemm_kernel<BN, CS><<<grid, kThreads, smem, st>>>(ta, tb, to, p);
+    mb_launch(tapgemm_kernel<BN, CS>, grid, dim3(kThreads), smem, st, ta, tb, to, p);
   } else {
     grid.x = (grid.x + CS - 1) / CS * CS;  // padding CTAs map to out-of-range tiles: loads zero-fill, stores masked
     cudaLaunchConfig_t cfg = {};
@@ -915,7 +931,7 @@ int launch_halo(const CUtensorMap& ta, const CUtensorMap& tb, const OutMaps& to,
     if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
     attr_smem = smem;
   }
-  tapgemm_halo_kernel<BN><<<grid, kThreads, smem, st>>>(ta, tb, to, p);
+  mb_launch(tapgemm_halo_kernel<BN>, grid, dim3(kThreads), smem, st, ta, tb, to, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "tapgemm_halo launch: %s", cudaGetErrorString(e));
   return MUNIT_OK;
@@ -936,7 +952,7 @@ int launch_wg(const CUtensorMap& ta, const CUtensorMap& tb, WgParams& p, dim3 gr
     if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
     attr_smem = smem;
   }
-  wgrad_kernel<BN><<<grid, kThreads, smem, st>>>(ta, tb, p);
+  mb_launch(wgrad_kernel<BN>, grid, dim3(kThreads), smem, st, ta, tb, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(e));
   return MUNIT_OK;
@@ -958,7 +974,7 @@ int launch_wg_row(const CUtensorMap& ta, const CUtensorMap& tb, WgParams& p, dim
     if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
     attr_smem = smem;
   }
-  wgrad_row_kernel<BN><<<grid, kThreads, smem, st>>>(ta, tb, p);
+  mb_launch(wgrad_row_kernel<BN>, grid, dim3(kThreads), smem, st, ta, tb, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "wgrad_row launch: %s", cudaGetErrorString(e));
   return MUNIT_OK;
