@@ -187,12 +187,21 @@ def profile_tensor_kernels(runner):
         return inner
 
     K.tapgemm, K.wgrad = wrap("tapgemm", orig_t), wrap("wgrad", orig_w)
+    trainer = runner.t
+    two = getattr(trainer, "parallel_streams", False)
     try:
+        # One stream (no cross-stream overlap inside an event pair) and a GPU that is kept ~0.5 s behind the host,
+        # so that every event / kernel is already queued when the device reaches it: the event pairs then bracket
+        # device time only, not the Python time spent building the next launch descriptor.
+        trainer.parallel_streams = False
         runner._prepare_host_state()
+        torch.cuda.synchronize()
+        torch.cuda._sleep(int(0.5 * 1.9e9))
         runner._eager_step()
         runner._advance()
         torch.cuda.synchronize()
     finally:
+        trainer.parallel_streams = two
         K.tapgemm, K.wgrad = orig_t, orig_w
     out = {}
     detail = []

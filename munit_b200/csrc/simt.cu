@@ -1639,16 +1639,24 @@ __global__ void __launch_bounds__(256, 4) norm_fwd_slab_kernel(const NormSlabArg
   float s0[8], s1[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) s0[e] = s1[e] = 0.f;
-#pragma unroll 4
-  for (int pix = p0 + pr; pix < p1; pix += 128) {
-    const uint4 u = *reinterpret_cast<const uint4*>(ybase + (long long)pix * c);
-    slab[(pix - p0) * 2 + half] = u;
-    const F8 x = unpack8(u);
+  constexpr int U = 8;
+  for (int pb = p0 + pr; pb < p1; pb += 128 * U) {
+    uint4 raw[U];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float d = x.v[e] - sh.v[e];
-      s0[e] += d;
-      s1[e] = fmaf(d, d, s1[e]);
+    for (int u = 0; u < U; ++u) raw[u] = *reinterpret_cast<const uint4*>(ybase + (long long)min(pb + u * 128, p1 - 1) * c);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pix = pb + u * 128;
+      if (pix < p1) {
+        slab[(pix - p0) * 2 + half] = raw[u];
+        const F8 x = unpack8(raw[u]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float d = x.v[e] - sh.v[e];
+          s0[e] += d;
+          s1[e] = fmaf(d, d, s1[e]);
+        }
+      }
     }
   }
   slab_block_reduce(s0, s1, wred, cpart);
@@ -1692,28 +1700,42 @@ __global__ void __launch_bounds__(256, 4) norm_fwd_slab_kernel(const NormSlabArg
   }
   const int h = p.h, w = p.w, out_pad = p.out_pad, res_pad = p.res_pad;
   const int hop = h + 2 * out_pad, wop = w + 2 * out_pad;
-#pragma unroll 2
-  for (int pix = p0 + pr; pix < p1; pix += 128) {
-    const int yy = pix / w, x = pix - yy * w;
-    F8 v = unpack8(slab[(pix - p0) * 2 + half]);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float o = fmaf(v.v[e], fa[e], fb[e]);
-      if (p.relu) o = fmaxf(o, 0.f);
-      v.v[e] = o;
-    }
+  for (int pb = p0 + pr; pb < p1; pb += 128 * U) {
+    uint4 rraw[U];
     if (p.res) {
-      const F8 rr = load8(p.res + (((long long)n * (h + 2 * res_pad) + yy + res_pad) * (w + 2 * res_pad) + x + res_pad) * c + ch0);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v.v[e] += rr.v[e];
+      for (int u = 0; u < U; ++u) {
+        const int pix = min(pb + u * 128, p1 - 1);
+        const int yy = pix / w, x = pix - yy * w;
+        rraw[u] = *reinterpret_cast<const uint4*>(p.res + (((long long)n * (h + 2 * res_pad) + yy + res_pad) * (w + 2 * res_pad) + x + res_pad) * c + ch0);
+      }
     }
-    const uint4 packed = pack8(v);
-    int prow[3], pcol[3];
-    const int nr = pad_positions(yy, h, out_pad, prow);
-    const int nc = pad_positions(x, w, out_pad, pcol);
-    for (int i = 0; i < nr; ++i)
-      for (int q = 0; q < nc; ++q)
-        *reinterpret_cast<uint4*>(p.out + (((long long)n * hop + prow[i]) * wop + pcol[q]) * c + ch0) = packed;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pix = pb + u * 128;
+      if (pix < p1) {
+        const int yy = pix / w, x = pix - yy * w;
+        F8 v = unpack8(slab[(pix - p0) * 2 + half]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float o = fmaf(v.v[e], fa[e], fb[e]);
+          if (p.relu) o = fmaxf(o, 0.f);
+          v.v[e] = o;
+        }
+        if (p.res) {
+          const F8 rr = unpack8(rraw[u]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v.v[e] += rr.v[e];
+        }
+        const uint4 packed = pack8(v);
+        int prow[3], pcol[3];
+        const int nr = pad_positions(yy, h, out_pad, prow);
+        const int nc = pad_positions(x, w, out_pad, pcol);
+        for (int i = 0; i < nr; ++i)
+          for (int q = 0; q < nc; ++q)
+            *reinterpret_cast<uint4*>(p.out + (((long long)n * hop + prow[i]) * wop + pcol[q]) * c + ch0) = packed;
+      }
+    }
   }
   slab_cluster_sync();  // no CTA exits while a peer may still read its cpart
 }
@@ -1738,21 +1760,36 @@ __global__ void __launch_bounds__(256, 3) norm_bwd_slab_kernel(const NormSlabArg
   float s0[8], s1[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) s0[e] = s1[e] = 0.f;
-#pragma unroll 2
-  for (int pix = p0 + pr; pix < p1; pix += 128) {
-    const int yy = pix / w, x = pix - yy * w;
-    const F8 g = fold_grad<1>(p.g_out, n, yy, x, ch0 >> 3, h, w, c, p.out_pad);
-    const uint4 u = *reinterpret_cast<const uint4*>(ybase + (long long)pix * c);
-    const uint4 gp = pack8(g);
-    slab[((pix - p0) * 2 + half) * 2] = u;
-    slab[((pix - p0) * 2 + half) * 2 + 1] = gp;
-    const F8 xv = unpack8(u);
+  constexpr int U = 4;
+  const int wop = w + 2 * p.out_pad;
+  const bf16* gbase = p.g_out + (long long)n * (h + 2 * p.out_pad) * wop * c + ch0;
+  for (int pb = p0 + pr; pb < p1; pb += 128 * U) {
+    FoldRaw<1> graw[U];
+    uint4 yraw[U];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float dz = g.v[e];  // sums from the unrounded fold; only the parked copy is bf16
-      if (p.relu && fmaf(xv.v[e], fa.v[e], fb.v[e]) <= 0.f) dz = 0.f;
-      s0[e] += dz;
-      s1[e] = fmaf(dz, xv.v[e] - fm.v[e], s1[e]);
+    for (int u = 0; u < U; ++u) {
+      const int pix = min(pb + u * 128, p1 - 1);
+      const int yy = pix / w, x = pix - yy * w;
+      fold_load<1>(graw[u], gbase, yy, x, wop, c, p.out_pad);
+      yraw[u] = *reinterpret_cast<const uint4*>(ybase + (long long)pix * c);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pix = pb + u * 128;
+      if (pix < p1) {
+        const int yy = pix / w, x = pix - yy * w;
+        const F8 g = fold_finish<1>(graw[u], gbase, yy, x, h, w, c, p.out_pad);
+        slab[((pix - p0) * 2 + half) * 2] = yraw[u];
+        slab[((pix - p0) * 2 + half) * 2 + 1] = pack8(g);
+        const F8 xv = unpack8(yraw[u]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float dz = g.v[e];  // sums from the unrounded fold; only the parked copy is bf16
+          if (p.relu && fmaf(xv.v[e], fa.v[e], fb.v[e]) <= 0.f) dz = 0.f;
+          s0[e] += dz;
+          s1[e] = fmaf(dz, xv.v[e] - fm.v[e], s1[e]);
+        }
+      }
     }
   }
   slab_block_reduce(s0, s1, wred, cpart);
