@@ -427,7 +427,9 @@ def main():
     ap.add_argument("--hd", action="store_true", help="config_HD (512x512, ExtraAdam)")
     ap.add_argument("--optimizer", default="")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--two-streams", type=int, default=1, help="fork the domain-a / domain-b branches onto two streams")
+    ap.add_argument("--two-streams", type=int, default=1,
+                    help="0: one stream; 1: domain-a / domain-b branches on two streams; 2: plus weight gradients on "
+                         "companion streams")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="train", choices=["train", "infer"])
     ap.add_argument("--dump-launches", default="", help="write per-launch tensor-kernel timings (profile pass) to this json")

@@ -16,9 +16,12 @@ from . import _lib, dp
 
 class StepRunner:
     def __init__(self, trainer, cfg: dict, batch: int, hw: int, use_graph: bool = True, world: int = 1,
-                 two_streams: bool = False):
+                 two_streams: int = 0):
+        """two_streams: 0 one stream; 1 the two domains' branches on two streams; 2 additionally every weight
+        gradient on a companion stream, joined before the optimizer step."""
         self.t, self.cfg, self.batch, self.hw = trainer, cfg, batch, hw
         trainer.parallel_streams = bool(two_streams and use_graph)
+        trainer.wgrad_overlap = bool(int(two_streams) >= 2 and use_graph)
         self.use_graph, self.world = use_graph, world
         dev = next(trainer.parameters()).device
         self.dev = dev

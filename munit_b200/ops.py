@@ -20,6 +20,48 @@ import os
 from . import geometry as G
 from . import kernels as K
 
+class _WgradOverlap:
+    """Weight gradients are consumed only by the optimizer step, so they need not sit on the critical chain
+    dgrad -> norm backward -> dgrad ...: when enabled (trainer / StepRunner with two_streams), each wgrad is
+    issued on a companion stream of the stream that runs the backward chain and joined before the optimizer step.
+    The operands are kept alive until the join (the caching allocator would otherwise hand their memory to later
+    kernels of the main stream)."""
+    enabled = False
+    streams: dict = {}   # backward-chain stream id -> its companion stream
+    active: list = []    # companion streams that received work since the last join
+    keep: list = []
+
+
+WG = _WgradOverlap()
+
+
+def wgrad_async(fn, *keep):
+    """Run fn() (wgrad launches that accumulate into a parameter-gradient arena) on the companion stream."""
+    if not WG.enabled:
+        fn()
+        return
+    cur = torch.cuda.current_stream()
+    ws = WG.streams.get(cur.cuda_stream)
+    if ws is None:
+        ws = WG.streams[cur.cuda_stream] = torch.cuda.Stream()
+    ws.wait_stream(cur)
+    with torch.cuda.stream(ws):
+        fn()
+    if ws not in WG.active:
+        WG.active.append(ws)
+    WG.keep.append(keep)
+
+
+def wgrad_join():
+    """Make the current stream wait for every outstanding companion-stream wgrad."""
+    if WG.active:
+        cur = torch.cuda.current_stream()
+        for ws in WG.active:
+            cur.wait_stream(ws)
+    WG.active.clear()
+    WG.keep.clear()
+
+
 # Normalisation statistics in the conv epilogue (no separate pass over the conv output); MUNIT_EPI_STATS=0 restores
 # the stand-alone statistics kernel.
 EPI_STATS = os.environ.get("MUNIT_EPI_STATS", "0") != "0"
@@ -243,14 +285,20 @@ class ConvFn(torch.autograd.Function):
                 gx = dxp
         if ctx.needs_input_grad[1]:
             buf = ctx.wbuf
-            if layer.first:
-                tmp = torch.zeros(layer.cout * layer.k * 64, dtype=torch.float32, device=dy.device)
-                K.wgrad(wg, dy, gemm_in, tmp)
-                tgt = buf if buf is not None else _grad_like_cl(weight)
-                K.gather_add(tmp, layer._idx_inv, _cl_weight(tgt))
+            tgt = buf if buf is not None else _grad_like_cl(weight)
+
+            def run():
+                if layer.first:
+                    tmp = torch.zeros(layer.cout * layer.k * 64, dtype=torch.float32, device=dy.device)
+                    K.wgrad(wg, dy, gemm_in, tmp)
+                    K.gather_add(tmp, layer._idx_inv, _cl_weight(tgt))
+                else:
+                    K.wgrad(wg, dy, gemm_in, _cl_weight(tgt))
+
+            if buf is not None:
+                wgrad_async(run, dy, gemm_in, tgt)
             else:
-                tgt = buf if buf is not None else _grad_like_cl(weight)
-                K.wgrad(wg, dy, gemm_in, _cl_weight(tgt))
+                run()
             gw = None if buf is not None else tgt
         return gx, gw, gb, None, None, None, None, None
 
@@ -290,10 +338,17 @@ class ConvOutFn(torch.autograd.Function):
             gx = torch.empty(n, hp, wp, layer.cin, dtype=torch.bfloat16, device=x.device)
             K.tapgemm(dg, dr, layer.w_dg, gx)
         if ctx.needs_input_grad[1]:
-            tmp = torch.zeros(32 * layer.k * 64, dtype=torch.float32, device=x.device)
-            K.wgrad(wg, dr, x, tmp)
             tgt = ctx.wbuf if ctx.wbuf is not None else _grad_like_cl(weight)
-            K.gather_add(tmp, layer._idx_inv, _cl_weight(tgt))
+
+            def run():
+                tmp = torch.zeros(32 * layer.k * 64, dtype=torch.float32, device=x.device)
+                K.wgrad(wg, dr, x, tmp)
+                K.gather_add(tmp, layer._idx_inv, _cl_weight(tgt))
+
+            if ctx.wbuf is not None:
+                wgrad_async(run, dr, x, tgt)
+            else:
+                run()
             gw = None if ctx.wbuf is not None else tgt
         return gx, gw, gb, None, None
 

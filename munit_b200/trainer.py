@@ -94,6 +94,7 @@ class MUNIT_Trainer(nn.Module):
         # of a step are independent for long stretches; forking them onto two streams gives the captured graph
         # parallel branches, which fills partial waves and hides launch latency of the many small kernels.
         self.parallel_streams = False
+        self.wgrad_overlap = False  # with parallel_streams: weight gradients on companion streams (ops.wgrad_async)
         self._side = None
 
     def _fork_join(self, fa, fb):
@@ -115,6 +116,7 @@ class MUNIT_Trainer(nn.Module):
     def _join_side(self):
         if self.parallel_streams and self._side is not None:
             torch.cuda.current_stream().wait_stream(self._side)
+        ops.wgrad_join()
 
     # ------------------------------------------------------------------ device
     def _apply(self, fn, *a, **k):
@@ -225,6 +227,7 @@ class MUNIT_Trainer(nn.Module):
         if synth:
             raise NotImplementedError("synthetic-pair losses are a 'next' item (SURVEY.md s8(f).4)")
         self.gen_opt.zero_grad()
+        ops.WG.enabled = bool(self.parallel_streams and self.wgrad_overlap)
         s_a, s_b = self._style_noise(x_a, x_b, s_a, s_b)
         cyc = hyperparameters["recon_x_cyc_w"] > 0
         if self.gen_state == 1 and x_a.shape == x_b.shape:
@@ -312,6 +315,7 @@ class MUNIT_Trainer(nn.Module):
     def _dis_backward(self, x_a, x_b, hyperparameters, s_a=None, s_b=None):
         """Losses + gradients of dis_update (everything up to, not including, the optimiser step)."""
         self.dis_opt.zero_grad()
+        ops.WG.enabled = bool(self.parallel_streams and self.wgrad_overlap)
         s_a, s_b = self._style_noise(x_a, x_b, s_a, s_b)
         with torch.no_grad():
             (c_a, s_a_prime), (c_b, s_b_prime) = self._fork_join(lambda: self._enc("a", x_a), lambda: self._enc("b", x_b))

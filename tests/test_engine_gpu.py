@@ -1,4 +1,5 @@
-"""engine.StepRunner: the CUDA-graph replayed step (one stream and two-stream fork/join variants) must reproduce
+"""engine.StepRunner: the CUDA-graph replayed step (one stream, two-stream fork/join, and fork/join with the weight
+gradients on companion streams) must reproduce
 the eager dis_update + gen_update sequence -- same losses and same weights after several steps."""
 import pytest
 import torch
@@ -20,7 +21,7 @@ def _run(mode, steps=3, optimizer="adam"):
     xb = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
     sd = t.style_dim
     styles = [torch.randn(2, sd, 1, 1, generator=g) for _ in range(4)]
-    r = StepRunner(t, cfg, 2, 64, use_graph=mode != "eager", two_streams=mode == "graph2")
+    r = StepRunner(t, cfg, 2, 64, use_graph=mode != "eager", two_streams={"graph2": 1, "graph3": 2}.get(mode, 0))
     r.load_inputs(xa, xb, *styles)
     pre = 2 if optimizer == "extraadam" else 1  # real eager steps before capture (ExtraAdam captures an even/odd pair)
     if mode != "eager":
@@ -40,10 +41,10 @@ def _run(mode, steps=3, optimizer="adam"):
 @pytest.mark.parametrize("optimizer", ["adam", "extraadam"])
 def test_graph_replay_matches_eager(optimizer):
     le, ge, de = _run("eager", optimizer=optimizer)
-    for mode in ("graph", "graph2"):
+    for mode in ("graph", "graph2", "graph3"):  # one stream; two branches; two branches + wgrad companion streams
         lg, gg, dg = _run(mode, optimizer=optimizer)
         for i, ((a, b), (c, d)) in enumerate(zip(le, lg)):
-            tol = 2e-3 * (1 + 2 * i)  # runs drift apart slowly (fp32-atomic noise amplified by bf16 storage)
+            tol = 5e-3 * (1 + 2 * i)  # runs drift apart (fp32-atomic order noise amplified by bf16 storage)
             assert abs(a - c) <= tol * abs(a) and abs(b - d) <= tol * abs(b), (mode, le, lg)
         # weights: split-K wgrad uses fp32 atomics, so two runs differ by ~1e-7 relative in the gradients; bf16
         # storage amplifies that to percent-level gradient differences within a step or two, so
