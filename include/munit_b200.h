@@ -280,6 +280,12 @@ int munit_avgpool3s2_bwd(const float* gy, float* gx, int nc, int h, int w, void*
 int munit_l1_fwd(const float* a, const float* b, float* loss, float scale, int64_t n, void* stream);
 int munit_l1_bwd(const float* a, const float* b, const float* gscale_dev, float scale, float* ga, float* gb, int64_t n,
                  void* stream);
+/* recon_criterion_mask (trainer.py:292-305): loss += scale * sum |(a - b) * keep[n, pixel]| with a, b NCHW fp32
+ * [N][C][HW] and keep [N][HW] fp32 (= 1 - mask, broadcast over channels); backward as munit_l1_bwd times keep. */
+int munit_l1_masked_fwd(const float* a, const float* b, const float* keep, float* loss, float scale, int n, int c,
+                        int hw, void* stream);
+int munit_l1_masked_bwd(const float* a, const float* b, const float* keep, const float* gscale_dev, float scale,
+                        float* ga, float* gb, int n, int c, int hw, void* stream);
 int munit_l1_bf16_fwd(const void* a, const void* b, float* loss, float scale, int64_t n, void* stream);
 int munit_l1_bf16_bwd(const void* a, const void* b, const float* gscale_dev, float scale, void* ga, void* gb,
                       int64_t n, void* stream);

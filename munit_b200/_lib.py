@@ -106,6 +106,8 @@ _SIGS = {
     "munit_avgpool3s2_bwd": ([_vp, _vp, _i, _i, _i, _vp], C.c_int),
     "munit_l1_fwd": ([_vp, _vp, _vp, _f, _i64, _vp], C.c_int),
     "munit_l1_bwd": ([_vp, _vp, _vp, _f, _vp, _vp, _i64, _vp], C.c_int),
+    "munit_l1_masked_fwd": ([_vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp], C.c_int),
+    "munit_l1_masked_bwd": ([_vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _i, _i, _vp], C.c_int),
     "munit_l1_bf16_fwd": ([_vp, _vp, _vp, _f, _i64, _vp], C.c_int),
     "munit_l1_bf16_bwd": ([_vp, _vp, _vp, _f, _vp, _vp, _i64, _vp], C.c_int),
     "munit_adam": ([_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _f, _f, _f, _f, _f, _i, _f, _vp, _vp], C.c_int),

@@ -1474,6 +1474,49 @@ __global__ void l1_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b, 
   }
 }
 
+// Masked L1 (recon_criterion_mask, trainer.py:292-305): images a, b are NCHW fp32, `keep` is a per-pixel weight
+// [N][1][H][W] (= 1 - mask) broadcast over channels; the mean runs over ALL N*C*H*W elements.
+__global__ void l1_masked_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                     const float* __restrict__ keep, float* __restrict__ loss, float scale, long long n,
+                                     int c, int hw) {
+  pdl_wait();
+  pdl_trigger();
+  float acc = 0.f;
+  const long long chw = (long long)c * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long img = i / chw;
+    const int pix = (int)(i % hw);
+    acc += fabsf((a[i] - b[i]) * keep[img * hw + pix]);
+  }
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  __shared__ float sh[32];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t += sh[i];
+    atomicAdd(loss, t * scale);
+  }
+}
+// d|k*(a-b)|/da = sign(k*(a-b)) * k
+__global__ void l1_masked_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                     const float* __restrict__ keep, const float* __restrict__ gscale_dev, float scale,
+                                     float* __restrict__ ga, float* __restrict__ gb, long long n, int c, int hw) {
+  pdl_wait();
+  pdl_trigger();
+  const float g = scale * (gscale_dev ? gscale_dev[0] : 1.f);
+  const long long chw = (long long)c * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long img = i / chw;
+    const int pix = (int)(i % hw);
+    const float k = keep[img * hw + pix];
+    const float d = (a[i] - b[i]) * k;
+    const float s = d > 0.f ? g * k : (d < 0.f ? -g * k : 0.f);
+    if (ga) ga[i] = s;
+    if (gb) gb[i] = -s;
+  }
+}
+
 // ------------------------------------------------------------------ Adam
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, float* __restrict__ p_saved, bf16* __restrict__ p_bf16, long long n,
@@ -2356,6 +2399,20 @@ int munit_l1_bwd(const float* a, const float* b, const float* gscale_dev, float 
                  void* stream) {
   mb_launch(l1_bwd_kernel<float>, dim3(grid_for(n)), dim3(256), 0, ST(stream), a, b, gscale_dev, scale, ga, gb, n);
   MB_CHECK_LAUNCH("l1_bwd");
+  return MUNIT_OK;
+}
+int munit_l1_masked_fwd(const float* a, const float* b, const float* keep, float* loss, float scale, int n, int c,
+                        int hw, void* stream) {
+  const long long total = (long long)n * c * hw;
+  mb_launch(l1_masked_fwd_kernel, dim3(grid_for(total, 256, 592)), dim3(256), 0, ST(stream), a, b, keep, loss, scale, total, c, hw);
+  MB_CHECK_LAUNCH("l1_masked_fwd");
+  return MUNIT_OK;
+}
+int munit_l1_masked_bwd(const float* a, const float* b, const float* keep, const float* gscale_dev, float scale,
+                        float* ga, float* gb, int n, int c, int hw, void* stream) {
+  const long long total = (long long)n * c * hw;
+  mb_launch(l1_masked_bwd_kernel, dim3(grid_for(total)), dim3(256), 0, ST(stream), a, b, keep, gscale_dev, scale, ga, gb, total, c, hw);
+  MB_CHECK_LAUNCH("l1_masked_bwd");
   return MUNIT_OK;
 }
 int munit_l1_bf16_fwd(const void* a, const void* b, float* loss, float scale, int64_t n, void* stream) {

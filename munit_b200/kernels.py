@@ -510,6 +510,20 @@ def l1_bwd(a, b, gscale_dev, scale, ga, gb):
     _count()
 
 
+def l1_masked_fwd(a, b, keep, loss, scale):
+    n, c, h, w = a.shape
+    check(lib.munit_l1_masked_fwd(a.data_ptr(), b.data_ptr(), keep.data_ptr(), loss.data_ptr(), float(scale), n, c, h * w,
+                                  _stream()), "l1_masked_fwd")
+    _count()
+
+
+def l1_masked_bwd(a, b, keep, gscale_dev, scale, ga, gb):
+    n, c, h, w = a.shape
+    check(lib.munit_l1_masked_bwd(a.data_ptr(), b.data_ptr(), keep.data_ptr(), _ptr(gscale_dev), float(scale), _ptr(ga),
+                                  _ptr(gb), n, c, h * w, _stream()), "l1_masked_bwd")
+    _count()
+
+
 def adam(p, g, m, v, p_saved, p_bf16, mode, save, lr, b1, b2, eps, wd, step, gscale=1.0, hyper_dev=None):
     check(lib.munit_adam(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(p_saved), _ptr(p_bf16), p.numel(),
                          mode, int(save), lr, b1, b2, eps, wd, step, gscale, _ptr(hyper_dev), _stream()), "adam")

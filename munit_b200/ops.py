@@ -541,6 +541,29 @@ class AvgPoolFn(torch.autograd.Function):
         return K.avgpool_bwd(gy.contiguous(), gx)
 
 
+class L1MaskedFn(torch.autograd.Function):
+    """recon_criterion_mask (trainer.py:292-305): mean over all elements of |(a - b) * keep|, keep = 1 - mask
+    given per pixel ([N,1,H,W] or [N,H,W]) and broadcast over channels."""
+
+    @staticmethod
+    def forward(ctx, a, b, keep):
+        a, b = a.contiguous(), b.contiguous()
+        n, c, h, w = a.shape
+        keep = keep.to(torch.float32).reshape(n, h * w).contiguous()
+        loss = torch.zeros(1, dtype=torch.float32, device=a.device)
+        K.l1_masked_fwd(a, b, keep, loss, 1.0 / a.numel())
+        ctx.save_for_backward(a, b, keep)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, keep = ctx.saved_tensors
+        ga = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        gb = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        K.l1_masked_bwd(a, b, keep, g.contiguous(), 1.0 / a.numel(), ga, gb)
+        return ga, gb, None
+
+
 class L1Fn(torch.autograd.Function):
     """recon_criterion (trainer.py:279-290): mean |a - b| over interiors.  a, b: fp32 tensors of the same
     shape, or acts with the same interior (halo widths pa, pb)."""

@@ -147,8 +147,9 @@ class MUNIT_Trainer(nn.Module):
 
     def recon_criterion_mask(self, input, target, mask):
         """mean |(input - target) * (1 - mask)| over all elements (trainer.py:292-305)."""
-        keep = 1 - mask
-        return _scalar(ops.L1Fn.apply((input * keep).float(), (target * keep).float(), 0, 0))
+        n, _, h, w = input.shape
+        keep = (1 - mask.to(input.device, torch.float32)).reshape(n, 1, h, w)
+        return _scalar(ops.L1MaskedFn.apply(input.float(), target.float(), keep))
 
     # ------------------------------------------------------------------ generator plumbing
     def _enc(self, which, x):
@@ -224,8 +225,6 @@ class MUNIT_Trainer(nn.Module):
 
     def _gen_backward(self, x_a, x_b, hyperparameters, mask_a=None, mask_b=None, synth=False, s_a=None, s_b=None):
         """Losses + gradients of gen_update (everything up to, not including, the optimiser step)."""
-        if synth:
-            raise NotImplementedError("synthetic-pair losses are a 'next' item (SURVEY.md s8(f).4)")
         self.gen_opt.zero_grad()
         ops.WG.enabled = bool(self.parallel_streams and self.wgrad_overlap)
         s_a, s_b = self._style_noise(x_a, x_b, s_a, s_b)
@@ -270,7 +269,12 @@ class MUNIT_Trainer(nn.Module):
             self.loss_gen_recon_s_b = self.recon_criterion(s_b_recon, s_b_prime)
         self.loss_gen_recon_c_a = self.recon_criterion(c_a_recon, c_a)
         self.loss_gen_recon_c_b = self.recon_criterion(c_b_recon, c_b)
+        # synthetic-pair reconstruction (trainer.py:452-464): pixels identical in the pair must stay aligned
         self.loss_gen_recon_synth = 0
+        if synth:
+            mask_alignment = (torch.sum(torch.abs(x_a - x_b), 1) == 0).unsqueeze(1).to(torch.float32)
+            self.loss_gen_recon_synth = (self.recon_criterion_mask(x_ab, x_b, 1 - mask_alignment)
+                                         + self.recon_criterion_mask(x_ba, x_a, 1 - mask_alignment))
         if self.recon_mask:
             self.loss_gen_cycrecon_x_a = self.recon_criterion_mask(x_aba, x_a, mask_a) if cyc else 0
             self.loss_gen_cycrecon_x_b = self.recon_criterion_mask(x_bab, x_b, mask_b) if cyc else 0
@@ -298,6 +302,7 @@ class MUNIT_Trainer(nn.Module):
             + hyperparameters["recon_c_w"] * self.loss_gen_recon_c_b
             + hyperparameters["recon_x_cyc_w"] * self.loss_gen_cycrecon_x_a
             + hyperparameters["recon_x_cyc_w"] * self.loss_gen_cycrecon_x_b
+            + hyperparameters["recon_synth_w"] * self.loss_gen_recon_synth
         )
         self.loss_gen_total.backward()
         self._join_side()  # backward nodes ran on their forward streams; the optimiser step waits for both

@@ -120,10 +120,14 @@ def nets_fixture():
     print("nets.pt ok")
 
 
-def step_fixture(tag, optimizer, gen_state, guided, hw, b, n_steps):
-    """dis_update + gen_update on the shimmed reference trainer (trainer.py:336-561,1133-1186)."""
+def step_fixture(tag, optimizer, gen_state, guided, hw, b, n_steps, masked_synth=False):
+    """dis_update + gen_update on the shimmed reference trainer (trainer.py:336-561,1133-1186).  masked_synth:
+    recon_mask = 1 with masks and synth=True with recon_synth_w > 0 (trainer.py:452-488)."""
     cfg = O.config_256_core(optimizer=optimizer, gen_state=gen_state, guided=guided,
                             crop_image_height=hw, crop_image_width=hw)
+    if masked_synth:
+        cfg["recon_mask"], cfg["recon_synth_w"] = 1, 5
+        torch.cuda.FloatTensor = torch.FloatTensor  # shim 3: trainer.py:456 casts the alignment mask to a CUDA type
     torch.manual_seed(0)
     t = ref_loader.make_trainer(cfg)
     if gen_state == 1:
@@ -137,6 +141,9 @@ def step_fixture(tag, optimizer, gen_state, guided, hw, b, n_steps):
     t.dis_a.load_state_dict(O.init_state_dict(O.dis_spec(cfg["dis"], 3), 23, "gaussian"))
     t.dis_b.load_state_dict(O.init_state_dict(O.dis_spec(cfg["dis"], 3), 24, "gaussian"))
     x_a, x_b = seeded_images(1234, b, hw, hw)
+    mask_a = mask_b = None
+    if masked_synth:
+        x_a, x_b, mask_a, mask_b = O.synthetic_pair(1234, b, hw)
     torch.manual_seed(99)  # style-code stream for the updates (trainer.py:366-367,1146-1147)
     steps = []
     for it in range(n_steps):
@@ -144,7 +151,10 @@ def step_fixture(tag, optimizer, gen_state, guided, hw, b, n_steps):
         t.update_learning_rate()
         t.dis_update(x_a, x_b, cfg)
         dis_g = {f"a/{n}": summarize(p.grad, 16) for n, p in t.dis_a.named_parameters()}
-        t.gen_update(x_a, x_b, cfg)
+        if masked_synth:
+            t.gen_update(x_a, x_b, cfg, mask_a, mask_b, synth=True)
+        else:
+            t.gen_update(x_a, x_b, cfg)
         rec = {k: float(getattr(t, k)) for k in dir(t) if k.startswith("loss_") and torch.is_tensor(getattr(t, k))}
         gens = {"": t.gen} if gen_state == 1 else {"a": t.gen_a, "b": t.gen_b}
         gen_g = {f"{gn}/{n}": summarize(p.grad, 16) for gn, g in gens.items() for n, p in g.named_parameters()}
@@ -153,7 +163,8 @@ def step_fixture(tag, optimizer, gen_state, guided, hw, b, n_steps):
         dis_w.update({f"b/{n}": summarize(p.data, 16) for n, p in t.dis_b.named_parameters()})
         steps.append(dict(losses=rec, dis_grads=dis_g, gen_grads=gen_g, gen_w=gen_w, dis_w=dis_w))
         print(tag, it, {k: round(v, 5) for k, v in rec.items()})
-    fx = dict(cfg=cfg, seeds=dict(gen=21, gen_b=22, dis_a=23, dis_b=24, img=1234, style=99), hw=hw, b=b, steps=steps)
+    fx = dict(cfg=cfg, seeds=dict(gen=21, gen_b=22, dis_a=23, dis_b=24, img=1234, style=99), hw=hw, b=b, steps=steps,
+              masked_synth=masked_synth)
     torch.save(fx, os.path.join(OUT, f"step_{tag}.pt"))
 
 
@@ -190,3 +201,4 @@ if __name__ == "__main__":
     nets_fixture()
     step_fixture("g1_guided_adam", "adam", 1, 1, 64, 2, 2)
     step_fixture("g0_sampled_extraadam", "extraadam", 0, 0, 64, 1, 2)
+    step_fixture("g1_masked_synth_adam", "adam", 1, 1, 64, 2, 1, masked_synth=True)

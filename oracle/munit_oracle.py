@@ -411,6 +411,19 @@ def l1(a, b):
     return torch.mean(torch.abs(a - b))
 
 
+def synthetic_pair(seed, b, hw):
+    """Seeded synthetic pair for the masked / synthetic-pair losses: x_b equals x_a except inside a box (so the
+    alignment mask of trainer.py:455 is non-trivial), plus two binary masks [b,1,hw,hw]."""
+    g = torch.Generator().manual_seed(seed)
+    x_a = torch.rand(b, 3, hw, hw, generator=g) * 2 - 1
+    x_b = x_a.clone()
+    x_b[:, :, hw // 4: hw // 2 + 5, hw // 8: hw // 2] = torch.rand(b, 3, hw // 4 + 5, hw // 2 - hw // 8, generator=g) * 2 - 1
+    mask_a = (torch.rand(b, 1, hw, hw, generator=g) > 0.6).float()
+    mask_b = torch.zeros(b, 1, hw, hw)
+    mask_b[:, :, hw // 3:, : hw // 2] = 1.0
+    return x_a, x_b, mask_a, mask_b
+
+
 def l1_masked(a, b, mask):
     """recon_criterion_mask trainer.py:292-305 (mean over *all* elements)."""
     return torch.mean(torch.abs((a - b) * (1 - mask)))
@@ -549,7 +562,9 @@ class OracleTrainer:
         self.dis_grads = grads
         return total.detach()
 
-    def gen_update(self, x_a, x_b, s_a=None, s_b=None):
+    def gen_update(self, x_a, x_b, s_a=None, s_b=None, mask_a=None, mask_b=None, synth=False):
+        """trainer.py:336-561 incl. the masked cycle loss (recon_mask == 1, trainer.py:466-488) and the
+        synthetic-pair reconstruction loss (synth=True, trainer.py:452-464)."""
         cfg, B = self.cfg, x_a.shape[0]
         if s_a is None:  # trainer.py:366-367
             s_a = torch.randn(B, self.style_dim, 1, 1)
@@ -573,8 +588,17 @@ class OracleTrainer:
         else:
             L["loss_gen_recon_s_a"], L["loss_gen_recon_s_b"] = l1(s_a_recon, s_a_p), l1(s_b_recon, s_b_p)
         L["loss_gen_recon_c_a"], L["loss_gen_recon_c_b"] = l1(c_a_recon, c_a), l1(c_b_recon, c_b)
-        L["loss_gen_cycrecon_x_a"] = l1(x_aba, x_a) if cyc else 0
-        L["loss_gen_cycrecon_x_b"] = l1(x_bab, x_b) if cyc else 0
+        if cfg.get("recon_mask", 0) == 1:
+            L["loss_gen_cycrecon_x_a"] = l1_masked(x_aba, x_a, mask_a) if cyc else 0
+            L["loss_gen_cycrecon_x_b"] = l1_masked(x_bab, x_b, mask_b) if cyc else 0
+        else:
+            L["loss_gen_cycrecon_x_a"] = l1(x_aba, x_a) if cyc else 0
+            L["loss_gen_cycrecon_x_b"] = l1(x_bab, x_b) if cyc else 0
+        L["loss_gen_recon_synth"] = 0
+        if synth:
+            mask_alignment = (torch.sum(torch.abs(x_a - x_b), 1) == 0).unsqueeze(1).float()
+            L["loss_gen_recon_synth"] = (l1_masked(x_ab, x_b, 1 - mask_alignment)
+                                         + l1_masked(x_ba, x_a, 1 - mask_alignment))
         dp = cfg["dis"]
         L["loss_gen_adv_a"] = calc_gen_loss(self.dis_a, dp, x_ba)
         L["loss_gen_adv_b"] = calc_gen_loss(self.dis_b, dp, x_ab)
@@ -582,7 +606,8 @@ class OracleTrainer:
                  + cfg["recon_x_w"] * (L["loss_gen_recon_x_a"] + L["loss_gen_recon_x_b"])
                  + cfg["recon_s_w"] * (L["loss_gen_recon_s_a"] + L["loss_gen_recon_s_b"])
                  + cfg["recon_c_w"] * (L["loss_gen_recon_c_a"] + L["loss_gen_recon_c_b"])
-                 + cfg["recon_x_cyc_w"] * (L["loss_gen_cycrecon_x_a"] + L["loss_gen_cycrecon_x_b"]))
+                 + cfg["recon_x_cyc_w"] * (L["loss_gen_cycrecon_x_a"] + L["loss_gen_cycrecon_x_b"])
+                 + cfg.get("recon_synth_w", 0) * L["loss_gen_recon_synth"])
         grads = self._grads(total, self.gen_params)
         self.gen_opt.apply(grads, self.iterations)
         self.losses.update({k: float(v) for k, v in L.items()})

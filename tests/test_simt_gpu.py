@@ -276,3 +276,23 @@ def test_adam_modes(golden):
                 K.adam(p, g.cuda(), m, v, saved, pb, 2, False, 1e-3, 0.5, 0.999, 1e-8, 1e-4, it + 1)
             assert torch.allclose(p.cpu(), fx[name][it], rtol=1e-5, atol=1e-6), (name, it)
             assert torch.equal(pb.float(), bf16_round(p))
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 16, 24), (3, 3, 64, 64)])
+def test_l1_masked(shape):
+    """recon_criterion_mask (trainer.py:292-305): value and both gradients against the oracle expression."""
+    from munit_b200 import ops
+
+    n, c, h, w = shape
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randn(n, c, h, w, device="cuda", generator=g, requires_grad=True)
+    b = torch.randn(n, c, h, w, device="cuda", generator=g, requires_grad=True)
+    mask = (torch.rand(n, 1, h, w, device="cuda", generator=g) > 0.5).float()
+    ref = O.l1_masked(a, b, mask)
+    ref.backward()
+    ga_ref, gb_ref = a.grad.clone(), b.grad.clone()
+    a.grad = b.grad = None
+    out = ops.L1MaskedFn.apply(a, b, 1 - mask)
+    (out * 1.0).sum().backward()
+    assert abs(float(out) - float(ref)) <= 1e-5 * abs(float(ref))
+    assert torch.allclose(a.grad, ga_ref, atol=1e-9) and torch.allclose(b.grad, gb_ref, atol=1e-9)

@@ -35,12 +35,17 @@ def _build(cfg, sd):
     return t.cuda(), O.OracleTrainer(cfg, gsd, da, db)
 
 
-@pytest.mark.parametrize("tag", ["g1_guided_adam", "g0_sampled_extraadam"])
+@pytest.mark.parametrize("tag", ["g1_guided_adam", "g0_sampled_extraadam", "g1_masked_synth_adam"])
 def test_training_steps_vs_reference(golden, tag):
     fx = golden(f"step_{tag}.pt")
     cfg, sd = fx["cfg"], fx["seeds"]
     t, orc = _build(cfg, sd)
     x_a, x_b = _images(sd["img"], fx["b"], fx["hw"])
+    extra, gpu_extra = {}, {}
+    if fx.get("masked_synth"):  # masked cycle loss + synthetic-pair loss (trainer.py:452-488)
+        x_a, x_b, mask_a, mask_b = O.synthetic_pair(sd["img"], fx["b"], fx["hw"])
+        extra = dict(mask_a=mask_a, mask_b=mask_b, synth=True)
+        gpu_extra = dict(mask_a=mask_a.cuda(), mask_b=mask_b.cuda(), synth=True)
     xa, xb = x_a.cuda(), x_b.cuda()
     torch.manual_seed(sd["style"])
     worst = {}
@@ -50,11 +55,11 @@ def test_training_steps_vs_reference(golden, tag):
         t.update_learning_rate()
         rng = torch.get_rng_state()
         t.dis_update(xa, xb, cfg)
-        t.gen_update(xa, xb, cfg)
+        t.gen_update(xa, xb, cfg, **gpu_extra)
         rng_after = torch.get_rng_state()
         torch.set_rng_state(rng)  # the oracle consumes the same host style-code stream
         orc.dis_update(x_a, x_b)
-        orc.gen_update(x_a, x_b)
+        orc.gen_update(x_a, x_b, **extra)
         assert torch.equal(torch.get_rng_state(), rng_after), "style-code RNG consumption differs from the reference"
         for k, v in ref["losses"].items():
             ours = float(getattr(t, k))
