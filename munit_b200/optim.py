@@ -128,27 +128,38 @@ class FlatAdam(Optimizer):
         return loss
 
     # ------------------------------------------------------------------ checkpoint contract (trainer.save/resume)
+    def _state_view(self, arena, p, off):
+        """The slice of `arena` that belongs to parameter p, shaped and strided like p itself (the arenas keep
+        conv weights in channels_last order, so a flat reshape would scramble them)."""
+        return arena.as_strided(p.shape, p.stride(), off)
+
     def state_dict(self):
-        """Same layout as torch.optim.Adam.state_dict(): per-parameter step / exp_avg / exp_avg_sq."""
+        """Interchangeable with torch.optim.Adam.state_dict() (what the reference writes to optimizer.pt,
+        trainer.py:1401-1429): per-parameter step / exp_avg / exp_avg_sq with the parameter's logical shape."""
         if not self._arena_built:
             self.build_arena()
         state = {}
         for i, (p, (off, n)) in enumerate(zip(self._all_params(), self.slices)):
             state[i] = dict(step=torch.tensor(float(self.step_count)),
-                            exp_avg=self.m_arena[off:off + n].clone(), exp_avg_sq=self.v_arena[off:off + n].clone())
+                            exp_avg=self._state_view(self.m_arena, p, off).clone(),
+                            exp_avg_sq=self._state_view(self.v_arena, p, off).clone())
         groups = [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]
         groups[0]["params"] = list(range(len(self.slices)))
         return dict(state=state, param_groups=groups)
 
     def load_state_dict(self, sd):
+        """Accepts this class's state_dict() and torch.optim.Adam's (a reference optimizer.pt)."""
         if not self._arena_built:
             self.build_arena()
-        for i, (off, n) in enumerate(self.slices):
+        for i, (p, (off, n)) in enumerate(zip(self._all_params(), self.slices)):
             st = sd["state"].get(i)
             if st is None:
                 continue
-            self.m_arena[off:off + n].copy_(st["exp_avg"].reshape(-1))
-            self.v_arena[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+            for arena, key in ((self.m_arena, "exp_avg"), (self.v_arena, "exp_avg_sq")):
+                src = st[key]
+                if src.numel() != n:
+                    raise ValueError(f"optimizer state {key}[{i}] has {src.numel()} elements, parameter has {n}")
+                self._state_view(arena, p, off).copy_(src.reshape(p.shape) if src.dim() != p.dim() else src)
             self.step_count = int(float(st["step"]))
         for g, sg in zip(self.param_groups, sd["param_groups"]):
             for k in ("lr", "betas", "eps", "weight_decay"):

@@ -124,3 +124,54 @@ def test_state_dict_roundtrip_and_checkpoint(tmp_path):
         y1 = t.forward(xa, xb)[0]
         y2 = t2.forward(xa, xb)[0]
     assert torch.equal(y1, y2)
+
+
+def test_optimizer_state_interchanges_with_torch_adam():
+    """optimizer.pt written by the reference holds torch.optim.Adam state (trainer.py:1401-1429); FlatAdam keeps
+    conv weights channels_last inside flat arenas, so its state_dict / load_state_dict must translate by logical
+    shape, both ways, and a step taken after loading must match torch's."""
+    from munit_b200.optim import FlatAdam
+
+    torch.manual_seed(0)
+    shapes = [(8, 4, 3, 3), (8,), (5, 7)]
+
+    def params():
+        g = torch.Generator().manual_seed(1)
+        ps = [torch.nn.Parameter(torch.randn(*s, generator=g).cuda()) for s in shapes]
+        ps[0].data = ps[0].data.contiguous(memory_format=torch.channels_last)
+        return ps
+
+    kw = dict(lr=1e-3, betas=(0.5, 0.999), weight_decay=1e-4)
+    gr = torch.Generator().manual_seed(2)
+    grads = [[torch.randn(*s, generator=gr).cuda() for s in shapes] for _ in range(3)]
+    # torch: two steps, checkpoint, third step
+    pt = params()
+    ot = torch.optim.Adam(pt, **kw)
+    for k in range(2):
+        for p, g in zip(pt, grads[k]):
+            p.grad = g.clone()
+        ot.step()
+    sd_torch = ot.state_dict()
+    # ours: start from torch's weights + state, take the third step
+    po = params()
+    for p, q in zip(po, pt):
+        p.data.copy_(q.data)
+    oo = FlatAdam(po, **kw)
+    oo.load_state_dict(sd_torch)
+    for p, g in zip(po, grads[2]):
+        p.grad.copy_(g)
+    oo.step()
+    for p, g in zip(pt, grads[2]):
+        p.grad = g.clone()
+    ot.step()
+    for p, q in zip(po, pt):
+        assert torch.allclose(p.data, q.data, rtol=1e-5, atol=1e-7)
+    # and back: torch loads our state_dict
+    sd_ours = oo.state_dict()
+    for i, s in enumerate(shapes):
+        assert tuple(sd_ours["state"][i]["exp_avg"].shape) == s
+        assert torch.allclose(sd_ours["state"][i]["exp_avg"], ot.state_dict()["state"][i]["exp_avg"], rtol=1e-5, atol=1e-8)
+        v_o, v_t = sd_ours["state"][i]["exp_avg_sq"], ot.state_dict()["state"][i]["exp_avg_sq"]
+        assert float(((v_o - v_t).abs() / (v_t.abs() + 1e-12)).max()) < 1e-4, float(((v_o - v_t).abs() / (v_t.abs() + 1e-12)).max())
+    ot2 = torch.optim.Adam(params(), **kw)
+    ot2.load_state_dict(sd_ours)
