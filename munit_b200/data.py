@@ -1,0 +1,158 @@
+"""Host-side input pipeline for scripts/train.py (reference: scripts/data.py:9-154, scripts/utils.py:50-250,
+458-636).  Decoding, resize, crop and flip stay on the host workers exactly as in the reference (PIL +
+torchvision transforms, same order: flip -> resize -> random crop -> to-tensor -> normalise to [-1, 1]); the
+trainer consumes the NCHW fp32 batches the reference consumes, so nothing downstream changes."""
+from __future__ import annotations
+
+import os
+import random
+from typing import Callable, List, Optional, Sequence
+
+import torch
+from torch.utils.data import DataLoader, Dataset
+
+IMG_EXTENSIONS = (".jpg", ".jpeg", ".png", ".ppm", ".bmp")
+
+
+def default_loader(path: str):
+    from PIL import Image
+
+    return Image.open(path).convert("RGB")
+
+
+def read_list(flist: str) -> List[str]:
+    """One path per line (blank lines ignored) -- data.py:13-23."""
+    with open(flist, "r") as f:
+        return [ln.strip() for ln in f if ln.strip()]
+
+
+def list_images(folder: str) -> List[str]:
+    """Every image under `folder`, sorted, recursively -- data.py:113-123."""
+    out = []
+    for root, _, names in sorted(os.walk(folder)):
+        out += [os.path.join(root, n) for n in sorted(names) if n.lower().endswith(IMG_EXTENSIONS)]
+    return out
+
+
+class ImageFilelist(Dataset):
+    """data.py:26-49: `flist` is a list file (or a python list) of paths relative to `root`."""
+
+    def __init__(self, root: str, flist, transform: Optional[Callable] = None, loader: Callable = default_loader):
+        self.root, self.transform, self.loader = root, transform, loader
+        self.imlist = read_list(flist) if isinstance(flist, str) else list(flist)
+
+    def __getitem__(self, index):
+        img = self.loader(os.path.join(self.root, self.imlist[index]))
+        return self.transform(img) if self.transform is not None else img
+
+    def __len__(self):
+        return len(self.imlist)
+
+
+class ImageFolder(Dataset):
+    """data.py:126-154."""
+
+    def __init__(self, root: str, transform: Optional[Callable] = None, return_paths: bool = False,
+                 loader: Callable = default_loader):
+        self.imgs = list_images(root)
+        if not self.imgs:
+            raise RuntimeError("Found 0 images in: " + root + "\nSupported image extensions are: " + ",".join(IMG_EXTENSIONS))
+        self.root, self.transform, self.return_paths, self.loader = root, transform, return_paths, loader
+
+    def __getitem__(self, index):
+        path = self.imgs[index]
+        img = self.loader(path)
+        if self.transform is not None:
+            img = self.transform(img)
+        return (img, path) if self.return_paths else img
+
+    def __len__(self):
+        return len(self.imgs)
+
+
+def image_transform(train: bool, new_size: Optional[int], height: int, width: int, crop: bool):
+    """utils.py:218-240 / 706-728."""
+    from torchvision import transforms
+
+    steps = []
+    if train:
+        steps.append(transforms.RandomHorizontalFlip())
+    if new_size is not None:
+        steps.append(transforms.Resize(new_size))
+    if crop:
+        steps.append(transforms.RandomCrop((height, width)))
+    steps += [transforms.ToTensor(), transforms.Normalize((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))]
+    return transforms.Compose(steps)
+
+
+def _loader(dataset, batch_size, train, num_workers):
+    return DataLoader(dataset=dataset, batch_size=batch_size, shuffle=train, drop_last=True, num_workers=num_workers,
+                      pin_memory=True, persistent_workers=num_workers > 0)
+
+
+def get_data_loader_list(root, file_list, batch_size, train, new_size=None, height=256, width=256, num_workers=4,
+                         crop=True):
+    return _loader(ImageFilelist(root, file_list, image_transform(train, new_size, height, width, crop)), batch_size,
+                   train, num_workers)
+
+
+def get_data_loader_folder(input_folder, batch_size, train, new_size=None, height=256, width=256, num_workers=4,
+                           crop=True):
+    return _loader(ImageFolder(input_folder, image_transform(train, new_size, height, width, crop)), batch_size, train,
+                   num_workers)
+
+
+def get_all_data_loaders(conf: dict):
+    """train A, train B, test A, test B (utils.py:50-156): `data_root` with trainA/testA/trainB/testB folders, or
+    per-split folder + list-file keys."""
+    bs, nw = conf["batch_size"], conf["num_workers"]
+    size_a = size_b = conf.get("new_size")
+    if "new_size" not in conf:
+        size_a, size_b = conf["new_size_a"], conf["new_size_b"]
+    h, w = conf["crop_image_height"], conf["crop_image_width"]
+    if "data_root" in conf:
+        mk = lambda split, train, size: get_data_loader_folder(  # noqa: E731
+            os.path.join(conf["data_root"], split), bs, train, size, h if train else size, w if train else size, nw, True)
+        return mk("trainA", True, size_a), mk("trainB", True, size_b), mk("testA", False, size_a), mk("testB", False, size_b)
+    mk = lambda dom, split, train, size: get_data_loader_list(  # noqa: E731
+        conf[f"data_folder_{split}_{dom}"], conf[f"data_list_{split}_{dom}"], bs, train, size, h if train else size,
+        w if train else size, nw, True)
+    return mk("a", "train", True, size_a), mk("b", "train", True, size_b), mk("a", "test", False, size_a), mk("b", "test", False, size_b)
+
+
+class PairedWithMask(Dataset):
+    """Synthetic pairs (utils.py:458-581 without the segmentation maps): image A, image B and a binary mask that
+    share ONE random flip / resize / crop, so identical pixels stay aligned (trainer.py:452-464 relies on it)."""
+
+    def __init__(self, list_a: Sequence[str], list_b: Sequence[str], list_mask: Sequence[str], new_size, height, width,
+                 train: bool = True, loader: Callable = default_loader):
+        assert len(list_a) == len(list_b) == len(list_mask)
+        self.a, self.b, self.m = list(list_a), list(list_b), list(list_mask)
+        self.new_size, self.h, self.w, self.train, self.loader = new_size, height, width, train, loader
+
+    def __len__(self):
+        return len(self.a)
+
+    def __getitem__(self, i):
+        import torchvision.transforms.functional as TF
+        from PIL import Image
+
+        a, b = self.loader(self.a[i]), self.loader(self.b[i])
+        m = Image.open(self.m[i]).convert("L")
+        if self.train and random.random() > 0.5:
+            a, b, m = TF.hflip(a), TF.hflip(b), TF.hflip(m)
+        if self.new_size is not None:
+            a, b = TF.resize(a, self.new_size), TF.resize(b, self.new_size)
+            m = TF.resize(m, self.new_size, interpolation=TF.InterpolationMode.NEAREST)
+        wd, ht = a.size
+        top = random.randint(0, max(ht - self.h, 0)) if self.train else max(ht - self.h, 0) // 2
+        left = random.randint(0, max(wd - self.w, 0)) if self.train else max(wd - self.w, 0) // 2
+        a, b, m = (TF.crop(t, top, left, self.h, self.w) for t in (a, b, m))
+        norm = lambda t: TF.normalize(TF.to_tensor(t), (0.5, 0.5, 0.5), (0.5, 0.5, 0.5))  # noqa: E731
+        return norm(a), norm(b), (TF.to_tensor(m) > 0.5).float()
+
+
+def get_synthetic_data_loader(list_a, list_b, list_mask, batch_size, train, new_size=None, height=256, width=256,
+                              num_workers=4):
+    ds = PairedWithMask(read_list(list_a), read_list(list_b), read_list(list_mask), new_size, height, width, train)
+    return _loader(ds, batch_size, train, num_workers)

@@ -94,3 +94,49 @@ def get_model_list(dirname, key):
         return None
     gen_models.sort()
     return gen_models[-1]
+
+
+# ------------------------------------------------------------------ train.py helpers (utils.py:768-835,1118-1128)
+def prepare_sub_folder(output_directory):
+    """images/ and checkpoints/ under the run directory; returns (checkpoint_directory, image_directory)."""
+    image_directory = os.path.join(output_directory, "images")
+    checkpoint_directory = os.path.join(output_directory, "checkpoints")
+    for d in (image_directory, checkpoint_directory):
+        if not os.path.exists(d):
+            print("Creating directory: {}".format(d))
+            os.makedirs(d)
+    return checkpoint_directory, image_directory
+
+
+def _write_images(image_outputs, display_image_num, file_name):
+    import torchvision.utils as vutils
+
+    rows = [im.expand(-1, 3, -1, -1)[:display_image_num] for im in image_outputs]  # grey -> 3 channels
+    grid = vutils.make_grid(torch.cat(rows, 0).data, nrow=display_image_num, padding=0, normalize=True)
+    vutils.save_image(grid, file_name, nrow=1)
+
+
+def write_2images(image_outputs, display_image_num, image_directory, postfix, comet_exp=None):
+    """First half of `image_outputs` is the a->b strip, second half b->a (trainer.sample order)."""
+    n = len(image_outputs)
+    names = ["%s/gen_a2b_%s.jpg" % (image_directory, postfix), "%s/gen_b2a_%s.jpg" % (image_directory, postfix)]
+    _write_images(image_outputs[0:n // 2], display_image_num, names[0])
+    _write_images(image_outputs[n // 2:n], display_image_num, names[1])
+    if comet_exp is not None:
+        for nm in names:
+            comet_exp.log_image(nm)
+
+
+class Timer:
+    def __init__(self, msg):
+        self.msg, self.start_time = msg, None
+
+    def __enter__(self):
+        import time
+
+        self.start_time = time.time()
+
+    def __exit__(self, exc_type, exc_value, exc_tb):
+        import time
+
+        print(self.msg % (time.time() - self.start_time))
