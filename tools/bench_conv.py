@@ -28,8 +28,10 @@ def run_rect(name, iters=20, nbuf=4):
     xs = [torch.randn(n, hp, wp, cin, device="cuda").to(torch.bfloat16) for _ in range(nbuf)]
     wf = (torch.randn(cout, kh * kw * cin, device="cuda") * 0.05).to(torch.bfloat16)
     ys = [torch.empty(n, ho, wo, cout, dtype=torch.bfloat16, device="cuda") for _ in range(nbuf)]
-    fwd = G.plan_fwd(n, hp, wp, cin, kh, kw, s, 1, cout, (ho * wo * cout, wo * cout, cout, 0, 0))
-    dg = G.plan_dgrad(n, hp, wp, cin, kh, kw, s, 1, cout)
+    halo = int(os.environ.get("HALO", 0))
+    fwd = G.plan_fwd(n, hp, wp, cin, kh, kw, s, 1, cout, (ho * wo * cout, wo * cout, cout, 0, 0), halo=halo)
+    dg = G.plan_dgrad(n, hp, wp, cin, kh, kw, s, 1, cout, halo=halo if cout >= 64 else 0)
+    print("halo fwd/dgrad:", fwd.halo, dg.halo, "tile", (fwd.tw, fwd.th, fwd.tn))
     wd = (torch.randn(cin, dg.b_k, device="cuda") * 0.05).to(torch.bfloat16)
     dxs = [torch.empty(n, hp, wp, cin, dtype=torch.bfloat16, device="cuda") for _ in range(nbuf)]
     wg = G.plan_wgrad(n, hp, wp, cin, kh, kw, s, 1, cout, cout, kh * kw * cin, cin, 1)
