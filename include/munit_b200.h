@@ -88,6 +88,11 @@ typedef struct {
                       stats_kind 2: stats[((n*4T + tile*4 + q)*(C/64) + c/64)*2 + {0,1}]             (channel-reduced)
                       -> munit_norm_finalize_parts. */
   int32_t stats_kind;
+  int32_t ksplit;  /* > 1: split the (tap, chunk) loop over ksplit CTAs per tile; each adds its fp32 partial tile to
+                      `scratch` (red.global.add) and nothing is written to `out`, bias / act are not applied:
+                      follow with munit_splitk_finish.  For layers with too few output tiles to fill the GPU
+                      (the deep discriminator layers).  Excludes halo, stats and cluster. */
+  float* scratch;  /* zero-initialised fp32 buffer with exactly the element geometry of `out` (same o_s* strides) */
 } munit_tapgemm_desc;
 
 int munit_tapgemm(const munit_tapgemm_desc* d, void* stream);
@@ -130,6 +135,10 @@ typedef struct {
                        row), loads dY and one widened X box per 8x8 pixel block and feeds each tap through a shifted
                        UMMA descriptor into its own TMEM accumulator (row_taps * bn <= 512, bn <= 128) */
 } munit_wgrad_desc;
+
+/* out[i] = bf16(act(scratch[i] + bias[i % c])) over n contiguous elements (c = innermost channel extent, bias may
+ * be NULL): the second half of a split-K munit_tapgemm. */
+int munit_splitk_finish(const float* scratch, const float* bias, int act, void* out, int64_t n, int c, void* stream);
 
 int munit_wgrad(const munit_wgrad_desc* d, void* stream);
 

@@ -31,7 +31,7 @@ class TapGemmDesc(C.Structure):
         ("out", C.c_void_p), ("o_sn", C.c_int64), ("o_sy", C.c_int64), ("o_sx", C.c_int64),
         ("o_ymul", C.c_int32), ("o_xmul", C.c_int32), ("n_store", C.c_int32),
         ("bias", C.c_void_p), ("act", C.c_int32), ("stages", C.c_int32), ("cluster", C.c_int32), ("halo", C.c_int32),
-        ("stats", C.c_void_p), ("stats_kind", C.c_int32),
+        ("stats", C.c_void_p), ("stats_kind", C.c_int32), ("ksplit", C.c_int32), ("scratch", C.c_void_p),
     ]
 
 
@@ -64,6 +64,7 @@ _SIGS = {
     "munit_init": ([], C.c_int),
     "munit_error_flag_ptr": ([C.POINTER(C.c_void_p)], C.c_int),
     "munit_tapgemm": ([C.POINTER(TapGemmDesc), _vp], C.c_int),
+    "munit_splitk_finish": ([_vp, _vp, _i, _vp, _i64, _i, _vp], C.c_int),
     "munit_wgrad": ([C.POINTER(WgradDesc), _vp], C.c_int),
     "munit_image_to_act": ([_vp, _vp, _i, _i, _i, _i, _i, _i, _vp], C.c_int),
     "munit_image_to_kwexp": ([_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp], C.c_int),

@@ -1474,6 +1474,25 @@ __global__ void l1_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b, 
   }
 }
 
+// Second half of a split-K tap-GEMM: fp32 partial sums -> (+bias) -> activation -> bf16, 8 elements per thread.
+__global__ void splitk_finish_kernel(const float* __restrict__ scratch, const float* __restrict__ bias, int act,
+                                     bf16* __restrict__ out, long long n8, int c) {
+  pdl_wait();
+  pdl_trigger();
+  const float slope = act == MUNIT_ACT_RELU ? 0.f : (act == MUNIT_ACT_LRELU ? 0.2f : 1.f);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    F8 v = loadf8(scratch + i * 8);
+    if (bias) {
+      const F8 b = loadf8(bias + (int)((i * 8) % c));
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v.v[e] += b.v[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v.v[e] = act == MUNIT_ACT_TANH ? tanhf(v.v[e]) : fmaxf(v.v[e], slope * v.v[e]);
+    store8(out + i * 8, v);
+  }
+}
+
 // Masked L1 (recon_criterion_mask, trainer.py:292-305): images a, b are NCHW fp32, `keep` is a per-pixel weight
 // [N][1][H][W] (= 1 - mask) broadcast over channels; the mean runs over ALL N*C*H*W elements.
 __global__ void l1_masked_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
@@ -2401,6 +2420,13 @@ int munit_l1_bwd(const float* a, const float* b, const float* gscale_dev, float 
   MB_CHECK_LAUNCH("l1_bwd");
   return MUNIT_OK;
 }
+int munit_splitk_finish(const float* scratch, const float* bias, int act, void* out, int64_t n, int c, void* stream) {
+  if (n % 8 || c % 8) return mb_fail(MUNIT_ERR_ARG, "splitk_finish: n and c must be multiples of 8");
+  mb_launch(splitk_finish_kernel, dim3(grid_for(n / 8)), dim3(256), 0, ST(stream), scratch, bias, act, BF(out), (long long)(n / 8), c);
+  MB_CHECK_LAUNCH("splitk_finish");
+  return MUNIT_OK;
+}
+
 int munit_l1_masked_fwd(const float* a, const float* b, const float* keep, float* loss, float scale, int n, int c,
                         int hw, void* stream) {
   const long long total = (long long)n * c * hw;

@@ -42,6 +42,10 @@ struct FwdParams {
   // normalisation statistics of the stored tile, written by the epilogue (munit_tapgemm_desc.stats)
   float* stats;
   int stats_kind, stats_c;
+  // split-K (munit_tapgemm_desc.ksplit > 1): blockIdx.z = phase * ksplit + slice; each CTA accumulates its slice of
+  // the (tap, chunk) loop and adds its fp32 partial tile into `scratch`, which has the geometry of `out`
+  float* scratch;
+  int ksplit;
   int* err;
   int tap_off[MUNIT_MAX_TAPS][5];
 };
@@ -150,8 +154,12 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int tnn = t / p.tiles_y;
   const int x0 = tx * p.tw, y0 = ty * p.th, n0 = tnn * p.tn;
   const int n_tile = blockIdx.y;
-  const int phase_id = blockIdx.z;
-  const int num_kb = p.num_taps * p.chunks;
+  const int phase_id = blockIdx.z / p.ksplit;
+  const int k_slice = blockIdx.z - phase_id * p.ksplit;
+  const int total_kb = p.num_taps * p.chunks;
+  const int kb_begin = (int)(((long long)total_kb * k_slice) / p.ksplit);
+  const int kb_end = (int)(((long long)total_kb * (k_slice + 1)) / p.ksplit);
+  const int num_kb = kb_end - kb_begin;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_a);
@@ -189,7 +197,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int bk0 = p.b_k0[phase_id];
       int stage = 0;
       uint32_t ph = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
         const int tap = kb / p.chunks;
         const int kc = kb - tap * p.chunks;
         mbar_wait(smem_u32(&empty_bar[stage]), ph ^ 1, dead, p.err);
@@ -253,7 +261,33 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tc_fence_after();
     const float slope = act_slope(p.act);
     const bool is_tanh = p.act == MUNIT_ACT_TANH;
-    if constexpr (BN >= 64) {
+    if (p.scratch) {
+      // split-K: raw fp32 partial tile -> red.add into the scratch (bias / activation / bf16 in munit_splitk_finish)
+      const int dx = row % p.tw;
+      const int dy = (row / p.tw) % p.th;
+      const int dn = row / (p.tw * p.th);
+      const int n = n0 + dn, y = y0 + dy, x = x0 + dx;
+      const bool valid = (n < p.n_img) && (y < p.out_h) && (x < p.out_w) && num_kb > 0;
+      float* sptr = p.scratch + (long long)n * p.o_sn + (long long)(y * p.o_ymul + p.o_yoff[phase_id]) * p.o_sy +
+                    (long long)(x * p.o_xmul + p.o_xoff[phase_id]) * p.o_sx + n_tile * BN;
+      constexpr int kChunk = BN < 32 ? 16 : 32;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += kChunk) {
+        uint32_t v[kChunk];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0;
+        if (kChunk == 32) tmem_ld_32x32(taddr, v);
+        else tmem_ld_32x16(taddr, v);
+        tmem_ld_wait();
+        if (valid && !dead) {
+          const int col0 = n_tile * BN + c0;
+#pragma unroll
+          for (int j = 0; j < kChunk; j += 4)
+            if (col0 + j < p.n_store)
+              red_add_v4_f32(sptr + c0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                             __uint_as_float(v[j + 3]));
+        }
+      }
+    } else if constexpr (BN >= 64) {
       // The pipeline stages are idle now (every MMA has completed): stage the bf16 tile there, one
       // [128 px x 64 ch] SWIZZLE_128B box per 64-channel group, and let TMA write full lines.
       constexpr int kGroups = BN / 64;
@@ -1050,7 +1084,14 @@ extern "C" int munit_tapgemm(const munit_tapgemm_desc* d, void* stream) {
     p.dbg = dbg;
   }
   memcpy(p.tap_off, d->tap_off, sizeof(p.tap_off));
-  dim3 grid(p.tiles_x * p.tiles_y * p.tiles_n, (unsigned)(d->b_rows / d->bn), d->phases);
+  p.ksplit = d->ksplit > 1 ? d->ksplit : 1;
+  p.scratch = p.ksplit > 1 ? d->scratch : nullptr;
+  if (p.ksplit > 1) {
+    if (!d->scratch) return mb_fail(MUNIT_ERR_ARG, "tapgemm: ksplit > 1 needs a zeroed fp32 scratch");
+    if (p.ksplit > d->num_taps * d->chunks) return mb_fail(MUNIT_ERR_ARG, "tapgemm: ksplit exceeds taps * chunks");
+    if (d->halo || d->stats || d->cluster > 1) return mb_fail(MUNIT_ERR_ARG, "tapgemm: ksplit excludes halo / stats / cluster");
+  }
+  dim3 grid(p.tiles_x * p.tiles_y * p.tiles_n, (unsigned)(d->b_rows / d->bn), d->phases * p.ksplit);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (d->halo) {
     // halo-resident variant: validated stride-1 geometry (see include/munit_b200.h)

@@ -58,8 +58,29 @@ def stats_splits(plan, kind: int) -> int:
     return 4 * tiles * (plan.b_rows // 64 if kind == 2 else 1)
 
 
+def auto_ksplit(plan) -> int:
+    """Split-K factor for launches whose output tiles cannot fill the GPU (the deepest discriminator layers:
+    <= 8 CTAs each walking >= 64 K blocks one after the other).  1 = no split.  Wider thresholds were measured
+    slower in the two-stream step: the memset + finish launches and the fp32 atomics cost more than the short
+    kernels, which already overlap with the other branch (38.39 ms unsplit, 39.33 ms at <= 48 CTAs / >= 16 blocks,
+    37.92 ms at <= 8 / >= 64)."""
+    if getattr(plan, "halo", 0) or not _AUTO_KSPLIT:
+        return 1
+    gx, gy, gz = plan.grid
+    ctas = gx * gy * gz
+    num_kb = plan.num_taps * plan.chunks
+    if ctas == 0 or ctas > _KSPLIT_MAX_CTAS or num_kb < _KSPLIT_MIN_KB:
+        return 1
+    return max(1, min(num_kb // 4, 16, 296 // ctas))
+
+
+_AUTO_KSPLIT = _os.environ.get("MUNIT_KSPLIT", "1") != "0"
+_KSPLIT_MAX_CTAS = int(_os.environ.get("MUNIT_KSPLIT_CTAS", "8"))
+_KSPLIT_MIN_KB = int(_os.environ.get("MUNIT_KSPLIT_KB", "64"))
+
+
 def tapgemm(plan, a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, bias=None, act="none", stages=0, cluster=0,
-            stats=None, stats_kind=0):
+            stats=None, stats_kind=0, ksplit=0):
     """out (bf16) <- act(tapconv(a; b) + bias) as described by `plan` (geometry.TapGemmPlan).  `stats` (fp32,
     n_img * stats_splits(plan, kind) * (C if kind == 1 else 1) * 2 floats) receives the norm partials."""
     _lib.init()
@@ -91,12 +112,22 @@ def tapgemm(plan, a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, bias=None
         assert bias.dtype == torch.float32 and bias.numel() >= plan.b_rows
     d.bias, d.act, d.stages, d.cluster = _ptr(bias), ACT[act], stages, cluster
     d.halo = int(getattr(plan, "halo", 0))
+    ksplit = ksplit or (auto_ksplit(plan) if stats is None and cluster <= 1 else 1)
+    scratch = None
+    if ksplit > 1:
+        assert out.is_contiguous() and plan.n_store == plan.b_rows and out.shape[-1] == plan.b_rows
+        scratch = torch.zeros(out.shape, dtype=torch.float32, device=out.device)
+        d.ksplit, d.scratch = ksplit, scratch.data_ptr()
     if stats is not None:
         assert stats.dtype == torch.float32 and stats_kind in (1, 2)
         assert stats.numel() == plan.n_img * stats_splits(plan, stats_kind) * (plan.b_rows if stats_kind == 1 else 1) * 2
         d.stats, d.stats_kind = stats.data_ptr(), stats_kind
     check(lib.munit_tapgemm(C.byref(d), _stream()), "munit_tapgemm")
     _count()
+    if scratch is not None:
+        check(lib.munit_splitk_finish(scratch.data_ptr(), _ptr(bias), ACT[act], out.data_ptr(), out.numel(),
+                                      out.shape[-1], _stream()), "splitk_finish")
+        _count()
     return out
 
 

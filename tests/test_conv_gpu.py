@@ -227,3 +227,50 @@ def test_epilogue_statistics(n, h, w, cin, cout, k, s, pad, halo, mode):
     ref = K.norm_finalize(stats, shift, mode, p_w, p_b, ldw, ho * wo)
     for i, name in enumerate(("mean", "rinv", "a", "b")):
         assert rel_l2(coef[i], ref[i]) < 2e-5, (name, rel_l2(coef[i], ref[i]))
+
+
+SPLITK_CASES = [
+    # n, h, w, cin, cout, k, s, pad
+    (8, 8, 8, 256, 512, 4, 2, 1),    # deep discriminator layer: 1 M tile x 2 N tiles, 64 K blocks
+    (8, 16, 16, 256, 512, 4, 2, 1),
+    (2, 16, 16, 64, 64, 3, 1, 1),
+    (3, 8, 8, 256, 512, 4, 2, 1),
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,k,s,pad", SPLITK_CASES)
+@pytest.mark.parametrize("ksplit", [0, 3, 8])
+def test_tapgemm_split_k(n, h, w, cin, cout, k, s, pad, ksplit):
+    """Split-K tap-GEMM (fp32 red.add into a scratch + munit_splitk_finish) for launches with too few output
+    tiles: forward (bias + LeakyReLU in the finish kernel) and input gradient (stride-2: four phases) must match
+    torch conv2d like the unsplit kernel does.  ksplit=0 lets kernels.auto_ksplit decide."""
+    from munit_b200 import geometry as G, kernels as K
+
+    xp, wt, bias = _setup(n, h, w, cin, cout, k, s, pad, 7)
+    xp = xp.requires_grad_(True)
+    y_lin = F.conv2d(xp, wt, bias, stride=s)
+    y_ref = F.leaky_relu(y_lin, 0.2)
+    gy = bf16_round(torch.randn_like(y_lin))
+    y_lin.backward(gy)
+    hp, wp = xp.shape[2:]
+    ho, wo = y_ref.shape[2:]
+    plan = G.plan_fwd(n, hp, wp, cin, k, k, s, s, cout, (ho * wo * cout, wo * cout, cout, 0, 0))
+    a = nhwc(xp.detach()).to(torch.bfloat16)
+    b = wt.permute(0, 2, 3, 1).reshape(cout, -1).contiguous().to(torch.bfloat16)
+    out = torch.full((n, ho, wo, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    launches0 = K._lib.launches
+    K.tapgemm(plan, a, b, out, bias, "lrelu", ksplit=ksplit)
+    split = K._lib.launches - launches0 == 2
+    assert split == (ksplit > 1 or K.auto_ksplit(plan) > 1)
+    torch.cuda.synchronize()
+    assert error_flag() == 0
+    assert rel_l2(out, nhwc(y_ref.detach())) < TOL, rel_l2(out, nhwc(y_ref.detach()))
+    dplan = G.plan_dgrad(n, hp, wp, cin, k, k, s, s, cout)
+    idx = G.dgrad_index_map(cout, cin, k, k, s, s, cin, max(64, cout)).cuda()
+    wd = torch.empty(cin, idx.numel() // cin, dtype=torch.bfloat16, device="cuda")
+    K.gather_cast(wt.permute(0, 2, 3, 1).contiguous().reshape(-1), idx, wd)
+    dxp = torch.full((n, hp, wp, cin), float("nan"), dtype=torch.bfloat16, device="cuda")
+    K.tapgemm(dplan, nhwc(gy).to(torch.bfloat16), wd, dxp, ksplit=min(ksplit, dplan.num_taps * dplan.chunks))
+    torch.cuda.synchronize()
+    assert error_flag() == 0
+    assert rel_l2(dxp, nhwc(xp.grad)) < TOL, rel_l2(dxp, nhwc(xp.grad))
