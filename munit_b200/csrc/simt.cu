@@ -965,7 +965,22 @@ __device__ __forceinline__ void norm_bwd_apply_body(Blk blk, const bf16* __restr
           d.v[e] = fmaf(fca.v[e], dz, fmaf(k1.v[e], xv.v[e], k0.v[e]));
         }
         store8(dy + ((long long)bb * hw + pix) * c + g * 8, d);
-        if (g_res) store8(g_res + (((long long)bb * (h + 2 * res_pad) + yy + res_pad) * (w + 2 * res_pad) + x + res_pad) * c + g * 8, gr);
+        if (g_res) {
+          const int hrp = h + 2 * res_pad, wrp = w + 2 * res_pad;
+          store8(g_res + (((long long)bb * hrp + yy + res_pad) * wrp + x + res_pad) * c + g * 8, gr);
+          // the halo of g_res carries no gradient: every halo cell is zeroed by the one border pixel that mirrors
+          // onto it, so the caller need not clear the buffer first
+          if (res_pad > 0 && (yy <= res_pad || x <= res_pad || yy >= h - 1 - res_pad || x >= w - 1 - res_pad)) {
+            int prow[3], pcol[3];
+            const int nr = pad_positions(yy, h, res_pad, prow);
+            const int nc = pad_positions(x, w, res_pad, pcol);
+            for (int i = 0; i < nr; ++i)
+              for (int q2 = 0; q2 < nc; ++q2)
+                if (i | q2)
+                  *reinterpret_cast<uint4*>(g_res + (((long long)bb * hrp + prow[i]) * wrp + pcol[q2]) * c + g * 8) =
+                      make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
       }
     }
   }

@@ -390,7 +390,7 @@ def norm_bwd(g_out, out_pad, upsample, y, coef, relu, mode, p_w, ldw, g_w, g_b, 
     dy = torch.empty_like(y)
     g_res = None
     if want_res:
-        g_res = torch.zeros(n, h + 2 * res_pad, w + 2 * res_pad, c, dtype=torch.bfloat16, device=y.device)
+        g_res = torch.empty(n, h + 2 * res_pad, w + 2 * res_pad, c, dtype=torch.bfloat16, device=y.device)  # halo zeroed by the kernel
     check(lib.munit_norm_bwd_apply(g_out.data_ptr(), out_pad, upsample, y.data_ptr(), a.data_ptr(), b.data_ptr(),
                                    int(relu), mean.data_ptr(), rinv.data_ptr(), k[0].data_ptr(), k[1].data_ptr(),
                                    k[2].data_ptr(), dy.data_ptr(), _ptr(g_res), res_pad, n, h, w, c, _stream()),
