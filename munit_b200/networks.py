@@ -405,14 +405,11 @@ class _AdaINMixin:
     def assign_adain_params(self, adain_params, model):
         """networks.py:230-239: per AdaIN layer (module order) columns [:C] -> bias, [C:2C] -> weight.
         The slices stay strided views of the MLP output: the norm kernels index them directly."""
-        for m in model.modules():
-            if m.__class__.__name__ == "AdaptiveInstanceNorm2d":
-                mean = adain_params[:, : m.num_features]
-                std = adain_params[:, m.num_features: 2 * m.num_features]
-                m.bias = mean
-                m.weight = std
-                if adain_params.size(1) > 2 * m.num_features:
-                    adain_params = adain_params[:, 2 * m.num_features:]
+        mods = [m for m in model.modules() if m.__class__.__name__ == "AdaptiveInstanceNorm2d"]
+        outs = ops.AdainSplitFn.apply(adain_params, tuple(m.num_features for m in mods))
+        for i, m in enumerate(mods):
+            m.bias = outs[2 * i]
+            m.weight = outs[2 * i + 1]
 
     def get_num_adain_params(self, model):
         """networks.py:241-247."""

@@ -395,6 +395,35 @@ class NormFn(torch.autograd.Function):
         return dy, ret_w, ret_b, g_res, None, None, None, None, None, None, None
 
 
+class AdainSplitFn(torch.autograd.Function):
+    """assign_adain_params (networks.py:230-239) as ONE autograd node: per AdaIN layer the columns [:C] (bias) and
+    [C:2C] (weight) of the MLP output, returned as strided views (the norm kernels index them in place).  The
+    backward concatenates the 2L slice gradients with one kernel; the reference's chain of nested slices costs a
+    zero-fill, a copy and an add per slice (~190 launches per generator update)."""
+
+    @staticmethod
+    def forward(ctx, params, sizes):
+        outs, off = [], 0
+        for c in sizes:
+            outs.append(params[:, off:off + c])
+            outs.append(params[:, off + c:off + 2 * c])
+            off += 2 * c
+        ctx.sizes, ctx.shape, ctx.used = tuple(sizes), tuple(params.shape), off
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        n, total = ctx.shape
+        parts = []
+        for i, g in enumerate(grads):
+            c = ctx.sizes[i // 2]
+            parts.append(g if g is not None else torch.zeros(n, c, dtype=torch.float32, device=grads[0].device if grads[0] is not None else None))
+        if ctx.used < total:
+            ref = next(g for g in grads if g is not None)
+            parts.append(torch.zeros(n, total - ctx.used, dtype=ref.dtype, device=ref.device))
+        return torch.cat(parts, 1), None
+
+
 class ToActFn(torch.autograd.Function):
     """NCHW fp32 (public tensor format) -> act with reflect halo."""
 
