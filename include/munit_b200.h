@@ -312,6 +312,33 @@ int munit_adam(float* p, const float* g, float* m, float* v, float* p_saved, voi
 int munit_fill_f32(float* p, float v, int64_t n, void* stream);
 int munit_add_bf16(void* dst, const void* src, int64_t n, void* stream);
 
+/* ---- domain-adaptation heads: `domainClassifier` scripts/utils.py:1370-1392 --------------
+ * MaxPool2d(2) (utils.py:1374,1376) on NHWC bf16: x [N][H+2P][W+2P][C] (interior read) -> y [N][H/2][W/2][C];
+ * backward writes every position of dx [N][H+2P][W+2P][C] (halo = 0; first maximum in row-major order wins). */
+int munit_maxpool2_fwd(const void* x, int in_pad, void* y, int n, int h, int w, int c, void* stream);
+int munit_maxpool2_bwd(const void* gy, const void* x, int in_pad, void* dx, int n, int h, int w, int c, void* stream);
+/* nn.BatchNorm2d of BasicBlock (utils.py:1300-1309).  Consumes the per-(n,c) partials of munit_norm_stats
+ * (stats [n_total][splits][C][2], shift [n_total][C]) and writes the coefficient vectors munit_norm_apply /
+ * munit_norm_bwd_* take, identical for the first n_out samples.  training != 0: batch statistics over
+ * n_total*hw values (biased variance), running_mean / running_var (may be NULL) updated with `momentum` and
+ * the unbiased variance; training == 0: running statistics.  n_total > n_out: the rows of other data-parallel
+ * ranks were gathered in (synchronised BatchNorm). */
+int munit_bn_finalize(const float* stats, int splits, const float* shift, int n_total, int n_out, const float* gamma,
+                      const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                      int training, float* mean, float* rinv, float* a, float* b, int hw, int c, void* stream);
+/* sums [n_total][splits][C][2] from munit_norm_bwd_reduce -> ca, cb, cc [n_local][C] (dx = ca*dz + cb*xhat + cc);
+ * g_gamma / g_beta (+=, may be NULL) from this rank's rows [n0, n0 + n_local). */
+int munit_bn_bwd_finalize(const float* sums, int splits, int n_total, int n0, int n_local, const float* gamma,
+                          const float* rinv, int training, float* ca, float* cb, float* cc, float* g_gamma,
+                          float* g_beta, int hw, int c, void* stream);
+/* out = relu(a + b), n bf16 elements (BasicBlock.forward residual tail, utils.py:1327-1329). */
+int munit_add_relu(const void* a, const void* b, void* out, int64_t n, void* stream);
+/* loss = scale * sum((x - target)^2) over n fp32 values (compute_classifier_sr_loss, trainer.py:658-667);
+ * dx = gscale_dev[0] * 2 * scale * (x - target). */
+int munit_mse_const_fwd(const float* x, float target, float* loss, float scale, int n, void* stream);
+int munit_mse_const_bwd(const float* x, float target, const float* gscale_dev, float scale, float* dx, int n,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

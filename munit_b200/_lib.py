@@ -114,6 +114,13 @@ _SIGS = {
     "munit_adam": ([_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _f, _f, _f, _f, _f, _i, _f, _vp, _vp], C.c_int),
     "munit_fill_f32": ([_vp, _f, _i64, _vp], C.c_int),
     "munit_add_bf16": ([_vp, _vp, _i64, _vp], C.c_int),
+    "munit_maxpool2_fwd": ([_vp, _i, _vp, _i, _i, _i, _i, _vp], C.c_int),
+    "munit_maxpool2_bwd": ([_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp], C.c_int),
+    "munit_bn_finalize": ([_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _vp, _vp, _i, _i, _vp], C.c_int),
+    "munit_bn_bwd_finalize": ([_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp], C.c_int),
+    "munit_add_relu": ([_vp, _vp, _vp, _i64, _vp], C.c_int),
+    "munit_mse_const_fwd": ([_vp, _f, _vp, _f, _i, _vp], C.c_int),
+    "munit_mse_const_bwd": ([_vp, _f, _vp, _f, _vp, _i, _vp], C.c_int),
 }
 for _name, (_args, _res) in _SIGS.items():
     _fn = getattr(lib, _name)  # AttributeError here == header/library mismatch: fail loudly

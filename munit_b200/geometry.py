@@ -163,6 +163,11 @@ def _x_view(n, hp, wp, c, sy, sx):
     raise ValueError(f"unsupported stride ({sy},{sx})")
 
 
+def _shift_tap(t, zpad):
+    """Tap offset of a stride-1 view [c, x, y, n] moved by the implicit zero padding."""
+    return t if not zpad else [t[0], t[1] - zpad, t[2] - zpad] + list(t[3:])
+
+
 def conv_out(hp, k, s):
     return (hp - k) // s + 1
 
@@ -172,14 +177,18 @@ def halo_ok(kh, kw, sy, sx, out_h, out_w, bn) -> bool:
     return sy == 1 and sx == 1 and kw <= 9 and kh * kw > 1 and bn >= 64 and out_h >= 8 and out_w >= 8
 
 
-def plan_fwd(n, hp, wp, c, kh, kw, sy, sx, co_rows, out_geom, n_store=None, halo=0) -> TapGemmPlan:
+def plan_fwd(n, hp, wp, c, kh, kw, sy, sx, co_rows, out_geom, n_store=None, halo=0, zpad=0) -> TapGemmPlan:
     """Forward conv: x [n,hp,wp,c] -> out.  out_geom = (o_sn, o_sy, o_sx, y_off, x_off) in elements:
-    pixel (b, y, x) is stored at out + b*o_sn + (y+y_off)*o_sy + (x+x_off)*o_sx."""
+    pixel (b, y, x) is stored at out + b*o_sn + (y+y_off)*o_sy + (x+x_off)*o_sx.
+    zpad > 0: implicit zero padding of that width (nn.Conv2d(padding=zpad), utils.py:1238-1261) -- the buffer
+    stays unpadded, the taps start at -zpad and TMA zero-fills what falls outside (stride 1 only)."""
     assert c % 64 == 0, "input channels must be a multiple of 64"
-    ho, wo = conv_out(hp, kh, sy), conv_out(wp, kw, sx)
+    assert zpad == 0 or (sy == 1 and sx == 1), "implicit zero padding is built for stride-1 convolutions"
+    ho, wo = conv_out(hp + 2 * zpad, kh, sy), conv_out(wp + 2 * zpad, kw, sx)
     rank, dims, strides, mx, my, mn, off, box = _x_view(n, hp, wp, c, sy, sx)
     tw, th, tn = pick_tile(wo, ho, n, 128)
-    taps = [off(i, j) for i in range(kh) for j in range(kw)]
+    taps = [_shift_tap(off(i, j), zpad) for i in range(kh) for j in range(kw)]
+    halo = 0 if zpad else halo
     o_sn, o_sy, o_sx, y_off, x_off = out_geom
     bn = pick_bn(co_rows)
     halo = halo if halo_ok(kh, kw, sy, sx, ho, wo, bn) else 0
@@ -193,10 +202,13 @@ def plan_fwd(n, hp, wp, c, kh, kw, sy, sx, co_rows, out_geom, n_store=None, halo
         o_xmul=1, n_store=co_rows if n_store is None else n_store)
 
 
-def plan_dgrad(n, hp, wp, c_rows, kh, kw, sy, sx, co_c, halo=0) -> TapGemmPlan:
+def plan_dgrad(n, hp, wp, c_rows, kh, kw, sy, sx, co_c, halo=0, zpad=0) -> TapGemmPlan:
     """Input gradient: dy [n,ho,wo,co_c] (unpadded; out-of-range taps read zero through TMA) ->
-    dxp [n,hp,wp,c_rows] (gradient w.r.t. the *padded* conv input, every position written)."""
-    ho, wo = conv_out(hp, kh, sy), conv_out(wp, kw, sx)
+    dxp [n,hp,wp,c_rows] (gradient w.r.t. the *padded* conv input, every position written).
+    zpad > 0 (implicit zero padding, see plan_fwd): [hp, wp] is the unpadded input and the taps shift by +zpad."""
+    assert zpad == 0 or (sy == 1 and sx == 1)
+    ho, wo = conv_out(hp + 2 * zpad, kh, sy), conv_out(wp + 2 * zpad, kw, sx)
+    halo = 0 if zpad else halo
     ck = max(64, co_c)
     assert ck % 64 == 0
     e = 2
@@ -207,7 +219,7 @@ def plan_dgrad(n, hp, wp, c_rows, kh, kw, sy, sx, co_c, halo=0) -> TapGemmPlan:
     assert hp % sy == 0 and wp % sx == 0
     oh, ow = hp // sy, wp // sx
     tw, th, tn = pick_tile(ow, oh, n, 128)
-    taps = [[0, -b, -a, 0] for a in range(na) for b in range(nb)]
+    taps = [[0, zpad - b, zpad - a, 0] for a in range(na) for b in range(nb)]
     phases = sy * sx
     kper = na * nb * ck
     halo = halo if halo_ok(kh, kw, sy, sx, oh, ow, pick_bn(c_rows)) else 0
@@ -224,13 +236,16 @@ def plan_dgrad(n, hp, wp, c_rows, kh, kw, sy, sx, co_c, halo=0) -> TapGemmPlan:
 
 
 def plan_wgrad(n, hp, wp, c, kh, kw, sy, sx, co_c, m_total, s_m, s_t, s_n, n_total=None, swap=None,
-               row_share=False) -> WgradPlan:
-    """Weight gradient: dw[m, tap, cin] += sum_pix dy[pix, m] * x[pix@tap, cin]."""
-    ho, wo = conv_out(hp, kh, sy), conv_out(wp, kw, sx)
+               row_share=False, zpad=0) -> WgradPlan:
+    """Weight gradient: dw[m, tap, cin] += sum_pix dy[pix, m] * x[pix@tap, cin].
+    zpad > 0: x is unpadded and implicitly zero-padded (see plan_fwd)."""
+    assert zpad == 0 or (sy == 1 and sx == 1)
+    ho, wo = conv_out(hp + 2 * zpad, kh, sy), conv_out(wp + 2 * zpad, kw, sx)
     e = 2
     rank, dims, strides, mx, my, mn, off, box = _x_view(n, hp, wp, c, sy, sx)
     pw, ph, pn = pick_tile(wo, ho, n, 64)
-    taps = [off(i, j) for i in range(kh) for j in range(kw)]
+    taps = [_shift_tap(off(i, j), zpad) for i in range(kh) for j in range(kw)]
+    row_share = row_share and not zpad
     n_total = c if n_total is None else n_total
     if swap is None:  # put the wider channel count on the 128-row M operand
         swap = m_total <= 64 and n_total >= 128

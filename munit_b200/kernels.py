@@ -571,3 +571,103 @@ def add_bf16(dst, src):
     check(lib.munit_add_bf16(dst.data_ptr(), src.data_ptr(), dst.numel(), _stream()), "add_bf16")
     _count()
     return dst
+
+
+# ---------------------------------------------------------------- domain-adaptation heads (csrc/heads.cu)
+def maxpool2_fwd(x, in_pad):
+    n, hp, wp, c = x.shape
+    h, w = hp - 2 * in_pad, wp - 2 * in_pad
+    y = torch.empty(n, h // 2, w // 2, c, dtype=torch.bfloat16, device=x.device)
+    check(lib.munit_maxpool2_fwd(x.data_ptr(), in_pad, y.data_ptr(), n, h, w, c, _stream()), "maxpool2_fwd")
+    _count()
+    return y
+
+
+def maxpool2_bwd(gy, x, in_pad):
+    n, hp, wp, c = x.shape
+    dx = torch.empty_like(x)
+    check(lib.munit_maxpool2_bwd(gy.data_ptr(), x.data_ptr(), in_pad, dx.data_ptr(), n, hp - 2 * in_pad, wp - 2 * in_pad,
+                                 c, _stream()), "maxpool2_bwd")
+    _count()
+    return dx
+
+
+def _gather_ranks(t):
+    """[n, ...] of every data-parallel rank stacked along dim 0 (synchronised BatchNorm); returns (all, n0)."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1 or not SYNC_BN:
+        return t, 0
+    out = torch.empty((dist.get_world_size() * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t.contiguous())
+    return out, dist.get_rank() * t.shape[0]
+
+
+# BatchNorm statistics over the global batch when torch.distributed is initialised (MUNIT_SYNC_BN=0: per rank).
+SYNC_BN = _os.environ.get("MUNIT_SYNC_BN", "1") != "0"
+
+
+def bn_fwd(y, gamma, beta, running_mean, running_var, momentum, eps, training, relu):
+    """nn.BatchNorm2d (+ReLU) on y [N,H,W,C] bf16 -> (out [N,H,W,C], coef[4][N][C] = mean, rinv, a, b)."""
+    n, h, w, c = y.shape
+    coef = torch.empty(4, n, c, dtype=torch.float32, device=y.device)
+    if training:
+        stats, shift = norm_stats(y)
+        splits = stats.shape[1]
+        stats, _ = _gather_ranks(stats)
+        shift, _ = _gather_ranks(shift)
+        n_total = stats.shape[0]
+        sp, shp = stats.data_ptr(), shift.data_ptr()
+    else:
+        splits, n_total, sp, shp = 0, 0, 0, 0
+    check(lib.munit_bn_finalize(sp, splits, shp, n_total, n, _ptr(gamma), _ptr(beta), _ptr(running_mean),
+                                _ptr(running_var), float(momentum), float(eps), int(training), coef[0].data_ptr(),
+                                coef[1].data_ptr(), coef[2].data_ptr(), coef[3].data_ptr(), h * w, c, _stream()),
+          "bn_finalize")
+    _count()
+    return norm_apply(y, coef[2], coef[3], relu, None, 0, 0, 1), coef
+
+
+def bn_bwd(g_out, y, coef, relu, gamma, g_gamma, g_beta, training):
+    """dy of bn_fwd; g_gamma / g_beta (+=, may be None)."""
+    n, h, w, c = y.shape
+    mean, rinv, a, b = coef[0], coef[1], coef[2], coef[3]
+    splits = lib.munit_norm_splits(h * w, c)
+    sums = torch.empty(n, splits, c, 2, dtype=torch.float32, device=y.device)
+    check(lib.munit_norm_bwd_reduce(g_out.data_ptr(), 0, 1, y.data_ptr(), a.data_ptr(), b.data_ptr(), int(relu),
+                                    mean.data_ptr(), rinv.data_ptr(), sums.data_ptr(), n, h, w, c, _stream()),
+          "norm_bwd_reduce")
+    sums_all, n0 = _gather_ranks(sums) if training else (sums, 0)
+    k = torch.empty(3, n, c, dtype=torch.float32, device=y.device)
+    check(lib.munit_bn_bwd_finalize(sums_all.data_ptr(), splits, sums_all.shape[0], n0, n, _ptr(gamma), rinv.data_ptr(),
+                                    int(training), k[0].data_ptr(), k[1].data_ptr(), k[2].data_ptr(), _ptr(g_gamma),
+                                    _ptr(g_beta), h * w, c, _stream()), "bn_bwd_finalize")
+    dy = torch.empty_like(y)
+    check(lib.munit_norm_bwd_apply(g_out.data_ptr(), 0, 1, y.data_ptr(), a.data_ptr(), b.data_ptr(), int(relu),
+                                   mean.data_ptr(), rinv.data_ptr(), k[0].data_ptr(), k[1].data_ptr(), k[2].data_ptr(),
+                                   dy.data_ptr(), 0, 0, n, h, w, c, _stream()), "norm_bwd_apply")
+    _count(3)
+    return dy
+
+
+def add_relu(a, b):
+    out = torch.empty_like(a)
+    check(lib.munit_add_relu(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), _stream()), "add_relu")
+    _count()
+    return out
+
+
+def mse_const_fwd(x, target, scale):
+    loss = torch.empty(1, dtype=torch.float32, device=x.device)
+    check(lib.munit_mse_const_fwd(x.data_ptr(), float(target), loss.data_ptr(), float(scale), x.numel(), _stream()),
+          "mse_const_fwd")
+    _count()
+    return loss
+
+
+def mse_const_bwd(x, target, gscale_dev, scale):
+    dx = torch.empty_like(x)
+    check(lib.munit_mse_const_bwd(x.data_ptr(), float(target), gscale_dev.data_ptr(), float(scale), dx.data_ptr(),
+                                  x.numel(), _stream()), "mse_const_bwd")
+    _count()
+    return dx

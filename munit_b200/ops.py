@@ -105,8 +105,11 @@ class ConvLayer:
     """Per-convolution host state: geometry, bf16 weight shadows, cached plans.  Not an nn.Module --
     owned by Conv2dBlock next to the nn.Conv2d that holds the fp32 master parameters."""
 
-    def __init__(self, cin, cout, k, stride, pad):
-        self.cin, self.cout, self.k, self.stride, self.pad = cin, cout, k, stride, pad
+    def __init__(self, cin, cout, k, stride, pad, zpad=0):
+        """pad: reflect halo the input act carries; zpad: implicit zero padding (nn.Conv2d(padding=zpad)) of an
+        input act without halo -- out-of-range taps are TMA zero fill (geometry.plan_fwd)."""
+        self.cin, self.cout, self.k, self.stride, self.pad, self.zpad = cin, cout, k, stride, pad, zpad
+        assert not (pad and zpad)
         self.first = cin < 64  # image-space layer: kw-expanded GEMM (K = 64 per kh tap)
         # narrow-output layer (64->3 7x7 tanh): vertical GEMM with N = (kw, co) + horizontal combine
         self.last = (not self.first) and cout <= 4 and k <= 8 and stride == 1
@@ -183,18 +186,19 @@ class ConvLayer:
                 kh, kw, sy, sx, c = k, 1, s, 1, 64
             else:
                 kh, kw, sy, sx, c = k, k, s, s, self.cin
-            ho, wo = G.conv_out(hp, kh, sy), G.conv_out(wp, kw, sx)
+            zp = self.zpad
+            ho, wo = G.conv_out(hp + 2 * zp, kh, sy), G.conv_out(wp + 2 * zp, kw, sx)
             hop, wop = ho + 2 * out_pad, wo + 2 * out_pad
             fwd = G.plan_fwd(n, hp, wp, c, kh, kw, sy, sx, self.co_rows,
                              (hop * wop * self.co_rows, wop * self.co_rows, self.co_rows, out_pad, out_pad),
-                             halo=_want_halo(kh, kw, ho, wo))
-            dg = G.plan_dgrad(n, hp, wp, c, kh, kw, sy, sx, self.co_rows, halo=_want_halo(kh, kw, hp, wp))
+                             halo=_want_halo(kh, kw, ho, wo), zpad=zp)
+            dg = G.plan_dgrad(n, hp, wp, c, kh, kw, sy, sx, self.co_rows, halo=_want_halo(kh, kw, hp, wp), zpad=zp)
             if self.first:
                 wg = G.plan_wgrad(n, hp, wp, 64, kh, 1, sy, 1, self.co_rows, self.cout, kh * 64, 64, 1)
             elif self.last:
                 wg = G.plan_wgrad(n, hp, wp, 64, kh, 1, 1, 1, 32, 32, kh * 64, 64, 1)
             else:
-                wg = G.plan_wgrad(n, hp, wp, c, kh, kw, sy, sx, self.co_rows, self.cout, kh * kw * c, c, 1)
+                wg = G.plan_wgrad(n, hp, wp, c, kh, kw, sy, sx, self.co_rows, self.cout, kh * kw * c, c, 1, zpad=zp)
             # direct-form algorithmic work of this layer instance: 1 MAC = 2 FLOP
             flops = 2.0 * n * ho * wo * self.cout * self.k * self.k * self.cin
             fwd.alg_flops = dg.alg_flops = wg.alg_flops = flops
@@ -630,3 +634,84 @@ class L1Fn(torch.autograd.Function):
             return full
 
         return embed(ga, ctx.shapes[0], pa), embed(gb, ctx.shapes[1], pb), None, None
+
+
+# ------------------------------------------------------------------ domain-adaptation heads (utils.py:1276-1392)
+class MaxPool2Fn(torch.autograd.Function):
+    """nn.MaxPool2d(2) (utils.py:1374,1376): interior of an act with halo `in_pad` -> act without halo.  The
+    backward returns the gradient of the whole padded buffer (halo = 0), as the producer's backward expects."""
+
+    @staticmethod
+    def forward(ctx, x, in_pad: int):
+        x = x.contiguous()
+        ctx.in_pad = in_pad
+        ctx.save_for_backward(x)
+        return K.maxpool2_fwd(x, in_pad)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        return K.maxpool2_bwd(gy.contiguous(), x, ctx.in_pad), None
+
+
+class BatchNormFn(torch.autograd.Function):
+    """nn.BatchNorm2d (+ReLU) of BasicBlock (utils.py:1300-1309,1316-1323) on a raw conv output [N,H,W,C]:
+    per-channel batch statistics (training; running statistics updated in place) or running statistics (eval),
+    then the generic normalise / backward-apply kernels."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, running_mean, running_var, training: bool, relu: bool, momentum: float,
+                eps: float):
+        y = y.contiguous()
+        out, coef = K.bn_fwd(y, gamma, beta, running_mean, running_var, momentum, eps, training, relu)
+        ctx.cfg = (training, relu)
+        ctx.wbuf, ctx.bbuf = _param_grad_buf(gamma), _param_grad_buf(beta)
+        ctx.save_for_backward(y, coef, gamma)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        training, relu = ctx.cfg
+        y, coef, gamma = ctx.saved_tensors
+        c = y.shape[3]
+        g_w = g_b = ret_w = ret_b = None
+        if ctx.needs_input_grad[1]:
+            g_w = ctx.wbuf if ctx.wbuf is not None else torch.zeros(c, dtype=torch.float32, device=y.device)
+            ret_w = None if ctx.wbuf is not None else g_w
+        if ctx.needs_input_grad[2]:
+            g_b = ctx.bbuf if ctx.bbuf is not None else torch.zeros(c, dtype=torch.float32, device=y.device)
+            ret_b = None if ctx.bbuf is not None else g_b
+        dy = K.bn_bwd(g_out.contiguous(), y, coef, relu, gamma, g_w, g_b, training)
+        return dy, ret_w, ret_b, None, None, None, None, None, None
+
+
+class AddReluFn(torch.autograd.Function):
+    """out = relu(a + b) (BasicBlock.forward, utils.py:1327-1329); both inputs receive g * (out > 0)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        out = K.add_relu(a.contiguous(), b.contiguous())
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (out,) = ctx.saved_tensors
+        d = K.act_bwd(g.contiguous(), out, 0, "relu")
+        return d, d
+
+
+class MseConstFn(torch.autograd.Function):
+    """mean((x - target)^2) over all elements of an fp32 tensor (trainer.py:658-667)."""
+
+    @staticmethod
+    def forward(ctx, x, target: float):
+        x = x.contiguous()
+        ctx.target = float(target)
+        ctx.save_for_backward(x)
+        return K.mse_const_fwd(x, target, 1.0 / x.numel())
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return K.mse_const_bwd(x, ctx.target, g.contiguous(), 1.0 / x.numel()), None

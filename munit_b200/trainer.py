@@ -9,7 +9,12 @@ dis_a, dis_b, gen_opt, dis_opt, s_a, s_b, style_dim, iterations, loss_*.
 Differences that do not change results: the generator pass of dis_update runs without autograd (the
 reference records it and then .detach()es, trainer.py:1178-1179); gen_update does not compute the
 discriminator weight gradients the reference computes and discards (trainer.py:490-491 vs :1145).
-Out of scope (raise NotImplementedError): semantic_w, domain_adv_w, adaptation heads, vgg_w, synth pairs.
+Domain-adaptation head: `adaptation.dfeat_lambda > 0` builds domain_classifier_sr_a / _b
+(trainer.py:162-179), `adaptation.adv_lambda > 0` adds compute_classifier_sr_loss(fool=True) to gen_update
+(:521-525,555) and domain_classifier_sr_update (:1237-1265) trains the classifiers; in gen_update the classifier
+weight gradients, which the reference computes and zeroes unused (:1241), are not computed.
+Out of scope (raise NotImplementedError): semantic_w, domain_adv_w (the reference's compute_domain_adv_loss returns
+None, :669-714), output classifiers, sem_seg_lambda, vgg_w.
 """
 from __future__ import annotations
 
@@ -19,6 +24,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .heads import domainClassifier
 from .networks import AdaINGen, AdaINGen_double, MsImageDis
 from .optim import ExtraAdam, FlatAdam
 from .ops import Act
@@ -45,12 +51,15 @@ class MUNIT_Trainer(nn.Module):
                        ("vgg_w", "load_vgg16 always raises in the reference")):
             if hyperparameters.get(k, 0) > 0:
                 raise NotImplementedError(f"{k} > 0 is outside the B200 hot path ({why}); see SURVEY.md s2")
-        for k in ("dfeat_lambda", "adv_lambda", "sem_seg_lambda", "output_classifier_lambda", "output_adv_lambda"):
+        for k in ("sem_seg_lambda", "output_classifier_lambda", "output_adv_lambda"):
             if hyperparameters["adaptation"].get(k, 0) > 0:
                 raise NotImplementedError(f"adaptation.{k} > 0 is outside the B200 hot path; see SURVEY.md s8(f)")
+        if hyperparameters["adaptation"].get("adv_lambda", 0) > 0 and not hyperparameters["adaptation"].get("dfeat_lambda", 0) > 0:
+            # the reference would fail with AttributeError in gen_update (trainer.py:162,521-525,652)
+            raise ValueError("adaptation.adv_lambda > 0 needs adaptation.dfeat_lambda > 0 (the classifiers are only built then)")
         optimizer = FlatAdam if "extra" not in hyperparameters["optimizer"] else ExtraAdam
         self.domain_classif_ab = False
-        self.use_classifier_sr = False
+        self.use_classifier_sr = hyperparameters["adaptation"].get("dfeat_lambda", 0) > 0
         self.train_seg = False
         self.use_output_classifier_sr = False
 
@@ -90,6 +99,18 @@ class MUNIT_Trainer(nn.Module):
         self.dis_a.apply(weights_init("gaussian"))
         self.dis_b.apply(weights_init("gaussian"))
         self.iterations = 0
+        # Classifier on the content features for the synthetic / real adaptation (trainer.py:162-179): built after
+        # the generator / discriminator initialisation, b before a, initialised a before b -- the reference's order,
+        # so a seeded construction draws the same values.
+        if self.use_classifier_sr:
+            self.domain_classifier_sr_b = domainClassifier(256)
+            self.domain_classifier_sr_a = domainClassifier(256)
+            dann_params = list(self.domain_classifier_sr_a.parameters()) + list(self.domain_classifier_sr_b.parameters())
+            self.classif_opt_sr = optimizer([p for p in dann_params if p.requires_grad], lr=lr, betas=(beta1, beta2),
+                                            weight_decay=hyperparameters["weight_decay"])
+            self.domain_classifier_sr_a.apply(weights_init("gaussian"))
+            self.domain_classifier_sr_b.apply(weights_init("gaussian"))
+            self.classif_sr_scheduler = get_scheduler(self.classif_opt_sr, hyperparameters)
         # Two-stream mode (set by engine.StepRunner under CUDA-graph capture): the domain-a and domain-b branches
         # of a step are independent for long stretches; forking them onto two streams gives the captured graph
         # parallel branches, which fills partial waves and hides launch latency of the many small kernels.
@@ -137,6 +158,13 @@ class MUNIT_Trainer(nn.Module):
             self.gen_opt.extrapolation()
         else:
             self.gen_opt.step()
+
+    def classif_opt_sr_step(self):
+        """trainer.py:243-250."""
+        if "extra" in self.hyperparameters["optimizer"] and (self.iterations % 2 == 0):
+            self.classif_opt_sr.extrapolation()
+        else:
+            self.classif_opt_sr.step()
 
     # ------------------------------------------------------------------ losses (trainer.py:279-305)
     def recon_criterion(self, input, target):
@@ -288,7 +316,10 @@ class MUNIT_Trainer(nn.Module):
         self.loss_gen_vgg_b = 0
         self.loss_sem_seg = 0
         self.domain_adv_loss = 0
-        self.loss_classifier_sr = 0
+        # adaptation loss on the content features: fool the synthetic / real classifiers (trainer.py:521-525)
+        adv_lambda = hyperparameters["adaptation"].get("adv_lambda", 0)
+        self.loss_classifier_sr = (self.compute_classifier_sr_loss(c_a, c_b, domain_synth=synth, fool=True, frozen=True)
+                                   if adv_lambda > 0 else 0)
         self.loss_output_classifier_sr = 0
         # total loss (trainer.py:539-558)
         self.loss_gen_total = (
@@ -304,10 +335,43 @@ class MUNIT_Trainer(nn.Module):
             + hyperparameters["recon_x_cyc_w"] * self.loss_gen_cycrecon_x_b
             + hyperparameters["recon_synth_w"] * self.loss_gen_recon_synth
         )
+        if adv_lambda > 0:
+            self.loss_gen_total = self.loss_gen_total + adv_lambda * self.loss_classifier_sr
         self.loss_gen_total.backward()
         self._join_side()  # backward nodes ran on their forward streams; the optimiser step waits for both
         self._last = dict(x_ab=x_ab.detach(), x_ba=x_ba.detach())
         self._release_graph()
+
+    # ------------------------------------------------------------------ adaptation head (trainer.py:638-667,1237-1265)
+    def compute_classifier_sr_loss(self, c_a, c_b, domain_synth=False, fool=False, frozen=False):
+        """mean((D_a(c_a) - t)^2) + mean((D_b(c_b) - t)^2) with t = 0.5 (fool), 0 (synthetic) or 1 (real);
+        c_a / c_b: content codes (ops.Act or NCHW fp32).  frozen: no classifier weight gradients."""
+        target = 0.5 if fool else (0.0 if domain_synth else 1.0)
+        out_a, out_b = self._fork_join(lambda: self.domain_classifier_sr_a(c_a, frozen=frozen),
+                                       lambda: self.domain_classifier_sr_b(c_b, frozen=frozen))
+        return _scalar(ops.MseConstFn.apply(out_a.float(), target)) + _scalar(ops.MseConstFn.apply(out_b.float(), target))
+
+    def domain_classifier_sr_update(self, x_a, x_b, domain_synth, lambda_classifier, step=None, comet_exp=None):
+        """One update of the two content-feature classifiers on detached content codes (trainer.py:1237-1265)."""
+        self.classif_opt_sr.zero_grad()
+        ops.WG.enabled = False
+        with torch.no_grad():
+            c_a, _ = self._enc("a", x_a)
+            c_b, _ = self._enc("b", x_b)
+        loss = self.compute_classifier_sr_loss(c_a, c_b, domain_synth, fool=False)
+        loss = lambda_classifier * loss
+        loss.backward()
+        self._join_side()
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            world = torch.distributed.get_world_size()
+            if world > 1:  # data parallel: sum the per-rank gradients, 1/world fused into the update
+                from . import dp
+                dp.allreduce_arena(self.classif_opt_sr.g_arena)
+                self.classif_opt_sr.grad_scale = 1.0 / world
+        self.classif_opt_sr_step()
+        self.loss_classifier_sr_update = loss.detach()
+        if comet_exp is not None and self.iterations % 100 == 0:
+            comet_exp.log_metric("loss_classifier_sr", loss.cpu().detach(), step=step)
 
     def dis_update(self, x_a, x_b, hyperparameters, comet_exp=None, s_a=None, s_b=None):
         """One discriminator update (trainer.py:1133-1186)."""

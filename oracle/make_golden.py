@@ -120,11 +120,41 @@ def nets_fixture():
     print("nets.pt ok")
 
 
-def step_fixture(tag, optimizer, gen_state, guided, hw, b, n_steps, masked_synth=False):
+def classifier_fixture():
+    """domainClassifier (utils.py:1370-1392) forward / backward in train mode (BatchNorm batch statistics + running
+    update), then an eval-mode forward on the updated running statistics."""
+    ref_loader.load()
+    import utils as ref_utils
+
+    sd = O.init_classifier_state_dict(31)
+    m = ref_utils.domainClassifier(256)
+    m.load_state_dict(sd)
+    m.train()
+    g = torch.Generator().manual_seed(32)
+    x = (torch.randn(2, 256, 64, 64, generator=g) * 1.5).requires_grad_(True)
+    y = m(x)
+    gy = torch.randn(y.shape, generator=g)
+    y.backward(gy)
+    after = {k: v.detach().clone() for k, v in m.state_dict().items() if "running" in k or "tracked" in k}
+    grads = {n: p_.grad.clone() if p_.numel() <= 4096 else summarize(p_.grad, 256) for n, p_ in m.named_parameters()}
+    m.eval()
+    with torch.no_grad():
+        y_eval = m(x.detach())
+    fx = dict(seed=31, x_seed=32, y=y.detach().clone(), gy=gy, gx=summarize(x.grad, 1024), gx_absmax=float(x.grad.abs().max()),
+              grads=grads, running_after=after, y_eval=y_eval.clone())
+    torch.save(fx, os.path.join(OUT, "classifier.pt"))
+    print("classifier.pt ok", y.detach().reshape(-1), y_eval.reshape(-1))
+
+
+def step_fixture(tag, optimizer, gen_state, guided, hw, b, n_steps, masked_synth=False, adaptation=False):
     """dis_update + gen_update on the shimmed reference trainer (trainer.py:336-561,1133-1186).  masked_synth:
-    recon_mask = 1 with masks and synth=True with recon_synth_w > 0 (trainer.py:452-488)."""
+    recon_mask = 1 with masks and synth=True with recon_synth_w > 0 (trainer.py:452-488).  adaptation: the
+    config_256 values adaptation.adv_lambda = 6, dfeat_lambda = 1 (content-feature classifiers, trainer.py:162-179,
+    521-525) and one domain_classifier_sr_update (trainer.py:1237-1265) after gen_update, as train.py:193-207."""
     cfg = O.config_256_core(optimizer=optimizer, gen_state=gen_state, guided=guided,
                             crop_image_height=hw, crop_image_width=hw)
+    if adaptation:
+        cfg["adaptation"].update(adv_lambda=6, dfeat_lambda=1)
     if masked_synth:
         cfg["recon_mask"], cfg["recon_synth_w"] = 1, 5
         torch.cuda.FloatTensor = torch.FloatTensor  # shim 3: trainer.py:456 casts the alignment mask to a CUDA type
@@ -140,6 +170,9 @@ def step_fixture(tag, optimizer, gen_state, guided, hw, b, n_steps, masked_synth
         t.gen_b.load_state_dict(gb)
     t.dis_a.load_state_dict(O.init_state_dict(O.dis_spec(cfg["dis"], 3), 23, "gaussian"))
     t.dis_b.load_state_dict(O.init_state_dict(O.dis_spec(cfg["dis"], 3), 24, "gaussian"))
+    if adaptation:
+        t.domain_classifier_sr_a.load_state_dict(O.init_classifier_state_dict(25))
+        t.domain_classifier_sr_b.load_state_dict(O.init_classifier_state_dict(26))
     x_a, x_b = seeded_images(1234, b, hw, hw)
     mask_a = mask_b = None
     if masked_synth:
@@ -149,6 +182,14 @@ def step_fixture(tag, optimizer, gen_state, guided, hw, b, n_steps, masked_synth
     for it in range(n_steps):
         t.iterations = it
         t.update_learning_rate()
+        extra = {}
+        if adaptation:
+            # (train.py:193-207 runs this after gen_update; here it goes first so that the classifier update is
+            # pinned on the initial generator and not on weights that carry Adam's sign-amplified fp noise)
+            t.domain_classifier_sr_update(x_a, x_b, False, cfg["adaptation"]["dfeat_lambda"], it + 1)
+            cls = {"a": t.domain_classifier_sr_a, "b": t.domain_classifier_sr_b}
+            extra = dict(cls_g={f"{cn}/{n}": summarize(p.grad, 16) for cn, c in cls.items() for n, p in c.named_parameters()},
+                         cls_w={f"{cn}/{n}": summarize(p.data, 16) for cn, c in cls.items() for n, p in c.named_parameters()})
         t.dis_update(x_a, x_b, cfg)
         dis_g = {f"a/{n}": summarize(p.grad, 16) for n, p in t.dis_a.named_parameters()}
         if masked_synth:
@@ -161,10 +202,13 @@ def step_fixture(tag, optimizer, gen_state, guided, hw, b, n_steps, masked_synth
         gen_w = {f"{gn}/{n}": summarize(p.data, 16) for gn, g in gens.items() for n, p in g.named_parameters()}
         dis_w = {f"a/{n}": summarize(p.data, 16) for n, p in t.dis_a.named_parameters()}
         dis_w.update({f"b/{n}": summarize(p.data, 16) for n, p in t.dis_b.named_parameters()})
-        steps.append(dict(losses=rec, dis_grads=dis_g, gen_grads=gen_g, gen_w=gen_w, dis_w=dis_w))
+        if adaptation:
+            extra["cls_running"] = {f"{cn}/{n}": v.detach().clone() for cn, c in cls.items()
+                                    for n, v in c.state_dict().items() if "running" in n or "tracked" in n}
+        steps.append(dict(losses=rec, dis_grads=dis_g, gen_grads=gen_g, gen_w=gen_w, dis_w=dis_w, **extra))
         print(tag, it, {k: round(v, 5) for k, v in rec.items()})
-    fx = dict(cfg=cfg, seeds=dict(gen=21, gen_b=22, dis_a=23, dis_b=24, img=1234, style=99), hw=hw, b=b, steps=steps,
-              masked_synth=masked_synth)
+    fx = dict(cfg=cfg, seeds=dict(gen=21, gen_b=22, dis_a=23, dis_b=24, cls_a=25, cls_b=26, img=1234, style=99), hw=hw,
+              b=b, steps=steps, masked_synth=masked_synth, adaptation=adaptation)
     torch.save(fx, os.path.join(OUT, f"step_{tag}.pt"))
 
 
@@ -196,9 +240,15 @@ def adam_fixture():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "adaptation":  # only the fixtures of SURVEY.md 8(f).2
+        classifier_fixture()
+        step_fixture("g1_adaptation_adam", "adam", 1, 1, 256, 1, 1, adaptation=True)
+        sys.exit(0)
     layers_fixture()
     adam_fixture()
     nets_fixture()
     step_fixture("g1_guided_adam", "adam", 1, 1, 64, 2, 2)
     step_fixture("g0_sampled_extraadam", "extraadam", 0, 0, 64, 1, 2)
     step_fixture("g1_masked_synth_adam", "adam", 1, 1, 64, 2, 1, masked_synth=True)
+    classifier_fixture()
+    step_fixture("g1_adaptation_adam", "adam", 1, 1, 256, 1, 1, adaptation=True)

@@ -430,6 +430,97 @@ def l1_masked(a, b, mask):
 
 
 # --------------------------------------------------------------------------
+# domain-adaptation head (utils.py:1238-1392, trainer.py:638-667)
+# --------------------------------------------------------------------------
+def domain_classifier_spec():
+    """Parameter / buffer inventory of utils.py:1370-1392 domainClassifier(256) (state_dict order)."""
+    spec = []
+    for blk, cin, cout in (("BasicBlock1.", 256, 128), ("BasicBlock2.", 128, 64)):
+        spec.append((blk + "conv1.weight", (cout, cin, 3, 3)))
+        spec += _bn_spec(blk + "bn1.", cout)
+        spec.append((blk + "conv2.weight", (cout, cout, 3, 3)))
+        spec += _bn_spec(blk + "bn2.", cout)
+        spec.append((blk + "downsample.0.weight", (cout, cin, 1, 1)))
+        spec += _bn_spec(blk + "downsample.1.", cout)
+    spec += [("fc.weight", (1, 64)), ("fc.bias", (1,))]
+    return spec
+
+
+def _bn_spec(p, c):
+    return [(p + "weight", (c,)), (p + "bias", (c,)), (p + "running_mean", (c,)), (p + "running_var", (c,)),
+            (p + "num_batches_tracked", ())]
+
+
+def init_classifier_state_dict(seed: int) -> SD:
+    """weights_init("gaussian") on domainClassifier (trainer.py:175-176): Conv / Linear weights N(0, 0.02), fc bias
+    0; BatchNorm keeps nn.BatchNorm2d's defaults (weight 1, bias 0, running 0 / 1) -- here gamma / beta are drawn
+    away from 1 / 0 so that the fixtures exercise them."""
+    g = torch.Generator().manual_seed(seed)
+    sd: SD = {}
+    for name, shape in domain_classifier_spec():
+        if name.endswith("num_batches_tracked"):
+            sd[name] = torch.zeros((), dtype=torch.long)
+        elif name.endswith("running_mean"):
+            sd[name] = torch.zeros(shape)
+        elif name.endswith("running_var"):
+            sd[name] = torch.ones(shape)
+        elif ".bn" in name or "downsample.1." in name:
+            sd[name] = (1.0 + 0.2 * torch.randn(shape, generator=g)) if name.endswith("weight") else 0.1 * torch.randn(shape, generator=g)
+        elif name == "fc.bias":
+            sd[name] = torch.zeros(shape)
+        else:
+            sd[name] = torch.randn(shape, generator=g) * 0.02
+    return sd
+
+
+def batch_norm(sd: SD, p: str, x, training: bool, momentum=0.1, eps=1e-5):
+    """nn.BatchNorm2d (utils.py:1300,1303,1308): training -> per-channel mean / *biased* variance over (N,H,W),
+    running statistics updated in place with the *unbiased* variance; eval -> running statistics."""
+    if training:
+        mu = x.mean(dim=(0, 2, 3))
+        var = ((x - mu.view(1, -1, 1, 1)) ** 2).mean(dim=(0, 2, 3))
+        with torch.no_grad():
+            m = x.numel() / x.shape[1]
+            sd[p + "running_mean"].mul_(1 - momentum).add_(momentum * mu.detach())
+            sd[p + "running_var"].mul_(1 - momentum).add_(momentum * var.detach() * m / max(m - 1, 1))
+            if p + "num_batches_tracked" in sd:
+                sd[p + "num_batches_tracked"] += 1
+    else:
+        mu, var = sd[p + "running_mean"], sd[p + "running_var"]
+    y = (x - mu.view(1, -1, 1, 1)) / torch.sqrt(var.view(1, -1, 1, 1) + eps)
+    return y * sd[p + "weight"].view(1, -1, 1, 1) + sd[p + "bias"].view(1, -1, 1, 1)
+
+
+def basic_block(sd: SD, p: str, x, training: bool):
+    """BasicBlock.forward utils.py:1311-1331 with the conv1x1 + bn shortcut (inplanes != planes)."""
+    out = _q(F.conv2d(x, _qw(sd[p + "conv1.weight"]), None, padding=1))
+    out = _q(torch.relu(batch_norm(sd, p + "bn1.", out, training)))
+    out = _q(F.conv2d(out, _qw(sd[p + "conv2.weight"]), None, padding=1))
+    out = _q(batch_norm(sd, p + "bn2.", out, training))
+    idn = _q(F.conv2d(x, _qw(sd[p + "downsample.0.weight"]), None))
+    idn = _q(batch_norm(sd, p + "downsample.1.", idn, training))
+    return _q(torch.relu(out + idn))
+
+
+def domain_classifier(sd: SD, x, training: bool = True):
+    """domainClassifier.forward utils.py:1380-1392: content code [N,256,64,64] -> [N,1] ([1] for N == 1)."""
+    y = F.max_pool2d(x, 2)
+    y = basic_block(sd, "BasicBlock1.", y, training)
+    y = F.max_pool2d(y, 2)
+    y = basic_block(sd, "BasicBlock2.", y, training)
+    y = F.avg_pool2d(y, (16, 16))
+    return F.linear(y.squeeze(), sd["fc.weight"], sd["fc.bias"])
+
+
+def classifier_sr_loss(sd_a: SD, sd_b: SD, c_a, c_b, domain_synth=False, fool=False, training=True):
+    """compute_classifier_sr_loss trainer.py:638-667."""
+    o_a = domain_classifier(sd_a, c_a, training)
+    o_b = domain_classifier(sd_b, c_b, training)
+    t = 0.5 if fool else (0.0 if domain_synth else 1.0)
+    return torch.mean((o_a - t) ** 2) + torch.mean((o_b - t) ** 2)
+
+
+# --------------------------------------------------------------------------
 # optimisers
 # --------------------------------------------------------------------------
 def adam_torch_step(p, g, m, v, step, lr, b1, b2, eps, wd):
@@ -506,11 +597,13 @@ class OracleTrainer:
     """Functional MUNIT_Trainer hot path: trainer.py:28-127 (setup), :336-561 (gen_update),
     :1133-1186 (dis_update).  Weights come in as state_dicts with the reference's keys."""
 
-    def __init__(self, cfg: dict, gen_sd, dis_a_sd: SD, dis_b_sd: SD):
+    def __init__(self, cfg: dict, gen_sd, dis_a_sd: SD, dis_b_sd: SD, cls_a_sd: Optional[SD] = None,
+                 cls_b_sd: Optional[SD] = None):
         self.cfg = cfg
         self.gen_state, self.guided = cfg["gen_state"], cfg["guided"]
         self.style_dim = cfg["gen"]["style_dim"]
-        req = lambda sd: {k: (v.clone().requires_grad_(True) if not k.endswith(("running_mean", "running_var")) else v.clone())
+        req = lambda sd: {k: (v.clone().requires_grad_(True)
+                              if not k.endswith(("running_mean", "running_var", "num_batches_tracked")) else v.clone())
                           for k, v in sd.items()}
         if self.gen_state == 1:
             self.gen_sd = {"": req(gen_sd)}
@@ -532,6 +625,11 @@ class OracleTrainer:
         mk = lambda ps: OracleOpt({k: v.data for k, v in ps.items()}, cfg["lr"], cfg["beta1"], cfg["beta2"],
                                   cfg["weight_decay"], extra)
         self.gen_opt, self.dis_opt = mk(self.gen_params), mk(self.dis_params)
+        self.cls_a = self.cls_b = None
+        if cls_a_sd is not None:  # trainer.py:162-179
+            self.cls_a, self.cls_b = req(cls_a_sd), req(cls_b_sd)
+            self.cls_params = flat({"a": self.cls_a, "b": self.cls_b})
+            self.cls_opt = mk(self.cls_params)
         self.iterations = 0
         self.losses: Dict[str, float] = {}
 
@@ -608,6 +706,10 @@ class OracleTrainer:
                  + cfg["recon_c_w"] * (L["loss_gen_recon_c_a"] + L["loss_gen_recon_c_b"])
                  + cfg["recon_x_cyc_w"] * (L["loss_gen_cycrecon_x_a"] + L["loss_gen_cycrecon_x_b"])
                  + cfg.get("recon_synth_w", 0) * L["loss_gen_recon_synth"])
+        adv_lambda = cfg["adaptation"].get("adv_lambda", 0)
+        if adv_lambda > 0:  # trainer.py:521-525,555
+            L["loss_classifier_sr"] = classifier_sr_loss(self.cls_a, self.cls_b, c_a, c_b, synth, fool=True)
+            total = total + adv_lambda * L["loss_classifier_sr"]
         grads = self._grads(total, self.gen_params)
         self.gen_opt.apply(grads, self.iterations)
         self.losses.update({k: float(v) for k, v in L.items()})
@@ -615,6 +717,18 @@ class OracleTrainer:
         self.gen_grads = grads
         self.last = dict(x_ab=x_ab.detach(), x_ba=x_ba.detach())
         return total.detach()
+
+    def domain_classifier_sr_update(self, x_a, x_b, domain_synth, lambda_classifier):
+        """trainer.py:1237-1265: the classifiers learn synthetic (0) / real (1) on detached content codes."""
+        with torch.no_grad():
+            c_a, _ = self.enc_a(x_a)
+            c_b, _ = self.enc_b(x_b)
+        loss = lambda_classifier * classifier_sr_loss(self.cls_a, self.cls_b, c_a, c_b, domain_synth, fool=False)
+        grads = self._grads(loss, self.cls_params)
+        self.cls_opt.apply(grads, self.iterations)
+        self.losses["loss_classifier_sr_update"] = float(loss)
+        self.cls_grads = grads
+        return loss.detach()
 
     @torch.no_grad()
     def translate(self, x_a, styles):

@@ -72,3 +72,30 @@ def test_paired_with_mask_shares_one_crop_and_flip(tmp_path):
         # wherever the pair differs the mask is set: crop and flip were applied identically to all three
         assert float((differs * (1 - mask)).sum()) == 0.0
         assert float(differs.sum()) > 0
+
+
+def test_seeded_construction_matches_reference_with_adaptation_heads():
+    """Same seed -> the reference's initial weights bit for bit, including the domain classifiers that are built
+    after the generator initialisation (trainer.py:162-179).  Needs /root/reference (build container only)."""
+    import pytest
+    import torch
+
+    from oracle import munit_oracle as O
+    from oracle import ref_loader
+
+    if not ref_loader.available():
+        pytest.skip("reference checkout not present")
+    from munit_b200.trainer import MUNIT_Trainer
+
+    cfg = O.config_256_core()
+    cfg["adaptation"].update(adv_lambda=6, dfeat_lambda=1)
+    torch.manual_seed(0)
+    rt = ref_loader.make_trainer(cfg)
+    torch.manual_seed(0)
+    ot = MUNIT_Trainer(cfg)
+    for name in ("domain_classifier_sr_a", "domain_classifier_sr_b", "gen", "dis_a"):
+        rs, os_ = getattr(rt, name).state_dict(), getattr(ot, name).state_dict()
+        assert list(rs.keys()) == list(os_.keys()), name
+        for k in rs:
+            assert torch.equal(rs[k], os_[k]), (name, k)
+    assert torch.equal(rt.s_a, ot.s_a) and torch.equal(rt.s_b, ot.s_b)

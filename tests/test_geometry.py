@@ -60,6 +60,38 @@ def test_fwd_dgrad_wgrad_plans(n, h, w, cin, cout, k, s, pad):
     assert torch.allclose(dw.view(cout, k, k, cin), wt_r.grad.permute(0, 2, 3, 1), atol=1e-2, rtol=1e-3)
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout,k,zp", [(2, 8, 8, 64, 128, 3, 1), (1, 5, 7, 128, 64, 3, 1),
+                                                  (2, 4, 4, 64, 64, 1, 0), (1, 6, 6, 64, 64, 5, 2)])
+def test_zero_padded_conv_plans(n, h, w, cin, cout, k, zp):
+    """conv3x3 / conv1x1 of the domain-classifier BasicBlock (utils.py:1238-1274): zero padding is implicit --
+    unpadded buffers, taps starting at -zp, out-of-range reads are zero (TMA fill)."""
+    torch.manual_seed(1)
+    x = torch.randn(n, cin, h, w, requires_grad=True)
+    wt = (torch.randn(cout, cin, k, k) * 0.1).requires_grad_(True)
+    y_ref = F.conv2d(x, wt, None, padding=zp)
+    gy = torch.randn_like(y_ref)
+    y_ref.backward(gy)
+    ho, wo = y_ref.shape[2:]
+    assert (ho, wo) == (h, w)
+    plan = G.plan_fwd(n, h, w, cin, k, k, 1, 1, cout, (ho * wo * cout, wo * cout, cout, 0, 0), zpad=zp)
+    wmat = wt.detach().permute(0, 2, 3, 1).reshape(cout, -1)
+    out = torch.zeros(n * ho * wo * cout)
+    E.tapgemm(plan, nhwc(x.detach()).reshape(-1), wmat, out)
+    assert torch.allclose(out.view(n, ho, wo, cout), nhwc(y_ref.detach()), atol=1e-3, rtol=1e-4)
+    ck = max(64, cout)
+    dplan = G.plan_dgrad(n, h, w, cin, k, k, 1, 1, cout, zpad=zp)
+    idx = G.dgrad_index_map(cout, cin, k, k, 1, 1, cin, ck)
+    wflat = wt.detach().permute(0, 2, 3, 1).reshape(-1)
+    wd = torch.where(idx >= 0, wflat[idx.clamp(min=0).long()], torch.zeros(())).view(cin, -1)
+    dx = torch.full((n * h * w * cin,), float("nan"))
+    E.tapgemm(dplan, nhwc(gy).reshape(-1), wd, dx)
+    assert torch.allclose(dx.view(n, h, w, cin), nhwc(x.grad), atol=1e-3, rtol=1e-4)
+    wplan = G.plan_wgrad(n, h, w, cin, k, k, 1, 1, cout, cout, k * k * cin, cin, 1, zpad=zp)
+    dw = torch.zeros(cout * k * k * cin)
+    E.wgrad(wplan, nhwc(gy).reshape(-1), nhwc(x.detach()).reshape(-1), dw)
+    assert torch.allclose(dw.view(cout, k, k, cin), wt.grad.permute(0, 2, 3, 1), atol=1e-2, rtol=1e-3)
+
+
 def test_fwd_into_padded_output():
     n, h, w, c, k, pad, po = 1, 8, 8, 64, 3, 1, 2
     x = torch.randn(n, c, h, w)
