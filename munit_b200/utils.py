@@ -1,6 +1,6 @@
 """Hot-path helpers of cc-ai/MUNIT `scripts/utils.py`: get_config (:743-758), get_scheduler (:1066-1090),
-weights_init (:1093-1115), get_model_list (:887-908).  Data loaders, FID, segmentation and domain
-classifiers are out of scope."""
+weights_init (:1093-1115), get_model_list (:887-908); conv3x3 / conv1x1 / BasicBlock / domainClassifier
+(:1238-1392) are re-exported from munit_b200.heads.  FID and segmentation are out of scope."""
 from __future__ import annotations
 
 import math
@@ -140,3 +140,6 @@ class Timer:
         import time
 
         print(self.msg % (time.time() - self.start_time))
+
+
+from .heads import BasicBlock, conv1x1, conv3x3, domainClassifier  # noqa: E402,F401  (utils.py:1238-1392)

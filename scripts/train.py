@@ -2,8 +2,9 @@
 same outputs (images/, checkpoints/, config.yaml under <output_path>/outputs/<config name>).
 
 Differences, all on the side of doing less: comet_ml is optional (absent -> no experiment logging); the
-semantic-segmentation, VGG, FID and domain-classifier branches are outside the hot path and exit
-with a message if the config enables them; the training loop also runs when semantic_w == 0 (the reference only
+semantic-segmentation, VGG, FID, domain_adv_w and output-classifier branches are outside the hot path
+and exit with a message if the config enables them (the content-feature classifiers of adaptation.adv_lambda /
+dfeat_lambda are built: train.py:193-207,261-274); the training loop also runs when semantic_w == 0 (the reference only
 loops under semantic_w != 0, train.py:159).  Masks (recon_mask: 1) and synthetic pairs (synthetic_frequency > 0)
 are supported through the list-file keys the reference uses."""
 from __future__ import print_function
@@ -40,8 +41,8 @@ def _unsupported(config):
     if config.get("eval_fid", 0) > 0:
         off.append("eval_fid")
     ad = config.get("adaptation", {})
-    if any(ad.get(k, 0) for k in ("adv_lambda", "output_adv_lambda", "sem_seg_lambda", "dfeat_lambda")):
-        off.append("adaptation.* heads")
+    if any(ad.get(k, 0) for k in ("output_adv_lambda", "output_classifier_lambda", "sem_seg_lambda")):
+        off.append("adaptation.output_* / sem_seg_lambda heads")
     return off
 
 
@@ -119,6 +120,12 @@ def main(argv=None):
                 trainer.dis_update(images_a, images_b, config, comet_exp)
                 if (iterations + 1) % ratio == 0:
                     trainer.gen_update(images_a, images_b, config, mask_a, mask_b, comet_exp)
+                # content-feature classifier update on real pairs (train.py:193-207)
+                classif_now = (trainer.use_classifier_sr
+                               and (iterations + 1) % config["adaptation"]["classif_frequency"] == 0)
+                if classif_now:
+                    trainer.domain_classifier_sr_update(images_a, images_b, False, config["adaptation"]["dfeat_lambda"],
+                                                        iterations + 1, comet_exp)
                 if synth_iter is not None and iterations % config["synthetic_frequency"] == 0:
                     try:
                         images_as, images_bs, mask_s = next(synth_iter)
@@ -128,6 +135,9 @@ def main(argv=None):
                     images_as, images_bs, mask_s = images_as.cuda(), images_bs.cuda(), mask_s.cuda()
                     trainer.dis_update(images_as, images_bs, config, comet_exp)
                     trainer.gen_update(images_as, images_bs, config, mask_s, mask_s, comet_exp, True)
+                    if classif_now:  # ... and on the synthetic pair (train.py:261-274)
+                        trainer.domain_classifier_sr_update(images_as, images_bs, True,
+                                                            config["adaptation"]["dfeat_lambda"], iterations + 1, comet_exp)
                 torch.cuda.synchronize()
             if (iterations + 1) % config["image_save_iter"] == 0:
                 with torch.no_grad():

@@ -43,8 +43,11 @@ def test_graph_replay_matches_eager(optimizer):
     le, ge, de = _run("eager", optimizer=optimizer)
     for mode in ("graph", "graph2", "graph3"):  # one stream; two branches; two branches + wgrad companion streams
         lg, gg, dg = _run(mode, optimizer=optimizer)
+        pre = 2 if optimizer == "extraadam" else 1
         for i, ((a, b), (c, d)) in enumerate(zip(le, lg)):
-            tol = 5e-3 * (1 + 2 * i)  # runs drift apart (fp32-atomic order noise amplified by bf16 storage)
+            # runs drift apart step by step (fp32-atomic order noise amplified by bf16 storage); the
+            # compared losses start after `pre` un-compared steps (measured: 0.53 % on the third ExtraAdam step)
+            tol = 5e-3 * (1 + 2 * (i + pre - 1))
             assert abs(a - c) <= tol * abs(a) and abs(b - d) <= tol * abs(b), (mode, le, lg)
         # weights: split-K wgrad uses fp32 atomics, so two runs differ by ~1e-7 relative in the gradients; bf16
         # storage amplifies that to percent-level gradient differences within a step or two, so

@@ -114,3 +114,33 @@ def test_train_script_masks_and_synthetic_pairs(tmp_path):
     cfg_path = _config(tmp, **over)
     assert main(["--config", cfg_path, "--output_path", tmp]) == 2
     assert os.path.isfile(os.path.join(tmp, "outputs", "tiny", "checkpoints", "gen_00000002.pt"))
+
+
+def test_train_script_adaptation_heads(tmp_path):
+    """config_256's adaptation terms (adv_lambda 6, dfeat_lambda 1) through the training loop at 256x256: the
+    classifier-fooling loss in gen_update and a domain_classifier_sr_update every `classif_frequency` iterations
+    (train.py:193-207)."""
+    tmp = str(tmp_path)
+    for k, split in enumerate(("trainA", "trainB", "testA", "testB")):
+        _images(os.path.join(tmp, "data", split), 2, 20 + k, size=(272, 264))
+    cfg = O.config_256_core()
+    cfg["adaptation"].update(adv_lambda=6, dfeat_lambda=1, classif_frequency=1)
+    main = _train_main()
+    cfg_path = _config(tmp, crop_image_height=256, crop_image_width=256, new_size=256, adaptation=cfg["adaptation"],
+                       ratio_disc_gen=1, max_iter=2, image_save_iter=100, snapshot_save_iter=100)
+    import munit_b200.trainer as T
+
+    seen = []
+    orig = T.MUNIT_Trainer.domain_classifier_sr_update
+
+    def spy(self, *a, **k):
+        out = orig(self, *a, **k)
+        seen.append((float(self.loss_classifier_sr_update), float(self.loss_classifier_sr)))
+        return out
+
+    T.MUNIT_Trainer.domain_classifier_sr_update = spy
+    try:
+        assert main(["--config", cfg_path, "--output_path", tmp]) == 2
+    finally:
+        T.MUNIT_Trainer.domain_classifier_sr_update = orig
+    assert len(seen) == 2 and all(np.isfinite(v) for pair in seen for v in pair), seen
