@@ -324,6 +324,11 @@ def run_b200(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(tt[0]), float(tt[1])
     prof = profile_tensor_kernels(runner)
+    overlap_note = (sum(len(g.buckets) for g in trainer.grad_sync.values()),
+                    sum(g.early_pass for g in trainer.grad_sync.values()), runner.overlap)
+    if world > 1:
+        runner.release()  # captured graphs reference the communicator: drop them before the process group goes
+        dist.barrier()
     dom_us, dom_tf = dominant_launch_time(args.batch) if rank == 0 else (0.0, 0.0)
     if rank == 0 and args.dump_launches:
         json.dump(prof["detail"], open(args.dump_launches, "w"))
@@ -349,6 +354,11 @@ def run_b200(args):
         config=dict(workload=workload_name(args.batch, hw, args.hd),
                     global_batch=args.batch * world, gen_state=cfg["gen_state"], guided=cfg["guided"],
                     optimizer=cfg["optimizer"], parallelism=f"dp{world}", cuda_graph=not args.no_graph, two_streams=bool(args.two_streams),
+                    grad_exchange=("none (1 GPU)" if world == 1 else
+                                   ("NCCL all-reduce per ready bucket, overlapped with backward, captured in the step graph "
+                                    f"({overlap_note[0]} buckets, {overlap_note[1]} launched before the end "
+                                    "of their backward pass)"
+                                    if overlap_note[2] else "NCCL all-reduce of the whole arena between three captured segments")),
                     l2="per-step working set (several GB of bf16 activations) >> 126 MB L2; no explicit flush"),
         e2e=dict(value=e2e_per_s, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=8,
                  last_losses=dict(dis=last[0], gen=last[1])),

@@ -1,8 +1,9 @@
 """Step runner: one MUNIT training step (dis_update + gen_update, train.py:182-187) executed as CUDA
 graph replays -- a step issues ~2000 kernels, so Python launch overhead would otherwise dominate at
 B = 8 -- and batch data parallelism: one process per GPU, replicated weights, gradients of the flat
-arenas summed with NCCL all-reduce (torch.distributed) between the captured segments, the 1/world scale
-fused into the Adam kernel.  All norms are per-sample and every loss is a batch mean, so sharding the
+arenas summed with NCCL all-reduce (torch.distributed) bucket by bucket as the backward pass completes them
+(dp.GradSync, captured into the graph; MUNIT_DP_OVERLAP=0: whole arenas between three captured segments), the
+1/world scale fused into the Adam kernel.  All norms are per-sample and every loss is a batch mean, so sharding the
 batch and averaging gradients equals the single-GPU large-batch step."""
 from __future__ import annotations
 
@@ -11,7 +12,9 @@ from typing import Dict, Optional
 import torch
 import torch.distributed as dist
 
-from . import _lib, dp
+import os
+
+from . import _lib, dp, ops
 
 
 class StepRunner:
@@ -40,6 +43,20 @@ class StepRunner:
             opt.build_arena()
             opt.enable_graph_hyper()
             opt.grad_scale = 1.0 / world
+        # Gradient exchange.  Default for world > 1: dp.GradSync -- each bucket of a gradient arena is all-reduced
+        # as soon as the backward pass has completed it, overlapped with the remaining dgrad / wgrad kernels, and
+        # the collectives are captured into the step's CUDA graph.  MUNIT_DP_OVERLAP=0: the whole arena is reduced
+        # between three captured segments (no NCCL inside a capture).
+        self.overlap = world > 1 and os.environ.get("MUNIT_DP_OVERLAP", "1") != "0"
+        ops.SYNCS.clear()
+        trainer.grad_sync = {}
+        if self.overlap:
+            dp._wgrad_streams = ops._active_wgrad_streams
+            bb = int(float(os.environ.get("MUNIT_DP_BUCKET_MB", "25")) * (1 << 20))
+            for name, opt in (("dis", trainer.dis_opt), ("gen", trainer.gen_opt)):
+                gs = dp.GradSync(opt.g_arena, opt.slices, bucket_bytes=bb)
+                trainer.grad_sync[name] = gs
+                ops.SYNCS.append(gs)
         self.iter = 0
         # Warm-up and capture share ONE side stream: autograd grad-accumulator nodes remember the stream
         # they were created on, and a node surviving from warm-up on another stream would make the
@@ -60,7 +77,7 @@ class StepRunner:
         self.t.gen_opt_step()
 
     def _allreduce(self, opt):
-        if self.world > 1:
+        if self.world > 1 and not self.overlap:
             dp.allreduce_arena(opt.g_arena)
 
     def _eager_step(self):
@@ -86,13 +103,16 @@ class StepRunner:
         if self.extra:  # python-side flag ExtraAdam.step() checks; device state is untouched by capture
             for o in (self.t.dis_opt, self.t.gen_opt):
                 o._have_copy = parity == 1
-        segs = [self._seg_dis, self._seg_mid, self._seg_end] if self.world > 1 else [self._eager_step]
+        split = self.world > 1 and not self.overlap
+        segs = [self._seg_dis, self._seg_mid, self._seg_end] if split else [self._eager_step]
         graphs = []
         pool = None
         before = _lib.launches
+        # captured NCCL collectives: the process group's watchdog thread may touch CUDA while this thread captures
+        mode = "thread_local" if self.overlap else "global"
         for fn in segs:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool, stream=self.stream):
+            with torch.cuda.graph(g, pool=pool, stream=self.stream, capture_error_mode=mode):
                 fn()
             pool = g.pool()
             graphs.append(g)
@@ -145,7 +165,7 @@ class StepRunner:
         else:
             graphs = self.graphs[self.iter % 2 if self.extra else 0]
             t = self.t
-            if self.world > 1:
+            if len(graphs) == 3:
                 graphs[0].replay()
                 self._allreduce(t.dis_opt)
                 graphs[1].replay()
@@ -160,6 +180,17 @@ class StepRunner:
                 if self.extra:
                     opt._have_copy = (self.iter % 2 == 0)
         self._advance()
+
+    def release(self):
+        """Drop the captured graphs (they hold references to the NCCL communicator's kernels: destroy them before
+        torch.distributed.destroy_process_group(), which otherwise waits on them at exit)."""
+        import gc
+
+        torch.cuda.synchronize()
+        self.graphs.clear()
+        self.loss_refs.clear()
+        gc.collect()
+        torch.cuda.synchronize()
 
     def load_inputs(self, x_a, x_b, s_a, s_b, s_a2, s_b2):
         """Host (pinned) -> device copies of one step's inputs: images and the four style-code draws

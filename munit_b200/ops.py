@@ -62,6 +62,33 @@ def wgrad_join():
     WG.keep.clear()
 
 
+# Data-parallel gradient synchronisation (dp.GradSync instances, one per optimiser arena): Functions that own
+# parameters report their uses (forward) and the completion of their gradient launches (backward), so that a
+# bucket of the flat gradient arena can be all-reduced as soon as it is final -- overlapped with the rest of the
+# backward pass.  Empty list = single GPU, zero overhead.
+SYNCS: list = []
+
+
+def _track_use(ctx, needs, *bufs):
+    """Forward: remember which pre-allocated gradient buffers the backward of this node will complete."""
+    ctx.tracked = ()
+    if SYNCS and needs:
+        ctx.tracked = tuple(b for b in bufs if b is not None)
+        for b in ctx.tracked:
+            for s in SYNCS:
+                s.note_use(b)
+
+
+def _track_done(ctx):
+    for b in getattr(ctx, "tracked", ()):
+        for s in SYNCS:
+            s.note_done(b)
+
+
+def _active_wgrad_streams():
+    return list(WG.active)
+
+
 # Normalisation statistics in the conv epilogue (no separate pass over the conv output); MUNIT_EPI_STATS=0 restores
 # the stand-alone statistics kernel.
 EPI_STATS = os.environ.get("MUNIT_EPI_STATS", "0") != "0"
@@ -254,6 +281,7 @@ class ConvFn(torch.autograd.Function):
         ctx.layer, ctx.act, ctx.out_pad, ctx.image_pad = layer, act, out_pad, image_pad
         ctx.has_bias = bias is not None
         ctx.wbuf, ctx.bbuf = _param_grad_buf(weight), _param_grad_buf(bias)
+        _track_use(ctx, ctx.needs_input_grad[1], ctx.wbuf, ctx.bbuf)
         ctx.save_for_backward(gemm_in, out, weight)
         if stats_kind:
             ctx.mark_non_differentiable(part)
@@ -304,6 +332,7 @@ class ConvFn(torch.autograd.Function):
             else:
                 run()
             gw = None if buf is not None else tgt
+        _track_done(ctx)
         return gx, gw, gb, None, None, None, None, None
 
 
@@ -323,6 +352,7 @@ class ConvOutFn(torch.autograd.Function):
         ctx.layer, ctx.act = layer, act
         ctx.wbuf, ctx.bbuf = _param_grad_buf(weight), _param_grad_buf(bias)
         ctx.has_bias = bias is not None
+        _track_use(ctx, ctx.needs_input_grad[1], ctx.wbuf, ctx.bbuf)
         ctx.save_for_backward(x, out, weight)
         return out
 
@@ -354,6 +384,7 @@ class ConvOutFn(torch.autograd.Function):
             else:
                 run()
             gw = None if ctx.wbuf is not None else tgt
+        _track_done(ctx)
         return gx, gw, gb, None, None
 
 
@@ -374,6 +405,7 @@ class NormFn(torch.autograd.Function):
         out, coef = K.norm_fwd(y, mode, p_w, p_b, ldw, eps, relu, residual, res_pad, out_pad, upsample, part)
         ctx.cfg = (mode, relu, res_pad, out_pad, upsample, eps, ldw, residual is not None)
         ctx.wbuf, ctx.bbuf = _param_grad_buf(p_w), _param_grad_buf(p_b)
+        _track_use(ctx, mode == "ln" and ctx.needs_input_grad[1], ctx.wbuf, ctx.bbuf)
         ctx.save_for_backward(y, coef, p_w)
         return out
 
@@ -396,6 +428,7 @@ class NormFn(torch.autograd.Function):
             ret_b = None if ctx.bbuf is not None else g_b
         dy, g_res = K.norm_bwd(g_out.contiguous(), out_pad, upsample, y, coef, relu, mode, p_w, ldw, g_w, g_b, ldg,
                                has_res and ctx.needs_input_grad[3], res_pad, eps)
+        _track_done(ctx)
         return dy, ret_w, ret_b, g_res, None, None, None, None, None, None, None
 
 
@@ -497,6 +530,7 @@ class LinearFn(torch.autograd.Function):
         y = K.linear_fwd(x, weight, bias, relu)
         ctx.relu = relu
         ctx.wbuf, ctx.bbuf = _param_grad_buf(weight), _param_grad_buf(bias)
+        _track_use(ctx, ctx.needs_input_grad[1], ctx.wbuf, ctx.bbuf)
         ctx.save_for_backward(x, weight, y)
         return y
 
@@ -510,6 +544,7 @@ class LinearFn(torch.autograd.Function):
             db = ctx.bbuf if ctx.bbuf is not None else torch.zeros(weight.shape[0], dtype=torch.float32,
                                                                       device=x.device)
         dx = K.linear_bwd(x, weight, y, gy.contiguous(), ctx.relu, ctx.needs_input_grad[0], dw, db)
+        _track_done(ctx)
         return (dx, None if (not need_w or ctx.wbuf is not None) else dw,
                 None if (not need_w or ctx.bbuf is not None) else db, None)
 
@@ -539,6 +574,7 @@ class DisHeadFn(torch.autograd.Function):
         out = K.dis_head_fwd(t.contiguous(), wv, bias, target, loss, scale)
         ctx.cfg = (target, scale)
         ctx.wbuf, ctx.bbuf = _param_grad_buf(weight), _param_grad_buf(bias)
+        _track_use(ctx, ctx.needs_input_grad[1], ctx.wbuf, ctx.bbuf)
         ctx.save_for_backward(t, weight, out)
         omap = out.view(n, 1, h, w)
         ctx.mark_non_differentiable(omap)
@@ -555,6 +591,7 @@ class DisHeadFn(torch.autograd.Function):
             db = ctx.bbuf if ctx.bbuf is not None else torch.zeros(1, dtype=torch.float32, device=t.device)
         dy = K.dis_head_bwd(t, weight.reshape(-1).contiguous(), out, target, g_loss.contiguous(), scale,
                             dw.view(-1) if dw is not None else None, db)
+        _track_done(ctx)
         return (dy if ctx.needs_input_grad[0] else None,
                 None if (not need_w or ctx.wbuf is not None) else dw,
                 None if (not need_w or ctx.bbuf is not None) else db, None, None)

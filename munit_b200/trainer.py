@@ -114,6 +114,9 @@ class MUNIT_Trainer(nn.Module):
         # Two-stream mode (set by engine.StepRunner under CUDA-graph capture): the domain-a and domain-b branches
         # of a step are independent for long stretches; forking them onto two streams gives the captured graph
         # parallel branches, which fills partial waves and hides launch latency of the many small kernels.
+        # Data parallelism: dp.GradSync per optimiser arena ("gen" / "dis"), installed by engine.StepRunner; the
+        # gradient all-reduce of a bucket starts as soon as the backward pass has completed it.
+        self.grad_sync = {}
         self.parallel_streams = False
         self.wgrad_overlap = False  # with parallel_streams: weight gradients on companion streams (ops.wgrad_async)
         self._side = None
@@ -254,6 +257,9 @@ class MUNIT_Trainer(nn.Module):
     def _gen_backward(self, x_a, x_b, hyperparameters, mask_a=None, mask_b=None, synth=False, s_a=None, s_b=None):
         """Losses + gradients of gen_update (everything up to, not including, the optimiser step)."""
         self.gen_opt.zero_grad()
+        gsync = self.grad_sync.get("gen")
+        if gsync is not None:
+            gsync.begin()
         ops.WG.enabled = bool(self.parallel_streams and self.wgrad_overlap)
         s_a, s_b = self._style_noise(x_a, x_b, s_a, s_b)
         cyc = hyperparameters["recon_x_cyc_w"] > 0
@@ -339,6 +345,8 @@ class MUNIT_Trainer(nn.Module):
             self.loss_gen_total = self.loss_gen_total + adv_lambda * self.loss_classifier_sr
         self.loss_gen_total.backward()
         self._join_side()  # backward nodes ran on their forward streams; the optimiser step waits for both
+        if gsync is not None:
+            gsync.finish()  # reduce the buckets that are still local, wait for the ones already in flight
         self._last = dict(x_ab=x_ab.detach(), x_ba=x_ba.detach())
         self._release_graph()
 
@@ -384,6 +392,9 @@ class MUNIT_Trainer(nn.Module):
     def _dis_backward(self, x_a, x_b, hyperparameters, s_a=None, s_b=None):
         """Losses + gradients of dis_update (everything up to, not including, the optimiser step)."""
         self.dis_opt.zero_grad()
+        dsync = self.grad_sync.get("dis")
+        if dsync is not None:
+            dsync.begin()
         ops.WG.enabled = bool(self.parallel_streams and self.wgrad_overlap)
         s_a, s_b = self._style_noise(x_a, x_b, s_a, s_b)
         with torch.no_grad():
@@ -401,6 +412,8 @@ class MUNIT_Trainer(nn.Module):
         self.loss_dis_total = hyperparameters["gan_w"] * self.loss_dis_a + hyperparameters["gan_w"] * self.loss_dis_b
         self.loss_dis_total.backward()
         self._join_side()
+        if dsync is not None:
+            dsync.finish()
         self._release_graph()
 
     def _release_graph(self):

@@ -51,6 +51,51 @@ def _worker(rank, world, initfile, result_q):
         ref_flat = torch.cat([t.reshape(-1) for t in g_full])
         err = float((flat - ref_flat).norm() / ref_flat.norm())
         assert err < 1e-5, err
+        # 4. readiness-driven bucketed all-reduce (dp.GradSync): buckets are whole parameters cut from the tail, a
+        #    bucket is reduced as soon as every use of every parameter in it is done, always in the same order
+        sizes = [64, 640, 128, 1280, 64, 320, 192]
+        offs, o = [], 0
+        for n in sizes:
+            offs.append((o, n))
+            o += n
+        g = torch.Generator().manual_seed(100 + rank)
+        arena = torch.randn(o, generator=g)
+        ref = arena.clone()
+        dist.all_reduce(ref)
+        gs = dp.GradSync(arena, offs, bucket_bytes=4 * 700)
+        assert gs.buckets[0][1] == o and gs.buckets[-1][0] == 0
+        assert all(a[0] == b[1] for a, b in zip(gs.buckets, gs.buckets[1:]))
+        starts = {s for s, _ in offs}
+        assert all(s in starts for s, _ in gs.buckets)  # parameters are never split
+        views = [arena[s:s + n] for s, n in offs]
+        gs.begin()
+        for v in views[:-1]:  # the last parameter is not used in this pass: its gradient (zero) is already final
+            gs.note_use(v)
+        gs.note_use(views[1])  # one parameter used twice (a weight shared by two calls)
+        order = [5, 4, 3, 1, 2, 0, 1] if rank == 0 else [4, 5, 1, 3, 2, 1, 0]  # ranks may finish in different orders
+        seen_early = []
+        for i in order:
+            gs.note_done(views[i])
+            seen_early.append(gs.launched_early)
+        # buckets: [3,4,5,6] [1,2] [0].  Rank 0 completes bucket [0] before bucket [1,2]: it is held back so that
+        # every rank issues the collectives in the same order
+        assert seen_early == ([0, 0, 1, 1, 1, 1, 3] if rank == 0 else [0, 0, 0, 1, 1, 2, 3]), seen_early
+        gs.finish()
+        assert torch.equal(arena, ref)
+        # same again with every parameter used: buckets go out during the "backward"
+        arena.copy_(torch.randn(o, generator=g))
+        ref = arena.clone()
+        dist.all_reduce(ref)
+        gs.begin()
+        for v in views:
+            gs.note_use(v)
+        for i in reversed(range(len(views))):
+            gs.note_done(views[i])
+        assert gs.launched_early == 3 + len(gs.buckets)  # (the counter is cumulative)
+        gs.finish()
+        assert torch.equal(arena, ref)
+        foreign = torch.zeros(8)
+        gs.begin(); gs.note_use(foreign); gs.note_done(foreign); gs.finish()  # buffers of other arenas are ignored
         result_q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         result_q.put((rank, repr(e)))
