@@ -194,6 +194,8 @@ def profile_tensor_kernels(runner):
         # so that every event / kernel is already queued when the device reaches it: the event pairs then bracket
         # device time only, not the Python time spent building the next launch descriptor.
         trainer.parallel_streams = False
+        from munit_b200.networks import MsImageDis
+        scale_streams, MsImageDis.scale_streams = MsImageDis.scale_streams, False
         runner._prepare_host_state()
         torch.cuda.synchronize()
         torch.cuda._sleep(int(0.5 * 1.9e9))
@@ -202,6 +204,7 @@ def profile_tensor_kernels(runner):
         torch.cuda.synchronize()
     finally:
         trainer.parallel_streams = two
+        MsImageDis.scale_streams = scale_streams
         K.tapgemm, K.wgrad = orig_t, orig_w
     out = {}
     detail = []

@@ -24,6 +24,8 @@ class StepRunner:
         gradient on a companion stream, joined before the optimizer step."""
         self.t, self.cfg, self.batch, self.hw = trainer, cfg, batch, hw
         trainer.parallel_streams = bool(two_streams and use_graph)
+        from .networks import MsImageDis
+        MsImageDis.scale_streams = bool(two_streams and use_graph) and os.environ.get("MUNIT_DIS_SCALE_STREAMS", "1") != "0"
         trainer.wgrad_overlap = bool(int(two_streams) >= 2 and use_graph)
         self.use_graph, self.world = use_graph, world
         dev = next(trainer.parameters()).device

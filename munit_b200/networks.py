@@ -560,20 +560,50 @@ class MsImageDis(nn.Module):
         cnn_x += [nn.Conv2d(dim, 1, 1, 1, 0)]
         return nn.Sequential(*cnn_x)
 
+    # Scale-parallel execution (set by the trainer together with its two-stream mode): the per-scale networks share
+    # nothing but the image pyramid, and the deeper layers of the smaller scales launch a handful of CTAs each --
+    # so the pyramid is built first and the scales run on their own streams (scale 0 on the caller's), forward and,
+    # because autograd replays nodes on their forward stream, backward.
+    scale_streams = False
+
+    def _pyramid(self, x):
+        xs = [x]
+        for _ in range(len(self.cnns) - 1):
+            xs.append(ops.AvgPoolFn.apply(xs[-1]))
+        return xs
+
+    def _fork_scales(self, fns):
+        if not MsImageDis.scale_streams or len(fns) == 1 or not torch.cuda.is_available():
+            return [f() for f in fns]
+        cur = torch.cuda.current_stream()
+        if getattr(self, "_streams", None) is None:
+            self._streams = [torch.cuda.Stream() for _ in fns[1:]]
+        for st in self._streams:
+            st.wait_stream(cur)
+        out = [fns[0]()]
+        for st, f in zip(self._streams, fns[1:]):
+            with torch.cuda.stream(st):
+                out.append(f())
+            ops.note_side_stream(st)
+        for st in self._streams:
+            cur.wait_stream(st)
+        return out
+
     def _run(self, x, target: float, frozen: bool = False):
         """Returns (per-scale maps, sum over scales of mean((out - target)^2))."""
-        outputs, loss = [], None
-        for s, model in enumerate(self.cnns):
+        def scale(model, xs):
             mods = list(model)
-            a = run_chain(mods[:-1], x, 0, frozen=frozen)
+            a = run_chain(mods[:-1], xs, 0, frozen=frozen)
             head = mods[-1]
             hw = head.weight.detach() if frozen else head.weight
             hb = head.bias.detach() if frozen else head.bias
-            omap, l = ops.DisHeadFn.apply(a.t, hw, hb, target, 1.0)
+            return ops.DisHeadFn.apply(a.t, hw, hb, target, 1.0)
+
+        res = self._fork_scales([(lambda m=m, xs=xs: scale(m, xs)) for m, xs in zip(self.cnns, self._pyramid(x))])
+        outputs, loss = [], None
+        for omap, l in res:
             outputs.append(omap)
             loss = l if loss is None else loss + l
-            if s + 1 < len(self.cnns):
-                x = ops.AvgPoolFn.apply(x)
         return outputs, loss
 
     def forward(self, x):
@@ -589,16 +619,21 @@ class MsImageDis(nn.Module):
             return (l0 + l1).squeeze(0)
         b = input_fake.shape[0]
         x = torch.cat([input_fake, input_real], 0)
-        loss = None
-        for s, model in enumerate(self.cnns):
+
+        def scale(model, xs):
             mods = list(model)
-            a = run_chain(mods[:-1], x, 0)
+            a = run_chain(mods[:-1], xs, 0)
             head = mods[-1]
+            ls = None
             for half, target in ((a.t[:b], 0.0), (a.t[b:], 1.0)):
                 _, l = ops.DisHeadFn.apply(half, head.weight, head.bias, target, 1.0)
-                loss = l if loss is None else loss + l
-            if s + 1 < len(self.cnns):
-                x = ops.AvgPoolFn.apply(x)
+                ls = l if ls is None else ls + l
+            return ls
+
+        res = self._fork_scales([(lambda m=m, xs=xs: scale(m, xs)) for m, xs in zip(self.cnns, self._pyramid(x))])
+        loss = res[0]
+        for l in res[1:]:
+            loss = loss + l
         return loss.squeeze(0)
 
     def calc_gen_loss(self, input_fake, frozen: bool = False):

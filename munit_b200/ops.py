@@ -62,6 +62,25 @@ def wgrad_join():
     WG.keep.clear()
 
 
+# Extra compute streams that received work in the current update (e.g. the discriminator's per-scale streams):
+# the trainer orders the optimizer step after them once the backward pass is over (parameter gradients are written
+# by kernels, not AccumulateGrad nodes, so autograd does not do it).
+SIDE_ACTIVE: list = []
+
+
+def note_side_stream(st):
+    if st not in SIDE_ACTIVE:
+        SIDE_ACTIVE.append(st)
+
+
+def join_side_streams():
+    if SIDE_ACTIVE:
+        cur = torch.cuda.current_stream()
+        for st in SIDE_ACTIVE:
+            cur.wait_stream(st)
+    SIDE_ACTIVE.clear()
+
+
 # Data-parallel gradient synchronisation (dp.GradSync instances, one per optimiser arena): Functions that own
 # parameters report their uses (forward) and the completion of their gradient launches (backward), so that a
 # bucket of the flat gradient arena can be all-reduced as soon as it is final -- overlapped with the rest of the

@@ -140,6 +140,7 @@ class MUNIT_Trainer(nn.Module):
     def _join_side(self):
         if self.parallel_streams and self._side is not None:
             torch.cuda.current_stream().wait_stream(self._side)
+        ops.join_side_streams()
         ops.wgrad_join()
 
     # ------------------------------------------------------------------ device
