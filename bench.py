@@ -271,7 +271,7 @@ def run_b200(args):
     torch.manual_seed(0)  # identical replicas on every rank
     trainer = MUNIT_Trainer(cfg).cuda()
     runner = StepRunner(trainer, cfg, args.batch, hw, use_graph=not args.no_graph, world=world,
-                        two_streams=args.two_streams)
+                        two_streams=args.two_streams, reuse_forward=bool(args.reuse_forward))
     x_a, x_b = synthetic_images(args.batch, hw, 1234 + rank)
     x_a_h, x_b_h = x_a.pin_memory(), x_b.pin_memory()
     sd = trainer.style_dim
@@ -332,6 +332,37 @@ def run_b200(args):
     if world > 1:
         runner.release()  # captured graphs reference the communicator: drop them before the process group goes
         dist.barrier()
+    # ---- informational: the same step with gen_update picking up dis_update's generator pass (trainer.reuse_forward)
+    reuse_line = None
+    if world == 1 and not args.reuse_forward and not args.no_graph and cfg["guided"] == 1 and cfg["gen_state"] == 1:
+        runner.release()
+        r2 = StepRunner(trainer, cfg, args.batch, hw, use_graph=True, world=1, two_streams=args.two_streams,
+                        reuse_forward=True)
+        r2.iter = runner.iter
+        r2.load_inputs(x_a_h, x_b_h, *s_host)
+        r2.warmup_and_capture(1)
+        for _ in range(args.warmup):
+            r2.step()
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            r2.step()
+        g1.record()
+        torch.cuda.synchronize()
+        ms2 = g0.elapsed_time(g1)
+        ls2 = r2.losses()
+        reuse_line = dict(value=args.steps / (ms2 / 1000.0), unit=UNIT, ms_per_step=ms2 / args.steps,
+                          gpu_launches_per_step=r2.launches_per_step,
+                          last_losses=dict(dis=float(ls2["loss_dis_total"]), gen=float(ls2["loss_gen_total"])),
+                          note="NOT the headline: same dis_update + gen_update calls with trainer.reuse_forward = True "
+                               "-- gen_update reuses the generator pass (encode x_a, x_b; decode within / across "
+                               "domains) that dis_update ran on the same batch and the same generator weights "
+                               "(guided = 1), 155 of the step's 1395 GMAC per pair are not computed twice; losses, "
+                               "gradients and both optimizer steps as in the headline run "
+                               "(tests/test_trainer_gpu.py::test_forward_reuse_between_updates_is_transparent)")
+        r2.release()
+        trainer.reuse_forward = False
     dom_us, dom_tf = dominant_launch_time(args.batch) if rank == 0 else (0.0, 0.0)
     if rank == 0 and args.dump_launches:
         json.dump(prof["detail"], open(args.dump_launches, "w"))
@@ -383,6 +414,10 @@ def run_b200(args):
                       step_frac=(algo_tflop_step / (ms / args.steps / 1000.0)) / peaks["tflops"]),
         cpu_baseline=dict(value=cpu_v, unit=UNIT, cores=os.cpu_count(), kind=cpu_kind, sample=cpu_sample),
     )
+    if reuse_line is not None:
+        line["forward_reuse"] = reuse_line
+    if args.reuse_forward:
+        line["config"]["reuse_forward"] = True
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -477,6 +512,9 @@ def main():
                     help="0: one stream; 1: domain-a / domain-b branches on two streams; 2: plus weight gradients on "
                          "companion streams")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reuse-forward", type=int, default=0,
+                    help="1: gen_update reuses the generator pass of the preceding dis_update (trainer.reuse_forward); "
+                         "the default run reports it next to the headline as `forward_reuse`")
     ap.add_argument("--workload", default="train", choices=["train", "infer"])
     ap.add_argument("--dump-launches", default="", help="write per-launch tensor-kernel timings (profile pass) to this json")
     args = ap.parse_args()

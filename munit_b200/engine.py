@@ -19,10 +19,12 @@ from . import _lib, dp, ops
 
 class StepRunner:
     def __init__(self, trainer, cfg: dict, batch: int, hw: int, use_graph: bool = True, world: int = 1,
-                 two_streams: int = 0):
+                 two_streams: int = 0, reuse_forward: bool = False):
         """two_streams: 0 one stream; 1 the two domains' branches on two streams; 2 additionally every weight
-        gradient on a companion stream, joined before the optimizer step."""
+        gradient on a companion stream, joined before the optimizer step.  reuse_forward: gen_update picks up the
+        generator pass dis_update already ran on the same batch and weights (trainer.reuse_forward)."""
         self.t, self.cfg, self.batch, self.hw = trainer, cfg, batch, hw
+        trainer.reuse_forward = bool(reuse_forward)
         trainer.parallel_streams = bool(two_streams and use_graph)
         from .networks import MsImageDis
         MsImageDis.scale_streams = bool(two_streams and use_graph) and os.environ.get("MUNIT_DIS_SCALE_STREAMS", "1") != "0"

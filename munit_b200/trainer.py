@@ -194,11 +194,12 @@ class MUNIT_Trainer(nn.Module):
             return (self.gen_a if which == "a" else self.gen_b).decode(c, s)
         return self.gen.decode(c, s, 1 if which == "a" else 2)
 
-    def _gen_forward_batched(self, x_a, x_b, s_a, s_b):
-        """The first three stages of gen_update (trainer.py:400-419) for the shared-style generator, with calls
-        that use the SAME weights on independent inputs merged into one batch: the style encoder sees [x_a; x_b]
-        and [x_ba; x_ab], each decoder sees its within-domain and cross-domain pair together.  Every norm is per
-        sample, so the results are those of the reference's one-call-per-tensor sequence."""
+    def _gen_forward_stage12(self, x_a, x_b, s_a, s_b):
+        """The first two stages of gen_update (trainer.py:400-412) for the shared-style generator -- encode both
+        images, decode within and across domains -- with calls that use the SAME weights on independent inputs
+        merged into one batch: the style encoder sees [x_a; x_b], each decoder sees its within-domain and
+        cross-domain pair together.  Every norm is per sample, so the results are those of the reference's
+        one-call-per-tensor sequence."""
         g = self.gen
         b = x_a.shape[0]
 
@@ -217,6 +218,16 @@ class MUNIT_Trainer(nn.Module):
                                      lambda: g.decode(in2, st2, 2))    # [x_b_recon; x_ab]
         x_a_recon, x_ba = out1[:b], out1[b:]
         x_b_recon, x_ab = out2[:b], out2[b:]
+        return c_a, s_a_prime, c_b, s_b_prime, x_a_recon, x_b_recon, x_ba, x_ab
+
+    def _gen_forward_batched(self, x_a, x_b, s_a, s_b, stage12=None):
+        """Stages 1-3 of gen_update (trainer.py:400-419); `stage12`: the first two stages if they were already
+        computed on the same inputs and weights (see _dis_backward)."""
+        g = self.gen
+        b = x_a.shape[0]
+        if stage12 is None:
+            stage12 = self._gen_forward_stage12(x_a, x_b, s_a, s_b)
+        c_a, s_a_prime, c_b, s_b_prime, x_a_recon, x_b_recon, x_ba, x_ab = stage12
         xre_cat = torch.cat([x_ba, x_ab], 0)
         (c_b_recon, s_re), c_a_recon = self._fork_join(
             lambda: (g.enc1_content.forward_act(x_ba, 1), g.enc_style(xre_cat)),
@@ -224,6 +235,25 @@ class MUNIT_Trainer(nn.Module):
         s_a_recon, s_b_recon = s_re[:b], s_re[b:]
         return (c_a, s_a_prime, c_b, s_b_prime, x_a_recon, x_b_recon, x_ba, x_ab, c_b_recon, s_a_recon, c_a_recon,
                 s_b_recon)
+
+    # ------------------------------------------------------------------ forward reuse between the two updates
+    # With guided == 1 the generator pass of dis_update (encode x_a, x_b; decode across domains with the encoded
+    # styles, trainer.py:1149-1165) computes exactly what the first two stages of the following gen_update compute
+    # again on the same batch with the same weights (trainer.py:400-412) -- the discriminator step in between does
+    # not touch the generator.  With `reuse_forward` set, dis_update runs those stages once *with* autograd (the
+    # reference also records them and then detaches, trainer.py:1178-1179) and keeps them; gen_update picks them
+    # up if, and only if, it is called on the same tensors (object and version) before any generator weight
+    # changed.  Results are those of the separate passes (tests/test_trainer_gpu.py); 2S+2C+2D+2M = 155 of the
+    # step's 1395 GMAC are not computed twice.
+    reuse_forward = False
+
+    def _reuse_key(self, x_a, x_b):
+        return (x_a.data_ptr(), x_a._version, tuple(x_a.shape), x_b.data_ptr(), x_b._version, tuple(x_b.shape),
+                self.gen_opt.step_count, self.gen.enc_style.model[0].conv.weight._version)
+
+    def _can_reuse(self, x_a, x_b):
+        return (self.reuse_forward and self.gen_state == 1 and self.guided == 1 and x_a.shape == x_b.shape
+                and torch.is_grad_enabled())
 
     def _style_noise(self, x_a, x_b, s_a, s_b):
         """Host-generator draws in the reference's order (trainer.py:366-367,1146-1147) unless supplied."""
@@ -257,16 +287,23 @@ class MUNIT_Trainer(nn.Module):
 
     def _gen_backward(self, x_a, x_b, hyperparameters, mask_a=None, mask_b=None, synth=False, s_a=None, s_b=None):
         """Losses + gradients of gen_update (everything up to, not including, the optimiser step)."""
-        self.gen_opt.zero_grad()
+        cache, self._fwd_cache = getattr(self, "_fwd_cache", None), None
+        stage12 = None
+        if cache is not None and self._can_reuse(x_a, x_b) and cache[0] == self._reuse_key(x_a, x_b):
+            stage12 = cache[1]  # gradients and the gradient-sync pass were opened by _dis_backward
+        del cache
         gsync = self.grad_sync.get("gen")
-        if gsync is not None:
-            gsync.begin()
+        if stage12 is None:
+            self.gen_opt.zero_grad()
+            if gsync is not None:
+                gsync.begin()
         ops.WG.enabled = bool(self.parallel_streams and self.wgrad_overlap)
         s_a, s_b = self._style_noise(x_a, x_b, s_a, s_b)
         cyc = hyperparameters["recon_x_cyc_w"] > 0
         if self.gen_state == 1 and x_a.shape == x_b.shape:
             (c_a, s_a_prime, c_b, s_b_prime, x_a_recon, x_b_recon, x_ba, x_ab, c_b_recon, s_a_recon, c_a_recon,
-             s_b_recon) = self._gen_forward_batched(x_a, x_b, s_a, s_b)
+             s_b_recon) = self._gen_forward_batched(x_a, x_b, s_a, s_b, stage12)
+            del stage12
         else:
             # encode
             c_a, s_a_prime = self._enc("a", x_a)
@@ -398,15 +435,28 @@ class MUNIT_Trainer(nn.Module):
             dsync.begin()
         ops.WG.enabled = bool(self.parallel_streams and self.wgrad_overlap)
         s_a, s_b = self._style_noise(x_a, x_b, s_a, s_b)
-        with torch.no_grad():
-            (c_a, s_a_prime), (c_b, s_b_prime) = self._fork_join(lambda: self._enc("a", x_a), lambda: self._enc("b", x_b))
-            if self.guided == 0:
-                sty_a, sty_b = s_a, s_b
-            elif self.guided == 1:
-                sty_a, sty_b = s_a_prime, s_b_prime
-            else:
-                print("self.guided unknown value:", self.guided)
-            x_ba, x_ab = self._fork_join(lambda: self._dec("a", c_b, sty_a), lambda: self._dec("b", c_a, sty_b))
+        self._fwd_cache = None
+        if self._can_reuse(x_a, x_b):
+            # generator pass shared with the gen_update that follows (see reuse_forward above)
+            self.gen_opt.zero_grad()
+            gsync = self.grad_sync.get("gen")
+            if gsync is not None:
+                gsync.begin()
+            stage12 = self._gen_forward_stage12(x_a, x_b, s_a, s_b)
+            x_ba, x_ab = stage12[6], stage12[7]
+            self._fwd_cache = (self._reuse_key(x_a, x_b), stage12)
+            del stage12
+        else:
+            with torch.no_grad():
+                (c_a, s_a_prime), (c_b, s_b_prime) = self._fork_join(lambda: self._enc("a", x_a),
+                                                                     lambda: self._enc("b", x_b))
+                if self.guided == 0:
+                    sty_a, sty_b = s_a, s_b
+                elif self.guided == 1:
+                    sty_a, sty_b = s_a_prime, s_b_prime
+                else:
+                    print("self.guided unknown value:", self.guided)
+                x_ba, x_ab = self._fork_join(lambda: self._dec("a", c_b, sty_a), lambda: self._dec("b", c_a, sty_b))
         # D loss
         self.loss_dis_a, self.loss_dis_b = self._fork_join(lambda: self.dis_a.calc_dis_loss(x_ba.detach(), x_a),
                                                            lambda: self.dis_b.calc_dis_loss(x_ab.detach(), x_b))

@@ -104,6 +104,68 @@ def test_training_steps_vs_reference(golden, tag):
     print(tag, "loss rel err worst:", {k: round(v, 4) for k, v in worst.items()})
 
 
+@pytest.mark.parametrize("optimizer,gan_w", [("adam", 3), ("extraadam", 3), ("adam", 0)])
+def test_forward_reuse_between_updates_is_transparent(optimizer, gan_w, monkeypatch):
+    """trainer.reuse_forward: gen_update picks up the generator pass of the dis_update that preceded it on the same
+    batch (guided == 1).  Same losses, same gradients, same weights as the separate passes; and no reuse when the
+    batch or the generator weights changed in between."""
+    from munit_b200.trainer import MUNIT_Trainer
+
+    from munit_b200 import kernels as K
+
+    # split-K launches (fp32 atomics; picked for the few-tile layers of this 64x64 test) are the one source of
+    # run-to-run noise in the forward pass; without them the comparison below is exact up to the 1e-7 atomics of wgrad
+    monkeypatch.setattr(K, "_AUTO_KSPLIT", False)
+    cfg = O.config_256_core(optimizer=optimizer, gan_w=gan_w)
+    xa, xb = [v.cuda() for v in _images(9, 2, 64)]
+    out = {}
+    for reuse in (False, True):
+        torch.manual_seed(3)
+        t = MUNIT_Trainer(cfg).cuda()
+        t.reuse_forward = reuse
+        torch.manual_seed(11)
+        rec = []
+        for it in range(2):
+            t.iterations = it
+            t.dis_update(xa, xb, cfg)
+            assert (getattr(t, "_fwd_cache", None) is not None) == reuse
+            t.gen_update(xa, xb, cfg)
+            assert getattr(t, "_fwd_cache", None) is None
+            rec.append({k: float(getattr(t, k)) for k in ("loss_dis_total", "loss_gen_total", "loss_gen_recon_x_a",
+                                                          "loss_gen_adv_a", "loss_gen_cycrecon_x_b")})
+            if it == 0:
+                g_first = t.gen_opt.g_arena.clone()
+        torch.cuda.synchronize()
+        out[reuse] = (rec, g_first, t.gen_opt.p_arena.clone(), t.dis_opt.p_arena.clone(), t.gen_opt.g_arena.clone())
+    for it, (a, b) in enumerate(zip(out[False][0], out[True][0])):
+        for k in a:
+            tol = 1e-5 if it == 0 else 1e-2  # second update: runs have drifted apart (see below)
+            assert abs(a[k] - b[k]) <= tol * abs(a[k]) + 1e-5, (it, k, a[k], b[k])
+    # first update: same weights on both sides -> forward bitwise equal, gradients equal up to wgrad's atomic-order
+    # noise (measured cosine 1.0000001); after it the +-lr sign noise of Adam's first step separates any two runs
+    # (DESIGN.md s4), so the second update is held by its losses
+    cos = lambda u, v: float(torch.dot(u, v) / (u.norm() * v.norm()))
+    print("forward reuse: gradient cosine first / second update:", cos(out[False][1], out[True][1]),
+          cos(out[False][4], out[True][4]))
+    assert cos(out[False][1], out[True][1]) > 0.99999
+    assert float((out[False][2] - out[True][2]).abs().max()) <= 2.5 * cfg["lr"] * 2
+    assert float((out[False][3] - out[True][3]).abs().max()) <= 2.5 * cfg["lr"] * 2
+    # a different batch in between -> the stale pass must not be picked up
+    torch.manual_seed(3)
+    t = MUNIT_Trainer(cfg).cuda()
+    t.reuse_forward = True
+    t.iterations = 0
+    t.dis_update(xa, xb, cfg)
+    xc = xa.flip(0).contiguous()
+    t.gen_update(xc, xb, cfg)          # other tensor: falls back to its own forward
+    torch.manual_seed(3)               # (the same sequence without reuse)
+    t2 = MUNIT_Trainer(cfg).cuda()
+    t2.iterations = 0
+    t2.dis_update(xa, xb, cfg)
+    t2.gen_update(xc, xb, cfg)
+    assert abs(float(t.loss_gen_recon_x_a) - float(t2.loss_gen_recon_x_a)) <= 2e-3 * abs(float(t2.loss_gen_recon_x_a))
+
+
 def test_state_dict_roundtrip_and_checkpoint(tmp_path):
     from munit_b200.trainer import MUNIT_Trainer
 
