@@ -75,6 +75,9 @@ def main(argv=None):
     config.setdefault("recon_mask", 0)
     trainer = MUNIT_Trainer(config)
     trainer.cuda()
+    # opt-in extension key (not in the reference's configs): gen_update reuses the generator pass of the dis_update
+    # that preceded it on the same batch (exactly transparent; pays off when ratio_disc_gen == 1 and guided == 1)
+    trainer.reuse_forward = bool(config.get("reuse_forward", 0))
     train_loader_a, train_loader_b, test_loader_a, test_loader_b = D.get_all_data_loaders(config)
     synthetic_loader = None
     if config.get("synthetic_frequency", 0) > 0:
