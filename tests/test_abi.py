@@ -37,3 +37,25 @@ def test_no_fallback_without_gpu():
         pytest.skip("GPU present")
     with pytest.raises(_lib.MunitError):
         _lib.check(_lib.lib.munit_init(), "munit_init")
+
+
+def test_product_path_never_touches_the_oracle():
+    """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline / reference
+    arm may import it.  The package and the drop-in scripts must not (a product path that routes through the CPU
+    restatement would void every parity claim)."""
+    import glob
+
+    offenders = []
+    files = glob.glob(os.path.join(ROOT, "munit_b200", "**", "*.py"), recursive=True)
+    files += glob.glob(os.path.join(ROOT, "scripts", "*.py"))
+    for path in files:
+        src = open(path).read()
+        if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M) or "munit_oracle" in src or "ref_loader" in src:
+            offenders.append(os.path.relpath(path, ROOT))
+    assert not offenders, offenders
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    # bench.py: every oracle import sits inside the CPU-baseline / reference-arm function
+    for m in re.finditer(r"^(\s*)from oracle import", bench, flags=re.M):
+        assert len(m.group(1)) >= 4, "oracle import at module level of bench.py"
+    before = bench[: bench.index("from oracle import")]
+    assert "def cpu_reference_steps" in before, "oracle import outside cpu_reference_steps"
