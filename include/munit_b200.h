@@ -331,6 +331,10 @@ int munit_bn_finalize(const float* stats, int splits, const float* shift, int n_
 int munit_bn_bwd_finalize(const float* sums, int splits, int n_total, int n0, int n_local, const float* gamma,
                           const float* rinv, int training, float* ca, float* cb, float* cc, float* g_gamma,
                           float* g_beta, int hw, int c, void* stream);
+/* Replicate (clamp-to-edge) halo of width pad around the interior of act [N][H+2P][W+2P][C], in place: the input
+ * layout of the phase form of nn.Upsample(2) + ReflectionPad2d(2) + 5x5 conv (networks.py:534-545; experimental,
+ * geometry.plan_upconv_phases). */
+int munit_halo_fill_replicate(void* act, int n, int h, int w, int c, int pad, void* stream);
 /* out = relu(a + b), n bf16 elements (BasicBlock.forward residual tail, utils.py:1327-1329). */
 int munit_add_relu(const void* a, const void* b, void* out, int64_t n, void* stream);
 /* loss = scale * sum((x - target)^2) over n fp32 values (compute_classifier_sr_loss, trainer.py:658-667);

@@ -118,6 +118,7 @@ _SIGS = {
     "munit_maxpool2_bwd": ([_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp], C.c_int),
     "munit_bn_finalize": ([_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _vp, _vp, _i, _i, _vp], C.c_int),
     "munit_bn_bwd_finalize": ([_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp], C.c_int),
+    "munit_halo_fill_replicate": ([_vp, _i, _i, _i, _i, _i, _vp], C.c_int),
     "munit_add_relu": ([_vp, _vp, _vp, _i64, _vp], C.c_int),
     "munit_mse_const_fwd": ([_vp, _f, _vp, _f, _i, _vp], C.c_int),
     "munit_mse_const_bwd": ([_vp, _f, _vp, _f, _vp, _i, _vp], C.c_int),

@@ -336,3 +336,75 @@ def rspace_index_maps(cout, cin, kh, kw, kwp=8, cop=4, ck=64):
     m = fwd >= 0
     inv[fwd[m].long()] = torch.arange(fwd.numel(), dtype=torch.int32)[m]
     return fwd, dg.reshape(-1), inv
+
+
+# ---------------------------------------------------------------------------- nearest-2x upsample + 5x5 conv as phase GEMMs
+# nn.Upsample(scale_factor=2) -> ReflectionPad2d(2) -> Conv2d(k=5) (networks.py:534-545) reads every low-res pixel four
+# times.  Per axis, output row 2i sees the low-res rows (i-1, i, i+1) with the tap sums (w0+w1, w2+w3, w4), row 2i+1
+# sees them with (w0, w1+w2, w3+w4): four 3x3 "phase" convolutions on the low-res input, 9 MACs per output instead of
+# 25.  With *replicate* padding of the low-res input this equals reflect padding of the up-sampled image everywhere
+# except the outermost output row / column on each side (there the two mirrored up-sampled pixels belong to different
+# low-res pixels), which take their own tap sums: top/left (0, w1+w2+w3, w0+w4), bottom/right mirrored.  So: 4 row
+# types x 4 column types = 16 weight sets of 3x3 taps; one 4-phase launch writes every output with the interior sets,
+# then four thin launches (rows 0 and 2H-1, columns 0 and 2W-1) and four one-pixel launches (corners) overwrite the
+# ring.  EXPERIMENTAL (no-grad forward only, MUNIT_UPCONV_PHASE=1): the plans below are verified against F.conv2d by
+# tests/test_geometry.py through the descriptor emulation; GPU validation is the next round's first step.
+UP_ROW_TYPES = {
+    # type -> 3 x 5 matrix A[d][k]: low-res row (i - 1 + d) collects tap k
+    0: [[1, 1, 0, 0, 0], [0, 0, 1, 1, 0], [0, 0, 0, 0, 1]],   # even output row 2i (interior)
+    1: [[1, 0, 0, 0, 0], [0, 1, 1, 0, 0], [0, 0, 0, 1, 1]],   # odd output row 2i+1 (interior)
+    2: [[0, 0, 0, 0, 0], [0, 1, 1, 1, 0], [1, 0, 0, 0, 1]],   # output row 0
+    3: [[1, 0, 0, 0, 1], [0, 1, 1, 1, 0], [0, 0, 0, 0, 0]],   # output row 2H-1
+}
+
+
+def upconv_phase_weights(weight):
+    """weight [Co, Ci, 5, 5] (any float dtype) -> [Co, 16, 3, 3, Ci]: the tap sums of every (row type, column type),
+    type index = 4 * row_type + col_type.  Pure tensor arithmetic (runs on whatever device `weight` lives on)."""
+    import torch
+
+    co, ci, kh, kw = weight.shape
+    assert kh == 5 and kw == 5, "phase decomposition is built for the 5x5 decoder layers"
+    a = torch.tensor([UP_ROW_TYPES[t] for t in range(4)], dtype=weight.dtype, device=weight.device)  # [4, 3, 5]
+    w = weight.permute(0, 2, 3, 1)  # [Co, ky, kx, Ci]
+    rows = (a[None, :, :, :, None, None] * w[:, None, None, :, :, :]).sum(3)          # [Co, rt, dy, kx, Ci]
+    full = (a[None, None, None, :, :, :, None] * rows[:, :, :, None, None, :, :]).sum(5)  # [Co, rt, dy, ct, dx, Ci]
+    return full.permute(0, 1, 3, 2, 4, 5).reshape(co, 16, 3, 3, ci).contiguous()
+
+
+def plan_upconv_phases(n, h, w, c, co_rows, out_geom) -> List[TapGemmPlan]:
+    """Launch list for y = conv5x5(reflect_pad2(nearest_up2(x))).  x is given as [n, h+2, w+2, c] with a *replicate*
+    halo of 1; the weight matrix is [co_rows][16][3][3][c] (upconv_phase_weights, K contiguous); out_geom as in
+    plan_fwd for the [2h, 2w] output.  Launch in list order (later launches overwrite the ring)."""
+    assert c % 64 == 0 and h >= 2 and w >= 2
+    e = 2
+    dims = [c, w + 2, h + 2, n]
+    strides = [e, c * e, (w + 2) * c * e, (h + 2) * (w + 2) * c * e]
+    o_sn, o_sy, o_sx, y_off, x_off = out_geom
+    bn = pick_bn(co_rows)
+    kper = 9 * c
+
+    def launch(i0, nh, j0, nw, phases):
+        tw, th, tn = pick_tile(nw, nh, n, 128)
+        taps = [[0, j0 + dx, i0 + dy, 0] for dy in range(3) for dx in range(3)]
+        return TapGemmPlan(
+            a_rank=4, a_dim=dims, a_stride=strides, a_box=[64, tw, th, tn], b_rows=co_rows, b_k=16 * kper, bn=bn,
+            tw=tw, th=th, tn=tn, out_w=nw, out_h=nh, n_img=n, mx=[0, 1, 0, 0], my=[0, 0, 1, 0], mn=[0, 0, 0, 1],
+            num_taps=9, chunks=c // 64, tap_off=taps, phases=len(phases),
+            b_k0=[(4 * rt + ct) * kper for rt, ct, _, _ in phases],
+            o_yoff=[2 * i0 + py + y_off for _, _, py, _ in phases], o_xoff=[2 * j0 + px + x_off for _, _, _, px in phases],
+            o_sn=o_sn, o_sy=o_sy, o_sx=o_sx, o_ymul=2, o_xmul=2, n_store=co_rows)
+
+    plans = [launch(0, h, 0, w, [(py, px, py, px) for py in (0, 1) for px in (0, 1)])]   # interior sets everywhere
+    plans.append(launch(0, 1, 0, w, [(2, 0, 0, 0), (2, 1, 0, 1)]))                          # output row 0
+    plans.append(launch(h - 1, 1, 0, w, [(3, 0, 1, 0), (3, 1, 1, 1)]))                      # output row 2h-1
+    plans.append(launch(0, h, 0, 1, [(0, 2, 0, 0), (1, 2, 1, 0)]))                          # output column 0
+    plans.append(launch(0, h, w - 1, 1, [(0, 3, 0, 1), (1, 3, 1, 1)]))                      # output column 2w-1
+    for i0, rt, py in ((0, 2, 0), (h - 1, 3, 1)):                                           # corners
+        for j0, ct, px in ((0, 2, 0), (w - 1, 3, 1)):
+            plans.append(launch(i0, 1, j0, 1, [(rt, ct, py, px)]))
+    flops = 2.0 * n * (2 * h) * (2 * w) * co_rows * 25 * c
+    for p in plans:
+        p.alg_flops = 0.0
+    plans[0].alg_flops = flops  # direct-form work of the layer, booked on the main launch
+    return plans

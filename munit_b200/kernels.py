@@ -671,3 +671,12 @@ def mse_const_bwd(x, target, gscale_dev, scale):
                                   x.numel(), _stream()), "mse_const_bwd")
     _count()
     return dx
+
+
+def halo_fill_replicate(act, pad):
+    """Replicate halo in place (experimental phase form of upsample + 5x5 conv)."""
+    n, hp, wp, c = act.shape
+    check(lib.munit_halo_fill_replicate(act.data_ptr(), n, hp - 2 * pad, wp - 2 * pad, c, pad, _stream()),
+          "halo_fill_replicate")
+    _count()
+    return act

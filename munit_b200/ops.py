@@ -253,6 +253,48 @@ class ConvLayer:
         return p
 
 
+# EXPERIMENTAL, off by default (MUNIT_UPCONV_PHASE=1): nearest-2x upsample + 5x5 conv as 3x3 phase GEMMs on the
+# low-res input in no-grad forward passes (inference, the generator pass of dis_update): 36 % of the MACs and a
+# quarter of the activation bytes.  The launch plans are verified on the CPU (tests/test_geometry.py); the GPU path
+# below has not run on a B200 yet -- tests/test_conv_gpu.py::test_upconv_phase_forward is skipped unless the switch
+# is set.
+UPCONV_PHASE = os.environ.get("MUNIT_UPCONV_PHASE", "0") != "0"
+
+
+def upconv_phase_ok(layer: "ConvLayer") -> bool:
+    return (UPCONV_PHASE and not torch.is_grad_enabled() and layer.k == 5 and layer.stride == 1 and layer.pad == 2
+            and not layer.first and not layer.last and not layer.zpad)
+
+
+def upconv_phase_forward(x_lo: torch.Tensor, weight, bias, layer: "ConvLayer") -> torch.Tensor:
+    """x_lo: [N, H+2, W+2, C] low-res act whose interior is valid (the halo is rewritten here with replicate
+    padding, in place).  Returns the raw conv output [N, 2H, 2W, co_rows] of Upsample(2) -> reflect pad 2 -> 5x5 conv."""
+    assert not torch.is_grad_enabled(), "the phase form is a forward-only path"
+    n, hp, wp, c = x_lo.shape
+    h, w = hp - 2, wp - 2
+    K.halo_fill_replicate(x_lo, 1)
+    ver = (weight._version, weight.data_ptr(), None if bias is None else bias._version)
+    if getattr(layer, "_up_ver", None) != ver:
+        wph = G.upconv_phase_weights(weight.detach().float())                    # [Co, 16, 3, 3, Ci] fp32
+        mat = torch.zeros(layer.co_rows, 16 * 9 * c, dtype=torch.bfloat16, device=weight.device)
+        mat[: layer.cout] = wph.reshape(layer.cout, -1).to(torch.bfloat16)
+        layer.w_up, layer._up_ver = mat, ver
+        layer._up_bias = torch.zeros(layer.co_rows, dtype=torch.float32, device=weight.device)
+        if bias is not None:
+            layer._up_bias[: layer.cout] = bias.detach()
+    key = ("up", n, h, w)
+    plans = layer._plans.get(key)
+    if plans is None:
+        ho, wo = 2 * h, 2 * w
+        plans = G.plan_upconv_phases(n, h, w, c, layer.co_rows, (ho * wo * layer.co_rows, wo * layer.co_rows,
+                                                                layer.co_rows, 0, 0))
+        layer._plans[key] = plans
+    out = torch.empty(n, 2 * h, 2 * w, layer.co_rows, dtype=torch.bfloat16, device=x_lo.device)
+    for p in plans:  # interior sets everywhere, then the ring launches overwrite rows / columns / corners
+        K.tapgemm(p, x_lo, layer.w_up, out, layer._up_bias if bias is not None else None, "none", ksplit=1)
+    return out
+
+
 def _want_halo(kh, kw, out_h, out_w) -> int:
     """Use the halo-resident tap-GEMM variant where it measured faster (profiles/r1_halo.md): many taps (5x5 and
     up) and an output extent that 8 x 16 tiles cover with <= 10 % waste.  (The UMMA descriptor base offset stays 0:

@@ -193,3 +193,42 @@ def test_rspace_narrow_output_layer():
     E.wgrad(wplan, dr.reshape(-1), nhwc(xp.detach()).reshape(-1), tmp)
     dw = torch.where(inv_i >= 0, tmp[inv_i.clamp(min=0).long()], torch.zeros(()))
     assert torch.allclose(dw.view(cout, k, k, cin), wt_r.grad.permute(0, 2, 3, 1), atol=1e-2, rtol=1e-3)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 4, 6, 64, 64), (1, 8, 8, 128, 64), (3, 2, 2, 64, 128), (1, 5, 3, 64, 16)])
+def test_upsample_5x5_as_phase_gemms(n, h, w, cin, cout):
+    """nearest-2x upsample + reflect pad 2 + 5x5 conv (networks.py:534-545) == one 4-phase 3x3 launch on the
+    replicate-padded low-res input plus eight ring launches with their own tap sums (geometry.plan_upconv_phases)."""
+    torch.manual_seed(4)
+    x = torch.randn(n, cin, h, w)
+    wt = torch.randn(cout, cin, 5, 5) * 0.1
+    bias = torch.randn(cout)
+    up = F.interpolate(x, scale_factor=2, mode="nearest")
+    y_ref = F.conv2d(F.pad(up, (2,) * 4, mode="reflect"), wt, bias)
+    xr = F.pad(x, (1,) * 4, mode="replicate")
+    wph = G.upconv_phase_weights(wt)
+    assert tuple(wph.shape) == (cout, 16, 3, 3, cin)
+    # interior sets: even/even phase sums the 2x2 taps (0..1, 0..1) into its first entry
+    assert torch.allclose(wph[:, 0, 0, 0], wt[:, :, 0:2, 0:2].sum((2, 3)), atol=1e-6)
+    ho, wo = 2 * h, 2 * w
+    plans = G.plan_upconv_phases(n, h, w, cin, cout, (ho * wo * cout, wo * cout, cout, 0, 0))
+    assert len(plans) == 9 and plans[0].phases == 4
+    out = torch.full((n * ho * wo * cout,), float("nan"))
+    for p in plans:
+        E.tapgemm(p, nhwc(xr).reshape(-1), wph.reshape(cout, -1), out, bias, "none")
+    got = out.view(n, ho, wo, cout)
+    assert torch.allclose(got, nhwc(y_ref), atol=2e-3, rtol=1e-4), float((got - nhwc(y_ref)).abs().max())
+    # the interior launch alone is already exact away from the ring
+    out1 = torch.zeros(n * ho * wo * cout)
+    E.tapgemm(plans[0], nhwc(xr).reshape(-1), wph.reshape(cout, -1), out1, bias, "none")
+    assert torch.allclose(out1.view(n, ho, wo, cout)[:, 1:-1, 1:-1], nhwc(y_ref)[:, 1:-1, 1:-1], atol=2e-3, rtol=1e-4)
+
+
+def test_upsample_phase_gemm_issues_a_third_of_the_macs():
+    """At the decoder's real shapes the phase form issues 36 % of the direct form's MACs (+ the thin ring launches)."""
+    for n, h, c, co in ((8, 64, 256, 128), (8, 128, 128, 64)):
+        plans = G.plan_upconv_phases(n, h, h, c, co, (4 * h * h * co, 2 * h * co, co, 0, 0))
+        direct = 2.0 * n * (2 * h) ** 2 * co * 25 * c
+        assert plans[0].alg_flops == direct
+        assert abs(plans[0].flops() / direct - 0.36) < 1e-6
+        assert sum(p.flops() for p in plans[1:]) < 0.04 * direct
