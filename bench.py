@@ -285,6 +285,19 @@ def run_b200(args):
     torch.manual_seed(1000 + rank)
     draw_styles()
     runner.load_inputs(x_a_h, x_b_h, *s_host)
+    if args.ncu_step:
+        # For `ncu --profile-from-start off ...`: two eager warm-up steps, then exactly one eager step inside the
+        # profiler range (about 1800 launches, a couple of minutes under ncu instead of the whole benchmark).
+        for _ in range(2):
+            runner.step()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        runner.step()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"ncu_step": "one eager dis_update+gen_update in the profiler range",
+                          "launches": runner.launches_per_step}))
+        return
     runner.warmup_and_capture(2)
     for _ in range(args.warmup):
         runner.step()
@@ -516,9 +529,14 @@ def main():
                     help="1: gen_update reuses the generator pass of the preceding dis_update (trainer.reuse_forward); "
                          "the default run reports it next to the headline as `forward_reuse`")
     ap.add_argument("--workload", default="train", choices=["train", "infer"])
+    ap.add_argument("--ncu-step", action="store_true",
+                    help="profiling aid: eager mode, one step inside torch.cuda.profiler.start/stop (use with "
+                         "ncu --profile-from-start off); prints no benchmark number")
     ap.add_argument("--dump-launches", default="", help="write per-launch tensor-kernel timings (profile pass) to this json")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.ncu_step:
+        args.no_graph, args.two_streams = True, 0
     if args.impl == "reference":
         run_reference_arm(args)
     elif args.workload == "infer":

@@ -5,7 +5,8 @@
     python tools/ncu_step.py launches.csv > profiles/<round>_launches_by_kernel.txt
 
 A step is delimited by its two adam_kernel launches (discriminator, then generator update); the last complete step of
-the file's first half is reported (eager, one stream: ncu serialises launches and flushes caches, so compare shares)."""
+the file's first half is reported, or step `argv[2]` (0 for a `bench.py --ncu-step` file, which holds exactly one)
+(eager, one stream: ncu serialises launches and flushes caches, so compare shares)."""
 import csv
 import re
 import sys
@@ -23,7 +24,7 @@ for r in csv.DictReader(lines):
     rows.append((r["Kernel Name"], us))
 adam = [i for i, (k, _) in enumerate(rows) if "adam_kernel" in k]
 pick = int(sys.argv[2]) if len(sys.argv) > 2 else max(0, len(adam) // 2 - 1) // 2 * 2
-if len(adam) < pick + 3:
+if len(adam) < pick + 2:
     sys.exit("not enough adam launches to cut a step: %d" % len(adam))
 lo, hi = adam[pick - 1] + 1 if pick > 0 else 0, adam[pick + 1] + 1
 step = rows[lo:hi]
