@@ -348,34 +348,39 @@ def run_b200(args):
     # ---- informational: the same step with gen_update picking up dis_update's generator pass (trainer.reuse_forward)
     reuse_line = None
     if world == 1 and not args.reuse_forward and not args.no_graph and cfg["guided"] == 1 and cfg["gen_state"] == 1:
-        runner.release()
-        r2 = StepRunner(trainer, cfg, args.batch, hw, use_graph=True, world=1, two_streams=args.two_streams,
-                        reuse_forward=True)
-        r2.iter = runner.iter
-        r2.load_inputs(x_a_h, x_b_h, *s_host)
-        r2.warmup_and_capture(1)
-        for _ in range(args.warmup):
-            r2.step()
-        torch.cuda.synchronize()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for _ in range(args.steps):
-            r2.step()
-        g1.record()
-        torch.cuda.synchronize()
-        ms2 = g0.elapsed_time(g1)
-        ls2 = r2.losses()
-        reuse_line = dict(value=args.steps / (ms2 / 1000.0), unit=UNIT, ms_per_step=ms2 / args.steps,
-                          gpu_launches_per_step=r2.launches_per_step,
-                          last_losses=dict(dis=float(ls2["loss_dis_total"]), gen=float(ls2["loss_gen_total"])),
-                          note="NOT the headline: same dis_update + gen_update calls with trainer.reuse_forward = True "
-                               "-- gen_update reuses the generator pass (encode x_a, x_b; decode within / across "
-                               "domains) that dis_update ran on the same batch and the same generator weights "
-                               "(guided = 1), 155 of the step's 1395 GMAC per pair are not computed twice; losses, "
-                               "gradients and both optimizer steps as in the headline run "
-                               "(tests/test_trainer_gpu.py::test_forward_reuse_between_updates_is_transparent)")
-        r2.release()
-        trainer.reuse_forward = False
+        try:
+            runner.release()
+            r2 = StepRunner(trainer, cfg, args.batch, hw, use_graph=True, world=1, two_streams=args.two_streams,
+                            reuse_forward=True)
+            r2.iter = runner.iter
+            r2.load_inputs(x_a_h, x_b_h, *s_host)
+            r2.warmup_and_capture(1)
+            for _ in range(args.warmup):
+                r2.step()
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(args.steps):
+                r2.step()
+            g1.record()
+            torch.cuda.synchronize()
+            ms2 = g0.elapsed_time(g1)
+            ls2 = r2.losses()
+            reuse_line = dict(value=args.steps / (ms2 / 1000.0), unit=UNIT, ms_per_step=ms2 / args.steps,
+                              gpu_launches_per_step=r2.launches_per_step,
+                              last_losses=dict(dis=float(ls2["loss_dis_total"]), gen=float(ls2["loss_gen_total"])),
+                              note="NOT the headline: same dis_update + gen_update calls with trainer.reuse_forward = True "
+                                   "-- gen_update reuses the generator pass (encode x_a, x_b; decode within / across "
+                                   "domains) that dis_update ran on the same batch and the same generator weights "
+                                   "(guided = 1), 155 of the step's 1395 GMAC per pair are not computed twice; losses, "
+                                   "gradients and both optimizer steps as in the headline run "
+                                   "(tests/test_trainer_gpu.py::test_forward_reuse_between_updates_is_transparent)")
+            r2.release()
+            trainer.reuse_forward = False
+        except Exception as exc:  # informational line only: never lose the headline over it
+            reuse_line = dict(error=repr(exc))
+            trainer.reuse_forward = False
+
     dom_us, dom_tf = dominant_launch_time(args.batch) if rank == 0 else (0.0, 0.0)
     if rank == 0 and args.dump_launches:
         json.dump(prof["detail"], open(args.dump_launches, "w"))
