@@ -408,3 +408,53 @@ def plan_upconv_phases(n, h, w, c, co_rows, out_geom) -> List[TapGemmPlan]:
         p.alg_flops = 0.0
     plans[0].alg_flops = flops  # direct-form work of the layer, booked on the main launch
     return plans
+
+
+def upconv_dgrad_index_map(co, ci, c_rows, ck):
+    """Index map into the [Co][16][3][3][Ci] phase-weight tensor for the interior dgrad matrix of the phase form:
+    [c_rows (ci)][36 taps = (py, px, dy, dx)][ck (co)]  <-  wph[co, 4*py + px, dy, dx, ci]."""
+    import torch
+
+    src = torch.arange(co * 16 * 9 * ci, dtype=torch.int32).view(co, 16, 3, 3, ci)
+    idx = torch.full((c_rows, 2, 2, 3, 3, ck), -1, dtype=torch.int32)
+    for py in range(2):
+        for px in range(2):
+            idx[:ci, py, px, :, :, :co] = src[:, 4 * py + px].permute(3, 1, 2, 0)
+    return idx.reshape(-1)
+
+
+def plan_upconv_dgrad_interior(n, h, w, c_rows, co_c) -> TapGemmPlan:
+    """Interior part of the phase-form input gradient: dy0 [n, 2h, 2w, co_c] (the gradient of the conv output with
+    its outermost ring ZEROED -- the ring pixels use other tap sums and are handled separately) ->
+    dxr [n, h+2, w+2, c_rows], the gradient w.r.t. the replicate-padded low-res input (every position written).
+    dy0 is read through a space-to-depth view [2*co, w, 2, h, n]; 36 taps (py, px, dy, dx)."""
+    assert co_c % 64 == 0
+    e = 2
+    dims = [2 * co_c, w, 2, h, n]
+    strides = [e, 2 * co_c * e, 2 * w * co_c * e, 4 * w * co_c * e, 4 * h * w * co_c * e]
+    oh, ow = h + 2, w + 2
+    tw, th, tn = pick_tile(ow, oh, n, 128)
+    taps = [[px * co_c, -dx, py, -dy, 0] for py in range(2) for px in range(2) for dy in range(3) for dx in range(3)]
+    return TapGemmPlan(
+        a_rank=5, a_dim=dims, a_stride=strides, a_box=[64, tw, 1, th, tn], b_rows=c_rows, b_k=36 * co_c,
+        bn=pick_bn(c_rows), tw=tw, th=th, tn=tn, out_w=ow, out_h=oh, n_img=n, mx=[0, 1, 0, 0, 0], my=[0, 0, 0, 1, 0],
+        mn=[0, 0, 0, 0, 1], num_taps=36, chunks=co_c // 64, tap_off=taps, phases=1, b_k0=[0], o_yoff=[0], o_xoff=[0],
+        o_sn=oh * ow * c_rows, o_sy=ow * c_rows, o_sx=c_rows, o_ymul=1, o_xmul=1, n_store=c_rows)
+
+
+def plan_upconv_wgrad_interior(n, h, w, c, co_c, py, px) -> WgradPlan:
+    """Interior part of the phase-form weight gradient for output phase (py, px): accumulates
+    dwph[co][4*py + px][dy][dx][ci] += sum_{i,j} dy0[2i+py, 2j+px][co] * xr[i+dy, j+dx][ci] into the phase-gradient
+    scratch [co][16][3][3][ci] (dy0 ring-zeroed as in plan_upconv_dgrad_interior; xr = replicate-padded low-res
+    input [n, h+2, w+2, c]).  The caller offsets the dy0 base pointer by (py*2w + px)*co_c elements; the view
+    below then walks every second row / column."""
+    e = 2
+    pw, ph, pn = pick_tile(w, h, n, 64)
+    taps = [[0, dx, dy, 0] for dy in range(3) for dx in range(3)]
+    return WgradPlan(
+        a_rank=4, a_dim=[co_c, w, h, n], a_stride=[e, 2 * co_c * e, 4 * w * co_c * e, 4 * h * w * co_c * e],
+        a_box=[64, pw, ph, pn], a_mx=[0, 1, 0, 0], a_my=[0, 0, 1, 0], a_mn=[0, 0, 0, 1],
+        b_rank=4, b_dim=[c, w + 2, h + 2, n], b_stride=[e, c * e, (w + 2) * c * e, (h + 2) * (w + 2) * c * e],
+        b_box=[64, pw, ph, pn], b_mx=[0, 1, 0, 0], b_my=[0, 0, 1, 0], b_mn=[0, 0, 0, 1],
+        pw=pw, ph=ph, pn=pn, out_w=w, out_h=h, n_img=n, m_total=co_c, n_total=c, bn=128 if c % 128 == 0 else 64,
+        num_taps=9, tap_off=taps, s_m=16 * 9 * c, s_t=c, s_n=1)

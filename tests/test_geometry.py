@@ -232,3 +232,53 @@ def test_upsample_phase_gemm_issues_a_third_of_the_macs():
         assert plans[0].alg_flops == direct
         assert abs(plans[0].flops() / direct - 0.36) < 1e-6
         assert sum(p.flops() for p in plans[1:]) < 0.04 * direct
+
+
+def _ring_zeroed(g):
+    g = g.clone()
+    g[:, :, 0] = 0; g[:, :, -1] = 0; g[:, :, :, 0] = 0; g[:, :, :, -1] = 0
+    return g
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 4, 6, 64, 64), (1, 5, 3, 128, 64), (1, 4, 4, 64, 128)])
+def test_upsample_phase_form_interior_backward_plans(n, h, w, cin, cout):
+    """Interior share of the phase-form backward (EXPERIMENTAL blueprint, see tests/test_upconv_math_cpu.py): with the
+    ring of dY zeroed, one 36-tap launch over the space-to-depth view of dY gives the gradient of the replicate-padded
+    low-res input, and four 9-tap wgrad launches give the interior phase-weight gradients -- both equal autograd of
+    the direct formulation restricted to the interior output pixels."""
+    torch.manual_seed(5)
+    x = torch.randn(n, cin, h, w)
+    wt = torch.randn(cout, cin, 5, 5) * 0.1
+    xr = F.pad(x, (1,) * 4, mode="replicate").requires_grad_(True)
+    wph = G.upconv_phase_weights(wt).requires_grad_(True)                      # [co, 16, 3, 3, ci]
+    # interior-type forward as plain convs (autograd reference for the interior share)
+    y = torch.zeros(n, cout, 2 * h, 2 * w)
+    parts = {}
+    for py in (0, 1):
+        for px in (0, 1):
+            parts[(py, px)] = F.conv2d(xr, wph[:, 4 * py + px].permute(0, 3, 1, 2))
+    y = torch.stack([torch.stack([parts[(py, px)] for px in (0, 1)], -1) for py in (0, 1)], -3)  # [n,co,h,2,w,2]
+    y = y.reshape(n, cout, 2 * h, 2 * w)
+    gy0 = _ring_zeroed(torch.randn(n, cout, 2 * h, 2 * w))
+    y.backward(gy0)
+    # ---- dgrad
+    ck = max(64, cout)
+    plan = G.plan_upconv_dgrad_interior(n, h, w, cin, cout)
+    idx = G.upconv_dgrad_index_map(cout, cin, cin, ck)
+    flat = wph.detach().reshape(-1)
+    wd = torch.where(idx >= 0, flat[idx.clamp(min=0).long()], torch.zeros(())).view(cin, -1)
+    assert ck == cout, "test shapes keep co a multiple of 64"
+    dxr = torch.full((n * (h + 2) * (w + 2) * cin,), float("nan"))
+    E.tapgemm(plan, nhwc(gy0).reshape(-1), wd, dxr)
+    assert torch.allclose(dxr.view(n, h + 2, w + 2, cin), nhwc(xr.grad), atol=2e-3, rtol=1e-4)
+    # ---- wgrad, one launch per output phase, into the [co][16][3][3][ci] scratch
+    dw = torch.zeros(cout * 16 * 9 * cin)
+    g_flat = nhwc(gy0).reshape(-1)
+    for py in (0, 1):
+        for px in (0, 1):
+            wp_ = G.plan_upconv_wgrad_interior(n, h, w, cin, cout, py, px)
+            base = (py * 2 * w + px) * cout
+            E.wgrad(wp_, g_flat[base:], nhwc(xr.detach()).reshape(-1), dw[(4 * py + px) * 9 * cin:])
+    got = dw.view(cout, 16, 3, 3, cin)
+    assert torch.allclose(got[:, [0, 1, 4, 5]], wph.grad[:, [0, 1, 4, 5]], atol=1e-2, rtol=1e-3)
+    assert float(got[:, [2, 3, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15]].abs().max()) == 0  # ring types untouched here
