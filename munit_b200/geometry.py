@@ -458,3 +458,88 @@ def plan_upconv_wgrad_interior(n, h, w, c, co_c, py, px) -> WgradPlan:
         b_box=[64, pw, ph, pn], b_mx=[0, 1, 0, 0], b_my=[0, 0, 1, 0], b_mn=[0, 0, 0, 1],
         pw=pw, ph=ph, pn=pn, out_w=w, out_h=h, n_img=n, m_total=co_c, n_total=c, bn=128 if c % 128 == 0 else 64,
         num_taps=9, tap_off=taps, s_m=16 * 9 * c, s_t=c, s_n=1)
+
+
+# Ring share of the phase-form backward.  The outermost output row / column on each side is cut out of dY into
+# strips with the four corner pixels zeroed (they have their own (first|last, first|last) types and are too few for
+# a GEMM):   top / bottom strip [n, 2w, co]   (output rows 0 and 2h-1),   left / right strip [n, 2h, co].
+# side: 0 top, 1 bottom, 2 left, 3 right; its row (or column) type is 2 (first) for top / left, 3 (last) otherwise.
+def upconv_ring_dgrad_index_map(co, ci, c_rows, ck, side):
+    """[c_rows (ci)][3 phases (the strip-normal offset d)][6 taps = (p, e)][ck (co)]: p the parity along the strip,
+    e the tap along the strip  <-  wph[co, type, dy, dx, ci] with (dy, dx) = (d, e) for top / bottom, (e, d) for
+    left / right and type = 4*rt + p (top / bottom) or 4*p + ct (left / right)."""
+    import torch
+
+    src = torch.arange(co * 16 * 9 * ci, dtype=torch.int32).view(co, 16, 3, 3, ci)
+    t = 2 if side in (0, 2) else 3
+    idx = torch.full((c_rows, 3, 2, 3, ck), -1, dtype=torch.int32)
+    for d in range(3):
+        for p in range(2):
+            for e_ in range(3):
+                if side < 2:
+                    v = src[:, 4 * t + p, d, e_]
+                else:
+                    v = src[:, 4 * p + t, e_, d]
+                idx[:ci, d, p, e_, :co] = v.t()
+    return idx.reshape(-1)
+
+
+def plan_upconv_dgrad_ring(n, h, w, c_rows, co_c, side) -> TapGemmPlan:
+    """strip -> its contribution to the gradient of the replicate-padded low-res input, as a 3-wide band:
+    top / bottom: band [n, 3, w+2, c_rows] = rows (0..2) / (h-1 .. h+1) of dxr; left / right: [n, h+2, 3, c_rows] =
+    columns (0..2) / (w-1 .. w+1).  Phase d writes band line d; 6 taps (parity, tap along the strip)."""
+    assert co_c % 64 == 0
+    e = 2
+    horiz = side < 2
+    length = w if horiz else h            # low-res extent along the strip
+    dims = [2 * co_c, length, 1, n]
+    strides = [e, 2 * co_c * e, 2 * length * co_c * e, 2 * length * co_c * e]
+    ol = length + 2
+    taps = [[p * co_c, -e_, 0, 0] for p in range(2) for e_ in range(3)]
+    if horiz:
+        ow, oh = ol, 1
+        o_sn, o_sy, o_sx = 3 * ol * c_rows, ol * c_rows, c_rows
+        mx, my = [0, 1, 0, 0], [0, 0, 1, 0]
+        yoff, xoff = [0, 1, 2], [0, 0, 0]
+    else:
+        ow, oh = 1, ol
+        o_sn, o_sy, o_sx = ol * 3 * c_rows, 3 * c_rows, c_rows
+        mx, my = [0, 0, 1, 0], [0, 1, 0, 0]   # the GEMM's y walks the strip
+        yoff, xoff = [0, 0, 0], [0, 1, 2]
+    tw, th, tn = pick_tile(ow, oh, n, 128)
+    box = [64, tw, 1, tn] if horiz else [64, th, 1, tn]
+    return TapGemmPlan(
+        a_rank=4, a_dim=dims, a_stride=strides, a_box=box, b_rows=c_rows, b_k=3 * 6 * co_c, bn=pick_bn(c_rows),
+        tw=tw, th=th, tn=tn, out_w=ow, out_h=oh, n_img=n, mx=mx, my=my, mn=[0, 0, 0, 1], num_taps=6,
+        chunks=co_c // 64, tap_off=taps, phases=3, b_k0=[d * 6 * co_c for d in range(3)], o_yoff=yoff, o_xoff=xoff,
+        o_sn=o_sn, o_sy=o_sy, o_sx=o_sx, o_ymul=1, o_xmul=1, n_store=c_rows)
+
+
+def plan_upconv_wgrad_ring(n, h, w, c, co_c, side, p) -> WgradPlan:
+    """Ring share of the phase-weight gradient: strip pixels of parity p along the strip against the three low-res
+    rows (columns) they read.  Accumulates into the [co][16][3][3][ci] scratch at type 4*rt + p (top / bottom) or
+    4*p + ct (left / right); the caller offsets the strip base pointer by p*co_c elements and the scratch pointer by
+    type*9*c.  xr: replicate-padded low-res input [n, h+2, w+2, c]."""
+    e = 2
+    horiz = side < 2
+    length = w if horiz else h
+    line0 = 0 if side in (0, 2) else ((h - 1) if horiz else (w - 1))   # first of the three xr rows / columns read
+    if horiz:
+        pw, ph, pn = pick_tile(length, 1, n, 64)
+        a_mx, a_my = [0, 1, 0, 0], [0, 0, 1, 0]
+        taps = [[0, dx, line0 + dy, 0] for dy in range(3) for dx in range(3)]
+        a_box = [64, pw, 1, pn]
+        ow, oh = length, 1
+    else:
+        pw, ph, pn = pick_tile(1, length, n, 64)
+        a_mx, a_my = [0, 0, 1, 0], [0, 1, 0, 0]
+        taps = [[0, line0 + dx, dy, 0] for dy in range(3) for dx in range(3)]
+        a_box = [64, ph, 1, pn]
+        ow, oh = 1, length
+    return WgradPlan(
+        a_rank=4, a_dim=[co_c, length, 1, n], a_stride=[e, 2 * co_c * e, 2 * length * co_c * e, 2 * length * co_c * e],
+        a_box=a_box, a_mx=a_mx, a_my=a_my, a_mn=[0, 0, 0, 1],
+        b_rank=4, b_dim=[c, w + 2, h + 2, n], b_stride=[e, c * e, (w + 2) * c * e, (h + 2) * (w + 2) * c * e],
+        b_box=[64, pw, ph, pn], b_mx=[0, 1, 0, 0], b_my=[0, 0, 1, 0], b_mn=[0, 0, 0, 1],
+        pw=pw, ph=ph, pn=pn, out_w=ow, out_h=oh, n_img=n, m_total=co_c, n_total=c, bn=128 if c % 128 == 0 else 64,
+        num_taps=9, tap_off=taps, s_m=16 * 9 * c, s_t=c, s_n=1)

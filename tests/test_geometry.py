@@ -282,3 +282,67 @@ def test_upsample_phase_form_interior_backward_plans(n, h, w, cin, cout):
     got = dw.view(cout, 16, 3, 3, cin)
     assert torch.allclose(got[:, [0, 1, 4, 5]], wph.grad[:, [0, 1, 4, 5]], atol=1e-2, rtol=1e-3)
     assert float(got[:, [2, 3, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15]].abs().max()) == 0  # ring types untouched here
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 4, 6, 64, 64), (1, 5, 3, 64, 128)])
+def test_upsample_phase_form_ring_backward_plans(n, h, w, cin, cout):
+    """Ring share of the phase-form backward (EXPERIMENTAL blueprint): the four strips (corners zeroed) through
+    geometry.plan_upconv_dgrad_ring / plan_upconv_wgrad_ring against autograd of the type-form forward restricted to
+    the non-corner ring pixels."""
+    torch.manual_seed(6)
+    x = torch.randn(n, cin, h, w)
+    wt = torch.randn(cout, cin, 5, 5) * 0.1
+    xr = F.pad(x, (1,) * 4, mode="replicate").requires_grad_(True)
+    wph = G.upconv_phase_weights(wt).requires_grad_(True)
+    gy = torch.randn(n, cout, 2 * h, 2 * w)
+    ring = torch.zeros(2 * h, 2 * w, dtype=torch.bool)
+    ring[0] = ring[-1] = True
+    ring[:, 0] = ring[:, -1] = True
+    for cy in (0, -1):
+        for cx in (0, -1):
+            ring[cy, cx] = False                                   # corners are handled apart
+    gy_ring = gy * ring
+    # type-form forward of the four strips (autograd reference)
+    loss = 0
+    def line(rt_or_ct, horiz, out_line, lo_line):
+        """sum over the strip's pixels of gy * y, y through the type weights."""
+        nonlocal loss
+        L = w if horiz else h
+        for p in (0, 1):
+            t = (4 * rt_or_ct + p) if horiz else (4 * p + rt_or_ct)
+            k = wph[:, t].permute(0, 3, 1, 2)                       # [co, ci, 3, 3]
+            if horiz:
+                yl = F.conv2d(xr[:, :, lo_line:lo_line + 3, :], k)  # [n, co, 1, w]
+                g = gy_ring[:, :, out_line, p::2].unsqueeze(2)
+            else:
+                yl = F.conv2d(xr[:, :, :, lo_line:lo_line + 3], k)  # [n, co, h, 1]
+                g = gy_ring[:, :, p::2, out_line].unsqueeze(3)
+            loss = loss + (yl * g).sum()
+    line(2, True, 0, 0); line(3, True, 2 * h - 1, h - 1); line(2, False, 0, 0); line(3, False, 2 * w - 1, w - 1)
+    loss.backward()
+    strips = {0: gy_ring[:, :, 0, :], 1: gy_ring[:, :, -1, :], 2: gy_ring[:, :, :, 0], 3: gy_ring[:, :, :, -1]}  # [n,co,L2]
+    dxr = torch.zeros(n, h + 2, w + 2, cin)
+    dw = torch.zeros(cout * 16 * 9 * cin)
+    flat_w = wph.detach().reshape(-1)
+    xr_flat = nhwc(xr.detach()).reshape(-1)
+    for side, s in strips.items():
+        sf = s.permute(0, 2, 1).contiguous().reshape(-1)            # [n, 2L, co]
+        L = w if side < 2 else h
+        plan = G.plan_upconv_dgrad_ring(n, h, w, cin, cout, side)
+        idx = G.upconv_ring_dgrad_index_map(cout, cin, cin, max(64, cout), side)
+        wd = torch.where(idx >= 0, flat_w[idx.clamp(min=0).long()], torch.zeros(())).view(cin, -1)
+        band = torch.full((n * 3 * (L + 2) * cin,), float("nan"))
+        E.tapgemm(plan, sf, wd, band)
+        if side < 2:
+            r0 = 0 if side == 0 else h - 1
+            dxr[:, r0:r0 + 3] += band.view(n, 3, w + 2, cin)
+        else:
+            c0 = 0 if side == 2 else w - 1
+            dxr[:, :, c0:c0 + 3] += band.view(n, h + 2, 3, cin)
+        t = 2 if side in (0, 2) else 3
+        for p in (0, 1):
+            typ = (4 * t + p) if side < 2 else (4 * p + t)
+            wp_ = G.plan_upconv_wgrad_ring(n, h, w, cin, cout, side, p)
+            E.wgrad(wp_, sf[p * cout:], xr_flat, dw[typ * 9 * cin:])
+    assert torch.allclose(dxr, nhwc(xr.grad), atol=2e-3, rtol=1e-4), float((dxr - nhwc(xr.grad)).abs().max())
+    assert torch.allclose(dw.view(cout, 16, 3, 3, cin), wph.grad, atol=1e-2, rtol=1e-3)
