@@ -183,7 +183,9 @@ class Conv2dBlock(nn.Module):
         # a per-channel bias is cancelled exactly by the mean subtraction of IN / AdaIN: skip it
         bias = b if self.norm_type == "ln" else None
         if pending_up:
-            y, part = ops.upconv_phase_forward(xin, w, bias, layer), None
+            y = (ops.UpConvPhaseFn.apply(xin, w, bias, layer) if torch.is_grad_enabled()
+                 else ops.upconv_phase_forward(xin, w, bias, layer))
+            part = None
         else:
             y, part = ops.ConvFn.apply(xin, w, bias, layer, "none", 0, self.padding, 2 if self.norm_type == "ln" else 1)
         n = y.shape[0]

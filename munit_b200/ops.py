@@ -253,46 +253,78 @@ class ConvLayer:
         return p
 
 
-# EXPERIMENTAL, off by default (MUNIT_UPCONV_PHASE=1): nearest-2x upsample + 5x5 conv as 3x3 phase GEMMs on the
-# low-res input in no-grad forward passes (inference, the generator pass of dis_update): 36 % of the MACs and a
-# quarter of the activation bytes.  The launch plans are verified on the CPU (tests/test_geometry.py); the GPU path
-# below has not run on a B200 yet -- tests/test_conv_gpu.py::test_upconv_phase_forward is skipped unless the switch
-# is set.
-UPCONV_PHASE = os.environ.get("MUNIT_UPCONV_PHASE", "0") != "0"
+# EXPERIMENTAL, off by default: nearest-2x upsample + 5x5 conv as 3x3 phase GEMMs on the low-res input (36 % of
+# the MACs, a quarter of the activation bytes; munit_b200/upconv.py).  MUNIT_UPCONV_PHASE=1: no-grad forward passes
+# only (inference, the generator pass of dis_update); =2: training too (backward in phase form, its glue still plain
+# tensor arithmetic).  Launch plans and the whole forward / backward orchestration are verified on the CPU through
+# the descriptor emulation (tests/test_geometry.py, tests/test_upconv_cpu.py); the GPU path has not run on a B200
+# yet -- tests/test_conv_gpu.py::test_upconv_phase_* are skipped unless the switch is set.
+UPCONV_PHASE = int(os.environ.get("MUNIT_UPCONV_PHASE", "0") or 0)
 
 
 def upconv_phase_ok(layer: "ConvLayer") -> bool:
-    return (UPCONV_PHASE and not torch.is_grad_enabled() and layer.k == 5 and layer.stride == 1 and layer.pad == 2
-            and not layer.first and not layer.last and not layer.zpad)
+    lvl = int(UPCONV_PHASE)
+    if not lvl or (lvl < 2 and torch.is_grad_enabled()):
+        return False
+    return (layer.k == 5 and layer.stride == 1 and layer.pad == 2 and not layer.first and not layer.last
+            and not layer.zpad and layer.co_rows == layer.cout and layer.cout % 64 == 0)
+
+
+def _upconv_refresh(layer: "ConvLayer", weight, bias, c):
+    """bf16 phase-weight matrix [co_rows][16*9*c] (+ fp32 bias) of a 5x5 layer, rebuilt when the master changed."""
+    ver = (weight._version, weight.data_ptr(), None if bias is None else bias._version)
+    if getattr(layer, "_up_ver", None) != ver:
+        wph = G.upconv_phase_weights(weight.detach().float())                    # [Co, 16, 3, 3, Ci] fp32
+        layer.w_up = wph.reshape(layer.cout, -1).to(torch.bfloat16).contiguous()
+        layer._up_bias = bias.detach().float().contiguous() if bias is not None else None
+        layer._up_ver = ver
 
 
 def upconv_phase_forward(x_lo: torch.Tensor, weight, bias, layer: "ConvLayer") -> torch.Tensor:
     """x_lo: [N, H+2, W+2, C] low-res act whose interior is valid (the halo is rewritten here with replicate
     padding, in place).  Returns the raw conv output [N, 2H, 2W, co_rows] of Upsample(2) -> reflect pad 2 -> 5x5 conv."""
-    assert not torch.is_grad_enabled(), "the phase form is a forward-only path"
-    n, hp, wp, c = x_lo.shape
-    h, w = hp - 2, wp - 2
+    from . import upconv
+
     K.halo_fill_replicate(x_lo, 1)
-    ver = (weight._version, weight.data_ptr(), None if bias is None else bias._version)
-    if getattr(layer, "_up_ver", None) != ver:
-        wph = G.upconv_phase_weights(weight.detach().float())                    # [Co, 16, 3, 3, Ci] fp32
-        mat = torch.zeros(layer.co_rows, 16 * 9 * c, dtype=torch.bfloat16, device=weight.device)
-        mat[: layer.cout] = wph.reshape(layer.cout, -1).to(torch.bfloat16)
-        layer.w_up, layer._up_ver = mat, ver
-        layer._up_bias = torch.zeros(layer.co_rows, dtype=torch.float32, device=weight.device)
-        if bias is not None:
-            layer._up_bias[: layer.cout] = bias.detach()
-    key = ("up", n, h, w)
-    plans = layer._plans.get(key)
-    if plans is None:
-        ho, wo = 2 * h, 2 * w
-        plans = G.plan_upconv_phases(n, h, w, c, layer.co_rows, (ho * wo * layer.co_rows, wo * layer.co_rows,
-                                                                layer.co_rows, 0, 0))
-        layer._plans[key] = plans
-    out = torch.empty(n, 2 * h, 2 * w, layer.co_rows, dtype=torch.bfloat16, device=x_lo.device)
-    for p in plans:  # interior sets everywhere, then the ring launches overwrite rows / columns / corners
-        K.tapgemm(p, x_lo, layer.w_up, out, layer._up_bias if bias is not None else None, "none", ksplit=1)
-    return out
+    _upconv_refresh(layer, weight, bias, x_lo.shape[3])
+    return upconv.forward(upconv.GpuLauncher(), x_lo, layer.w_up, layer._up_bias, layer.co_rows)
+
+
+class UpConvPhaseFn(torch.autograd.Function):
+    """Training form of upconv_phase_forward: forward as above, backward through upconv.backward (interior and
+    ring launches of the tap-GEMM / wgrad kernels; the gradient returned for x_lo has a zero halo, which is what
+    the producing norm's reflect-halo fold needs)."""
+
+    @staticmethod
+    def forward(ctx, x_lo, weight, bias, layer: ConvLayer):
+        out = upconv_phase_forward(x_lo, weight, bias, layer)
+        ctx.layer, ctx.has_bias = layer, bias is not None
+        ctx.wbuf, ctx.bbuf = _param_grad_buf(weight), _param_grad_buf(bias)
+        _track_use(ctx, ctx.needs_input_grad[1], ctx.wbuf, ctx.bbuf)
+        ctx.save_for_backward(x_lo, weight)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        from . import upconv
+
+        layer: ConvLayer = ctx.layer
+        x_lo, weight = ctx.saved_tensors
+        dy = g_out.contiguous()  # (its ring is zeroed in place below: this node is the only consumer of g_out)
+        gb = gw = None
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            tgt = ctx.bbuf if ctx.bbuf is not None else torch.zeros(layer.cout, dtype=torch.float32, device=dy.device)
+            K.colsum(dy, tgt, layer.cout)
+            gb = None if ctx.bbuf is not None else tgt
+        wph32 = G.upconv_phase_weights(weight.detach().float())
+        gx, dw5 = upconv.backward(upconv.GpuLauncher(), dy, x_lo, wph32, need_dx=ctx.needs_input_grad[0],
+                                  need_dw=ctx.needs_input_grad[1])
+        if dw5 is not None:
+            tgt = ctx.wbuf if ctx.wbuf is not None else _grad_like_cl(weight)
+            _cl_weight(tgt).add_(dw5.reshape(-1))
+            gw = None if ctx.wbuf is not None else tgt
+        _track_done(ctx)
+        return gx, gw, gb, None
 
 
 def _want_halo(kh, kw, out_h, out_w) -> int:

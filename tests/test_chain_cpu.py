@@ -53,3 +53,8 @@ def test_phase_form_schedule_is_opt_in_and_forward_only(monkeypatch):
     N.run_chain(list(dec.model), Act(torch.zeros(1), 1), 0)  # autograd on: the default schedule
     assert calls[3:5] == [("res", 2, 2, False), ("conv5", 2, 2, False)]
     assert not ops.upconv_phase_ok(dec.model[0].model[0].model[0].layer)  # 3x3 layers never qualify
+    # level 2: the training pass uses the phase form as well
+    monkeypatch.setattr(ops, "UPCONV_PHASE", 2)
+    calls.clear()
+    N.run_chain(list(dec.model), Act(torch.zeros(1), 1), 0)
+    assert calls == [("res", 1, 1, False)] * 4 + [("conv5", 1, 1, True), ("conv5", 3, 1, True), ("conv7", 0, 1, False)]

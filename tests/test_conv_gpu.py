@@ -302,3 +302,35 @@ def test_upconv_phase_forward(n, h, cin, cout):
     ring = torch.ones_like(ref, dtype=torch.bool)
     ring[:, :, 1:-1, 1:-1] = False
     assert float((got[ring] - ref[ring]).norm() / ref[ring].norm()) < 1e-2
+
+
+@pytest.mark.parametrize("n,h,cin,cout", [(2, 16, 256, 128), (1, 32, 128, 64)])
+def test_upconv_phase_training_function(n, h, cin, cout):
+    """EXPERIMENTAL (MUNIT_UPCONV_PHASE=2; skipped otherwise -- not yet run on a GPU; the orchestration is verified on
+    the CPU in tests/test_upconv_cpu.py): ops.UpConvPhaseFn forward + backward against autograd of the direct form."""
+    import torch.nn.functional as F
+
+    from munit_b200 import ops
+
+    if int(ops.UPCONV_PHASE) < 2:
+        pytest.skip("set MUNIT_UPCONV_PHASE=2 to run the experimental phase-form training path")
+    torch.manual_seed(0)
+    x = torch.randn(n, cin, h, h).to(torch.bfloat16).float()
+    wt = (torch.randn(cout, cin, 5, 5) * (2.0 / (25 * cin)) ** 0.5).to(torch.bfloat16).float()
+    bias = torch.randn(cout) * 0.1
+    xr, wr, br = x.clone().requires_grad_(True), wt.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    ref = F.conv2d(F.pad(F.interpolate(xr, scale_factor=2, mode="nearest"), (2,) * 4, mode="reflect"), wr, br)
+    gy = torch.randn_like(ref).to(torch.bfloat16).float()
+    ref.backward(gy)
+    layer = ops.ConvLayer(cin, cout, 5, 1, 2)
+    x_lo = F.pad(x, (1,) * 4, mode="reflect").permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda().requires_grad_(True)
+    wg = wt.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    bg = bias.cuda().requires_grad_(True)
+    y = ops.UpConvPhaseFn.apply(x_lo, wg, bg, layer)
+    assert rel_l2(y.float().cpu().permute(0, 3, 1, 2), ref.detach()) < 1e-2
+    y.backward(gy.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda())
+    gx = x_lo.grad.float().cpu().permute(0, 3, 1, 2)
+    assert float(gx[:, :, 0].abs().max()) == 0
+    assert rel_l2(gx[:, :, 1:-1, 1:-1], xr.grad) < 1e-2
+    assert rel_l2(wg.grad.cpu(), wr.grad) < 1e-2
+    assert rel_l2(bg.grad.cpu(), br.grad) < 1e-3
