@@ -14,9 +14,24 @@ by fused kernels once the path has been validated and measured on a B200 (it has
 """
 from __future__ import annotations
 
+import functools
+
 import torch
 
 from . import geometry as G
+
+
+_IDX_DEV = {}  # (id of the cached host map, device) -> device copy
+
+
+@functools.lru_cache(maxsize=None)
+def _dgrad_map(co, c, ck):
+    return G.upconv_dgrad_index_map(co, c, c, ck)
+
+
+@functools.lru_cache(maxsize=None)
+def _ring_map(co, c, ck, side):
+    return G.upconv_ring_dgrad_index_map(co, c, c, ck, side)
 
 
 class GpuLauncher:
@@ -37,8 +52,12 @@ class GpuLauncher:
     def gather(self, src_flat, idx, rows):
         from . import kernels as K
 
+        key = (id(idx), str(src_flat.device))
+        dev_idx = _IDX_DEV.get(key)
+        if dev_idx is None:  # the host maps are lru-cached objects: one upload per (shape, device)
+            dev_idx = _IDX_DEV[key] = idx.to(src_flat.device)
         dst = torch.empty(rows, idx.numel() // rows, dtype=torch.bfloat16, device=src_flat.device)
-        return K.gather_cast(src_flat, idx.to(src_flat.device), dst)
+        return K.gather_cast(src_flat.contiguous(), dev_idx, dst)
 
 
 def _tap_matrix(dtype, device):
@@ -83,13 +102,13 @@ def backward(L, gy, x_lo, wph32, need_dx=True, need_dw=True):
     if need_dx:
         ck = max(64, co)
         dxr = torch.empty(n, h + 2, w + 2, c, dtype=dt, device=dev)
-        wd = L.gather(wflat, G.upconv_dgrad_index_map(co, c, c, ck), c)
+        wd = L.gather(wflat, _dgrad_map(co, c, ck), c)
         L.tapgemm(G.plan_upconv_dgrad_interior(n, h, w, c, co), gy, wd, dxr)
         acc = dxr.float()
         for side, s in enumerate(strips):
             ln = (w if side < 2 else h) + 2
             band = torch.empty((n, 3, ln, c) if side < 2 else (n, ln, 3, c), dtype=dt, device=dev)
-            wr = L.gather(wflat, G.upconv_ring_dgrad_index_map(co, c, c, ck, side), c)
+            wr = L.gather(wflat, _ring_map(co, c, ck, side), c)
             L.tapgemm(G.plan_upconv_dgrad_ring(n, h, w, c, co, side), s.contiguous(), wr, band)
             if side == 0:
                 acc[:, 0:3] += band.float()
