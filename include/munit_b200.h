@@ -75,7 +75,10 @@ typedef struct {
   const float* bias; /* [b_rows] or NULL */
   int32_t act;
   int32_t stages;  /* 0 = auto */
-  int32_t cluster; /* CTAs per cluster sharing (multicasting) the weight tile: 0 = auto, 1, 2 or 4 */
+  int32_t out_f16; /* 1: store the output as IEEE fp16 (saturating) instead of bf16.  Used for raw conv outputs that
+                      feed a normalisation: they are only ever read by the norm kernels (never by a tensor-core
+                      operand), and the 3 extra mantissa bits keep sign(x - mean) -- the ReLU mask of
+                      networks.py:698-700 -- stable against the storage rounding (tests/test_networks_gpu.py) */
   int32_t halo;    /* 1: halo-resident variant (stride-1 rank-4 view, one phase, tw x th x tn = 8 x 16 x 1, taps on a
                       full KH x KW grid, KW <= 9): the activation tile + halo is loaded once per 64-channel chunk and
                       every tap reads it through a shifted UMMA descriptor.  0: one TMA box per tap. */
@@ -91,7 +94,7 @@ typedef struct {
   int32_t ksplit;  /* > 1: split the (tap, chunk) loop over ksplit CTAs per tile; each adds its fp32 partial tile to
                       `scratch` (red.global.add) and nothing is written to `out`, bias / act are not applied:
                       follow with munit_splitk_finish.  For layers with too few output tiles to fill the GPU
-                      (the deep discriminator layers).  Excludes halo, stats and cluster. */
+                      (the deep discriminator layers).  Excludes halo and stats. */
   float* scratch;  /* zero-initialised fp32 buffer with exactly the element geometry of `out` (same o_s* strides) */
 } munit_tapgemm_desc;
 
@@ -131,14 +134,12 @@ typedef struct {
   int32_t ksplit;   /* 0 = auto */
   int32_t stages;   /* 0 = auto */
   int32_t tap_on_a; /* 1: tap offsets shift A instead of B (swapped orientation A = X, B = dY) */
-  int32_t row_taps; /* > 0: row-sharing variant for stride-1 convs -- one CTA owns `row_taps` consecutive taps (a kernel
-                       row), loads dY and one widened X box per 8x8 pixel block and feeds each tap through a shifted
-                       UMMA descriptor into its own TMEM accumulator (row_taps * bn <= 512, bn <= 128) */
 } munit_wgrad_desc;
 
-/* out[i] = bf16(act(scratch[i] + bias[i % c])) over n contiguous elements (c = innermost channel extent, bias may
- * be NULL): the second half of a split-K munit_tapgemm. */
-int munit_splitk_finish(const float* scratch, const float* bias, int act, void* out, int64_t n, int c, void* stream);
+/* out[i] = bf16 (or fp16 when out_f16 != 0) of act(scratch[i] + bias[i % c]) over n contiguous elements (c =
+ * innermost channel extent, bias may be NULL): the second half of a split-K munit_tapgemm. */
+int munit_splitk_finish(const float* scratch, const float* bias, int act, void* out, int out_f16, int64_t n, int c,
+                        void* stream);
 
 int munit_wgrad(const munit_wgrad_desc* d, void* stream);
 
@@ -167,10 +168,11 @@ int munit_halo_fill(void* act, int n, int h, int w, int c, int pad, void* stream
 /* Number of pixel splits S the per-(n,c) reductions use for (hw, c); workspaces `stats` / `sums` below hold
  * N*S*C*2 floats.  Partials are added in a fixed order by the finalize calls (bit-reproducible). */
 int munit_norm_splits(int hw, int c);
-/* Per-(n,c) shifted sums over H*W of y [N][H][W][C] bf16:
+/* Per-(n,c) shifted sums over H*W of y [N][H][W][C] (bf16, or IEEE fp16 when y_f16 != 0 -- see
+ * munit_tapgemm_desc.out_f16; the same flag on the three calls below that read y):
  * stats[((n*S+s)*C+c)*2 + {0,1}] = split-s partial of {sum(x - sh), sum((x - sh)^2)}, shift[n*C+c] = sh = y[n,0,0,c].
  * (first half of nn.InstanceNorm2d networks.py:657 / F.batch_norm networks.py:834 / LayerNorm :865-871) */
-int munit_norm_stats(const void* y, float* stats, float* shift, int n, int hw, int c, void* stream);
+int munit_norm_stats(const void* y, int y_f16, float* stats, float* shift, int n, int hw, int c, void* stream);
 
 enum { MUNIT_NORM_IN = 0, MUNIT_NORM_ADAIN = 1, MUNIT_NORM_LN = 2 };
 /* stats -> per-(n,c) mean, rinv, and the affine (a, b) with out = a*x + b.
@@ -187,13 +189,13 @@ int munit_norm_finalize_parts(const float* stats, int splits, int kind, int mode
                               int c, void* stream);
 /* out_act[interior (+halo) (+2x nearest upsample)] = relu?(a*y + b) (+ residual interior).
  * residual (may be NULL) is an act buffer with halo res_pad and the same H, W, C. */
-int munit_norm_apply(const void* y, const float* a, const float* b, int relu, const void* residual, int res_pad,
+int munit_norm_apply(const void* y, int y_f16, const float* a, const float* b, int relu, const void* residual, int res_pad,
                      void* out_act, int out_pad, int upsample, int n, int h, int w, int c, void* stream);
 
 /* Backward of norm_apply + norm: g_out is the gradient w.r.t. out_act (full padded / upsampled extent).
  * pass 1: sums[(n*C+c)*2+{0,1}] = {sum dz, sum dz*xhat}, dz = fold(g_out) * relu'(a*y+b). */
-int munit_norm_bwd_reduce(const void* g_out, int out_pad, int upsample, const void* y, const float* a, const float* b,
-                          int relu, const float* mean, const float* rinv, float* sums, int n, int h, int w, int c,
+int munit_norm_bwd_reduce(const void* g_out, int out_pad, int upsample, const void* y, int y_f16, const float* a,
+                          const float* b, int relu, const float* mean, const float* rinv, float* sums, int n, int h, int w, int c,
                           void* stream);
 /* sums -> dx coefficients (ca, cb, cc): dx = ca*dz + cb*xhat + cc; parameter grads:
  * ADAIN: g_w[n*ldg + c] = sum dz*xhat, g_b[n*ldg + c] = sum dz; LN: g_w[c], g_b[c] summed over n (+=). */
@@ -201,40 +203,9 @@ int munit_norm_bwd_finalize(const float* sums, int mode, const float* p_w, int64
                             float* ca, float* cb, float* cc, float* g_w, float* g_b, int64_t ldg, int n, int hw, int c,
                             void* stream);
 /* pass 2: dy [N][H][W][C] bf16 = ca*dz + cb*xhat + cc; optional g_res (act buffer, halo res_pad, halo zeroed) = fold(g_out). */
-int munit_norm_bwd_apply(const void* g_out, int out_pad, int upsample, const void* y, const float* a, const float* b,
-                         int relu, const float* mean, const float* rinv, const float* ca, const float* cb,
+int munit_norm_bwd_apply(const void* g_out, int out_pad, int upsample, const void* y, int y_f16, const float* a,
+                         const float* b, int relu, const float* mean, const float* rinv, const float* ca, const float* cb,
                          const float* cc, void* dy, void* g_res, int res_pad, int n, int h, int w, int c, void* stream);
-
-/* Fused variants: ONE cooperative launch runs statistics -> finalize -> apply (forward) or reduce -> finalize ->
- * apply (backward) with grid-wide barriers in between, so the second read of y / g_out is served by L2 when the
- * caller keeps n*(bytes per sample) within it (munit_b200/kernels.py chunks the batch) and two kernel boundaries
- * per normalisation disappear.  Arguments mean what they mean in the three stand-alone calls above; `part` is the
- * split-partial workspace of N*S*C*2 floats with S = munit_norm_fused_splits(...).  That call returns 0 when the
- * shape cannot be co-resident on the device (caller falls back to the three-call sequence). */
-int munit_norm_fused_splits(int n, int hw, int c, int mode, int backward, int upsample);
-int munit_norm_fwd_fused(const void* y, float* part, float* shift, int mode, const float* p_w, const float* p_b,
-                         int64_t ldw, float eps, float* mean, float* rinv, float* a, float* b, int relu,
-                         const void* residual, int res_pad, void* out_act, int out_pad, int upsample, int n, int h, int w,
-                         int c, void* stream);
-int munit_norm_bwd_fused(const void* g_out, int out_pad, int upsample, const void* y, const float* a, const float* b,
-                         int relu, const float* mean, const float* rinv, float* part, int mode, const float* p_w,
-                         int64_t ldw, float eps, float* ca, float* cb, float* cc, float* g_w, float* g_b, int64_t ldg,
-                         void* dy, void* g_res, int res_pad, int n, int h, int w, int c, void* stream);
-
-/* Slab-resident InstanceNorm / AdaIN: a thread-block cluster owns (sample, 16 channels), keeps its part of the slab
- * in shared memory between the statistics and the apply pass and combines the per-CTA sums over distributed
- * shared memory - one launch and one DRAM pass over the inputs instead of three launches and two passes.
- * munit_norm_slab_ok returns the cluster size (> 0) when (mode, upsample, hw, c) can run this way (IN / ADAIN,
- * upsample 1, c % 16 == 0, hw <= 16384 forward / backward), else 0.  Arguments as in the stand-alone calls; the
- * forward also writes mean / rinv / a / b for the backward. */
-int munit_norm_slab_ok(int mode, int upsample, int hw, int c, int backward);
-int munit_norm_fwd_slab(const void* y, int mode, const float* p_w, const float* p_b, int64_t ldw, float eps,
-                        float* mean, float* rinv, float* a, float* b, int relu, const void* residual, int res_pad,
-                        void* out_act, int out_pad, int n, int h, int w, int c, void* stream);
-int munit_norm_bwd_slab(const void* g_out, int out_pad, const void* y, const float* a, const float* b, int relu,
-                        const float* mean, const float* rinv, int mode, const float* p_w, int64_t ldw, float* g_w,
-                        float* g_b, int64_t ldg, void* dy, void* g_res, int res_pad, int n, int h, int w, int c,
-                        void* stream);
 
 /* No-norm conv blocks: dy [N][H][W][C] = fold(g_out_act) * act'(out) where out is the forward output
  * (interior of out_act, halo `pad`; g_out has the same padded extent). */

@@ -30,7 +30,7 @@ class TapGemmDesc(C.Structure):
         ("o_yoff", C.c_int32 * MAX_PHASES), ("o_xoff", C.c_int32 * MAX_PHASES),
         ("out", C.c_void_p), ("o_sn", C.c_int64), ("o_sy", C.c_int64), ("o_sx", C.c_int64),
         ("o_ymul", C.c_int32), ("o_xmul", C.c_int32), ("n_store", C.c_int32),
-        ("bias", C.c_void_p), ("act", C.c_int32), ("stages", C.c_int32), ("cluster", C.c_int32), ("halo", C.c_int32),
+        ("bias", C.c_void_p), ("act", C.c_int32), ("stages", C.c_int32), ("out_f16", C.c_int32), ("halo", C.c_int32),
         ("stats", C.c_void_p), ("stats_kind", C.c_int32), ("ksplit", C.c_int32), ("scratch", C.c_void_p),
     ]
 
@@ -46,7 +46,7 @@ class WgradDesc(C.Structure):
         ("m_total", C.c_int32), ("n_total", C.c_int32), ("bn", C.c_int32), ("num_taps", C.c_int32),
         ("tap_off", (C.c_int32 * 5) * MAX_TAPS),
         ("dw", C.c_void_p), ("s_m", C.c_int64), ("s_t", C.c_int64), ("s_n", C.c_int64),
-        ("ksplit", C.c_int32), ("stages", C.c_int32), ("tap_on_a", C.c_int32), ("row_taps", C.c_int32),
+        ("ksplit", C.c_int32), ("stages", C.c_int32), ("tap_on_a", C.c_int32),
     ]
 
 
@@ -64,7 +64,7 @@ _SIGS = {
     "munit_init": ([], C.c_int),
     "munit_error_flag_ptr": ([C.POINTER(C.c_void_p)], C.c_int),
     "munit_tapgemm": ([C.POINTER(TapGemmDesc), _vp], C.c_int),
-    "munit_splitk_finish": ([_vp, _vp, _i, _vp, _i64, _i, _vp], C.c_int),
+    "munit_splitk_finish": ([_vp, _vp, _i, _vp, _i, _i64, _i, _vp], C.c_int),
     "munit_wgrad": ([C.POINTER(WgradDesc), _vp], C.c_int),
     "munit_image_to_act": ([_vp, _vp, _i, _i, _i, _i, _i, _i, _vp], C.c_int),
     "munit_image_to_kwexp": ([_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp], C.c_int),
@@ -73,23 +73,13 @@ _SIGS = {
     "munit_nchw_to_act": ([_vp, _vp, _i, _i, _i, _i, _i, _i, _vp], C.c_int),
     "munit_halo_fill": ([_vp, _i, _i, _i, _i, _i, _vp], C.c_int),
     "munit_norm_splits": ([_i, _i], C.c_int),
-    "munit_norm_stats": ([_vp, _vp, _vp, _i, _i, _i, _vp], C.c_int),
+    "munit_norm_stats": ([_vp, _i, _vp, _vp, _i, _i, _i, _vp], C.c_int),
     "munit_norm_finalize": ([_vp, _vp, _i, _vp, _vp, _i64, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp], C.c_int),
     "munit_norm_finalize_parts": ([_vp, _i, _i, _i, _vp, _vp, _i64, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp], C.c_int),
-    "munit_norm_apply": ([_vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp], C.c_int),
-    "munit_norm_bwd_reduce": ([_vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp], C.c_int),
+    "munit_norm_apply": ([_vp, _i, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp], C.c_int),
+    "munit_norm_bwd_reduce": ([_vp, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp], C.c_int),
     "munit_norm_bwd_finalize": ([_vp, _i, _vp, _i64, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp], C.c_int),
-    "munit_norm_bwd_apply": ([_vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], C.c_int),
-    "munit_norm_fused_splits": ([_i, _i, _i, _i, _i, _i], C.c_int),
-    "munit_norm_fwd_fused": ([_vp, _vp, _vp, _i, _vp, _vp, _i64, _f, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i,
-                              _i, _i, _vp], C.c_int),
-    "munit_norm_bwd_fused": ([_vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i64, _f, _vp, _vp, _vp, _vp, _vp,
-                              _i64, _vp, _vp, _i, _i, _i, _i, _i, _vp], C.c_int),
-    "munit_norm_slab_ok": ([_i, _i, _i, _i, _i], C.c_int),
-    "munit_norm_fwd_slab": ([_vp, _i, _vp, _vp, _i64, _f, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
-                            C.c_int),
-    "munit_norm_bwd_slab": ([_vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i,
-                             _i, _vp], C.c_int),
+    "munit_norm_bwd_apply": ([_vp, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], C.c_int),
     "munit_act_bwd": ([_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp], C.c_int),
     "munit_colsum": ([_vp, _vp, _i64, _i, _i, _vp], C.c_int),
     "munit_rspace_combine": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], C.c_int),

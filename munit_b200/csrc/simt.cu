@@ -1,16 +1,14 @@
 // Bandwidth-bound SIMT kernels of the MUNIT hot path (sm_100a): layout conversion, reflect halo,
 // InstanceNorm / AdaIN / LayerNorm forward+backward, activations, pooling, losses, MLP, Adam.
 // All activations are NHWC bf16 accessed as 128-bit (8-channel) vectors; statistics are fp32.
-#include <cooperative_groups.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
 
 #include "../../include/munit_b200.h"
 #include "common.h"
-
-namespace cg = cooperative_groups;
 
 namespace {
 
@@ -42,6 +40,29 @@ __device__ __forceinline__ F8 unpack8(const uint4& u) {
     r.v[2 * i + 1] = f.y;
   }
   return r;
+}
+// Raw convolution outputs in front of a normalisation are stored as IEEE fp16 (munit_tapgemm_desc.out_f16): H = true
+// decodes such a 128-bit vector, H = false the usual bf16 one.
+template <bool H>
+__device__ __forceinline__ F8 unpack8y(const uint4& u) {
+  if (!H) return unpack8(u);
+  F8 r;
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h[i]);
+    r.v[2 * i] = f.x;
+    r.v[2 * i + 1] = f.y;
+  }
+  return r;
+}
+template <bool H>
+__device__ __forceinline__ F8 load8y(const bf16* p) {
+  return unpack8y<H>(*reinterpret_cast<const uint4*>(p));
+}
+template <bool H>
+__device__ __forceinline__ float scalar_y(const bf16* p) {
+  return H ? __half2float(*reinterpret_cast<const __half*>(p)) : __bfloat162float(*p);
 }
 __device__ __forceinline__ uint4 pack8(const F8& r) {
   uint4 u;
@@ -316,12 +337,13 @@ __device__ __forceinline__ void sum_splits_to_smem(const float* __restrict__ par
   __syncthreads();
 }
 
+template <bool H>
 __device__ __forceinline__ void norm_stats_body(Blk blk, const bf16* __restrict__ y, float* __restrict__ stats,
                                                 float* __restrict__ shift, int hw, int c) {
   const int cg_own = threadIdx.x % (c / 8);
-  const F8 s = load8(y + ((long long)blk.by * hw) * c + cg_own * 8);  // per-thread constant: hoisted
+  const F8 s = load8y<H>(y + ((long long)blk.by * hw) * c + cg_own * 8);  // per-thread constant: hoisted
   auto fn = [&](int n, int pix, int cg, F8& u, F8& v) {
-    const F8 x = load8(y + ((long long)n * hw + pix) * c + cg * 8);
+    const F8 x = load8y<H>(y + ((long long)n * hw + pix) * c + cg * 8);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float d = x.v[e] - s.v[e];
@@ -332,13 +354,14 @@ __device__ __forceinline__ void norm_stats_body(Blk blk, const bf16* __restrict_
   reduce_nc(blk, fn, stats, hw, c);
   if (blk.bx == 0)
     for (int ch = threadIdx.x; ch < c; ch += blockDim.x)
-      shift[(long long)blk.by * c + ch] = __bfloat162float(y[((long long)blk.by * hw) * c + ch]);
+      shift[(long long)blk.by * c + ch] = scalar_y<H>(y + ((long long)blk.by * hw) * c + ch);
 }
+template <bool H>
 __global__ void norm_stats_kernel(const bf16* __restrict__ y, float* __restrict__ stats, float* __restrict__ shift,
                                   int hw, int c) {
   pdl_wait();
   pdl_trigger();
-  norm_stats_body(launch_blk(), y, stats, shift, hw, c);
+  norm_stats_body<H>(launch_blk(), y, stats, shift, hw, c);
 }
 
 __global__ void colsum_kernel(const bf16* __restrict__ dy, float* __restrict__ out, long long npix, int c, int c_out) {
@@ -606,7 +629,7 @@ __global__ void norm_finalize_ln_total_kernel(const float* __restrict__ part, in
 
 // Block = CG channel groups x R rows (256 threads), grid = (pixel splits, N): a thread keeps its (n, channel
 // group) coefficients in registers and walks pixels, so the per-(n,c) vectors are read once per thread.
-template <int UP>
+template <int UP, bool H>
 __device__ __forceinline__ void norm_apply_body(Blk blk, const bf16* __restrict__ y, const float* __restrict__ a,
                                                 const float* __restrict__ b, int relu, const bf16* __restrict__ res,
                                                 int res_pad, bf16* __restrict__ out, int out_pad, int n, int h, int w,
@@ -625,7 +648,7 @@ __device__ __forceinline__ void norm_apply_body(Blk blk, const bf16* __restrict_
 #pragma unroll 2
   for (int pix = p0 + r; pix < p1; pix += rows) {
     const int yy = pix / w, x = pix - yy * w;
-    F8 v = load8(y + ((long long)bb * hw + pix) * c + g * 8);
+    F8 v = load8y<H>(y + ((long long)bb * hw + pix) * c + g * 8);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float o = fmaf(v.v[e], fa.v[e], fb.v[e]);
@@ -658,13 +681,13 @@ __device__ __forceinline__ void norm_apply_body(Blk blk, const bf16* __restrict_
     }
   }
 }
-template <int UP>
+template <int UP, bool H>
 __global__ void norm_apply_kernel(const bf16* __restrict__ y, const float* __restrict__ a, const float* __restrict__ b,
                                   int relu, const bf16* __restrict__ res, int res_pad, bf16* __restrict__ out,
                                   int out_pad, int n, int h, int w, int c) {
   pdl_wait();
   pdl_trigger();
-  norm_apply_body<UP>(launch_blk(), y, a, b, relu, res, res_pad, out, out_pad, n, h, w, c);
+  norm_apply_body<UP, H>(launch_blk(), y, a, b, relu, res, res_pad, out, out_pad, n, h, w, c);
 }
 
 // gradient w.r.t. the unpadded, un-upsampled pixel: sum of g_out over every position that copied it.
@@ -767,7 +790,7 @@ struct FoldBatch {
 
 // sums = {sum dz, sum dz*(x - mean)}; the finalize kernels multiply the second by rinv (keeps this loop at 3
 // coefficient vectors so that four blocks fit per SM).
-template <int UP>
+template <int UP, bool H>
 __device__ __forceinline__ void norm_bwd_reduce_body(Blk blk, const bf16* __restrict__ g_out, int out_pad,
                                                      const bf16* __restrict__ y, const float* __restrict__ a,
                                                      const float* __restrict__ b, int relu,
@@ -806,7 +829,7 @@ __device__ __forceinline__ void norm_bwd_reduce_body(Blk blk, const bf16* __rest
         if (pix < p1) {
           const int yy = pix / w, x = pix - yy * w;
           const F8 g = fold_finish<UP>(gr[u], gbase, yy, x, h, w, c, out_pad);
-          const F8 xv = unpack8(yv[u]);
+          const F8 xv = unpack8y<H>(yv[u]);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             float dz = g.v[e];
@@ -819,7 +842,7 @@ __device__ __forceinline__ void norm_bwd_reduce_body(Blk blk, const bf16* __rest
     }
   reduce_nc_tail(blk, s0, s1, sums, c);
 }
-template <int UP>
+template <int UP, bool H>
 __global__ void __launch_bounds__(256, 2)
 norm_bwd_reduce_kernel(const bf16* __restrict__ g_out, int out_pad, const bf16* __restrict__ y,
                                        const float* __restrict__ a, const float* __restrict__ b, int relu,
@@ -827,7 +850,7 @@ norm_bwd_reduce_kernel(const bf16* __restrict__ g_out, int out_pad, const bf16* 
                                        float* __restrict__ sums, int h, int w, int c) {
   pdl_wait();
   pdl_trigger();
-  norm_bwd_reduce_body<UP>(launch_blk(), g_out, out_pad, y, a, b, relu, mean, sums, h, w, c);
+  norm_bwd_reduce_body<UP, H>(launch_blk(), g_out, out_pad, y, a, b, relu, mean, sums, h, w, c);
 }
 
 // one block per sample
@@ -909,7 +932,7 @@ __global__ void norm_bwd_finalize_kernel(const float* __restrict__ sums, int spl
   norm_bwd_finalize_body(blockIdx.x, sums, splits, mode, p_w, ldw, rinv, eps, ca, cb, cc, g_w, g_b, ldg, hw, c);
 }
 
-template <int UP>
+template <int UP, bool H>
 __device__ __forceinline__ void norm_bwd_apply_body(Blk blk, const bf16* __restrict__ g_out, int out_pad,
                                                     const bf16* __restrict__ y, const float* __restrict__ a,
                                                     const float* __restrict__ b, int relu,
@@ -956,7 +979,7 @@ __device__ __forceinline__ void norm_bwd_apply_body(Blk blk, const bf16* __restr
       if (pix < p1) {
         const int yy = pix / w, x = pix - yy * w;
         const F8 gr = fold_finish<UP>(graw[u], gbase, yy, x, h, w, c, out_pad);
-        const F8 xv = unpack8(yv[u]);
+        const F8 xv = unpack8y<H>(yv[u]);
         F8 d;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -985,7 +1008,7 @@ __device__ __forceinline__ void norm_bwd_apply_body(Blk blk, const bf16* __restr
     }
   }
 }
-template <int UP>
+template <int UP, bool H>
 __global__ void __launch_bounds__(256, 2)
 norm_bwd_apply_kernel(const bf16* __restrict__ g_out, int out_pad, const bf16* __restrict__ y,
                                       const float* __restrict__ a, const float* __restrict__ b, int relu,
@@ -995,78 +1018,7 @@ norm_bwd_apply_kernel(const bf16* __restrict__ g_out, int out_pad, const bf16* _
                                       int res_pad, int n, int h, int w, int c) {
   pdl_wait();
   pdl_trigger();
-  norm_bwd_apply_body<UP>(launch_blk(), g_out, out_pad, y, a, b, relu, mean, rinv, ca, cb, cc, dy, g_res, res_pad, n, h, w, c);
-}
-
-// ---- fused cooperative norm kernels: reduce -> grid sync -> finalize -> grid sync -> apply in ONE launch.  The
-// second read of y / g_out then comes from L2 (the host side sizes the sample chunk of a launch to fit), and two
-// kernel boundaries per normalisation disappear.  The phases are the bodies of the stand-alone kernels above, so
-// the arithmetic is identical up to the number of pixel splits.
-struct NormFusedArgs {
-  const bf16* y;
-  float* part;  // [n][splits][c][2] split partials (stats in the forward, sums in the backward)
-  float* shift;
-  int mode;
-  const float* p_w;
-  const float* p_b;
-  long long ldw;
-  float eps;
-  float *mean, *rinv, *a, *b;
-  int relu;
-  const bf16* res;  // fwd: residual input; bwd: unused
-  int res_pad;
-  bf16* out;  // fwd: output act
-  int out_pad;
-  // backward only
-  const bf16* g_out;
-  float *ca, *cb, *cc, *g_w, *g_b;
-  long long ldg;
-  bf16* dy;
-  bf16* g_res;
-  int n, h, w, c;
-};
-
-template <int UP>
-__global__ void __launch_bounds__(256, 3) norm_fwd_fused_kernel(const NormFusedArgs p) {
-  pdl_wait();
-  pdl_trigger();
-  cg::grid_group grid = cg::this_grid();
-  const Blk blk = launch_blk();
-  const int hw = p.h * p.w;
-  norm_stats_body(blk, p.y, p.part, p.shift, hw, p.c);
-  grid.sync();
-  if (p.mode != MUNIT_NORM_LN) {
-    if (blk.bx < (p.c + 31) / 32)
-      norm_finalize_nc_body(blk.bx, blk.by, p.part, blk.nbx, p.shift, p.mode == MUNIT_NORM_ADAIN, p.p_w, p.p_b, p.ldw,
-                            p.eps, p.mean, p.rinv, p.a, p.b, hw, p.c);
-  } else if (blk.bx == 0) {
-    norm_finalize_body(blk.by, p.part, blk.nbx, p.shift, p.mode, p.p_w, p.p_b, p.ldw, p.eps, p.mean, p.rinv, p.a, p.b,
-                       hw, p.c);
-  }
-  grid.sync();
-  norm_apply_body<UP>(blk, p.y, p.a, p.b, p.relu, p.res, p.res_pad, p.out, p.out_pad, p.n, p.h, p.w, p.c);
-}
-
-template <int UP>
-__global__ void __launch_bounds__(256, 2) norm_bwd_fused_kernel(const NormFusedArgs p) {
-  pdl_wait();
-  pdl_trigger();
-  cg::grid_group grid = cg::this_grid();
-  const Blk blk = launch_blk();
-  const int hw = p.h * p.w;
-  norm_bwd_reduce_body<UP>(blk, p.g_out, p.out_pad, p.y, p.a, p.b, p.relu, p.mean, p.part, p.h, p.w, p.c);
-  grid.sync();
-  if (p.mode != MUNIT_NORM_LN) {
-    if (blk.bx < (p.c + 31) / 32)
-      norm_bwd_finalize_nc_body(blk.bx, blk.by, p.part, blk.nbx, p.mode == MUNIT_NORM_ADAIN, p.p_w, p.ldw, p.rinv,
-                                p.ca, p.cb, p.cc, p.g_w, p.g_b, p.ldg, hw, p.c);
-  } else if (blk.bx == 0) {
-    norm_bwd_finalize_body(blk.by, p.part, blk.nbx, p.mode, p.p_w, p.ldw, p.rinv, p.eps, p.ca, p.cb, p.cc, p.g_w,
-                           p.g_b, p.ldg, hw, p.c);
-  }
-  grid.sync();
-  norm_bwd_apply_body<UP>(blk, p.g_out, p.out_pad, p.y, p.a, p.b, p.relu, p.mean, p.rinv, p.ca, p.cb, p.cc, p.dy,
-                          p.g_res, p.res_pad, p.n, p.h, p.w, p.c);
+  norm_bwd_apply_body<UP, H>(launch_blk(), g_out, out_pad, y, a, b, relu, mean, rinv, ca, cb, cc, dy, g_res, res_pad, n, h, w, c);
 }
 
 __global__ void act_bwd_kernel(const bf16* __restrict__ g_out, const bf16* __restrict__ out_act, int pad, int act,
@@ -1491,7 +1443,7 @@ __global__ void l1_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b, 
 
 // Second half of a split-K tap-GEMM: fp32 partial sums -> (+bias) -> activation -> bf16, 8 elements per thread.
 __global__ void splitk_finish_kernel(const float* __restrict__ scratch, const float* __restrict__ bias, int act,
-                                     bf16* __restrict__ out, long long n8, int c) {
+                                     bf16* __restrict__ out, long long n8, int c, int out_f16) {
   pdl_wait();
   pdl_trigger();
   const float slope = act == MUNIT_ACT_RELU ? 0.f : (act == MUNIT_ACT_LRELU ? 0.2f : 1.f);
@@ -1504,7 +1456,16 @@ __global__ void splitk_finish_kernel(const float* __restrict__ scratch, const fl
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) v.v[e] = act == MUNIT_ACT_TANH ? tanhf(v.v[e]) : fmaxf(v.v[e], slope * v.v[e]);
-    store8(out + i * 8, v);
+    if (out_f16) {
+      uint4 u;
+      __half2* hh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        hh[e] = __floats2half2_rn(fminf(fmaxf(v.v[2 * e], -65504.f), 65504.f), fminf(fmaxf(v.v[2 * e + 1], -65504.f), 65504.f));
+      *reinterpret_cast<uint4*>(out + i * 8) = u;
+    } else {
+      store8(out + i * 8, v);
+    }
   }
 }
 
@@ -1610,321 +1571,6 @@ __global__ void add_bf16_kernel(bf16* __restrict__ dst, const bf16* __restrict__
 }
 
 
-// ---- slab-resident InstanceNorm / AdaIN (one launch, one DRAM pass over the inputs) ---------------------------
-// IN / AdaIN statistics are independent per (sample, channel), so a thread-block cluster can own the slab
-// (sample n, 16 channels): each CTA of the cluster takes a pixel range, parks its part of the slab in shared memory
-// while it accumulates the sums, the per-CTA sums are combined over distributed shared memory in rank order
-// (deterministic), and the apply pass then reads shared memory instead of DRAM / L2.  No grid-wide barrier, 32 B
-// (full-sector) accesses per pixel.  Shapes whose slab does not fit (hw / 16 > the per-CTA pixel budget), LayerNorm
-// and the up-sampling apply use the three-kernel path.
-__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t slab_cluster_rank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t slab_cluster_size() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void slab_cluster_sync() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ float ld_dsmem_f32(const float* local, uint32_t rank) {
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_addr_u32(local)), "r"(rank));
-  float v;
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
-  return v;
-}
-// Sum this block's per-thread {u, v} 8-channel vectors (thread parity = which 8-channel half of the 16-channel
-// slab) into cpart[16][2] in a fixed order: xor-shuffles over equal-parity lanes, then the 8 warps in index order.
-__device__ __forceinline__ void slab_block_reduce(const float* s0, const float* s1, float (*wred)[2][8][2],
-                                                  float (*cpart)[2]) {
-  float a[8], b[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    a[e] = s0[e];
-    b[e] = s1[e];
-  }
-#pragma unroll
-  for (int o = 2; o < 32; o <<= 1) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      a[e] += __shfl_xor_sync(0xffffffffu, a[e], o);
-      b[e] += __shfl_xor_sync(0xffffffffu, b[e], o);
-    }
-  }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane < 2) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      wred[warp][lane][e][0] = a[e];
-      wred[warp][lane][e][1] = b[e];
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    const int ch = threadIdx.x >> 1, k = threadIdx.x & 1;
-    float t = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += wred[w][ch >> 3][ch & 7][k];
-    cpart[ch][k] = t;
-  }
-}
-
-struct NormSlabArgs {
-  const bf16* y;
-  int mode;  // MUNIT_NORM_IN or MUNIT_NORM_ADAIN
-  const float* p_w;
-  const float* p_b;
-  long long ldw;
-  float eps;
-  float *mean, *rinv, *a, *b;
-  int relu;
-  const bf16* res;
-  int res_pad;
-  bf16* out;
-  int out_pad;
-  // backward
-  const bf16* g_out;
-  float *g_w, *g_b;
-  long long ldg;
-  bf16* dy;
-  bf16* g_res;
-  int n, h, w, c;
-  int per;  // pixels per CTA
-};
-
-__global__ void __launch_bounds__(256, 4) norm_fwd_slab_kernel(const NormSlabArgs p) {
-  pdl_wait();
-  pdl_trigger();
-  extern __shared__ __align__(16) uint8_t slab_raw[];
-  uint4* slab = reinterpret_cast<uint4*>(slab_raw);  // [per][2] 8-channel chunks of y
-  __shared__ float wred[8][2][8][2];
-  __shared__ float cpart[16][2];
-  __shared__ float coef[16][2];
-  const uint32_t rank = slab_cluster_rank(), csize = slab_cluster_size();
-  const int cg16 = blockIdx.x / csize, n = blockIdx.y;
-  const int hw = p.h * p.w, c = p.c;
-  const int p0 = rank * p.per, p1 = min(hw, p0 + p.per);
-  const int half = threadIdx.x & 1, pr = threadIdx.x >> 1;
-  const int ch0 = cg16 * 16 + half * 8;
-  const bf16* ybase = p.y + (long long)n * hw * c + ch0;
-  const F8 sh = load8(ybase);  // shift = the sample's first pixel (same value in every CTA of the slab)
-  float s0[8], s1[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) s0[e] = s1[e] = 0.f;
-  constexpr int U = 8;
-  for (int pb = p0 + pr; pb < p1; pb += 128 * U) {
-    uint4 raw[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) raw[u] = *reinterpret_cast<const uint4*>(ybase + (long long)min(pb + u * 128, p1 - 1) * c);
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int pix = pb + u * 128;
-      if (pix < p1) {
-        slab[(pix - p0) * 2 + half] = raw[u];
-        const F8 x = unpack8(raw[u]);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float d = x.v[e] - sh.v[e];
-          s0[e] += d;
-          s1[e] = fmaf(d, d, s1[e]);
-        }
-      }
-    }
-  }
-  slab_block_reduce(s0, s1, wred, cpart);
-  slab_cluster_sync();  // every CTA's cpart is complete and visible cluster-wide
-  if (threadIdx.x < 16) {
-    const int ch = cg16 * 16 + threadIdx.x;
-    double a1 = 0.0, a2 = 0.0;
-    for (uint32_t r = 0; r < csize; ++r) {
-      a1 += (double)ld_dsmem_f32(&cpart[threadIdx.x][0], r);
-      a2 += (double)ld_dsmem_f32(&cpart[threadIdx.x][1], r);
-    }
-    const double cnt = (double)hw;
-    const double m1 = a1 / cnt;
-    double var = a2 / cnt - m1 * m1;  // biased (F.batch_norm / InstanceNorm2d)
-    if (var < 0.0) var = 0.0;
-    const float shv = __bfloat162float(p.y[(long long)n * hw * c + ch]);
-    const float mu = (float)((double)shv + m1);
-    const float ri = (float)(1.0 / sqrt(var + (double)p.eps));
-    float wv = 1.f, bv = 0.f;
-    if (p.mode == MUNIT_NORM_ADAIN) {
-      wv = p.p_w[(long long)n * p.ldw + ch];
-      bv = p.p_b[(long long)n * p.ldw + ch];
-    }
-    const float aa = ri * wv, bb = bv - mu * aa;
-    coef[threadIdx.x][0] = aa;
-    coef[threadIdx.x][1] = bb;
-    if (rank == 0) {
-      const long long i = (long long)n * c + ch;
-      p.mean[i] = mu;
-      p.rinv[i] = ri;
-      p.a[i] = aa;
-      p.b[i] = bb;
-    }
-  }
-  __syncthreads();
-  float fa[8], fb[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    fa[e] = coef[half * 8 + e][0];
-    fb[e] = coef[half * 8 + e][1];
-  }
-  const int h = p.h, w = p.w, out_pad = p.out_pad, res_pad = p.res_pad;
-  const int hop = h + 2 * out_pad, wop = w + 2 * out_pad;
-  for (int pb = p0 + pr; pb < p1; pb += 128 * U) {
-    uint4 rraw[U];
-    if (p.res) {
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int pix = min(pb + u * 128, p1 - 1);
-        const int yy = pix / w, x = pix - yy * w;
-        rraw[u] = *reinterpret_cast<const uint4*>(p.res + (((long long)n * (h + 2 * res_pad) + yy + res_pad) * (w + 2 * res_pad) + x + res_pad) * c + ch0);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int pix = pb + u * 128;
-      if (pix < p1) {
-        const int yy = pix / w, x = pix - yy * w;
-        F8 v = unpack8(slab[(pix - p0) * 2 + half]);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float o = fmaf(v.v[e], fa[e], fb[e]);
-          if (p.relu) o = fmaxf(o, 0.f);
-          v.v[e] = o;
-        }
-        if (p.res) {
-          const F8 rr = unpack8(rraw[u]);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v.v[e] += rr.v[e];
-        }
-        const uint4 packed = pack8(v);
-        int prow[3], pcol[3];
-        const int nr = pad_positions(yy, h, out_pad, prow);
-        const int nc = pad_positions(x, w, out_pad, pcol);
-        for (int i = 0; i < nr; ++i)
-          for (int q = 0; q < nc; ++q)
-            *reinterpret_cast<uint4*>(p.out + (((long long)n * hop + prow[i]) * wop + pcol[q]) * c + ch0) = packed;
-      }
-    }
-  }
-  slab_cluster_sync();  // no CTA exits while a peer may still read its cpart
-}
-
-__global__ void __launch_bounds__(256, 3) norm_bwd_slab_kernel(const NormSlabArgs p) {
-  pdl_wait();
-  pdl_trigger();
-  extern __shared__ __align__(16) uint8_t slab_raw[];
-  uint4* slab = reinterpret_cast<uint4*>(slab_raw);  // [per][2][2]: y chunk, folded-gradient chunk
-  __shared__ float wred[8][2][8][2];
-  __shared__ float cpart[16][2];
-  __shared__ float coef[16][3];
-  const uint32_t rank = slab_cluster_rank(), csize = slab_cluster_size();
-  const int cg16 = blockIdx.x / csize, n = blockIdx.y;
-  const int h = p.h, w = p.w, hw = h * w, c = p.c;
-  const int p0 = rank * p.per, p1 = min(hw, p0 + p.per);
-  const int half = threadIdx.x & 1, pr = threadIdx.x >> 1;
-  const int ch0 = cg16 * 16 + half * 8;
-  const long long co = (long long)n * c + ch0;
-  const F8 fa = loadf8(p.a + co), fb = loadf8(p.b + co), fm = loadf8(p.mean + co);
-  const bf16* ybase = p.y + (long long)n * hw * c + ch0;
-  float s0[8], s1[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) s0[e] = s1[e] = 0.f;
-  constexpr int U = 4;
-  const int wop = w + 2 * p.out_pad;
-  const bf16* gbase = p.g_out + (long long)n * (h + 2 * p.out_pad) * wop * c + ch0;
-  for (int pb = p0 + pr; pb < p1; pb += 128 * U) {
-    FoldRaw<1> graw[U];
-    uint4 yraw[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int pix = min(pb + u * 128, p1 - 1);
-      const int yy = pix / w, x = pix - yy * w;
-      fold_load<1>(graw[u], gbase, yy, x, wop, c, p.out_pad);
-      yraw[u] = *reinterpret_cast<const uint4*>(ybase + (long long)pix * c);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int pix = pb + u * 128;
-      if (pix < p1) {
-        const int yy = pix / w, x = pix - yy * w;
-        const F8 g = fold_finish<1>(graw[u], gbase, yy, x, h, w, c, p.out_pad);
-        slab[((pix - p0) * 2 + half) * 2] = yraw[u];
-        slab[((pix - p0) * 2 + half) * 2 + 1] = pack8(g);
-        const F8 xv = unpack8(yraw[u]);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float dz = g.v[e];  // sums from the unrounded fold; only the parked copy is bf16
-          if (p.relu && fmaf(xv.v[e], fa.v[e], fb.v[e]) <= 0.f) dz = 0.f;
-          s0[e] += dz;
-          s1[e] = fmaf(dz, xv.v[e] - fm.v[e], s1[e]);
-        }
-      }
-    }
-  }
-  slab_block_reduce(s0, s1, wred, cpart);
-  slab_cluster_sync();
-  if (threadIdx.x < 16) {
-    const int ch = cg16 * 16 + threadIdx.x;
-    const long long i = (long long)n * c + ch;
-    double a1 = 0.0, a2 = 0.0;
-    for (uint32_t r = 0; r < csize; ++r) {
-      a1 += (double)ld_dsmem_f32(&cpart[threadIdx.x][0], r);
-      a2 += (double)ld_dsmem_f32(&cpart[threadIdx.x][1], r);
-    }
-    const double cnt = (double)hw;
-    const float ri = p.rinv[i];
-    const float wv = p.mode == MUNIT_NORM_ADAIN ? p.p_w[(long long)n * p.ldw + ch] : 1.f;
-    const float A = ri * wv;
-    a2 *= (double)ri;  // sum dz*(x-mean) -> sum dz*xhat
-    const float cc = (float)(-(double)A * a1 / cnt);
-    const float cb = (float)(-(double)A * a2 / cnt);
-    const float k1 = cb * ri;
-    coef[threadIdx.x][0] = A;
-    coef[threadIdx.x][1] = k1;
-    coef[threadIdx.x][2] = cc - k1 * p.mean[i];
-    if (rank == 0 && p.mode == MUNIT_NORM_ADAIN) {
-      if (p.g_w) p.g_w[(long long)n * p.ldg + ch] = (float)a2;
-      if (p.g_b) p.g_b[(long long)n * p.ldg + ch] = (float)a1;
-    }
-  }
-  __syncthreads();
-  float fca[8], k1[8], k0[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    fca[e] = coef[half * 8 + e][0];
-    k1[e] = coef[half * 8 + e][1];
-    k0[e] = coef[half * 8 + e][2];
-  }
-  const int res_pad = p.res_pad;
-#pragma unroll 2
-  for (int pix = p0 + pr; pix < p1; pix += 128) {
-    const uint4 u = slab[((pix - p0) * 2 + half) * 2];
-    const uint4 gp = slab[((pix - p0) * 2 + half) * 2 + 1];
-    const F8 xv = unpack8(u), gq = unpack8(gp);
-    F8 d;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float dz = gq.v[e];
-      if (p.relu && fmaf(xv.v[e], fa.v[e], fb.v[e]) <= 0.f) dz = 0.f;
-      d.v[e] = fmaf(fca[e], dz, fmaf(k1[e], xv.v[e], k0[e]));
-    }
-    *reinterpret_cast<uint4*>(p.dy + ((long long)n * hw + pix) * c + ch0) = pack8(d);
-    if (p.g_res) {
-      const int yy = pix / w, x = pix - yy * w;
-      *reinterpret_cast<uint4*>(p.g_res + (((long long)n * (h + 2 * res_pad) + yy + res_pad) * (w + 2 * res_pad) + x + res_pad) * c + ch0) = gp;
-    }
-  }
-  slab_cluster_sync();
-}
-
 inline int grid_for(long long work, int threads = 256, int max_blocks = 148 * 16) {
   long long b = (work + threads - 1) / threads;
   if (b > max_blocks) b = max_blocks;
@@ -1959,83 +1605,6 @@ inline int apply_splits(int hw, int c, int n) {
   if (s < 1) s = 1;
   return s;
 }
-
-// Fused (cooperative) norm launches: every block of the grid must be resident at once.
-inline size_t fused_smem(int c) {
-  const int rows = 256 / (c / 8);
-  const size_t a = sizeof(float) * 2 * rows * c, b = sizeof(double) * 2 * c;
-  return a > b ? a : b;
-}
-inline int fused_capacity(int which) {  // 0: fwd<1>, 1: fwd<2>, 2: bwd<1>, 3: bwd<2>
-  static int cap[4] = {0, 0, 0, 0};
-  if (cap[which]) return cap[which];
-  int dev = 0, sms = 0, coop = 0, occ = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-  if (!coop) return cap[which] = -1;
-  const size_t sm = 16384;
-  cudaError_t e;
-  switch (which) {
-    case 0: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, norm_fwd_fused_kernel<1>, 256, sm); break;
-    case 1: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, norm_fwd_fused_kernel<2>, 256, sm); break;
-    case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, norm_bwd_fused_kernel<1>, 256, sm); break;
-    default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, norm_bwd_fused_kernel<2>, 256, sm); break;
-  }
-  if (e != cudaSuccess || occ < 1) return cap[which] = -1;
-  return cap[which] = occ * sms;
-}
-// pixel splits of a fused launch over n samples, or 0 when the shape cannot run fused
-inline int fused_splits(int which, int n, int hw, int c, int mode) {
-  if (c % 8 || c / 8 > 256 || 256 % (c / 8) || n < 1) return 0;
-  const int cap = fused_capacity(which);
-  if (cap < n) return 0;
-  const int rows = 256 / (c / 8);
-  int s = cap / n;
-  const int smax = (hw + rows - 1) / rows;  // at least one pixel per thread row
-  if (s > smax) s = smax;
-  if (s > 512) s = 512;
-  if (mode != MUNIT_NORM_LN && s < (c + 31) / 32) return 0;  // the channel-parallel finalize needs C/32 blocks per sample
-  return s < 1 ? 0 : s;
-}
-
-
-// Cluster size / pixels per CTA of a slab launch: smallest power-of-two cluster that keeps a CTA's pixel range
-// within `per_max`; 0 when the shape needs more than 16 CTAs per slab (caller uses the three-kernel path).
-inline int slab_cluster(int hw, int per_max, int* per) {
-  int cl = 1;
-  while (cl <= 16 && (hw + cl - 1) / cl > per_max) cl <<= 1;
-  if (cl > 16) return 0;
-  *per = (hw + cl - 1) / cl;
-  return cl;
-}
-inline int slab_launch(const void* fn, const NormSlabArgs& p, int cl, size_t smem, cudaStream_t st, const char* what) {
-  static bool attr_done[2] = {false, false};
-  const int which = fn == (const void*)norm_fwd_slab_kernel ? 0 : 1;
-  if (!attr_done[which]) {
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "%s: attributes: %s", what, cudaGetErrorString(e));
-    attr_done[which] = true;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(cl * (p.c / 16), p.n);
-  cfg.blockDim = dim3(256);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cl;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = which == 0 ? cudaLaunchKernelEx(&cfg, norm_fwd_slab_kernel, p) : cudaLaunchKernelEx(&cfg, norm_bwd_slab_kernel, p);
-  if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
-  return MUNIT_OK;
-}
-constexpr int kSlabFwdPer = 1024;  // pixels per CTA: 32 B/px forward (32 KB), 64 B/px backward (64 KB at most)
-constexpr int kSlabBwdPer = 512;
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 #define BF(p) reinterpret_cast<bf16*>(p)
@@ -2101,11 +1670,14 @@ int munit_norm_splits(int hw, int c) {
   return reduce_splits(hw, c);
 }
 
-int munit_norm_stats(const void* y, float* stats, float* shift, int n, int hw, int c, void* stream) {
+int munit_norm_stats(const void* y, int y_f16, float* stats, float* shift, int n, int hw, int c, void* stream) {
   if (c % 8 || c / 8 > 256 || 256 % (c / 8)) return mb_fail(MUNIT_ERR_ARG, "norm_stats: channels %d", c);
   const int rows = 256 / (c / 8);
   dim3 grid(reduce_splits(hw, c), n);
-  mb_launch(norm_stats_kernel, dim3(grid), dim3(256), sizeof(float) * 2 * rows * c, ST(stream), CBF(y), stats, shift, hw, c);
+  if (y_f16)
+    mb_launch(norm_stats_kernel<true>, dim3(grid), dim3(256), sizeof(float) * 2 * rows * c, ST(stream), CBF(y), stats, shift, hw, c);
+  else
+    mb_launch(norm_stats_kernel<false>, dim3(grid), dim3(256), sizeof(float) * 2 * rows * c, ST(stream), CBF(y), stats, shift, hw, c);
   MB_CHECK_LAUNCH("norm_stats");
   return MUNIT_OK;
 }
@@ -2148,35 +1720,40 @@ int munit_norm_finalize_parts(const float* stats, int splits, int kind, int mode
   return mb_fail(MUNIT_ERR_ARG, "norm_finalize_parts: kind %d does not match mode %d", kind, mode);
 }
 
-int munit_norm_apply(const void* y, const float* a, const float* b, int relu, const void* residual, int res_pad,
+int munit_norm_apply(const void* y, int y_f16, const float* a, const float* b, int relu, const void* residual, int res_pad,
                      void* out_act, int out_pad, int upsample, int n, int h, int w, int c, void* stream) {
   if (c % 8 || c / 8 > 256 || 256 % (c / 8)) return mb_fail(MUNIT_ERR_ARG, "norm_apply: channels %d", c);
   dim3 grid(apply_splits(h * w, c, n), n);
-  if (upsample == 2)
-    mb_launch(norm_apply_kernel<2>, dim3(grid), dim3(256), 0, ST(stream), CBF(y), a, b, relu, CBF(residual), res_pad, BF(out_act),
-                                                        out_pad, n, h, w, c);
-  else if (upsample == 1)
-    mb_launch(norm_apply_kernel<1>, dim3(grid), dim3(256), 0, ST(stream), CBF(y), a, b, relu, CBF(residual), res_pad, BF(out_act),
-                                                        out_pad, n, h, w, c);
-  else
-    return mb_fail(MUNIT_ERR_ARG, "norm_apply: upsample must be 1 or 2");
+  if (upsample != 1 && upsample != 2) return mb_fail(MUNIT_ERR_ARG, "norm_apply: upsample must be 1 or 2");
+#define MB_APPLY(UP_, H_)                                                                                          \
+  mb_launch(norm_apply_kernel<UP_, H_>, dim3(grid), dim3(256), 0, ST(stream), CBF(y), a, b, relu, CBF(residual), \
+            res_pad, BF(out_act), out_pad, n, h, w, c)
+  if (upsample == 2) {
+    if (y_f16) MB_APPLY(2, true); else MB_APPLY(2, false);
+  } else {
+    if (y_f16) MB_APPLY(1, true); else MB_APPLY(1, false);
+  }
+#undef MB_APPLY
   MB_CHECK_LAUNCH("norm_apply");
   return MUNIT_OK;
 }
 
-int munit_norm_bwd_reduce(const void* g_out, int out_pad, int upsample, const void* y, const float* a, const float* b,
+int munit_norm_bwd_reduce(const void* g_out, int out_pad, int upsample, const void* y, int y_f16, const float* a, const float* b,
                           int relu, const float* mean, const float* rinv, float* sums, int n, int h, int w, int c,
                           void* stream) {
   if (c % 8 || c / 8 > 256 || 256 % (c / 8)) return mb_fail(MUNIT_ERR_ARG, "norm_bwd_reduce: channels %d", c);
   const int rows = 256 / (c / 8);
   dim3 grid(reduce_splits(h * w, c), n);
   const size_t sm = sizeof(float) * 2 * rows * c;
-  if (upsample == 2)
-    mb_launch(norm_bwd_reduce_kernel<2>, dim3(grid), dim3(256), sm, ST(stream), CBF(g_out), out_pad, CBF(y), a, b, relu, mean, rinv, sums,
-                                                             h, w, c);
-  else
-    mb_launch(norm_bwd_reduce_kernel<1>, dim3(grid), dim3(256), sm, ST(stream), CBF(g_out), out_pad, CBF(y), a, b, relu, mean, rinv, sums,
-                                                             h, w, c);
+#define MB_BRED(UP_, H_)                                                                                           \
+  mb_launch(norm_bwd_reduce_kernel<UP_, H_>, dim3(grid), dim3(256), sm, ST(stream), CBF(g_out), out_pad, CBF(y), a, b, \
+            relu, mean, rinv, sums, h, w, c)
+  if (upsample == 2) {
+    if (y_f16) MB_BRED(2, true); else MB_BRED(2, false);
+  } else {
+    if (y_f16) MB_BRED(1, true); else MB_BRED(1, false);
+  }
+#undef MB_BRED
   MB_CHECK_LAUNCH("norm_bwd_reduce");
   return MUNIT_OK;
 }
@@ -2197,109 +1774,23 @@ int munit_norm_bwd_finalize(const float* sums, int mode, const float* p_w, int64
   return MUNIT_OK;
 }
 
-int munit_norm_bwd_apply(const void* g_out, int out_pad, int upsample, const void* y, const float* a, const float* b,
+int munit_norm_bwd_apply(const void* g_out, int out_pad, int upsample, const void* y, int y_f16, const float* a, const float* b,
                          int relu, const float* mean, const float* rinv, const float* ca, const float* cb,
                          const float* cc, void* dy, void* g_res, int res_pad, int n, int h, int w, int c,
                          void* stream) {
   if (c % 8 || c / 8 > 256 || 256 % (c / 8)) return mb_fail(MUNIT_ERR_ARG, "norm_bwd_apply: channels %d", c);
   dim3 grid(apply_splits(h * w, c, n), n);
-  if (upsample == 2)
-    mb_launch(norm_bwd_apply_kernel<2>, dim3(grid), dim3(256), 0, ST(stream), CBF(g_out), out_pad, CBF(y), a, b, relu, mean, rinv, ca, cb,
-                                                            cc, BF(dy), BF(g_res), res_pad, n, h, w, c);
-  else
-    mb_launch(norm_bwd_apply_kernel<1>, dim3(grid), dim3(256), 0, ST(stream), CBF(g_out), out_pad, CBF(y), a, b, relu, mean, rinv, ca, cb,
-                                                            cc, BF(dy), BF(g_res), res_pad, n, h, w, c);
+#define MB_BAPP(UP_, H_)                                                                                          \
+  mb_launch(norm_bwd_apply_kernel<UP_, H_>, dim3(grid), dim3(256), 0, ST(stream), CBF(g_out), out_pad, CBF(y), a, b, \
+            relu, mean, rinv, ca, cb, cc, BF(dy), BF(g_res), res_pad, n, h, w, c)
+  if (upsample == 2) {
+    if (y_f16) MB_BAPP(2, true); else MB_BAPP(2, false);
+  } else {
+    if (y_f16) MB_BAPP(1, true); else MB_BAPP(1, false);
+  }
+#undef MB_BAPP
   MB_CHECK_LAUNCH("norm_bwd_apply");
   return MUNIT_OK;
-}
-
-int munit_norm_fused_splits(int n, int hw, int c, int mode, int backward, int upsample) {
-  if (upsample != 1 && upsample != 2) return 0;
-  return fused_splits((backward ? 2 : 0) + (upsample == 2 ? 1 : 0), n, hw, c, mode);
-}
-
-int munit_norm_fwd_fused(const void* y, float* part, float* shift, int mode, const float* p_w, const float* p_b,
-                         int64_t ldw, float eps, float* mean, float* rinv, float* a, float* b, int relu,
-                         const void* residual, int res_pad, void* out_act, int out_pad, int upsample, int n, int h, int w,
-                         int c, void* stream) {
-  if (upsample != 1 && upsample != 2) return mb_fail(MUNIT_ERR_ARG, "norm_fwd_fused: upsample must be 1 or 2");
-  if (mode != MUNIT_NORM_IN && (!p_w || !p_b)) return mb_fail(MUNIT_ERR_ARG, "norm_fwd_fused: missing affine params");
-  const int which = upsample == 2 ? 1 : 0;
-  const int splits = fused_splits(which, n, h * w, c, mode);
-  if (splits < 1) return mb_fail(MUNIT_ERR_ARG, "norm_fwd_fused: shape n=%d hw=%d c=%d cannot run as one cooperative launch", n, h * w, c);
-  NormFusedArgs p{};
-  p.y = CBF(y); p.part = part; p.shift = shift; p.mode = mode; p.p_w = p_w; p.p_b = p_b; p.ldw = ldw; p.eps = eps;
-  p.mean = mean; p.rinv = rinv; p.a = a; p.b = b; p.relu = relu; p.res = CBF(residual); p.res_pad = res_pad;
-  p.out = BF(out_act); p.out_pad = out_pad; p.n = n; p.h = h; p.w = w; p.c = c;
-  void* args[] = {&p};
-  const void* fn = which ? (const void*)norm_fwd_fused_kernel<2> : (const void*)norm_fwd_fused_kernel<1>;
-  const cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(splits, n), dim3(256), args, fused_smem(c), ST(stream));
-  if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "norm_fwd_fused: %s", cudaGetErrorString(e));
-  MB_CHECK_LAUNCH("norm_fwd_fused");
-  return MUNIT_OK;
-}
-
-int munit_norm_bwd_fused(const void* g_out, int out_pad, int upsample, const void* y, const float* a, const float* b,
-                         int relu, const float* mean, const float* rinv, float* part, int mode, const float* p_w,
-                         int64_t ldw, float eps, float* ca, float* cb, float* cc, float* g_w, float* g_b, int64_t ldg,
-                         void* dy, void* g_res, int res_pad, int n, int h, int w, int c, void* stream) {
-  if (upsample != 1 && upsample != 2) return mb_fail(MUNIT_ERR_ARG, "norm_bwd_fused: upsample must be 1 or 2");
-  const int which = 2 + (upsample == 2 ? 1 : 0);
-  const int splits = fused_splits(which, n, h * w, c, mode);
-  if (splits < 1) return mb_fail(MUNIT_ERR_ARG, "norm_bwd_fused: shape n=%d hw=%d c=%d cannot run as one cooperative launch", n, h * w, c);
-  NormFusedArgs p{};
-  p.y = CBF(y); p.part = part; p.mode = mode; p.p_w = p_w; p.ldw = ldw; p.eps = eps;
-  p.mean = const_cast<float*>(mean); p.rinv = const_cast<float*>(rinv); p.a = const_cast<float*>(a);
-  p.b = const_cast<float*>(b); p.relu = relu; p.res_pad = res_pad; p.out_pad = out_pad; p.g_out = CBF(g_out);
-  p.ca = ca; p.cb = cb; p.cc = cc; p.g_w = g_w; p.g_b = g_b; p.ldg = ldg; p.dy = BF(dy); p.g_res = BF(g_res);
-  p.n = n; p.h = h; p.w = w; p.c = c;
-  void* args[] = {&p};
-  const void* fn = upsample == 2 ? (const void*)norm_bwd_fused_kernel<2> : (const void*)norm_bwd_fused_kernel<1>;
-  const cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(splits, n), dim3(256), args, fused_smem(c), ST(stream));
-  if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "norm_bwd_fused: %s", cudaGetErrorString(e));
-  MB_CHECK_LAUNCH("norm_bwd_fused");
-  return MUNIT_OK;
-}
-
-
-int munit_norm_slab_ok(int mode, int upsample, int hw, int c, int backward) {
-  if (mode == MUNIT_NORM_LN || upsample != 1 || c % 16 || hw < 1) return 0;
-  int per = 0;
-  int cl = slab_cluster(hw, backward ? kSlabBwdPer : kSlabFwdPer, &per);
-  if (!cl && backward) cl = slab_cluster(hw, 2 * kSlabBwdPer, &per);  // 64 KB slabs
-  return cl;
-}
-
-int munit_norm_fwd_slab(const void* y, int mode, const float* p_w, const float* p_b, int64_t ldw, float eps,
-                        float* mean, float* rinv, float* a, float* b, int relu, const void* residual, int res_pad,
-                        void* out_act, int out_pad, int n, int h, int w, int c, void* stream) {
-  if (mode == MUNIT_NORM_ADAIN && (!p_w || !p_b)) return mb_fail(MUNIT_ERR_ARG, "norm_fwd_slab: missing affine params");
-  int per = 0;
-  const int cl = (mode == MUNIT_NORM_LN || c % 16) ? 0 : slab_cluster(h * w, kSlabFwdPer, &per);
-  if (!cl) return mb_fail(MUNIT_ERR_ARG, "norm_fwd_slab: unsupported shape hw=%d c=%d mode=%d", h * w, c, mode);
-  if (out_pad >= h || out_pad >= w) return mb_fail(MUNIT_ERR_ARG, "norm_fwd_slab: reflect pad >= size");
-  NormSlabArgs p{};
-  p.y = CBF(y); p.mode = mode; p.p_w = p_w; p.p_b = p_b; p.ldw = ldw; p.eps = eps;
-  p.mean = mean; p.rinv = rinv; p.a = a; p.b = b; p.relu = relu; p.res = CBF(residual); p.res_pad = res_pad;
-  p.out = BF(out_act); p.out_pad = out_pad; p.n = n; p.h = h; p.w = w; p.c = c; p.per = per;
-  return slab_launch((const void*)norm_fwd_slab_kernel, p, cl, (size_t)per * 32, ST(stream), "norm_fwd_slab");
-}
-
-int munit_norm_bwd_slab(const void* g_out, int out_pad, const void* y, const float* a, const float* b, int relu,
-                        const float* mean, const float* rinv, int mode, const float* p_w, int64_t ldw, float* g_w,
-                        float* g_b, int64_t ldg, void* dy, void* g_res, int res_pad, int n, int h, int w, int c,
-                        void* stream) {
-  int per = 0;
-  int cl = (mode == MUNIT_NORM_LN || c % 16) ? 0 : slab_cluster(h * w, kSlabBwdPer, &per);
-  if (!cl && mode != MUNIT_NORM_LN && c % 16 == 0) cl = slab_cluster(h * w, 2 * kSlabBwdPer, &per);
-  if (!cl) return mb_fail(MUNIT_ERR_ARG, "norm_bwd_slab: unsupported shape hw=%d c=%d mode=%d", h * w, c, mode);
-  NormSlabArgs p{};
-  p.y = CBF(y); p.mode = mode; p.p_w = p_w; p.ldw = ldw;
-  p.mean = const_cast<float*>(mean); p.rinv = const_cast<float*>(rinv); p.a = const_cast<float*>(a);
-  p.b = const_cast<float*>(b); p.relu = relu; p.res_pad = res_pad; p.out_pad = out_pad; p.g_out = CBF(g_out);
-  p.g_w = g_w; p.g_b = g_b; p.ldg = ldg; p.dy = BF(dy); p.g_res = BF(g_res);
-  p.n = n; p.h = h; p.w = w; p.c = c; p.per = per;
-  return slab_launch((const void*)norm_bwd_slab_kernel, p, cl, (size_t)per * 64, ST(stream), "norm_bwd_slab");
 }
 
 int munit_act_bwd(const void* g_out, const void* out_act, int pad, int act, void* dy, int n, int h, int w, int c,
@@ -2435,9 +1926,10 @@ int munit_l1_bwd(const float* a, const float* b, const float* gscale_dev, float 
   MB_CHECK_LAUNCH("l1_bwd");
   return MUNIT_OK;
 }
-int munit_splitk_finish(const float* scratch, const float* bias, int act, void* out, int64_t n, int c, void* stream) {
+int munit_splitk_finish(const float* scratch, const float* bias, int act, void* out, int out_f16, int64_t n, int c,
+                        void* stream) {
   if (n % 8 || c % 8) return mb_fail(MUNIT_ERR_ARG, "splitk_finish: n and c must be multiples of 8");
-  mb_launch(splitk_finish_kernel, dim3(grid_for(n / 8)), dim3(256), 0, ST(stream), scratch, bias, act, BF(out), (long long)(n / 8), c);
+  mb_launch(splitk_finish_kernel, dim3(grid_for(n / 8)), dim3(256), 0, ST(stream), scratch, bias, act, BF(out), (long long)(n / 8), c, out_f16);
   MB_CHECK_LAUNCH("splitk_finish");
   return MUNIT_OK;
 }

@@ -3,6 +3,7 @@
 //   wgrad           : munit_wgrad    (MN-major A = dY, MN-major B = X, reduction over pixels)
 // Replaces nn.ReflectionPad2d + nn.Conv2d (networks.py:696) and their autograd backward.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -35,6 +36,7 @@ struct FwdParams {
   int n_store;
   const float* bias;
   int act;
+  int out_f16;  // store IEEE fp16 (saturating) instead of bf16: raw conv outputs that feed a normalisation
   int stages;
   int dbg;  // profiling knobs (env MUNIT_DBG): 1 skip A loads, 2 skip B loads, 4 skip MMA, 8 skip stores
   // halo-resident variant: window origin (tap offset minimum), box width / rows, descriptor base-offset mode
@@ -71,7 +73,7 @@ __device__ __forceinline__ float tanh_approx(float v) {
 //   kind 1 (IN / AdaIN): stats[((n*S + s)*C + c)*2 + {0,1}] = {sum x, sum x^2}, s = tile*4 + q, S = 4*tiles/image
 //   kind 2 (LayerNorm):  stats[(n*S + s)*2 + {0,1}] channel-reduced, s = (tile*4 + q)*(C/64) + c/64, S = 4*tiles*C/64
 __device__ __forceinline__ void staged_stats(uint32_t buf, int q, int lane, float* __restrict__ stats, int kind,
-                                             int c_total, int n, int tile, int tiles, int col0) {
+                                             int c_total, int n, int tile, int tiles, int col0, bool f16) {
   float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
 #pragma unroll 8
   for (int r = 0; r < 32; ++r) {
@@ -79,7 +81,15 @@ __device__ __forceinline__ void staged_stats(uint32_t buf, int q, int lane, floa
     const uint32_t addr = buf + row * 128 + (((lane >> 2) ^ (row & 7)) << 4) + ((lane & 3) << 2);
     uint32_t w;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(addr));
-    const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
+    float lo, hi;
+    if (f16) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+      lo = f.x;
+      hi = f.y;
+    } else {
+      lo = __uint_as_float(w << 16);
+      hi = __uint_as_float(w & 0xffff0000u);
+    }
     s1a += lo;
     s2a = fmaf(lo, lo, s2a);
     s1b += hi;
@@ -104,8 +114,13 @@ __device__ __forceinline__ void staged_stats(uint32_t buf, int q, int lane, floa
 }
 
 // 8 accumulators -> (+bias) -> activation -> 4 packed bf16x2 words
+__device__ __forceinline__ uint32_t pack_f16_sat(float a, float b) {
+  uint32_t r;  // upper half <- first source operand; satfinite clamps to +-65504 instead of producing inf
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
 __device__ __forceinline__ void epi8(const uint32_t* v, const float* __restrict__ bias, float slope, bool is_tanh,
-                                     uint32_t* out) {
+                                     uint32_t* out, bool f16 = false) {
   float f[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[e]);
@@ -121,13 +136,16 @@ __device__ __forceinline__ void epi8(const uint32_t* v, const float* __restrict_
 #pragma unroll
     for (int e = 0; e < 8; ++e) f[e] = tanh_approx(f[e]);
   }
+  if (f16) {
 #pragma unroll
-  for (int e = 0; e < 4; ++e) out[e] = pack_bf16(f[2 * e], f[2 * e + 1]);
+    for (int e = 0; e < 4; ++e) out[e] = pack_f16_sat(f[2 * e], f[2 * e + 1]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) out[e] = pack_bf16(f[2 * e], f[2 * e + 1]);
+  }
 }
 
-// CS = cluster size along the M-tile index: the CS CTAs of a cluster share the weight tile, each loads
-// BN/CS rows of it and multicasts them to all (cuts L2->SM weight traffic by CS).
-template <int BN, int CS>
+template <int BN>
 __global__ void __launch_bounds__(kThreads, BN <= 64 ? 4 : 2)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ OutMaps tmap_out, const __grid_constant__ FwdParams p) {
@@ -166,7 +184,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     prefetch_tmap(&tmap_b);
     for (int s = 0; s < stages; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), CS);  // released by the MMA warp of every CTA that multicasts into it
+      mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     mbar_init(smem_u32(&tmem_full_bar), 1);
     fence_mbar_init();
@@ -177,15 +195,12 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (CS > 1) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts / arrives remotely
   tc_fence_after();
   // PDL: barriers, tensor-map prefetch and the TMEM allocation above overlapped the previous kernel's tail; nothing
   // before this point touched memory another kernel writes.
   pdl_wait();
   pdl_trigger();
   const uint32_t tmem_base = tmem_base_slot;
-  const uint32_t cta_rank = CS > 1 ? cluster_ctarank() : 0;
-  constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -209,14 +224,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         c[0] += kc * 64;
         const uint32_t sa = smem_base + stage * kStageBytes;
         if (!(p.dbg & 1)) tma_load_nd(p.rank, sa, &tmap_a, fb, c);
-        if (p.dbg & 2) {
-        } else if (CS == 1) {
-          tma_load_2d(sa + kABytes, &tmap_b, fb, bk0 + kb * 64, n_tile * BN);
-        } else {
-          constexpr int kRows = BN / CS;  // this CTA's slice of the weight tile, broadcast to the cluster
-          tma_load_2d_mcast(sa + kABytes + cta_rank * kRows * 128, &tmap_b, fb, bk0 + kb * 64,
-                            n_tile * BN + cta_rank * kRows, kMask);
-        }
+        if (!(p.dbg & 2)) tma_load_2d(sa + kABytes, &tmap_b, fb, bk0 + kb * 64, n_tile * BN);
         if (++stage == stages) {
           stage = 0;
           ph ^= 1;
@@ -243,8 +251,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0);
           }
         }
-        if (CS == 1) umma_commit(smem_u32(&empty_bar[stage]));
-        else umma_commit_mcast(smem_u32(&empty_bar[stage]), kMask);
+        umma_commit(smem_u32(&empty_bar[stage]));
         if (++stage == stages) {
           stage = 0;
           ph ^= 1;
@@ -261,6 +268,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tc_fence_after();
     const float slope = act_slope(p.act);
     const bool is_tanh = p.act == MUNIT_ACT_TANH;
+    const bool f16 = p.out_f16 != 0;
     if (p.scratch) {
       // split-K: raw fp32 partial tile -> red.add into the scratch (bias / activation / bf16 in munit_splitk_finish)
       const int dx = row % p.tw;
@@ -307,7 +315,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               uint32_t o[4];
-              epi8(v + j, p.bias ? p.bias + col0 + h * 32 + j : nullptr, slope, is_tanh, o);
+              epi8(v + j, p.bias ? p.bias + col0 + h * 32 + j : nullptr, slope, is_tanh, o, f16);
               const int chunk = (h * 4 + (j >> 3)) ^ (row & 7);  // SWIZZLE_128B: 16B chunk index ^ (row % 8)
               const uint32_t dst = buf + row * 128 + chunk * 16;
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]),
@@ -324,7 +332,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         if (p.stats && store_group && !dead)
           staged_stats(buf, q, lane, p.stats, p.stats_kind, p.stats_c, n0, ty * p.tiles_x + tx,
-                       p.tiles_x * p.tiles_y, col0);
+                       p.tiles_x * p.tiles_y, col0, f16);
       }
       if (issuer) tma_store_wait_read0();
     } else {
@@ -349,7 +357,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int j = 0; j < kChunk; j += 8) {
             if (col0 + j < p.n_store) {
               uint32_t w[4];
-              epi8(v + j, p.bias ? p.bias + col0 + j : nullptr, slope, is_tanh, w);
+              epi8(v + j, p.bias ? p.bias + col0 + j : nullptr, slope, is_tanh, w, f16);
               *reinterpret_cast<uint4*>(optr + c0 + j) = make_uint4(w[0], w[1], w[2], w[3]);
             }
           }
@@ -359,7 +367,6 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (CS > 1) cluster_sync_all();  // no CTA exits while a peer can still write its smem / barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -489,6 +496,7 @@ tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     tc_fence_after();
     const float slope = act_slope(p.act);
     const bool is_tanh = p.act == MUNIT_ACT_TANH;
+    const bool f16 = p.out_f16 != 0;
     constexpr int kGroups = BN / 64;
     const bool issuer = (warp == 2 && lane == 0);
 #pragma unroll 1
@@ -505,7 +513,7 @@ tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             uint32_t o[4];
-            epi8(v + j, p.bias ? p.bias + col0 + h * 32 + j : nullptr, slope, is_tanh, o);
+            epi8(v + j, p.bias ? p.bias + col0 + h * 32 + j : nullptr, slope, is_tanh, o, f16);
             const int chunk = (h * 4 + (j >> 3)) ^ (row & 7);
             const uint32_t dst = buf + row * 128 + chunk * 16;
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]),
@@ -522,7 +530,7 @@ tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       if (p.stats && store_group && !dead)
         staged_stats(buf, q, lane, p.stats, p.stats_kind, p.stats_c, n0, ty * p.tiles_x + tx, p.tiles_x * p.tiles_y,
-                     col0);
+                     col0, f16);
     }
     if (issuer) tma_store_wait_read0();
   }
@@ -551,8 +559,6 @@ struct WgParams {
   int ksplit;
   int stages;
   int tap_on_a;  // tap offsets shift the A operand (swapped orientation: A = X, B = dY) instead of B
-  int row_taps;  // row-sharing variant: taps per group (one kernel row); 0 = one tap per CTA
-  int wb;        // row-sharing variant: B box width in pixels (8 + KW - 1)
   int* err;
   int tap_off[MUNIT_MAX_TAPS][5];
 };
@@ -714,160 +720,6 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 }
 
 // =============================================================================================
-// Row-sharing wgrad variant (stride-1 convolutions): one CTA owns a whole kernel ROW of taps (KW taps) for its
-// (Cout tile, Cin tile, pixel slice).  Per 8x8-pixel block it loads dY once and ONE [8 rows x (8+KW-1) cols x 64 ch]
-// box of X per channel group; each tap's B operand is a UMMA descriptor shifted by `tap * 128 B` into that box and
-// accumulates into its own TMEM column range (KW x BN <= 512 columns).  Shared-memory bytes per tap-MMA drop ~2-4x.
-// =============================================================================================
-template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
-wgrad_row_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const __grid_constant__ WgParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  constexpr int kNB = BN / 64;
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t b_box_bytes = ((uint32_t)p.wb * 8u * 128u + 1023u) & ~1023u;  // boxes stay 1024 B aligned
-  const uint32_t stage_bytes = 2 * kBoxBytes + kNB * b_box_bytes;
-  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
-  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-  __shared__ __align__(8) uint64_t tmem_full_bar;
-  __shared__ uint32_t tmem_base_slot;
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int stages = p.stages;
-  const int kw = p.row_taps;
-  const int grp = blockIdx.x / p.n_tiles;            // kernel row
-  const int n_tile = blockIdx.x - grp * p.n_tiles;
-  const int m_tile = blockIdx.y;
-  const int total_pb = p.blocks_x * p.blocks_y * p.blocks_n;
-  const int pb_begin = (int)(((long long)total_pb * blockIdx.z) / p.ksplit);
-  const int pb_end = (int)(((long long)total_pb * (blockIdx.z + 1)) / p.ksplit);
-  const int num_kb = pb_end - pb_begin;
-  const int tap0 = grp * kw;
-  const int ox = p.tap_off[tap0][1], oy = p.tap_off[tap0][2];  // window origin (taps of a row are ordered by dx)
-
-  if (threadIdx.x == 0) {
-    prefetch_tmap(&tmap_a);
-    prefetch_tmap(&tmap_b);
-    for (int s = 0; s < stages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
-    }
-    mbar_init(smem_u32(&tmem_full_bar), 1);
-    fence_mbar_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(smem_u32(&tmem_base_slot), 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  // PDL: barriers, tensor-map prefetch and the TMEM allocation above overlapped the previous kernel's tail; nothing
-  // before this point touched memory another kernel writes.
-  pdl_wait();
-  pdl_trigger();
-  const uint32_t tmem_base = tmem_base_slot;
-
-  if (num_kb > 0) {
-    if (warp == 0) {
-      if (elect_one()) {
-        bool dead = false;
-        int stage = 0;
-        uint32_t ph = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          int t = pb_begin + kb;
-          const int bx = t % p.blocks_x;
-          t /= p.blocks_x;
-          const int by = t % p.blocks_y;
-          const int n0 = t / p.blocks_y;
-          const int x0 = bx * 8, y0 = by * 8;
-          mbar_wait(smem_u32(&empty_bar[stage]), ph ^ 1, dead, p.err);
-          const uint32_t fb = smem_u32(&full_bar[stage]);
-          mbar_arrive_expect_tx(fb, 2 * kBoxBytes + kNB * (uint32_t)p.wb * 8u * 128u);
-          const uint32_t sa = smem_base + stage * stage_bytes;
-#pragma unroll
-          for (int i = 0; i < 2; ++i) tma_load_4d(sa + i * kBoxBytes, &tmap_a, fb, m_tile * 128 + i * 64, x0, y0, n0);
-#pragma unroll
-          for (int i = 0; i < kNB; ++i)
-            tma_load_4d(sa + 2 * kBoxBytes + i * b_box_bytes, &tmap_b, fb, n_tile * BN + i * 64, x0 + ox, y0 + oy, n0);
-          if (++stage == stages) {
-            stage = 0;
-            ph ^= 1;
-          }
-        }
-      }
-    } else if (warp == 1) {
-      if (elect_one()) {
-        bool dead = false;
-        constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
-        const uint32_t sbo_b = (uint32_t)p.wb * 128u;
-        int stage = 0;
-        uint32_t ph = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(smem_u32(&full_bar[stage]), ph, dead, p.err);
-          tc_fence_after();
-          const uint32_t sa = smem_base + stage * stage_bytes;
-          const uint32_t sb = sa + 2 * kBoxBytes;
-          for (int j = 0; j < kw; ++j) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              // A (dY): 16 pixels = 2 patch rows of 8 -> 2048 B per K step, 8-row groups 1024 B apart.
-              // B (X): same 2 patch rows inside the wider box, shifted by tap j: groups wb*128 B apart.
-              const uint64_t da = umma_desc_sw128(sa + k * 2048, kBoxBytes, 1024);
-              const uint64_t db = umma_desc_sw128(sb + (uint32_t)((2 * k) * p.wb + j) * 128u, b_box_bytes, sbo_b);
-              umma_bf16(tmem_base + j * BN, da, db, idesc, (kb | k) != 0);
-            }
-          }
-          umma_commit(smem_u32(&empty_bar[stage]));
-          if (++stage == stages) {
-            stage = 0;
-            ph ^= 1;
-          }
-        }
-        umma_commit(smem_u32(&tmem_full_bar));
-      }
-    } else {
-      bool dead = false;
-      const int q = warp & 3;
-      const int m = m_tile * 128 + q * 32 + lane;
-      mbar_wait(smem_u32(&tmem_full_bar), 0, dead, p.err);
-      tc_fence_after();
-#pragma unroll 1
-      for (int j = 0; j < kw; ++j) {
-        float* dst = p.dw + (long long)m * p.s_m + (long long)(tap0 + j) * p.s_t;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + j * BN + c0, v);
-          tmem_ld_wait();
-          if (m < p.m_total && !dead) {
-            const int nb = n_tile * BN + c0;
-            if (p.s_n == 1 && ((p.s_m | p.s_t) & 3) == 0 && (nb + 32 <= p.n_total)) {
-#pragma unroll
-              for (int e = 0; e < 32; e += 4)
-                red_add_v4_f32(dst + nb + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]),
-                               __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
-            } else {
-#pragma unroll
-              for (int e = 0; e < 32; ++e)
-                if (nb + e < p.n_total) red_add_f32(dst + (long long)(nb + e) * p.s_n, __uint_as_float(v[e]));
-            }
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
-// =============================================================================================
 // host side
 // =============================================================================================
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -908,7 +760,7 @@ int fwd_stages(int bn, int requested) {
   return bn == 128 ? 3 : 2;
 }
 
-template <int BN, int CS>
+template <int BN>
 int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, const OutMaps& to, FwdParams& p, dim3 grid,
                cudaStream_t st) {
   const int stage_bytes = kABytes + BN * 128;
@@ -916,29 +768,11 @@ int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, const OutMaps& to, 
   const size_t smem = (size_t)p.stages * stage_bytes + 1024;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BN, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
     attr_smem = smem;
   }
-  if (CS == 1) {
-    mb_launch(tapgemm_kernel<BN, CS>, grid, dim3(kThreads), smem, st, ta, tb, to, p);
-  } else {
-    grid.x = (grid.x + CS - 1) / CS * CS;  // padding CTAs map to out-of-range tiles: loads zero-fill, stores masked
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CS;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tapgemm_kernel<BN, CS>, ta, tb, to, p);
-    if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "tapgemm cluster launch: %s", cudaGetErrorString(e));
-  }
+  mb_launch(tapgemm_kernel<BN>, grid, dim3(kThreads), smem, st, ta, tb, to, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "tapgemm launch: %s", cudaGetErrorString(e));
   return MUNIT_OK;
@@ -992,28 +826,6 @@ int launch_wg(const CUtensorMap& ta, const CUtensorMap& tb, WgParams& p, dim3 gr
   return MUNIT_OK;
 }
 
-template <int BN>
-int launch_wg_row(const CUtensorMap& ta, const CUtensorMap& tb, WgParams& p, dim3 grid, cudaStream_t st) {
-  const size_t b_box = ((size_t)p.wb * 8 * 128 + 1023) & ~(size_t)1023;
-  const size_t stage_bytes = 2 * kBoxBytes + (BN / 64) * b_box;
-  int stages = p.stages;
-  if (stages <= 0) stages = (int)((200 * 1024) / stage_bytes);
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) stages = 2;
-  p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 1024;
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_row_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
-    attr_smem = smem;
-  }
-  mb_launch(wgrad_row_kernel<BN>, grid, dim3(kThreads), smem, st, ta, tb, p);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "wgrad_row launch: %s", cudaGetErrorString(e));
-  return MUNIT_OK;
-}
-
 }  // namespace
 
 int mb_tapgemm_init() {
@@ -1064,7 +876,7 @@ extern "C" int munit_tapgemm(const munit_tapgemm_desc* d, void* stream) {
   for (int i = 0; i < MUNIT_MAX_PHASES; ++i) { p.b_k0[i] = d->b_k0[i]; p.o_yoff[i] = d->o_yoff[i]; p.o_xoff[i] = d->o_xoff[i]; }
   p.out = reinterpret_cast<__nv_bfloat16*>(d->out);
   p.o_sn = d->o_sn; p.o_sy = d->o_sy; p.o_sx = d->o_sx; p.o_ymul = d->o_ymul; p.o_xmul = d->o_xmul;
-  p.n_store = d->n_store; p.bias = d->bias; p.act = d->act; p.stages = d->stages;
+  p.n_store = d->n_store; p.bias = d->bias; p.act = d->act; p.stages = d->stages; p.out_f16 = d->out_f16 ? 1 : 0;
   p.err = mb_error_flag();
   p.stats = d->stats; p.stats_kind = d->stats_kind; p.stats_c = d->b_rows;
   if (d->stats) {
@@ -1089,7 +901,7 @@ extern "C" int munit_tapgemm(const munit_tapgemm_desc* d, void* stream) {
   if (p.ksplit > 1) {
     if (!d->scratch) return mb_fail(MUNIT_ERR_ARG, "tapgemm: ksplit > 1 needs a zeroed fp32 scratch");
     if (p.ksplit > d->num_taps * d->chunks) return mb_fail(MUNIT_ERR_ARG, "tapgemm: ksplit exceeds taps * chunks");
-    if (d->halo || d->stats || d->cluster > 1) return mb_fail(MUNIT_ERR_ARG, "tapgemm: ksplit excludes halo / stats / cluster");
+    if (d->halo || d->stats) return mb_fail(MUNIT_ERR_ARG, "tapgemm: ksplit excludes halo / stats");
   }
   dim3 grid(p.tiles_x * p.tiles_y * p.tiles_n, (unsigned)(d->b_rows / d->bn), d->phases * p.ksplit);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1139,16 +951,9 @@ extern "C" int munit_tapgemm(const munit_tapgemm_desc* d, void* stream) {
     }
     return mb_fail(MUNIT_ERR_ARG, "tapgemm halo: bn %d unsupported", d->bn);
   }
-  // Weight-tile multicast across a cluster of M tiles (d->cluster: 0 = auto, 1/2/4 forced).  Measured on
-  // B200 (profiles/r1_multicast.md): the kernel is bound by bytes in flight per SM (smem capacity / TMA round
-  // trip), not by L2->SM bandwidth, so multicast only adds lock-step coupling -- auto therefore picks 1.
-  int cs = d->cluster;
-  if (cs <= 0) cs = 1;
-  if (cs != 1 && cs != 2 && cs != 4) return mb_fail(MUNIT_ERR_ARG, "tapgemm: cluster must be 1, 2 or 4");
-  if (d->bn < 64) cs = 1;
   uint64_t bdim[2] = {d->b_k, d->b_rows};
   uint64_t bstr[2] = {0, d->b_k * 2};
-  uint32_t bbox[2] = {64, (uint32_t)(d->bn / cs)};
+  uint32_t bbox[2] = {64, (uint32_t)d->bn};
   rc = make_tmap(&tb, d->b, 2, bdim, bstr, bbox);
   if (rc) return rc;
   // output views for the TMA-store epilogue (BN >= 64): one per phase, clipped to the valid extents
@@ -1166,75 +971,23 @@ extern "C" int munit_tapgemm(const munit_tapgemm_desc* d, void* stream) {
       if (rc) return rc;
     }
   }
-#define MB_FWD(BN_)                                                       \
-  case BN_:                                                               \
-    if (cs == 4) return launch_fwd<BN_, 4>(ta, tb, to, p, grid, st);      \
-    if (cs == 2) return launch_fwd<BN_, 2>(ta, tb, to, p, grid, st);      \
-    return launch_fwd<BN_, 1>(ta, tb, to, p, grid, st);
   switch (d->bn) {
-    case 16: return launch_fwd<16, 1>(ta, tb, to, p, grid, st);
-    case 32: return launch_fwd<32, 1>(ta, tb, to, p, grid, st);
-    MB_FWD(64)
-    MB_FWD(128)
-    MB_FWD(256)
+    case 16: return launch_fwd<16>(ta, tb, to, p, grid, st);
+    case 32: return launch_fwd<32>(ta, tb, to, p, grid, st);
+    case 64: return launch_fwd<64>(ta, tb, to, p, grid, st);
+    case 128: return launch_fwd<128>(ta, tb, to, p, grid, st);
+    case 256: return launch_fwd<256>(ta, tb, to, p, grid, st);
   }
-#undef MB_FWD
   return mb_fail(MUNIT_ERR_ARG, "tapgemm: bn %d unsupported", d->bn);
 }
 
 extern "C" int munit_wgrad(const munit_wgrad_desc* d, void* stream) {
   if (!d || !d->a || !d->b || !d->dw) return mb_fail(MUNIT_ERR_ARG, "wgrad: null pointer");
-  if (!d->row_taps) {
-    if (d->a_box[0] != 64 || d->b_box[0] != 64) return mb_fail(MUNIT_ERR_ARG, "wgrad: box[0] must be 64");
-    if (d->pw * d->ph * d->pn != 64) return mb_fail(MUNIT_ERR_ARG, "wgrad: pixel block must be 64");
-  }
+  if (d->a_box[0] != 64 || d->b_box[0] != 64) return mb_fail(MUNIT_ERR_ARG, "wgrad: box[0] must be 64");
+  if (d->pw * d->ph * d->pn != 64) return mb_fail(MUNIT_ERR_ARG, "wgrad: pixel block must be 64");
   if (d->num_taps < 1 || d->num_taps > MUNIT_MAX_TAPS) return mb_fail(MUNIT_ERR_ARG, "wgrad: taps");
   CUtensorMap ta, tb;
   int rc = 0;
-  if (d->row_taps > 0) {
-    // row-sharing variant: 8x8 pixel blocks, dY box [64 x 8 x 8], X box [64 x (8+KW-1) x 8]
-    if (d->a_rank != 4 || d->b_rank != 4 || d->tap_on_a || d->num_taps % d->row_taps || d->row_taps * d->bn > 512 ||
-        d->bn > 128)
-      return mb_fail(MUNIT_ERR_ARG, "wgrad row: needs rank-4 stride-1 views, taps %% row_taps == 0, row_taps*bn <= 512");
-    uint32_t abox[4] = {64, 8, 8, 1};
-    uint32_t bbox[4] = {64, (uint32_t)(8 + d->row_taps - 1), 8, 1};
-    rc = make_tmap(&ta, d->a, 4, d->a_dim, d->a_stride, abox);
-    if (rc) return rc;
-    rc = make_tmap(&tb, d->b, 4, d->b_dim, d->b_stride, bbox);
-    if (rc) return rc;
-    WgParams p;
-    memset(&p, 0, sizeof(p));
-    p.pw = 8; p.ph = 8; p.pn = 1;
-    p.blocks_x = (d->out_w + 7) / 8;
-    p.blocks_y = (d->out_h + 7) / 8;
-    p.blocks_n = d->n_img;
-    p.a_rank = p.b_rank = 4;
-    p.m_total = d->m_total; p.n_total = d->n_total; p.num_taps = d->num_taps;
-    p.n_tiles = (d->n_total + d->bn - 1) / d->bn;
-    p.dw = d->dw; p.s_m = d->s_m; p.s_t = d->s_t; p.s_n = d->s_n;
-    p.stages = d->stages; p.err = mb_error_flag();
-    p.row_taps = d->row_taps;
-    p.wb = 8 + d->row_taps - 1;
-    memcpy(p.tap_off, d->tap_off, sizeof(p.tap_off));
-    const int m_tiles = (d->m_total + 127) / 128;
-    const int groups = d->num_taps / d->row_taps;
-    const int total_pb = p.blocks_x * p.blocks_y * p.blocks_n;
-    int ks = d->ksplit;
-    if (ks <= 0) {
-      const int ctas = groups * p.n_tiles * m_tiles;  // one CTA per SM (512 TMEM columns): fill whole waves of 148
-      int waves = (ctas + 147) / 148;
-      ks = (waves * 148) / ctas;
-      const int max_ks = total_pb / 4 > 0 ? total_pb / 4 : 1;
-      if (ks > max_ks) ks = max_ks;
-    }
-    if (ks > total_pb) ks = total_pb;
-    if (ks < 1) ks = 1;
-    p.ksplit = ks;
-    dim3 grid(groups * p.n_tiles, m_tiles, ks);
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (d->bn == 64) return launch_wg_row<64>(ta, tb, p, grid, st);
-    return launch_wg_row<128>(ta, tb, p, grid, st);
-  }
   rc = make_tmap(&ta, d->a, d->a_rank, d->a_dim, d->a_stride, d->a_box);
   if (rc) return rc;
   rc = make_tmap(&tb, d->b, d->b_rank, d->b_dim, d->b_stride, d->b_box);

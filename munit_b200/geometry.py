@@ -126,7 +126,6 @@ class WgradPlan:
     s_t: int
     s_n: int
     tap_on_a: int = 0
-    row_taps: int = 0  # > 0: row-sharing kernel variant (stride 1, one kernel row of taps per CTA)
 
 
 def _pad5(v, fill=0):
@@ -236,7 +235,7 @@ def plan_dgrad(n, hp, wp, c_rows, kh, kw, sy, sx, co_c, halo=0, zpad=0) -> TapGe
 
 
 def plan_wgrad(n, hp, wp, c, kh, kw, sy, sx, co_c, m_total, s_m, s_t, s_n, n_total=None, swap=None,
-               row_share=False, zpad=0) -> WgradPlan:
+               zpad=0) -> WgradPlan:
     """Weight gradient: dw[m, tap, cin] += sum_pix dy[pix, m] * x[pix@tap, cin].
     zpad > 0: x is unpadded and implicitly zero-padded (see plan_fwd)."""
     assert zpad == 0 or (sy == 1 and sx == 1)
@@ -245,7 +244,6 @@ def plan_wgrad(n, hp, wp, c, kh, kw, sy, sx, co_c, m_total, s_m, s_t, s_n, n_tot
     rank, dims, strides, mx, my, mn, off, box = _x_view(n, hp, wp, c, sy, sx)
     pw, ph, pn = pick_tile(wo, ho, n, 64)
     taps = [_shift_tap(off(i, j), zpad) for i in range(kh) for j in range(kw)]
-    row_share = row_share and not zpad
     n_total = c if n_total is None else n_total
     if swap is None:  # put the wider channel count on the 128-row M operand
         swap = m_total <= 64 and n_total >= 128
@@ -259,12 +257,7 @@ def plan_wgrad(n, hp, wp, c, kh, kw, sy, sx, co_c, m_total, s_m, s_t, s_n, n_tot
             pw=pw, ph=ph, pn=pn, out_w=wo, out_h=ho, n_img=n, m_total=n_total, n_total=m_total, bn=bn,
             num_taps=len(taps), tap_off=taps, s_m=s_n, s_t=s_t, s_n=s_m, tap_on_a=1)
     bn = 128 if n_total % 128 == 0 else 64
-    row_taps = 0
-    if row_share and sy == 1 and sx == 1 and 2 <= kw <= 8 and ho >= 8 and wo >= 8:
-        bn = 128 if (kw * 128 <= 512 and n_total % 128 == 0) else 64
-        row_taps = kw
     return WgradPlan(
-        row_taps=row_taps,
         a_rank=4, a_dim=[co_c, wo, ho, n], a_stride=[e, co_c * e, wo * co_c * e, ho * wo * co_c * e],
         a_box=[64, pw, ph, pn], a_mx=[0, 1, 0, 0], a_my=[0, 0, 1, 0], a_mn=[0, 0, 0, 1],
         b_rank=rank, b_dim=dims, b_stride=strides, b_box=box(pw, ph, pn), b_mx=mx, b_my=my, b_mn=mn,

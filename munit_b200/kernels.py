@@ -18,6 +18,12 @@ def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
+def _f16(t) -> int:
+    """1 when a raw conv output is stored as fp16 (ops.ConvFn in front of a norm), 0 for bf16."""
+    assert t.dtype in (torch.bfloat16, torch.float16)
+    return int(t.dtype == torch.float16)
+
+
 def _count(n=1):
     _lib.launches += n
 
@@ -79,12 +85,12 @@ _KSPLIT_MAX_CTAS = int(_os.environ.get("MUNIT_KSPLIT_CTAS", "8"))
 _KSPLIT_MIN_KB = int(_os.environ.get("MUNIT_KSPLIT_KB", "64"))
 
 
-def tapgemm(plan, a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, bias=None, act="none", stages=0, cluster=0,
+def tapgemm(plan, a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, bias=None, act="none", stages=0,
             stats=None, stats_kind=0, ksplit=0):
     """out (bf16) <- act(tapconv(a; b) + bias) as described by `plan` (geometry.TapGemmPlan).  `stats` (fp32,
     n_img * stats_splits(plan, kind) * (C if kind == 1 else 1) * 2 floats) receives the norm partials."""
     _lib.init()
-    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and out.dtype in (torch.bfloat16, torch.float16)
     assert a.is_cuda and a.is_contiguous() and b.is_contiguous()
     assert b.numel() == plan.b_rows * plan.b_k, (b.shape, plan.b_rows, plan.b_k)
     d = TapGemmDesc()
@@ -110,9 +116,10 @@ def tapgemm(plan, a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, bias=None
     d.n_store = plan.n_store
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() >= plan.b_rows
-    d.bias, d.act, d.stages, d.cluster = _ptr(bias), ACT[act], stages, cluster
+    d.bias, d.act, d.stages = _ptr(bias), ACT[act], stages
+    d.out_f16 = _f16(out)
     d.halo = int(getattr(plan, "halo", 0))
-    ksplit = ksplit or (auto_ksplit(plan) if stats is None and cluster <= 1 else 1)
+    ksplit = ksplit or (auto_ksplit(plan) if stats is None else 1)
     scratch = None
     if ksplit > 1:
         assert out.is_contiguous() and plan.n_store == plan.b_rows and out.shape[-1] == plan.b_rows
@@ -125,7 +132,7 @@ def tapgemm(plan, a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, bias=None
     check(lib.munit_tapgemm(C.byref(d), _stream()), "munit_tapgemm")
     _count()
     if scratch is not None:
-        check(lib.munit_splitk_finish(scratch.data_ptr(), _ptr(bias), ACT[act], out.data_ptr(), out.numel(),
+        check(lib.munit_splitk_finish(scratch.data_ptr(), _ptr(bias), ACT[act], out.data_ptr(), _f16(out), out.numel(),
                                       out.shape[-1], _stream()), "splitk_finish")
         _count()
     return out
@@ -160,7 +167,6 @@ def wgrad(plan, dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, ksplit=0, s
             d.tap_off[t][i] = off[i] if i < len(off) else 0
     d.dw, d.s_m, d.s_t, d.s_n = dw.data_ptr(), plan.s_m, plan.s_t, plan.s_n
     d.ksplit, d.stages, d.tap_on_a = ksplit, stages, int(getattr(plan, "tap_on_a", 0))
-    d.row_taps = int(getattr(plan, "row_taps", 0))
     check(lib.munit_wgrad(C.byref(d), _stream()), "munit_wgrad")
     _count()
     return dw
@@ -229,7 +235,7 @@ def norm_stats(y):
     assert splits > 0, f"unsupported channel count {c}"
     stats = torch.empty(n, splits, c, 2, dtype=torch.float32, device=y.device)
     shift = torch.empty(n, c, dtype=torch.float32, device=y.device)
-    check(lib.munit_norm_stats(y.data_ptr(), stats.data_ptr(), shift.data_ptr(), n, h * w, c, _stream()), "norm_stats")
+    check(lib.munit_norm_stats(y.data_ptr(), _f16(y), stats.data_ptr(), shift.data_ptr(), n, h * w, c, _stream()), "norm_stats")
     _count()
     return stats, shift
 
@@ -248,46 +254,9 @@ def norm_apply(y, a, b, relu, residual, res_pad, out_pad, upsample):
     n, h, w, c = y.shape
     out = torch.empty(n, h * upsample + 2 * out_pad, w * upsample + 2 * out_pad, c, dtype=torch.bfloat16,
                       device=y.device)
-    check(lib.munit_norm_apply(y.data_ptr(), a.data_ptr(), b.data_ptr(), int(relu), _ptr(residual), res_pad,
+    check(lib.munit_norm_apply(y.data_ptr(), _f16(y), a.data_ptr(), b.data_ptr(), int(relu), _ptr(residual), res_pad,
                                out.data_ptr(), out_pad, upsample, n, h, w, c, _stream()), "norm_apply")
     _count()
-    return out
-
-
-# Fused cooperative norm launches (statistics -> finalize -> apply in one kernel).  A launch covers as many
-# samples as keep its re-read operands (y, and g_out in the backward) inside the L2 budget below, so the second
-# pass is served by L2.  Opt-in (MUNIT_NORM_FUSED=1): on B200 the two grid-wide barriers plus the cooperative
-# launch cost more than the two kernel boundaries and the L2 re-read save (43.7 -> 47.5 ms/step,
-# profiles/r1_norm_fused.md), so the three-kernel sequence stays the default.
-_NORM_FUSED = _os.environ.get("MUNIT_NORM_FUSED", "0") != "0"
-_NORM_L2_BYTES = int(float(_os.environ.get("MUNIT_NORM_L2MB", "48")) * (1 << 20))
-
-
-# Slab-resident IN / AdaIN (one cluster launch per normalisation, inputs read from DRAM once).  Opt-in
-# (MUNIT_NORM_SLAB=1): inside the captured step the conv output is still L2-resident when the statistics and
-# apply kernels read it, so the saved DRAM pass buys nothing and the two-pass-per-CTA kernel has less parallelism
-# than the three short launches (43.66 -> 44.15 ms/step, profiles/r1_norm_fused.md).
-_NORM_SLAB = _os.environ.get("MUNIT_NORM_SLAB", "0") != "0"
-
-
-def _slab_ok(mode, upsample, hw, c, backward):
-    return _NORM_SLAB and lib.munit_norm_slab_ok(NORM[mode], upsample, hw, c, int(backward)) > 0
-
-
-def _fused_chunks(n, bytes_per_sample, hw, c, mode, backward, upsample):
-    """Sample ranges [(n0, n1, splits)] of the fused launches, or None when the shape must run unfused."""
-    if not _NORM_FUSED:
-        return None
-    per = max(1, min(n, _NORM_L2_BYTES // max(1, bytes_per_sample)))
-    out = []
-    n0 = 0
-    while n0 < n:
-        n1 = min(n, n0 + per)
-        s = lib.munit_norm_fused_splits(n1 - n0, hw, c, NORM[mode], int(backward), upsample)
-        if s < 1:
-            return None
-        out.append((n0, n1, s))
-        n0 = n1
     return out
 
 
@@ -310,88 +279,28 @@ def norm_fwd(y, mode, p_w, p_b, ldw, eps, relu, residual, res_pad, out_pad, upsa
     if part is not None and part.numel():
         coef = norm_finalize_parts(part, 2 if mode == "ln" else 1, mode, p_w, p_b, ldw, n, h * w, c, eps)
         return norm_apply(y, coef[2], coef[3], relu, residual, res_pad, out_pad, upsample), coef
-    if _slab_ok(mode, upsample, h * w, c, False):
-        coef = torch.empty(4, n, c, dtype=torch.float32, device=y.device)
-        out = torch.empty(n, h + 2 * out_pad, w + 2 * out_pad, c, dtype=torch.bfloat16, device=y.device)
-        check(lib.munit_norm_fwd_slab(y.data_ptr(), NORM[mode], _ptr(p_w), _ptr(p_b), ldw, eps, coef[0].data_ptr(),
-                                      coef[1].data_ptr(), coef[2].data_ptr(), coef[3].data_ptr(), int(relu),
-                                      _ptr(residual), res_pad, out.data_ptr(), out_pad, n, h, w, c, _stream()),
-              "norm_fwd_slab")
-        _count()
-        return out, coef
-    chunks = _fused_chunks(n, y[0].numel() * 2, h * w, c, mode, False, upsample)
-    if chunks is None:
-        stats, shift = norm_stats(y)
-        coef = norm_finalize(stats, shift, mode, p_w, p_b, ldw, h * w, eps)
-        return norm_apply(y, coef[2], coef[3], relu, residual, res_pad, out_pad, upsample), coef
-    coef = torch.empty(4, n, c, dtype=torch.float32, device=y.device)
-    shift = torch.empty(n, c, dtype=torch.float32, device=y.device)
-    part = torch.empty(sum((n1 - n0) * s for n0, n1, s in chunks) * c * 2, dtype=torch.float32, device=y.device)
-    out = torch.empty(n, h * upsample + 2 * out_pad, w * upsample + 2 * out_pad, c, dtype=torch.bfloat16,
-                      device=y.device)
-    adain = mode == "adain"
-    off = 0
-    for n0, n1, s in chunks:
-        check(lib.munit_norm_fwd_fused(
-            y[n0:].data_ptr(), part[off:].data_ptr(), shift[n0:].data_ptr(), NORM[mode],
-            p_w[n0:].data_ptr() if adain else _ptr(p_w), p_b[n0:].data_ptr() if adain else _ptr(p_b), ldw, eps,
-            coef[0, n0:].data_ptr(), coef[1, n0:].data_ptr(), coef[2, n0:].data_ptr(), coef[3, n0:].data_ptr(),
-            int(relu), 0 if residual is None else residual[n0:].data_ptr(), res_pad, out[n0:].data_ptr(), out_pad,
-            upsample, n1 - n0, h, w, c, _stream()), "norm_fwd_fused")
-        off += (n1 - n0) * s * c * 2
-    _count(len(chunks))
-    return out, coef
+    stats, shift = norm_stats(y)
+    coef = norm_finalize(stats, shift, mode, p_w, p_b, ldw, h * w, eps)
+    return norm_apply(y, coef[2], coef[3], relu, residual, res_pad, out_pad, upsample), coef
 
 
 def norm_bwd(g_out, out_pad, upsample, y, coef, relu, mode, p_w, ldw, g_w, g_b, ldg, want_res, res_pad, eps=1e-5):
     """Returns (dy, g_res).  coef = (mean, rinv, a, b) from norm_finalize."""
     n, h, w, c = y.shape
     mean, rinv, a, b = coef[0], coef[1], coef[2], coef[3]
-    if _slab_ok(mode, upsample, h * w, c, True):
-        dy = torch.empty_like(y)
-        g_res = None
-        if want_res:
-            g_res = torch.zeros(n, h + 2 * res_pad, w + 2 * res_pad, c, dtype=torch.bfloat16, device=y.device)
-        check(lib.munit_norm_bwd_slab(g_out.data_ptr(), out_pad, y.data_ptr(), a.data_ptr(), b.data_ptr(), int(relu),
-                                      mean.data_ptr(), rinv.data_ptr(), NORM[mode], _ptr(p_w), ldw, _ptr(g_w),
-                                      _ptr(g_b), ldg, dy.data_ptr(), _ptr(g_res), res_pad, n, h, w, c, _stream()),
-              "norm_bwd_slab")
-        _count()
-        return dy, g_res
-    chunks = _fused_chunks(n, (y[0].numel() + g_out[0].numel()) * 2, h * w, c, mode, True, upsample)
-    if chunks is not None:
-        part = torch.empty(sum((n1 - n0) * s for n0, n1, s in chunks) * c * 2, dtype=torch.float32, device=y.device)
-        k = torch.empty(3, n, c, dtype=torch.float32, device=y.device)
-        dy = torch.empty_like(y)
-        g_res = None
-        if want_res:
-            g_res = torch.zeros(n, h + 2 * res_pad, w + 2 * res_pad, c, dtype=torch.bfloat16, device=y.device)
-        adain = mode == "adain"
-        off = 0
-        for n0, n1, s in chunks:
-            check(lib.munit_norm_bwd_fused(
-                g_out[n0:].data_ptr(), out_pad, upsample, y[n0:].data_ptr(), a[n0:].data_ptr(), b[n0:].data_ptr(),
-                int(relu), mean[n0:].data_ptr(), rinv[n0:].data_ptr(), part[off:].data_ptr(), NORM[mode],
-                p_w[n0:].data_ptr() if adain else _ptr(p_w), ldw, eps, k[0, n0:].data_ptr(), k[1, n0:].data_ptr(),
-                k[2, n0:].data_ptr(), g_w[n0:].data_ptr() if (adain and g_w is not None) else _ptr(g_w),
-                g_b[n0:].data_ptr() if (adain and g_b is not None) else _ptr(g_b), ldg, dy[n0:].data_ptr(),
-                0 if g_res is None else g_res[n0:].data_ptr(), res_pad, n1 - n0, h, w, c, _stream()), "norm_bwd_fused")
-            off += (n1 - n0) * s * c * 2
-        _count(len(chunks))
-        return dy, g_res
     sums = torch.empty(n, lib.munit_norm_splits(h * w, c), c, 2, dtype=torch.float32, device=y.device)
-    check(lib.munit_norm_bwd_reduce(g_out.data_ptr(), out_pad, upsample, y.data_ptr(), a.data_ptr(), b.data_ptr(),
+    check(lib.munit_norm_bwd_reduce(g_out.data_ptr(), out_pad, upsample, y.data_ptr(), _f16(y), a.data_ptr(), b.data_ptr(),
                                     int(relu), mean.data_ptr(), rinv.data_ptr(), sums.data_ptr(), n, h, w, c,
                                     _stream()), "norm_bwd_reduce")
     k = torch.empty(3, n, c, dtype=torch.float32, device=y.device)
     check(lib.munit_norm_bwd_finalize(sums.data_ptr(), NORM[mode], _ptr(p_w), ldw, rinv.data_ptr(), eps,
                                       k[0].data_ptr(), k[1].data_ptr(), k[2].data_ptr(), _ptr(g_w), _ptr(g_b), ldg, n,
                                       h * w, c, _stream()), "norm_bwd_finalize")
-    dy = torch.empty_like(y)
+    dy = torch.empty(y.shape, dtype=torch.bfloat16, device=y.device)
     g_res = None
     if want_res:
         g_res = torch.empty(n, h + 2 * res_pad, w + 2 * res_pad, c, dtype=torch.bfloat16, device=y.device)  # halo zeroed by the kernel
-    check(lib.munit_norm_bwd_apply(g_out.data_ptr(), out_pad, upsample, y.data_ptr(), a.data_ptr(), b.data_ptr(),
+    check(lib.munit_norm_bwd_apply(g_out.data_ptr(), out_pad, upsample, y.data_ptr(), _f16(y), a.data_ptr(), b.data_ptr(),
                                    int(relu), mean.data_ptr(), rinv.data_ptr(), k[0].data_ptr(), k[1].data_ptr(),
                                    k[2].data_ptr(), dy.data_ptr(), _ptr(g_res), res_pad, n, h, w, c, _stream()),
           "norm_bwd_apply")
@@ -634,7 +543,7 @@ def bn_bwd(g_out, y, coef, relu, gamma, g_gamma, g_beta, training):
     mean, rinv, a, b = coef[0], coef[1], coef[2], coef[3]
     splits = lib.munit_norm_splits(h * w, c)
     sums = torch.empty(n, splits, c, 2, dtype=torch.float32, device=y.device)
-    check(lib.munit_norm_bwd_reduce(g_out.data_ptr(), 0, 1, y.data_ptr(), a.data_ptr(), b.data_ptr(), int(relu),
+    check(lib.munit_norm_bwd_reduce(g_out.data_ptr(), 0, 1, y.data_ptr(), _f16(y), a.data_ptr(), b.data_ptr(), int(relu),
                                     mean.data_ptr(), rinv.data_ptr(), sums.data_ptr(), n, h, w, c, _stream()),
           "norm_bwd_reduce")
     sums_all, n0 = _gather_ranks(sums) if training else (sums, 0)
@@ -643,7 +552,7 @@ def bn_bwd(g_out, y, coef, relu, gamma, g_gamma, g_beta, training):
                                     int(training), k[0].data_ptr(), k[1].data_ptr(), k[2].data_ptr(), _ptr(g_gamma),
                                     _ptr(g_beta), h * w, c, _stream()), "bn_bwd_finalize")
     dy = torch.empty_like(y)
-    check(lib.munit_norm_bwd_apply(g_out.data_ptr(), 0, 1, y.data_ptr(), a.data_ptr(), b.data_ptr(), int(relu),
+    check(lib.munit_norm_bwd_apply(g_out.data_ptr(), 0, 1, y.data_ptr(), _f16(y), a.data_ptr(), b.data_ptr(), int(relu),
                                    mean.data_ptr(), rinv.data_ptr(), k[0].data_ptr(), k[1].data_ptr(), k[2].data_ptr(),
                                    dy.data_ptr(), 0, 0, n, h, w, c, _stream()), "norm_bwd_apply")
     _count(3)

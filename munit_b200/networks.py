@@ -185,8 +185,9 @@ class Conv2dBlock(nn.Module):
         if pending_up:
             y = (ops.UpConvPhaseFn.apply(xin, w, bias, layer) if torch.is_grad_enabled()
                  else ops.upconv_phase_forward(xin, w, bias, layer))
-            part = None
+            part, y_f16 = None, False
         else:
+            y_f16 = True  # raw conv output in front of a norm: fp16 bits (ops.ConvFn)
             y, part = ops.ConvFn.apply(xin, w, bias, layer, "none", 0, self.padding, 2 if self.norm_type == "ln" else 1)
         n = y.shape[0]
         if self.norm_type == "in":
@@ -198,7 +199,7 @@ class Conv2dBlock(nn.Module):
         res_t = residual.t if residual is not None else None
         res_pad = residual.pad if residual is not None else 0
         out = ops.NormFn.apply(y, p_w, p_b, res_t, self.norm_type, self.act_type == "relu", res_pad, out_pad,
-                               upsample, self.norm.eps if self.norm_type != "in" else 1e-5, part)
+                               upsample, self.norm.eps if self.norm_type != "in" else 1e-5, part, y_f16)
         return Act(out, out_pad)
 
     # -- public path (tensor in, tensor out) ----------------------------------------------

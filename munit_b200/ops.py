@@ -351,8 +351,12 @@ class ConvFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, layer: ConvLayer, act: str, out_pad: int, image_pad: int, stats_kind: int = 0):
-        """stats_kind 1 (IN / AdaIN) or 2 (LayerNorm): also return the normalisation partials the epilogue
-        computed from the stored tile (an empty tensor when this plan cannot produce them)."""
+        """stats_kind 1 (IN / AdaIN) or 2 (LayerNorm): the output feeds a normalisation.  It is then stored as IEEE
+        fp16 -- only the norm kernels ever read it, and the 3 extra mantissa bits keep the sign of x - mean (the ReLU
+        mask of networks.py:698-700) stable against the storage rounding -- but *typed* bf16 so that autograd does not
+        cast the bf16 gradient that comes back (NormFn views it as float16 again: y_f16=True).  Also returns the
+        normalisation partials the epilogue computed from the stored tile (an empty tensor when this plan cannot
+        produce them)."""
         layer.refresh(weight, bias)
         if layer.first:  # x is an NCHW fp32 image
             n, c, h, w = x.shape
@@ -362,7 +366,8 @@ class ConvFn(torch.autograd.Function):
             gemm_in = x
         n, hp, wp, _ = gemm_in.shape
         fwd, _, _, ho, wo = layer.plans(n, hp, wp, out_pad)
-        out = torch.empty(n, ho + 2 * out_pad, wo + 2 * out_pad, layer.co_rows, dtype=torch.bfloat16, device=x.device)
+        out = torch.empty(n, ho + 2 * out_pad, wo + 2 * out_pad, layer.co_rows,
+                          dtype=torch.float16 if stats_kind else torch.bfloat16, device=x.device)
         part = None
         if stats_kind:
             splits = K.stats_splits(fwd, stats_kind) if (EPI_STATS and out_pad == 0 and act == "none") else 0
@@ -375,10 +380,10 @@ class ConvFn(torch.autograd.Function):
         ctx.has_bias = bias is not None
         ctx.wbuf, ctx.bbuf = _param_grad_buf(weight), _param_grad_buf(bias)
         _track_use(ctx, ctx.needs_input_grad[1], ctx.wbuf, ctx.bbuf)
-        ctx.save_for_backward(gemm_in, out, weight)
+        ctx.save_for_backward(gemm_in, out if not stats_kind else out.new_empty(0), weight)
         if stats_kind:
             ctx.mark_non_differentiable(part)
-            return out, part
+            return out.view(torch.bfloat16), part
         return out
 
     @staticmethod
@@ -488,9 +493,12 @@ class NormFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, y, p_w, p_b, residual, mode: str, relu: bool, res_pad: int, out_pad: int, upsample: int,
-                eps: float, part=None):
+                eps: float, part=None, y_f16: bool = False):
+        """y_f16: y holds IEEE fp16 bits behind its bf16 dtype (raw conv output from ConvFn(stats_kind != 0))."""
         n, h, w, c = y.shape
         y = y.contiguous()
+        if y_f16:
+            y = y.view(torch.float16)
         ldw = 0
         if mode == "adain":
             assert p_w.stride(1) == 1 and p_b.stride(1) == 1 and p_w.stride(0) == p_b.stride(0)
@@ -522,7 +530,7 @@ class NormFn(torch.autograd.Function):
         dy, g_res = K.norm_bwd(g_out.contiguous(), out_pad, upsample, y, coef, relu, mode, p_w, ldw, g_w, g_b, ldg,
                                has_res and ctx.needs_input_grad[3], res_pad, eps)
         _track_done(ctx)
-        return dy, ret_w, ret_b, g_res, None, None, None, None, None, None, None
+        return dy, ret_w, ret_b, g_res, None, None, None, None, None, None, None, None
 
 
 class AdainSplitFn(torch.autograd.Function):

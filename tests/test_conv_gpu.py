@@ -160,28 +160,6 @@ def test_tapgemm_halo_variant(n, h, w, cin, cout, k, s, pad):
     assert rel_l2(dxp, nhwc(xp.grad)) < TOL, rel_l2(dxp, nhwc(xp.grad))
 
 
-@pytest.mark.parametrize("n,h,w,cin,cout,k,s,pad", [(2, 16, 16, 64, 128, 3, 1, 1), (8, 64, 64, 256, 256, 3, 1, 1),
-                                                    (1, 24, 40, 128, 128, 5, 1, 2), (2, 20, 12, 128, 64, 5, 1, 2)])
-def test_wgrad_row_sharing_variant(n, h, w, cin, cout, k, s, pad):
-    """Row-sharing wgrad (one CTA per kernel row, shifted descriptors into one widened X box)."""
-    from munit_b200 import geometry as G, kernels as K
-
-    xp, wt, _ = _setup(n, h, w, cin, cout, k, s, pad, 7)
-    wt = wt.requires_grad_(True)
-    y = F.conv2d(xp, wt, None, stride=s)
-    gy = bf16_round(torch.randn_like(y))
-    y.backward(gy)
-    hp, wp = xp.shape[2:]
-    plan = G.plan_wgrad(n, hp, wp, cin, k, k, s, s, cout, cout, k * k * cin, cin, 1, swap=False, row_share=True)
-    assert plan.row_taps == k
-    dw = torch.zeros(cout, k, k, cin, dtype=torch.float32, device="cuda")
-    K.wgrad(plan, nhwc(gy).to(torch.bfloat16), nhwc(xp).to(torch.bfloat16), dw)
-    torch.cuda.synchronize()
-    assert error_flag() == 0
-    err = rel_l2(dw, wt.grad.permute(0, 2, 3, 1))
-    assert err < TOL, err
-
-
 STATS_CASES = [
     # n, h, w, cin, cout, k, s, pad, halo
     (2, 64, 64, 256, 256, 3, 1, 1, 0),   # residual-block conv: tile (64, 2, 1)

@@ -73,7 +73,6 @@ def run(name, iters=20, nbuf=4):
     if os.environ.get("BN"):
         fwd.bn = int(os.environ["BN"])
     stages = int(os.environ.get("STAGES", 0))
-    cluster = int(os.environ.get("CLUSTER", 0))
     dg = G.plan_dgrad(n, hp, wp, cin, k, k, s, s, cout, halo=halo)
     ck = max(64, cout)
     wd = (torch.randn(cin, dg.b_k, device="cuda") * 0.05).to(torch.bfloat16)
@@ -81,15 +80,13 @@ def run(name, iters=20, nbuf=4):
     wg = G.plan_wgrad(n, hp, wp, cin, k, k, s, s, cout, cout, k * k * cin, cin, 1)
     if int(os.environ.get("WBN", 0)):
         wg.bn = int(os.environ["WBN"])
-    if os.environ.get("ROWSHARE"):
-        wg = G.plan_wgrad(n, hp, wp, cin, k, k, s, s, cout, cout, k * k * cin, cin, 1, swap=False, row_share=True)
     if os.environ.get("NOSWAP"):
         wg = G.plan_wgrad(n, hp, wp, cin, k, k, s, s, cout, cout, k * k * cin, cin, 1, swap=False)
     ksplit, wstages = int(os.environ.get("KSPLIT", 0)), int(os.environ.get("WSTAGES", 0))
     dw = torch.zeros(cout, k, k, cin, device="cuda")
     res = {}
-    for label, fn in (("fwd", lambda i: K.tapgemm(fwd, xs[i % nbuf], wf, ys[i % nbuf], stages=stages, cluster=cluster)),
-                      ("dgrad", lambda i: K.tapgemm(dg, ys[i % nbuf], wd, dxs[i % nbuf], cluster=cluster)),
+    for label, fn in (("fwd", lambda i: K.tapgemm(fwd, xs[i % nbuf], wf, ys[i % nbuf], stages=stages)),
+                      ("dgrad", lambda i: K.tapgemm(dg, ys[i % nbuf], wd, dxs[i % nbuf])),
                       ("wgrad", lambda i: K.wgrad(wg, ys[i % nbuf], xs[i % nbuf], dw, ksplit=ksplit, stages=wstages))):
         for i in range(3):
             fn(i)
