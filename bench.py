@@ -32,10 +32,34 @@ def workload_name(batch, hw, hd=False):
 
 
 def load_cfg(hd=False):
-    from munit_b200.utils import core_config, get_config
+    """configs/config_256.yaml (or config_HD.yaml) reduced to the benchmark configuration "config_256-core" (SURVEY.md
+    D3/D5): semantic / adaptation heads off; config_HD additionally gets `optimizer: extraadam` (BASELINE.json
+    configs[4]).  yaml only -- the reference arm must not load the product package (or its shared library)."""
+    import yaml
 
-    cfg = core_config(get_config(os.path.join(ROOT, "configs", "config_HD.yaml" if hd else "config_256.yaml")))
-    return cfg
+    with open(os.path.join(ROOT, "configs", "config_HD.yaml" if hd else "config_256.yaml")) as f:
+        conf = yaml.safe_load(f)
+    conf.setdefault("optimizer", "extraadam" if hd else "adam")
+    conf["semantic_w"] = 0
+    conf["recon_mask"] = 0
+    conf["domain_adv_w"] = 0
+    conf.setdefault("recon_synth_w", 0)
+    ad = dict(conf.get("adaptation") or {})
+    for k in ("full_adaptation", "output_classifier_lambda", "output_adv_lambda", "adv_lambda", "dfeat_lambda",
+              "sem_seg_lambda"):
+        ad[k] = 0
+    ad.setdefault("output_classif_freq", 1)
+    ad.setdefault("classif_frequency", 15)
+    conf["adaptation"] = ad
+    return conf
+
+
+def config_dict(cfg, batch, hw, world, hd=False):
+    """The `config` object of the JSON line: the workload only, identical for the B200 arm and the reference arm
+    (implementation details of the B200 arm go under `engine`)."""
+    return dict(workload=workload_name(batch, hw, hd), global_batch=batch * world, batch_per_gpu=batch, image=f"{hw}x{hw}",
+                gen_state=cfg["gen_state"], guided=cfg["guided"], optimizer=cfg["optimizer"], parallelism=f"dp{world}",
+                l2="per-step working set (several GB of activations) >> 126 MB L2; no explicit flush")
 
 
 def profiled_traffic():
@@ -97,55 +121,84 @@ def synthetic_images(batch, hw, seed):
 # ------------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the reference's algorithm on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_steps(cfg, hw, steps, warmup, batch_equiv, budget_s=150.0):
-    """Times dis_update+gen_update of the reference's CPU path at batch 1 (the reference's own batch size,
-    config_256.yaml:13).  Uses the unmodified reference when /root/reference is present, else the oracle
-    port (oracle/munit_oracle.py, pinned to the reference by tests/golden).  Returns steps/s scaled to
-    `batch_equiv` image pairs per step."""
+def _cpu_trainer(cfg):
+    """The reference trainer itself when /root/reference is present (build container), else the oracle port
+    (oracle/munit_oracle.py, pinned to the reference by tests/golden).  Returns (one_step(it, x_a, x_b), kind)."""
     from oracle import munit_oracle as O
     from oracle import ref_loader
 
-    torch.set_num_threads(os.cpu_count() or 1)
-    x_a, x_b = synthetic_images(1, hw, 1234)
-    kind = "port"
     if ref_loader.available():
         torch.manual_seed(0)
         tr = ref_loader.make_trainer(cfg)
-        kind = "reference"
 
-        def one(it):
+        def one(it, x_a, x_b):
             tr.iterations = it
             tr.dis_update(x_a, x_b, cfg)
             tr.gen_update(x_a, x_b, cfg)
+        return one, "reference"
+    double = cfg["gen_state"] == 1
+    if double:
+        gsd = O.init_state_dict(O.gen_spec(cfg["gen"], 3, True), 21, cfg["init"])
     else:
-        double = cfg["gen_state"] == 1
-        if double:
-            gsd = O.init_state_dict(O.gen_spec(cfg["gen"], 3, True), 21, cfg["init"])
-        else:
-            gsd = {k: O.init_state_dict(O.gen_spec(cfg["gen"], 3, False), s, cfg["init"]) for k, s in (("a", 21), ("b", 22))}
-        tr = O.OracleTrainer(cfg, gsd, O.init_state_dict(O.dis_spec(cfg["dis"], 3), 23, "gaussian"),
-                             O.init_state_dict(O.dis_spec(cfg["dis"], 3), 24, "gaussian"))
+        gsd = {k: O.init_state_dict(O.gen_spec(cfg["gen"], 3, False), s, cfg["init"]) for k, s in (("a", 21), ("b", 22))}
+    tr = O.OracleTrainer(cfg, gsd, O.init_state_dict(O.dis_spec(cfg["dis"], 3), 23, "gaussian"),
+                         O.init_state_dict(O.dis_spec(cfg["dis"], 3), 24, "gaussian"))
 
-        def one(it):
-            tr.iterations = it
-            tr.dis_update(x_a, x_b)
-            tr.gen_update(x_a, x_b)
+    def one(it, x_a, x_b):
+        tr.iterations = it
+        tr.dis_update(x_a, x_b)
+        tr.gen_update(x_a, x_b)
+    return one, "port"
+
+
+def cpu_reference_steps(cfg, hw, batch, steps, warmup, budget_s):
+    """Times REAL dis_update+gen_update steps of the reference's CPU path on `batch` image pairs (the B200 arm's
+    step), all host threads, fp32.  Runs `warmup` untimed steps and then up to `steps` timed ones, stopping early
+    once `budget_s` is spent (at least one timed step).  Returns (steps/s, kind, sample text, timed, warm)."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    one, kind = _cpu_trainer(cfg)
+    x_a, x_b = synthetic_images(batch, hw, 1234)
     t0 = time.time()
     times = []
+    warm = 0
     for it in range(warmup + steps):
         t1 = time.time()
-        one(it)
+        one(it, x_a, x_b)
         if it >= warmup:
             times.append(time.time() - t1)
+        else:
+            warm += 1
         if time.time() - t0 > budget_s and times:
             break
-    if not times:
-        times = [time.time() - t0]
-    per_step_b1 = sorted(times)[len(times) // 2]
-    value = 1.0 / (per_step_b1 * batch_equiv)
-    sample = (f"{len(times)} timed step(s) of dis_update+gen_update at batch 1 (the reference's batch size), {hw}x{hw}, "
-              f"fp32, median {per_step_b1:.2f} s/step; steps/s scaled by 1/{batch_equiv} to the batch-{batch_equiv} step")
-    return value, kind, sample, per_step_b1
+    per = sum(times) / len(times)
+    sample = (f"{len(times)} timed + {warm} warm-up step(s) of dis_update+gen_update on {batch} image pairs, {hw}x{hw}, "
+              f"fp32, {torch.get_num_threads()} threads, mean {per:.2f} s/step (no extrapolation)")
+    return 1.0 / per, kind, sample, len(times), warm
+
+
+def cpu_reference_infer(cfg, hw, nstyle, budget_s):
+    """test_batch.py semantics on the host cores: 1 content image x `nstyle` random styles (encode once, decode per
+    style; reference scripts/test_batch.py:146-164), output images / s."""
+    from oracle import munit_oracle as O
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = O.init_state_dict(O.gen_spec(cfg["gen"], 3, False), 21, cfg["init"])
+    g = O.Gen(sd, cfg["gen"], False)
+    x, _ = synthetic_images(1, hw, 1234)
+    times = []
+    t0 = time.time()
+    with torch.no_grad():
+        for it in range(4):
+            t1 = time.time()
+            c, _ = g.encode(x)
+            for _ in range(nstyle):
+                g.decode(c, torch.randn(1, cfg["gen"]["style_dim"], 1, 1))
+            if it:
+                times.append(time.time() - t1)
+            if time.time() - t0 > budget_s and times:
+                break
+    per = sum(times) / len(times)
+    return nstyle / per, f"{len(times)} timed pass(es) of 1 content image x {nstyle} styles, {hw}x{hw}, fp32, oracle port, {per:.2f} s/pass"
 
 
 def run_reference_arm(args):
@@ -153,40 +206,70 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cfg = load_cfg(args.hd)
-    hw = cfg["crop_image_height"]
-    v, kind, sample, per = cpu_reference_steps(cfg, hw, max(1, min(args.steps, 3)), 1, args.batch)
+    hw = args.hw or cfg["crop_image_height"]
     world = int(os.environ.get("WORLD_SIZE", args.gpus))
-    line = dict(impl="reference", metric=METRIC, value=v, unit=UNIT, n_gpus=world, steps=args.steps,
-                warmup=args.warmup, ms_per_step=1000.0 / v, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f32", data="synthetic",
-                config=dict(workload=workload_name(args.batch, hw, args.hd), optimizer=cfg["optimizer"]),
+    # a batch-8 step takes ~15 s on 16 cores: bound the run to a few minutes and report what actually ran
+    v, kind, sample, timed, warm = cpu_reference_steps(cfg, hw, args.batch, max(1, args.steps), min(args.warmup, 1),
+                                                       budget_s=args.ref_budget)
+    per = 1000.0 / v          # ms per real step of `batch` pairs
+    v = v * args.batch / 8.0  # UNIT counts steps of 8 image pairs
+    line = dict(impl="reference", metric=METRIC, value=v, unit=UNIT, n_gpus=world, steps=timed, warmup=warm,
+                ms_per_step=per, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", config=config_dict(cfg, args.batch, hw, world, args.hd),
                 cpu_baseline=dict(value=v, unit=UNIT, cores=os.cpu_count(), kind=kind, sample=sample),
-                e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+                e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                note=f"requested --steps {args.steps} --warmup {args.warmup}; ran {timed} timed / {warm} warm-up "
+                     f"steps inside a {args.ref_budget:.0f} s budget (one CPU process; at N > 1 the B200 arm's value is "
+                     "the whole job of N GPUs)")
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
-def profile_tensor_kernels(runner):
-    """One extra (untimed) eager step with CUDA events around every tap-GEMM / wgrad launch on the launching
-    stream: per-launch device time and direct-form FLOPs of the dominant kernel family."""
+def _bytes(*ts):
+    return float(sum(t.numel() * t.element_size() for t in ts if t is not None))
+
+
+def profile_kernels(runner):
+    """One extra (untimed) eager step with CUDA events around every tap-GEMM / wgrad / normalisation launch on the
+    launching stream: per-launch device time, direct-form FLOPs of the tensor kernels, bytes of the norm kernels."""
     from munit_b200 import kernels as K
 
     rec = {"tapgemm": [], "wgrad": []}
-    orig_t, orig_w = K.tapgemm, K.wgrad
+    nrec = {k: [] for k in ("norm_stats", "norm_finalize", "norm_apply", "norm_bwd_reduce", "norm_bwd_finalize",
+                            "norm_bwd_apply")}
+    names_t = ("tapgemm", "wgrad")
+    orig = {k: getattr(K, k) for k in names_t + tuple(nrec) + ("norm_finalize_parts", "norm_stats_finalize",
+                                                                 "norm_bwd_reduce_finalize")}
 
-    def wrap(name, fn):
-        def inner(plan, *a, **k):
+    def timed(fn, sink, meta):
+        def inner(*a, **k):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            out = fn(plan, *a, **k)
+            out = fn(*a, **k)
             e1.record()
-            rec[name].append((e0, e1, getattr(plan, "alg_flops", 0.0), plan))
+            sink.append((e0, e1) + meta(a, k, out))
             return out
         return inner
 
-    K.tapgemm, K.wgrad = wrap("tapgemm", orig_t), wrap("wgrad", orig_w)
+    K.tapgemm = timed(orig["tapgemm"], rec["tapgemm"], lambda a, k, o: (getattr(a[0], "alg_flops", 0.0), a[0]))
+    K.wgrad = timed(orig["wgrad"], rec["wgrad"], lambda a, k, o: (getattr(a[0], "alg_flops", 0.0), a[0]))
+    # norm kernels: (elements of the pre-norm tensor, bytes the launch actually touches)
+    K.norm_stats = timed(orig["norm_stats"], nrec["norm_stats"], lambda a, k, o: (a[0].numel(), _bytes(a[0])))
+    K.norm_finalize = timed(orig["norm_finalize"], nrec["norm_finalize"], lambda a, k, o: (0, _bytes(a[0])))
+    K.norm_finalize_parts = timed(orig["norm_finalize_parts"], nrec["norm_finalize"], lambda a, k, o: (0, _bytes(a[0])))
+    # fused statistics + finalize / reduce + finalize launches are booked under the pass that reads the big tensors
+    K.norm_stats_finalize = timed(orig["norm_stats_finalize"], nrec["norm_stats"], lambda a, k, o: (a[0].numel(), _bytes(a[0])))
+    K.norm_bwd_reduce_finalize = timed(orig["norm_bwd_reduce_finalize"], nrec["norm_bwd_reduce"],
+                                       lambda a, k, o: (a[3].numel(), _bytes(a[0], a[3])))
+    K.norm_apply = timed(orig["norm_apply"], nrec["norm_apply"],
+                         lambda a, k, o: (a[0].numel(), _bytes(a[0], o) + (_bytes(a[0]) if a[4] is not None else 0.0)))
+    K.norm_bwd_reduce = timed(orig["norm_bwd_reduce"], nrec["norm_bwd_reduce"],
+                              lambda a, k, o: (a[3].numel(), _bytes(a[0], a[3])))
+    K.norm_bwd_finalize = timed(orig["norm_bwd_finalize"], nrec["norm_bwd_finalize"], lambda a, k, o: (0, _bytes(a[0])))
+    K.norm_bwd_apply = timed(orig["norm_bwd_apply"], nrec["norm_bwd_apply"],
+                             lambda a, k, o: (a[3].numel(), _bytes(a[0], a[3], o[0], o[1])))
     trainer = runner.t
     two = getattr(trainer, "parallel_streams", False)
     try:
@@ -196,16 +279,28 @@ def profile_tensor_kernels(runner):
         trainer.parallel_streams = False
         from munit_b200.networks import MsImageDis
         scale_streams, MsImageDis.scale_streams = MsImageDis.scale_streams, False
-        runner._prepare_host_state()
-        torch.cuda.synchronize()
-        torch.cuda._sleep(int(0.5 * 1.9e9))
-        runner._eager_step()
-        runner._advance()
+        # On the runner's own stream, after one untimed eager step: the caching allocator then owns every block this
+        # step needs on this stream (a cudaMalloc in the middle of the step would drain the queue and put host time
+        # into the event pairs).
+        runner.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(runner.stream):
+            runner._prepare_host_state()
+            runner._eager_step()
+            runner._advance()
+            torch.cuda.synchronize()
+            for lst in list(rec.values()) + list(nrec.values()):
+                lst.clear()
+            runner._prepare_host_state()
+            torch.cuda._sleep(int(0.5 * 1.9e9))
+            runner._eager_step()
+            runner._advance()
+        torch.cuda.current_stream().wait_stream(runner.stream)
         torch.cuda.synchronize()
     finally:
         trainer.parallel_streams = two
         MsImageDis.scale_streams = scale_streams
-        K.tapgemm, K.wgrad = orig_t, orig_w
+        for k, v in orig.items():
+            setattr(K, k, v)
     out = {}
     detail = []
     for name, lst in rec.items():
@@ -222,12 +317,22 @@ def profile_tensor_kernels(runner):
                 d.update(m=plan.m_total, ncols=plan.n_total)
             detail.append(d)
     out["detail"] = detail
+    norm = {}
+    for name, lst in nrec.items():
+        ts = [a.elapsed_time(b) for a, b, _, _ in lst]
+        # an event pair that straddles a host-side stall (first-touch allocation behind the spin kernel) is not kernel
+        # time: pairs more than 20x the median of their family are replaced by the median
+        med = sorted(ts)[len(ts) // 2] if ts else 0.0
+        ts = [t if t <= 20.0 * med else med for t in ts]
+        norm[name] = dict(launches=len(lst), ms=sum(ts), elems=float(sum(e for _, _, e, _ in lst)),
+                          bytes=float(sum(by for _, _, _, by in lst)))
+    out["norm"] = norm
     return out
 
 
 def dominant_launch_time(batch, iters=40):
     """The most frequent launch of the step -- 3x3 256->256 conv forward on [batch, 64, 64] content codes,
-    tapgemm_kernel<256,1> -- timed back to back with ONE event pair around `iters` launches on rotating buffers
+    tapgemm_kernel<256> -- timed back to back with ONE event pair around `iters` launches on rotating buffers
     (per-launch event pairs add several us to a ~38 us kernel).  Returns (us per launch, TFLOP/s)."""
     from munit_b200 import geometry as G, kernels as K
 
@@ -251,207 +356,120 @@ def dominant_launch_time(batch, iters=40):
     return us, 2.0 * n * h * w * c * 9 * c / (us * 1e-6) / 1e12
 
 
-def run_b200(args):
-    import torch.distributed as dist
+class TrainRun:
+    """One timed configuration of the training step on this rank: trainer + StepRunner + pinned host inputs."""
 
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    rank = int(os.environ.get("RANK", 0))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from munit_b200 import _lib
-    from munit_b200.engine import StepRunner
-    from munit_b200.trainer import MUNIT_Trainer
+    def __init__(self, cfg, batch, hw, world, rank, args, reuse_forward=False):
+        from munit_b200.engine import StepRunner
+        from munit_b200.trainer import MUNIT_Trainer
 
-    cfg = load_cfg(args.hd)
-    if args.optimizer:
-        cfg["optimizer"] = args.optimizer
-    hw = args.hw or cfg["crop_image_height"]
-    torch.manual_seed(0)  # identical replicas on every rank
-    trainer = MUNIT_Trainer(cfg).cuda()
-    runner = StepRunner(trainer, cfg, args.batch, hw, use_graph=not args.no_graph, world=world,
-                        two_streams=args.two_streams, reuse_forward=bool(args.reuse_forward))
-    x_a, x_b = synthetic_images(args.batch, hw, 1234 + rank)
-    x_a_h, x_b_h = x_a.pin_memory(), x_b.pin_memory()
-    sd = trainer.style_dim
-    s_host = [torch.zeros(args.batch, sd, 1, 1).pin_memory() for _ in range(4)]
+        self.cfg, self.batch, self.hw, self.world, self.rank = cfg, batch, hw, world, rank
+        torch.manual_seed(0)  # identical replicas on every rank
+        self.trainer = MUNIT_Trainer(cfg).cuda()
+        self.runner = StepRunner(self.trainer, cfg, batch, hw, use_graph=not args.no_graph, world=world,
+                                 two_streams=args.two_streams, reuse_forward=reuse_forward)
+        x_a, x_b = synthetic_images(batch, hw, 1234 + rank)
+        self.x_a_h, self.x_b_h = x_a.pin_memory(), x_b.pin_memory()
+        self.sd = self.trainer.style_dim
+        self.s_host = [torch.zeros(batch, self.sd, 1, 1).pin_memory() for _ in range(4)]
+        torch.manual_seed(1000 + rank)
+        self.draw_styles()
+        self.runner.load_inputs(self.x_a_h, self.x_b_h, *self.s_host)
 
-    def draw_styles():
+    def draw_styles(self):
         # host-generator draws in the reference's order: dis_update (s_a, s_b) then gen_update (s_a, s_b)
-        for s in s_host:
-            s.copy_(torch.randn(args.batch, sd, 1, 1))
+        for s in self.s_host:
+            s.copy_(torch.randn(self.batch, self.sd, 1, 1))
 
-    torch.manual_seed(1000 + rank)
-    draw_styles()
-    runner.load_inputs(x_a_h, x_b_h, *s_host)
-    if args.ncu_step:
-        # For `ncu --profile-from-start off ...`: two eager warm-up steps, then exactly one eager step inside the
-        # profiler range (about 1800 launches, a couple of minutes under ncu instead of the whole benchmark).
-        for _ in range(2):
-            runner.step()
-        torch.cuda.synchronize()
-        torch.cuda.profiler.start()
-        runner.step()
-        torch.cuda.synchronize()
-        torch.cuda.profiler.stop()
-        print(json.dumps({"ncu_step": "one eager dis_update+gen_update in the profiler range",
-                          "launches": runner.launches_per_step}))
-        return
-    runner.warmup_and_capture(2)
-    for _ in range(args.warmup):
-        runner.step()
-    torch.cuda.synchronize()
-
-    def barrier():
-        if world > 1:
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    # ---- value: inputs resident in HBM
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        runner.step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    # ---- e2e: host buffers -> H2D every step, loss read back every step
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    last = None
-    for _ in range(args.steps):
-        draw_styles()
-        runner.load_inputs(x_a_h, x_b_h, *s_host)
-        runner.step()
-        ls = runner.losses()
-        last = (float(ls["loss_dis_total"]), float(ls["loss_gen_total"]))  # D2H + sync
-    f1.record()
-    barrier()
-    ms_e2e = f0.elapsed_time(f1)
-    clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        tt = torch.tensor([ms, ms_e2e], device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(tt[0]), float(tt[1])
-    prof = profile_tensor_kernels(runner)
-    overlap_note = (sum(len(g.buckets) for g in trainer.grad_sync.values()),
-                    sum(g.early_pass for g in trainer.grad_sync.values()), runner.overlap)
-    if world > 1:
-        runner.release()  # captured graphs reference the communicator: drop them before the process group goes
-        dist.barrier()
-    # ---- informational: the same step with gen_update picking up dis_update's generator pass (trainer.reuse_forward)
-    reuse_line = None
-    if world == 1 and not args.reuse_forward and not args.no_graph and cfg["guided"] == 1 and cfg["gen_state"] == 1:
-        try:
-            runner.release()
-            r2 = StepRunner(trainer, cfg, args.batch, hw, use_graph=True, world=1, two_streams=args.two_streams,
-                            reuse_forward=True)
-            r2.iter = runner.iter
-            r2.load_inputs(x_a_h, x_b_h, *s_host)
-            r2.warmup_and_capture(1)
-            for _ in range(args.warmup):
-                r2.step()
-            torch.cuda.synchronize()
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            g0.record()
-            for _ in range(args.steps):
-                r2.step()
-            g1.record()
-            torch.cuda.synchronize()
-            ms2 = g0.elapsed_time(g1)
-            ls2 = r2.losses()
-            reuse_line = dict(value=args.steps / (ms2 / 1000.0), unit=UNIT, ms_per_step=ms2 / args.steps,
-                              gpu_launches_per_step=r2.launches_per_step,
-                              last_losses=dict(dis=float(ls2["loss_dis_total"]), gen=float(ls2["loss_gen_total"])),
-                              note="NOT the headline: same dis_update + gen_update calls with trainer.reuse_forward = True "
-                                   "-- gen_update reuses the generator pass (encode x_a, x_b; decode within / across "
-                                   "domains) that dis_update ran on the same batch and the same generator weights "
-                                   "(guided = 1), 155 of the step's 1395 GMAC per pair are not computed twice; losses, "
-                                   "gradients and both optimizer steps as in the headline run "
-                                   "(tests/test_trainer_gpu.py::test_forward_reuse_between_updates_is_transparent)")
-            r2.release()
-            trainer.reuse_forward = False
-        except Exception as exc:  # informational line only: never lose the headline over it
-            reuse_line = dict(error=repr(exc))
-            trainer.reuse_forward = False
+    def prepare(self, warmup):
+        self.runner.warmup_and_capture(2)
+        for _ in range(warmup):
+            self.runner.step()
+        torch.cuda.synchronize()
 
-    dom_us, dom_tf = dominant_launch_time(args.batch) if rank == 0 else (0.0, 0.0)
-    if rank == 0 and args.dump_launches:
-        json.dump(prof["detail"], open(args.dump_launches, "w"))
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    peaks = measured_peaks()
-    steps_per_s = args.steps / (ms / 1000.0) * world  # batch-8-equivalent steps, whole job
-    e2e_per_s = args.steps / (ms_e2e / 1000.0) * world
-    tg = prof["tapgemm"]
-    ach = tg["flops"] / (tg["ms"] / 1000.0) / 1e12 if tg["ms"] > 0 else 0.0
-    wg = prof["wgrad"]
-    ach_w = wg["flops"] / (wg["ms"] / 1000.0) / 1e12 if wg["ms"] > 0 else 0.0
-    h2d = 2 * args.batch * 3 * hw * hw * 4 + 4 * args.batch * sd * 4 + 2 * 16
-    algo_tflop_step = 2.790 * args.batch * (hw / 256.0) ** 2  # SURVEY.md s8d, per sample pair at 256^2
-    cpu_v, cpu_kind, cpu_sample, _ = cpu_reference_steps(cfg, hw, 2, 1, args.batch, budget_s=40.0) \
-        if (world == 1 and not args.no_cpu_baseline) else (None, "port", "skipped (N>1 or --no-cpu-baseline)", None)
-    line = dict(
-        metric=METRIC, value=steps_per_s, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-        ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
-        data="synthetic",
-        config=dict(workload=workload_name(args.batch, hw, args.hd),
-                    global_batch=args.batch * world, gen_state=cfg["gen_state"], guided=cfg["guided"],
-                    optimizer=cfg["optimizer"], parallelism=f"dp{world}", cuda_graph=not args.no_graph, two_streams=bool(args.two_streams),
-                    grad_exchange=("none (1 GPU)" if world == 1 else
-                                   ("NCCL all-reduce per ready bucket, overlapped with backward, captured in the step graph "
-                                    f"({overlap_note[0]} buckets, {overlap_note[1]} launched before the end "
-                                    "of their backward pass)"
-                                    if overlap_note[2] else "NCCL all-reduce of the whole arena between three captured segments")),
-                    l2="per-step working set (several GB of bf16 activations) >> 126 MB L2; no explicit flush"),
-        e2e=dict(value=e2e_per_s, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=8,
-                 last_losses=dict(dis=last[0], gen=last[1])),
-        gpu_launches=(runner.launches_per_step or 0) * args.steps,
-        clocks=clocks,
-        roofline=dict(bound="tensor", kernel="tapgemm_kernel<BN> (conv fwd + dgrad, tcgen05)", achieved=ach,
-                      peak=peaks["tflops"], unit="TFLOP/s", frac=ach / peaks["tflops"] if peaks["tflops"] else None,
-                      traffic=profiled_traffic()[0], traffic_kernel=profiled_traffic()[1],
-                      peak_source=peaks["src"], launches_per_step=tg["launches"],
-                      kernel_ms_per_step=tg["ms"],
-                      note="achieved = direct-form FLOPs of all conv fwd/dgrad launches / their device time, one CUDA "
-                           "event pair per launch (the pair itself adds several us to each ~40 us launch)",
-                      dominant_launch=dict(kernel="tapgemm_kernel<256,1>, 3x3 256->256 forward on [B,64,64]",
-                                           us=dom_us, achieved=dom_tf,
-                                           frac=dom_tf / peaks["tflops"] if peaks["tflops"] else None,
-                                           method="one event pair around 40 back-to-back launches, rotating buffers"),
-                      wgrad=dict(achieved=ach_w, launches_per_step=wg["launches"], kernel_ms_per_step=wg["ms"]),
-                      step_algorithmic_tflop=algo_tflop_step,
-                      step_frac=(algo_tflop_step / (ms / args.steps / 1000.0)) / peaks["tflops"]),
-        cpu_baseline=dict(value=cpu_v, unit=UNIT, cores=os.cpu_count(), kind=cpu_kind, sample=cpu_sample),
-    )
-    if reuse_line is not None:
-        line["forward_reuse"] = reuse_line
-    if args.reuse_forward:
-        line["config"]["reuse_forward"] = True
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    def time_resident(self, steps):
+        """K steps with the inputs resident in HBM; returns ms (max over ranks)."""
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            self.runner.step()
+        e1.record()
+        self.barrier()
+        return self._max(e0.elapsed_time(e1))
+
+    def time_e2e(self, steps):
+        """K steps through the public entry: per step host randn of the style codes, pinned H2D of images + codes,
+        the step, D2H of both total losses."""
+        self.barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        last = None
+        for _ in range(steps):
+            self.draw_styles()
+            self.runner.load_inputs(self.x_a_h, self.x_b_h, *self.s_host)
+            self.runner.step()
+            ls = self.runner.losses()
+            last = (float(ls["loss_dis_total"]), float(ls["loss_gen_total"]))  # D2H + sync
+        f1.record()
+        self.barrier()
+        return self._max(f0.elapsed_time(f1)), last
+
+    def _max(self, ms):
+        if self.world > 1:
+            import torch.distributed as dist
+            tt = torch.tensor([ms], device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt[0])
+        return ms
+
+    def h2d_bytes(self):
+        return 2 * self.batch * 3 * self.hw * self.hw * 4 + 4 * self.batch * self.sd * 4 + 2 * 16
+
+    def close(self):
+        import gc
+        self.runner.release()
+        self.runner = self.trainer = None
+        gc.collect()
+        torch.cuda.empty_cache()
 
 
-def run_infer(args):
+def side_train_line(cfg, batch, hw, world, rank, args, steps, warmup, what):
+    """Informational extra configuration (never the headline): resident + e2e timing, no profiling pass."""
+    run = TrainRun(cfg, batch, hw, world, rank, args)
+    try:
+        run.prepare(warmup)
+        ms = run.time_resident(steps)
+        ms_e2e, last = run.time_e2e(steps)
+        launches = run.runner.launches_per_step
+        peaks = measured_peaks()
+        tflop = 2.790 * batch * (hw / 256.0) ** 2  # per GPU per step (SURVEY.md s8d)
+        return dict(workload=what, config=config_dict(cfg, batch, hw, world, hw >= 512), steps=steps, warmup=warmup,
+                    ms_per_step=ms / steps, steps_per_s=steps / (ms / 1000.0),
+                    pairs_per_s=steps * batch * world / (ms / 1000.0),
+                    e2e_pairs_per_s=steps * batch * world / (ms_e2e / 1000.0), gpu_launches_per_step=launches,
+                    step_frac_of_tensor_peak=(tflop / (ms / steps / 1000.0)) / peaks["tflops"],
+                    last_losses=dict(dis=last[0], gen=last[1]))
+    finally:
+        run.close()
+
+
+def infer_line(args, steps, with_cpu):
     """test_batch.py semantics (BASELINE.json configs[3]): 32 content images x 10 random style codes at 256^2,
     gen_state 0: one content-encode + 10 (MLP + decoder) passes per step -> output images / s."""
-    torch.cuda.set_device(0)
     from munit_b200 import _lib
     from munit_b200.trainer import MUNIT_Trainer
 
-    cfg = load_cfg(args.hd)
+    cfg = load_cfg(False)
     cfg["gen_state"], cfg["guided"] = 0, 0
-    hw = args.hw or cfg["crop_image_height"]
-    nimg, nstyle = args.batch if args.batch != 8 else 32, 10
+    hw = cfg["crop_image_height"]
+    nimg, nstyle = args.infer_batch, 10
     torch.manual_seed(0)
     t = MUNIT_Trainer(cfg).cuda().eval()
     x, _ = synthetic_images(nimg, hw, 1234)
@@ -477,19 +495,21 @@ def run_infer(args):
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g, stream=s):
         step()
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(3):
         g.replay()
     torch.cuda.synchronize()
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         g.replay()
     e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
+    ms = e0.elapsed_time(e1) / steps
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     host_out = torch.empty(nstyle, nimg, 3, hw, hw).pin_memory()
     f0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         styles_h.copy_(torch.randn(nstyle, t.style_dim, 1, 1))
         x_d.copy_(x_h, non_blocking=True); styles_d.copy_(styles_h, non_blocking=True)
         g.replay()
@@ -497,21 +517,214 @@ def run_infer(args):
             host_out[j].copy_(outs[j], non_blocking=True)
         torch.cuda.synchronize()
     f1.record(); torch.cuda.synchronize()
-    ms_e2e = f0.elapsed_time(f1) / args.steps
+    ms_e2e = f0.elapsed_time(f1) / steps
+    clocks = sampler.stop()
     peaks = measured_peaks()
     n_out = nimg * nstyle
     tflop = 0.9842 * nimg * (hw / 256.0) ** 2  # 492.1 GMAC per content image with 10 styles
     line = dict(metric="MUNIT style-sampled inference output imgs/sec 256^2", value=n_out / (ms / 1000.0), unit="images/s",
-                n_gpus=1, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms, higher_is_better=True,
-                scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                n_gpus=1, steps=steps, warmup=3, ms_per_step=ms, higher_is_better=True, dtype="bf16", data="synthetic",
                 config=dict(workload=f"test_batch: {nimg} content images x {nstyle} random styles, {hw}x{hw}, gen_state 0",
                             cuda_graph=True, l2="activations per step >> 126 MB L2; no explicit flush"),
                 e2e=dict(value=n_out / (ms_e2e / 1000.0), unit="images/s", h2d_bytes_per_step=int(x.numel() * 4 + styles_h.numel() * 4),
                          d2h_bytes_per_step=int(host_out.numel() * 4)),
-                gpu_launches=launches * args.steps,
+                gpu_launches=launches * steps, clocks=clocks,
                 roofline=dict(bound="tensor", achieved=tflop / (ms / 1000.0), peak=peaks["tflops"], unit="TFLOP/s",
                               frac=tflop / (ms / 1000.0) / peaks["tflops"], traffic=None, peak_source=peaks["src"],
                               note="whole-step direct-form FLOPs / step time"))
+    del g, t, outs
+    import gc
+    gc.collect(); torch.cuda.empty_cache()
+    if with_cpu:
+        v, sample = cpu_reference_infer(cfg, hw, nstyle, budget_s=20.0)
+        line["cpu_baseline"] = dict(value=v, unit="images/s", cores=os.cpu_count(), kind="port", sample=sample)
+    return line
+
+
+def run_b200(args):
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from munit_b200 import _lib  # noqa: F401  (fails loudly when the shared library is missing)
+
+    cfg = load_cfg(args.hd)
+    if args.optimizer:
+        cfg["optimizer"] = args.optimizer
+    hw = args.hw or cfg["crop_image_height"]
+    batch = args.batch
+    scaling = "weak"
+    if args.global_batch:
+        assert args.global_batch % world == 0, "--global-batch must be divisible by the number of GPUs"
+        batch, scaling = args.global_batch // world, "strong"
+    run = TrainRun(cfg, batch, hw, world, rank, args, reuse_forward=bool(args.reuse_forward))
+    runner, trainer = run.runner, run.trainer
+    if args.ncu_step:
+        # For `ncu --profile-from-start off ...`: two eager warm-up steps, then exactly one eager step inside the
+        # profiler range (about 1800 launches, a couple of minutes under ncu instead of the whole benchmark).
+        for _ in range(2):
+            runner.step()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        runner.step()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"ncu_step": "one eager dis_update+gen_update in the profiler range",
+                          "launches": runner.launches_per_step}))
+        return
+    run.prepare(args.warmup)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = run.time_resident(args.steps)          # value: inputs resident in HBM
+    ms_e2e, last = run.time_e2e(args.steps)     # e2e: host buffers -> H2D every step, losses read back every step
+    clocks = sampler.stop() if rank == 0 else None
+    prof = profile_kernels(runner)
+    overlap_note = (sum(len(g.buckets) for g in trainer.grad_sync.values()),
+                    sum(g.early_pass for g in trainer.grad_sync.values()), runner.overlap)
+    launches_per_step = runner.launches_per_step or 0
+    h2d = run.h2d_bytes()
+    run.close()
+    del runner, trainer
+    if world > 1:
+        dist.barrier()
+    extras = {}
+    side_steps = max(3, min(args.steps, 8))
+
+    def extra(name, fn):
+        try:
+            extras[name] = fn()
+        except Exception as exc:  # informational lines only: never lose the headline over one of them
+            extras[name] = dict(error=repr(exc)[:300])
+            import gc
+            gc.collect(); torch.cuda.empty_cache()
+
+    plain = not (args.hd or args.global_batch or args.no_extras or args.no_graph or args.hw or args.batch != 8)
+    # ---- informational: the same step with gen_update picking up dis_update's generator pass (trainer.reuse_forward)
+    if plain and world == 1 and not args.reuse_forward and cfg["guided"] == 1 and cfg["gen_state"] == 1:
+        def reuse():
+            r2 = TrainRun(cfg, batch, hw, world, rank, args, reuse_forward=True)
+            try:
+                r2.prepare(args.warmup)
+                ms2 = r2.time_resident(args.steps)
+                ls2 = r2.runner.losses()
+                return dict(value=args.steps / (ms2 / 1000.0), unit=UNIT, ms_per_step=ms2 / args.steps,
+                            gpu_launches_per_step=r2.runner.launches_per_step,
+                            last_losses=dict(dis=float(ls2["loss_dis_total"]), gen=float(ls2["loss_gen_total"])),
+                            note="NOT the headline: same dis_update + gen_update calls with trainer.reuse_forward = True "
+                                 "-- gen_update reuses the generator pass (encode x_a, x_b; decode within / across "
+                                 "domains) that dis_update ran on the same batch and the same generator weights "
+                                 "(guided = 1), 155 of the step's 1395 GMAC per pair are not computed twice; losses, "
+                                 "gradients and both optimizer steps as in the headline run "
+                                 "(tests/test_trainer_gpu.py::test_forward_reuse_between_updates_is_transparent)")
+            finally:
+                r2.trainer.reuse_forward = False
+                r2.close()
+        extra("forward_reuse", reuse)
+    # ---- informational: BASELINE.json configs[2] (global batch 64 over the N GPUs the driver passed: strong scaling),
+    # configs[4] (config_HD, 512^2, ExtraAdam) and configs[3] (32 x 10 style-sampled inference, one GPU)
+    if plain and 64 % world == 0:
+        extra("global_batch_64", lambda: side_train_line(
+            cfg, 64 // world, hw, world, rank, args, side_steps, 3,
+            f"config_256-core train step, GLOBAL batch 64 = {64 // world}/GPU x {world} GPU(s) (strong scaling over N)"))
+    if plain:
+        cfg_hd = load_cfg(True)
+        extra("hd", lambda: side_train_line(cfg_hd, args.hd_batch, cfg_hd["crop_image_height"], world, rank, args,
+                                            side_steps + side_steps % 2, 4,
+                                            f"config_HD train step (ExtraAdam, extrapolation/step pairs), "
+                                            f"batch {args.hd_batch}/GPU, 512x512"))
+    if plain and world == 1:
+        extra("infer", lambda: infer_line(args, side_steps, not args.no_cpu_baseline))
+    dom_us, dom_tf = dominant_launch_time(batch) if rank == 0 else (0.0, 0.0)
+    if rank == 0 and args.dump_launches:
+        json.dump(prof["detail"], open(args.dump_launches, "w"))
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = measured_peaks()
+    per8 = batch / 8.0                                            # UNIT counts steps of 8 image pairs
+    steps_per_s = args.steps / (ms / 1000.0) * world * per8       # whole job
+    e2e_per_s = args.steps / (ms_e2e / 1000.0) * world * per8
+    tg = prof["tapgemm"]
+    ach = tg["flops"] / (tg["ms"] / 1000.0) / 1e12 if tg["ms"] > 0 else 0.0
+    wg = prof["wgrad"]
+    ach_w = wg["flops"] / (wg["ms"] / 1000.0) / 1e12 if wg["ms"] > 0 else 0.0
+    algo_tflop_step = 2.790 * batch * (hw / 256.0) ** 2  # SURVEY.md s8d, per sample pair at 256^2
+    # normalisation family against the HBM roofline.  Algorithmic bytes: forward 4 B per element of
+    # the pre-norm tensor (read + write, statistics from the producer), backward 6 B + 4 B for the reduction pass.
+    nm = prof["norm"]
+    fwd_el = nm["norm_apply"]["elems"]
+    bwd_el = nm["norm_bwd_apply"]["elems"]
+    norm_ms = sum(v["ms"] for v in nm.values())
+    alg_bytes = 4.0 * fwd_el + 10.0 * bwd_el
+    moved = sum(v["bytes"] for v in nm.values())
+    ach_hbm = alg_bytes / (norm_ms / 1000.0) / 1e9 if norm_ms > 0 else 0.0
+    cpu_line = dict(value=None, unit=UNIT, cores=os.cpu_count(), kind="port", sample="skipped (N>1 or --no-cpu-baseline)")
+    if world == 1 and not args.no_cpu_baseline:
+        v, kind, sample, _, _ = cpu_reference_steps(cfg, hw, batch, 2, 0, budget_s=25.0)
+        cpu_line = dict(value=v * per8, unit=UNIT, cores=os.cpu_count(), kind=kind, sample=sample)
+    line = dict(
+        metric=METRIC, value=steps_per_s, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+        ms_per_step=ms / args.steps, higher_is_better=True, scaling=scaling, vs_baseline=None, dtype="bf16",
+        data="synthetic",
+        config=config_dict(cfg, batch, hw, world, args.hd),
+        engine=dict(cuda_graph=not args.no_graph, two_streams=bool(args.two_streams),
+                    grad_exchange=("none (1 GPU)" if world == 1 else
+                                   ("NCCL all-reduce per ready bucket, overlapped with backward, captured in the step graph "
+                                    f"({overlap_note[0]} buckets, {overlap_note[1]} launched before the end "
+                                    "of their backward pass)"
+                                    if overlap_note[2] else "NCCL all-reduce of the whole arena between three captured segments"))),
+        e2e=dict(value=e2e_per_s, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=8,
+                 last_losses=dict(dis=last[0], gen=last[1])),
+        gpu_launches=launches_per_step * args.steps,
+        clocks=clocks,
+        roofline=dict(bound="tensor", kernel="tapgemm_kernel<BN> (conv fwd + dgrad, tcgen05)", achieved=ach,
+                      peak=peaks["tflops"], unit="TFLOP/s", frac=ach / peaks["tflops"] if peaks["tflops"] else None,
+                      traffic=profiled_traffic()[0], traffic_kernel=profiled_traffic()[1],
+                      peak_source=peaks["src"], launches_per_step=tg["launches"],
+                      kernel_ms_per_step=tg["ms"],
+                      note="achieved = direct-form FLOPs of all conv fwd/dgrad launches / their device time inside the "
+                           "step, one CUDA event pair per launch (the pair itself adds several us to each ~40 us launch); "
+                           "in-step figures are graded against the sustained peak, the isolated launch against burst",
+                      dominant_launch=dict(kernel="tapgemm_kernel<256>, 3x3 256->256 forward on [B,64,64]",
+                                           us=dom_us, achieved=dom_tf, peak=peaks["tflops_burst"],
+                                           frac=dom_tf / peaks["tflops_burst"] if peaks["tflops_burst"] else None,
+                                           method="one event pair around 40 back-to-back launches, rotating buffers; "
+                                                  "denominator = burst bf16 peak (kernel timed alone)"),
+                      wgrad=dict(achieved=ach_w, launches_per_step=wg["launches"], kernel_ms_per_step=wg["ms"],
+                                 frac=ach_w / peaks["tflops"] if peaks["tflops"] else None),
+                      step_algorithmic_tflop=algo_tflop_step,
+                      step_frac=(algo_tflop_step / (ms / args.steps / 1000.0)) / peaks["tflops"]),
+        roofline_hbm=dict(bound="hbm", kernel="norm_stats / norm_apply / norm_bwd_reduce / norm_bwd_apply (+ finalize)",
+                          achieved=ach_hbm, peak=peaks["hbm"], unit="GB/s", frac=ach_hbm / peaks["hbm"] if peaks["hbm"] else None,
+                          kernel_ms_per_step=norm_ms, launches_per_step=sum(v["launches"] for v in nm.values()),
+                          algorithmic_bytes_per_step=alg_bytes, moved_bytes_per_step=moved,
+                          moved_gbs=moved / (norm_ms / 1000.0) / 1e9 if norm_ms > 0 else 0.0,
+                          per_kernel={k: dict(ms=v["ms"], launches=v["launches"],
+                                              gbs=(v["bytes"] / (v["ms"] / 1000.0) / 1e9 if v["ms"] > 0 else 0.0))
+                                      for k, v in nm.items()},
+                          note="achieved = algorithmic bytes (SURVEY.md 8d: 4 B per pre-norm element forward, 10 B "
+                               "backward) / summed device time of the family inside the step; moved = bytes the "
+                               "launches actually touch (statistics pass, 4x up-sampled writes and halos included)"),
+        cpu_baseline=cpu_line,
+    )
+    line.update(extras)
+    if args.reuse_forward:
+        line["config"]["reuse_forward"] = True
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_infer(args):
+    torch.cuda.set_device(0)
+    line = infer_line(args, args.steps, not args.no_cpu_baseline)
+    line.update(scaling="weak", vs_baseline=None)
     print(json.dumps(line))
 
 
@@ -522,14 +735,20 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="image pairs per GPU per step")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling: total image pairs per step, split over the GPUs (BASELINE.json configs[2]: 64)")
     ap.add_argument("--hw", type=int, default=0, help="override crop size")
     ap.add_argument("--hd", action="store_true", help="config_HD (512x512, ExtraAdam)")
+    ap.add_argument("--hd-batch", type=int, default=8, help="image pairs per GPU of the informational config_HD line")
+    ap.add_argument("--infer-batch", type=int, default=32, help="content images of the inference workload")
     ap.add_argument("--optimizer", default="")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--two-streams", type=int, default=1,
                     help="0: one stream; 1: domain-a / domain-b branches on two streams; 2: plus weight gradients on "
                          "companion streams")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline only (skip forward_reuse / global_batch_64 / hd / infer)")
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds of CPU time the reference arm may spend")
     ap.add_argument("--reuse-forward", type=int, default=0,
                     help="1: gen_update reuses the generator pass of the preceding dis_update (trainer.reuse_forward); "
                          "the default run reports it next to the headline as `forward_reuse`")

@@ -181,6 +181,12 @@ enum { MUNIT_NORM_IN = 0, MUNIT_NORM_ADAIN = 1, MUNIT_NORM_LN = 2 };
 int munit_norm_finalize(const float* stats, const float* shift, int mode, const float* p_w, const float* p_b,
                         int64_t ldw, float eps, float* mean, float* rinv, float* a, float* b, int n, int hw, int c,
                         void* stream);
+/* munit_norm_stats + munit_norm_finalize in ONE launch: every block publishes its partials and takes a ticket from
+ * tickets[n]; the block that draws the last ticket of sample n runs the finalize for it (partials added in split order,
+ * so the result is bit-identical to the two-call sequence).  `tickets`: N zero-initialised int32, returned to zero. */
+int munit_norm_stats_finalize(const void* y, int y_f16, float* stats, float* shift, int32_t* tickets, int mode,
+                              const float* p_w, const float* p_b, int64_t ldw, float eps, float* mean, float* rinv,
+                              float* a, float* b, int n, int hw, int c, void* stream);
 /* Same, from the split partials a convolution epilogue left (munit_tapgemm_desc.stats): `splits` partials per
  * sample, unshifted sums.  kind 1: per-channel partials [N][splits][C][2], mode IN or ADAIN; kind 2: channel-reduced
  * partials [N][splits][2], mode LN. */
@@ -202,6 +208,12 @@ int munit_norm_bwd_reduce(const void* g_out, int out_pad, int upsample, const vo
 int munit_norm_bwd_finalize(const float* sums, int mode, const float* p_w, int64_t ldw, const float* rinv, float eps,
                             float* ca, float* cb, float* cc, float* g_w, float* g_b, int64_t ldg, int n, int hw, int c,
                             void* stream);
+/* munit_norm_bwd_reduce + munit_norm_bwd_finalize in ONE launch (last block per sample finalizes, as above). */
+int munit_norm_bwd_reduce_finalize(const void* g_out, int out_pad, int upsample, const void* y, int y_f16, const float* a,
+                                   const float* b, int relu, const float* mean, const float* rinv, float* sums,
+                                   int32_t* tickets, int mode, const float* p_w, int64_t ldw, float eps, float* ca,
+                                   float* cb, float* cc, float* g_w, float* g_b, int64_t ldg, int n, int h, int w, int c,
+                                   void* stream);
 /* pass 2: dy [N][H][W][C] bf16 = ca*dz + cb*xhat + cc; optional g_res (act buffer, halo res_pad, halo zeroed) = fold(g_out). */
 int munit_norm_bwd_apply(const void* g_out, int out_pad, int upsample, const void* y, int y_f16, const float* a,
                          const float* b, int relu, const float* mean, const float* rinv, const float* ca, const float* cb,

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmunit_b200.so")
+LIB_PATH = os.environ.get("MUNIT_LIB") or os.path.join(_HERE, "libmunit_b200.so")  # MUNIT_LIB: A/B builds (dev aid)
 
 MAX_TAPS = 49
 MAX_PHASES = 4
@@ -75,6 +75,9 @@ _SIGS = {
     "munit_norm_splits": ([_i, _i], C.c_int),
     "munit_norm_stats": ([_vp, _i, _vp, _vp, _i, _i, _i, _vp], C.c_int),
     "munit_norm_finalize": ([_vp, _vp, _i, _vp, _vp, _i64, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp], C.c_int),
+    "munit_norm_stats_finalize": ([_vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _i64, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp], C.c_int),
+    "munit_norm_bwd_reduce_finalize": ([_vp, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _i64, _f, _vp, _vp, _vp,
+                                        _vp, _vp, _i64, _i, _i, _i, _i, _vp], C.c_int),
     "munit_norm_finalize_parts": ([_vp, _i, _i, _i, _vp, _vp, _i64, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp], C.c_int),
     "munit_norm_apply": ([_vp, _i, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp], C.c_int),
     "munit_norm_bwd_reduce": ([_vp, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp], C.c_int),

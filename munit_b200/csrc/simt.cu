@@ -319,16 +319,26 @@ __device__ __forceinline__ void sum_splits_to_smem(const float* __restrict__ par
     const float2* p = reinterpret_cast<const float2*>(part) + (long long)n * splits * c + ch;
     double s1 = 0.0, s2 = 0.0;
     int s = 0;
+    for (; s + 16 <= splits; s += 16) {
+      float2 v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __ldcg(p + (long long)(s + i) * c);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        s1 += (double)v[i].x;
+        s2 += (double)v[i].y;
+      }
+    }
     for (; s + 4 <= splits; s += 4) {
-      const float2 v0 = p[(long long)(s + 0) * c], v1 = p[(long long)(s + 1) * c];
-      const float2 v2 = p[(long long)(s + 2) * c], v3 = p[(long long)(s + 3) * c];
+      const float2 v0 = __ldcg(p + (long long)(s + 0) * c), v1 = __ldcg(p + (long long)(s + 1) * c);
+      const float2 v2 = __ldcg(p + (long long)(s + 2) * c), v3 = __ldcg(p + (long long)(s + 3) * c);
       s1 += (double)v0.x; s2 += (double)v0.y;
       s1 += (double)v1.x; s2 += (double)v1.y;
       s1 += (double)v2.x; s2 += (double)v2.y;
       s1 += (double)v3.x; s2 += (double)v3.y;
     }
     for (; s < splits; ++s) {
-      const float2 v = p[(long long)s * c];
+      const float2 v = __ldcg(p + (long long)s * c);
       s1 += (double)v.x; s2 += (double)v.y;
     }
     sm[ch * 2] = s1;
@@ -337,21 +347,60 @@ __device__ __forceinline__ void sum_splits_to_smem(const float* __restrict__ par
   __syncthreads();
 }
 
+// (yy, x) of pixel `pix` of a row-major H x W image: shift / mask when W is a power of two (lw = log2 W), else divide.
+__device__ __forceinline__ void pix_coords(int pix, int w, int lw, int& yy, int& x) {
+  if (lw >= 0) {
+    yy = pix >> lw;
+    x = pix & (w - 1);
+  } else {
+    yy = pix / w;
+    x = pix - yy * w;
+  }
+}
+inline int log2_or_neg(int w) {
+  int l = 0;
+  while ((1 << l) < w) ++l;
+  return (1 << l) == w ? l : -1;
+}
+// Does pixel (yy, x) of the H x W map have mirrored halo copies in the UP-sampled output padded by `pad`?
+template <int UP>
+__device__ __forceinline__ bool is_border(int yy, int x, int h, int w, int pad) {
+  const int r0 = yy * UP, c0 = x * UP;
+  return pad > 0 && (r0 <= pad || c0 <= pad || r0 + UP - 1 >= h * UP - 1 - pad || c0 + UP - 1 >= w * UP - 1 - pad);
+}
+
 template <bool H>
 __device__ __forceinline__ void norm_stats_body(Blk blk, const bf16* __restrict__ y, float* __restrict__ stats,
                                                 float* __restrict__ shift, int hw, int c) {
-  const int cg_own = threadIdx.x % (c / 8);
-  const F8 s = load8y<H>(y + ((long long)blk.by * hw) * c + cg_own * 8);  // per-thread constant: hoisted
-  auto fn = [&](int n, int pix, int cg, F8& u, F8& v) {
-    const F8 x = load8y<H>(y + ((long long)n * hw + pix) * c + cg * 8);
+  constexpr int U = 4;  // pixels whose loads a thread issues before it consumes any
+  const int cgs = c / 8;
+  const int rows = blockDim.x / cgs;
+  const int cg = threadIdx.x % cgs, r = threadIdx.x / cgs;
+  const int per = (hw + blk.nbx - 1) / blk.nbx;
+  const int p0 = blk.bx * per, p1 = min(hw, p0 + per);
+  const bf16* base = y + ((long long)blk.by * hw) * c + cg * 8;
+  const F8 s = load8y<H>(base);  // shift = first pixel of the sample (per-thread constant)
+  float s0[8], s1[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float d = x.v[e] - s.v[e];
-      u.v[e] = d;
-      v.v[e] = d * d;
+  for (int e = 0; e < 8; ++e) s0[e] = s1[e] = 0.f;
+  if (r < rows)
+    for (int pb = p0 + r; pb < p1; pb += rows * U) {
+      uint4 raw[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) raw[u] = *reinterpret_cast<const uint4*>(base + min(pb + u * rows, p1 - 1) * c);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (pb + u * rows < p1) {
+          const F8 x = unpack8y<H>(raw[u]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float d = x.v[e] - s.v[e];
+            s0[e] += d;
+            s1[e] = fmaf(d, d, s1[e]);
+          }
+        }
     }
-  };
-  reduce_nc(blk, fn, stats, hw, c);
+  reduce_nc_tail(blk, s0, s1, stats, c);
   if (blk.bx == 0)
     for (int ch = threadIdx.x; ch < c; ch += blockDim.x)
       shift[(long long)blk.by * c + ch] = scalar_y<H>(y + ((long long)blk.by * hw) * c + ch);
@@ -362,6 +411,23 @@ __global__ void norm_stats_kernel(const bf16* __restrict__ y, float* __restrict_
   pdl_wait();
   pdl_trigger();
   norm_stats_body<H>(launch_blk(), y, stats, shift, hw, c);
+}
+
+// "Last block done": every block of sample n publishes its partials, takes a ticket, and the block that draws the last
+// ticket runs the finalize for that sample (partials are added in split order -> the result does not depend on which
+// block that is).  The ticket returns to 0 for the next launch.
+__device__ __forceinline__ bool last_block_of_sample(int* __restrict__ tickets, int n, int nblocks) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(tickets + n, 1);
+    s_last = (t == nblocks - 1);
+    if (s_last) tickets[n] = 0;
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
 }
 
 __global__ void colsum_kernel(const bf16* __restrict__ dy, float* __restrict__ out, long long npix, int c, int c_out) {
@@ -520,7 +586,7 @@ __device__ __forceinline__ void norm_finalize_body(int n, const float* __restric
     // sample mean
     double s = 0.0;
     for (int ch = threadIdx.x; ch < c; ch += blockDim.x)
-      s += cnt * (double)shift[(long long)n * c + ch] + ssum[ch * 2];
+      s += cnt * (double)__ldcg(shift + (long long)n * c + ch) + ssum[ch * 2];
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0) sh[0][threadIdx.x >> 5] = s;
     __syncthreads();
@@ -533,7 +599,7 @@ __device__ __forceinline__ void norm_finalize_body(int n, const float* __restric
     const double mu = tot[0];
     double ss = 0.0;
     for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-      const double d = mu - (double)shift[(long long)n * c + ch];
+      const double d = mu - (double)__ldcg(shift + (long long)n * c + ch);
       const double s1 = ssum[ch * 2], s2 = ssum[ch * 2 + 1];
       ss += s2 - 2.0 * d * s1 + cnt * d * d;
     }
@@ -563,7 +629,7 @@ __device__ __forceinline__ void norm_finalize_body(int n, const float* __restric
       const double m1 = a1 / cnt;
       double var = a2 / cnt - m1 * m1;  // biased (F.batch_norm / InstanceNorm2d)
       if (var < 0.0) var = 0.0;
-      const float mu = (float)((double)shift[i] + m1);
+      const float mu = (float)((double)__ldcg(shift + i) + m1);
       const float ri = (float)(1.0 / sqrt(var + (double)eps));
       float wv = 1.f, bv = 0.f;
       if (mode == MUNIT_NORM_ADAIN) {
@@ -585,6 +651,21 @@ __global__ void norm_finalize_kernel(const float* __restrict__ stats, int splits
   pdl_wait();
   pdl_trigger();
   norm_finalize_body(blockIdx.x, stats, splits, shift, mode, p_w, p_b, ldw, eps, mean, rinv, a, b, hw, c);
+}
+
+// Statistics + finalize in ONE launch (last block of each sample finalizes; see last_block_of_sample).
+template <bool H>
+__global__ void norm_stats_finalize_kernel(const bf16* __restrict__ y, float* __restrict__ stats,
+                                           float* __restrict__ shift, int* __restrict__ tickets, int mode,
+                                           const float* __restrict__ p_w, const float* __restrict__ p_b, long long ldw,
+                                           float eps, float* __restrict__ mean, float* __restrict__ rinv,
+                                           float* __restrict__ a, float* __restrict__ b, int hw, int c) {
+  pdl_wait();
+  pdl_trigger();
+  const Blk blk = launch_blk();
+  norm_stats_body<H>(blk, y, stats, shift, hw, c);
+  if (!last_block_of_sample(tickets, blk.by, blk.nbx)) return;
+  norm_finalize_body(blk.by, stats, blk.nbx, shift, mode, p_w, p_b, ldw, eps, mean, rinv, a, b, hw, c);
 }
 
 // LayerNorm finalize from channel-reduced, unshifted partials [N][splits][2] (convolution epilogue statistics):
@@ -629,11 +710,35 @@ __global__ void norm_finalize_ln_total_kernel(const float* __restrict__ part, in
 
 // Block = CG channel groups x R rows (256 threads), grid = (pixel splits, N): a thread keeps its (n, channel
 // group) coefficients in registers and walks pixels, so the per-(n,c) vectors are read once per thread.
+// Slow path of the forward apply, kept out of line so that the hot loop stays small: a pixel within `out_pad` of an
+// edge is written to its interior position(s) AND to the mirrored halo cells (nn.ReflectionPad2d of the consumer).
+template <int UP>
+__device__ __noinline__ void store_border(bf16* __restrict__ obase, uint4 packed, int yy, int x, int h, int w, int c,
+                                          int out_pad) {
+  const int ho = h * UP, wo = w * UP, wop = wo + 2 * out_pad;
+#pragma unroll
+  for (int uy = 0; uy < UP; ++uy) {
+    int prow[3];
+    const int nr = pad_positions(yy * UP + uy, ho, out_pad, prow);
+#pragma unroll
+    for (int ux = 0; ux < UP; ++ux) {
+      int pcol[3];
+      const int nc = pad_positions(x * UP + ux, wo, out_pad, pcol);
+      for (int i = 0; i < nr; ++i)
+        for (int q = 0; q < nc; ++q) *reinterpret_cast<uint4*>(obase + (prow[i] * wop + pcol[q]) * c) = packed;
+    }
+  }
+}
+
 template <int UP, bool H>
 __device__ __forceinline__ void norm_apply_body(Blk blk, const bf16* __restrict__ y, const float* __restrict__ a,
                                                 const float* __restrict__ b, int relu, const bf16* __restrict__ res,
                                                 int res_pad, bf16* __restrict__ out, int out_pad, int n, int h, int w,
-                                                int c) {
+                                                int c, int lw) {
+#ifndef MB_APPLY_U1
+#define MB_APPLY_U1 2  // 2 beats 4 and 8 (more co-resident blocks; tools/bench_norm.py, profiles/r2_norm.md)
+#endif
+  constexpr int U = UP == 1 ? MB_APPLY_U1 : 2;  // pixels whose loads are in flight per thread
   const int cgs = c / 8;
   const int rows = blockDim.x / cgs;
   const int g = threadIdx.x % cgs, r = threadIdx.x / cgs;
@@ -642,41 +747,52 @@ __device__ __forceinline__ void norm_apply_body(Blk blk, const bf16* __restrict_
   const int hw = h * w;
   const int per = (hw + blk.nbx - 1) / blk.nbx;
   const int p0 = blk.bx * per, p1 = min(hw, p0 + per);
-  const int ho = h * UP, wo = w * UP;
-  const int hop = ho + 2 * out_pad, wop = wo + 2 * out_pad;
+  const int wop = w * UP + 2 * out_pad;
+  const int wrp = w + 2 * res_pad;
   const F8 fa = loadf8(a + (long long)bb * c + g * 8), fb = loadf8(b + (long long)bb * c + g * 8);
-#pragma unroll 2
-  for (int pix = p0 + r; pix < p1; pix += rows) {
-    const int yy = pix / w, x = pix - yy * w;
-    F8 v = load8y<H>(y + ((long long)bb * hw + pix) * c + g * 8);
+  const bf16* ybase = y + (long long)bb * hw * c + g * 8;
+  const bf16* rbase = res ? res + ((long long)bb * (h + 2 * res_pad) * wrp + (long long)res_pad * wrp + res_pad) * c + g * 8 : nullptr;
+  bf16* obase = out + (long long)bb * (h * UP + 2 * out_pad) * wop * c + g * 8;
+  for (int pb = p0 + r; pb < p1; pb += rows * U) {
+    uint4 raw[U], rr[U];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float o = fmaf(v.v[e], fa.v[e], fb.v[e]);
-      if (relu) o = fmaxf(o, 0.f);
-      v.v[e] = o;
-    }
-    if (res) {
-      const F8 rr = load8(res + (((long long)bb * (h + 2 * res_pad) + yy + res_pad) * (w + 2 * res_pad) + x + res_pad) * c + g * 8);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v.v[e] += rr.v[e];
-    }
-    uint4 packed;
-    {
-      __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&packed);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) hh[e] = __floats2bfloat162_rn(v.v[2 * e], v.v[2 * e + 1]);
+    for (int u = 0; u < U; ++u) {
+      const int pix = min(pb + u * rows, p1 - 1);  // tail: harmless duplicate loads, masked below
+      raw[u] = *reinterpret_cast<const uint4*>(ybase + pix * c);
+      if (res) {
+        int yy, x;
+        pix_coords(pix, w, lw, yy, x);
+        rr[u] = *reinterpret_cast<const uint4*>(rbase + (yy * wrp + x) * c);
+      }
     }
 #pragma unroll
-    for (int uy = 0; uy < UP; ++uy) {
-      int prow[3];
-      const int nr = pad_positions(yy * UP + uy, ho, out_pad, prow);
+    for (int u = 0; u < U; ++u) {
+      const int pix = pb + u * rows;
+      if (pix < p1) {
+        F8 v = unpack8y<H>(raw[u]);
 #pragma unroll
-      for (int ux = 0; ux < UP; ++ux) {
-        int pcol[3];
-        const int nc = pad_positions(x * UP + ux, wo, out_pad, pcol);
-        for (int i = 0; i < nr; ++i)
-          for (int q = 0; q < nc; ++q)
-            *reinterpret_cast<uint4*>(out + (((long long)bb * hop + prow[i]) * wop + pcol[q]) * c + g * 8) = packed;
+        for (int e = 0; e < 8; ++e) {
+          float o = fmaf(v.v[e], fa.v[e], fb.v[e]);
+          if (relu) o = fmaxf(o, 0.f);
+          v.v[e] = o;
+        }
+        if (res) {
+          const F8 q = unpack8(rr[u]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v.v[e] += q.v[e];
+        }
+        const uint4 packed = pack8(v);
+        int yy, x;
+        pix_coords(pix, w, lw, yy, x);
+        if (!is_border<UP>(yy, x, h, w, out_pad)) {
+          bf16* o0 = obase + ((yy * UP + out_pad) * wop + x * UP + out_pad) * c;
+#pragma unroll
+          for (int uy = 0; uy < UP; ++uy)
+#pragma unroll
+            for (int ux = 0; ux < UP; ++ux) *reinterpret_cast<uint4*>(o0 + (uy * wop + ux) * c) = packed;
+        } else {
+          store_border<UP>(obase, packed, yy, x, h, w, c, out_pad);
+        }
       }
     }
   }
@@ -684,10 +800,10 @@ __device__ __forceinline__ void norm_apply_body(Blk blk, const bf16* __restrict_
 template <int UP, bool H>
 __global__ void norm_apply_kernel(const bf16* __restrict__ y, const float* __restrict__ a, const float* __restrict__ b,
                                   int relu, const bf16* __restrict__ res, int res_pad, bf16* __restrict__ out,
-                                  int out_pad, int n, int h, int w, int c) {
+                                  int out_pad, int n, int h, int w, int c, int lw) {
   pdl_wait();
   pdl_trigger();
-  norm_apply_body<UP, H>(launch_blk(), y, a, b, relu, res, res_pad, out, out_pad, n, h, w, c);
+  norm_apply_body<UP, H>(launch_blk(), y, a, b, relu, res, res_pad, out, out_pad, n, h, w, c, lw);
 }
 
 // gradient w.r.t. the unpadded, un-upsampled pixel: sum of g_out over every position that copied it.
@@ -746,12 +862,34 @@ __device__ __forceinline__ void fold_load(FoldRaw<UP>& o, const bf16* __restrict
 #pragma unroll
     for (int ux = 0; ux < UP; ++ux)
       o.v[uy * UP + ux] =
-          *reinterpret_cast<const uint4*>(base + ((long long)(yy * UP + uy + pad) * wop + x * UP + ux + pad) * c);
+          *reinterpret_cast<const uint4*>(base + ((yy * UP + uy + pad) * wop + x * UP + ux + pad) * c);
+}
+// Slow path of the fold, out of line: adds the mirrored halo copies of a border pixel to acc.
+template <int UP>
+__device__ __noinline__ void fold_border(F8& acc, const bf16* __restrict__ base, int yy, int x, int h, int w, int c,
+                                         int pad) {
+  const int ho = h * UP, wo = w * UP, wop = wo + 2 * pad;
+#pragma unroll
+  for (int uy = 0; uy < UP; ++uy) {
+    int rows[3];
+    const int nr = pad_positions(yy * UP + uy, ho, pad, rows);
+#pragma unroll
+    for (int ux = 0; ux < UP; ++ux) {
+      int cols[3];
+      const int nc = pad_positions(x * UP + ux, wo, pad, cols);
+      for (int r = 0; r < nr; ++r)
+        for (int q = 0; q < nc; ++q) {
+          if (r == 0 && q == 0) continue;  // the interior copy is already in acc
+          const F8 t = load8(base + (rows[r] * wop + cols[q]) * c);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc.v[e] += t.v[e];
+        }
+    }
+  }
 }
 template <int UP>
 __device__ __forceinline__ F8 fold_finish(const FoldRaw<UP>& o, const bf16* __restrict__ base, int yy, int x, int h,
                                           int w, int c, int pad) {
-  const int ho = h * UP, wo = w * UP, wop = wo + 2 * pad;
   F8 acc = unpack8(o.v[0]);
 #pragma unroll
   for (int i = 1; i < UP * UP; ++i) {
@@ -759,33 +897,19 @@ __device__ __forceinline__ F8 fold_finish(const FoldRaw<UP>& o, const bf16* __re
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc.v[e] += t.v[e];
   }
-  const int r0 = yy * UP, c0 = x * UP;
-  const bool border = pad > 0 && (r0 <= pad || c0 <= pad || r0 + UP - 1 >= ho - 1 - pad || c0 + UP - 1 >= wo - 1 - pad);
-  if (border) {
-#pragma unroll
-    for (int uy = 0; uy < UP; ++uy) {
-      int rows[3];
-      const int nr = pad_positions(r0 + uy, ho, pad, rows);
-#pragma unroll
-      for (int ux = 0; ux < UP; ++ux) {
-        int cols[3];
-        const int nc = pad_positions(c0 + ux, wo, pad, cols);
-        for (int r = 0; r < nr; ++r)
-          for (int q = 0; q < nc; ++q) {
-            if (r == 0 && q == 0) continue;  // the interior copy is already in acc
-            const F8 t = load8(base + ((long long)rows[r] * wop + cols[q]) * c);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc.v[e] += t.v[e];
-          }
-      }
-    }
-  }
+  if (is_border<UP>(yy, x, h, w, pad)) fold_border<UP>(acc, base, yy, x, h, w, c, pad);
   return acc;
 }
 // pixels a thread keeps in flight per batch
 template <int UP>
 struct FoldBatch {
-  static constexpr int U = UP == 1 ? 8 : 2;
+#ifndef MB_BWD_U1
+#define MB_BWD_U1 4
+#endif
+#ifndef MB_BWD_OCC
+#define MB_BWD_OCC 2
+#endif
+  static constexpr int U = UP == 1 ? MB_BWD_U1 : 2;
 };
 
 // sums = {sum dz, sum dz*(x - mean)}; the finalize kernels multiply the second by rinv (keeps this loop at 3
@@ -795,7 +919,7 @@ __device__ __forceinline__ void norm_bwd_reduce_body(Blk blk, const bf16* __rest
                                                      const bf16* __restrict__ y, const float* __restrict__ a,
                                                      const float* __restrict__ b, int relu,
                                                      const float* __restrict__ mean, float* __restrict__ sums, int h,
-                                                     int w, int c) {
+                                                     int w, int c, int lw) {
   constexpr int U = FoldBatch<UP>::U;
   const int hw = h * w;
   const int cgs = c / 8;
@@ -819,15 +943,17 @@ __device__ __forceinline__ void norm_bwd_reduce_body(Blk blk, const bf16* __rest
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int pix = min(pb + u * rows, p1 - 1);  // tail: harmless duplicate loads, masked below
-        const int yy = pix / w, x = pix - yy * w;
+        int yy, x;
+        pix_coords(pix, w, lw, yy, x);
         fold_load<UP>(gr[u], gbase, yy, x, wop, c, out_pad);
-        yv[u] = *reinterpret_cast<const uint4*>(ybase + (long long)pix * c);
+        yv[u] = *reinterpret_cast<const uint4*>(ybase + pix * c);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int pix = pb + u * rows;
         if (pix < p1) {
-          const int yy = pix / w, x = pix - yy * w;
+          int yy, x;
+          pix_coords(pix, w, lw, yy, x);
           const F8 g = fold_finish<UP>(gr[u], gbase, yy, x, h, w, c, out_pad);
           const F8 xv = unpack8y<H>(yv[u]);
 #pragma unroll
@@ -843,14 +969,14 @@ __device__ __forceinline__ void norm_bwd_reduce_body(Blk blk, const bf16* __rest
   reduce_nc_tail(blk, s0, s1, sums, c);
 }
 template <int UP, bool H>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, MB_BWD_OCC)
 norm_bwd_reduce_kernel(const bf16* __restrict__ g_out, int out_pad, const bf16* __restrict__ y,
                                        const float* __restrict__ a, const float* __restrict__ b, int relu,
                                        const float* __restrict__ mean, const float* __restrict__ rinv,
-                                       float* __restrict__ sums, int h, int w, int c) {
+                                       float* __restrict__ sums, int h, int w, int c, int lw) {
   pdl_wait();
   pdl_trigger();
-  norm_bwd_reduce_body<UP, H>(launch_blk(), g_out, out_pad, y, a, b, relu, mean, sums, h, w, c);
+  norm_bwd_reduce_body<UP, H>(launch_blk(), g_out, out_pad, y, a, b, relu, mean, sums, h, w, c, lw);
 }
 
 // one block per sample
@@ -932,6 +1058,37 @@ __global__ void norm_bwd_finalize_kernel(const float* __restrict__ sums, int spl
   norm_bwd_finalize_body(blockIdx.x, sums, splits, mode, p_w, ldw, rinv, eps, ca, cb, cc, g_w, g_b, ldg, hw, c);
 }
 
+// Backward reduce + finalize in ONE launch (last block of each sample finalizes).
+template <int UP, bool H>
+__global__ void __launch_bounds__(256, MB_BWD_OCC)
+norm_bwd_reduce_finalize_kernel(const bf16* __restrict__ g_out, int out_pad, const bf16* __restrict__ y,
+                                const float* __restrict__ a, const float* __restrict__ b, int relu,
+                                const float* __restrict__ mean, const float* __restrict__ rinv, float* __restrict__ sums,
+                                int* __restrict__ tickets, int mode, const float* __restrict__ p_w, long long ldw,
+                                float eps, float* __restrict__ ca, float* __restrict__ cb, float* __restrict__ cc,
+                                float* __restrict__ g_w, float* __restrict__ g_b, long long ldg, int h, int w, int c,
+                                int lw) {
+  pdl_wait();
+  pdl_trigger();
+  const Blk blk = launch_blk();
+  norm_bwd_reduce_body<UP, H>(blk, g_out, out_pad, y, a, b, relu, mean, sums, h, w, c, lw);
+  if (!last_block_of_sample(tickets, blk.by, blk.nbx)) return;
+  norm_bwd_finalize_body(blk.by, sums, blk.nbx, mode, p_w, ldw, rinv, eps, ca, cb, cc, g_w, g_b, ldg, h * w, c);
+}
+
+// Slow path of the residual-gradient store, out of line: zero the halo cells that mirror border pixel (yy, x) (the halo
+// of g_res carries no gradient; every halo cell is zeroed by the one border pixel that mirrors onto it, so the caller
+// need not clear the buffer first).
+__device__ __noinline__ void zero_res_halo(bf16* __restrict__ rbase, int yy, int x, int h, int w, int c, int res_pad) {
+  const int wrp = w + 2 * res_pad;
+  int prow[3], pcol[3];
+  const int nr = pad_positions(yy, h, res_pad, prow);
+  const int nc = pad_positions(x, w, res_pad, pcol);
+  for (int i = 0; i < nr; ++i)
+    for (int q2 = 0; q2 < nc; ++q2)
+      if (i | q2) *reinterpret_cast<uint4*>(rbase + (prow[i] * wrp + pcol[q2]) * c) = make_uint4(0u, 0u, 0u, 0u);
+}
+
 template <int UP, bool H>
 __device__ __forceinline__ void norm_bwd_apply_body(Blk blk, const bf16* __restrict__ g_out, int out_pad,
                                                     const bf16* __restrict__ y, const float* __restrict__ a,
@@ -939,7 +1096,8 @@ __device__ __forceinline__ void norm_bwd_apply_body(Blk blk, const bf16* __restr
                                                     const float* __restrict__ mean, const float* __restrict__ rinv,
                                                     const float* __restrict__ ca, const float* __restrict__ cb,
                                                     const float* __restrict__ cc, bf16* __restrict__ dy,
-                                                    bf16* __restrict__ g_res, int res_pad, int n, int h, int w, int c) {
+                                                    bf16* __restrict__ g_res, int res_pad, int n, int h, int w, int c,
+                                                    int lw) {
   const int cgs = c / 8;
   const int rows = blockDim.x / cgs;
   const int g = threadIdx.x % cgs, r = threadIdx.x / cgs;
@@ -961,23 +1119,28 @@ __device__ __forceinline__ void norm_bwd_apply_body(Blk blk, const bf16* __restr
   }
   constexpr int U = FoldBatch<UP>::U;
   const int wop = w * UP + 2 * out_pad;
+  const int wrp = w + 2 * res_pad;
   const bf16* gbase = g_out + (long long)bb * (h * UP + 2 * out_pad) * wop * c + g * 8;
   const bf16* ybase = y + (long long)bb * hw * c + g * 8;
+  bf16* dbase = dy + (long long)bb * hw * c + g * 8;
+  bf16* rbase = g_res ? g_res + (long long)bb * (h + 2 * res_pad) * wrp * c + g * 8 : nullptr;
   for (int pb = p0 + r; pb < p1; pb += rows * U) {
     FoldRaw<UP> graw[U];
     uint4 yv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int pix = min(pb + u * rows, p1 - 1);  // tail: harmless duplicate loads, masked below
-      const int yy = pix / w, x = pix - yy * w;
+      int yy, x;
+      pix_coords(pix, w, lw, yy, x);
       fold_load<UP>(graw[u], gbase, yy, x, wop, c, out_pad);
-      yv[u] = *reinterpret_cast<const uint4*>(ybase + (long long)pix * c);
+      yv[u] = *reinterpret_cast<const uint4*>(ybase + pix * c);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int pix = pb + u * rows;
       if (pix < p1) {
-        const int yy = pix / w, x = pix - yy * w;
+        int yy, x;
+        pix_coords(pix, w, lw, yy, x);
         const F8 gr = fold_finish<UP>(graw[u], gbase, yy, x, h, w, c, out_pad);
         const F8 xv = unpack8y<H>(yv[u]);
         F8 d;
@@ -987,38 +1150,27 @@ __device__ __forceinline__ void norm_bwd_apply_body(Blk blk, const bf16* __restr
           if (relu && fmaf(xv.v[e], fa.v[e], fb.v[e]) <= 0.f) dz = 0.f;
           d.v[e] = fmaf(fca.v[e], dz, fmaf(k1.v[e], xv.v[e], k0.v[e]));
         }
-        store8(dy + ((long long)bb * hw + pix) * c + g * 8, d);
-        if (g_res) {
-          const int hrp = h + 2 * res_pad, wrp = w + 2 * res_pad;
-          store8(g_res + (((long long)bb * hrp + yy + res_pad) * wrp + x + res_pad) * c + g * 8, gr);
-          // the halo of g_res carries no gradient: every halo cell is zeroed by the one border pixel that mirrors
-          // onto it, so the caller need not clear the buffer first
-          if (res_pad > 0 && (yy <= res_pad || x <= res_pad || yy >= h - 1 - res_pad || x >= w - 1 - res_pad)) {
-            int prow[3], pcol[3];
-            const int nr = pad_positions(yy, h, res_pad, prow);
-            const int nc = pad_positions(x, w, res_pad, pcol);
-            for (int i = 0; i < nr; ++i)
-              for (int q2 = 0; q2 < nc; ++q2)
-                if (i | q2)
-                  *reinterpret_cast<uint4*>(g_res + (((long long)bb * hrp + prow[i]) * wrp + pcol[q2]) * c + g * 8) =
-                      make_uint4(0u, 0u, 0u, 0u);
-          }
+        store8(dbase + pix * c, d);
+        if (rbase) {
+          store8(rbase + ((yy + res_pad) * wrp + x + res_pad) * c, gr);
+          if (res_pad > 0 && (yy <= res_pad || x <= res_pad || yy >= h - 1 - res_pad || x >= w - 1 - res_pad))
+            zero_res_halo(rbase, yy, x, h, w, c, res_pad);
         }
       }
     }
   }
 }
 template <int UP, bool H>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, MB_BWD_OCC)
 norm_bwd_apply_kernel(const bf16* __restrict__ g_out, int out_pad, const bf16* __restrict__ y,
                                       const float* __restrict__ a, const float* __restrict__ b, int relu,
                                       const float* __restrict__ mean, const float* __restrict__ rinv,
                                       const float* __restrict__ ca, const float* __restrict__ cb,
                                       const float* __restrict__ cc, bf16* __restrict__ dy, bf16* __restrict__ g_res,
-                                      int res_pad, int n, int h, int w, int c) {
+                                      int res_pad, int n, int h, int w, int c, int lw) {
   pdl_wait();
   pdl_trigger();
-  norm_bwd_apply_body<UP, H>(launch_blk(), g_out, out_pad, y, a, b, relu, mean, rinv, ca, cb, cc, dy, g_res, res_pad, n, h, w, c);
+  norm_bwd_apply_body<UP, H>(launch_blk(), g_out, out_pad, y, a, b, relu, mean, rinv, ca, cb, cc, dy, g_res, res_pad, n, h, w, c, lw);
 }
 
 __global__ void act_bwd_kernel(const bf16* __restrict__ g_out, const bf16* __restrict__ out_act, int pad, int act,
@@ -1682,6 +1834,26 @@ int munit_norm_stats(const void* y, int y_f16, float* stats, float* shift, int n
   return MUNIT_OK;
 }
 
+int munit_norm_stats_finalize(const void* y, int y_f16, float* stats, float* shift, int32_t* tickets, int mode,
+                              const float* p_w, const float* p_b, int64_t ldw, float eps, float* mean, float* rinv,
+                              float* a, float* b, int n, int hw, int c, void* stream) {
+  if (c % 8 || c / 8 > 256 || 256 % (c / 8)) return mb_fail(MUNIT_ERR_ARG, "norm_stats_finalize: channels %d", c);
+  if (mode != MUNIT_NORM_IN && (!p_w || !p_b)) return mb_fail(MUNIT_ERR_ARG, "norm_stats_finalize: missing affine params");
+  if (!tickets) return mb_fail(MUNIT_ERR_ARG, "norm_stats_finalize: tickets");
+  const int rows = 256 / (c / 8);
+  size_t sm = sizeof(float) * 2 * rows * c;
+  if (sm < sizeof(double) * 2 * c) sm = sizeof(double) * 2 * c;
+  dim3 grid(reduce_splits(hw, c), n);
+  if (y_f16)
+    mb_launch(norm_stats_finalize_kernel<true>, dim3(grid), dim3(256), sm, ST(stream), CBF(y), stats, shift, tickets, mode, p_w,
+              p_b, (long long)ldw, eps, mean, rinv, a, b, hw, c);
+  else
+    mb_launch(norm_stats_finalize_kernel<false>, dim3(grid), dim3(256), sm, ST(stream), CBF(y), stats, shift, tickets, mode, p_w,
+              p_b, (long long)ldw, eps, mean, rinv, a, b, hw, c);
+  MB_CHECK_LAUNCH("norm_stats_finalize");
+  return MUNIT_OK;
+}
+
 int munit_norm_finalize(const float* stats, const float* shift, int mode, const float* p_w, const float* p_b,
                         int64_t ldw, float eps, float* mean, float* rinv, float* a, float* b, int n, int hw, int c,
                         void* stream) {
@@ -1727,7 +1899,7 @@ int munit_norm_apply(const void* y, int y_f16, const float* a, const float* b, i
   if (upsample != 1 && upsample != 2) return mb_fail(MUNIT_ERR_ARG, "norm_apply: upsample must be 1 or 2");
 #define MB_APPLY(UP_, H_)                                                                                          \
   mb_launch(norm_apply_kernel<UP_, H_>, dim3(grid), dim3(256), 0, ST(stream), CBF(y), a, b, relu, CBF(residual), \
-            res_pad, BF(out_act), out_pad, n, h, w, c)
+            res_pad, BF(out_act), out_pad, n, h, w, c, log2_or_neg(w))
   if (upsample == 2) {
     if (y_f16) MB_APPLY(2, true); else MB_APPLY(2, false);
   } else {
@@ -1747,7 +1919,7 @@ int munit_norm_bwd_reduce(const void* g_out, int out_pad, int upsample, const vo
   const size_t sm = sizeof(float) * 2 * rows * c;
 #define MB_BRED(UP_, H_)                                                                                           \
   mb_launch(norm_bwd_reduce_kernel<UP_, H_>, dim3(grid), dim3(256), sm, ST(stream), CBF(g_out), out_pad, CBF(y), a, b, \
-            relu, mean, rinv, sums, h, w, c)
+            relu, mean, rinv, sums, h, w, c, log2_or_neg(w))
   if (upsample == 2) {
     if (y_f16) MB_BRED(2, true); else MB_BRED(2, false);
   } else {
@@ -1755,6 +1927,32 @@ int munit_norm_bwd_reduce(const void* g_out, int out_pad, int upsample, const vo
   }
 #undef MB_BRED
   MB_CHECK_LAUNCH("norm_bwd_reduce");
+  return MUNIT_OK;
+}
+
+int munit_norm_bwd_reduce_finalize(const void* g_out, int out_pad, int upsample, const void* y, int y_f16, const float* a,
+                                   const float* b, int relu, const float* mean, const float* rinv, float* sums,
+                                   int32_t* tickets, int mode, const float* p_w, int64_t ldw, float eps, float* ca,
+                                   float* cb, float* cc, float* g_w, float* g_b, int64_t ldg, int n, int h, int w, int c,
+                                   void* stream) {
+  if (c % 8 || c / 8 > 256 || 256 % (c / 8)) return mb_fail(MUNIT_ERR_ARG, "norm_bwd_reduce_finalize: channels %d", c);
+  if (upsample != 1 && upsample != 2) return mb_fail(MUNIT_ERR_ARG, "norm_bwd_reduce_finalize: upsample must be 1 or 2");
+  if (!tickets) return mb_fail(MUNIT_ERR_ARG, "norm_bwd_reduce_finalize: tickets");
+  const int rows = 256 / (c / 8);
+  size_t sm = sizeof(float) * 2 * rows * c;
+  if (sm < sizeof(double) * 2 * c) sm = sizeof(double) * 2 * c;
+  dim3 grid(reduce_splits(h * w, c), n);
+#define MB_BRF(UP_, H_)                                                                                              \
+  mb_launch(norm_bwd_reduce_finalize_kernel<UP_, H_>, dim3(grid), dim3(256), sm, ST(stream), CBF(g_out), out_pad, CBF(y), \
+            a, b, relu, mean, rinv, sums, tickets, mode, p_w, (long long)ldw, eps, ca, cb, cc, g_w, g_b, (long long)ldg, h, \
+            w, c, log2_or_neg(w))
+  if (upsample == 2) {
+    if (y_f16) MB_BRF(2, true); else MB_BRF(2, false);
+  } else {
+    if (y_f16) MB_BRF(1, true); else MB_BRF(1, false);
+  }
+#undef MB_BRF
+  MB_CHECK_LAUNCH("norm_bwd_reduce_finalize");
   return MUNIT_OK;
 }
 
@@ -1782,7 +1980,7 @@ int munit_norm_bwd_apply(const void* g_out, int out_pad, int upsample, const voi
   dim3 grid(apply_splits(h * w, c, n), n);
 #define MB_BAPP(UP_, H_)                                                                                          \
   mb_launch(norm_bwd_apply_kernel<UP_, H_>, dim3(grid), dim3(256), 0, ST(stream), CBF(g_out), out_pad, CBF(y), a, b, \
-            relu, mean, rinv, ca, cb, cc, BF(dy), BF(g_res), res_pad, n, h, w, c)
+            relu, mean, rinv, ca, cb, cc, BF(dy), BF(g_res), res_pad, n, h, w, c, log2_or_neg(w))
   if (upsample == 2) {
     if (y_f16) MB_BAPP(2, true); else MB_BAPP(2, false);
   } else {

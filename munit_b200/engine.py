@@ -69,8 +69,6 @@ class StepRunner:
 
     # ------------------------------------------------------------------ pieces of a step
     def _seg_dis(self):
-        for opt in (self.t.dis_opt, self.t.gen_opt):
-            opt.upload_hyper()
         self.t._dis_backward(self.x_a, self.x_b, self.cfg, self.s_a, self.s_b)
 
     def _seg_mid(self):
@@ -155,8 +153,9 @@ class StepRunner:
     def _prepare_host_state(self):
         t = self.t
         t.iterations = self.iter
-        for opt in (t.dis_opt, t.gen_opt):
-            opt.stage_hyper(opt.step_count + 1)
+        if not torch.cuda.is_current_stream_capturing():
+            for opt in (t.dis_opt, t.gen_opt):  # H2D of {lr, bias corrections} ahead of the replay, race-free ring
+                opt.upload_hyper(opt.step_count + 1)
 
     def _advance(self):
         self.iter += 1

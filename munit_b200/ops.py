@@ -552,12 +552,14 @@ class AdainSplitFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         n, total = ctx.shape
+        ref = next((g for g in grads if g is not None), None)
+        if ref is None:
+            return None, None
         parts = []
         for i, g in enumerate(grads):
             c = ctx.sizes[i // 2]
-            parts.append(g if g is not None else torch.zeros(n, c, dtype=torch.float32, device=grads[0].device if grads[0] is not None else None))
+            parts.append(g if g is not None else torch.zeros(n, c, dtype=ref.dtype, device=ref.device))
         if ctx.used < total:
-            ref = next(g for g in grads if g is not None)
             parts.append(torch.zeros(n, total - ctx.used, dtype=ref.dtype, device=ref.device))
         return torch.cat(parts, 1), None
 

@@ -43,9 +43,14 @@ class FlatAdam(Optimizer):
         self._arena_built = False
         self.step_count = 0
         self.grad_scale = 1.0  # 1/world_size under data parallelism (fused into the update)
-        # CUDA-graph mode: {lr, 1-b1^t, 1-b2^t} live in a device array refreshed from pinned host memory
-        self.hyper_host = None
+        # CUDA-graph mode: {lr, 1-b1^t, 1-b2^t} live in a device array.  It is refreshed by an H2D copy that is
+        # enqueued *outside* the captured graph, from a ring of pinned host slots: a slot is rewritten only after the
+        # copy that last read it has completed (event per slot), so un-synchronised replay loops can never pick up the
+        # scalars of a later step (the round-1 design re-used one pinned buffer inside the graph and could).
+        self.hyper_ring = None
         self.hyper_dev = None
+        self._ring_events = []
+        self._ring_pos = 0
 
     # ------------------------------------------------------------------ arena
     def _all_params(self) -> List[torch.nn.Parameter]:
@@ -97,29 +102,45 @@ class FlatAdam(Optimizer):
         self.step_count += 1
         if mode != 0 and self.saved_arena is None:
             self.saved_arena = torch.empty_like(self.p_arena)
+        if self.hyper_dev is not None and not torch.cuda.is_current_stream_capturing():
+            # eager call (trainer.*_opt_step outside a StepRunner replay, after resume, ...): the device scalars must
+            # describe THIS step; inside a capture the runner uploads them before every replay
+            self.upload_hyper(self.step_count)
         K.adam(self.p_arena, self.g_arena, self.m_arena, self.v_arena, self.saved_arena, None, mode, save, g["lr"],
                g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self.step_count, self.grad_scale,
                self.hyper_dev)
         _bump_versions(self._all_params())
 
     # ------------------------------------------------------------------ CUDA-graph support
+    HYPER_RING = 32
+
     def enable_graph_hyper(self):
         """Route lr / bias corrections through device memory so a captured step can be replayed."""
         if not self._arena_built:
             self.build_arena()
         if self.hyper_dev is None:
-            self.hyper_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+            self.hyper_ring = torch.zeros(self.HYPER_RING, 4, dtype=torch.float32).pin_memory()
             self.hyper_dev = torch.zeros(4, dtype=torch.float32, device=self.p_arena.device)
+            self._ring_events = [None] * self.HYPER_RING
+            self.upload_hyper(self.step_count + 1)  # never leave the device scalars at 0 (lr / 0 -> NaN)
 
-    def stage_hyper(self, step: int):
-        """Write the scalars for optimiser step `step` (1-based) into the pinned staging buffer."""
+    def upload_hyper(self, step: int):
+        """Enqueue, on the current stream, the H2D copy of the scalars for optimiser step `step` (1-based).  Must be
+        called outside a graph capture."""
         g = self.param_groups[0]
-        self.hyper_host[0] = g["lr"]
-        self.hyper_host[1] = 1.0 - g["betas"][0] ** step
-        self.hyper_host[2] = 1.0 - g["betas"][1] ** step
-
-    def upload_hyper(self):
-        self.hyper_dev.copy_(self.hyper_host, non_blocking=True)
+        slot = self._ring_pos % self.HYPER_RING
+        self._ring_pos += 1
+        ev = self._ring_events[slot]
+        if ev is not None:
+            ev.synchronize()  # the copy that last read this slot (HYPER_RING uploads ago) has finished
+        row = self.hyper_ring[slot]
+        row[0] = g["lr"]
+        row[1] = 1.0 - g["betas"][0] ** step
+        row[2] = 1.0 - g["betas"][1] ** step
+        self.hyper_dev.copy_(row, non_blocking=True)
+        ev = ev or torch.cuda.Event()
+        ev.record()
+        self._ring_events[slot] = ev
 
     @torch.no_grad()
     def step(self, closure=None):

@@ -1,14 +1,14 @@
-mkdir -p gpurun_out/r2b
+mkdir -p gpurun_out/r2g
 cd /root/repo
-for f in tests/test_simt_gpu.py tests/test_networks_gpu.py tests/test_conv_gpu.py tests/test_heads_gpu.py tests/test_trainer_gpu.py tests/test_engine_gpu.py tests/test_train_script_gpu.py; do
-  b=$(basename $f .py)
-  timeout 900 python -m pytest $f -m gpu -q -s --no-header -p no:cacheprovider > gpurun_out/r2b/$b.log 2>&1
-  echo "$b exit=$?"; tail -3 gpurun_out/r2b/$b.log
-done
-grep -h "^block" gpurun_out/r2b/test_networks_gpu.log
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2b/bench.json 2> gpurun_out/r2b/bench.err; echo "bench rc=$?"
+echo "== default"; python tools/bench_norm.py 2>&1 | tail -8 | cut -c1-110
+echo "== apply U2"; MUNIT_LIB=/root/repo/munit_b200/csrc/variants/lib_au2.so python tools/bench_norm.py 2>&1 | tail -8 | cut -c1-60
+echo "== apply U8"; MUNIT_LIB=/root/repo/munit_b200/csrc/variants/lib_au8.so python tools/bench_norm.py 2>&1 | tail -8 | cut -c1-60
+for lb in 1 0 1 0; do
+MUNIT_NORM_LASTBLOCK=$lb python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/r2g/bench_lb$lb.json 2> gpurun_out/r2g/bench.err; echo "lastblock=$lb rc=$?"
 python - <<PY
 import json
-d=json.loads(open("gpurun_out/r2b/bench.json").read().strip().splitlines()[-1])
-print(d["value"], d["ms_per_step"], d["e2e"]["last_losses"], d["roofline"]["achieved"], d["roofline"]["kernel_ms_per_step"])
+d=json.loads(open("gpurun_out/r2g/bench_lb$lb.json").read().strip().splitlines()[-1])
+print("value", d["value"], "ms", d["ms_per_step"], d["gpu_launches"]/10)
+h=d["roofline_hbm"]; print("hbm", round(h["achieved"]), round(h["frac"],3), round(h["kernel_ms_per_step"],2), {k: round(v["ms"],2) for k,v in h["per_kernel"].items()})
 PY
+done

@@ -55,3 +55,46 @@ def test_graph_replay_matches_eager(optimizer):
         lr, n_steps = 1e-4, len(le) + 2
         assert float((gg - ge).abs().max()) <= 2.5 * lr * n_steps, mode
         assert float((dg - de).abs().max()) <= 2.5 * lr * n_steps, mode
+
+
+def test_adam_scalars_in_unsynchronised_replays():
+    """ADVICE r1 (engine.py:155): the per-step Adam scalars {lr, 1-b1^t, 1-b2^t} reach the captured update through
+    device memory.  The host runs far ahead of the device here (a spin kernel holds the stream while 12 replays are
+    queued, more than nothing ever synchronises) and every replay must still see the scalars of ITS step: the result
+    has to equal torch.optim.Adam step for step."""
+    from munit_b200.optim import FlatAdam
+
+    torch.manual_seed(0)
+    n, steps = 1 << 14, 12
+    p = torch.nn.Parameter(torch.randn(n, device="cuda"))
+    ref = p.detach().clone().requires_grad_(True)
+    kw = dict(lr=1e-3, betas=(0.5, 0.999), eps=1e-8, weight_decay=1e-4)
+    opt, topt = FlatAdam([p], **kw), torch.optim.Adam([ref], **kw)
+    opt.build_arena()
+    opt.enable_graph_hyper()
+    g = torch.randn(n, device="cuda")
+    p.grad.copy_(g)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    count = opt.step_count
+    with torch.cuda.graph(graph, stream=s):
+        opt.step()
+    opt.step_count = count  # the capture ran no kernel
+    torch.cuda.synchronize()
+    torch.cuda._sleep(int(0.3 * 1.9e9))  # the device stays behind the host for the whole loop
+    for _ in range(steps):
+        opt.upload_hyper(opt.step_count + 1)
+        graph.replay()
+        opt.step_count += 1
+    torch.cuda.synchronize()
+    for _ in range(steps):
+        ref.grad = g.clone()
+        topt.step()
+    assert float((opt.p_arena[:n] - ref.detach()).abs().max()) < 2e-6
+    # and an eager call afterwards (outside any runner) uses fresh scalars too (ADVICE r1, optim.py:100)
+    opt.step()
+    ref.grad = g.clone()
+    topt.step()
+    torch.cuda.synchronize()
+    assert float((opt.p_arena[:n] - ref.detach()).abs().max()) < 2e-6

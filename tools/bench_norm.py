@@ -3,11 +3,13 @@ backward: reduce -> finalize -> apply) on the shapes of the MUNIT generator.  Ea
 into one CUDA graph and the graph replay is timed, so the numbers carry graph-replay launch behaviour rather than
 Python / ctypes launch overhead.  Usage: python tools/bench_norm.py [out.json]"""
 import json
+import os
 import sys
 
 import torch
 
-from munit_b200 import kernels as K
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from munit_b200 import kernels as K  # noqa: E402
 
 R = 20
 
@@ -44,7 +46,7 @@ def main():
               ("ln_up2", "ln", 8, 256, 256, 64, 3, 1, True, False), ("adain_up", "adain", 8, 64, 64, 256, 2, 2, False, True)]
     for name, mode, n, h, w, c, out_pad, up, relu, res_on in shapes:
         g = torch.Generator(device="cuda").manual_seed(0)
-        y = (torch.randn(n, h, w, c, device="cuda", generator=g) * 1.3 + 0.2).to(torch.bfloat16)
+        y = (torch.randn(n, h, w, c, device="cuda", generator=g) * 1.3 + 0.2).to(torch.float16)
         resid = torch.randn(n, h + 2, w + 2, c, device="cuda", generator=g).to(torch.bfloat16) if res_on else None
         p_w = p_b = None
         ldw = 0
@@ -70,16 +72,12 @@ def main():
                       el + gel + (el if res_on else 0))
         r["fwd(3)"] = (graph_time(lambda: K.norm_fwd(y, mode, p_w, p_b, ldw, 1e-5, relu, resid, 1, out_pad, up)),
                        2 * el + gel + (el if res_on else 0))
-        from munit_b200._lib import NORM, lib
-        st = lambda: torch.cuda.current_stream().cuda_stream
-        ptr = lambda t: 0 if t is None else t.data_ptr()
-        sums = torch.empty(n, lib.munit_norm_splits(h * w, c), c, 2, device="cuda")
-        kk = torch.empty(3, n, c, device="cuda")
-        dy = torch.empty_like(y)
-        gres = torch.zeros(n, h + 2, w + 2, c, dtype=torch.bfloat16, device="cuda") if res_on else None
-        r["b_reduce"] = (graph_time(lambda: lib.munit_norm_bwd_reduce(g_out.data_ptr(), out_pad, up, y.data_ptr(), coef[2].data_ptr(), coef[3].data_ptr(), int(relu), coef[0].data_ptr(), coef[1].data_ptr(), sums.data_ptr(), n, h, w, c, st())), el + gel)
-        r["b_final"] = (graph_time(lambda: lib.munit_norm_bwd_finalize(sums.data_ptr(), NORM[mode], ptr(p_w), ldw, coef[1].data_ptr(), 1e-5, kk[0].data_ptr(), kk[1].data_ptr(), kk[2].data_ptr(), ptr(g_w), ptr(g_b), ldg, n, h * w, c, st())), 0)
-        r["b_apply"] = (graph_time(lambda: lib.munit_norm_bwd_apply(g_out.data_ptr(), out_pad, up, y.data_ptr(), coef[2].data_ptr(), coef[3].data_ptr(), int(relu), coef[0].data_ptr(), coef[1].data_ptr(), kk[0].data_ptr(), kk[1].data_ptr(), kk[2].data_ptr(), dy.data_ptr(), ptr(gres), 1, n, h, w, c, st())), 2 * el + gel + (el if res_on else 0))
+        sums = K.norm_bwd_reduce(g_out, out_pad, up, y, coef, relu)
+        kk = K.norm_bwd_finalize(sums, coef, mode, p_w, ldw, g_w, g_b, ldg, h * w)
+        r["b_reduce"] = (graph_time(lambda: K.norm_bwd_reduce(g_out, out_pad, up, y, coef, relu)), el + gel)
+        r["b_final"] = (graph_time(lambda: K.norm_bwd_finalize(sums, coef, mode, p_w, ldw, g_w, g_b, ldg, h * w)), 0)
+        r["b_apply"] = (graph_time(lambda: K.norm_bwd_apply(g_out, out_pad, up, y, coef, relu, kk, res_on, 1)),
+                        2 * el + gel + (el if res_on else 0))
         r["bwd(3)"] = (graph_time(lambda: K.norm_bwd(g_out, out_pad, up, y, coef, relu, mode, p_w, ldw, g_w, g_b, ldg,
                                                      res_on, 1)), 2 * (el + gel) + el + (el if res_on else 0))
         res[name] = {k: {"us": round(v[0], 2), "gbs": round(v[1] / v[0] / 1e3, 1) if v[1] else None} for k, v in r.items()}

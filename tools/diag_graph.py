@@ -52,7 +52,7 @@ def dis_fb():
     l.backward()
 for m in ("global", "thread_local", "relaxed"):
     try_capture("dis fwd+bwd", dis_fb, m)
-try_capture("upload_hyper", lambda: t.dis_opt.upload_hyper())
+try_capture("upload_hyper", lambda: t.dis_opt.upload_hyper(t.dis_opt.step_count + 1))
 try_capture("dis_opt_step", lambda: t.dis_opt_step())
 for m in ("global", "thread_local", "relaxed"):
     try_capture("_seg_dis", r._seg_dis, m)
