@@ -162,6 +162,13 @@ int munit_act_to_nchw(const void* act, float* y, int n, int c, int h, int w, int
 /* NCHW fp32 -> act interior (channels >= C up to CP zeroed); follow with munit_halo_fill. */
 int munit_nchw_to_act(const float* x, void* act, int n, int c, int h, int w, int pad, int cp, void* stream);
 
+/* Tail of the input pipeline on the GPU (utils.py:218-240: RandomCrop -> RandomHorizontalFlip -> ToTensor ->
+ * Normalize(0.5, 0.5)): img = one decoded, resized uint8 HWC image [ih][iw][3] in device memory; out = the ch x cw
+ * crop at (top, left), mirrored when flip != 0, as NCHW fp32 [3][ch][cw] in [-1, 1], bit-identical to the host
+ * transforms. */
+int munit_u8_crop_normalize(const uint8_t* img, int ih, int iw, int top, int left, int flip, float* out, int ch, int cw,
+                            void* stream);
+
 /* In-place reflect halo fill of an act buffer from its interior. */
 int munit_halo_fill(void* act, int n, int h, int w, int c, int pad, void* stream);
 

@@ -71,6 +71,7 @@ _SIGS = {
     "munit_kwexp_to_image_grad": ([_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp], C.c_int),
     "munit_act_to_nchw": ([_vp, _vp, _i, _i, _i, _i, _i, _i, _vp], C.c_int),
     "munit_nchw_to_act": ([_vp, _vp, _i, _i, _i, _i, _i, _i, _vp], C.c_int),
+    "munit_u8_crop_normalize": ([_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp], C.c_int),
     "munit_halo_fill": ([_vp, _i, _i, _i, _i, _i, _vp], C.c_int),
     "munit_norm_splits": ([_i, _i], C.c_int),
     "munit_norm_stats": ([_vp, _i, _vp, _vp, _i, _i, _i, _vp], C.c_int),

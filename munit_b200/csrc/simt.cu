@@ -129,6 +129,27 @@ __global__ void image_to_act_kernel(const float* __restrict__ x, bf16* __restric
   }
 }
 
+// Input pipeline tail on the GPU (reference: transforms.RandomCrop -> RandomHorizontalFlip -> ToTensor ->
+// Normalize((.5,.5,.5),(.5,.5,.5)), utils.py:218-240): one decoded + resized uint8 HWC image -> the cropped (and
+// optionally mirrored) NCHW fp32 sample in [-1, 1].  Same fp32 operations as torch (x / 255, then (x - 0.5) / 0.5,
+// IEEE division), so the result is bit-identical to the host transforms; the host ships 3 B per pixel instead of 12.
+__global__ void u8_crop_normalize_kernel(const uint8_t* __restrict__ img, int ih, int iw, int top, int left, int flip,
+                                         float* __restrict__ out, int ch, int cw) {
+  pdl_wait();
+  pdl_trigger();
+  const int total = ch * cw;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int y = i / cw, x = i - y * cw;
+    const int sx = flip ? (left + cw - 1 - x) : (left + x);
+    const uint8_t* px = img + ((long long)(top + y) * iw + sx) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = __fdiv_rn((float)px[c], 255.f);
+      out[(long long)c * total + i] = __fdiv_rn(v - 0.5f, 0.5f);
+    }
+  }
+}
+
 __global__ void image_to_kwexp_kernel(const float* __restrict__ x, bf16* __restrict__ e, int n, int c, int h, int w,
                                       int pad, int kw, int sx, int wo, int kwp, int cp) {
   pdl_wait();
@@ -1772,6 +1793,15 @@ int munit_image_to_act(const float* x, void* act, int n, int c, int h, int w, in
   const long long total = (long long)n * (h + 2 * pad) * (w + 2 * pad);
   mb_launch(image_to_act_kernel, dim3(grid_for(total)), dim3(256), 0, ST(stream), x, BF(act), n, c, h, w, pad, cp);
   MB_CHECK_LAUNCH("image_to_act");
+  return MUNIT_OK;
+}
+
+int munit_u8_crop_normalize(const uint8_t* img, int ih, int iw, int top, int left, int flip, float* out, int ch, int cw,
+                            void* stream) {
+  if (top < 0 || left < 0 || top + ch > ih || left + cw > iw) return mb_fail(MUNIT_ERR_ARG, "u8_crop_normalize: crop outside the image");
+  mb_launch(u8_crop_normalize_kernel, dim3(grid_for((long long)ch * cw)), dim3(256), 0, ST(stream), img, ih, iw, top, left, flip, out,
+            ch, cw);
+  MB_CHECK_LAUNCH("u8_crop_normalize");
   return MUNIT_OK;
 }
 

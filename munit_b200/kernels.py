@@ -200,6 +200,20 @@ def kwexp_to_image_grad(de, n, c, h, w, pad, kw, sx, kwp, cp):
     return dx
 
 
+def u8_crop_normalize(img_u8, top, left, flip, out):
+    """img_u8 [H, W, 3] uint8 (device) -> out [3, ch, cw] fp32 in [-1, 1]: crop at (top, left), optional mirror,
+    ToTensor + Normalize(0.5, 0.5) (utils.py:218-240)."""
+    _lib.init()
+    assert img_u8.dtype == torch.uint8 and img_u8.is_cuda and img_u8.is_contiguous() and img_u8.shape[2] == 3
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.shape[0] == 3
+    ih, iw, _ = img_u8.shape
+    _, ch, cw = out.shape
+    check(lib.munit_u8_crop_normalize(img_u8.data_ptr(), ih, iw, int(top), int(left), int(bool(flip)), out.data_ptr(), ch,
+                                      cw, _stream()), "u8_crop_normalize")
+    _count()
+    return out
+
+
 def act_to_nchw(act, c, pad):
     n, hp, wp, cp = act.shape
     h, w = hp - 2 * pad, wp - 2 * pad

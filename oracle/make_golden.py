@@ -146,7 +146,7 @@ def classifier_fixture():
     print("classifier.pt ok", y.detach().reshape(-1), y_eval.reshape(-1))
 
 
-def step_fixture(tag, optimizer, gen_state, guided, hw, b, n_steps, masked_synth=False, adaptation=False):
+def step_fixture(tag, optimizer, gen_state, guided, hw, b, n_steps, masked_synth=False, adaptation=False, style_dim=None):
     """dis_update + gen_update on the shimmed reference trainer (trainer.py:336-561,1133-1186).  masked_synth:
     recon_mask = 1 with masks and synth=True with recon_synth_w > 0 (trainer.py:452-488).  adaptation: the
     config_256 values adaptation.adv_lambda = 6, dfeat_lambda = 1 (content-feature classifiers, trainer.py:162-179,
@@ -155,6 +155,8 @@ def step_fixture(tag, optimizer, gen_state, guided, hw, b, n_steps, masked_synth
                             crop_image_height=hw, crop_image_width=hw)
     if adaptation:
         cfg["adaptation"].update(adv_lambda=6, dfeat_lambda=1)
+    if style_dim is not None:
+        cfg["gen"]["style_dim"] = style_dim
     if masked_synth:
         cfg["recon_mask"], cfg["recon_synth_w"] = 1, 5
         torch.cuda.FloatTensor = torch.FloatTensor  # shim 3: trainer.py:456 casts the alignment mask to a CUDA type
@@ -212,6 +214,168 @@ def step_fixture(tag, optimizer, gen_state, guided, hw, b, n_steps, masked_synth
     torch.save(fx, os.path.join(OUT, f"step_{tag}.pt"))
 
 
+def _pool(t, k):
+    """Low-resolution fingerprint of an image batch (average pooling by k), fp16."""
+    import torch.nn.functional as F
+    return F.avg_pool2d(t.detach().float(), k).half()
+
+
+def autocast_grad_cosines():
+    """How far does the REFERENCE ITSELF move when only its convolutions become bf16 tensor-core convolutions?  One
+    dis_update + gen_update of the unmodified reference trainer with nn.Conv2d patched to round its input, weight and
+    output to bf16 (fp32 accumulation, everything else fp32 -- torch.autocast("cpu") cannot run the reference: AdaIN's
+    F.batch_norm rejects the mixed dtypes it produces) against the same update in fp32, same seeded weights, inputs and
+    style codes: per-tensor gradient cosine / norm ratio and the losses.  tests/test_trainer_gpu.py prints this beside
+    the B200 figures (VERDICT r1, next #1): it is the floor any bf16 convolution pipeline has against the fp32 path."""
+    import torch.nn.functional as F
+
+    cfg = O.config_256_core(crop_image_height=64, crop_image_width=64)
+    out = {}
+    orig = torch.nn.Conv2d._conv_forward
+    rnd = lambda t, g: O._RoundSTE.apply(t, g)
+
+    def bf16_conv(self, x, w, b):
+        return rnd(F.conv2d(rnd(x, True), rnd(w, False), b, self.stride, self.padding, self.dilation, self.groups), True)
+
+    for mode in ("fp32", "bf16"):
+        torch.manual_seed(0)
+        t = ref_loader.make_trainer(cfg)
+        t.gen.load_state_dict(O.init_state_dict(O.gen_spec(cfg["gen"], 3, True), 21, "kaiming"))
+        t.dis_a.load_state_dict(O.init_state_dict(O.dis_spec(cfg["dis"], 3), 23, "gaussian"))
+        t.dis_b.load_state_dict(O.init_state_dict(O.dis_spec(cfg["dis"], 3), 24, "gaussian"))
+        x_a, x_b = seeded_images(1234, 2, 64, 64)
+        torch.manual_seed(99)
+        t.iterations = 0
+        torch.nn.Conv2d._conv_forward = bf16_conv if mode == "bf16" else orig
+        try:
+            t.dis_update(x_a, x_b, cfg)
+            dis_g = {f"dis_a/{n}": p.grad.detach().float().clone() for n, p in t.dis_a.named_parameters()}
+            t.gen_update(x_a, x_b, cfg)
+        finally:
+            torch.nn.Conv2d._conv_forward = orig
+        grads = {f"/{n}": p.grad.detach().float().clone() for n, p in t.gen.named_parameters() if p.grad is not None}
+        grads.update(dis_g)
+        losses = {k: float(getattr(t, k)) for k in dir(t) if k.startswith("loss_") and torch.is_tensor(getattr(t, k))}
+        out[mode] = (grads, losses)
+    cos, ratio = {}, {}
+    for k, g32 in out["fp32"][0].items():
+        g16 = out["bf16"][0][k]
+        if float(g32.norm()) < 1e-7:
+            continue
+        cos[k] = float(torch.dot(g16.reshape(-1), g32.reshape(-1)) / (g16.norm() * g32.norm() + 1e-30))
+        ratio[k] = float(g16.norm() / g32.norm())
+    res = dict(cos=cos, ratio=ratio, losses_fp32=out["fp32"][1], losses_bf16=out["bf16"][1])
+    srt = sorted(cos.values())
+    print("reference with bf16 convolutions vs fp32: grad cosine worst %.4f median %.4f" % (srt[0], srt[len(srt) // 2]))
+    torch.save(res, os.path.join(OUT, "autocast_ref.pt"))
+
+
+def sample_fixture():
+    """MUNIT_Trainer.sample / sample_fid / forward of the reference (trainer.py:307-334,773-928,1087-1131) on seeded
+    weights: gen_state 1 / guided 1 and gen_state 0 / guided 0 (random second style: host RNG after manual_seed)."""
+    fx = {}
+    for tag, gs, gd in (("g1", 1, 1), ("g0", 0, 0)):
+        cfg = O.config_256_core(gen_state=gs, guided=gd, crop_image_height=64, crop_image_width=64, display_size=3)
+        torch.manual_seed(5)
+        t = ref_loader.make_trainer(cfg)
+        if gs == 1:
+            t.gen.load_state_dict(O.init_state_dict(O.gen_spec(cfg["gen"], 3, True), 21, "kaiming"))
+        else:
+            t.gen_a.load_state_dict(O.init_state_dict(O.gen_spec(cfg["gen"], 3, False), 21, "kaiming"))
+            t.gen_b.load_state_dict(O.init_state_dict(O.gen_spec(cfg["gen"], 3, False), 22, "kaiming"))
+        x_a, x_b = seeded_images(77, 3, 64, 64)
+        torch.manual_seed(123)
+        with torch.no_grad():
+            outs = t.sample(x_a, x_b)
+            rng_after = torch.get_rng_state()
+            fid = t.sample_fid(x_a, x_b) if gd == 1 else None
+            fwd = t.forward(x_a, x_b)
+        fx[tag] = dict(cfg=cfg, sample=[o.detach().clone() for o in outs], rng_after=rng_after,
+                       sample_fid=None if fid is None else fid.detach().clone(), forward=[o.detach().clone() for o in fwd],
+                       s_a=t.s_a.clone(), s_b=t.s_b.clone())
+        print("sample", tag, [tuple(o.shape) for o in outs])
+    torch.save(fx, os.path.join(OUT, "sample.pt"))
+
+
+def demo_fixture():
+    """The reference's shipped demo images (input_folder/, Style_Image/) through the test.py flow (test.py:86-129,
+    gen_state 1, style image) and the test_batch.py flow (test_batch.py:146-164, gen_state 0, random styles) of the
+    reference generators on seeded weights.  The images are stored already resized to new_size = 256 (what
+    transforms.Resize(256) makes of them: the inference scripts' first step, a no-op on the stored files); the
+    reference outputs as 4x average-pooled fingerprints."""
+    from PIL import Image
+    from torchvision import transforms
+
+    networks, _ = ref_loader.load()
+    demo = os.path.join(OUT, "demo")
+    os.makedirs(os.path.join(demo, "input_folder"), exist_ok=True)
+    os.makedirs(os.path.join(demo, "Style_Image"), exist_ok=True)
+    src = [("input_folder/demo_image1.jpg", "input_folder/demo_image1.png"),
+           ("input_folder/demo_image2.jpg", "input_folder/demo_image2.png"),
+           ("input_folder/demo_image3.png", "input_folder/demo_image3.png"),
+           ("Style_Image/style_image.png", "Style_Image/style_image.png")]
+    for a, b in src:
+        im = transforms.Resize(256)(Image.open(os.path.join(ref_loader.REF_ROOT, a)).convert("RGB"))
+        im.save(os.path.join(demo, b), optimize=True)
+    tf = transforms.Compose([transforms.Resize(256), transforms.ToTensor(), transforms.Normalize((0.5,) * 3, (0.5,) * 3)])
+    load = lambda rel: tf(Image.open(os.path.join(demo, rel)).convert("RGB")).unsqueeze(0)
+    cfg = O.config_256_core()
+    fx = dict(seeds=dict(gen=41, gen_a=42, gen_b=43, style=1), files=[b for _, b in src[:3]], pool=4)
+    # ---- test.py: style of the style image, generator "2" checkpoint
+    gen = networks.AdaINGen_double(3, cfg["gen"])
+    gen.load_state_dict(O.init_state_dict(O.gen_spec(cfg["gen"], 3, True), 41, "kaiming"))
+    outs = []
+    with torch.no_grad():
+        _, s_b = gen.encode(load("Style_Image/style_image.png"), 2)
+        for rel in fx["files"]:
+            c_a, _ = gen.encode(load(rel), 1)
+            outs.append(_pool((gen.decode(c_a, s_b, 2) + 1) / 2.0, 4))
+    fx["test_py"] = dict(s_b=s_b.clone(), outputs=outs, shapes=[tuple(o.shape) for o in outs])
+    # ---- test_batch.py: 3 random styles per image, a2b
+    ga, gb = networks.AdaINGen(3, cfg["gen"]), networks.AdaINGen(3, cfg["gen"])
+    ga.load_state_dict(O.init_state_dict(O.gen_spec(cfg["gen"], 3, False), 42, "kaiming"))
+    gb.load_state_dict(O.init_state_dict(O.gen_spec(cfg["gen"], 3, False), 43, "kaiming"))
+    # the script's own order of host-RNG use (test_batch.py:89-164): seed, trainer construction (weight init + display
+    # codes), checkpoint load, style_fixed, the DataLoader iterator's base-seed draw, then one style draw per image
+    num_style = 3
+    torch.manual_seed(1)
+    ref_loader.make_trainer(O.config_256_core(gen_state=0, guided=0))
+    style_fixed = torch.randn(num_style, cfg["gen"]["style_dim"], 1, 1)  # unused unless --synchronized
+    torch.empty((), dtype=torch.int64).random_()  # what creating the DataLoader iterator draws (torch.utils.data)
+    tb = []
+    with torch.no_grad():
+        for rel in fx["files"]:
+            img = load(rel)
+            style = torch.randn(num_style, cfg["gen"]["style_dim"], 1, 1)
+            content, _ = ga.encode(img)
+            tb.append([_pool((gb.decode(content, style[j:j + 1]) + 1) / 2.0, 4) for j in range(num_style)])
+    fx["test_batch"] = dict(num_style=num_style, outputs=tb)
+    torch.save(fx, os.path.join(OUT, "demo.pt"))
+    print("demo.pt ok", fx["test_py"]["shapes"])
+
+
+def infer_fixture():
+    """BASELINE.json configs[3] at its full shape: 32 content images x 10 random styles, 256x256, gen_state 0
+    (test_batch.py:146-164 semantics); reference outputs as 16x average-pooled fingerprints."""
+    networks, _ = ref_loader.load()
+    cfg = O.config_256_core(gen_state=0, guided=0)
+    ga, gb = networks.AdaINGen(3, cfg["gen"]), networks.AdaINGen(3, cfg["gen"])
+    ga.load_state_dict(O.init_state_dict(O.gen_spec(cfg["gen"], 3, False), 42, "kaiming"))
+    gb.load_state_dict(O.init_state_dict(O.gen_spec(cfg["gen"], 3, False), 43, "kaiming"))
+    x, _ = seeded_images(1234, 32, 256, 256)
+    torch.manual_seed(7)
+    styles = torch.randn(10, cfg["gen"]["style_dim"], 1, 1)
+    outs = torch.empty(10, 32, 3, 16, 16, dtype=torch.float16)
+    with torch.no_grad():
+        for b0 in range(0, 32, 8):
+            content, _ = ga.encode(x[b0:b0 + 8])
+            for j in range(10):
+                outs[j, b0:b0 + 8] = _pool(gb.decode(content, styles[j:j + 1].expand(8, -1, -1, -1)), 16)
+            print("infer fixture", b0)
+    torch.save(dict(seeds=dict(gen_a=42, gen_b=43, img=1234, style=7), styles=styles, outputs=outs, pool=16),
+               os.path.join(OUT, "infer_32x10.pt"))
+
+
 def adam_fixture():
     """torch.optim.Adam (what trainer.py:41-45 instantiates) and the reference ExtraAdam on a toy problem."""
     ref_loader.load()
@@ -240,9 +404,19 @@ def adam_fixture():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
-    if len(sys.argv) > 1 and sys.argv[1] == "adaptation":  # only the fixtures of SURVEY.md 8(f).2
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what == "adaptation":  # only the fixtures of SURVEY.md 8(f).2
         classifier_fixture()
         step_fixture("g1_adaptation_adam", "adam", 1, 1, 256, 1, 1, adaptation=True)
+        sys.exit(0)
+    if what == "r2":  # round-2 additions only (benchmark shapes, sampling, demo images)
+        sample_fixture()
+        demo_fixture()
+        autocast_grad_cosines()
+        step_fixture("g1_guided_adam_sd8", "adam", 1, 1, 64, 2, 1, style_dim=8)
+        step_fixture("g1_guided_adam_b8_256", "adam", 1, 1, 256, 8, 1)
+        step_fixture("g1_guided_extraadam_hd512", "extraadam", 1, 1, 512, 1, 2)
+        infer_fixture()
         sys.exit(0)
     layers_fixture()
     adam_fixture()
@@ -252,3 +426,10 @@ if __name__ == "__main__":
     step_fixture("g1_masked_synth_adam", "adam", 1, 1, 64, 2, 1, masked_synth=True)
     classifier_fixture()
     step_fixture("g1_adaptation_adam", "adam", 1, 1, 256, 1, 1, adaptation=True)
+    sample_fixture()
+    demo_fixture()
+    autocast_grad_cosines()
+    step_fixture("g1_guided_adam_sd8", "adam", 1, 1, 64, 2, 1, style_dim=8)
+    step_fixture("g1_guided_adam_b8_256", "adam", 1, 1, 256, 8, 1)
+    step_fixture("g1_guided_extraadam_hd512", "extraadam", 1, 1, 512, 1, 2)
+    infer_fixture()

@@ -51,18 +51,29 @@ def main():
         transform = transforms.Compose([transforms.Resize(new_size), transforms.ToTensor(),
                                         transforms.Normalize((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))])
 
-        def load(path):
+        def load(path, multiple):
+            """Resize(new_size) -> ToTensor -> Normalize (test.py:88-94), then the image is cut (right / bottom) to the
+            largest extent the strided encoders map exactly: a multiple of 4 for the content path (2 stride-2 layers)
+            and of 16 for the style encoder (4).  The reference feeds the resized image as is and its stride-2
+            convolutions silently ignore the odd last row / column, its up-sampling decoder returns 4 * floor(W / 4)
+            columns (341 -> 340): output sizes are therefore the same, and only the few output columns whose receptive
+            field reaches the dropped input column differ (tests/test_inference_gpu.py compares against the
+            reference's outputs on its own demo images)."""
             x = transform(Image.open(path).convert("RGB")).unsqueeze(0)
-            h, w = x.shape[2] // 16 * 16, x.shape[3] // 16 * 16  # the style encoder halves the size 4 times
+            h, w = x.shape[2] // multiple * multiple, x.shape[3] // multiple * multiple
+            if h == 0 or w == 0:
+                sys.exit("image %s is smaller than %d pixels after Resize(%d)" % (path, multiple, new_size))
             return x[:, :, :h, :w].contiguous().cuda()
 
-        _, s_b = trainer.gen.encode(load(opts.style), 2)
+        # (the reference calls gen.encode(), which also runs the style encoder on the content image and the content
+        # encoder on the style image and discards both, test.py:100,114; only the halves that are used run here)
+        s_b = trainer.gen.enc_style(load(opts.style, 16))
         for j, path_xa in enumerate(list_non_flooded):
-            x_a = load(path_xa)
+            x_a = load(path_xa, 4)
             if opts.save_input:
                 vutils.save_image(((x_a + 1) / 2.0).data, os.path.join(opts.output_folder, "input{:03d}.jpg".format(j)),
                                   padding=0, normalize=True)
-            c_a, _ = trainer.gen.encode(x_a, 1)
+            c_a = trainer.gen.enc1_content.forward_act(x_a, 1)
             x_ab = trainer.gen.decode(c_a, s_b, 2)
             outputs = (x_ab + 1) / 2.0
             vutils.save_image(outputs.data, os.path.join(opts.output_folder, "output{:03d}.jpg".format(j)), padding=0,

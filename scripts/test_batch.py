@@ -29,8 +29,10 @@ parser.add_argument("--trainer", type=str, default="MUNIT", help="MUNIT")
 
 
 def translate(encode, decode, images, styles):
-    """images [B,3,H,W], styles [S,style_dim,1,1] -> [S][B,3,H,W]: one encode, S decodes (batched over B)."""
-    content, _ = encode(images)
+    """images [B,3,H,W], styles [S,style_dim,1,1] -> [S][B,3,H,W]: one content encode, S decodes (batched over B).
+    `encode` returns the content code only (the reference's gen.encode also runs the style encoder on the content
+    image and discards the result, test_batch.py:154)."""
+    content = encode(images)
     return [decode(content, styles[j:j + 1].expand(images.shape[0], -1, -1, -1).contiguous())
             for j in range(styles.shape[0])]
 
@@ -54,15 +56,20 @@ def main():
     trainer.gen_b.load_state_dict(state_dict["b"])
     trainer.cuda()
     trainer.eval()
-    encode = trainer.gen_a.encode if opts.a2b else trainer.gen_b.encode
+    enc = trainer.gen_a.enc_content if opts.a2b else trainer.gen_b.enc_content
+    encode = lambda x: enc.forward_act(x, 1)
     decode = trainer.gen_b.decode if opts.a2b else trainer.gen_a.decode
     tf = transforms.Compose([transforms.Resize(config.get("new_size_a", config["new_size"])), transforms.ToTensor(),
                              transforms.Normalize((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))])
     style_fixed = torch.randn(opts.num_style, style_dim, 1, 1).cuda()
+    # the reference iterates a torch DataLoader here (test_batch.py:110-112,148): creating its iterator draws one int64
+    # base seed from the host generator before the per-image style codes are drawn -- same draw, same codes
+    torch.empty((), dtype=torch.int64).random_()
     with torch.no_grad():
         for i, path in enumerate(sorted(glob.glob(os.path.join(opts.input_folder, "*")))):
             x = tf(Image.open(path).convert("RGB")).unsqueeze(0)
-            h, w = x.shape[2] // 16 * 16, x.shape[3] // 16 * 16
+            # cut to a multiple of 4 (2 stride-2 layers): the reference's output has 4 * floor(W / 4) columns too
+            h, w = x.shape[2] // 4 * 4, x.shape[3] // 4 * 4
             images = x[:, :, :h, :w].contiguous().cuda()
             style = style_fixed if opts.synchronized else torch.randn(opts.num_style, style_dim, 1, 1).cuda()
             for j, out in enumerate(translate(encode, decode, images, style)):

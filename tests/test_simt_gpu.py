@@ -281,3 +281,41 @@ def test_l1_masked(shape):
     (out * 1.0).sum().backward()
     assert abs(float(out) - float(ref)) <= 1e-5 * abs(float(ref))
     assert torch.allclose(a.grad, ga_ref, atol=1e-9) and torch.allclose(b.grad, gb_ref, atol=1e-9)
+
+
+@pytest.mark.parametrize("flip", [0, 1])
+def test_u8_crop_normalize_is_bit_exact(flip):
+    """GPU tail of the input pipeline == transforms.RandomCrop / hflip / ToTensor / Normalize."""
+    from munit_b200 import kernels as K
+
+    g = torch.Generator().manual_seed(4)
+    img = torch.randint(0, 256, (37, 53, 3), dtype=torch.uint8, generator=g)
+    top, left, ch, cw = 5, 11, 24, 32
+    ref = img[top:top + ch, left:left + cw].permute(2, 0, 1).float().div(255)
+    if flip:
+        ref = ref.flip(2)
+    ref = (ref - 0.5) / 0.5
+    out = torch.empty(3, ch, cw, device="cuda")
+    K.u8_crop_normalize(img.cuda(), top, left, flip, out)
+    assert torch.equal(out.cpu(), ref)
+
+
+def test_gpu_preproc_loader_matches_host_pipeline(tmp_path):
+    """data.GpuPreprocLoader (workers: decode + flip + resize, device: crop + normalise) yields the batches the host
+    pipeline (data.get_data_loader_folder, the reference's transforms) yields for the same seed."""
+    from PIL import Image
+
+    from munit_b200 import data as D
+
+    g = torch.Generator().manual_seed(0)
+    for i in range(6):
+        arr = torch.randint(0, 256, (40 + 3 * i, 70 - 2 * i, 3), dtype=torch.uint8, generator=g).numpy()
+        Image.fromarray(arr).save(tmp_path / f"im{i}.png")
+    kw = dict(batch_size=2, train=True, new_size=36, height=32, width=32, num_workers=0, crop=True)
+    torch.manual_seed(11)
+    host = [b.clone() for b in D.get_data_loader_folder(str(tmp_path), **kw)]
+    torch.manual_seed(11)
+    dev = [b.cpu() for b in D.get_gpu_data_loader_folder(str(tmp_path), **kw)]
+    assert len(host) == len(dev) == 3
+    for a, b in zip(host, dev):
+        assert torch.equal(a, b)
