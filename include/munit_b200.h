@@ -96,6 +96,9 @@ typedef struct {
                       follow with munit_splitk_finish.  For layers with too few output tiles to fill the GPU
                       (the deep discriminator layers).  Excludes halo and stats. */
   float* scratch;  /* zero-initialised fp32 buffer with exactly the element geometry of `out` (same o_s* strides) */
+  int32_t pair;    /* 1: CTA-pair kernel (tcgen05 cta_group::2, bn 128 or 256, not halo): two adjacent M tiles per
+                      2-CTA cluster share one weight tile, each CTA loads half of its rows -- fewer L2 -> SM bytes
+                      per FLOP on the wide layers.  Same results as pair = 0. */
 } munit_tapgemm_desc;
 
 int munit_tapgemm(const munit_tapgemm_desc* d, void* stream);

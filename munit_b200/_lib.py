@@ -32,6 +32,7 @@ class TapGemmDesc(C.Structure):
         ("o_ymul", C.c_int32), ("o_xmul", C.c_int32), ("n_store", C.c_int32),
         ("bias", C.c_void_p), ("act", C.c_int32), ("stages", C.c_int32), ("out_f16", C.c_int32), ("halo", C.c_int32),
         ("stats", C.c_void_p), ("stats_kind", C.c_int32), ("ksplit", C.c_int32), ("scratch", C.c_void_p),
+        ("pair", C.c_int32),
     ]
 
 

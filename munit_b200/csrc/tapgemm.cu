@@ -374,6 +374,206 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 }
 
 // =============================================================================================
+// CTA-pair variant (tcgen05 cta_group::2): two CTAs on the two SMs of a TPC (a cluster of 2 along the M-tile index)
+// compute two adjacent 128-pixel tiles against the SAME weight tile.  Each CTA loads its own activation tile and only
+// HALF of the weight rows (BN/2 output channels); the pair MMA (M = 256, N = BN, issued by one thread of the even CTA)
+// reads both halves.  L2 -> SM bytes per tile and k-block drop from 16 + BN/8 KB to 16 + BN/16 KB (48 -> 32 KB at
+// BN = 256), which is what bounds the single-CTA kernel on the 256-channel layers (profiles/r2_pair.md), and the
+// smaller stage lets three stages fit while two CTAs still share an SM.
+// =============================================================================================
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 2)
+tapgemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ OutMaps tmap_out, const __grid_constant__ FwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int kBRows = BN / 2;           // weight rows this CTA holds
+  constexpr int kBBytes = kBRows * 128;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr int kTmemCols = BN;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];   // used in the leader CTA only
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stages = p.stages;
+  const uint32_t cta_rank = cluster_ctarank();  // 0 = leader (even CTA of the pair)
+
+  int t = blockIdx.x;
+  const int tx = t % p.tiles_x;
+  t /= p.tiles_x;
+  const int ty = t % p.tiles_y;
+  const int tnn = t / p.tiles_y;  // >= tiles_n for the padding CTA of an odd tile count: loads zero-fill, stores are clipped
+  const int x0 = tx * p.tw, y0 = ty * p.th, n0 = tnn * p.tn;
+  const int n_tile = blockIdx.y;
+  const int phase_id = blockIdx.z / p.ksplit;
+  const int k_slice = blockIdx.z - phase_id * p.ksplit;
+  const int total_kb = p.num_taps * p.chunks;
+  const int kb_begin = (int)(((long long)total_kb * k_slice) / p.ksplit);
+  const int kb_end = (int)(((long long)total_kb * (k_slice + 1)) / p.ksplit);
+  const int num_kb = kb_end - kb_begin;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&tmem_full_bar), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_cg2(smem_u32(&tmem_base_slot), kTmemCols);
+    tmem_relinquish_cg2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers exist before anything arrives on them remotely
+  tc_fence_after();
+  pdl_wait();
+  pdl_trigger();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (elect_one()) {
+      bool dead = false;
+      int base[5];
+#pragma unroll
+      for (int d = 0; d < 5; ++d) base[d] = x0 * p.mx[d] + y0 * p.my[d] + n0 * p.mn[d];
+      const int bk0 = p.b_k0[phase_id];
+      int stage = 0;
+      uint32_t ph = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        const int tap = kb / p.chunks;
+        const int kc = kb - tap * p.chunks;
+        mbar_wait(smem_u32(&empty_bar[stage]), ph ^ 1, dead, p.err);
+        const uint32_t fb = smem_u32(&full_bar[stage]);  // (the loads clear the peer bit: the leader's barrier)
+        if (cta_rank == 0) mbar_arrive_expect_tx(fb, 2 * kStageBytes);
+        int c[5];
+#pragma unroll
+        for (int d = 0; d < 5; ++d) c[d] = base[d] + p.tap_off[tap][d];
+        c[0] += kc * 64;
+        const uint32_t sa = smem_base + stage * kStageBytes;
+        tma_load_nd_cg2(p.rank, sa, &tmap_a, fb, c);
+        tma_load_2d_cg2(sa + kABytes, &tmap_b, fb, bk0 + kb * 64, n_tile * BN + (int)cta_rank * kBRows);
+        if (++stage == stages) {
+          stage = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (cta_rank == 0 && elect_one()) {
+      bool dead = false;
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
+      int stage = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&full_bar[stage]), ph, dead, p.err);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * kStageBytes;
+        const uint32_t sb = sa + kABytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da = umma_desc_sw128(sa + k * 32, 0, 1024);
+          const uint64_t db = umma_desc_sw128(sb + k * 32, 0, 1024);
+          umma_bf16_cg2(tmem_base, da, db, idesc, (kb | k) != 0);
+        }
+        umma_commit_cg2(smem_u32(&empty_bar[stage]), 3);  // frees the stage in both CTAs
+        if (++stage == stages) {
+          stage = 0;
+          ph ^= 1;
+        }
+      }
+      umma_commit_cg2(smem_u32(&tmem_full_bar), 3);  // both epilogues may drain their half of the accumulator
+    }
+  } else {
+    // ===================== epilogue (both CTAs, each its own 128-pixel tile) =====================
+    bool dead = false;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    mbar_wait(smem_u32(&tmem_full_bar), 0, dead, p.err);
+    tc_fence_after();
+    const float slope = act_slope(p.act);
+    const bool is_tanh = p.act == MUNIT_ACT_TANH;
+    const bool f16 = p.out_f16 != 0;
+    if (p.scratch) {
+      const int dx = row % p.tw;
+      const int dy = (row / p.tw) % p.th;
+      const int dn = row / (p.tw * p.th);
+      const int n = n0 + dn, y = y0 + dy, x = x0 + dx;
+      const bool valid = (n < p.n_img) && (y < p.out_h) && (x < p.out_w) && num_kb > 0;
+      float* sptr = p.scratch + (long long)n * p.o_sn + (long long)(y * p.o_ymul + p.o_yoff[phase_id]) * p.o_sy +
+                    (long long)(x * p.o_xmul + p.o_xoff[phase_id]) * p.o_sx + n_tile * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+        tmem_ld_wait();
+        if (valid && !dead) {
+          const int col0 = n_tile * BN + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            if (col0 + j < p.n_store)
+              red_add_v4_f32(sptr + c0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                             __uint_as_float(v[j + 3]));
+        }
+      }
+    } else {
+      // every MMA has completed and the producers are done: the pipeline stages are free for staging the bf16 tile
+      constexpr int kGroups = BN / 64;
+      const bool issuer = (warp == 2 && lane == 0);
+#pragma unroll 1
+      for (int g = 0; g < kGroups; ++g) {
+        const uint32_t buf = smem_base + g * kABytes;
+        const int col0 = n_tile * BN + g * 64;
+        const bool store_group = col0 < p.n_store;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * 64 + h * 32, v);
+          tmem_ld_wait();
+          if (store_group) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint32_t o[4];
+              epi8(v + j, p.bias ? p.bias + col0 + h * 32 + j : nullptr, slope, is_tanh, o, f16);
+              const int chunk = (h * 4 + (j >> 3)) ^ (row & 7);
+              const uint32_t dst = buf + row * 128 + chunk * 16;
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]),
+                           "r"(o[3])
+                           : "memory");
+            }
+          }
+        }
+        fence_proxy_async();
+        named_bar_sync(1, 128);
+        if (issuer && store_group && !dead) {
+          tma_store_4d(&tmap_out.m[phase_id], buf, col0, x0, y0, n0);
+          tma_store_commit();
+        }
+        if (p.stats && store_group && !dead && tnn < p.tiles_n)
+          staged_stats(buf, q, lane, p.stats, p.stats_kind, p.stats_c, n0, ty * p.tiles_x + tx,
+                       p.tiles_x * p.tiles_y, col0, f16);
+      }
+      if (issuer) tma_store_wait_read0();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // neither CTA frees TMEM / exits while the pair's MMAs or remote arrives can still touch it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_cg2(tmem_base, kTmemCols);
+  }
+}
+
+// =============================================================================================
 // Halo-resident variant for stride-1 convolutions (3x3 / 5x5 / 7x1 ...): per 64-channel chunk ONE TMA box
 // [RB rows x WB cols x 64 ch] covering the 8 x 16 pixel tile plus its (KH-1, KW-1) halo lands in shared memory and
 // every tap's A operand is a shifted UMMA descriptor into it (start += (wy*WB + wx)*128 B, 8-row groups = one
@@ -779,6 +979,32 @@ int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, const OutMaps& to, 
 }
 
 template <int BN>
+int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const OutMaps& to, FwdParams& p, dim3 grid,
+                cudaStream_t st) {
+  const int stage_bytes = kABytes + (BN / 2) * 128;
+  // three stages while two CTAs (of two different pairs) still share an SM (<= ~113 KB each); the epilogue stages
+  // BN/64 16 KB boxes in the same memory
+  int stages = p.stages > 0 ? p.stages : 3;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  size_t smem = (size_t)stages * stage_bytes + 1024;
+  const size_t need_epi = (size_t)(BN / 64) * kABytes + 1024;
+  if (smem < need_epi) smem = need_epi;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+    attr_smem = smem;
+  }
+  grid.x = (grid.x + 1) / 2 * 2;  // whole pairs; the padding CTA maps to an out-of-range tile
+  mb_launch(tapgemm_pair_kernel<BN>, grid, dim3(kThreads), smem, st, ta, tb, to, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "tapgemm_pair launch: %s", cudaGetErrorString(e));
+  return MUNIT_OK;
+}
+
+template <int BN>
 int launch_halo(const CUtensorMap& ta, const CUtensorMap& tb, const OutMaps& to, FwdParams& p, dim3 grid,
                 cudaStream_t st) {
   const size_t a_bytes = ((size_t)p.halo_wb * p.halo_rb * 128 + 1023) & ~(size_t)1023;
@@ -951,9 +1177,10 @@ extern "C" int munit_tapgemm(const munit_tapgemm_desc* d, void* stream) {
     }
     return mb_fail(MUNIT_ERR_ARG, "tapgemm halo: bn %d unsupported", d->bn);
   }
+  const bool pair = d->pair && (d->bn == 128 || d->bn == 256) && !d->halo;
   uint64_t bdim[2] = {d->b_k, d->b_rows};
   uint64_t bstr[2] = {0, d->b_k * 2};
-  uint32_t bbox[2] = {64, (uint32_t)d->bn};
+  uint32_t bbox[2] = {64, (uint32_t)(pair ? d->bn / 2 : d->bn)};
   rc = make_tmap(&tb, d->b, 2, bdim, bstr, bbox);
   if (rc) return rc;
   // output views for the TMA-store epilogue (BN >= 64): one per phase, clipped to the valid extents
@@ -971,6 +1198,7 @@ extern "C" int munit_tapgemm(const munit_tapgemm_desc* d, void* stream) {
       if (rc) return rc;
     }
   }
+  if (pair) return d->bn == 256 ? launch_pair<256>(ta, tb, to, p, grid, st) : launch_pair<128>(ta, tb, to, p, grid, st);
   switch (d->bn) {
     case 16: return launch_fwd<16>(ta, tb, to, p, grid, st);
     case 32: return launch_fwd<32>(ta, tb, to, p, grid, st);

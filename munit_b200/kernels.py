@@ -80,13 +80,15 @@ def auto_ksplit(plan) -> int:
     return max(1, min(num_kb // 4, 16, 296 // ctas))
 
 
+# CTA-pair (cta_group::2) tap-GEMM for the bn 128 / 256 launches (include/munit_b200.h, munit_tapgemm_desc.pair)
+PAIR = _os.environ.get("MUNIT_PAIR", "1") != "0"
 _AUTO_KSPLIT = _os.environ.get("MUNIT_KSPLIT", "1") != "0"
 _KSPLIT_MAX_CTAS = int(_os.environ.get("MUNIT_KSPLIT_CTAS", "8"))
 _KSPLIT_MIN_KB = int(_os.environ.get("MUNIT_KSPLIT_KB", "64"))
 
 
 def tapgemm(plan, a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, bias=None, act="none", stages=0,
-            stats=None, stats_kind=0, ksplit=0):
+            stats=None, stats_kind=0, ksplit=0, pair=None):
     """out (bf16) <- act(tapconv(a; b) + bias) as described by `plan` (geometry.TapGemmPlan).  `stats` (fp32,
     n_img * stats_splits(plan, kind) * (C if kind == 1 else 1) * 2 floats) receives the norm partials."""
     _lib.init()
@@ -118,6 +120,7 @@ def tapgemm(plan, a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, bias=None
         assert bias.dtype == torch.float32 and bias.numel() >= plan.b_rows
     d.bias, d.act, d.stages = _ptr(bias), ACT[act], stages
     d.out_f16 = _f16(out)
+    d.pair = int(PAIR if pair is None else pair)
     d.halo = int(getattr(plan, "halo", 0))
     ksplit = ksplit or (auto_ksplit(plan) if stats is None else 1)
     scratch = None
