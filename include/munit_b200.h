@@ -230,9 +230,11 @@ int munit_norm_bwd_apply(const void* g_out, int out_pad, int upsample, const voi
                          const float* cc, void* dy, void* g_res, int res_pad, int n, int h, int w, int c, void* stream);
 
 /* No-norm conv blocks: dy [N][H][W][C] = fold(g_out_act) * act'(out) where out is the forward output
- * (interior of out_act, halo `pad`; g_out has the same padded extent). */
+ * (interior of out_act, halo `pad`; g_out has the same padded extent).
+ * dbias (optional, needs 256 % (c/8) == 0): dbias[ch] += sum over pixels of dy for ch < c_out -- the convolution's
+ * bias gradient in the same pass (otherwise munit_colsum). */
 int munit_act_bwd(const void* g_out, const void* out_act, int pad, int act, void* dy, int n, int h, int w, int c,
-                  void* stream);
+                  float* dbias, int c_out, void* stream);
 /* dbias[c] += sum over pixels of dy [npix][C] bf16, for c < c_out (<= C). */
 int munit_colsum(const void* dy, float* dbias, int64_t npix, int c, int c_out, void* stream);
 
@@ -250,6 +252,18 @@ int munit_rspace_expand(const float* g, const float* out, void* dr, float* dbias
  * dst[i] = idx[i] >= 0 ? bf16(src[idx[i]]) : 0 -- the index map (built once per layer on the host) encodes
  * tap order, channel padding, the dgrad transpose and the stride-2 phase split. */
 int munit_gather_cast(const float* src, const int32_t* idx, void* dst, int64_t n, void* stream);
+/* Every shadow of one optimiser arena in one launch (after the Adam update, optim.FlatAdam): a device array of
+ * segments sorted by block0; segment s owns blocks [block0, block0 + ceil(n / MUNIT_GATHER_BLOCK)), idx == NULL is the
+ * identity map (plain fp32 -> bf16 cast).  nblocks = total blocks of all segments. */
+#define MUNIT_GATHER_BLOCK 2048
+typedef struct {
+  const float* src;
+  const int32_t* idx;
+  void* dst;
+  int64_t n;
+  int64_t block0;
+} munit_gather_seg;
+int munit_gather_cast_multi(const munit_gather_seg* segs, int nseg, int64_t nblocks, void* stream);
 /* dst[i] += src[idx[i]] for idx[i] >= 0: moves wgrad results from a padded GEMM layout into .grad. */
 int munit_gather_add(const float* src, const int32_t* idx, float* dst, int64_t n, void* stream);
 int munit_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
@@ -324,10 +338,6 @@ int munit_bn_finalize(const float* stats, int splits, const float* shift, int n_
 int munit_bn_bwd_finalize(const float* sums, int splits, int n_total, int n0, int n_local, const float* gamma,
                           const float* rinv, int training, float* ca, float* cb, float* cc, float* g_gamma,
                           float* g_beta, int hw, int c, void* stream);
-/* Replicate (clamp-to-edge) halo of width pad around the interior of act [N][H+2P][W+2P][C], in place: the input
- * layout of the phase form of nn.Upsample(2) + ReflectionPad2d(2) + 5x5 conv (networks.py:534-545; experimental,
- * geometry.plan_upconv_phases). */
-int munit_halo_fill_replicate(void* act, int n, int h, int w, int c, int pad, void* stream);
 /* out = relu(a + b), n bf16 elements (BasicBlock.forward residual tail, utils.py:1327-1329). */
 int munit_add_relu(const void* a, const void* b, void* out, int64_t n, void* stream);
 /* loss = scale * sum((x - target)^2) over n fp32 values (compute_classifier_sr_loss, trainer.py:658-667);

@@ -85,11 +85,12 @@ _SIGS = {
     "munit_norm_bwd_reduce": ([_vp, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp], C.c_int),
     "munit_norm_bwd_finalize": ([_vp, _i, _vp, _i64, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp], C.c_int),
     "munit_norm_bwd_apply": ([_vp, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], C.c_int),
-    "munit_act_bwd": ([_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp], C.c_int),
+    "munit_act_bwd": ([_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp], C.c_int),
     "munit_colsum": ([_vp, _vp, _i64, _i, _i, _vp], C.c_int),
     "munit_rspace_combine": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], C.c_int),
     "munit_rspace_expand": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], C.c_int),
     "munit_gather_cast": ([_vp, _vp, _vp, _i64, _vp], C.c_int),
+    "munit_gather_cast_multi": ([_vp, _i, _i64, _vp], C.c_int),
     "munit_gather_add": ([_vp, _vp, _vp, _i64, _vp], C.c_int),
     "munit_cast_bf16": ([_vp, _vp, _i64, _vp], C.c_int),
     "munit_linear_fwd": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp], C.c_int),
@@ -113,7 +114,6 @@ _SIGS = {
     "munit_maxpool2_bwd": ([_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp], C.c_int),
     "munit_bn_finalize": ([_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _vp, _vp, _i, _i, _vp], C.c_int),
     "munit_bn_bwd_finalize": ([_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp], C.c_int),
-    "munit_halo_fill_replicate": ([_vp, _i, _i, _i, _i, _i, _vp], C.c_int),
     "munit_add_relu": ([_vp, _vp, _vp, _i64, _vp], C.c_int),
     "munit_mse_const_fwd": ([_vp, _f, _vp, _f, _i, _vp], C.c_int),
     "munit_mse_const_bwd": ([_vp, _f, _vp, _f, _vp, _i, _vp], C.c_int),

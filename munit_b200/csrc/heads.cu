@@ -215,28 +215,6 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums, int split
   if (g_beta) g_beta[ch] += (float)l1;
 }
 
-// ------------------------------------------------------------------ replicate halo (clamp-to-edge) of an act
-// For the phase form of nearest-2x upsample + 5x5 conv (geometry.plan_upconv_phases): the low-res input carries a
-// replicate halo of 1.  Every halo position copies its clamped interior pixel (interior pixels are only read).
-__global__ void halo_fill_replicate_kernel(bf16* __restrict__ act, int n, int h, int w, int c, int pad) {
-  pdl_wait();
-  pdl_trigger();
-  const int hp = h + 2 * pad, wp = w + 2 * pad, cg = c / 8;
-  const long long total = (long long)n * hp * wp * cg;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long t = i;
-    const int g = (int)(t % cg); t /= cg;
-    const int xp = (int)(t % wp); t /= wp;
-    const int yp = (int)(t % hp);
-    const int b = (int)(t / hp);
-    const int y = yp - pad, x = xp - pad;
-    if (y >= 0 && y < h && x >= 0 && x < w) continue;
-    const int sy = min(max(y, 0), h - 1) + pad, sx = min(max(x, 0), w - 1) + pad;
-    const uint4 v = *reinterpret_cast<const uint4*>(act + (((long long)b * hp + sy) * wp + sx) * c + g * 8);
-    *reinterpret_cast<uint4*>(act + (((long long)b * hp + yp) * wp + xp) * c + g * 8) = v;
-  }
-}
-
 // ------------------------------------------------------------------ relu(a + b)
 __global__ void add_relu_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ out,
                                 long long n8) {
@@ -325,14 +303,6 @@ int munit_bn_bwd_finalize(const float* sums, int splits, int n_total, int n0, in
   mb_launch(bn_bwd_finalize_kernel, dim3((c + 63) / 64), dim3(64), 0, ST(stream), sums, splits, n_total, n0, n_local, gamma, rinv,
             training, ca, cb, cc, g_gamma, g_beta, hw, c);
   MB_CHECK_LAUNCH("bn_bwd_finalize");
-  return MUNIT_OK;
-}
-
-int munit_halo_fill_replicate(void* act, int n, int h, int w, int c, int pad, void* stream) {
-  if (c % 8 || pad < 1 || h < 1 || w < 1) return mb_fail(MUNIT_ERR_ARG, "halo_fill_replicate: c %% 8, pad >= 1");
-  const long long total = (long long)n * (h + 2 * pad) * (w + 2 * pad) * (c / 8);
-  mb_launch(halo_fill_replicate_kernel, dim3(grid_for(total)), dim3(256), 0, ST(stream), BF(act), n, h, w, c, pad);
-  MB_CHECK_LAUNCH("halo_fill_replicate");
   return MUNIT_OK;
 }
 

@@ -1194,11 +1194,16 @@ norm_bwd_apply_kernel(const bf16* __restrict__ g_out, int out_pad, const bf16* _
   norm_bwd_apply_body<UP, H>(launch_blk(), g_out, out_pad, y, a, b, relu, mean, rinv, ca, cb, cc, dy, g_res, res_pad, n, h, w, c, lw);
 }
 
+// dbias (optional): dbias[ch] += sum over pixels of dy, ch < c_out -- the bias gradient of the convolution in the same
+// pass (256 % (c/8) == 0, so a thread keeps its channel group over the whole grid-stride loop).
 __global__ void act_bwd_kernel(const bf16* __restrict__ g_out, const bf16* __restrict__ out_act, int pad, int act,
-                               bf16* __restrict__ dy, int n, int h, int w, int c) {
+                               bf16* __restrict__ dy, int n, int h, int w, int c, float* __restrict__ dbias, int c_out) {
   pdl_wait();
   pdl_trigger();
   const int cg = c / 8;
+  float bs[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) bs[e] = 0.f;
   const long long total = (long long)n * h * w * cg;
   const int hp = h + 2 * pad, wp = w + 2 * pad;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -1217,7 +1222,24 @@ __global__ void act_bwd_kernel(const bf16* __restrict__ g_out, const bf16* __res
         else gr.v[e] *= (1.f - o.v[e] * o.v[e]);
       }
     }
-    store8(dy + i * 8, gr);
+    const uint4 packed = pack8(gr);
+    *reinterpret_cast<uint4*>(dy + i * 8) = packed;
+    if (dbias) {
+      const F8 st = unpack8(packed);  // sum what was stored (bf16), as munit_colsum would read it back
+#pragma unroll
+      for (int e = 0; e < 8; ++e) bs[e] += st.v[e];
+    }
+  }
+  if (dbias) {
+    __shared__ float red[256][9];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[threadIdx.x][e] = bs[e];
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < c_out; ch += blockDim.x) {
+      float a = 0.f;
+      for (int t = ch >> 3; t < (int)blockDim.x; t += cg) a += red[t][ch & 7];
+      atomicAdd(dbias + ch, a);
+    }
   }
 }
 
@@ -1319,6 +1341,29 @@ __global__ void gather_cast_kernel(const float* __restrict__ src, const int* __r
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int j = idx[i];
     dst[i] = __float2bfloat16(j >= 0 ? src[j] : 0.f);
+  }
+}
+// All weight shadows of one optimiser arena in ONE launch: block b finds its segment (the last one whose first block is
+// <= b; segments are sorted) and converts MUNIT_GATHER_BLOCK elements of it.
+__global__ void gather_cast_multi_kernel(const munit_gather_seg* __restrict__ segs, int nseg) {
+  pdl_wait();
+  pdl_trigger();
+  int lo = 0, hi = nseg - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (segs[mid].block0 <= (long long)blockIdx.x) lo = mid;
+    else hi = mid - 1;
+  }
+  const munit_gather_seg s = segs[lo];
+  bf16* __restrict__ dst = static_cast<bf16*>(s.dst);
+  const long long base = ((long long)blockIdx.x - s.block0) * MUNIT_GATHER_BLOCK;
+#pragma unroll
+  for (int k = 0; k < MUNIT_GATHER_BLOCK / 256; ++k) {
+    const long long i = base + k * 256 + threadIdx.x;
+    if (i < s.n) {
+      const long long j = s.idx ? (long long)s.idx[i] : i;
+      dst[i] = __float2bfloat16(j >= 0 ? s.src[j] : 0.f);
+    }
   }
 }
 __global__ void gather_add_kernel(const float* __restrict__ src, const int* __restrict__ idx, float* __restrict__ dst,
@@ -2022,10 +2067,12 @@ int munit_norm_bwd_apply(const void* g_out, int out_pad, int upsample, const voi
 }
 
 int munit_act_bwd(const void* g_out, const void* out_act, int pad, int act, void* dy, int n, int h, int w, int c,
-                  void* stream) {
+                  float* dbias, int c_out, void* stream) {
   if (c % 8) return mb_fail(MUNIT_ERR_ARG, "act_bwd: c %% 8");
+  if (dbias && (256 % (c / 8) || c_out > c)) return mb_fail(MUNIT_ERR_ARG, "act_bwd: bias gradient needs 256 %% (c/8) == 0");
   const long long total = (long long)n * h * w * (c / 8);
-  mb_launch(act_bwd_kernel, dim3(grid_for(total)), dim3(256), 0, ST(stream), CBF(g_out), CBF(out_act), pad, act, BF(dy), n, h, w, c);
+  mb_launch(act_bwd_kernel, dim3(grid_for(total)), dim3(256), 0, ST(stream), CBF(g_out), CBF(out_act), pad, act, BF(dy), n, h, w, c,
+            dbias, c_out);
   MB_CHECK_LAUNCH("act_bwd");
   return MUNIT_OK;
 }
@@ -2060,6 +2107,12 @@ int munit_rspace_expand(const float* g, const float* out, void* dr, float* dbias
 int munit_gather_cast(const float* src, const int32_t* idx, void* dst, int64_t n, void* stream) {
   mb_launch(gather_cast_kernel, dim3(grid_for(n)), dim3(256), 0, ST(stream), src, idx, BF(dst), n);
   MB_CHECK_LAUNCH("gather_cast");
+  return MUNIT_OK;
+}
+int munit_gather_cast_multi(const munit_gather_seg* segs, int nseg, int64_t nblocks, void* stream) {
+  if (nseg < 1 || nblocks < 1 || nblocks > 0x7fffffffLL) return mb_fail(MUNIT_ERR_ARG, "gather_cast_multi: nseg / nblocks");
+  mb_launch(gather_cast_multi_kernel, dim3((unsigned)nblocks), dim3(256), 0, ST(stream), segs, nseg);
+  MB_CHECK_LAUNCH("gather_cast_multi");
   return MUNIT_OK;
 }
 int munit_gather_add(const float* src, const int32_t* idx, float* dst, int64_t n, void* stream) {

@@ -329,210 +329,3 @@ def rspace_index_maps(cout, cin, kh, kw, kwp=8, cop=4, ck=64):
     m = fwd >= 0
     inv[fwd[m].long()] = torch.arange(fwd.numel(), dtype=torch.int32)[m]
     return fwd, dg.reshape(-1), inv
-
-
-# ---------------------------------------------------------------------------- nearest-2x upsample + 5x5 conv as phase GEMMs
-# nn.Upsample(scale_factor=2) -> ReflectionPad2d(2) -> Conv2d(k=5) (networks.py:534-545) reads every low-res pixel four
-# times.  Per axis, output row 2i sees the low-res rows (i-1, i, i+1) with the tap sums (w0+w1, w2+w3, w4), row 2i+1
-# sees them with (w0, w1+w2, w3+w4): four 3x3 "phase" convolutions on the low-res input, 9 MACs per output instead of
-# 25.  With *replicate* padding of the low-res input this equals reflect padding of the up-sampled image everywhere
-# except the outermost output row / column on each side (there the two mirrored up-sampled pixels belong to different
-# low-res pixels), which take their own tap sums: top/left (0, w1+w2+w3, w0+w4), bottom/right mirrored.  So: 4 row
-# types x 4 column types = 16 weight sets of 3x3 taps; one 4-phase launch writes every output with the interior sets,
-# then four thin launches (rows 0 and 2H-1, columns 0 and 2W-1) and four one-pixel launches (corners) overwrite the
-# ring.  EXPERIMENTAL (no-grad forward only, MUNIT_UPCONV_PHASE=1): the plans below are verified against F.conv2d by
-# tests/test_geometry.py through the descriptor emulation; GPU validation is the next round's first step.
-UP_ROW_TYPES = {
-    # type -> 3 x 5 matrix A[d][k]: low-res row (i - 1 + d) collects tap k
-    0: [[1, 1, 0, 0, 0], [0, 0, 1, 1, 0], [0, 0, 0, 0, 1]],   # even output row 2i (interior)
-    1: [[1, 0, 0, 0, 0], [0, 1, 1, 0, 0], [0, 0, 0, 1, 1]],   # odd output row 2i+1 (interior)
-    2: [[0, 0, 0, 0, 0], [0, 1, 1, 1, 0], [1, 0, 0, 0, 1]],   # output row 0
-    3: [[1, 0, 0, 0, 1], [0, 1, 1, 1, 0], [0, 0, 0, 0, 0]],   # output row 2H-1
-}
-
-
-def upconv_phase_weights(weight):
-    """weight [Co, Ci, 5, 5] (any float dtype) -> [Co, 16, 3, 3, Ci]: the tap sums of every (row type, column type),
-    type index = 4 * row_type + col_type.  Pure tensor arithmetic (runs on whatever device `weight` lives on)."""
-    import torch
-
-    co, ci, kh, kw = weight.shape
-    assert kh == 5 and kw == 5, "phase decomposition is built for the 5x5 decoder layers"
-    a = torch.tensor([UP_ROW_TYPES[t] for t in range(4)], dtype=weight.dtype, device=weight.device)  # [4, 3, 5]
-    w = weight.permute(0, 2, 3, 1)  # [Co, ky, kx, Ci]
-    rows = (a[None, :, :, :, None, None] * w[:, None, None, :, :, :]).sum(3)          # [Co, rt, dy, kx, Ci]
-    full = (a[None, None, None, :, :, :, None] * rows[:, :, :, None, None, :, :]).sum(5)  # [Co, rt, dy, ct, dx, Ci]
-    return full.permute(0, 1, 3, 2, 4, 5).reshape(co, 16, 3, 3, ci).contiguous()
-
-
-def plan_upconv_phases(n, h, w, c, co_rows, out_geom) -> List[TapGemmPlan]:
-    """Launch list for y = conv5x5(reflect_pad2(nearest_up2(x))).  x is given as [n, h+2, w+2, c] with a *replicate*
-    halo of 1; the weight matrix is [co_rows][16][3][3][c] (upconv_phase_weights, K contiguous); out_geom as in
-    plan_fwd for the [2h, 2w] output.  Launch in list order (later launches overwrite the ring)."""
-    assert c % 64 == 0 and h >= 2 and w >= 2
-    e = 2
-    dims = [c, w + 2, h + 2, n]
-    strides = [e, c * e, (w + 2) * c * e, (h + 2) * (w + 2) * c * e]
-    o_sn, o_sy, o_sx, y_off, x_off = out_geom
-    bn = pick_bn(co_rows)
-    kper = 9 * c
-
-    def launch(i0, nh, j0, nw, phases):
-        tw, th, tn = pick_tile(nw, nh, n, 128)
-        taps = [[0, j0 + dx, i0 + dy, 0] for dy in range(3) for dx in range(3)]
-        return TapGemmPlan(
-            a_rank=4, a_dim=dims, a_stride=strides, a_box=[64, tw, th, tn], b_rows=co_rows, b_k=16 * kper, bn=bn,
-            tw=tw, th=th, tn=tn, out_w=nw, out_h=nh, n_img=n, mx=[0, 1, 0, 0], my=[0, 0, 1, 0], mn=[0, 0, 0, 1],
-            num_taps=9, chunks=c // 64, tap_off=taps, phases=len(phases),
-            b_k0=[(4 * rt + ct) * kper for rt, ct, _, _ in phases],
-            o_yoff=[2 * i0 + py + y_off for _, _, py, _ in phases], o_xoff=[2 * j0 + px + x_off for _, _, _, px in phases],
-            o_sn=o_sn, o_sy=o_sy, o_sx=o_sx, o_ymul=2, o_xmul=2, n_store=co_rows)
-
-    plans = [launch(0, h, 0, w, [(py, px, py, px) for py in (0, 1) for px in (0, 1)])]   # interior sets everywhere
-    plans.append(launch(0, 1, 0, w, [(2, 0, 0, 0), (2, 1, 0, 1)]))                          # output row 0
-    plans.append(launch(h - 1, 1, 0, w, [(3, 0, 1, 0), (3, 1, 1, 1)]))                      # output row 2h-1
-    plans.append(launch(0, h, 0, 1, [(0, 2, 0, 0), (1, 2, 1, 0)]))                          # output column 0
-    plans.append(launch(0, h, w - 1, 1, [(0, 3, 0, 1), (1, 3, 1, 1)]))                      # output column 2w-1
-    for i0, rt, py in ((0, 2, 0), (h - 1, 3, 1)):                                           # corners
-        for j0, ct, px in ((0, 2, 0), (w - 1, 3, 1)):
-            plans.append(launch(i0, 1, j0, 1, [(rt, ct, py, px)]))
-    flops = 2.0 * n * (2 * h) * (2 * w) * co_rows * 25 * c
-    for p in plans:
-        p.alg_flops = 0.0
-    plans[0].alg_flops = flops  # direct-form work of the layer, booked on the main launch
-    return plans
-
-
-def upconv_dgrad_index_map(co, ci, c_rows, ck):
-    """Index map into the [Co][16][3][3][Ci] phase-weight tensor for the interior dgrad matrix of the phase form:
-    [c_rows (ci)][36 taps = (py, px, dy, dx)][ck (co)]  <-  wph[co, 4*py + px, dy, dx, ci]."""
-    import torch
-
-    src = torch.arange(co * 16 * 9 * ci, dtype=torch.int32).view(co, 16, 3, 3, ci)
-    idx = torch.full((c_rows, 2, 2, 3, 3, ck), -1, dtype=torch.int32)
-    for py in range(2):
-        for px in range(2):
-            idx[:ci, py, px, :, :, :co] = src[:, 4 * py + px].permute(3, 1, 2, 0)
-    return idx.reshape(-1)
-
-
-def plan_upconv_dgrad_interior(n, h, w, c_rows, co_c) -> TapGemmPlan:
-    """Interior part of the phase-form input gradient: dy0 [n, 2h, 2w, co_c] (the gradient of the conv output with
-    its outermost ring ZEROED -- the ring pixels use other tap sums and are handled separately) ->
-    dxr [n, h+2, w+2, c_rows], the gradient w.r.t. the replicate-padded low-res input (every position written).
-    dy0 is read through a space-to-depth view [2*co, w, 2, h, n]; 36 taps (py, px, dy, dx)."""
-    assert co_c % 64 == 0
-    e = 2
-    dims = [2 * co_c, w, 2, h, n]
-    strides = [e, 2 * co_c * e, 2 * w * co_c * e, 4 * w * co_c * e, 4 * h * w * co_c * e]
-    oh, ow = h + 2, w + 2
-    tw, th, tn = pick_tile(ow, oh, n, 128)
-    taps = [[px * co_c, -dx, py, -dy, 0] for py in range(2) for px in range(2) for dy in range(3) for dx in range(3)]
-    return TapGemmPlan(
-        a_rank=5, a_dim=dims, a_stride=strides, a_box=[64, tw, 1, th, tn], b_rows=c_rows, b_k=36 * co_c,
-        bn=pick_bn(c_rows), tw=tw, th=th, tn=tn, out_w=ow, out_h=oh, n_img=n, mx=[0, 1, 0, 0, 0], my=[0, 0, 0, 1, 0],
-        mn=[0, 0, 0, 0, 1], num_taps=36, chunks=co_c // 64, tap_off=taps, phases=1, b_k0=[0], o_yoff=[0], o_xoff=[0],
-        o_sn=oh * ow * c_rows, o_sy=ow * c_rows, o_sx=c_rows, o_ymul=1, o_xmul=1, n_store=c_rows)
-
-
-def plan_upconv_wgrad_interior(n, h, w, c, co_c, py, px) -> WgradPlan:
-    """Interior part of the phase-form weight gradient for output phase (py, px): accumulates
-    dwph[co][4*py + px][dy][dx][ci] += sum_{i,j} dy0[2i+py, 2j+px][co] * xr[i+dy, j+dx][ci] into the phase-gradient
-    scratch [co][16][3][3][ci] (dy0 ring-zeroed as in plan_upconv_dgrad_interior; xr = replicate-padded low-res
-    input [n, h+2, w+2, c]).  The caller offsets the dy0 base pointer by (py*2w + px)*co_c elements; the view
-    below then walks every second row / column."""
-    e = 2
-    pw, ph, pn = pick_tile(w, h, n, 64)
-    taps = [[0, dx, dy, 0] for dy in range(3) for dx in range(3)]
-    return WgradPlan(
-        a_rank=4, a_dim=[co_c, w, h, n], a_stride=[e, 2 * co_c * e, 4 * w * co_c * e, 4 * h * w * co_c * e],
-        a_box=[64, pw, ph, pn], a_mx=[0, 1, 0, 0], a_my=[0, 0, 1, 0], a_mn=[0, 0, 0, 1],
-        b_rank=4, b_dim=[c, w + 2, h + 2, n], b_stride=[e, c * e, (w + 2) * c * e, (h + 2) * (w + 2) * c * e],
-        b_box=[64, pw, ph, pn], b_mx=[0, 1, 0, 0], b_my=[0, 0, 1, 0], b_mn=[0, 0, 0, 1],
-        pw=pw, ph=ph, pn=pn, out_w=w, out_h=h, n_img=n, m_total=co_c, n_total=c, bn=128 if c % 128 == 0 else 64,
-        num_taps=9, tap_off=taps, s_m=16 * 9 * c, s_t=c, s_n=1)
-
-
-# Ring share of the phase-form backward.  The outermost output row / column on each side is cut out of dY into
-# strips with the four corner pixels zeroed (they have their own (first|last, first|last) types and are too few for
-# a GEMM):   top / bottom strip [n, 2w, co]   (output rows 0 and 2h-1),   left / right strip [n, 2h, co].
-# side: 0 top, 1 bottom, 2 left, 3 right; its row (or column) type is 2 (first) for top / left, 3 (last) otherwise.
-def upconv_ring_dgrad_index_map(co, ci, c_rows, ck, side):
-    """[c_rows (ci)][3 phases (the strip-normal offset d)][6 taps = (p, e)][ck (co)]: p the parity along the strip,
-    e the tap along the strip  <-  wph[co, type, dy, dx, ci] with (dy, dx) = (d, e) for top / bottom, (e, d) for
-    left / right and type = 4*rt + p (top / bottom) or 4*p + ct (left / right)."""
-    import torch
-
-    src = torch.arange(co * 16 * 9 * ci, dtype=torch.int32).view(co, 16, 3, 3, ci)
-    t = 2 if side in (0, 2) else 3
-    idx = torch.full((c_rows, 3, 2, 3, ck), -1, dtype=torch.int32)
-    for d in range(3):
-        for p in range(2):
-            for e_ in range(3):
-                if side < 2:
-                    v = src[:, 4 * t + p, d, e_]
-                else:
-                    v = src[:, 4 * p + t, e_, d]
-                idx[:ci, d, p, e_, :co] = v.t()
-    return idx.reshape(-1)
-
-
-def plan_upconv_dgrad_ring(n, h, w, c_rows, co_c, side) -> TapGemmPlan:
-    """strip -> its contribution to the gradient of the replicate-padded low-res input, as a 3-wide band:
-    top / bottom: band [n, 3, w+2, c_rows] = rows (0..2) / (h-1 .. h+1) of dxr; left / right: [n, h+2, 3, c_rows] =
-    columns (0..2) / (w-1 .. w+1).  Phase d writes band line d; 6 taps (parity, tap along the strip)."""
-    assert co_c % 64 == 0
-    e = 2
-    horiz = side < 2
-    length = w if horiz else h            # low-res extent along the strip
-    dims = [2 * co_c, length, 1, n]
-    strides = [e, 2 * co_c * e, 2 * length * co_c * e, 2 * length * co_c * e]
-    ol = length + 2
-    taps = [[p * co_c, -e_, 0, 0] for p in range(2) for e_ in range(3)]
-    if horiz:
-        ow, oh = ol, 1
-        o_sn, o_sy, o_sx = 3 * ol * c_rows, ol * c_rows, c_rows
-        mx, my = [0, 1, 0, 0], [0, 0, 1, 0]
-        yoff, xoff = [0, 1, 2], [0, 0, 0]
-    else:
-        ow, oh = 1, ol
-        o_sn, o_sy, o_sx = ol * 3 * c_rows, 3 * c_rows, c_rows
-        mx, my = [0, 0, 1, 0], [0, 1, 0, 0]   # the GEMM's y walks the strip
-        yoff, xoff = [0, 0, 0], [0, 1, 2]
-    tw, th, tn = pick_tile(ow, oh, n, 128)
-    box = [64, tw, 1, tn] if horiz else [64, th, 1, tn]
-    return TapGemmPlan(
-        a_rank=4, a_dim=dims, a_stride=strides, a_box=box, b_rows=c_rows, b_k=3 * 6 * co_c, bn=pick_bn(c_rows),
-        tw=tw, th=th, tn=tn, out_w=ow, out_h=oh, n_img=n, mx=mx, my=my, mn=[0, 0, 0, 1], num_taps=6,
-        chunks=co_c // 64, tap_off=taps, phases=3, b_k0=[d * 6 * co_c for d in range(3)], o_yoff=yoff, o_xoff=xoff,
-        o_sn=o_sn, o_sy=o_sy, o_sx=o_sx, o_ymul=1, o_xmul=1, n_store=c_rows)
-
-
-def plan_upconv_wgrad_ring(n, h, w, c, co_c, side, p) -> WgradPlan:
-    """Ring share of the phase-weight gradient: strip pixels of parity p along the strip against the three low-res
-    rows (columns) they read.  Accumulates into the [co][16][3][3][ci] scratch at type 4*rt + p (top / bottom) or
-    4*p + ct (left / right); the caller offsets the strip base pointer by p*co_c elements and the scratch pointer by
-    type*9*c.  xr: replicate-padded low-res input [n, h+2, w+2, c]."""
-    e = 2
-    horiz = side < 2
-    length = w if horiz else h
-    line0 = 0 if side in (0, 2) else ((h - 1) if horiz else (w - 1))   # first of the three xr rows / columns read
-    if horiz:
-        pw, ph, pn = pick_tile(length, 1, n, 64)
-        a_mx, a_my = [0, 1, 0, 0], [0, 0, 1, 0]
-        taps = [[0, dx, line0 + dy, 0] for dy in range(3) for dx in range(3)]
-        a_box = [64, pw, 1, pn]
-        ow, oh = length, 1
-    else:
-        pw, ph, pn = pick_tile(1, length, n, 64)
-        a_mx, a_my = [0, 0, 1, 0], [0, 1, 0, 0]
-        taps = [[0, line0 + dx, dy, 0] for dy in range(3) for dx in range(3)]
-        a_box = [64, ph, 1, pn]
-        ow, oh = 1, length
-    return WgradPlan(
-        a_rank=4, a_dim=[co_c, length, 1, n], a_stride=[e, 2 * co_c * e, 2 * length * co_c * e, 2 * length * co_c * e],
-        a_box=a_box, a_mx=a_mx, a_my=a_my, a_mn=[0, 0, 0, 1],
-        b_rank=4, b_dim=[c, w + 2, h + 2, n], b_stride=[e, c * e, (w + 2) * c * e, (h + 2) * (w + 2) * c * e],
-        b_box=[64, pw, ph, pn], b_mx=[0, 1, 0, 0], b_my=[0, 0, 1, 0], b_mn=[0, 0, 0, 1],
-        pw=pw, ph=ph, pn=pn, out_w=ow, out_h=oh, n_img=n, m_total=co_c, n_total=c, bn=128 if c % 128 == 0 else 64,
-        num_taps=9, tap_off=taps, s_m=16 * 9 * c, s_t=c, s_n=1)

@@ -408,12 +408,18 @@ def norm_bwd(g_out, out_pad, upsample, y, coef, relu, mode, p_w, ldw, g_w, g_b, 
     return norm_bwd_apply(g_out, out_pad, upsample, y, coef, relu, k, want_res, res_pad)
 
 
-def act_bwd(g_out, out_act, pad, act):
+def act_bwd_takes_bias(c):
+    return 256 % (c // 8) == 0
+
+
+def act_bwd(g_out, out_act, pad, act, dbias=None, c_out=None):
+    """dbias (fp32, optional): += column sums of the result over the first c_out channels (the bias gradient)."""
     n, hp, wp, c = out_act.shape
     h, w = hp - 2 * pad, wp - 2 * pad
     dy = torch.empty(n, h, w, c, dtype=torch.bfloat16, device=g_out.device)
-    check(lib.munit_act_bwd(g_out.data_ptr(), out_act.data_ptr(), pad, ACT[act], dy.data_ptr(), n, h, w, c, _stream()),
-          "act_bwd")
+    assert dbias is None or act_bwd_takes_bias(c)
+    check(lib.munit_act_bwd(g_out.data_ptr(), out_act.data_ptr(), pad, ACT[act], dy.data_ptr(), n, h, w, c,
+                            _ptr(dbias), c if c_out is None else c_out, _stream()), "act_bwd")
     _count()
     return dy
 
@@ -457,6 +463,26 @@ def gather_add(src, idx, dst):
     check(lib.munit_gather_add(src.data_ptr(), idx.data_ptr(), dst.data_ptr(), dst.numel(), _stream()), "gather_add")
     _count()
     return dst
+
+
+GATHER_BLOCK = 2048  # MUNIT_GATHER_BLOCK
+
+
+def gather_seg_table(segs, device):
+    """segs: list of (src fp32 tensor, idx int32 tensor or None, dst bf16 tensor) -> (device table, nseg, nblocks) for
+    gather_cast_multi (munit_gather_seg: src, idx, dst, n, block0 as five 64-bit words)."""
+    rows, b0 = [], 0
+    for src, idx, dst in segs:
+        n = dst.numel()
+        assert idx is None or idx.numel() == n
+        rows.append([src.data_ptr(), 0 if idx is None else idx.data_ptr(), dst.data_ptr(), n, b0])
+        b0 += (n + GATHER_BLOCK - 1) // GATHER_BLOCK
+    return torch.tensor(rows, dtype=torch.int64).to(device), len(rows), b0
+
+
+def gather_cast_multi(table, nseg, nblocks):
+    check(lib.munit_gather_cast_multi(table.data_ptr(), nseg, nblocks, _stream()), "gather_cast_multi")
+    _count()
 
 
 def cast_bf16(src, dst):
@@ -680,12 +706,3 @@ def mse_const_bwd(x, target, gscale_dev, scale):
                                   x.numel(), _stream()), "mse_const_bwd")
     _count()
     return dx
-
-
-def halo_fill_replicate(act, pad):
-    """Replicate halo in place (experimental phase form of upsample + 5x5 conv)."""
-    n, hp, wp, c = act.shape
-    check(lib.munit_halo_fill_replicate(act.data_ptr(), n, hp - 2 * pad, wp - 2 * pad, c, pad, _stream()),
-          "halo_fill_replicate")
-    _count()
-    return act

@@ -153,17 +153,13 @@ class Conv2dBlock(nn.Module):
 
     # -- internal fast path ---------------------------------------------------------------
     def forward_act(self, x, out_pad: int = 0, upsample: int = 1, residual: Optional[Act] = None,
-                    frozen: bool = False, pending_up: bool = False) -> Act:
-        """x: Act (any halo) or an NCHW fp32 image for the first (Cin<64) layers.  pending_up (experimental,
-        ops.UPCONV_PHASE): x is the *low-res* act with a halo of 1 and this 5x5 layer applies the nearest-2x
-        upsample itself, as phase GEMMs."""
+                    frozen: bool = False) -> Act:
+        """x: Act (any halo) or an NCHW fp32 image for the first (Cin<64) layers."""
         layer = self.layer
         if isinstance(x, Act):
             if layer.first:
                 raise ValueError("image-space layer expects an NCHW tensor")
-            if pending_up:
-                assert x.pad == 1 and self.norm_type != "none" and ops.upconv_phase_ok(layer)
-            elif x.pad != self.padding:
+            if x.pad != self.padding:
                 x = Act(ops.RepadFn.apply(x.t, x.pad, self.padding), self.padding)
             xin = x.t
         elif layer.first:
@@ -182,13 +178,8 @@ class Conv2dBlock(nn.Module):
             return Act(out, out_pad)
         # a per-channel bias is cancelled exactly by the mean subtraction of IN / AdaIN: skip it
         bias = b if self.norm_type == "ln" else None
-        if pending_up:
-            y = (ops.UpConvPhaseFn.apply(xin, w, bias, layer) if torch.is_grad_enabled()
-                 else ops.upconv_phase_forward(xin, w, bias, layer))
-            part, y_f16 = None, False
-        else:
-            y_f16 = True  # raw conv output in front of a norm: fp16 bits (ops.ConvFn)
-            y, part = ops.ConvFn.apply(xin, w, bias, layer, "none", 0, self.padding, 2 if self.norm_type == "ln" else 1)
+        y_f16 = True  # raw conv output in front of a norm: fp16 bits (ops.ConvFn)
+        y, part = ops.ConvFn.apply(xin, w, bias, layer, "none", 0, self.padding, 2 if self.norm_type == "ln" else 1)
         n = y.shape[0]
         if self.norm_type == "in":
             p_w = p_b = None
@@ -282,28 +273,20 @@ def run_chain(mods, x, final_pad: int = 0, frozen: bool = False) -> Act:
     nearest-2x upsample, networks.py:534) that its consumer needs, so neither is ever a separate op."""
     flat = _flatten(mods)
     i = 0
-    pending_up = False
     while i < len(flat):
         m = flat[i]
         j, up = i + 1, 1
         if j < len(flat) and isinstance(flat[j], nn.Upsample):
             up, j = 2, j + 1
         next_pad = _required_pad(flat[j]) if j < len(flat) else final_pad
-        # experimental phase form: the consumer upsamples (low-res act with a halo of 1 instead of 4x the pixels)
-        defer = (up == 2 and j < len(flat) and isinstance(flat[j], Conv2dBlock) and flat[j].norm_type != "none"
-                 and ops.upconv_phase_ok(flat[j].layer))
-        if defer:
-            up, next_pad = 1, 1
         if isinstance(m, Conv2dBlock):
-            x = m.forward_act(x, next_pad, up, frozen=frozen, pending_up=pending_up)
+            x = m.forward_act(x, next_pad, up, frozen=frozen)
         elif isinstance(m, ResBlock):
-            assert not pending_up
             x = m.forward_act(x, next_pad, up)
         elif isinstance(m, nn.Upsample):
             raise ValueError("nn.Upsample must follow a normalised block (it is fused into its producer)")
         else:
             raise ValueError(f"unsupported module in chain: {type(m).__name__}")
-        pending_up = defer
         i = j
     return x
 

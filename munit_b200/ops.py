@@ -16,6 +16,7 @@ from typing import Optional
 import torch
 
 import os
+import weakref
 
 from . import geometry as G
 from . import kernels as K
@@ -147,6 +148,37 @@ def _grad_like_cl(weight: torch.Tensor) -> torch.Tensor:
         memory_format=torch.channels_last)
 
 
+# Layers whose bf16 shadows exist, keyed by the address of their fp32 master.  An optimiser refreshes every shadow of
+# its arena with ONE launch right after the parameter update (refresh_shadows) instead of one or two launches per layer
+# at the next use (reference: the fp32 nn.Conv2d weights are used directly, networks.py:688).
+_SHADOWED = weakref.WeakValueDictionary()
+_SHADOW_GEN = [0]
+
+
+def refresh_shadows(opt, params):
+    """Called by optim.FlatAdam after it changed `params` (and bumped their versions).  No-op for layers not built
+    yet; inside a graph capture the segment table must already exist (it is built by the eager warm-up steps)."""
+    cache = getattr(opt, "_shadow_cache", None)
+    if cache is None or cache[0] != _SHADOW_GEN[0]:
+        if torch.cuda.is_current_stream_capturing():
+            return  # stale table and no way to upload one here: the lazy per-layer path serves this capture
+        layers, segs = [], []
+        for p in params:
+            layer = _SHADOWED.get(p.data_ptr())
+            seg = layer.shadow_segments(p) if layer is not None else None
+            if seg:
+                layers.append((layer, p))
+                segs += seg
+        table = K.gather_seg_table(segs, params[0].device) if segs else None
+        cache = opt._shadow_cache = (_SHADOW_GEN[0], layers, table, segs)
+    _, layers, table, _ = cache
+    if table is None:
+        return
+    K.gather_cast_multi(*table)
+    for layer, p in layers:
+        layer._wver = (p._version, p.data_ptr())
+
+
 class ConvLayer:
     """Per-convolution host state: geometry, bf16 weight shadows, cached plans.  Not an nn.Module --
     owned by Conv2dBlock next to the nn.Conv2d that holds the fp32 master parameters."""
@@ -168,7 +200,7 @@ class ConvLayer:
             self.c_buf = cin
         self.co_rows = 32 if self.last else ((cout + 15) // 16) * 16
         self.ck = max(64, self.co_rows)  # K extent per tap of the dgrad matrix
-        self._ver = None
+        self._wver = self._bver = None
         self.w_fwd = self.w_dg = self.bias_p = None
         self._idx_fwd = self._idx_dg = self._idx_inv = None
         self._plans = {}
@@ -196,30 +228,45 @@ class ConvLayer:
         self._identity_fwd = (not c.first) and c.co_rows == c.cout
 
     def refresh(self, weight, bias, force=False):
-        """(Re)build the bf16 GEMM operands from the fp32 master weights when they changed."""
-        ver = (weight._version, weight.data_ptr(), None if bias is None else bias._version)
-        if not force and ver == self._ver:
-            return
-        dev = weight.device
-        if self._idx_fwd is None or self._idx_fwd.device != dev:
-            self._build_maps(dev)
-            self.w_fwd = torch.empty(self.co_rows, self._idx_fwd.numel() // self.co_rows, dtype=torch.bfloat16,
-                                     device=dev)
-            rows = 64 if self.first else self.cin
-            self.w_dg = torch.empty(rows, self._idx_dg.numel() // rows, dtype=torch.bfloat16, device=dev)
-            self.bias_p = torch.zeros(self.co_rows, dtype=torch.float32, device=dev)
-        src = _cl_weight(weight.detach())
-        if self._identity_fwd:
-            K.cast_bf16(src, self.w_fwd)
-        else:
-            K.gather_cast(src, self._idx_fwd, self.w_fwd)
-        K.gather_cast(src, self._idx_dg, self.w_dg)
+        """(Re)build the bf16 GEMM operands from the fp32 master weights when they changed.  After an optimiser step
+        refresh_shadows() has normally done it already (one launch for the whole arena) and this is a no-op."""
+        wver = (weight._version, weight.data_ptr())
+        if force or wver != self._wver:
+            dev = weight.device
+            rebuilt = self._idx_fwd is None or self._idx_fwd.device != dev
+            if rebuilt:
+                self._build_maps(dev)
+                self.w_fwd = torch.empty(self.co_rows, self._idx_fwd.numel() // self.co_rows, dtype=torch.bfloat16,
+                                         device=dev)
+                rows = 64 if self.first else self.cin
+                self.w_dg = torch.empty(rows, self._idx_dg.numel() // rows, dtype=torch.bfloat16, device=dev)
+                self.bias_p = torch.zeros(self.co_rows, dtype=torch.float32, device=dev)
+            src = _cl_weight(weight.detach())
+            if self._identity_fwd:
+                K.cast_bf16(src, self.w_fwd)
+            else:
+                K.gather_cast(src, self._idx_fwd, self.w_fwd)
+            K.gather_cast(src, self._idx_dg, self.w_dg)
+            self._wver = wver
+            if rebuilt or _SHADOWED.get(wver[1]) is not self:
+                _SHADOWED[wver[1]] = self
+                _SHADOW_GEN[0] += 1
         if bias is not None and not self.last:
             if self.co_rows == self.cout:
-                self.bias_p = bias.detach()
+                self.bias_p = bias.detach()  # a view of the master: always current
             else:
-                self.bias_p[: self.cout].copy_(bias.detach())
-        self._ver = ver
+                bver = (bias._version, bias.data_ptr())
+                if force or bver != self._bver:
+                    self.bias_p[: self.cout].copy_(bias.detach())
+                    self._bver = bver
+
+    def shadow_segments(self, weight):
+        """(src, idx, dst) triples of this layer's shadows for kernels.gather_seg_table, or None when the master is not
+        stored channels_last in place (then the lazy path of refresh() keeps serving it)."""
+        src = _cl_weight(weight.detach())
+        if src.data_ptr() != weight.data_ptr() or self._idx_fwd is None or self._idx_fwd.device != weight.device:
+            return None
+        return [(src, None if self._identity_fwd else self._idx_fwd, self.w_fwd), (src, self._idx_dg, self.w_dg)]
 
     # ---- plans ----------------------------------------------------------------------------
     def plans(self, n, hp, wp, out_pad):
@@ -251,80 +298,6 @@ class ConvLayer:
             p = (fwd, dg, wg, ho, wo)
             self._plans[key] = p
         return p
-
-
-# EXPERIMENTAL, off by default: nearest-2x upsample + 5x5 conv as 3x3 phase GEMMs on the low-res input (36 % of
-# the MACs, a quarter of the activation bytes; munit_b200/upconv.py).  MUNIT_UPCONV_PHASE=1: no-grad forward passes
-# only (inference, the generator pass of dis_update); =2: training too (backward in phase form, its glue still plain
-# tensor arithmetic).  Launch plans and the whole forward / backward orchestration are verified on the CPU through
-# the descriptor emulation (tests/test_geometry.py, tests/test_upconv_cpu.py); the GPU path has not run on a B200
-# yet -- tests/test_conv_gpu.py::test_upconv_phase_* are skipped unless the switch is set.
-UPCONV_PHASE = int(os.environ.get("MUNIT_UPCONV_PHASE", "0") or 0)
-
-
-def upconv_phase_ok(layer: "ConvLayer") -> bool:
-    lvl = int(UPCONV_PHASE)
-    if not lvl or (lvl < 2 and torch.is_grad_enabled()):
-        return False
-    return (layer.k == 5 and layer.stride == 1 and layer.pad == 2 and not layer.first and not layer.last
-            and not layer.zpad and layer.co_rows == layer.cout and layer.cout % 64 == 0)
-
-
-def _upconv_refresh(layer: "ConvLayer", weight, bias, c):
-    """bf16 phase-weight matrix [co_rows][16*9*c] (+ fp32 bias) of a 5x5 layer, rebuilt when the master changed."""
-    ver = (weight._version, weight.data_ptr(), None if bias is None else bias._version)
-    if getattr(layer, "_up_ver", None) != ver:
-        wph = G.upconv_phase_weights(weight.detach().float())                    # [Co, 16, 3, 3, Ci] fp32
-        layer.w_up = wph.reshape(layer.cout, -1).to(torch.bfloat16).contiguous()
-        layer._up_bias = bias.detach().float().contiguous() if bias is not None else None
-        layer._up_ver = ver
-
-
-def upconv_phase_forward(x_lo: torch.Tensor, weight, bias, layer: "ConvLayer") -> torch.Tensor:
-    """x_lo: [N, H+2, W+2, C] low-res act whose interior is valid (the halo is rewritten here with replicate
-    padding, in place).  Returns the raw conv output [N, 2H, 2W, co_rows] of Upsample(2) -> reflect pad 2 -> 5x5 conv."""
-    from . import upconv
-
-    K.halo_fill_replicate(x_lo, 1)
-    _upconv_refresh(layer, weight, bias, x_lo.shape[3])
-    return upconv.forward(upconv.GpuLauncher(), x_lo, layer.w_up, layer._up_bias, layer.co_rows)
-
-
-class UpConvPhaseFn(torch.autograd.Function):
-    """Training form of upconv_phase_forward: forward as above, backward through upconv.backward (interior and
-    ring launches of the tap-GEMM / wgrad kernels; the gradient returned for x_lo has a zero halo, which is what
-    the producing norm's reflect-halo fold needs)."""
-
-    @staticmethod
-    def forward(ctx, x_lo, weight, bias, layer: ConvLayer):
-        out = upconv_phase_forward(x_lo, weight, bias, layer)
-        ctx.layer, ctx.has_bias = layer, bias is not None
-        ctx.wbuf, ctx.bbuf = _param_grad_buf(weight), _param_grad_buf(bias)
-        _track_use(ctx, ctx.needs_input_grad[1], ctx.wbuf, ctx.bbuf)
-        ctx.save_for_backward(x_lo, weight)
-        return out
-
-    @staticmethod
-    def backward(ctx, g_out):
-        from . import upconv
-
-        layer: ConvLayer = ctx.layer
-        x_lo, weight = ctx.saved_tensors
-        dy = g_out.contiguous()  # (its ring is zeroed in place below: this node is the only consumer of g_out)
-        gb = gw = None
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            tgt = ctx.bbuf if ctx.bbuf is not None else torch.zeros(layer.cout, dtype=torch.float32, device=dy.device)
-            K.colsum(dy, tgt, layer.cout)
-            gb = None if ctx.bbuf is not None else tgt
-        wph32 = G.upconv_phase_weights(weight.detach().float())
-        gx, dw5 = upconv.backward(upconv.GpuLauncher(), dy, x_lo, wph32, need_dx=ctx.needs_input_grad[0],
-                                  need_dw=ctx.needs_input_grad[1])
-        if dw5 is not None:
-            tgt = ctx.wbuf if ctx.wbuf is not None else _grad_like_cl(weight)
-            _cl_weight(tgt).add_(dw5.reshape(-1))
-            gw = None if ctx.wbuf is not None else tgt
-        _track_done(ctx)
-        return gx, gw, gb, None
 
 
 def _want_halo(kh, kw, out_h, out_w) -> int:
@@ -393,16 +366,20 @@ class ConvFn(torch.autograd.Function):
         n, hp, wp, _ = gemm_in.shape
         _, dg, wg, ho, wo = layer.plans(n, hp, wp, ctx.out_pad)
         g_out = g_out.contiguous()
-        if ctx.act != "none" or ctx.out_pad > 0:
-            dy = K.act_bwd(g_out, out, ctx.out_pad, ctx.act)
-        else:
-            dy = g_out
-        gx = gw = gb = None
+        gx = gw = gb = tgt = None
         if ctx.has_bias and ctx.needs_input_grad[2]:
             buf = ctx.bbuf
-            tgt = buf if buf is not None else torch.zeros(layer.cout, dtype=torch.float32, device=dy.device)
-            K.colsum(dy, tgt, layer.cout)
+            tgt = buf if buf is not None else torch.zeros(layer.cout, dtype=torch.float32, device=g_out.device)
             gb = None if buf is not None else tgt
+        if ctx.act != "none" or ctx.out_pad > 0:
+            fused = tgt is not None and K.act_bwd_takes_bias(out.shape[3])  # bias gradient in the same pass
+            dy = K.act_bwd(g_out, out, ctx.out_pad, ctx.act, tgt if fused else None, layer.cout)
+            if fused:
+                tgt = None
+        else:
+            dy = g_out
+        if tgt is not None:
+            K.colsum(dy, tgt, layer.cout)
         if ctx.needs_input_grad[0]:
             rows = 64 if layer.first else layer.cin
             dxp = torch.empty(n, hp, wp, rows, dtype=torch.bfloat16, device=dy.device)

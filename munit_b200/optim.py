@@ -109,7 +109,11 @@ class FlatAdam(Optimizer):
         K.adam(self.p_arena, self.g_arena, self.m_arena, self.v_arena, self.saved_arena, None, mode, save, g["lr"],
                g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self.step_count, self.grad_scale,
                self.hyper_dev)
-        _bump_versions(self._all_params())
+        ps = self._all_params()
+        _bump_versions(ps)
+        from . import ops  # (ops does not import optim)
+
+        ops.refresh_shadows(self, ps)  # every bf16 weight shadow of this arena, one launch
 
     # ------------------------------------------------------------------ CUDA-graph support
     HYPER_RING = 32

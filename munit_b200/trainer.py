@@ -120,26 +120,37 @@ class MUNIT_Trainer(nn.Module):
         self.parallel_streams = False
         self.wgrad_overlap = False  # with parallel_streams: weight gradients on companion streams (ops.wgrad_async)
         self._side = None
+        self._side_used = 0
 
-    def _fork_join(self, fa, fb):
-        """fa() on the current stream, fb() on the side stream, then join.  Fork/join discipline keeps the
-        caching allocator safe: every side-stream region starts after all earlier work of the main stream."""
+    def _fork_join(self, fa, *fbs):
+        """fa() on the current stream, every other function on its own side stream, then join.  Fork/join discipline
+        keeps the caching allocator safe: every side-stream region starts after all earlier work of the main stream."""
         if not self.parallel_streams:
-            return fa(), fb()
+            return (fa(),) + tuple(f() for f in fbs)
         cur = torch.cuda.current_stream()
         if self._side is None:
-            self._side = torch.cuda.Stream()
-        side = self._side
-        side.wait_stream(cur)
-        ra = fa()
-        with torch.cuda.stream(side):
-            rb = fb()
-        cur.wait_stream(side)
-        return ra, rb
+            self._side = []
+        while len(self._side) < len(fbs):
+            self._side.append(torch.cuda.Stream())
+        sides = self._side[:len(fbs)]
+        self._side_used = max(self._side_used, len(sides))
+        for side in sides:
+            side.wait_stream(cur)
+        res = [fa()]
+        for side, f in zip(sides, fbs):
+            with torch.cuda.stream(side):
+                res.append(f())
+        for side in sides:
+            cur.wait_stream(side)
+        return tuple(res)
 
     def _join_side(self):
         if self.parallel_streams and self._side is not None:
-            torch.cuda.current_stream().wait_stream(self._side)
+            # only the streams forked since the last join (backward nodes run on their forward streams); a stream
+            # that took no part in the current graph capture must not be waited on
+            for side in self._side[:self._side_used]:
+                torch.cuda.current_stream().wait_stream(side)
+            self._side_used = 0
         ops.join_side_streams()
         ops.wgrad_join()
 
@@ -207,8 +218,10 @@ class MUNIT_Trainer(nn.Module):
             return Act(torch.cat([u.t, v.t], 0), u.pad)
 
         xab_cat = torch.cat([x_a, x_b], 0)
-        (c_a, s_both), c_b = self._fork_join(lambda: (g.enc1_content.forward_act(x_a, 1), g.enc_style(xab_cat)),
-                                             lambda: g.enc2_content.forward_act(x_b, 1))
+        # (the shared style encoder is independent of both content encoders: third stream)
+        c_a, c_b, s_both = self._fork_join(lambda: g.enc1_content.forward_act(x_a, 1),
+                                           lambda: g.enc2_content.forward_act(x_b, 1),
+                                           lambda: g.enc_style(xab_cat))
         s_a_prime, s_b_prime = s_both[:b], s_both[b:]
         sty_a = s_a if self.guided == 0 else s_a_prime   # style used for the cross-domain decode into a
         sty_b = s_b if self.guided == 0 else s_b_prime
@@ -229,9 +242,9 @@ class MUNIT_Trainer(nn.Module):
             stage12 = self._gen_forward_stage12(x_a, x_b, s_a, s_b)
         c_a, s_a_prime, c_b, s_b_prime, x_a_recon, x_b_recon, x_ba, x_ab = stage12
         xre_cat = torch.cat([x_ba, x_ab], 0)
-        (c_b_recon, s_re), c_a_recon = self._fork_join(
-            lambda: (g.enc1_content.forward_act(x_ba, 1), g.enc_style(xre_cat)),
-            lambda: g.enc2_content.forward_act(x_ab, 1))
+        c_b_recon, c_a_recon, s_re = self._fork_join(lambda: g.enc1_content.forward_act(x_ba, 1),
+                                                     lambda: g.enc2_content.forward_act(x_ab, 1),
+                                                     lambda: g.enc_style(xre_cat))
         s_a_recon, s_b_recon = s_re[:b], s_re[b:]
         return (c_a, s_a_prime, c_b, s_b_prime, x_a_recon, x_b_recon, x_ba, x_ab, c_b_recon, s_a_recon, c_a_recon,
                 s_b_recon)

@@ -1,18 +1,16 @@
 """networks.run_chain scheduling on the CPU (no kernels run: the blocks' forward_act is replaced by recorders):
-which producer writes which halo / upsample for its consumer -- the default schedule, and the experimental
-phase-form schedule (ops.UPCONV_PHASE) in which the 5x5 consumers upsample themselves in no-grad passes."""
+which producer writes which halo / upsample for its consumer."""
 import torch
 
 from munit_b200 import networks as N
-from munit_b200 import ops
 from munit_b200.ops import Act
 
 
 def _record(monkeypatch):
     calls = []
 
-    def conv_fa(self, x, out_pad=0, upsample=1, residual=None, frozen=False, pending_up=False):
-        calls.append(("conv%d" % self.layer.k, out_pad, upsample, pending_up))
+    def conv_fa(self, x, out_pad=0, upsample=1, residual=None, frozen=False):
+        calls.append(("conv%d" % self.layer.k, out_pad, upsample, False))
         return x
 
     def res_fa(self, x, out_pad=0, upsample=1):
@@ -39,22 +37,3 @@ def test_default_schedule_producer_writes_upsample_and_halo(monkeypatch):
     enc = N.ContentEncoder(2, 4, 3, 64, "in", "relu", pad_type="reflect")
     N.run_chain(list(enc.model), torch.zeros(1, 3, 8, 8), 1)
     assert calls == [("conv7", 1, 1, False), ("conv4", 1, 1, False), ("conv4", 1, 1, False)] + [("res", 1, 1, False)] * 4
-
-
-def test_phase_form_schedule_is_opt_in_and_forward_only(monkeypatch):
-    calls = _record(monkeypatch)
-    dec = _decoder()
-    monkeypatch.setattr(ops, "UPCONV_PHASE", True)
-    with torch.no_grad():
-        N.run_chain(list(dec.model), Act(torch.zeros(1), 1), 0)
-    # the producers keep the low resolution and a halo of 1; both 5x5 layers upsample themselves
-    assert calls == [("res", 1, 1, False)] * 4 + [("conv5", 1, 1, True), ("conv5", 3, 1, True), ("conv7", 0, 1, False)]
-    calls.clear()
-    N.run_chain(list(dec.model), Act(torch.zeros(1), 1), 0)  # autograd on: the default schedule
-    assert calls[3:5] == [("res", 2, 2, False), ("conv5", 2, 2, False)]
-    assert not ops.upconv_phase_ok(dec.model[0].model[0].model[0].layer)  # 3x3 layers never qualify
-    # level 2: the training pass uses the phase form as well
-    monkeypatch.setattr(ops, "UPCONV_PHASE", 2)
-    calls.clear()
-    N.run_chain(list(dec.model), Act(torch.zeros(1), 1), 0)
-    assert calls == [("res", 1, 1, False)] * 4 + [("conv5", 1, 1, True), ("conv5", 3, 1, True), ("conv7", 0, 1, False)]

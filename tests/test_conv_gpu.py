@@ -252,63 +252,3 @@ def test_tapgemm_split_k(n, h, w, cin, cout, k, s, pad, ksplit):
     torch.cuda.synchronize()
     assert error_flag() == 0
     assert rel_l2(dxp, nhwc(xp.grad)) < TOL, rel_l2(dxp, nhwc(xp.grad))
-
-
-@pytest.mark.parametrize("n,h,cin,cout", [(2, 16, 256, 128), (1, 32, 128, 64), (3, 8, 64, 64)])
-def test_upconv_phase_forward(n, h, cin, cout):
-    """EXPERIMENTAL path (MUNIT_UPCONV_PHASE=1; skipped otherwise -- it has not run on a GPU yet, the plans are
-    CPU-verified in tests/test_geometry.py): nearest-2x upsample + reflect pad 2 + 5x5 conv as phase GEMMs on the
-    low-res input, against F.conv2d."""
-    import torch.nn.functional as F
-
-    from munit_b200 import ops
-
-    if not ops.UPCONV_PHASE:
-        pytest.skip("set MUNIT_UPCONV_PHASE=1 to run the experimental phase-form forward")
-    torch.manual_seed(0)
-    x = torch.randn(n, cin, h, h).to(torch.bfloat16).float()
-    wt = (torch.randn(cout, cin, 5, 5) * (2.0 / (25 * cin)) ** 0.5).to(torch.bfloat16).float()
-    bias = torch.randn(cout) * 0.1
-    ref = F.conv2d(F.pad(F.interpolate(x, scale_factor=2, mode="nearest"), (2,) * 4, mode="reflect"), wt, bias)
-    layer = ops.ConvLayer(cin, cout, 5, 1, 2)
-    x_lo = F.pad(x, (1,) * 4, mode="reflect").permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
-    with torch.no_grad():
-        y = ops.upconv_phase_forward(x_lo, wt.cuda().contiguous(memory_format=torch.channels_last), bias.cuda(), layer)
-    got = y.float().cpu().permute(0, 3, 1, 2)[:, :cout]
-    err = float((got - ref).norm() / ref.norm())
-    assert err < 1e-2, err  # phase weights are sums of up to 9 taps rounded once to bf16
-    ring = torch.ones_like(ref, dtype=torch.bool)
-    ring[:, :, 1:-1, 1:-1] = False
-    assert float((got[ring] - ref[ring]).norm() / ref[ring].norm()) < 1e-2
-
-
-@pytest.mark.parametrize("n,h,cin,cout", [(2, 16, 256, 128), (1, 32, 128, 64)])
-def test_upconv_phase_training_function(n, h, cin, cout):
-    """EXPERIMENTAL (MUNIT_UPCONV_PHASE=2; skipped otherwise -- not yet run on a GPU; the orchestration is verified on
-    the CPU in tests/test_upconv_cpu.py): ops.UpConvPhaseFn forward + backward against autograd of the direct form."""
-    import torch.nn.functional as F
-
-    from munit_b200 import ops
-
-    if int(ops.UPCONV_PHASE) < 2:
-        pytest.skip("set MUNIT_UPCONV_PHASE=2 to run the experimental phase-form training path")
-    torch.manual_seed(0)
-    x = torch.randn(n, cin, h, h).to(torch.bfloat16).float()
-    wt = (torch.randn(cout, cin, 5, 5) * (2.0 / (25 * cin)) ** 0.5).to(torch.bfloat16).float()
-    bias = torch.randn(cout) * 0.1
-    xr, wr, br = x.clone().requires_grad_(True), wt.clone().requires_grad_(True), bias.clone().requires_grad_(True)
-    ref = F.conv2d(F.pad(F.interpolate(xr, scale_factor=2, mode="nearest"), (2,) * 4, mode="reflect"), wr, br)
-    gy = torch.randn_like(ref).to(torch.bfloat16).float()
-    ref.backward(gy)
-    layer = ops.ConvLayer(cin, cout, 5, 1, 2)
-    x_lo = F.pad(x, (1,) * 4, mode="reflect").permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda().requires_grad_(True)
-    wg = wt.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
-    bg = bias.cuda().requires_grad_(True)
-    y = ops.UpConvPhaseFn.apply(x_lo, wg, bg, layer)
-    assert rel_l2(y.float().cpu().permute(0, 3, 1, 2), ref.detach()) < 1e-2
-    y.backward(gy.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda())
-    gx = x_lo.grad.float().cpu().permute(0, 3, 1, 2)
-    assert float(gx[:, :, 0].abs().max()) == 0
-    assert rel_l2(gx[:, :, 1:-1, 1:-1], xr.grad) < 1e-2
-    assert rel_l2(wg.grad.cpu(), wr.grad) < 1e-2
-    assert rel_l2(bg.grad.cpu(), br.grad) < 1e-3

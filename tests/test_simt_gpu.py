@@ -157,6 +157,45 @@ def test_act_bwd_and_colsum(act):
     db = torch.zeros(c, device="cuda")
     K.colsum(dy, db)
     assert rel_l2(db, dy.float().sum(dim=(0, 1, 2))) < 1e-4
+    # ... and the same bias gradient from the act_bwd pass itself (first 48 channels only: c_out < C)
+    for c_out, cc in ((c, 64), (48, 64), (256, 256)):
+        g2 = torch.randn(n, h + 2 * pad, w + 2 * pad, cc, device="cuda").to(torch.bfloat16)
+        o2 = torch.randn_like(g2)
+        db2 = torch.full((cc,), 1.0, device="cuda")
+        dy2 = K.act_bwd(g2, o2, pad, act, db2, c_out)
+        assert torch.equal(dy2, K.act_bwd(g2, o2, pad, act))
+        ref = 1.0 + dy2.float().sum(dim=(0, 1, 2))
+        assert rel_l2(db2[:c_out], ref[:c_out]) < 1e-4 and float((db2[c_out:] - 1.0).abs().max() if c_out < cc else 0) == 0
+
+
+def test_gather_cast_multi_matches_per_segment_gathers():
+    """munit_gather_cast_multi (all weight shadows of an arena in one launch): segments of ragged sizes, with and
+    without an index map, must equal munit_gather_cast / munit_cast_bf16 bit for bit."""
+    from munit_b200 import kernels as K
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    arena = torch.randn(50000, device="cuda", generator=g)
+    segs, refs = [], []
+    off = 0
+    for i, (n_src, n_dst) in enumerate([(1000, 4096), (7, 1), (2048, 2048), (5000, 2049), (12345, 30000), (64, 64)]):
+        src = arena[off:off + n_src]
+        off += n_src
+        idx = None if (i % 3 == 2) else torch.randint(-1, n_src, (n_dst,), device="cuda", dtype=torch.int32, generator=g)
+        n_dst = n_dst if idx is not None else n_src
+        dst = torch.full((n_dst,), 7.0, dtype=torch.bfloat16, device="cuda")
+        ref = torch.empty_like(dst)
+        if idx is None:
+            K.cast_bf16(src, ref)
+        else:
+            K.gather_cast(src, idx, ref)
+        segs.append((src, idx, dst))
+        refs.append(ref)
+    table, nseg, nblocks = K.gather_seg_table(segs, "cuda")
+    assert nseg == 6 and nblocks == sum((d.numel() + K.GATHER_BLOCK - 1) // K.GATHER_BLOCK for _, _, d in segs)
+    K.gather_cast_multi(table, nseg, nblocks)
+    torch.cuda.synchronize()
+    for (_, _, dst), ref in zip(segs, refs):
+        assert torch.equal(dst, ref)
 
 
 def test_gather_cast_add():

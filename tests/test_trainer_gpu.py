@@ -294,3 +294,44 @@ def test_optimizer_state_interchanges_with_torch_adam():
         assert float(((v_o - v_t).abs() / (v_t.abs() + 1e-12)).max()) < 1e-4, float(((v_o - v_t).abs() / (v_t.abs() + 1e-12)).max())
     ot2 = torch.optim.Adam(params(), **kw)
     ot2.load_state_dict(sd_ours)
+
+
+def test_optimizer_refreshes_all_weight_shadows_in_one_launch():
+    """optim.FlatAdam._launch -> ops.refresh_shadows: every bf16 GEMM operand (forward matrix and transposed / phase-split
+    dgrad matrix) of the arena's convolutions is regenerated by ONE gather launch right after the parameter update,
+    bit-identical to the per-layer gather, and the next forward does not refresh again."""
+    from munit_b200 import _lib, networks as N
+    from munit_b200.optim import FlatAdam
+
+    torch.manual_seed(0)
+    blocks = [N.Conv2dBlock(3, 64, 7, 1, 3, norm="none", activation="lrelu", pad_type="reflect"),   # kw-expanded first layer
+              N.Conv2dBlock(64, 128, 4, 2, 1, norm="in", activation="relu", pad_type="reflect"),    # stride-2 phase-split dgrad
+              N.Conv2dBlock(128, 64, 3, 1, 1, norm="none", activation="lrelu", pad_type="reflect"),
+              N.Conv2dBlock(64, 3, 7, 1, 3, norm="none", activation="tanh", pad_type="reflect")]    # narrow-output layer
+    net = torch.nn.Sequential(*blocks).cuda()
+    opt = FlatAdam(list(net.parameters()), lr=1e-2, betas=(0.5, 0.999), weight_decay=1e-4)
+    opt.zero_grad()
+    x = torch.randn(2, 3, 32, 32, device="cuda")
+    for it in range(2):
+        y = net(x)
+        y.square().mean().backward()
+        before = _lib.launches
+        opt.step()
+        assert _lib.launches - before == 2, "adam + one shadow launch"   # not 1 + 2 per layer
+        opt.zero_grad()
+    torch.cuda.synchronize()
+    for b in blocks:
+        layer = b.layer
+        got_f, got_d = layer.w_fwd.clone(), layer.w_dg.clone()
+        assert layer._wver == (b.conv.weight._version, b.conv.weight.data_ptr())   # the next forward will not refresh
+        layer.refresh(b.conv.weight, b.conv.bias, force=True)                      # per-layer path
+        torch.cuda.synchronize()
+        assert torch.equal(got_f, layer.w_fwd) and torch.equal(got_d, layer.w_dg)
+    before = _lib.launches
+    with torch.no_grad():
+        net(x)
+    n_fwd = _lib.launches - before
+    before = _lib.launches
+    with torch.no_grad():
+        net(x)
+    assert _lib.launches - before == n_fwd  # no hidden refresh launches in the first of the two
