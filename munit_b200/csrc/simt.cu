@@ -885,10 +885,14 @@ __device__ __forceinline__ void fold_load(FoldRaw<UP>& o, const bf16* __restrict
       o.v[uy * UP + ux] =
           *reinterpret_cast<const uint4*>(base + ((yy * UP + uy + pad) * wop + x * UP + ux + pad) * c);
 }
-// Slow path of the fold, out of line: adds the mirrored halo copies of a border pixel to acc.
+// Slow path of the fold, out of line: the sum of the mirrored halo copies of a border pixel.  Returned by value (and
+// added by the caller inside the border branch) so that the caller's accumulator never has to live in local memory:
+// passing it by reference cost every pixel, border or not, a store + load of all eight values.
 template <int UP>
-__device__ __noinline__ void fold_border(F8& acc, const bf16* __restrict__ base, int yy, int x, int h, int w, int c,
-                                         int pad) {
+__device__ __noinline__ F8 fold_border_sum(const bf16* __restrict__ base, int yy, int x, int h, int w, int c, int pad) {
+  F8 acc;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc.v[e] = 0.f;
   const int ho = h * UP, wo = w * UP, wop = wo + 2 * pad;
 #pragma unroll
   for (int uy = 0; uy < UP; ++uy) {
@@ -907,6 +911,14 @@ __device__ __noinline__ void fold_border(F8& acc, const bf16* __restrict__ base,
         }
     }
   }
+  return acc;
+}
+template <int UP>
+__device__ __forceinline__ void fold_border(F8& acc, const bf16* __restrict__ base, int yy, int x, int h, int w, int c,
+                                            int pad) {
+  const F8 extra = fold_border_sum<UP>(base, yy, x, h, w, c, pad);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc.v[e] += extra.v[e];
 }
 template <int UP>
 __device__ __forceinline__ F8 fold_finish(const FoldRaw<UP>& o, const bf16* __restrict__ base, int yy, int x, int h,
