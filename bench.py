@@ -64,7 +64,7 @@ def config_dict(cfg, batch, hw, world, hd=False):
 
 def profiled_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if os.path.isfile(p):
         d = json.load(open(p))
         return d["dram_bytes_read_per_launch"] + d["dram_bytes_write_per_launch"], d["kernel"]
