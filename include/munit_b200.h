@@ -271,6 +271,11 @@ int munit_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
 /* y[b][o] = act(sum_i x[b][i]*w[o][i] + bias[o])  (nn.Linear networks.py:712,744-748; fp32) */
 int munit_linear_fwd(const float* x, const float* w, const float* bias, float* y, int b, int in, int out, int relu,
                      void* stream);
+/* The style MLP that emits the AdaIN parameters (MLP networks.py:583-597 with n_blk = 3, AdaINGen.decode :456-461) in one
+ * launch: h1 = relu(W1 x + b1) [b][dim], h2 = relu(W2 h1 + b2) [b][dim], y = W3 h2 + b3 [b][out]; h1, h2 are kept for
+ * the backward pass (munit_linear_bwd per layer).  fp32, weights [out][in] row-major as nn.Linear. */
+int munit_mlp3_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                   const float* b3, float* h1, float* h2, float* y, int b, int in, int dim, int out, void* stream);
 /* dx[b][i] = sum_o dy'[b][o] w[o][i]; dw[o][i] += sum_b dy'[b][o] x[b][i]; db[o] += sum_b dy'; dy' = dy*relu'(y). */
 int munit_linear_bwd(const float* x, const float* w, const float* y, const float* dy, int relu, float* dx, float* dw,
                      float* db, int b, int in, int out, void* stream);

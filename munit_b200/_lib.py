@@ -94,6 +94,7 @@ _SIGS = {
     "munit_gather_add": ([_vp, _vp, _vp, _i64, _vp], C.c_int),
     "munit_cast_bf16": ([_vp, _vp, _i64, _vp], C.c_int),
     "munit_linear_fwd": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp], C.c_int),
+    "munit_mlp3_fwd": ([_vp] * 10 + [_i, _i, _i, _i, _vp], C.c_int),
     "munit_linear_bwd": ([_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp], C.c_int),
     "munit_gap_fwd": ([_vp, _vp, _i, _i, _i, _vp], C.c_int),
     "munit_gap_bwd": ([_vp, _vp, _i, _i, _i, _vp], C.c_int),

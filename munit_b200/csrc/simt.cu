@@ -1413,6 +1413,66 @@ __global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __re
     y[(long long)bb * out + o] = relu ? fmaxf(acc, 0.f) : acc;
   }
 }
+// The whole style MLP (networks.py:583-597: Linear + ReLU, Linear + ReLU, Linear -> AdaIN parameters) in ONE launch.
+// grid = (output chunks of the last layer, batch chunks of kMlpB samples); every block recomputes the two hidden
+// layers for its batch chunk in shared memory (d x d MACs per sample: cheaper than a second and third launch) and
+// then produces its slice of the outputs; the first output chunk also stores the hidden activations for backward.
+// A warp owns one output feature at a time: lanes split the input dimension (coalesced weight rows, conflict-free
+// shared-memory reads of the activations) and keep one partial sum per sample.
+constexpr int kMlpB = 16;
+__device__ __forceinline__ void mlp_layer_smem(const float* __restrict__ w, const float* __restrict__ bias,
+                                               const float* __restrict__ in_s, int in_dim, int nb, int o_begin, int o_end,
+                                               bool relu, float* __restrict__ out_s, int out_ld, int out_off,
+                                               float* __restrict__ out_g, long long g_ld) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int o = o_begin + warp; o < o_end; o += nwarps) {
+    float acc[kMlpB];
+#pragma unroll
+    for (int b = 0; b < kMlpB; ++b) acc[b] = 0.f;
+    const float* wr = w + (long long)o * in_dim;
+    for (int k = lane; k < in_dim; k += 32) {
+      const float wv = wr[k];
+#pragma unroll
+      for (int b = 0; b < kMlpB; ++b) acc[b] = fmaf(wv, in_s[b * in_dim + k], acc[b]);
+    }
+#pragma unroll
+    for (int b = 0; b < kMlpB; ++b)
+      for (int sft = 16; sft > 0; sft >>= 1) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], sft);
+    const float bv = bias ? bias[o] : 0.f;
+#pragma unroll
+    for (int b = 0; b < kMlpB; ++b)
+      if (lane == b && b < nb) {  // lane b finishes sample b
+        float v = acc[b] + bv;
+        if (relu) v = fmaxf(v, 0.f);
+        if (out_s) out_s[b * out_ld + o - out_off] = v;
+        if (out_g) out_g[(long long)b * g_ld + o] = v;
+      }
+  }
+}
+__global__ void __launch_bounds__(256)
+mlp3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w1, const float* __restrict__ b1,
+                const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w3,
+                const float* __restrict__ b3, float* __restrict__ h1, float* __restrict__ h2, float* __restrict__ y,
+                int batch, int in0, int d, int out, int o_chunk) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ float msm[];  // x [kMlpB][in0] | h1 [kMlpB][d] | h2 [kMlpB][d]
+  float* xs = msm;
+  float* h1s = xs + kMlpB * in0;
+  float* h2s = h1s + kMlpB * d;
+  const int b0 = blockIdx.y * kMlpB, nb = min(kMlpB, batch - b0);
+  for (int i = threadIdx.x; i < kMlpB * in0; i += blockDim.x) xs[i] = (i / in0) < nb ? x[(long long)b0 * in0 + i] : 0.f;
+  __syncthreads();
+  const bool keep = blockIdx.x == 0;
+  mlp_layer_smem(w1, b1, xs, in0, nb, 0, d, true, h1s, d, 0, keep ? h1 + (long long)b0 * d : nullptr, d);
+  for (int i = threadIdx.x; i < (kMlpB - nb) * d; i += blockDim.x) h1s[nb * d + i] = 0.f;
+  __syncthreads();
+  mlp_layer_smem(w2, b2, h1s, d, nb, 0, d, true, h2s, d, 0, keep ? h2 + (long long)b0 * d : nullptr, d);
+  for (int i = threadIdx.x; i < (kMlpB - nb) * d; i += blockDim.x) h2s[nb * d + i] = 0.f;
+  __syncthreads();
+  const int o0 = blockIdx.x * o_chunk;
+  mlp_layer_smem(w3, b3, h2s, d, nb, o0, min(out, o0 + o_chunk), false, nullptr, 0, 0, y + (long long)b0 * out, out);
+}
 // dx[b][i] = sum_o dyp[b][o] w[o][i]: grid (o-chunks of 64, b); threads over i; partial sums via atomicAdd
 __global__ void linear_bwd_dx_kernel(const float* __restrict__ w, const float* __restrict__ y,
                                      const float* __restrict__ dy, int relu, float* __restrict__ dx, int b, int in,
@@ -2143,6 +2203,26 @@ int munit_linear_fwd(const float* x, const float* w, const float* bias, float* y
   const long long threads = (long long)b * out * 32;
   mb_launch(linear_fwd_kernel, dim3(nblocks(threads, 256)), dim3(256), 0, ST(stream), x, w, bias, y, b, in, out, relu);
   MB_CHECK_LAUNCH("linear_fwd");
+  return MUNIT_OK;
+}
+int munit_mlp3_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                   const float* b3, float* h1, float* h2, float* y, int b, int in, int dim, int out, void* stream) {
+  if (b < 1 || in < 1 || dim < 1 || out < 1) return mb_fail(MUNIT_ERR_ARG, "mlp3_fwd: sizes");
+  const size_t sm = sizeof(float) * kMlpB * ((size_t)in + 2 * (size_t)dim);
+  if (sm > 200 * 1024) return mb_fail(MUNIT_ERR_ARG, "mlp3_fwd: in + 2 * dim = %d too large for shared memory", in + 2 * dim);
+  static size_t attr = 48 * 1024;
+  if (sm > attr) {
+    cudaError_t e = cudaFuncSetAttribute(mlp3_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "cudaFuncSetAttribute(mlp3): %s", cudaGetErrorString(e));
+    attr = sm;
+  }
+  // one output chunk per ~SM: the hidden layers are recomputed per block, so fewer, fatter chunks when `out` is small
+  int chunks = (out + 63) / 64;
+  if (chunks > 148) chunks = 148;
+  const int o_chunk = (out + chunks - 1) / chunks;
+  dim3 grid((out + o_chunk - 1) / o_chunk, (b + kMlpB - 1) / kMlpB);
+  mb_launch(mlp3_fwd_kernel, dim3(grid), dim3(256), sm, ST(stream), x, w1, b1, w2, b2, w3, b3, h1, h2, y, b, in, dim, out, o_chunk);
+  MB_CHECK_LAUNCH("mlp3_fwd");
   return MUNIT_OK;
 }
 int munit_linear_bwd(const float* x, const float* w, const float* y, const float* dy, int relu, float* dx, float* dw,

@@ -502,6 +502,20 @@ def linear_fwd(x, w, bias, relu):
     return y
 
 
+def mlp3_fwd(x, w1, b1, w2, b2, w3, b3):
+    """relu(W1 x + b1) -> relu(W2 . + b2) -> W3 . + b3 in one launch; returns (h1, h2, y)."""
+    b, i = x.shape
+    d, o = w1.shape[0], w3.shape[0]
+    assert w1.shape == (d, i) and w2.shape == (d, d) and w3.shape == (o, d)
+    h1 = torch.empty(b, d, dtype=torch.float32, device=x.device)
+    h2 = torch.empty(b, d, dtype=torch.float32, device=x.device)
+    y = torch.empty(b, o, dtype=torch.float32, device=x.device)
+    check(lib.munit_mlp3_fwd(x.data_ptr(), w1.data_ptr(), _ptr(b1), w2.data_ptr(), _ptr(b2), w3.data_ptr(), _ptr(b3),
+                             h1.data_ptr(), h2.data_ptr(), y.data_ptr(), b, i, d, o, _stream()), "mlp3_fwd")
+    _count()
+    return h1, h2, y
+
+
 def linear_bwd(x, w, y, dy, relu, need_dx, dw, db):
     b, i = x.shape
     o = w.shape[0]

@@ -629,6 +629,47 @@ class LinearFn(torch.autograd.Function):
                 None if (not need_w or ctx.bbuf is not None) else db, None)
 
 
+class Mlp3Fn(torch.autograd.Function):
+    """The style MLP of AdaINGen (networks.py:583-597, n_blk = 3: Linear+ReLU, Linear+ReLU, Linear) that emits the AdaIN
+    parameters: the forward pass is ONE kernel (munit_mlp3_fwd); the backward pass runs the per-layer linear
+    backward kernels on the hidden activations the forward kernel kept."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, w3, b3):
+        x = x.contiguous()
+        h1, h2, y = K.mlp3_fwd(x, w1, b1, w2, b2, w3, b3)
+        params = (w1, b1, w2, b2, w3, b3)
+        ctx.bufs = tuple(_param_grad_buf(p) for p in params)
+        ctx.need_w = any(ctx.needs_input_grad[1:])
+        _track_use(ctx, ctx.need_w, *ctx.bufs)
+        ctx.save_for_backward(x, h1, h2, y, w1, w2, w3)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, h1, h2, y, w1, w2, w3 = ctx.saved_tensors
+        outs = [None] * 6
+
+        def grads(i, w):
+            if not ctx.need_w:
+                return None, None
+            dw = ctx.bufs[2 * i] if ctx.bufs[2 * i] is not None else torch.zeros_like(w)
+            db = ctx.bufs[2 * i + 1] if ctx.bufs[2 * i + 1] is not None else torch.zeros(
+                w.shape[0], dtype=torch.float32, device=w.device)
+            outs[2 * i] = None if ctx.bufs[2 * i] is not None else dw
+            outs[2 * i + 1] = None if ctx.bufs[2 * i + 1] is not None else db
+            return dw, db
+
+        dw, db = grads(2, w3)
+        g2 = K.linear_bwd(h2, w3, y, gy.contiguous(), False, True, dw, db)
+        dw, db = grads(1, w2)
+        g1 = K.linear_bwd(h1, w2, h2, g2, True, True, dw, db)
+        dw, db = grads(0, w1)
+        gx = K.linear_bwd(x, w1, h1, g1, True, ctx.needs_input_grad[0], dw, db)
+        _track_done(ctx)
+        return (gx, *outs)
+
+
 class GapFn(torch.autograd.Function):
     """nn.AdaptiveAvgPool2d(1) (networks.py:471) on an act with no halo -> fp32 [N, C]."""
 

@@ -229,6 +229,35 @@ def test_linear_fwd_bwd():
     assert rel_l2(dx, x.grad) < 1e-5 and rel_l2(dw, w.grad) < 1e-5 and rel_l2(db, bias.grad) < 1e-5
 
 
+@pytest.mark.parametrize("b,i,d,o", [(16, 8, 256, 4096), (5, 8, 256, 4096), (40, 16, 64, 100), (1, 8, 256, 2048)])
+def test_style_mlp_one_kernel(b, i, d, o):
+    """networks.MLP (networks.py:583-597) with the shipped shape runs its forward pass as ONE kernel
+    (munit_mlp3_fwd, ops.Mlp3Fn); outputs and all gradients against the same MLP in plain torch fp32."""
+    from munit_b200 import _lib
+    from munit_b200.networks import MLP
+
+    torch.manual_seed(0)
+    mlp = MLP(i, o, d, 3, norm="none", activ="relu").cuda()
+    x = torch.randn(b, i, 1, 1, device="cuda", requires_grad=True)
+    before = _lib.launches
+    y = mlp(x)
+    assert _lib.launches - before == 1
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    got = [x.grad.clone()] + [p.grad.clone() for p in mlp.parameters()]
+    x.grad = None
+    mlp.zero_grad()
+    fcs = [blk.fc for blk in mlp.model]
+    h = x.reshape(b, -1)
+    ref = F.linear(torch.relu(F.linear(torch.relu(F.linear(h, fcs[0].weight, fcs[0].bias)), fcs[1].weight, fcs[1].bias)),
+                   fcs[2].weight, fcs[2].bias)
+    ref.backward(gy)
+    assert rel_l2(y, ref) < 1e-5
+    want = [x.grad] + [p.grad for p in mlp.parameters()]
+    for g, w in zip(got, want):
+        assert rel_l2(g, w) < 1e-4, (g.shape, rel_l2(g, w))
+
+
 def test_gap_and_dis_head():
     from munit_b200 import kernels as K
 
