@@ -759,6 +759,7 @@ struct WgParams {
   int ksplit;
   int stages;
   int tap_on_a;  // tap offsets shift the A operand (swapped orientation: A = X, B = dY) instead of B
+  int dbg;       // profiling knob (env MUNIT_WG_DBG): 1 skip the red.add stores of the epilogue
   int* err;
   int tap_off[MUNIT_MAX_TAPS][5];
 };
@@ -895,7 +896,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
         tmem_ld_wait();
-        if (m < p.m_total && !dead) {
+        if (m < p.m_total && !dead && !(p.dbg & 1)) {
           const int nb = n_tile * BN + c0;
           if (p.s_n == 1 && ((p.s_m | p.s_t) & 3) == 0 && (nb + 32 <= p.n_total)) {
 #pragma unroll
@@ -1236,6 +1237,14 @@ extern "C" int munit_wgrad(const munit_wgrad_desc* d, void* stream) {
   p.dw = d->dw; p.s_m = d->s_m; p.s_t = d->s_t; p.s_n = d->s_n;
   p.stages = d->stages; p.err = mb_error_flag();
   p.tap_on_a = d->tap_on_a;
+  {
+    static int wdbg = -1;
+    if (wdbg < 0) {
+      const char* e = getenv("MUNIT_WG_DBG");
+      wdbg = e ? atoi(e) : 0;
+    }
+    p.dbg = wdbg;
+  }
   memcpy(p.tap_off, d->tap_off, sizeof(p.tap_off));
   const int m_tiles = (d->m_total + 127) / 128;
   const int total_pb = p.blocks_x * p.blocks_y * p.blocks_n;
