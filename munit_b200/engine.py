@@ -30,6 +30,11 @@ class StepRunner:
         MsImageDis.scale_streams = bool(two_streams and use_graph) and os.environ.get("MUNIT_DIS_SCALE_STREAMS", "1") != "0"
         trainer.wgrad_overlap = bool(int(two_streams) >= 2 and use_graph)
         self.use_graph, self.world = use_graph, world
+        # gen_update's generator pass issued under the discriminator update (trainer._early_generator_forward); needs the
+        # whole step in one graph (no early pass across the segment boundaries of the split gradient exchange)
+        split_exchange = world > 1 and os.environ.get("MUNIT_DP_OVERLAP", "1") == "0"
+        trainer.overlap_updates = (bool(two_streams and use_graph) and not reuse_forward and not split_exchange
+                                   and os.environ.get("MUNIT_OVERLAP_UPDATES", "1") != "0")
         dev = next(trainer.parameters()).device
         self.dev = dev
         sd = trainer.style_dim
@@ -69,7 +74,8 @@ class StepRunner:
 
     # ------------------------------------------------------------------ pieces of a step
     def _seg_dis(self):
-        self.t._dis_backward(self.x_a, self.x_b, self.cfg, self.s_a, self.s_b)
+        self.t._dis_backward(self.x_a, self.x_b, self.cfg, self.s_a, self.s_b,
+                             early_gen=(self.s_a2, self.s_b2) if self.t.overlap_updates else None)
 
     def _seg_mid(self):
         self.t.dis_opt_step()

@@ -119,8 +119,15 @@ class MUNIT_Trainer(nn.Module):
         self.grad_sync = {}
         self.parallel_streams = False
         self.wgrad_overlap = False  # with parallel_streams: weight gradients on companion streams (ops.wgrad_async)
-        self._side = None
-        self._side_used = 0
+        # Side streams per stream *context*: 0 = the step's main line, 1 = the early generator pass of gen_update that
+        # engine.StepRunner overlaps with the discriminator update (_early_generator_forward).
+        self._side = {}
+        self._side_used = {}
+        self._ctx = 0
+        self._gstream = None
+        self._early = None
+        self.overlap_updates = False
+        self.early_used = 0  # gen_update calls that picked up an early generator pass
 
     def _fork_join(self, fa, *fbs):
         """fa() on the current stream, every other function on its own side stream, then join.  Fork/join discipline
@@ -128,12 +135,11 @@ class MUNIT_Trainer(nn.Module):
         if not self.parallel_streams:
             return (fa(),) + tuple(f() for f in fbs)
         cur = torch.cuda.current_stream()
-        if self._side is None:
-            self._side = []
-        while len(self._side) < len(fbs):
-            self._side.append(torch.cuda.Stream())
-        sides = self._side[:len(fbs)]
-        self._side_used = max(self._side_used, len(sides))
+        pool = self._side.setdefault(self._ctx, [])
+        while len(pool) < len(fbs):
+            pool.append(torch.cuda.Stream())
+        sides = pool[:len(fbs)]
+        self._side_used[self._ctx] = max(self._side_used.get(self._ctx, 0), len(sides))
         for side in sides:
             side.wait_stream(cur)
         res = [fa()]
@@ -144,15 +150,47 @@ class MUNIT_Trainer(nn.Module):
             cur.wait_stream(side)
         return tuple(res)
 
-    def _join_side(self):
-        if self.parallel_streams and self._side is not None:
+    def _join_side(self, ctxs=(0,)):
+        if self.parallel_streams:
             # only the streams forked since the last join (backward nodes run on their forward streams); a stream
             # that took no part in the current graph capture must not be waited on
-            for side in self._side[:self._side_used]:
-                torch.cuda.current_stream().wait_stream(side)
-            self._side_used = 0
+            cur = torch.cuda.current_stream()
+            for ctx in ctxs:
+                if ctx == 1 and self._gstream is not None:
+                    cur.wait_stream(self._gstream)
+                for side in self._side.get(ctx, [])[:self._side_used.get(ctx, 0)]:
+                    cur.wait_stream(side)
+                self._side_used[ctx] = 0
         ops.join_side_streams()
         ops.wgrad_join()
+
+    # ------------------------------------------------------------------ gen_update's forward under the dis update
+    # The generator pass of gen_update (encode, decode, encode again: trainer.py:400-419) reads the generator
+    # weights, the images and its own style draws -- nothing dis_update writes.  Under the step runner it is issued
+    # on its own stream (with its own side streams) right after dis_update's no-grad generator pass, so that it fills
+    # the SMs the discriminator's small deep-scale launches leave idle; gen_update joins it before it needs the
+    # *updated* discriminator for the adversarial loss, so every result is what the sequential order produces.
+    def _early_key(self, x_a, x_b, s_a, s_b):
+        return (x_a.data_ptr(), x_a._version, x_b.data_ptr(), x_b._version, s_a.data_ptr(), s_a._version,
+                s_b.data_ptr(), s_b._version, self.gen_opt.step_count)
+
+    def _early_generator_forward(self, x_a, x_b, s_a, s_b):
+        cur = torch.cuda.current_stream()
+        if self._gstream is None:
+            self._gstream = torch.cuda.Stream()
+        g = self._gstream
+        g.wait_stream(cur)
+        self._ctx = 1
+        try:
+            with torch.cuda.stream(g):
+                self.gen_opt.zero_grad()
+                gsync = self.grad_sync.get("gen")
+                if gsync is not None:
+                    gsync.begin()
+                out = self._gen_forward_batched(x_a, x_b, s_a, s_b, None)
+        finally:
+            self._ctx = 0
+        self._early = (self._early_key(x_a, x_b, s_a, s_b), out)
 
     # ------------------------------------------------------------------ device
     def _apply(self, fn, *a, **k):
@@ -306,14 +344,28 @@ class MUNIT_Trainer(nn.Module):
             stage12 = cache[1]  # gradients and the gradient-sync pass were opened by _dis_backward
         del cache
         gsync = self.grad_sync.get("gen")
-        if stage12 is None:
+        early, self._early = self._early, None
+        if early is not None and (s_a is None or early[0] != self._early_key(x_a, x_b, s_a, s_b)):
+            # not the step the early pass was issued for: join and drop it, then run the normal order
+            torch.cuda.current_stream().wait_stream(self._gstream)
+            early = None
+        join = (0,)
+        if early is not None:
+            torch.cuda.current_stream().wait_stream(self._gstream)  # gradients / sync pass were opened by the early pass
+            join = (0, 1)  # its backward nodes run on the early streams
+            self.early_used += 1
+        elif stage12 is None:
             self.gen_opt.zero_grad()
             if gsync is not None:
                 gsync.begin()
         ops.WG.enabled = bool(self.parallel_streams and self.wgrad_overlap)
         s_a, s_b = self._style_noise(x_a, x_b, s_a, s_b)
         cyc = hyperparameters["recon_x_cyc_w"] > 0
-        if self.gen_state == 1 and x_a.shape == x_b.shape:
+        if early is not None:
+            (c_a, s_a_prime, c_b, s_b_prime, x_a_recon, x_b_recon, x_ba, x_ab, c_b_recon, s_a_recon, c_a_recon,
+             s_b_recon) = early[1]
+            del early
+        elif self.gen_state == 1 and x_a.shape == x_b.shape:
             (c_a, s_a_prime, c_b, s_b_prime, x_a_recon, x_b_recon, x_ba, x_ab, c_b_recon, s_a_recon, c_a_recon,
              s_b_recon) = self._gen_forward_batched(x_a, x_b, s_a, s_b, stage12)
             del stage12
@@ -395,7 +447,7 @@ class MUNIT_Trainer(nn.Module):
         if adv_lambda > 0:
             self.loss_gen_total = self.loss_gen_total + adv_lambda * self.loss_classifier_sr
         self.loss_gen_total.backward()
-        self._join_side()  # backward nodes ran on their forward streams; the optimiser step waits for both
+        self._join_side(join)  # backward nodes ran on their forward streams; the optimiser step waits for all of them
         if gsync is not None:
             gsync.finish()  # reduce the buckets that are still local, wait for the ones already in flight
         self._last = dict(x_ab=x_ab.detach(), x_ba=x_ba.detach())
@@ -440,8 +492,10 @@ class MUNIT_Trainer(nn.Module):
             comet_exp.log_metric("loss_dis_b", self.loss_dis_b.cpu().detach())
             comet_exp.log_metric("loss_dis_a", self.loss_dis_a.cpu().detach())
 
-    def _dis_backward(self, x_a, x_b, hyperparameters, s_a=None, s_b=None):
-        """Losses + gradients of dis_update (everything up to, not including, the optimiser step)."""
+    def _dis_backward(self, x_a, x_b, hyperparameters, s_a=None, s_b=None, early_gen=None):
+        """Losses + gradients of dis_update (everything up to, not including, the optimiser step).  early_gen: the
+        (s_a, s_b) style draws of the gen_update that follows on the same batch -- its generator pass is then issued
+        here, overlapped with the discriminator work (_early_generator_forward)."""
         self.dis_opt.zero_grad()
         dsync = self.grad_sync.get("dis")
         if dsync is not None:
@@ -470,6 +524,10 @@ class MUNIT_Trainer(nn.Module):
                 else:
                     print("self.guided unknown value:", self.guided)
                 x_ba, x_ab = self._fork_join(lambda: self._dec("a", c_b, sty_a), lambda: self._dec("b", c_a, sty_b))
+            self._early = None
+            if (early_gen is not None and self.overlap_updates and self.parallel_streams and self.gen_state == 1
+                    and x_a.shape == x_b.shape):
+                self._early_generator_forward(x_a, x_b, *early_gen)
         # D loss
         self.loss_dis_a, self.loss_dis_b = self._fork_join(lambda: self.dis_a.calc_dis_loss(x_ba.detach(), x_a),
                                                            lambda: self.dis_b.calc_dis_loss(x_ab.detach(), x_b))

@@ -35,6 +35,9 @@ def _run(mode, steps=3, optimizer="adam"):
         ls = r.losses()
         losses.append((float(ls["loss_dis_total"]), float(ls["loss_gen_total"])))
     torch.cuda.synchronize()
+    # two-stream runners issue gen_update's generator pass under the discriminator update (trainer.overlap_updates):
+    # every captured / warm-up step must have picked it up, the eager and one-stream runners never
+    assert (t.early_used > 0) == (mode in ("graph2", "graph3")), (mode, t.early_used)
     return losses, t.gen_opt.p_arena.clone(), t.dis_opt.p_arena.clone()
 
 
