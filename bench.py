@@ -541,6 +541,42 @@ def infer_line(args, steps, with_cpu):
     return line
 
 
+class Watchdog:
+    """Deadline for phases that can stop making progress (a hung collective, a device-side deadlock): when it expires the
+    process leaves with os._exit -- after rank 0 has printed the headline line with whatever extras finished (exit 0), or
+    with exit code 3 when the headline itself never completed.  Every rank runs its own; no communication needed."""
+
+    def __init__(self):
+        import threading
+        self.lock = threading.Lock()
+        self.deadline, self.what, self.emit = None, "", None
+        threading.Thread(target=self._run, daemon=True).start()
+
+    def arm(self, what, seconds, emit=None):
+        with self.lock:
+            self.what, self.deadline, self.emit = what, time.time() + seconds, emit
+
+    def disarm(self):
+        with self.lock:
+            self.deadline = None
+
+    def _run(self):
+        while True:
+            time.sleep(1.0)
+            with self.lock:
+                d, what, emit = self.deadline, self.what, self.emit
+            if d is not None and time.time() > d:
+                code = 3
+                try:
+                    sys.stderr.write(f"bench.py watchdog: '{what}' made no progress before its deadline\n")
+                    sys.stderr.flush()
+                    if emit is not None:
+                        emit(what)
+                        code = 0
+                finally:
+                    os._exit(code)
+
+
 def run_b200(args):
     import torch.distributed as dist
 
@@ -548,6 +584,8 @@ def run_b200(args):
     rank = int(os.environ.get("RANK", 0))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
+    dog = Watchdog()
+    dog.arm("headline", 480.0)  # a healthy default run needs ~30 s for the headline (+ ~45 s CPU baseline at N = 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from munit_b200 import _lib  # noqa: F401  (fails loudly when the shared library is missing)
@@ -592,16 +630,106 @@ def run_b200(args):
     del runner, trainer
     if world > 1:
         dist.barrier()
+    # ---- the headline line is complete BEFORE any informational extra runs: an extra can fail or even hang (watchdog)
+    # without taking the headline down
+    dom_us, dom_tf = dominant_launch_time(batch) if rank == 0 else (0.0, 0.0)
+    if rank == 0 and args.dump_launches:
+        json.dump(prof["detail"], open(args.dump_launches, "w"))
+    line = None
+    if rank == 0:
+        peaks = measured_peaks()
+        per8 = batch / 8.0                                            # UNIT counts steps of 8 image pairs
+        steps_per_s = args.steps / (ms / 1000.0) * world * per8       # whole job
+        e2e_per_s = args.steps / (ms_e2e / 1000.0) * world * per8
+        tg = prof["tapgemm"]
+        ach = tg["flops"] / (tg["ms"] / 1000.0) / 1e12 if tg["ms"] > 0 else 0.0
+        wg = prof["wgrad"]
+        ach_w = wg["flops"] / (wg["ms"] / 1000.0) / 1e12 if wg["ms"] > 0 else 0.0
+        algo_tflop_step = 2.790 * batch * (hw / 256.0) ** 2  # SURVEY.md s8d, per sample pair at 256^2
+        # normalisation family against the HBM roofline.  Algorithmic bytes: forward 4 B per element of
+        # the pre-norm tensor (read + write, statistics from the producer), backward 6 B + 4 B for the reduction pass.
+        nm = prof["norm"]
+        fwd_el = nm["norm_apply"]["elems"]
+        bwd_el = nm["norm_bwd_apply"]["elems"]
+        norm_ms = sum(v["ms"] for v in nm.values())
+        alg_bytes = 4.0 * fwd_el + 10.0 * bwd_el
+        moved = sum(v["bytes"] for v in nm.values())
+        ach_hbm = alg_bytes / (norm_ms / 1000.0) / 1e9 if norm_ms > 0 else 0.0
+        cpu_line = dict(value=None, unit=UNIT, cores=os.cpu_count(), kind="port", sample="skipped (N>1 or --no-cpu-baseline)")
+        if world == 1 and not args.no_cpu_baseline:
+            v, kind, sample, _, _ = cpu_reference_steps(cfg, hw, batch, 2, 0, budget_s=25.0)
+            cpu_line = dict(value=v * per8, unit=UNIT, cores=os.cpu_count(), kind=kind, sample=sample)
+        line = dict(
+            metric=METRIC, value=steps_per_s, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+            ms_per_step=ms / args.steps, higher_is_better=True, scaling=scaling, vs_baseline=None, dtype="bf16",
+            data="synthetic",
+            config=config_dict(cfg, batch, hw, world, args.hd),
+            engine=dict(cuda_graph=not args.no_graph, two_streams=bool(args.two_streams),
+                        grad_exchange=("none (1 GPU)" if world == 1 else
+                                       ("NCCL all-reduce per ready bucket, overlapped with backward, captured in the step graph "
+                                        f"({overlap_note[0]} buckets, {overlap_note[1]} launched before the end "
+                                        "of their backward pass)"
+                                        if overlap_note[2] else "NCCL all-reduce of the whole arena between three captured segments"))),
+            e2e=dict(value=e2e_per_s, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=8,
+                     last_losses=dict(dis=last[0], gen=last[1])),
+            gpu_launches=launches_per_step * args.steps,
+            clocks=clocks,
+            roofline=dict(bound="tensor", kernel="tapgemm_kernel<BN> (conv fwd + dgrad, tcgen05)", achieved=ach,
+                          peak=peaks["tflops"], unit="TFLOP/s", frac=ach / peaks["tflops"] if peaks["tflops"] else None,
+                          traffic=profiled_traffic()[0], traffic_kernel=profiled_traffic()[1],
+                          peak_source=peaks["src"], launches_per_step=tg["launches"],
+                          kernel_ms_per_step=tg["ms"],
+                          note="achieved = direct-form FLOPs of all conv fwd/dgrad launches / their device time inside the "
+                               "step, one CUDA event pair per launch (the pair itself adds several us to each ~40 us launch); "
+                               "in-step figures are graded against the sustained peak, the isolated launch against burst",
+                          dominant_launch=dict(kernel="tapgemm_kernel<256>, 3x3 256->256 forward on [B,64,64]",
+                                               us=dom_us, achieved=dom_tf, peak=peaks["tflops_burst"],
+                                               frac=dom_tf / peaks["tflops_burst"] if peaks["tflops_burst"] else None,
+                                               method="one event pair around 40 back-to-back launches, rotating buffers; "
+                                                      "denominator = burst bf16 peak (kernel timed alone)"),
+                          wgrad=dict(achieved=ach_w, launches_per_step=wg["launches"], kernel_ms_per_step=wg["ms"],
+                                     frac=ach_w / peaks["tflops"] if peaks["tflops"] else None),
+                          step_algorithmic_tflop=algo_tflop_step,
+                          step_frac=(algo_tflop_step / (ms / args.steps / 1000.0)) / peaks["tflops"]),
+            roofline_hbm=dict(bound="hbm", kernel="norm_stats / norm_apply / norm_bwd_reduce / norm_bwd_apply (+ finalize)",
+                              achieved=ach_hbm, peak=peaks["hbm"], unit="GB/s", frac=ach_hbm / peaks["hbm"] if peaks["hbm"] else None,
+                              kernel_ms_per_step=norm_ms, launches_per_step=sum(v["launches"] for v in nm.values()),
+                              algorithmic_bytes_per_step=alg_bytes, moved_bytes_per_step=moved,
+                              moved_gbs=moved / (norm_ms / 1000.0) / 1e9 if norm_ms > 0 else 0.0,
+                              per_kernel={k: dict(ms=v["ms"], launches=v["launches"],
+                                                  gbs=(v["bytes"] / (v["ms"] / 1000.0) / 1e9 if v["ms"] > 0 else 0.0))
+                                          for k, v in nm.items()},
+                              note="achieved = algorithmic bytes (SURVEY.md 8d: 4 B per pre-norm element forward, 10 B "
+                                   "backward) / summed device time of the family inside the step; moved = bytes the "
+                                   "launches actually touch (statistics pass, 4x up-sampled writes and halos included)"),
+            cpu_baseline=cpu_line,
+        )
+        if args.reuse_forward:
+            line["config"]["reuse_forward"] = True
     extras = {}
     side_steps = max(3, min(args.steps, 8))
 
+    extra_limit = 300.0  # seconds per extra (a healthy one needs 15-60 s)
+
+    def abandon(what):
+        if rank == 0:
+            extras[what] = dict(error=f"abandoned by the watchdog: no progress within {extra_limit:.0f} s")
+            out = dict(line)
+            out.update(extras)
+            print(json.dumps(out), flush=True)
+
     def extra(name, fn):
+        dog.arm(name, extra_limit, abandon)
         try:
             extras[name] = fn()
         except Exception as exc:  # informational lines only: never lose the headline over one of them
             extras[name] = dict(error=repr(exc)[:300])
             import gc
             gc.collect(); torch.cuda.empty_cache()
+        finally:
+            dog.disarm()
+
+    dog.disarm()
 
     plain = not (args.hd or args.global_batch or args.no_extras or args.no_graph or args.hw or args.batch != 8)
     # ---- informational: the same step with gen_update picking up dis_update's generator pass (trainer.reuse_forward)
@@ -639,86 +767,13 @@ def run_b200(args):
                                             f"batch {args.hd_batch}/GPU, 512x512"))
     if plain and world == 1:
         extra("infer", lambda: infer_line(args, side_steps, not args.no_cpu_baseline))
-    dom_us, dom_tf = dominant_launch_time(batch) if rank == 0 else (0.0, 0.0)
-    if rank == 0 and args.dump_launches:
-        json.dump(prof["detail"], open(args.dump_launches, "w"))
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    peaks = measured_peaks()
-    per8 = batch / 8.0                                            # UNIT counts steps of 8 image pairs
-    steps_per_s = args.steps / (ms / 1000.0) * world * per8       # whole job
-    e2e_per_s = args.steps / (ms_e2e / 1000.0) * world * per8
-    tg = prof["tapgemm"]
-    ach = tg["flops"] / (tg["ms"] / 1000.0) / 1e12 if tg["ms"] > 0 else 0.0
-    wg = prof["wgrad"]
-    ach_w = wg["flops"] / (wg["ms"] / 1000.0) / 1e12 if wg["ms"] > 0 else 0.0
-    algo_tflop_step = 2.790 * batch * (hw / 256.0) ** 2  # SURVEY.md s8d, per sample pair at 256^2
-    # normalisation family against the HBM roofline.  Algorithmic bytes: forward 4 B per element of
-    # the pre-norm tensor (read + write, statistics from the producer), backward 6 B + 4 B for the reduction pass.
-    nm = prof["norm"]
-    fwd_el = nm["norm_apply"]["elems"]
-    bwd_el = nm["norm_bwd_apply"]["elems"]
-    norm_ms = sum(v["ms"] for v in nm.values())
-    alg_bytes = 4.0 * fwd_el + 10.0 * bwd_el
-    moved = sum(v["bytes"] for v in nm.values())
-    ach_hbm = alg_bytes / (norm_ms / 1000.0) / 1e9 if norm_ms > 0 else 0.0
-    cpu_line = dict(value=None, unit=UNIT, cores=os.cpu_count(), kind="port", sample="skipped (N>1 or --no-cpu-baseline)")
-    if world == 1 and not args.no_cpu_baseline:
-        v, kind, sample, _, _ = cpu_reference_steps(cfg, hw, batch, 2, 0, budget_s=25.0)
-        cpu_line = dict(value=v * per8, unit=UNIT, cores=os.cpu_count(), kind=kind, sample=sample)
-    line = dict(
-        metric=METRIC, value=steps_per_s, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-        ms_per_step=ms / args.steps, higher_is_better=True, scaling=scaling, vs_baseline=None, dtype="bf16",
-        data="synthetic",
-        config=config_dict(cfg, batch, hw, world, args.hd),
-        engine=dict(cuda_graph=not args.no_graph, two_streams=bool(args.two_streams),
-                    grad_exchange=("none (1 GPU)" if world == 1 else
-                                   ("NCCL all-reduce per ready bucket, overlapped with backward, captured in the step graph "
-                                    f"({overlap_note[0]} buckets, {overlap_note[1]} launched before the end "
-                                    "of their backward pass)"
-                                    if overlap_note[2] else "NCCL all-reduce of the whole arena between three captured segments"))),
-        e2e=dict(value=e2e_per_s, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=8,
-                 last_losses=dict(dis=last[0], gen=last[1])),
-        gpu_launches=launches_per_step * args.steps,
-        clocks=clocks,
-        roofline=dict(bound="tensor", kernel="tapgemm_kernel<BN> (conv fwd + dgrad, tcgen05)", achieved=ach,
-                      peak=peaks["tflops"], unit="TFLOP/s", frac=ach / peaks["tflops"] if peaks["tflops"] else None,
-                      traffic=profiled_traffic()[0], traffic_kernel=profiled_traffic()[1],
-                      peak_source=peaks["src"], launches_per_step=tg["launches"],
-                      kernel_ms_per_step=tg["ms"],
-                      note="achieved = direct-form FLOPs of all conv fwd/dgrad launches / their device time inside the "
-                           "step, one CUDA event pair per launch (the pair itself adds several us to each ~40 us launch); "
-                           "in-step figures are graded against the sustained peak, the isolated launch against burst",
-                      dominant_launch=dict(kernel="tapgemm_kernel<256>, 3x3 256->256 forward on [B,64,64]",
-                                           us=dom_us, achieved=dom_tf, peak=peaks["tflops_burst"],
-                                           frac=dom_tf / peaks["tflops_burst"] if peaks["tflops_burst"] else None,
-                                           method="one event pair around 40 back-to-back launches, rotating buffers; "
-                                                  "denominator = burst bf16 peak (kernel timed alone)"),
-                      wgrad=dict(achieved=ach_w, launches_per_step=wg["launches"], kernel_ms_per_step=wg["ms"],
-                                 frac=ach_w / peaks["tflops"] if peaks["tflops"] else None),
-                      step_algorithmic_tflop=algo_tflop_step,
-                      step_frac=(algo_tflop_step / (ms / args.steps / 1000.0)) / peaks["tflops"]),
-        roofline_hbm=dict(bound="hbm", kernel="norm_stats / norm_apply / norm_bwd_reduce / norm_bwd_apply (+ finalize)",
-                          achieved=ach_hbm, peak=peaks["hbm"], unit="GB/s", frac=ach_hbm / peaks["hbm"] if peaks["hbm"] else None,
-                          kernel_ms_per_step=norm_ms, launches_per_step=sum(v["launches"] for v in nm.values()),
-                          algorithmic_bytes_per_step=alg_bytes, moved_bytes_per_step=moved,
-                          moved_gbs=moved / (norm_ms / 1000.0) / 1e9 if norm_ms > 0 else 0.0,
-                          per_kernel={k: dict(ms=v["ms"], launches=v["launches"],
-                                              gbs=(v["bytes"] / (v["ms"] / 1000.0) / 1e9 if v["ms"] > 0 else 0.0))
-                                      for k, v in nm.items()},
-                          note="achieved = algorithmic bytes (SURVEY.md 8d: 4 B per pre-norm element forward, 10 B "
-                               "backward) / summed device time of the family inside the step; moved = bytes the "
-                               "launches actually touch (statistics pass, 4x up-sampled writes and halos included)"),
-        cpu_baseline=cpu_line,
-    )
-    line.update(extras)
-    if args.reuse_forward:
-        line["config"]["reuse_forward"] = True
-    print(json.dumps(line))
+    if rank == 0:
+        line.update(extras)
+        print(json.dumps(line), flush=True)
+    dog.arm("teardown", 60.0, lambda what: None)  # (the line is out: leave with exit code 0 whatever happens now)
     if world > 1:
         dist.destroy_process_group()
+    dog.disarm()
 
 
 def run_infer(args):

@@ -35,6 +35,17 @@ class StepRunner:
         split_exchange = world > 1 and os.environ.get("MUNIT_DP_OVERLAP", "1") == "0"
         trainer.overlap_updates = (bool(two_streams and use_graph) and not reuse_forward and not split_exchange
                                    and os.environ.get("MUNIT_OVERLAP_UPDATES", "1") != "0")
+        # Data parallel: the round-2 concurrency features (CTA-pair clusters, third stream, early generator pass) have
+        # run at 2 GPUs only -- the one 8-GPU run with all of them on completed the headline and then stopped making
+        # progress inside a later graph replay (device-side, cause not isolated before the GPU budget ended;
+        # profiles/r2_dp8_hang.md).  Until that is understood, ranks of a multi-GPU job execute the step the way
+        # round 1 validated at 2 / 4 / 8 GPUs: two streams, single-CTA tap-GEMMs, sequential updates.
+        # MUNIT_DP_FEATURES=1 turns the features back on.
+        if world > 1 and os.environ.get("MUNIT_DP_FEATURES", "0") == "0":
+            from . import kernels as _K
+            trainer.overlap_updates = False
+            trainer.style_stream = False
+            _K.PAIR = False
         dev = next(trainer.parameters()).device
         self.dev = dev
         sd = trainer.style_dim

@@ -127,6 +127,7 @@ class MUNIT_Trainer(nn.Module):
         self._gstream = None
         self._early = None
         self.overlap_updates = False
+        self.style_stream = True  # shared style encoder on a third stream (engine.StepRunner turns it off under DP)
         self.early_used = 0  # gen_update calls that picked up an early generator pass
 
     def _fork_join(self, fa, *fbs):
@@ -256,10 +257,13 @@ class MUNIT_Trainer(nn.Module):
             return Act(torch.cat([u.t, v.t], 0), u.pad)
 
         xab_cat = torch.cat([x_a, x_b], 0)
-        # (the shared style encoder is independent of both content encoders: third stream)
-        c_a, c_b, s_both = self._fork_join(lambda: g.enc1_content.forward_act(x_a, 1),
-                                           lambda: g.enc2_content.forward_act(x_b, 1),
-                                           lambda: g.enc_style(xab_cat))
+        if self.style_stream:  # the shared style encoder is independent of both content encoders: third stream
+            c_a, c_b, s_both = self._fork_join(lambda: g.enc1_content.forward_act(x_a, 1),
+                                               lambda: g.enc2_content.forward_act(x_b, 1),
+                                               lambda: g.enc_style(xab_cat))
+        else:
+            (c_a, s_both), c_b = self._fork_join(lambda: (g.enc1_content.forward_act(x_a, 1), g.enc_style(xab_cat)),
+                                                 lambda: g.enc2_content.forward_act(x_b, 1))
         s_a_prime, s_b_prime = s_both[:b], s_both[b:]
         sty_a = s_a if self.guided == 0 else s_a_prime   # style used for the cross-domain decode into a
         sty_b = s_b if self.guided == 0 else s_b_prime
@@ -280,9 +284,14 @@ class MUNIT_Trainer(nn.Module):
             stage12 = self._gen_forward_stage12(x_a, x_b, s_a, s_b)
         c_a, s_a_prime, c_b, s_b_prime, x_a_recon, x_b_recon, x_ba, x_ab = stage12
         xre_cat = torch.cat([x_ba, x_ab], 0)
-        c_b_recon, c_a_recon, s_re = self._fork_join(lambda: g.enc1_content.forward_act(x_ba, 1),
-                                                     lambda: g.enc2_content.forward_act(x_ab, 1),
-                                                     lambda: g.enc_style(xre_cat))
+        if self.style_stream:
+            c_b_recon, c_a_recon, s_re = self._fork_join(lambda: g.enc1_content.forward_act(x_ba, 1),
+                                                         lambda: g.enc2_content.forward_act(x_ab, 1),
+                                                         lambda: g.enc_style(xre_cat))
+        else:
+            (c_b_recon, s_re), c_a_recon = self._fork_join(
+                lambda: (g.enc1_content.forward_act(x_ba, 1), g.enc_style(xre_cat)),
+                lambda: g.enc2_content.forward_act(x_ab, 1))
         s_a_recon, s_b_recon = s_re[:b], s_re[b:]
         return (c_a, s_a_prime, c_b, s_b_prime, x_a_recon, x_b_recon, x_ba, x_ab, c_b_recon, s_a_recon, c_a_recon,
                 s_b_recon)

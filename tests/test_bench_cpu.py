@@ -1,0 +1,101 @@
+"""bench.py host logic that needs no GPU: the watchdog that keeps a hung informational extra (or a hung headline) from
+turning into a silent 10-minute NCCL timeout."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(code):
+    return subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, timeout=120, text=True)
+
+
+def test_watchdog_emits_the_headline_and_exits_zero():
+    r = _run("import bench, time, json\n"
+             "d = bench.Watchdog()\n"
+             "d.arm('hd', 1.0, lambda w: print(json.dumps({'value': 1.5, w: {'error': 'abandoned'}}), flush=True))\n"
+             "time.sleep(60)\n")
+    assert r.returncode == 0, r.stderr[-500:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["value"] == 1.5 and "error" in line["hd"]
+    assert "watchdog" in r.stderr
+
+
+def test_watchdog_without_a_headline_fails_loudly_and_disarm_works():
+    r = _run("import bench, time\nd = bench.Watchdog()\nd.arm('headline', 1.0)\ntime.sleep(60)\n")
+    assert r.returncode == 3 and r.stdout.strip() == ""
+    r = _run("import bench, time\nd = bench.Watchdog()\nd.arm('x', 1.0)\nd.disarm()\ntime.sleep(3)\nprint('alive')\n")
+    assert r.returncode == 0 and r.stdout.strip() == "alive"
+
+
+def test_run_b200_assembles_and_prints_one_line_with_everything_mocked(monkeypatch, capsys):
+    """Control flow of the B200 arm without a GPU: trainer / runner / kernels replaced by stand-ins; the JSON line must
+    carry the contract keys, the extras, and be printed exactly once -- also when an extra raises."""
+    import argparse
+    import types
+
+    import torch
+
+    import bench
+
+    class FakeRun:
+        def __init__(self, cfg, batch, hw, world, rank, args, reuse_forward=False):
+            gs = types.SimpleNamespace(buckets=[1, 2], early_pass=2)
+            self.trainer = types.SimpleNamespace(grad_sync={"gen": gs}, reuse_forward=False)
+            self.runner = types.SimpleNamespace(launches_per_step=1400, overlap=False,
+                                                losses=lambda: dict(loss_dis_total=1.0, loss_gen_total=2.0))
+        def prepare(self, warmup): pass
+        def time_resident(self, steps): return 35.0 * steps
+        def time_e2e(self, steps): return 36.0 * steps, (9.0, 40.0)
+        def h2d_bytes(self): return 123
+        def close(self): pass
+
+    fam = dict(launches=1, ms=1.0, flops=1e12)
+    nrm = {k: dict(launches=1, ms=1.0, elems=1e6, bytes=4e6) for k in
+           ("norm_stats", "norm_finalize", "norm_apply", "norm_bwd_reduce", "norm_bwd_finalize", "norm_bwd_apply")}
+    monkeypatch.setattr(bench, "TrainRun", FakeRun)
+    monkeypatch.setattr(bench, "profile_kernels", lambda r: dict(tapgemm=fam, wgrad=fam, norm=nrm, detail=[]))
+    monkeypatch.setattr(bench, "dominant_launch_time", lambda b: (36.0, 1050.0))
+    monkeypatch.setattr(bench, "cpu_reference_steps", lambda *a, **k: (0.05, "port", "mock", 2, 0))
+    monkeypatch.setattr(bench, "infer_line", lambda *a, **k: dict(value=8000.0))
+    calls = []
+
+    def side(cfg, batch, hw, world, rank, args, steps, warmup, what):
+        calls.append(what)
+        if "config_HD" in what:
+            raise RuntimeError("boom")
+        return dict(ms_per_step=100.0)
+
+    monkeypatch.setattr(bench, "side_train_line", side)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda i: None)
+    monkeypatch.setattr(torch.cuda, "empty_cache", lambda: None)
+
+    class FakeSampler:
+        def __init__(self, i): pass
+        def start(self): pass
+        def stop(self): return dict(sm_mhz=1900, sm_max_mhz=1965, reasons=[])
+
+    monkeypatch.setattr(bench, "ClockSampler", FakeSampler)
+    import munit_b200
+    monkeypatch.setitem(sys.modules, "munit_b200._lib", types.SimpleNamespace())
+    monkeypatch.setattr(munit_b200, "_lib", types.SimpleNamespace(), raising=False)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    args = argparse.Namespace(gpus=1, steps=20, warmup=3, impl="b200", batch=8, global_batch=0, hw=0, hd=False, hd_batch=8,
+                              infer_batch=32, optimizer="", no_graph=False, two_streams=1, no_cpu_baseline=False,
+                              no_extras=False, ref_budget=150.0, reuse_forward=0, workload="train", ncu_step=False,
+                              dump_launches="")
+    bench.run_b200(args)
+    out = [l for l in capsys.readouterr().out.splitlines() if l.strip()]
+    assert len(out) == 1
+    line = json.loads(out[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in line, k
+    assert abs(line["ms_per_step"] - 35.0) < 1e-9 and abs(line["value"] - 1000.0 / 35.0) < 1e-6
+    assert line["roofline"]["frac"] and line["roofline_hbm"]["frac"] and line["cpu_baseline"]["kind"] == "port"
+    assert line["forward_reuse"]["value"] and line["global_batch_64"]["ms_per_step"] == 100.0
+    assert "boom" in line["hd"]["error"] and line["infer"]["value"] == 8000.0
+    assert len(calls) == 2
