@@ -332,7 +332,7 @@ def profile_kernels(runner):
 
 def dominant_launch_time(batch, iters=40):
     """The most frequent launch of the step -- 3x3 256->256 conv forward on [batch, 64, 64] content codes,
-    tapgemm_kernel<256> -- timed back to back with ONE event pair around `iters` launches on rotating buffers
+    tapgemm_pair_kernel<256> (tapgemm_kernel<256> on multi-GPU ranks, engine.StepRunner) -- timed back to back with ONE event pair around `iters` launches on rotating buffers
     (per-launch event pairs add several us to a ~38 us kernel).  Returns (us per launch, TFLOP/s)."""
     from munit_b200 import geometry as G, kernels as K
 
@@ -682,7 +682,8 @@ def run_b200(args):
                           note="achieved = direct-form FLOPs of all conv fwd/dgrad launches / their device time inside the "
                                "step, one CUDA event pair per launch (the pair itself adds several us to each ~40 us launch); "
                                "in-step figures are graded against the sustained peak, the isolated launch against burst",
-                          dominant_launch=dict(kernel="tapgemm_kernel<256>, 3x3 256->256 forward on [B,64,64]",
+                          dominant_launch=dict(kernel=("tapgemm_pair_kernel<256> (cta_group::2)" if world == 1 else
+                                                       "tapgemm_kernel<256>") + ", 3x3 256->256 forward on [B,64,64]",
                                                us=dom_us, achieved=dom_tf, peak=peaks["tflops_burst"],
                                                frac=dom_tf / peaks["tflops_burst"] if peaks["tflops_burst"] else None,
                                                method="one event pair around 40 back-to-back launches, rotating buffers; "
