@@ -710,7 +710,7 @@ def run_b200(args):
     extras = {}
     side_steps = max(3, min(args.steps, 8))
 
-    extra_limit = 300.0  # seconds per extra (a healthy one needs 15-60 s)
+    extra_limit = 180.0  # seconds per extra (a healthy one needs 15-60 s)
 
     def abandon(what):
         if rank == 0:
