@@ -1,5 +1,6 @@
 // Library bootstrap + error plumbing for the C-ABI in include/munit_b200.h.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -27,6 +28,15 @@ bool mb_pdl_enabled() {
     on = (e && e[0] == '1') ? 1 : 0;  // opt-in: measured 0.7-0.9 ms/step slower than plain stream order (profiles/r1_pdl.md)
   }
   return on == 1;
+}
+
+void mb_nvtx_mark(const char* name) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MUNIT_NVTX");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (on == 1) nvtxMarkA(name);
 }
 
 extern "C" int munit_version(void) { return 100; }

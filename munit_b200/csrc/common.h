@@ -8,10 +8,15 @@ int mb_fail(int code, const char* fmt, ...);
 int* mb_error_flag();
 int mb_tapgemm_init();
 
+// NVTX (MUNIT_NVTX=1, off by default): one marker per library launch, named after the entry point, so that a timeline
+// tool (Nsight Systems / Compute with --nvtx) can attribute the ~1400 kernels of a step to the call that issued them.
+void mb_nvtx_mark(const char* name);
+
 #define MB_CHECK_LAUNCH(name)                                                         \
   do {                                                                                \
     cudaError_t e__ = cudaGetLastError();                                             \
     if (e__ != cudaSuccess) return mb_fail(2, name ": %s", cudaGetErrorString(e__)); \
+    mb_nvtx_mark(name);                                                               \
   } while (0)
 
 // Programmatic dependent launch (PDL): every kernel of this library starts with pdl_wait() - it blocks until the

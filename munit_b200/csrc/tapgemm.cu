@@ -976,6 +976,7 @@ int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, const OutMaps& to, 
   mb_launch(tapgemm_kernel<BN>, grid, dim3(kThreads), smem, st, ta, tb, to, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "tapgemm launch: %s", cudaGetErrorString(e));
+  mb_nvtx_mark("tapgemm");
   return MUNIT_OK;
 }
 
@@ -1002,6 +1003,7 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const OutMaps& to,
   mb_launch(tapgemm_pair_kernel<BN>, grid, dim3(kThreads), smem, st, ta, tb, to, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "tapgemm_pair launch: %s", cudaGetErrorString(e));
+  mb_nvtx_mark("tapgemm (cta pair)");
   return MUNIT_OK;
 }
 
@@ -1029,6 +1031,7 @@ int launch_halo(const CUtensorMap& ta, const CUtensorMap& tb, const OutMaps& to,
   mb_launch(tapgemm_halo_kernel<BN>, grid, dim3(kThreads), smem, st, ta, tb, to, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "tapgemm_halo launch: %s", cudaGetErrorString(e));
+  mb_nvtx_mark("tapgemm (halo-resident)");
   return MUNIT_OK;
 }
 
@@ -1050,6 +1053,7 @@ int launch_wg(const CUtensorMap& ta, const CUtensorMap& tb, WgParams& p, dim3 gr
   mb_launch(wgrad_kernel<BN>, grid, dim3(kThreads), smem, st, ta, tb, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return mb_fail(MUNIT_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(e));
+  mb_nvtx_mark("wgrad");
   return MUNIT_OK;
 }
 

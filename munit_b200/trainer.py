@@ -35,6 +35,23 @@ def _scalar(t):
     return t.reshape(())
 
 
+class _nvtx:
+    """NVTX range around the two update phases when MUNIT_NVTX=1 (the library marks every launch, csrc/api.cu)."""
+    on = os.environ.get("MUNIT_NVTX", "0") == "1"
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _nvtx.on:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _nvtx.on:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 class MUNIT_Trainer(nn.Module):
     def __init__(self, hyperparameters):
         super().__init__()
@@ -346,6 +363,10 @@ class MUNIT_Trainer(nn.Module):
                 comet_exp.log_metric(k, getattr(self, k).cpu().detach())
 
     def _gen_backward(self, x_a, x_b, hyperparameters, mask_a=None, mask_b=None, synth=False, s_a=None, s_b=None):
+        with _nvtx("munit gen_update"):
+            return self._gen_backward_impl(x_a, x_b, hyperparameters, mask_a, mask_b, synth, s_a, s_b)
+
+    def _gen_backward_impl(self, x_a, x_b, hyperparameters, mask_a=None, mask_b=None, synth=False, s_a=None, s_b=None):
         """Losses + gradients of gen_update (everything up to, not including, the optimiser step)."""
         cache, self._fwd_cache = getattr(self, "_fwd_cache", None), None
         stage12 = None
@@ -502,6 +523,10 @@ class MUNIT_Trainer(nn.Module):
             comet_exp.log_metric("loss_dis_a", self.loss_dis_a.cpu().detach())
 
     def _dis_backward(self, x_a, x_b, hyperparameters, s_a=None, s_b=None, early_gen=None):
+        with _nvtx("munit dis_update"):
+            return self._dis_backward_impl(x_a, x_b, hyperparameters, s_a, s_b, early_gen)
+
+    def _dis_backward_impl(self, x_a, x_b, hyperparameters, s_a=None, s_b=None, early_gen=None):
         """Losses + gradients of dis_update (everything up to, not including, the optimiser step).  early_gen: the
         (s_a, s_b) style draws of the gen_update that follows on the same batch -- its generator pass is then issued
         here, overlapped with the discriminator work (_early_generator_forward)."""
