@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _run(code):
-    return subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, timeout=120, text=True)
+    return subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, timeout=300, text=True)
 
 
 def test_watchdog_emits_the_headline_and_exits_zero():
