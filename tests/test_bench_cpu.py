@@ -99,3 +99,25 @@ def test_run_b200_assembles_and_prints_one_line_with_everything_mocked(monkeypat
     assert line["forward_reuse"]["value"] and line["global_batch_64"]["ms_per_step"] == 100.0
     assert "boom" in line["hd"]["error"] and line["infer"]["value"] == 8000.0
     assert len(calls) == 2
+
+
+def test_gather_segment_table_layout():
+    """kernels.gather_seg_table (host side of munit_gather_cast_multi): five 64-bit words per segment -- source, index
+    map (0 = identity), destination, element count, first block -- with block ranges that tile the launch grid."""
+    import torch
+
+    from munit_b200 import kernels as K
+
+    src = torch.zeros(10000)
+    segs = [(src[:100], torch.zeros(5000, dtype=torch.int32), torch.zeros(5000, dtype=torch.bfloat16)),
+            (src[100:2148], None, torch.zeros(2048, dtype=torch.bfloat16)),
+            (src[3000:], torch.zeros(1, dtype=torch.int32), torch.zeros(1, dtype=torch.bfloat16))]
+    table, nseg, nblocks = K.gather_seg_table(segs, "cpu")
+    assert nseg == 3 and table.dtype == torch.int64 and tuple(table.shape) == (3, 5)
+    per = K.GATHER_BLOCK
+    want_blocks = [(5000 + per - 1) // per, 1, 1]
+    assert nblocks == sum(want_blocks)
+    b0 = 0
+    for row, (s, i, d), nb in zip(table.tolist(), segs, want_blocks):
+        assert row == [s.data_ptr(), 0 if i is None else i.data_ptr(), d.data_ptr(), d.numel(), b0]
+        b0 += nb
