@@ -708,7 +708,7 @@ def run_b200(args):
         if args.reuse_forward:
             line["config"]["reuse_forward"] = True
     extras = {}
-    side_steps = max(3, min(args.steps, 8))
+    side_steps = max(3, min(args.steps, 8 if world == 1 else 4))  # (multi-GPU: short extras, profiles/r2_dp8_hang.md)
 
     extra_limit = 180.0  # seconds per extra (a healthy one needs 15-60 s)
 
