@@ -13,15 +13,92 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import signal
 import subprocess
 import sys
 import threading
 import time
 
-import torch
-
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
+
+# ------------------------------------------------------------------------------------------------
+# Supervisor (one-GPU B200 arm only).  The benchmark proper runs in a child process; if that child makes no progress --
+# its own watchdog ends it with exit code 3, or the limit below expires -- it is killed (which tears its CUDA context
+# down, hung kernels included) and the headline is measured once more in the conservative configuration (single-CTA
+# tap-GEMMs, sequential updates, no extras).  Reason: one multi-GPU run of the full round-2 feature set stopped inside a
+# graph replay for a reason that was not isolated (profiles/r2_dp8_hang.md); a single shot of this benchmark must not
+# be lost to an event like that.  MUNIT_BENCH_SUPERVISE=0 runs in-process (also automatic under ncu / nsys).
+# ------------------------------------------------------------------------------------------------
+RETRY_ENV = {"MUNIT_PAIR": "0", "MUNIT_OVERLAP_UPDATES": "0"}
+
+
+def wants_supervisor(argv, env):
+    if env.get("MUNIT_BENCH_CHILD") == "1" or env.get("MUNIT_BENCH_SUPERVISE", "1") == "0":
+        return False
+    if int(env.get("WORLD_SIZE", "1") or 1) > 1:
+        return False  # multi-GPU ranks cannot be restarted one by one: they keep the in-process watchdog only
+    if any(k.startswith(("NV_NSIGHT", "NV_COMPUTE_PROFILER", "NSYS_", "CUDA_INJECTION")) for k in env):
+        return False  # under a profiler: keep the kernels in the profiled process
+    flags = set(argv)
+    if flags & {"--ncu-step", "-h", "--help"}:
+        return False
+    for i, a in enumerate(argv):
+        val = a.split("=", 1)[1] if "=" in a else (argv[i + 1] if i + 1 < len(argv) else "")
+        if a.split("=", 1)[0] == "--impl" and val == "reference":
+            return False
+        if a.split("=", 1)[0] == "--workload" and val == "infer":
+            return False
+        if a.split("=", 1)[0] == "--gpus" and val not in ("", "1"):
+            return False
+    return True
+
+
+def supervise(argv, cmd=None, limits=(720.0, 330.0), out=None):
+    """Returns the process exit code.  `cmd`: the child command without the benchmark arguments (tests substitute it)."""
+    out = out or sys.stdout
+    cmd = cmd or [sys.executable, os.path.abspath(__file__)]
+    attempts = [({}, [], limits[0]), (RETRY_ENV, ["--no-extras"], limits[1])]
+    why = ""
+    for i, (env_add, extra_args, limit) in enumerate(attempts):
+        env = dict(os.environ, MUNIT_BENCH_CHILD="1")
+        env.update(env_add)
+        p = subprocess.Popen(cmd + list(argv) + extra_args, env=env, stdout=subprocess.PIPE, text=True, start_new_session=True)
+        try:
+            text, _ = p.communicate(timeout=limit)
+            rc = p.returncode
+        except subprocess.TimeoutExpired:
+            try:
+                os.killpg(p.pid, signal.SIGKILL)
+            except OSError:
+                pass
+            text, _ = p.communicate()
+            rc = -9
+        lines = [ln for ln in (text or "").splitlines() if ln.startswith("{")]
+        if rc == 0 and lines:
+            line = lines[-1]
+            if i > 0:
+                try:
+                    d = json.loads(line)
+                    d["supervisor"] = (f"first attempt ended without a result ({why}); this line is a second run with "
+                                       + " ".join(f"{k}={v}" for k, v in RETRY_ENV.items()) + " --no-extras")
+                    line = json.dumps(d)
+                except ValueError:
+                    pass
+            out.write(line + "\n")
+            out.flush()
+            return 0
+        why = f"exit code {rc}" if rc != -9 else f"killed after {limit:.0f} s without finishing"
+        sys.stderr.write(f"bench.py supervisor: attempt {i + 1} gave no result ({why})\n")
+        sys.stderr.flush()
+    return 3
+
+
+if __name__ == "__main__" and wants_supervisor(sys.argv[1:], os.environ):
+    sys.exit(supervise(sys.argv[1:]))
+
+import torch  # noqa: E402  (after the supervisor: the supervising process never touches CUDA)
 
 METRIC = "MUNIT train steps/sec (gen+dis) 256^2"
 UNIT = "steps/s (1 step = dis_update+gen_update on 8 image pairs)"
@@ -585,7 +662,7 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dog = Watchdog()
-    dog.arm("headline", 480.0)  # a healthy default run needs ~30 s for the headline (+ ~45 s CPU baseline at N = 1)
+    dog.arm("headline", 360.0)  # a healthy default run needs ~30 s for the headline (+ ~45 s CPU baseline at N = 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from munit_b200 import _lib  # noqa: F401  (fails loudly when the shared library is missing)
@@ -719,8 +796,14 @@ def run_b200(args):
             out.update(extras)
             print(json.dumps(out), flush=True)
 
+    extras_deadline = time.time() + 300.0  # all extras together (the supervisor's limit covers headline + this)
+
     def extra(name, fn):
-        dog.arm(name, extra_limit, abandon)
+        left = extras_deadline - time.time()
+        if left < 20.0:
+            extras[name] = dict(skipped="the time budget of the informational extras was used up")
+            return
+        dog.arm(name, min(extra_limit, left), abandon)
         try:
             extras[name] = fn()
         except Exception as exc:  # informational lines only: never lose the headline over one of them

@@ -121,3 +121,59 @@ def test_gather_segment_table_layout():
     for row, (s, i, d), nb in zip(table.tolist(), segs, want_blocks):
         assert row == [s.data_ptr(), 0 if i is None else i.data_ptr(), d.data_ptr(), d.numel(), b0]
         b0 += nb
+
+
+def test_supervisor_passes_the_line_through_and_retries_a_hung_child(tmp_path):
+    """bench.supervise: a healthy child's JSON line goes out unchanged; a child that hangs (or dies) is killed and the
+    benchmark runs once more with the conservative environment, the line then says so; two failures -> exit code 3."""
+    import io
+
+    import bench
+
+    fake = tmp_path / "fake_bench.py"
+    fake.write_text(
+        "import json, os, sys, time\n"
+        "mode = os.environ.get('FAKE_MODE', 'ok')\n"
+        "assert os.environ.get('MUNIT_BENCH_CHILD') == '1'\n"
+        "conservative = os.environ.get('MUNIT_PAIR') == '0' and '--no-extras' in sys.argv\n"
+        "if mode == 'hang_first' and not conservative:\n"
+        "    time.sleep(600)\n"
+        "if mode == 'die_first' and not conservative:\n"
+        "    sys.exit(3)\n"
+        "if mode == 'always_die':\n"
+        "    sys.exit(1)\n"
+        "print('some log line')\n"
+        "print(json.dumps({'metric': 'm', 'value': 28.7 if not conservative else 27.0, 'args': sys.argv[1:]}))\n")
+    cmd = [sys.executable, str(fake)]
+
+    def run(mode, limits=(5.0, 30.0)):
+        os.environ["FAKE_MODE"] = mode
+        try:
+            buf = io.StringIO()
+            rc = bench.supervise(["--steps", "20"], cmd=cmd, limits=limits, out=buf)
+        finally:
+            del os.environ["FAKE_MODE"]
+        return rc, buf.getvalue()
+
+    rc, text = run("ok")
+    assert rc == 0 and text.count("\n") == 1
+    d = json.loads(text)
+    assert d["value"] == 28.7 and d["args"] == ["--steps", "20"] and "supervisor" not in d
+    for mode in ("hang_first", "die_first"):
+        rc, text = run(mode)
+        d = json.loads(text)
+        assert rc == 0 and d["value"] == 27.0 and d["args"] == ["--steps", "20", "--no-extras"]
+        assert "MUNIT_PAIR=0" in d["supervisor"] and "first attempt" in d["supervisor"]
+    rc, text = run("always_die")
+    assert rc == 3 and text == ""
+
+
+def test_supervisor_is_only_for_the_one_gpu_b200_arm():
+    import bench
+
+    w = bench.wants_supervisor
+    assert w([], {}) and w(["--gpus", "1", "--steps", "20", "--warmup", "3"], {}) and w(["--gpus=1"], {})
+    assert not w(["--gpus", "8"], {}) and not w([], {"WORLD_SIZE": "2"}) and not w(["--impl", "reference"], {})
+    assert not w(["--impl=reference"], {}) and not w(["--workload", "infer"], {}) and not w(["--ncu-step"], {})
+    assert not w([], {"MUNIT_BENCH_CHILD": "1"}) and not w([], {"MUNIT_BENCH_SUPERVISE": "0"})
+    assert not w([], {"NV_COMPUTE_PROFILER_PERFWORKS_DIR": "/x"}) and w([], {"WORLD_SIZE": "1", "RANK": "0"})
