@@ -64,17 +64,23 @@ def supervise(argv, cmd=None, limits=(720.0, 330.0), out=None):
     for i, (env_add, extra_args, limit) in enumerate(attempts):
         env = dict(os.environ, MUNIT_BENCH_CHILD="1")
         env.update(env_add)
-        p = subprocess.Popen(cmd + list(argv) + extra_args, env=env, stdout=subprocess.PIPE, text=True, start_new_session=True)
+        p = subprocess.Popen(cmd + list(argv) + extra_args, env=env, stdout=subprocess.PIPE, text=True)
+
+        def forward(signum, frame, p=p):  # the supervisor is being stopped: take the child along
+            p.kill()
+            sys.exit(128 + signum)
+
+        old_handlers = {sg: signal.signal(sg, forward) for sg in (signal.SIGTERM, signal.SIGINT)}
         try:
             text, _ = p.communicate(timeout=limit)
             rc = p.returncode
         except subprocess.TimeoutExpired:
-            try:
-                os.killpg(p.pid, signal.SIGKILL)
-            except OSError:
-                pass
+            p.kill()
             text, _ = p.communicate()
             rc = -9
+        finally:
+            for sg, h in old_handlers.items():
+                signal.signal(sg, h)
         lines = [ln for ln in (text or "").splitlines() if ln.startswith("{")]
         if rc == 0 and lines:
             line = lines[-1]
@@ -97,6 +103,12 @@ def supervise(argv, cmd=None, limits=(720.0, 330.0), out=None):
 
 if __name__ == "__main__" and wants_supervisor(sys.argv[1:], os.environ):
     sys.exit(supervise(sys.argv[1:]))
+if __name__ == "__main__" and os.environ.get("MUNIT_BENCH_CHILD") == "1":
+    try:  # die with the supervisor, however it dies (Linux: PR_SET_PDEATHSIG)
+        import ctypes
+        ctypes.CDLL("libc.so.6", use_errno=True).prctl(1, int(signal.SIGKILL), 0, 0, 0)
+    except Exception:
+        pass
 
 import torch  # noqa: E402  (after the supervisor: the supervising process never touches CUDA)
 
